@@ -1,0 +1,381 @@
+/*
+ * gpx.h -- C ABI of the B200-native batched-Paxos engine (gigapaxos hot path).
+ *
+ * This is the drop-in boundary. gigapaxos has no FFI seam on this
+ * path today; the seam defined here is the narrow waist already present in the
+ * Java code.  Every entry point cites the reference interface it replaces
+ * (paths relative to /root/reference/src/edu/umass/cs/gigapaxos/):
+ *
+ *   gpx_engine_create / gpx_config_from_properties
+ *        <- PaxosConfig.java:64,83-90 (gigapaxos.properties), PaxosManager ctor
+ *           PaxosManager.java:392-462
+ *   gpx_create_groups        <- PaxosManager.createPaxosInstance :632, batch form :664-691,
+ *                               HotRestoreInfo.createHRI paxosutil/HotRestoreInfo.java:145-157,
+ *                               PaxosInstanceStateMachine.initiateRecovery :591-675
+ *   gpx_destroy_groups       <- PaxosManager.kill :2162
+ *   gpx_dump_rows/load_rows  <- PaxosManager pause/unpause :2284,:2370 (HotRestoreInfo field set)
+ *   gpx_patch                <- PaxosAcceptor.handlePrepare :245-251 (ballot bump),
+ *                               jumpSlot :564-578, forceStop :154; coordinator install/resign
+ *   gpx_propose              <- RequestBatcher.enqueueImpl/dequeueImpl RequestBatcher.java:112-234,
+ *                               PISM.handleRequest :767 / handleProposal :818,
+ *                               PaxosCoordinatorState.propose :233-263
+ *   gpx_handle_accepts       <- PISM.handleAccept :1080-1166 (+ AbstractPaxosLogger.logAndMessage :157)
+ *   gpx_handle_accept_replies<- PISM.handleBatchedAcceptReply :1370 / handleAcceptReply :1248
+ *   gpx_handle_decisions     <- PISM.handleBatchedCommit :1480 / handleCommittedRequest :1432 /
+ *                               extractExecuteAndCheckpoint :1619 (EXEC records replace app.execute :1802)
+ *   gpx_round                <- one full pass of the above for co-located replicas
+ *                               (PaxosManager.send :2098-2128 routing incl. loopback)
+ *   gpx_log_read             <- SQLPaxosLogger.journal :965-1036 / Journaler.appendToLogFile :814-826
+ *   gpx_wire_*               <- paxospackets byte codecs (RequestPacket.java:819-1024,
+ *                               AcceptPacket.java:95-138, BatchedAcceptReply.java:103-173,
+ *                               BatchedCommit.java:184-252, PaxosPacket.java:443-476)
+ *
+ * Conventions (mirror the reference): int return codes are for API
+ * misuse only; protocol-level rejects (stopped group, stale ballot, unknown
+ * acceptor, window overflow) are counted and dropped, never fatal.  The engine is
+ * single-submitter and batch-synchronous: one call = one batch, per-group order
+ * inside a batch is the order of the records in the batch.  The caller owns all
+ * input and output buffers; the engine owns device memory.
+ *
+ * All records are little-endian, fixed size, 16-byte multiples.
+ * A `gid` is a dense handle for one (paxosID, version) instance -- the analogue
+ * of a PaxosInstanceStateMachine object reference; the version drop rule
+ * (PISM :441-447) is applied where (paxosID, version) is mapped to a gid
+ * (gpx_wire_decode_*).
+ */
+#ifndef GPX_H
+#define GPX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPX_ABI_VERSION 1
+
+#define GPX_MAX_GROUP_SIZE 16 /* PC.MAX_GROUP_SIZE, PaxosConfig.java:532 */
+#define GPX_MAX_LANES 8       /* co-located replicas (lanes) per engine */
+#define GPX_MAX_WINDOW 8      /* per-group in-flight slot window W (power of two) */
+#define GPX_MAX_MSETS 4096    /* distinct member sets per engine */
+
+/* return codes (API misuse / environment only) */
+enum {
+  GPX_OK = 0,
+  GPX_EINVAL = -1,
+  GPX_ENOMEM = -2,
+  GPX_ECUDA = -3,
+  GPX_ENOGPU = -4,
+  GPX_ERANGE = -5,
+  GPX_EIO = -6
+};
+
+/* PaxosAcceptor.STATES ordinals (PaxosAcceptor.java:87-92); FREE = no instance */
+enum {
+  GPX_ST_RECOVERY = 0,
+  GPX_ST_ACTIVE_1 = 1,
+  GPX_ST_ACTIVE_2 = 2,
+  GPX_ST_STOPPED = 3,
+  GPX_ST_FREE = 255
+};
+
+/* record flags (uint16 `flags` of gpx_pvalue_hdr, low half of request/exec flags) */
+#define GPX_F_STOP 0x0001u       /* RequestPacket.stop */
+#define GPX_F_VOID 0x0002u       /* hole: ignore this record / frame */
+#define GPX_F_ACCEPT 0x0004u     /* log frame / record is an ACCEPT (48 B + blob) */
+#define GPX_F_DECISION 0x0008u   /* log frame / record is a DECISION (32 B) */
+#define GPX_F_META 0x0010u       /* decision log frame is PValuePacket.getMetaDecision() form */
+#define GPX_F_CKPT 0x0020u       /* exec: PISM.shouldCheckpoint() is true for this slot */
+#define GPX_F_LOGGED 0x0040u     /* accept reply was released by a log append (LogMessagingTask) */
+#define GPX_F_NACK 0x0080u       /* accept reply carries a ballot higher than the accept's */
+#define GPX_F_EXTRA 0x0100u      /* exec/decision came from the reconstructDecision path */
+
+/* request status written by gpx_propose (one int32 per request) */
+#define GPX_RS_BATCHED (-1)      /* latched into the batch of an earlier request of the group */
+#define GPX_RS_FORWARD (-2)      /* coordinator is a remote node: forward PROPOSAL (host) */
+#define GPX_RS_REFUSED_STOP (-3) /* PCS.propose refused: previous proposal is a STOP */
+#define GPX_RS_BACKPRESSURE (-4) /* proposal window full (W in flight); resubmit later */
+#define GPX_RS_DROPPED (-5)      /* group stopped / free (PISM :456-460) */
+#define GPX_RS_PREACTIVE (-6)    /* coordinator exists but is not active: host slow path */
+#define GPX_RS_NOCOORD (-7)      /* no usable coordinator on any local lane: host slow path */
+
+/* ---- records -------------------------------------------------------------- */
+
+/* client request handed to the RequestBatcher (RequestPacket essentials), 32 B */
+typedef struct gpx_request_rec {
+  uint32_t gid;
+  uint32_t flags;       /* bit0 GPX_F_STOP; bits 8..11 entry lane */
+  int64_t req_id;       /* RequestPacket.requestID */
+  uint32_t payload_off; /* byte offset of requestValue in the batch payload arena */
+  uint32_t payload_len;
+  int32_t entry_node;   /* RequestPacket.entryReplica (node id) */
+  uint32_t client;      /* opaque client handle, carried through */
+} gpx_request_rec;
+
+/* common prefix of ACCEPT and DECISION (PValuePacket), 32 B */
+typedef struct gpx_pvalue_hdr {
+  uint32_t gid;
+  int32_t slot;      /* ProposalPacket.slot */
+  int32_t bnum;      /* Ballot.ballotNumber */
+  int32_t bcoord;    /* Ballot.coordinatorID (node id) */
+  int32_t median_cp; /* PValuePacket.medianCheckpointedSlot */
+  uint16_t flags;    /* GPX_F_* */
+  uint16_t dst_mask; /* local lanes this record is addressed to */
+  int64_t req_id;    /* requestID of the first request of the slot */
+} gpx_pvalue_hdr;
+
+typedef gpx_pvalue_hdr gpx_decision_rec; /* DECISION / one slot of a BATCHED_COMMIT, 32 B */
+
+/* ACCEPT (AcceptPacket), 48 B.  The request body ("blob") lives in a payload
+ * arena: nreq==1 -> the raw requestValue bytes; nreq>1 -> nreq x gpx_batch_ent
+ * followed by the concatenated requestValues (RequestPacket.batched). */
+typedef struct gpx_accept_rec {
+  gpx_pvalue_hdr h;
+  uint32_t payload_off;
+  uint32_t payload_len;
+  uint32_t nreq;
+  int32_t sender; /* AcceptPacket.sender (node id) == coordinator that issued it */
+} gpx_accept_rec;
+
+/* per-request entry of a batched blob, 16 B */
+typedef struct gpx_batch_ent {
+  int64_t req_id;
+  uint32_t len;
+  uint32_t flags; /* bit0 STOP; bits 8.. entry lane (as gpx_request_rec.flags) */
+} gpx_batch_ent;
+
+/* ACCEPT_REPLY / one slot of a BATCHED_ACCEPT_REPLY, 32 B */
+typedef struct gpx_accept_reply_rec {
+  uint32_t gid;
+  int32_t slot;   /* AcceptReplyPacket.slotNumber */
+  int32_t bnum;   /* acceptor's ballot after handling the accept */
+  int32_t bcoord;
+  int32_t max_cp; /* AcceptReplyPacket.maxCheckpointedSlot (= acceptor slot - 1) */
+  uint32_t who;   /* bits 0..7 acceptor member index, 8..15 destination member index
+                     (the accept's sender), 16..31 flags (GPX_F_VOID|LOGGED|NACK) */
+  int64_t req_id;
+} gpx_accept_reply_rec;
+
+#define GPX_WHO(acc_idx, dst_idx, flags) \
+  ((uint32_t)(acc_idx) | ((uint32_t)(dst_idx) << 8) | ((uint32_t)(flags) << 16))
+#define GPX_WHO_ACC(w) ((w) & 0xffu)
+#define GPX_WHO_DST(w) (((w) >> 8) & 0xffu)
+#define GPX_WHO_FLAGS(w) ((w) >> 16)
+
+/* in-order execution record handed to the Replicable app, 24 B */
+typedef struct gpx_exec_rec {
+  uint32_t gid;
+  int32_t slot;
+  int64_t req_id;
+  uint32_t payload_off; /* (byte offset of the blob in the lane's log ring) / 16 */
+  uint32_t flags;       /* GPX_F_STOP|VOID|CKPT|EXTRA; bits 8..11 lane; bits 16..31 nreq */
+} gpx_exec_rec;
+
+/* ---- log ring ---------------------------------------------------------------
+ * One ring per lane.  A ring is a sequence of segments, one per kernel launch
+ * that logs: [gpx_log_seg_hdr 64 B][n_slots record images][payload area].
+ * ACCEPT segment: images are gpx_accept_rec (48 B); image.payload_off is relative
+ * to the segment's payload area; unlogged records have GPX_F_VOID.
+ * DECISION segment: images are gpx_decision_rec (32 B), no payload area.
+ * (SQLPaxosLogger.journal frames {int32 len}{packet bytes}, :1000-1003; gpx_wire_*
+ * re-frames segments into that byte format.) */
+#define GPX_SEG_MAGIC 0x53585047u /* "GPXS" */
+typedef struct gpx_log_seg_hdr {
+  uint32_t magic;
+  uint16_t type; /* GPX_F_ACCEPT or GPX_F_DECISION */
+  uint16_t lane;
+  uint32_t n_slots;       /* record images reserved */
+  uint32_t n_valid;       /* images actually written (<= n_slots) */
+  uint64_t payload_bytes; /* payload area bytes (ACCEPT segments) */
+  uint64_t seq;           /* segment sequence number of this lane */
+  uint64_t ring_off;      /* absolute ring offset of this header */
+  uint32_t rec_bytes;     /* 48 or 32 */
+  uint32_t reserved[5];
+} gpx_log_seg_hdr;
+
+/* ---- group management ------------------------------------------------------- */
+
+/* HotRestoreInfo field set for one (lane, gid) row, paxosutil/HotRestoreInfo.java:31-120 */
+typedef struct gpx_row {
+  uint32_t gid;
+  uint32_t lane;
+  int32_t version;
+  int32_t acc_slot;       /* accSlot */
+  int32_t acc_bnum;       /* accBallot */
+  int32_t acc_bcoord;
+  int32_t acc_gc_slot;    /* accGCSlot */
+  int32_t state;          /* GPX_ST_* */
+  int32_t coord_exists;   /* coordBallot != null */
+  int32_t coord_active;
+  int32_t coord_bnum;
+  int32_t coord_bcoord;
+  int32_t next_proposal_slot;
+  int32_t n_members;
+  int32_t members[GPX_MAX_GROUP_SIZE];    /* sorted ascending node ids */
+  int32_t node_slots[GPX_MAX_GROUP_SIZE]; /* PaxosCoordinatorState.nodeSlotNumbers */
+} gpx_row;
+
+#define GPX_INIT_BATCH 0   /* HotRestoreInfo.createHRI path (PaxosManager.java:664-691) */
+#define GPX_INIT_DEFAULT 1 /* PISM.initiateRecovery + putInitialState path (:591-703) */
+
+typedef struct gpx_group_desc {
+  uint32_t gid;
+  int32_t version;
+  int32_t name_hash; /* Java String.hashCode() of the paxosID */
+  int32_t n_members;
+  int32_t members[GPX_MAX_GROUP_SIZE]; /* node ids, any order (sorted by the engine) */
+  int32_t init_mode;                   /* GPX_INIT_* */
+} gpx_group_desc;
+
+/* host -> device state patch (slow path effects), applied between batches */
+enum {
+  GPX_PATCH_SET_BALLOT = 1,    /* acceptor ballot <- (a,b) if higher (handlePrepare) */
+  GPX_PATCH_JUMP_SLOT = 2,     /* acceptor.jumpSlot(a) */
+  GPX_PATCH_SET_STATE = 3,     /* acceptor state <- a (forceStop, setActive) */
+  GPX_PATCH_INSTALL_COORD = 4, /* coordinator (bnum=a, bcoord=b, next=c, active=d) */
+  GPX_PATCH_RESIGN_COORD = 5,  /* coordinator <- null */
+  GPX_PATCH_SET_GC = 6         /* acceptedGCSlot <- a */
+};
+typedef struct gpx_patch_rec {
+  uint32_t gid;
+  uint32_t lane;
+  int32_t op;
+  int32_t a, b, c, d;
+  int32_t reserved;
+} gpx_patch_rec;
+
+/* ---- configuration ----------------------------------------------------------- */
+
+typedef struct gpx_config {
+  uint32_t abi_version;
+  int32_t device;            /* CUDA device ordinal */
+  uint32_t max_groups;       /* PINSTANCES_CAPACITY analogue: rows per lane */
+  uint32_t n_lanes;          /* co-located replicas */
+  int32_t lane_node[GPX_MAX_LANES]; /* node id served by each lane */
+  uint32_t window;           /* W: 1,2,4,8 */
+  uint32_t max_group_size;   /* <= GPX_MAX_GROUP_SIZE: node_slots columns allocated */
+  uint64_t log_ring_bytes;   /* per lane, power of two; 0 => logging disabled (DISABLE_LOGGING) */
+  uint32_t max_batch_recs;   /* largest record batch one call may carry */
+  uint64_t max_batch_payload;/* largest payload arena one call may carry */
+  /* gigapaxos.properties subset (PaxosConfig.java PC enum), same defaults */
+  int32_t batching_enabled;        /* BATCHING_ENABLED :309 (true) */
+  int32_t max_batch_size;          /* MAX_BATCH_SIZE :403 (2000) */
+  int64_t max_batch_bytes;         /* min(NIO MAX_PAYLOAD_SIZE 4MB, MAX_LOG_MESSAGE_SIZE 5MB) */
+  int32_t request_size_estimate;   /* RequestPacket.SIZE_ESTIMATE (:1351-1367) */
+  int32_t checkpoint_interval;     /* CHECKPOINT_INTERVAL :410 (400) */
+  double cpi_noise;                /* CPI_NOISE :746 (0) */
+  int32_t gc_majority_executed;    /* GC_MAJORITY_EXECUTED :882 (true) */
+  int32_t log_meta_decisions;      /* LOG_META_DECISIONS :588 (true) */
+  int32_t journaling_enabled;      /* ENABLE_JOURNALING :240 (true): executed accepts leave memory */
+  int32_t batched_accept_replies;  /* BATCHED_ACCEPT_REPLIES :458 */
+  int32_t batched_commits;         /* BATCHED_COMMITS :466 */
+  int32_t short_circuit_local;     /* SHORT_CIRCUIT_LOCAL :834 */
+  int32_t min_pp_batch_size;       /* MIN_PP_BATCH_SIZE :860 */
+  int32_t digest_requests;         /* DIGEST_REQUESTS :788 (false) */
+  int32_t reserved[8];
+} gpx_config;
+
+typedef struct gpx_counters {
+  uint64_t accepts_handled, accepts_acked, accepts_nacked, accepts_logged, accepts_dropped;
+  uint64_t replies_handled, replies_ignored, preempted, coordinators_resigned;
+  uint64_t decisions_made, decisions_handled, decisions_dropped, placeholders;
+  uint64_t executed, stops_executed, checkpoints_due;
+  uint64_t proposals, requests_batched, requests_rejected;
+  uint64_t window_overflow, kernel_launches;
+  uint64_t reserved[7];
+} gpx_counters;
+
+typedef struct gpx_engine gpx_engine;
+
+/* ---- lifecycle ---------------------------------------------------------------- */
+void gpx_config_defaults(gpx_config* cfg);
+/* parse the gigapaxos.properties keys the engine consumes; unknown keys ignored */
+int gpx_config_from_properties(const char* path, gpx_config* cfg);
+int gpx_engine_create(const gpx_config* cfg, gpx_engine** out);
+void gpx_engine_destroy(gpx_engine* e);
+const char* gpx_last_error(void);
+const char* gpx_build_info(void); /* "cuda sm_100a ..." or "oracle" */
+
+/* ---- groups -------------------------------------------------------------------- */
+int gpx_create_groups(gpx_engine* e, uint32_t n, const gpx_group_desc* descs);
+int gpx_destroy_groups(gpx_engine* e, uint32_t n, const uint32_t* gids);
+int gpx_dump_rows(gpx_engine* e, uint32_t n, const uint32_t* gids, uint32_t lane, gpx_row* out);
+int gpx_load_rows(gpx_engine* e, uint32_t n, const gpx_row* rows);
+int gpx_patch(gpx_engine* e, uint32_t n, const gpx_patch_rec* patches);
+
+/* ---- data path: host buffers in, host buffers out (H2D and D2H inside) ---------- */
+
+/* RequestBatcher + PCS.propose.  reqs must be grouped by gid (per-group FIFO order
+ * preserved).  out_accepts capacity n; out_blob capacity blob_cap bytes (>= payload_bytes
+ * + 16*n); status[n] receives the slot (>0) or a GPX_RS_* code. */
+int gpx_propose(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                uint64_t payload_bytes, gpx_accept_rec* out_accepts, uint32_t* n_accepts,
+                uint8_t* out_blob, uint64_t blob_cap, uint64_t* blob_bytes, int32_t* status);
+
+/* handleAccept at every local lane in rec.dst_mask.  accepts must be grouped by gid.
+ * out_replies[n * n_lanes] (index i*n_lanes+lane, GPX_F_VOID where not addressed/dropped).
+ * out_extra_exec (cap extra_cap) receives EXEC records released by reconstructDecision. */
+int gpx_handle_accepts(gpx_engine* e, uint32_t n, const gpx_accept_rec* accepts,
+                       const uint8_t* blob, uint64_t blob_bytes, gpx_accept_reply_rec* out_replies,
+                       gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
+
+/* handleAcceptReply at the destination lane of each reply; replies grouped by gid.
+ * out_decisions capacity n. */
+int gpx_handle_accept_replies(gpx_engine* e, uint32_t n, const gpx_accept_reply_rec* replies,
+                              gpx_decision_rec* out_decisions, uint32_t* n_decisions);
+
+/* handleBatchedCommit per slot at every local lane in rec.dst_mask; grouped by gid.
+ * out_exec[n * n_lanes] primary EXEC record per (decision, lane) (VOID if none);
+ * further in-order executions released by the same decision go to out_extra_exec. */
+int gpx_handle_decisions(gpx_engine* e, uint32_t n, const gpx_decision_rec* decisions,
+                         gpx_exec_rec* out_exec, gpx_exec_rec* out_extra_exec, uint32_t extra_cap,
+                         uint32_t* n_extra);
+
+/* One full round for co-located replicas: propose -> accept -> tally -> commit, all
+ * inter-replica records staying in HBM.  Host request buffers in, EXEC records out
+ * (out_exec[n * n_lanes], extras appended to out_extra_exec). */
+int gpx_round(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+              uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
+              gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
+
+/* ---- log ring ------------------------------------------------------------------- */
+/* copy ring bytes [from, min(head, from+cap)) of `lane` into dst; *head receives the ring head */
+int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_t cap,
+                 uint64_t* n_copied, uint64_t* head);
+
+/* ---- introspection ---------------------------------------------------------------- */
+int gpx_get_counters(gpx_engine* e, gpx_counters* out);
+int gpx_reset_counters(gpx_engine* e);
+
+/* ---- device-resident API (bench `value`, multi-GPU shards): all pointers are device
+ * pointers owned by the caller, `stream` is a cudaStream_t ------------------------------ */
+typedef struct gpx_dev_round_bufs {
+  const gpx_request_rec* reqs; /* [n] device */
+  const uint8_t* payload;      /* device */
+  uint64_t payload_bytes;
+  uint32_t n;
+  int32_t* status;             /* [n] device */
+  gpx_exec_rec* exec;          /* [n * n_lanes] device */
+} gpx_dev_round_bufs;
+int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream);
+/* per-kernel CUDA-event timing of the last gpx_round_device calls (ms, accumulated) */
+typedef struct gpx_kernel_times {
+  double propose_ms, accept_ms, tally_ms, commit_ms;
+  uint64_t launches;
+} gpx_kernel_times;
+int gpx_enable_kernel_timing(gpx_engine* e, int on);
+int gpx_get_kernel_times(gpx_engine* e, gpx_kernel_times* out, int reset);
+
+/* ---- helpers shared with the reference semantics ---------------------------------- */
+int32_t gpx_java_string_hash(const char* s, size_t len); /* String.hashCode() */
+/* PISM.roundRobinCoordinator :2251-2256 on sorted members */
+int32_t gpx_round_robin_coordinator(int32_t name_hash, const int32_t* sorted_members, int32_t n,
+                                    int32_t ballotnum);
+/* PISM.getCPI :2694-2697 */
+int32_t gpx_get_cpi(int32_t cpi, double noise, int32_t name_hash);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPX_H */

@@ -1,0 +1,1501 @@
+/*
+ * gpx_oracle.cpp -- CPU ORACLE for the gigapaxos phase-2 hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under gigapaxos_b200/ may include, link, load or
+ * call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs do, and only as the checker / the CPU arm.
+ *
+ * This is a single-threaded restatement of the reference's Java semantics, class by
+ * class, with java.util.TreeMap -> std::map.  Each function cites the reference
+ * file:line it follows (paths relative to /root/reference/src/edu/umass/cs/gigapaxos/).
+ *
+ * PARITY PINNING: the reference holds no golden vectors for this path;
+ * the reference JVM cannot run in the build container (no java/javac).  The oracle is
+ * pinned by transliterations of the reference's own self-checking main() tests
+ * (gpxo_selftest below): PaxosAcceptor.java:749-776, PaxosCoordinatorState.java:1179-1214,
+ * paxosutil/WaitforUtility.java:147-163, PaxosPacketBatcher.java:556-567 (Ballot),
+ * paxosutil/HotRestoreInfo.java:159-175 (the one literal-valued test), RFC 1321 vectors
+ * for MD5 (digest bytes are "parity unpinned" by the reference).
+ *
+ * It exposes the same record-level C ABI as include/gpx.h with the prefix gpxo_ so that
+ * tests feed identical batches to the CUDA engine and to this file and compare bytes.
+ *
+ * Two deliberate, documented modelling choices (DESIGN.md "Canonical execution"):
+ *  (1) per-group FIFO arrival order and "all requests of the group present in the call,
+ *      cut by MAX_BATCH_SIZE / byte limit" batching -- one admissible execution of
+ *      RequestBatcher.dequeueImpl (RequestBatcher.java:168-234);
+ *  (2) decisions are delivered value-less to every replica (the BATCHED_COMMIT form,
+ *      PISM.handleBatchedCommit :1480-1528), i.e. SHORT_CIRCUIT_LOCAL does not
+ *      short-circuit commits; a replica resolves the value from its accepted window.
+ * With window == 0 the maps are unbounded exactly like the Java TreeMaps; with
+ * window == W the bounded-window rules of the device engine are applied on top.
+ */
+#include "../include/gpx.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+typedef int32_t i32;
+typedef uint32_t u32;
+typedef int64_t i64;
+typedef uint64_t u64;
+
+/* Java int subtraction (wraps) */
+static inline i32 jsub(i32 a, i32 b) { return (i32)((u32)a - (u32)b); }
+
+/* paxosutil/Ballot.java:34-116 */
+struct Ballot {
+  i32 num, coord;
+  /* compareTo :60-66 */
+  i32 compareTo(const Ballot& b) const { return num != b.num ? jsub(num, b.num) : jsub(coord, b.coord); }
+  bool equals(const Ballot& b) const { return compareTo(b) == 0; } /* :76 */
+  i32 hashCode() const { return (i32)((u32)(100 + num) * (u32)(100 + num) + (u32)coord); } /* :86 */
+  std::string toString() const { return std::to_string(num) + ":" + std::to_string(coord); }
+};
+
+/* PValuePacket essentials (paxospackets/PValuePacket.java) */
+struct PValue {
+  i32 slot = 0;
+  Ballot bal{0, 0};
+  i64 req_id = 0;
+  bool stop = false;
+  bool has_value = false; /* RequestPacket.hasRequestValue :1369 */
+  i32 median_cp = -1;
+  u32 nreq = 0, plen = 0, frame_ref = 0;
+};
+
+enum { ST_RECOVERY = 0, ST_ACTIVE_1 = 1, ST_ACTIVE_2 = 2, ST_STOPPED = 3, ST_FREE = 255 };
+
+/* group flags surfaced to the host slow path */
+enum { GF_OVERFLOW = 1, GF_NEEDS_SYNC = 2 };
+
+/* ------------------------------------------------------------------------------
+ * PaxosAcceptor.java
+ * ---------------------------------------------------------------------------- */
+struct Acceptor {
+  i32 _slot = 0, ballotNum = -1, ballotCoord = -1, acceptedGCSlot = -1; /* :94-99 */
+  uint8_t state = ST_FREE;
+  uint8_t flags = 0;
+  std::map<i32, PValue> acceptedProposals, committedRequests; /* :108-109 */
+  bool journaling = true; /* GET_ACCEPTED_PVALUES_FROM_DISK :75-76 */
+  int W = 0;
+
+  bool isStopped() const { return state == ST_STOPPED; }
+  Ballot getBallot() const { return Ballot{ballotNum, ballotCoord}; }
+
+  /* bounded-window store rule (device ring indexed by slot mod W) */
+  void accStore(const PValue& pv) {
+    if (W > 0) {
+      bool staleNew = jsub(pv.slot, _slot) < 0;
+      for (auto it = acceptedProposals.begin(); it != acceptedProposals.end();) {
+        if (it->first != pv.slot && (((u32)it->first) & (u32)(W - 1)) == (((u32)pv.slot) & (u32)(W - 1))) {
+          bool occStale = jsub(it->first, _slot) < 0;
+          if (staleNew && !occStale) return; /* never evict a live entry for a stale accept */
+          it = acceptedProposals.erase(it);
+        } else
+          ++it;
+      }
+    }
+    acceptedProposals[pv.slot] = pv;
+  }
+
+  /* handlePrepare ballot bump :245-251 (phase 1 itself is host slow path) */
+  void bumpBallot(Ballot b) {
+    if (b.compareTo(getBallot()) > 0) {
+      ballotNum = b.num;
+      ballotCoord = b.coord;
+    }
+  }
+
+  /* acceptAndUpdateBallot :302-322; returns false iff stopped (Java null) */
+  bool acceptAndUpdateBallot(const PValue& accept, Ballot* out) {
+    if (isStopped()) return false;
+    if (accept.bal.compareTo(getBallot()) >= 0) { /* :311 */
+      ballotNum = accept.bal.num;
+      ballotCoord = accept.bal.coord;
+      if (jsub(accept.slot, acceptedGCSlot) > 0) accStore(accept); /* :315-316 */
+    }
+    garbageCollectAccepted(accept.median_cp); /* :320 */
+    *out = getBallot();
+    return true;
+  }
+
+  /* garbageCollectAccepted :476-494 */
+  void garbageCollectAccepted(i32 gcSlot) {
+    if (jsub(_slot, gcSlot) <= 0) gcSlot = _slot - 1; /* :481-482 */
+    if (jsub(gcSlot, acceptedGCSlot) > 0) {           /* :484 */
+      acceptedGCSlot = gcSlot;
+      for (auto it = acceptedProposals.begin(); it != acceptedProposals.end();)
+        if (jsub(it->first, gcSlot) <= 0)
+          it = acceptedProposals.erase(it);
+        else
+          ++it;
+    }
+    garbageCollectDecisions(gcSlot);
+  }
+
+  /* garbageCollectDecisions :496-506 */
+  void garbageCollectDecisions(i32 slot) {
+    if (jsub(slot, _slot) >= 0) return;
+    for (auto it = committedRequests.begin(); it != committedRequests.end();)
+      if (jsub(slot, it->first) > 0)
+        it = committedRequests.erase(it);
+      else
+        ++it;
+  }
+
+  /* reconstructDecision :369-385 */
+  bool reconstructDecision(i32 slot, PValue* out) const {
+    auto c = committedRequests.find(slot);
+    if (c == committedRequests.end()) return false;
+    if (c->second.has_value) {
+      *out = c->second;
+      return true;
+    }
+    auto a = acceptedProposals.find(slot);
+    if (a != acceptedProposals.end() && a->second.bal.equals(c->second.bal)) {
+      *out = a->second; /* new PValuePacket(accept).makeDecision(committed.medianCP) */
+      out->median_cp = c->second.median_cp;
+      out->has_value = true;
+      return true;
+    }
+    return false;
+  }
+
+  /* executed :462-474 */
+  void executed(i32 s, bool stop) {
+    if (s == _slot) {
+      _slot = (i32)((u32)_slot + 1u);
+      if (stop) state = ST_STOPPED;
+      if (isStopped()) committedRequests.clear();
+    } else {
+      fprintf(stderr, "oracle: YIKES asked to execute %d when expecting %d\n", s, _slot);
+      abort();
+    }
+  }
+
+  /* putAndRemoveNextExecutable :325-366; decision is never null on this path */
+  bool putAndRemoveNextExecutable(const PValue& decision, PValue* out) {
+    if (isStopped()) return false;
+    garbageCollectAccepted(decision.median_cp); /* :340 */
+    if (jsub(decision.slot, _slot) >= 0) {      /* :343 */
+      auto it = committedRequests.find(decision.slot);
+      if (it == committedRequests.end() || !it->second.has_value) committedRequests[decision.slot] = decision;
+    }
+    bool have = false;
+    if (committedRequests.count(_slot)) { /* :352 */
+      PValue nx;
+      if (reconstructDecision(_slot, &nx) && nx.has_value) {
+        committedRequests.erase(_slot);
+        executed(nx.slot, nx.stop);
+        *out = nx;
+        have = true;
+      }
+    }
+    if (have && journaling) acceptedProposals.erase(out->slot); /* :360-362 */
+    return have;
+  }
+
+  /* jumpSlot :564-578 */
+  void jumpSlot(i32 slotNumber) {
+    for (i32 i = _slot; jsub(i, slotNumber) < 0; i = (i32)((u32)i + 1u)) {
+      executed(i, false);
+      committedRequests.erase(i);
+      if (journaling) acceptedProposals.erase(i);
+    }
+  }
+};
+
+/* ------------------------------------------------------------------------------
+ * paxosutil/WaitforUtility.java:34-115
+ * ---------------------------------------------------------------------------- */
+struct WaitforUtility {
+  std::vector<i32> members;
+  std::vector<bool> responded;
+  int heardCount = 0;
+  WaitforUtility() {}
+  explicit WaitforUtility(const std::vector<i32>& m) : members(m), responded(m.size(), false) {}
+  int getIndex(i32 node) const { /* :108-115 (last match wins) */
+    int index = -1;
+    for (size_t i = 0; i < members.size(); i++)
+      if (members[i] == node) index = (int)i;
+    return index;
+  }
+  bool updateHeardFrom(i32 node) { /* :51-62 */
+    bool changed = false;
+    int index = getIndex(node);
+    if (index >= 0 && index < (int)members.size()) {
+      if (!responded[index]) {
+        changed = true;
+        heardCount++;
+      }
+      responded[index] = true;
+    }
+    return changed;
+  }
+  bool heardFromMajority() const { return heardCount > (int)members.size() / 2; } /* :64-68 */
+  bool contains(i32 node) const { return getIndex(node) >= 0; }
+  u32 mask() const {
+    u32 m = 0;
+    for (size_t i = 0; i < responded.size() && i < 32; i++)
+      if (responded[i]) m |= 1u << i;
+    return m;
+  }
+};
+
+/* ------------------------------------------------------------------------------
+ * PaxosCoordinator.java + PaxosCoordinatorState.java (phase 2 only)
+ * ---------------------------------------------------------------------------- */
+struct Proposal {
+  PValue pvalue;
+  WaitforUtility waitfor;
+};
+enum { PT_NONE = 0, PT_DECISION = 1, PT_PREEMPTED = 2 };
+
+struct Coordinator {
+  bool exists = false;
+  bool active = false;
+  i32 myBallotNum = 0, myBallotCoord = 0;
+  i32 nextProposalSlotNumber = 0;
+  std::vector<i32> nodeSlotNumbers;
+  std::map<i32, Proposal> myProposals;
+  int W = 0;
+
+  Ballot getBallot() const { return Ballot{myBallotNum, myBallotCoord}; }
+
+  /* PaxosCoordinatorState ctor :163-178 / PaxosCoordinator.createCoordinator :91-104 */
+  void create(i32 bnum, i32 coord, i32 slot, size_t nMembers, bool recoveryOrZero) {
+    exists = true;
+    myBallotNum = bnum;
+    myBallotCoord = coord;
+    nextProposalSlotNumber = slot;
+    nodeSlotNumbers.assign(nMembers, -1);
+    myProposals.clear();
+    active = (bnum == 0 || recoveryOrZero);
+  }
+
+  /* getMedianMinus :867-875 */
+  i32 getMajorityCommittedSlot() const {
+    std::vector<i32> copy(nodeSlotNumbers);
+    std::sort(copy.begin(), copy.end());
+    size_t medianMinus = copy.size() % 2 == 0 ? copy.size() / 2 - 1 : copy.size() / 2;
+    return copy[medianMinus];
+  }
+
+  /* PCS.propose :233-263 (+ initCommander :841-851).  rc: 0 accept issued, 1 queued
+   * pre-active (no accept), -3 refused after stop, -4 window full (device rule) */
+  int propose(const std::vector<i32>& members, PValue req, PValue* acceptOut) {
+    auto prev = myProposals.find(nextProposalSlotNumber - 1);
+    if (prev != myProposals.end() && prev->second.pvalue.stop) return GPX_RS_REFUSED_STOP; /* :235-239 */
+    if (W > 0)
+      for (auto& kv : myProposals)
+        if ((((u32)kv.first) & (u32)(W - 1)) == (((u32)nextProposalSlotNumber) & (u32)(W - 1)))
+          return GPX_RS_BACKPRESSURE;
+    req.slot = nextProposalSlotNumber;
+    nextProposalSlotNumber = (i32)((u32)nextProposalSlotNumber + 1u);
+    req.bal = getBallot();
+    Proposal p;
+    p.pvalue = req;
+    p.waitfor = WaitforUtility(members);
+    myProposals[req.slot] = p; /* :247 */
+    if (active) {
+      *acceptOut = req;
+      acceptOut->median_cp = getMajorityCommittedSlot(); /* AcceptPacket(coord, pvalue, medianMinus) */
+      return 0;
+    }
+    return 1;
+  }
+
+  /* recordSlotNumber :809-825 -- NOTE plain '<', not wrap-aware */
+  void recordSlotNumber(const std::vector<i32>& members, i32 acceptor, i32 maxCheckpointedSlot) {
+    for (size_t i = 0; i < members.size(); i++)
+      if (members[i] == acceptor)
+        if (nodeSlotNumbers[i] < maxCheckpointedSlot) nodeSlotNumbers[i] = maxCheckpointedSlot;
+  }
+
+  /* handleAcceptReplyMyBallot :597-640 */
+  int handleAcceptReplyMyBallot(const std::vector<i32>& members, i32 acceptor, i32 slot, i32 maxCP, PValue* out) {
+    recordSlotNumber(members, acceptor, maxCP);
+    auto it = myProposals.find(slot);
+    if (it == myProposals.end()) return PT_NONE;
+    it->second.waitfor.updateHeardFrom(acceptor);
+    if (it->second.waitfor.heardFromMajority()) {
+      *out = it->second.pvalue;
+      out->median_cp = getMajorityCommittedSlot(); /* makeDecision(getMajorityCommittedSlot()) :630 */
+      myProposals.erase(it);                       /* :635 */
+      return PT_DECISION;
+    }
+    return PT_NONE;
+  }
+
+  /* handleAcceptReplyHigherBallot :661-675 */
+  int handleAcceptReplyHigherBallot(i32 slot, PValue* out) {
+    auto it = myProposals.find(slot);
+    if (it == myProposals.end()) return PT_NONE;
+    *out = it->second.pvalue;
+    myProposals.erase(it);
+    return PT_PREEMPTED;
+  }
+
+  bool preemptedFully() const { return myProposals.empty(); } /* :677-683 */
+
+  /* PaxosCoordinator.handleAcceptReply PaxosCoordinator.java:210-250 */
+  int handleAcceptReply(const std::vector<i32>& members, i32 acceptor, Ballot rb, i32 slot, i32 maxCP, PValue* out) {
+    if (!exists || !active) return PT_NONE; /* :212 */
+    i32 c = rb.compareTo(getBallot());
+    if (c > 0) return handleAcceptReplyHigherBallot(slot, out);
+    if (c == 0) return handleAcceptReplyMyBallot(members, acceptor, slot, maxCP, out);
+    return PT_NONE; /* :241 lower ballot ignored */
+  }
+};
+
+/* Java String.hashCode */
+static i32 javaStringHash(const char* s, size_t n) {
+  u32 h = 0;
+  for (size_t i = 0; i < n; i++) h = 31u * h + (u32)(unsigned char)s[i];
+  return (i32)h;
+}
+/* Math.abs (abs(MIN_VALUE) stays negative) */
+static i32 javaAbs(i32 v) { return v < 0 ? (i32)(0u - (u32)v) : v; }
+/* Java % on ints truncates toward zero, same as C */
+
+/* PISM.roundRobinCoordinator :2251-2256 */
+static i32 roundRobinCoordinator(i32 nameHash, const i32* members, i32 n, i32 ballotnum) {
+  i32 idx = javaAbs((i32)((u32)ballotnum + (u32)nameHash)) % n;
+  if (idx < 0) idx = -idx; /* abs(MIN_VALUE) % n is <= 0 in Java and would throw on the array access */
+  return members[idx];
+}
+/* PISM.getCPI :2694-2697 */
+static i32 getCPI(i32 cpi, double noise, i32 nameHash) {
+  return (i32)(cpi * (1 - noise) + (javaAbs(nameHash) % cpi) * 2 * noise);
+}
+/* PISM.lastCheckpointSlot :2594-2599 */
+static i32 lastCheckpointSlot(i32 slot, i32 checkpointInterval) {
+  i32 lcp = slot - slot % checkpointInterval;
+  if (lcp < 0 && ((lcp = jsub(lcp, checkpointInterval)) > 0)) lcp = lastCheckpointSlot(INT32_MAX, checkpointInterval);
+  return lcp;
+}
+
+/* ------------------------------------------------------------------------------
+ * MD5 (RFC 1321) -- RequestPacket.getDigest paxospackets/RequestPacket.java:1414-1430
+ * uses java.security.MessageDigest("MD5"), which is not under /root/reference.
+ * ---------------------------------------------------------------------------- */
+static void md5(const uint8_t* msg, size_t len, uint8_t out[16]) {
+  static const u32 K[64] = {
+      0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
+      0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
+      0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
+      0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
+      0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
+      0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
+      0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
+      0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+  static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9,  14, 20, 5, 9,
+                            14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
+                            4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+  u32 a0 = 0x67452301, b0 = 0xefcdab89, c0 = 0x98badcfe, d0 = 0x10325476;
+  size_t padded = ((len + 8) / 64 + 1) * 64;
+  std::vector<uint8_t> m(padded, 0);
+  memcpy(m.data(), msg, len);
+  m[len] = 0x80;
+  u64 bits = (u64)len * 8;
+  for (int i = 0; i < 8; i++) m[padded - 8 + i] = (uint8_t)(bits >> (8 * i));
+  for (size_t off = 0; off < padded; off += 64) {
+    u32 M[16];
+    for (int i = 0; i < 16; i++)
+      M[i] = (u32)m[off + 4 * i] | ((u32)m[off + 4 * i + 1] << 8) | ((u32)m[off + 4 * i + 2] << 16) |
+             ((u32)m[off + 4 * i + 3] << 24);
+    u32 A = a0, B = b0, C = c0, D = d0;
+    for (int i = 0; i < 64; i++) {
+      u32 F;
+      int g;
+      if (i < 16) {
+        F = (B & C) | (~B & D);
+        g = i;
+      } else if (i < 32) {
+        F = (D & B) | (~D & C);
+        g = (5 * i + 1) % 16;
+      } else if (i < 48) {
+        F = B ^ C ^ D;
+        g = (3 * i + 5) % 16;
+      } else {
+        F = C ^ (B | ~D);
+        g = (7 * i) % 16;
+      }
+      F = F + A + K[i] + M[g];
+      A = D;
+      D = C;
+      C = B;
+      B = B + ((F << S[i]) | (F >> (32 - S[i])));
+    }
+    a0 += A;
+    b0 += B;
+    c0 += C;
+    d0 += D;
+  }
+  u32 r[4] = {a0, b0, c0, d0};
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) out[4 * i + j] = (uint8_t)(r[i] >> (8 * j));
+}
+
+/* ------------------------------------------------------------------------------
+ * paxosutil/HotRestoreInfo.java:60-120 string form ('|' separated)
+ * Util.arrayOfIntToString -> "[a, b, c]"
+ * ---------------------------------------------------------------------------- */
+static std::string arrayOfIntToString(const std::vector<i32>& a) {
+  std::string s = "[";
+  for (size_t i = 0; i < a.size(); i++) {
+    s += std::to_string(a[i]);
+    if (i + 1 < a.size()) s += ", ";
+  }
+  return s + "]";
+}
+static std::vector<i32> stringToIntArray(const std::string& s) {
+  std::vector<i32> out;
+  std::string cur;
+  for (char ch : s) {
+    if ((ch >= '0' && ch <= '9') || ch == '-')
+      cur += ch;
+    else if (!cur.empty()) {
+      out.push_back((i32)atol(cur.c_str()));
+      cur.clear();
+    }
+  }
+  if (!cur.empty()) out.push_back((i32)atol(cur.c_str()));
+  return out;
+}
+struct HotRestoreInfo {
+  std::string paxosID;
+  i32 version = 0;
+  std::vector<i32> members;
+  i32 accSlot = 0;
+  Ballot accBallot{0, 0};
+  i32 accGCSlot = 0;
+  bool hasCoord = false;
+  Ballot coordBallot{0, 0};
+  i32 nextProposalSlot = 0;
+  bool hasNodeSlots = false;
+  std::vector<i32> nodeSlots;
+  std::string toString() const {
+    return paxosID + "|" + std::to_string(version) + "|" + arrayOfIntToString(members) + "|" +
+           std::to_string(accSlot) + "|" + accBallot.toString() + "|" + std::to_string(accGCSlot) + "|" +
+           (hasCoord ? coordBallot.toString() : std::string("null")) + "|" + std::to_string(nextProposalSlot) + "|" +
+           (hasNodeSlots ? arrayOfIntToString(nodeSlots) : std::string("null"));
+  }
+  static Ballot parseBallot(const std::string& s) {
+    size_t c = s.find(':');
+    return Ballot{(i32)atol(s.substr(0, c).c_str()), (i32)atol(s.substr(c + 1).c_str())};
+  }
+  static HotRestoreInfo parse(const std::string& ser) {
+    std::vector<std::string> t;
+    size_t start = 0;
+    while (true) {
+      size_t p = ser.find('|', start);
+      if (p == std::string::npos) {
+        t.push_back(ser.substr(start));
+        break;
+      }
+      t.push_back(ser.substr(start, p - start));
+      start = p + 1;
+    }
+    HotRestoreInfo h;
+    h.paxosID = t[0];
+    h.version = (i32)atol(t[1].c_str());
+    h.members = stringToIntArray(t[2]);
+    h.accSlot = (i32)atol(t[3].c_str());
+    h.accGCSlot = (i32)atol(t[5].c_str());
+    h.accBallot = parseBallot(t[4]);
+    h.hasCoord = t[6] != "null";
+    if (h.hasCoord) h.coordBallot = parseBallot(t[6]);
+    h.nextProposalSlot = (i32)atol(t[7].c_str());
+    h.hasNodeSlots = t[8] != "null";
+    if (h.hasNodeSlots) h.nodeSlots = stringToIntArray(t[8]);
+    return h;
+  }
+};
+
+/* ------------------------------------------------------------------------------
+ * record-level engine (same C ABI as the CUDA engine, prefix gpxo_)
+ * ---------------------------------------------------------------------------- */
+struct Group {
+  bool live = false;
+  i32 version = 0;
+  i32 name_hash = 0;
+  std::vector<i32> members; /* sorted (PISM ctor :205) */
+  i32 cpi = 400;
+};
+struct Lane {
+  i32 node = 0;
+  std::vector<Acceptor> acc;
+  std::vector<Coordinator> coord;
+  std::vector<uint8_t> ring;
+  u64 seg_seq = 0;
+};
+
+static thread_local std::string g_err;
+
+}  // namespace
+
+struct gpxo_engine {
+  gpx_config cfg;
+  std::vector<Group> groups;
+  std::vector<Lane> lanes;
+  gpx_counters ctr;
+  u32 L() const { return cfg.n_lanes; }
+  int W() const { return (int)cfg.window; }
+
+  int laneOfNode(i32 node) const {
+    for (u32 l = 0; l < cfg.n_lanes; l++)
+      if (lanes[l].node == node) return (int)l;
+    return -1;
+  }
+  int memberIdx(const Group& g, i32 node) const {
+    int idx = -1;
+    for (size_t i = 0; i < g.members.size(); i++)
+      if (g.members[i] == node) idx = (int)i;
+    return idx;
+  }
+  u32 localMask(const Group& g) const {
+    u32 m = 0;
+    for (u32 l = 0; l < cfg.n_lanes; l++)
+      if (memberIdx(g, lanes[l].node) >= 0) m |= 1u << l;
+    return m;
+  }
+  bool usable(u32 gid, u32 lane) const {
+    if (gid >= groups.size() || !groups[gid].live) return false;
+    uint8_t st = lanes[lane].acc[gid].state;
+    return st == ST_ACTIVE_1 || st == ST_ACTIVE_2;
+  }
+
+  /* ring: append a segment, return offset of header */
+  u64 segBegin(u32 lane, uint16_t type, u32 n_slots, u32 rec_bytes, u64 payload_bytes) {
+    Lane& ln = lanes[lane];
+    u64 off = ln.ring.size();
+    u64 total = 64 + (u64)n_slots * rec_bytes + ((payload_bytes + 15) & ~(u64)15);
+    ln.ring.resize(off + total, 0);
+    gpx_log_seg_hdr h;
+    memset(&h, 0, sizeof h);
+    h.magic = GPX_SEG_MAGIC;
+    h.type = type;
+    h.lane = (uint16_t)lane;
+    h.n_slots = n_slots;
+    h.n_valid = n_slots;
+    h.payload_bytes = (payload_bytes + 15) & ~(u64)15;
+    h.seq = ln.seg_seq++;
+    h.ring_off = off;
+    h.rec_bytes = rec_bytes;
+    memcpy(&ln.ring[off], &h, sizeof h);
+    return off;
+  }
+
+  /* PISM.shouldCheckpoint :2037-2041 */
+  bool shouldCheckpoint(const Group& g, const PValue& d) const { return (d.slot % g.cpi == 0) || d.stop; }
+
+  gpx_exec_rec makeExec(u32 gid, u32 lane, const Group& g, const PValue& x, bool extra) const {
+    gpx_exec_rec r;
+    r.gid = gid;
+    r.slot = x.slot;
+    r.req_id = x.req_id;
+    r.payload_off = x.frame_ref;
+    u32 f = (x.stop ? GPX_F_STOP : 0) | (shouldCheckpoint(g, x) ? GPX_F_CKPT : 0) | (extra ? GPX_F_EXTRA : 0);
+    r.flags = f | (lane << 8) | (x.nreq << 16);
+    return r;
+  }
+
+  /* PISM.extractExecuteAndCheckpoint :1619-1701 (execution itself is the host app's) */
+  void EEC(Acceptor& A, const PValue& loggedDecision, std::vector<PValue>& out) {
+    if (A.isStopped()) return;
+    PValue nx;
+    while (A.putAndRemoveNextExecutable(loggedDecision, &nx)) {
+      out.push_back(nx);
+      ctr.executed++;
+      if (nx.stop) {
+        ctr.stops_executed++;
+        break;
+      }
+    }
+  }
+
+  /* the logged form of a decision, PISM.handleCommittedRequest :1446-1466 */
+  bool decisionLogImage(const Acceptor& A, u32 gid, u32 lane, const PValue& committed, gpx_decision_rec* img) const {
+    if (!(committed.has_value || cfg.log_meta_decisions)) return false;
+    auto ca = A.acceptedProposals.find(committed.slot);
+    bool meta = cfg.log_meta_decisions && ca != A.acceptedProposals.end() &&
+                ca->second.bal.compareTo(committed.bal) >= 0;
+    img->gid = gid;
+    img->slot = committed.slot;
+    img->bnum = committed.bal.num;
+    img->bcoord = committed.bal.coord;
+    img->median_cp = meta ? -1 : committed.median_cp; /* getMetaDecision() resets medianCP :212-218 */
+    img->flags = (uint16_t)(GPX_F_DECISION | (meta ? GPX_F_META : 0) | (committed.stop ? GPX_F_STOP : 0));
+    img->dst_mask = (uint16_t)(1u << lane);
+    img->req_id = committed.req_id;
+    return true;
+  }
+};
+
+namespace {
+static void put_event_exec(std::vector<gpx_exec_rec>& v, const gpx_exec_rec& r) { v.push_back(r); }
+}
+
+extern "C" {
+
+const char* gpxo_last_error(void) { return g_err.c_str(); }
+const char* gpxo_build_info(void) { return "oracle (CPU restatement of the Java reference; test infrastructure)"; }
+
+void gpxo_config_defaults(gpx_config* c) {
+  memset(c, 0, sizeof *c);
+  c->abi_version = GPX_ABI_VERSION;
+  c->device = 0;
+  c->max_groups = 1024;
+  c->n_lanes = 3;
+  c->lane_node[0] = 100; /* TC.TEST_START_NODE_ID testing/TESTPaxosConfig.java:100 */
+  c->lane_node[1] = 101;
+  c->lane_node[2] = 102;
+  c->window = 8;
+  c->max_group_size = 3;
+  c->log_ring_bytes = 1ull << 26;
+  c->max_batch_recs = 1u << 16;
+  c->max_batch_payload = 1ull << 24;
+  c->batching_enabled = 1;
+  c->max_batch_size = 2000;
+  c->max_batch_bytes = 4 * 1024 * 1024;
+  c->request_size_estimate = 512;
+  c->checkpoint_interval = 400;
+  c->cpi_noise = 0;
+  c->gc_majority_executed = 1;
+  c->log_meta_decisions = 1;
+  c->journaling_enabled = 1;
+  c->batched_accept_replies = 1;
+  c->batched_commits = 1;
+  c->short_circuit_local = 1;
+  c->min_pp_batch_size = 3;
+  c->digest_requests = 0;
+}
+
+int gpxo_engine_create(const gpx_config* cfg, gpxo_engine** out) {
+  if (!cfg || !out || cfg->abi_version != GPX_ABI_VERSION) return GPX_EINVAL;
+  if (cfg->n_lanes == 0 || cfg->n_lanes > GPX_MAX_LANES) return GPX_EINVAL;
+  if (cfg->window != 0 && (cfg->window > GPX_MAX_WINDOW || (cfg->window & (cfg->window - 1)))) return GPX_EINVAL;
+  gpxo_engine* e = new gpxo_engine();
+  e->cfg = *cfg;
+  memset(&e->ctr, 0, sizeof e->ctr);
+  e->groups.resize(cfg->max_groups);
+  e->lanes.resize(cfg->n_lanes);
+  for (u32 l = 0; l < cfg->n_lanes; l++) {
+    e->lanes[l].node = cfg->lane_node[l];
+    e->lanes[l].acc.resize(cfg->max_groups);
+    e->lanes[l].coord.resize(cfg->max_groups);
+  }
+  *out = e;
+  return GPX_OK;
+}
+void gpxo_engine_destroy(gpxo_engine* e) { delete e; }
+
+/* PaxosManager.createPaxosInstance(Map,Set) :664-691 -> HotRestoreInfo.createHRI :145-157 (GPX_INIT_BATCH)
+ * or PISM.initiateRecovery :591-675 + putInitialState :692-699 (GPX_INIT_DEFAULT) */
+int gpxo_create_groups(gpxo_engine* e, uint32_t n, const gpx_group_desc* d) {
+  for (u32 k = 0; k < n; k++) {
+    if (d[k].gid >= e->cfg.max_groups || d[k].n_members <= 0 || d[k].n_members > GPX_MAX_GROUP_SIZE) return GPX_ERANGE;
+    Group& g = e->groups[d[k].gid];
+    g.live = true;
+    g.version = d[k].version;
+    g.name_hash = d[k].name_hash;
+    g.members.assign(d[k].members, d[k].members + d[k].n_members);
+    std::sort(g.members.begin(), g.members.end());
+    g.cpi = getCPI(e->cfg.checkpoint_interval, e->cfg.cpi_noise, g.name_hash);
+    i32 coord0 = roundRobinCoordinator(g.name_hash, g.members.data(), (i32)g.members.size(), 0);
+    for (u32 l = 0; l < e->L(); l++) {
+      Acceptor& A = e->lanes[l].acc[d[k].gid];
+      Coordinator& C = e->lanes[l].coord[d[k].gid];
+      A = Acceptor();
+      C = Coordinator();
+      A.W = e->W();
+      C.W = e->W();
+      A.journaling = e->cfg.journaling_enabled != 0;
+      if (e->memberIdx(g, e->lanes[l].node) < 0) continue; /* lane not a member: no instance */
+      if (d[k].init_mode == GPX_INIT_BATCH) {
+        /* createHRI: accSlot=1, accBallot=(0,coord), accGCSlot=-1, coordBallot=(0,coord),
+         * nextProposalSlot=1, nodeSlots=new int[R] (zeros); PISM.hotRestore :677-689 */
+        A._slot = 1;
+        A.ballotNum = 0;
+        A.ballotCoord = coord0;
+        A.acceptedGCSlot = -1;
+        A.state = ST_ACTIVE_1;
+        if (coord0 == e->lanes[l].node) {
+          C.create(0, coord0, 1, g.members.size(), true);
+          C.nodeSlotNumbers.assign(g.members.size(), 0); /* setNodeSlots(hri.nodeSlots) */
+        }
+      } else {
+        /* initiateRecovery: acceptor (0, rrCoord(0)), slot 0; putInitialState ->
+         * handleCheckpoint -> jumpSlot(1); setGCSlotAfterPuttingInitialSlot -> gc 0;
+         * coordinator at rr node with nextProposalSlot=1, nodeSlots=-1 */
+        A._slot = 0;
+        A.ballotNum = 0;
+        A.ballotCoord = coord0;
+        A.acceptedGCSlot = -1;
+        A.state = ST_ACTIVE_1;
+        A.jumpSlot(1);
+        A.acceptedGCSlot = 0;
+        if (coord0 == e->lanes[l].node) C.create(0, coord0, 1, g.members.size(), true);
+      }
+    }
+  }
+  return GPX_OK;
+}
+
+int gpxo_destroy_groups(gpxo_engine* e, uint32_t n, const uint32_t* gids) {
+  for (u32 k = 0; k < n; k++) {
+    if (gids[k] >= e->cfg.max_groups) return GPX_ERANGE;
+    e->groups[gids[k]].live = false;
+    for (u32 l = 0; l < e->L(); l++) {
+      e->lanes[l].acc[gids[k]] = Acceptor();
+      e->lanes[l].coord[gids[k]] = Coordinator();
+    }
+  }
+  return GPX_OK;
+}
+
+int gpxo_dump_rows(gpxo_engine* e, uint32_t n, const uint32_t* gids, uint32_t lane, gpx_row* out) {
+  if (lane >= e->L()) return GPX_ERANGE;
+  for (u32 k = 0; k < n; k++) {
+    u32 gid = gids[k];
+    if (gid >= e->cfg.max_groups) return GPX_ERANGE;
+    const Group& g = e->groups[gid];
+    const Acceptor& A = e->lanes[lane].acc[gid];
+    const Coordinator& C = e->lanes[lane].coord[gid];
+    gpx_row& r = out[k];
+    memset(&r, 0, sizeof r);
+    r.gid = gid;
+    r.lane = lane;
+    r.version = g.version;
+    r.acc_slot = A._slot;
+    r.acc_bnum = A.ballotNum;
+    r.acc_bcoord = A.ballotCoord;
+    r.acc_gc_slot = A.acceptedGCSlot;
+    r.state = g.live ? A.state : GPX_ST_FREE;
+    r.coord_exists = C.exists;
+    r.coord_active = C.exists && C.active;
+    r.coord_bnum = C.exists ? C.myBallotNum : 0;
+    r.coord_bcoord = C.exists ? C.myBallotCoord : 0;
+    r.next_proposal_slot = C.exists ? C.nextProposalSlotNumber : 0;
+    r.n_members = (i32)g.members.size();
+    for (size_t i = 0; i < g.members.size(); i++) {
+      r.members[i] = g.members[i];
+      r.node_slots[i] = C.exists ? C.nodeSlotNumbers[i] : 0;
+    }
+  }
+  return GPX_OK;
+}
+
+int gpxo_load_rows(gpxo_engine* e, uint32_t n, const gpx_row* rows) {
+  for (u32 k = 0; k < n; k++) {
+    const gpx_row& r = rows[k];
+    if (r.gid >= e->cfg.max_groups || r.lane >= e->L() || r.n_members <= 0 || r.n_members > GPX_MAX_GROUP_SIZE)
+      return GPX_ERANGE;
+    Group& g = e->groups[r.gid];
+    g.live = true;
+    g.version = r.version;
+    g.members.assign(r.members, r.members + r.n_members);
+    std::sort(g.members.begin(), g.members.end());
+    Acceptor& A = e->lanes[r.lane].acc[r.gid];
+    Coordinator& C = e->lanes[r.lane].coord[r.gid];
+    A = Acceptor();
+    C = Coordinator();
+    A.W = e->W();
+    C.W = e->W();
+    A.journaling = e->cfg.journaling_enabled != 0;
+    A._slot = r.acc_slot;
+    A.ballotNum = r.acc_bnum;
+    A.ballotCoord = r.acc_bcoord;
+    A.acceptedGCSlot = r.acc_gc_slot;
+    A.state = (uint8_t)r.state;
+    if (r.coord_exists) {
+      C.create(r.coord_bnum, r.coord_bcoord, r.next_proposal_slot, g.members.size(), true);
+      C.active = r.coord_active != 0;
+      C.nodeSlotNumbers.assign(r.node_slots, r.node_slots + r.n_members);
+    }
+  }
+  return GPX_OK;
+}
+
+int gpxo_patch(gpxo_engine* e, uint32_t n, const gpx_patch_rec* p) {
+  for (u32 k = 0; k < n; k++) {
+    if (p[k].gid >= e->cfg.max_groups || p[k].lane >= e->L()) return GPX_ERANGE;
+    Group& g = e->groups[p[k].gid];
+    Acceptor& A = e->lanes[p[k].lane].acc[p[k].gid];
+    Coordinator& C = e->lanes[p[k].lane].coord[p[k].gid];
+    switch (p[k].op) {
+      case GPX_PATCH_SET_BALLOT: A.bumpBallot(Ballot{p[k].a, p[k].b}); break;
+      case GPX_PATCH_JUMP_SLOT:
+        if (jsub(p[k].a, A._slot) > 0) A.jumpSlot(p[k].a);
+        break;
+      case GPX_PATCH_SET_STATE:
+        A.state = (uint8_t)p[k].a;
+        if (A.isStopped()) A.committedRequests.clear();
+        break;
+      case GPX_PATCH_INSTALL_COORD:
+        C.create(p[k].a, p[k].b, p[k].c, g.members.size(), p[k].d != 0);
+        C.active = p[k].d != 0;
+        break;
+      case GPX_PATCH_RESIGN_COORD: C = Coordinator(); C.W = e->W(); break;
+      case GPX_PATCH_SET_GC: A.acceptedGCSlot = p[k].a; break;
+      default: return GPX_EINVAL;
+    }
+  }
+  return GPX_OK;
+}
+
+/* RequestBatcher.dequeueImpl RequestBatcher.java:168-234 (canonical rule) +
+ * PISM.handleRequest :767 / handleProposal :818-888 + PCS.propose :233-263 */
+int gpxo_propose(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                 uint64_t payload_bytes, gpx_accept_rec* out_accepts, uint32_t* n_accepts, uint8_t* out_blob,
+                 uint64_t blob_cap, uint64_t* blob_bytes, int32_t* status) {
+  (void)payload_bytes;
+  u32 na = 0;
+  u64 bb = 0;
+  u32 i = 0;
+  while (i < n) {
+    u32 gid = reqs[i].gid;
+    u32 j = i;
+    while (j < n && reqs[j].gid == gid) j++;
+    /* run [i, j) */
+    u32 entry = (reqs[i].flags >> 8) & 0xf;
+    auto setAll = [&](u32 a, u32 b, i32 code) {
+      for (u32 k = a; k < b; k++) status[k] = code;
+      e->ctr.requests_rejected += (b - a);
+    };
+    if (entry >= e->L() || !e->usable(gid, entry)) {
+      setAll(i, j, GPX_RS_DROPPED);
+      i = j;
+      continue;
+    }
+    Group& g = e->groups[gid];
+    /* handleProposal at the entry lane: PaxosCoordinator.exists(c, paxosState.getBallot()) :824 */
+    int clane = -1;
+    {
+      Acceptor& Ae = e->lanes[entry].acc[gid];
+      Coordinator& Ce = e->lanes[entry].coord[gid];
+      if (Ce.exists && Ce.getBallot().compareTo(Ae.getBallot()) >= 0)
+        clane = (int)entry;
+      else {
+        int fl = e->laneOfNode(Ae.ballotCoord); /* forward to paxosState.getBallotCoord() :862 */
+        if (fl < 0) {
+          setAll(i, j, GPX_RS_FORWARD);
+          i = j;
+          continue;
+        }
+        if (fl == (int)entry) { /* coordinator == myID: force run for coordinator (host) :874-885 */
+          setAll(i, j, GPX_RS_NOCOORD);
+          i = j;
+          continue;
+        }
+        if (!e->usable(gid, (u32)fl)) {
+          setAll(i, j, GPX_RS_DROPPED);
+          i = j;
+          continue;
+        }
+        Acceptor& Af = e->lanes[fl].acc[gid];
+        Coordinator& Cf = e->lanes[fl].coord[gid];
+        if (Cf.exists && Cf.getBallot().compareTo(Af.getBallot()) >= 0)
+          clane = fl;
+        else {
+          setAll(i, j, GPX_RS_NOCOORD);
+          i = j;
+          continue;
+        }
+      }
+    }
+    Coordinator& C = e->lanes[clane].coord[gid];
+    u32 k = i;
+    while (k < j) {
+      /* one batch: first + following within limits (RequestBatcher :198-219) */
+      i64 totalByteLength = (i64)reqs[k].payload_len + e->cfg.request_size_estimate;
+      i32 totalBatchSize = 1;
+      u32 b = k + 1;
+      if (e->cfg.batching_enabled)
+        while (b < j) {
+          totalByteLength += (i64)reqs[b].payload_len + e->cfg.request_size_estimate;
+          if (totalByteLength > e->cfg.max_batch_bytes) break;
+          totalBatchSize += 1;
+          if (totalBatchSize > e->cfg.max_batch_size) break;
+          b++;
+        }
+      u32 nreq = b - k;
+      PValue req;
+      req.req_id = reqs[k].req_id;
+      req.stop = false;
+      for (u32 q = k; q < b; q++) req.stop = req.stop || (reqs[q].flags & GPX_F_STOP); /* isStopRequest :1069 */
+      req.has_value = true;
+      req.nreq = nreq;
+      PValue acc;
+      int rc = C.propose(g.members, req, &acc);
+      if (rc == GPX_RS_REFUSED_STOP || rc == GPX_RS_BACKPRESSURE) {
+        setAll(k, j, rc); /* the rest of the run meets the same refusal */
+        break;
+      }
+      if (rc == 1) { /* pre-active: queued at the coordinator without an ACCEPT */
+        for (u32 q = k; q < b; q++) status[q] = GPX_RS_PREACTIVE;
+        k = b;
+        continue;
+      }
+      /* blob */
+      u64 boff = bb;
+      u32 plen;
+      if (nreq == 1) {
+        plen = reqs[k].payload_len;
+        if (bb + ((plen + 15) & ~15u) > blob_cap) return GPX_ERANGE;
+        memcpy(out_blob + bb, payload + reqs[k].payload_off, plen);
+        if (plen & 15) memset(out_blob + bb + plen, 0, 16 - (plen & 15));
+      } else {
+        u64 total = (u64)nreq * 16;
+        for (u32 q = k; q < b; q++) total += reqs[q].payload_len;
+        plen = (u32)total;
+        if (bb + ((total + 15) & ~(u64)15) > blob_cap) return GPX_ERANGE;
+        u64 w = bb;
+        for (u32 q = k; q < b; q++) {
+          gpx_batch_ent be;
+          be.req_id = reqs[q].req_id;
+          be.len = reqs[q].payload_len;
+          be.flags = reqs[q].flags;
+          memcpy(out_blob + w, &be, 16);
+          w += 16;
+        }
+        for (u32 q = k; q < b; q++) {
+          memcpy(out_blob + w, payload + reqs[q].payload_off, reqs[q].payload_len);
+          w += reqs[q].payload_len;
+        }
+        if (w & 15) memset(out_blob + w, 0, 16 - (w & 15));
+      }
+      bb += ((u64)plen + 15) & ~(u64)15;
+      gpx_accept_rec& a = out_accepts[na++];
+      a.h.gid = gid;
+      a.h.slot = acc.slot;
+      a.h.bnum = acc.bal.num;
+      a.h.bcoord = acc.bal.coord;
+      a.h.median_cp = acc.median_cp;
+      a.h.flags = (uint16_t)(GPX_F_ACCEPT | (req.stop ? GPX_F_STOP : 0));
+      a.h.dst_mask = (uint16_t)e->localMask(g);
+      a.h.req_id = req.req_id;
+      a.payload_off = (u32)boff;
+      a.payload_len = plen;
+      a.nreq = nreq;
+      a.sender = C.myBallotCoord;
+      status[k] = acc.slot;
+      for (u32 q = k + 1; q < b; q++) status[q] = GPX_RS_BATCHED;
+      e->ctr.proposals++;
+      e->ctr.requests_batched += nreq;
+      k = b;
+    }
+    i = j;
+  }
+  *n_accepts = na;
+  *blob_bytes = bb;
+  return GPX_OK;
+}
+
+/* PISM.handleAccept :1080-1166 at every addressed local lane */
+int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
+                        uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra_exec,
+                        uint32_t extra_cap, uint32_t* n_extra) {
+  u32 L = e->L();
+  std::vector<u64> seg(L), pay(L);
+  for (u32 l = 0; l < L; l++) {
+    seg[l] = e->segBegin(l, GPX_F_ACCEPT, n, 48, blob_bytes);
+    pay[l] = seg[l] + 64 + (u64)n * 48;
+  }
+  std::vector<gpx_exec_rec> extras;
+  for (u32 i = 0; i < n; i++) {
+    const gpx_accept_rec& r = accepts[i];
+    for (u32 l = 0; l < L; l++) {
+      gpx_accept_reply_rec& rep = out_replies[(u64)i * L + l];
+      memset(&rep, 0, sizeof rep);
+      rep.gid = r.h.gid;
+      rep.slot = r.h.slot;
+      rep.who = GPX_WHO(0xff, 0xff, GPX_F_VOID);
+      gpx_accept_rec img = r;
+      img.h.flags = GPX_F_VOID;
+      auto writeImg = [&]() { memcpy(&e->lanes[l].ring[seg[l] + 64 + (u64)i * 48], &img, 48); };
+      if (!(r.h.dst_mask & (1u << l)) || (r.h.flags & GPX_F_VOID)) {
+        writeImg();
+        continue;
+      }
+      if (!e->usable(r.h.gid, l)) { /* PISM :456-460 stopped / no instance -> dropped */
+        e->ctr.accepts_dropped++;
+        writeImg();
+        continue;
+      }
+      Group& g = e->groups[r.h.gid];
+      Acceptor& A = e->lanes[l].acc[r.h.gid];
+      int myIdx = e->memberIdx(g, e->lanes[l].node);
+      if (myIdx < 0) {
+        e->ctr.accepts_dropped++;
+        writeImg();
+        continue;
+      }
+      if (e->W() > 0 && jsub(r.h.slot, A._slot) >= e->W()) { /* device window rule */
+        A.flags |= GF_OVERFLOW;
+        e->ctr.window_overflow++;
+        e->ctr.accepts_dropped++;
+        writeImg();
+        continue;
+      }
+      e->ctr.accepts_handled++;
+      PValue accept;
+      accept.slot = r.h.slot;
+      accept.bal = Ballot{r.h.bnum, r.h.bcoord};
+      accept.req_id = r.h.req_id;
+      accept.stop = (r.h.flags & GPX_F_STOP) != 0;
+      accept.has_value = true;
+      accept.median_cp = r.h.median_cp;
+      accept.nreq = r.nreq;
+      accept.plen = r.payload_len;
+      accept.frame_ref = (u32)((pay[l] + r.payload_off) / 16);
+      /* prev = paxosState.getAccept(accept.slot) :1123 */
+      bool hasPrev = A.acceptedProposals.count(accept.slot) != 0;
+      PValue prev;
+      if (hasPrev) prev = A.acceptedProposals[accept.slot];
+      /* a duplicate of an already accepted pvalue keeps the frame it was logged in */
+      if (hasPrev && prev.bal.equals(accept.bal)) accept.frame_ref = prev.frame_ref;
+      Ballot ballot;
+      if (!A.acceptAndUpdateBallot(accept, &ballot)) {
+        writeImg();
+        continue;
+      }
+      /* AcceptReplyPacket :1139-1143 */
+      rep.bnum = ballot.num;
+      rep.bcoord = ballot.coord;
+      rep.max_cp = e->cfg.gc_majority_executed ? A._slot - 1 : lastCheckpointSlot(A._slot - 1, g.cpi);
+      rep.req_id = r.h.req_id;
+      int dstIdx = e->memberIdx(g, r.sender);
+      /* toLog :1146-1149 */
+      bool toLog = accept.bal.compareTo(ballot) >= 0 && jsub(accept.slot, A.acceptedGCSlot) > 0 &&
+                   (!hasPrev || prev.bal.compareTo(accept.bal) < 0);
+      bool nack = ballot.compareTo(accept.bal) > 0;
+      u32 rf = (toLog ? GPX_F_LOGGED : 0) | (nack ? GPX_F_NACK : 0);
+      rep.who = GPX_WHO(myIdx, dstIdx < 0 ? 0xff : dstIdx, rf);
+      if (nack)
+        e->ctr.accepts_nacked++;
+      else
+        e->ctr.accepts_acked++;
+      if (toLog) {
+        e->ctr.accepts_logged++;
+        img = r;
+        img.h.dst_mask = (uint16_t)(1u << l);
+        memcpy(&e->lanes[l].ring[pay[l] + r.payload_off], blob + r.payload_off, r.payload_len);
+      }
+      writeImg();
+      /* reconstructDecision(accept.slot) -> handleCommittedRequest :1158-1161 */
+      PValue rd;
+      if (A.reconstructDecision(accept.slot, &rd)) {
+        /* the re-log of the reconstructed decision (logDecision :1446) is deliberately omitted:
+         * its placeholder was logged on arrival and replay of {placeholder, accept} is
+         * idempotent (DESIGN.md "Deliberate omissions") */
+        std::vector<PValue> ex;
+        e->EEC(A, rd, ex);
+        for (auto& x : ex) put_event_exec(extras, e->makeExec(r.h.gid, l, g, x, true));
+      }
+    }
+  }
+  u32 ne = 0;
+  for (auto& x : extras)
+    if (ne < extra_cap) out_extra_exec[ne++] = x;
+  if (n_extra) *n_extra = (u32)extras.size();
+  return GPX_OK;
+}
+
+/* PISM.handleBatchedAcceptReply :1370-1419 -> handleAcceptReply :1248-1365 per slot */
+int gpxo_handle_accept_replies(gpxo_engine* e, uint32_t n, const gpx_accept_reply_rec* replies,
+                               gpx_decision_rec* out_decisions, uint32_t* n_decisions) {
+  u32 nd = 0;
+  for (u32 i = 0; i < n; i++) {
+    const gpx_accept_reply_rec& r = replies[i];
+    u32 wf = GPX_WHO_FLAGS(r.who);
+    if (wf & GPX_F_VOID) continue;
+    if (r.gid >= e->cfg.max_groups || !e->groups[r.gid].live) {
+      e->ctr.replies_ignored++;
+      continue;
+    }
+    Group& g = e->groups[r.gid];
+    u32 dstIdx = GPX_WHO_DST(r.who), accIdx = GPX_WHO_ACC(r.who);
+    if (dstIdx >= g.members.size()) {
+      e->ctr.replies_ignored++;
+      continue;
+    }
+    int lane = e->laneOfNode(g.members[dstIdx]);
+    if (lane < 0 || !e->usable(r.gid, (u32)lane)) {
+      e->ctr.replies_ignored++;
+      continue;
+    }
+    e->ctr.replies_handled++;
+    Coordinator& C = e->lanes[lane].coord[r.gid];
+    i32 acceptorNode = accIdx < g.members.size() ? g.members[accIdx] : INT32_MIN;
+    Ballot rb{r.bnum, r.bcoord};
+    PValue pv;
+    int t = C.handleAcceptReply(g.members, acceptorNode, rb, r.slot, r.max_cp, &pv);
+    /* nullifyCoordinatorIfPreemptedFully :1353-1356 / PaxosCoordinator.isPreemptedFully :109-114 */
+    if (C.exists && rb.compareTo(C.getBallot()) > 0 && C.preemptedFully()) {
+      C = Coordinator();
+      C.W = e->W();
+      e->ctr.coordinators_resigned++;
+    }
+    if (t == PT_DECISION) {
+      gpx_decision_rec& d = out_decisions[nd++];
+      d.gid = r.gid;
+      d.slot = pv.slot;
+      d.bnum = pv.bal.num;
+      d.bcoord = pv.bal.coord;
+      d.median_cp = pv.median_cp;
+      d.flags = (uint16_t)(GPX_F_DECISION | (pv.stop ? GPX_F_STOP : 0));
+      d.dst_mask = (uint16_t)e->localMask(g);
+      d.req_id = pv.req_id;
+      e->ctr.decisions_made++;
+    } else if (t == PT_PREEMPTED) {
+      e->ctr.preempted++; /* dropped: FORWARD_PREEMPTED_REQUESTS=false PaxosConfig.java:927 */
+    }
+  }
+  *n_decisions = nd;
+  return GPX_OK;
+}
+
+/* PISM.handleBatchedCommit :1480-1528 per slot -> handleCommittedRequest :1432-1478 ->
+ * extractExecuteAndCheckpoint :1619-1701 */
+int gpxo_handle_decisions(gpxo_engine* e, uint32_t n, const gpx_decision_rec* decisions, gpx_exec_rec* out_exec,
+                          gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  u32 L = e->L();
+  std::vector<u64> seg(L);
+  for (u32 l = 0; l < L; l++) seg[l] = e->segBegin(l, GPX_F_DECISION, n, 32, 0);
+  std::vector<gpx_exec_rec> extras;
+  for (u32 i = 0; i < n; i++) {
+    const gpx_decision_rec& r = decisions[i];
+    for (u32 l = 0; l < L; l++) {
+      gpx_exec_rec& ex = out_exec[(u64)i * L + l];
+      memset(&ex, 0, sizeof ex);
+      ex.gid = r.gid;
+      ex.slot = r.slot;
+      ex.flags = GPX_F_VOID | (l << 8);
+      gpx_decision_rec img = r;
+      img.flags = GPX_F_VOID;
+      auto writeImg = [&]() { memcpy(&e->lanes[l].ring[seg[l] + 64 + (u64)i * 32], &img, 32); };
+      if (!(r.dst_mask & (1u << l)) || (r.flags & GPX_F_VOID)) {
+        writeImg();
+        continue;
+      }
+      if (!e->usable(r.gid, l)) {
+        e->ctr.decisions_dropped++;
+        writeImg();
+        continue;
+      }
+      Group& g = e->groups[r.gid];
+      Acceptor& A = e->lanes[l].acc[r.gid];
+      if (e->W() > 0 && jsub(r.slot, A._slot) >= e->W()) {
+        A.flags |= GF_OVERFLOW | GF_NEEDS_SYNC;
+        e->ctr.window_overflow++;
+        e->ctr.decisions_dropped++;
+        writeImg();
+        continue;
+      }
+      e->ctr.decisions_handled++;
+      Ballot cb{r.bnum, r.bcoord};
+      PValue d;
+      auto a = A.acceptedProposals.find(r.slot);
+      if (a != A.acceptedProposals.end() && a->second.bal.equals(cb)) { /* :1488 */
+        d = a->second;
+        d.median_cp = r.median_cp;
+        d.has_value = true;
+      } else { /* placeholder :1514-1522 */
+        d = PValue();
+        d.slot = r.slot;
+        d.bal = cb;
+        d.median_cp = r.median_cp;
+        d.has_value = false;
+        e->ctr.placeholders++;
+      }
+      if (e->decisionLogImage(A, r.gid, l, d, &img)) { /* logDecision :1446-1466 */
+      }
+      writeImg();
+      std::vector<PValue> xs;
+      e->EEC(A, d, xs);
+      for (size_t k = 0; k < xs.size(); k++) {
+        if (k == 0)
+          ex = e->makeExec(r.gid, l, g, xs[k], false);
+        else
+          extras.push_back(e->makeExec(r.gid, l, g, xs[k], true));
+        if (e->shouldCheckpoint(g, xs[k])) e->ctr.checkpoints_due++;
+      }
+      if (!A.isStopped() && !d.has_value && jsub(d.slot, A._slot) >= 0 && xs.empty()) A.flags |= GF_NEEDS_SYNC;
+    }
+  }
+  u32 ne = 0;
+  for (auto& x : extras)
+    if (ne < extra_cap) out_extra_exec[ne++] = x;
+  if (n_extra) *n_extra = (u32)extras.size();
+  return GPX_OK;
+}
+
+/* one full round for co-located replicas (PaxosManager.send routing :2098-2128) */
+int gpxo_round(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+               uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
+               gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  u32 L = e->L();
+  std::vector<gpx_accept_rec> acc(n);
+  std::vector<uint8_t> blob(payload_bytes + 32ull * n + 64);
+  u32 na = 0;
+  u64 bb = 0;
+  int rc = gpxo_propose(e, n, reqs, payload, payload_bytes, acc.data(), &na, blob.data(), blob.size(), &bb, status);
+  if (rc) return rc;
+  std::vector<gpx_accept_reply_rec> rep((size_t)na * L + 1);
+  u32 nx1 = 0, nx2 = 0;
+  rc = gpxo_handle_accepts(e, na, acc.data(), blob.data(), bb, rep.data(), out_extra_exec, extra_cap, &nx1);
+  if (rc) return rc;
+  std::vector<gpx_decision_rec> dec((size_t)na * L + 1);
+  u32 nd = 0;
+  rc = gpxo_handle_accept_replies(e, na * L, rep.data(), dec.data(), &nd);
+  if (rc) return rc;
+  u32 used = nx1 < extra_cap ? nx1 : extra_cap;
+  rc = gpxo_handle_decisions(e, nd, dec.data(), out_exec, out_extra_exec + used, extra_cap - used, &nx2);
+  if (rc) return rc;
+  *n_exec_slots = nd * L;
+  if (n_extra) *n_extra = nx1 + nx2;
+  return GPX_OK;
+}
+
+int gpxo_log_read(gpxo_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_t cap, uint64_t* n_copied,
+                  uint64_t* head) {
+  if (lane >= e->L()) return GPX_ERANGE;
+  const std::vector<uint8_t>& r = e->lanes[lane].ring;
+  u64 h = r.size();
+  u64 nb = from < h ? std::min<u64>(cap, h - from) : 0;
+  if (nb) memcpy(dst, r.data() + from, nb);
+  if (n_copied) *n_copied = nb;
+  if (head) *head = h;
+  return GPX_OK;
+}
+
+int gpxo_get_counters(gpxo_engine* e, gpx_counters* out) {
+  *out = e->ctr;
+  return GPX_OK;
+}
+int gpxo_reset_counters(gpxo_engine* e) {
+  memset(&e->ctr, 0, sizeof e->ctr);
+  return GPX_OK;
+}
+/* group flags (GF_*) of one lane, for the host slow-path list */
+int gpxo_get_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out) {
+  if (lane >= e->L()) return GPX_ERANGE;
+  for (u32 k = 0; k < n; k++) out[k] = gids[k] < e->cfg.max_groups ? e->lanes[lane].acc[gids[k]].flags : 0;
+  return GPX_OK;
+}
+
+int32_t gpxo_java_string_hash(const char* s, size_t len) { return javaStringHash(s, len); }
+int32_t gpxo_round_robin_coordinator(int32_t name_hash, const int32_t* sorted_members, int32_t n, int32_t ballotnum) {
+  return roundRobinCoordinator(name_hash, sorted_members, n, ballotnum);
+}
+int32_t gpxo_get_cpi(int32_t cpi, double noise, int32_t name_hash) { return getCPI(cpi, noise, name_hash); }
+int32_t gpxo_last_checkpoint_slot(int32_t slot, int32_t cpi) { return lastCheckpointSlot(slot, cpi); }
+void gpxo_md5(const uint8_t* msg, size_t len, uint8_t out[16]) { md5(msg, len, out); }
+
+/* HotRestoreInfo string round trip: parse `in`, re-serialise into out (cap bytes) */
+int gpxo_hri_roundtrip(const char* in, char* out, size_t cap) {
+  HotRestoreInfo h = HotRestoreInfo::parse(in);
+  std::string s = h.toString();
+  if (s.size() + 1 > cap) return GPX_ERANGE;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return GPX_OK;
+}
+int gpxo_hri_from_row(const char* paxosID, const gpx_row* r, char* out, size_t cap) {
+  HotRestoreInfo h;
+  h.paxosID = paxosID;
+  h.version = r->version;
+  h.members.assign(r->members, r->members + r->n_members);
+  h.accSlot = r->acc_slot;
+  h.accBallot = Ballot{r->acc_bnum, r->acc_bcoord};
+  h.accGCSlot = r->acc_gc_slot;
+  h.hasCoord = r->coord_exists != 0;
+  h.coordBallot = Ballot{r->coord_bnum, r->coord_bcoord};
+  h.nextProposalSlot = r->next_proposal_slot;
+  h.hasNodeSlots = r->coord_exists != 0;
+  h.nodeSlots.assign(r->node_slots, r->node_slots + r->n_members);
+  std::string s = h.toString();
+  if (s.size() + 1 > cap) return GPX_ERANGE;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return GPX_OK;
+}
+
+/* ------------------------------------------------------------------------------
+ * Self-tests: transliterations of the reference's own main()/JUnit tests.
+ * Returns 0 on success, else the number of the failing check (message in last_error).
+ * ---------------------------------------------------------------------------- */
+static u64 g_rng = 0x9E3779B97F4A7C15ull;
+static u64 splitmix() {
+  u64 z = (g_rng += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static double rnd() { return (double)(splitmix() >> 11) / (double)(1ull << 53); }
+
+#define CHECK(n, cond)                                      \
+  do {                                                      \
+    if (!(cond)) {                                          \
+      g_err = std::string("selftest check failed: ") + #cond; \
+      return (n);                                           \
+    }                                                       \
+  } while (0)
+
+int gpxo_selftest(uint64_t seed) {
+  g_rng = seed ? seed : 1;
+  /* 1. Ballot: PaxosPacketBatcher.main :556-567 + compareTo wraparound */
+  {
+    Ballot b1{43, 578}, b2{43, 578};
+    CHECK(1, b1.equals(b2));
+    CHECK(2, b1.hashCode() == b2.hashCode());
+    CHECK(3, (Ballot{1, 0}).compareTo(Ballot{0, 5}) > 0);
+    CHECK(4, (Ballot{0, 2}).compareTo(Ballot{0, 1}) > 0);
+    CHECK(5, (Ballot{INT32_MIN, 0}).compareTo(Ballot{INT32_MAX, 0}) > 0); /* wraparound :62-63 */
+  }
+  /* 2. WaitforUtility.main :147-163 */
+  {
+    WaitforUtility w(std::vector<i32>{0, 9, 4, 23});
+    CHECK(10, !w.contains(32));
+    CHECK(11, w.contains(9));
+    CHECK(12, w.getIndex(4) == 2);
+    CHECK(13, w.updateHeardFrom(9));
+    CHECK(14, !w.heardFromMajority());
+    CHECK(15, w.updateHeardFrom(23));
+    CHECK(16, !w.heardFromMajority());
+    CHECK(17, w.updateHeardFrom(0));
+    CHECK(18, w.heardFromMajority());
+    CHECK(19, !w.updateHeardFrom(0)); /* idempotent */
+  }
+  /* 3. PaxosAcceptor.testAcceptor :749-776 (100k random accepts, then 100k random prepares) */
+  {
+    Acceptor acceptor;
+    acceptor.ballotNum = 22;
+    acceptor.ballotCoord = 1;
+    acceptor._slot = 7;
+    acceptor.state = ST_ACTIVE_1;
+    const int numTests = 100000;
+    for (int i = 0; i < numTests; i++) {
+      PValue accept;
+      accept.slot = (i32)(rnd() * INT32_MAX); /* getRandomAccept :728-738 */
+      accept.bal = Ballot{(i32)(rnd() * INT32_MAX), (i32)(rnd() * INT32_MAX)};
+      accept.req_id = (i64)splitmix();
+      accept.has_value = true;
+      accept.median_cp = 0;
+      Ballot before = acceptor.getBallot(), response;
+      CHECK(30, acceptor.acceptAndUpdateBallot(accept, &response));
+      CHECK(31, response.compareTo(accept.bal) >= 0);
+      CHECK(32, response.compareTo(before) >= 0);
+    }
+    for (int i = 0; i < numTests; i++) {
+      Ballot pb{(i32)(rnd() * INT32_MAX), (i32)(rnd() * INT32_MAX)};
+      Ballot before = acceptor.getBallot();
+      acceptor.bumpBallot(pb); /* handlePrepare :239-251 */
+      CHECK(33, acceptor.getBallot().compareTo(pb) >= 0);
+      CHECK(34, acceptor.getBallot().compareTo(before) >= 0);
+    }
+  }
+  /* 4. PaxosCoordinatorState.main, phase-2 half :1179-1214 (43 members, random preemption) */
+  {
+    const int numMembers = 43;
+    std::vector<i32> members(numMembers);
+    members[0] = 21;
+    for (int i = 1; i < numMembers; i++) members[i] = members[i - 1] + 1 + (int)(rnd() * 10);
+    Coordinator pcs;
+    pcs.create(2, 21, 0, numMembers, true);
+    pcs.active = true;
+    for (int i = 0; i < 100; i++) {
+      PValue req, acc;
+      req.req_id = (i64)splitmix();
+      req.has_value = true;
+      CHECK(40, pcs.propose(members, req, &acc) == 0);
+      CHECK(41, acc.slot == i && acc.bal.num == 2 && acc.bal.coord == 21);
+    }
+    std::vector<i32> slots;
+    for (auto& kv : pcs.myProposals) slots.push_back(kv.first);
+    for (i32 s : slots) {
+      CHECK(42, !pcs.preemptedFully());
+      for (int j = 0; j < numMembers; j++) {
+        PValue out;
+        if (rnd() > 0.99) { /* a single member's higher-ballot reply preempts */
+          int t = pcs.handleAcceptReplyHigherBallot(s, &out);
+          CHECK(43, t == PT_NONE || t == PT_PREEMPTED);
+          if (t == PT_PREEMPTED) CHECK(44, !pcs.myProposals.count(out.slot));
+        } else {
+          bool present = pcs.myProposals.count(s) != 0;
+          int heardBefore = present ? pcs.myProposals[s].waitfor.heardCount : 0;
+          int t = pcs.handleAcceptReplyMyBallot(members, members[j], s, -1, &out);
+          CHECK(45, t == PT_NONE || t == PT_DECISION);
+          if (t == PT_DECISION) {
+            CHECK(46, !pcs.myProposals.count(out.slot));
+            CHECK(47, heardBefore + 1 > numMembers / 2); /* decisions only on majority */
+          }
+        }
+      }
+    }
+    CHECK(48, pcs.myProposals.empty());
+  }
+  /* 5. HotRestoreInfoTest.testToStringAndBack paxosutil/HotRestoreInfo.java:159-175 (literal values) */
+  {
+    HotRestoreInfo h;
+    h.paxosID = "paxos0";
+    h.version = 2;
+    h.members = {1, 4, 67};
+    h.accSlot = 5;
+    h.accBallot = Ballot{3, 4};
+    h.accGCSlot = 3;
+    h.hasCoord = true;
+    h.coordBallot = Ballot{45, 67};
+    h.nextProposalSlot = 34;
+    h.hasNodeSlots = true;
+    h.nodeSlots = {1, 3, 5};
+    std::string s1 = h.toString();
+    CHECK(50, s1 == "paxos0|2|[1, 4, 67]|5|3:4|3|45:67|34|[1, 3, 5]");
+    CHECK(51, HotRestoreInfo::parse(s1).toString() == s1);
+  }
+  /* 6. medianMinus :867-875, roundRobinCoordinator :2251-2256, String.hashCode */
+  {
+    Coordinator c;
+    c.create(0, 1, 1, 3, true);
+    c.nodeSlotNumbers = {5, 1, 3};
+    CHECK(60, c.getMajorityCommittedSlot() == 3);
+    c.nodeSlotNumbers = {5, 1, 3, 9};
+    CHECK(61, c.getMajorityCommittedSlot() == 3); /* even: index n/2-1 */
+    CHECK(62, javaStringHash("paxos0", 6) == -995235643);
+    CHECK(63, javaStringHash("", 0) == 0);
+    i32 m[3] = {100, 101, 102};
+    CHECK(64, roundRobinCoordinator(javaStringHash("paxos0", 6), m, 3, 0) == m[995235643 % 3]);
+    CHECK(65, getCPI(400, 0.0, 12345) == 400);
+    CHECK(66, lastCheckpointSlot(805, 400) == 800);
+  }
+  /* 7. MD5: RFC 1321 appendix A.5 test suite */
+  {
+    struct { const char* in; const char* hex; } v[] = {
+        {"", "d41d8cd98f00b204e9800998ecf8427e"},
+        {"a", "0cc175b9c0f1b6a831c399e269772661"},
+        {"abc", "900150983cd24fb0d6963f7d28e17f72"},
+        {"message digest", "f96b697d7cb7938d525a2f31aaf161d0"},
+        {"abcdefghijklmnopqrstuvwxyz", "c3fcd3d76192e4007dfb496cca67e13b"},
+        {"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789", "d174ab98d277d9f5a5611c2c9f419d9f"},
+        {"12345678901234567890123456789012345678901234567890123456789012345678901234567890",
+         "57edf4a22be3c955ac49da2e2107b67a"}};
+    for (auto& t : v) {
+      uint8_t d[16];
+      md5((const uint8_t*)t.in, strlen(t.in), d);
+      char hex[33];
+      for (int i = 0; i < 16; i++) snprintf(hex + 2 * i, 3, "%02x", d[i]);
+      CHECK(70, std::string(hex) == t.hex);
+    }
+  }
+  return 0;
+}
+
+} /* extern "C" */
