@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- Paxos decisions/sec of the B200 engine on BASELINE.json's metric.
+
+A *step* is one full Paxos round over every group of the workload: one client request per
+group enters the RequestBatcher, the coordinator proposes (k_propose), all R co-located
+replicas accept + log (k_accept), the coordinator tallies the replies (k_tally) and all
+replicas commit + emit in-order EXEC records (k_commit).  One step decides one slot per group.
+
+  value  : decisions/s with the request batch already resident in HBM (gpx_round_device)
+  e2e    : the same metric through the public C-ABI call gpx_round with HOST buffers
+           (pinned), H2D of the requests and D2H of status + EXEC records inside the timing
+  roofline: accept-batch kernel, algorithmic bytes (193+2P per ACCEPT at one acceptor,
+           SURVEY.md 8d) / CUDA-event duration, vs the measured HBM copy peak
+  cpu_baseline: the CPU oracle (a port of the Java path, reference JVM unavailable) on the
+           host cores, groups sharded over threads
+
+`--impl reference` times that CPU port alone with all host threads (the reference is
+Java-only and no JVM exists in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg2": dict(name="3-replica, 100K groups, 1-byte NoopApp requests, single B200", G=100_000, R=3, P=1),
+    "cfg3": dict(name="3-replica, 1M groups, 64-byte requests (per-GPU shard of BASELINE config 3)", G=1_000_000, R=3,
+                 P=64),
+    "1m1b": dict(name="3-replica, 1M groups, 1-byte requests, single B200 (north_star target size)", G=1_000_000,
+                 R=3, P=1),
+}
+NODES = (100, 101, 102, 103, 104)
+
+
+def b_acc(P: int) -> int:
+    """Algorithmic bytes per ACCEPT at one acceptor (SURVEY.md 8d / BASELINE.md 3)."""
+    return 193 + 2 * P
+
+
+def b_slot(R: int, P: int) -> int:
+    return R * (193 + 2 * P) + R * (64 + 8 * R) + 32 + R * 153
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def java_hash(s: str) -> int:
+    h = 0
+    for ch in s:
+        h = (31 * h + ord(ch)) & 0xFFFFFFFF
+    return h - (1 << 32) if h >= (1 << 31) else h
+
+
+def shard_names(G: int, rank: int, world: int, prefix="NoopPaxosApp"):
+    """Groups of this rank: home_gpu(name) = |String.hashCode(name)| mod world."""
+    names = []
+    i = 0
+    while len(names) < G:
+        s = f"{prefix}{i}"
+        if world == 1 or abs(java_hash(s)) % world == rank:
+            names.append(s)
+        i += 1
+    return names
+
+
+def make_descs(abi, names, R):
+    d = np.zeros(len(names), dtype=abi.group_desc_dtype)
+    d["gid"] = np.arange(len(names), dtype=np.uint32)
+    d["name_hash"] = [java_hash(s) for s in names]
+    d["n_members"] = R
+    for i in range(R):
+        d["members"][:, i] = NODES[i]
+    d["init_mode"] = abi.INIT_BATCH  # TESTPaxosNode uses batch creation for NUM_GROUPS > 10000
+    return d
+
+
+def make_batch(abi, G, P, seed):
+    rng = np.random.default_rng(seed)
+    stride = (P + 15) // 16 * 16
+    reqs = np.zeros(G, dtype=abi.request_dtype)
+    reqs["gid"] = np.arange(G, dtype=np.uint32)
+    reqs["flags"] = 0
+    reqs["req_id"] = rng.integers(1, 1 << 62, size=G, dtype=np.int64)
+    reqs["payload_off"] = np.arange(G, dtype=np.uint32) * stride
+    reqs["payload_len"] = P
+    reqs["entry_node"] = NODES[0]
+    reqs["client"] = np.arange(G, dtype=np.uint32)
+    alphabet = np.frombuffer(b"0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz", dtype=np.uint8)
+    pay = np.zeros((G, stride), dtype=np.uint8)
+    pay[:, :P] = alphabet[rng.integers(0, 62, size=(G, P))]
+    return reqs, pay.reshape(-1)
+
+
+def engine_config(lib, G, R, P, device):
+    cfg = lib.config_defaults()
+    cfg.device = device
+    cfg.max_groups = G
+    cfg.n_lanes = R
+    for i in range(R):
+        cfg.lane_node[i] = NODES[i]
+    cfg.window = 8
+    cfg.max_group_size = R
+    cfg.max_batch_recs = G
+    stride = (P + 15) // 16 * 16
+    cfg.max_batch_payload = G * stride
+    per_round = 64 + 48 * G + G * stride + 64 + 32 * G
+    ring = 1 << 26
+    while ring < 4 * per_round:
+        ring <<= 1
+    cfg.log_ring_bytes = ring
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="gpx_clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                t = [x.strip() for x in line.split(",")]
+                if len(t) < 9:
+                    continue
+                try:
+                    sm.append(float(t[1]))
+                    mx.append(float(t[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   t[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the Java path) with groups sharded over host threads
+# --------------------------------------------------------------------------------------------
+def cpu_decisions_per_sec(G, R, P, budget_s, threads):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_library
+    from gigapaxos_b200 import abi
+    from gigapaxos_b200.abi import Engine
+
+    lib = oracle_library()
+    T = max(1, min(threads, G))
+    per = [G // T + (1 if i < G % T else 0) for i in range(T)]
+    engines, batches = [], []
+    for t in range(T):
+        cfg = engine_config(lib, per[t], R, P, 0)
+        cfg.log_ring_bytes = 1 << 20
+        e = Engine(lib, cfg)
+        e.create_groups(make_descs(abi, [f"NoopPaxosApp{t}_{i}" for i in range(per[t])], R))
+        engines.append(e)
+        batches.append(make_batch(abi, per[t], P, 100 + t))
+
+    fn = lib.fn("round")
+
+    class Worker:
+        def __init__(self, e, batch):
+            self.e = e
+            self.reqs, self.pay = batch
+            n = len(self.reqs)
+            self.status = np.zeros(n, np.int32)
+            self.ex = np.zeros(n * R, abi.exec_dtype)
+            self.extra = np.zeros(16, abi.exec_dtype)
+
+        def round(self):
+            n = len(self.reqs)
+            ns, nx = C.c_uint32(0), C.c_uint32(0)
+            rc = fn(self.e.handle, C.c_uint32(n), self.reqs.ctypes.data_as(C.c_void_p),
+                    self.pay.ctypes.data_as(C.c_void_p), C.c_uint64(self.pay.size),
+                    self.status.ctypes.data_as(C.c_void_p), self.ex.ctypes.data_as(C.c_void_p), C.byref(ns),
+                    self.extra.ctypes.data_as(C.c_void_p), C.c_uint32(16), C.byref(nx))
+            assert rc == 0 and ns.value == n * R
+
+    workers = [Worker(e, b) for e, b in zip(engines, batches)]
+
+    def run_rounds(k):
+        def body(w):
+            for _ in range(k):
+                w.round()
+        ts = [threading.Thread(target=body, args=(w,)) for w in workers]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    run_rounds(1)  # warm-up (page faults, allocator)
+    t1 = run_rounds(1)
+    k = int(max(1, min(200, budget_s / max(t1, 1e-6))))
+    # the oracle's log is an ever-growing vector: bound the rounds so memory stays small
+    k = min(k, max(1, int(2e9 / max(1, G * (48 + 16 + 32) * R))))
+    dt = run_rounds(k)
+    for e in engines:
+        e.close()
+    return G * k / dt, k, dt, T
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--groups", type=int, default=0, help="override groups per GPU")
+    ap.add_argument("--payload", type=int, default=0, help="override request payload bytes")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+
+    wl = dict(WORKLOADS[args.workload])
+    if args.groups:
+        wl["G"] = args.groups
+    if args.payload:
+        wl["P"] = args.payload
+    G, R, P = wl["G"], wl["R"], wl["P"]
+    K, W = args.steps, max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "paxos_decisions_per_sec"
+    config = {
+        "workload": wl["name"], "groups_per_gpu": G, "replicas": R, "payload_bytes": P, "window": 8,
+        "requests_per_group_per_step": 1,
+        "placement": "packed: all R replicas of a group on the GPU that owns the group; groups sharded by "
+                     "|String.hashCode(paxosID)| mod n_gpus; no data-path collective",
+        "l2": "none" if args.no_flush else "flushed between timed steps (256 MiB write, outside the timed events)",
+        "init": "batch creation (HotRestoreInfo.createHRI)",
+    }
+
+    if args.impl == "reference":
+        # The reference is Java-only and this image has no JVM: the CPU arm is the oracle port.
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        v, k, dt, T = cpu_decisions_per_sec(G, R, P, max(5.0, min(60.0, 0.5 * (K + W))), threads)
+        line = {
+            "impl": "reference", "metric": metric, "value": v, "unit": "decisions/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": "decisions/s", "cores": T, "kind": "port",
+                             "sample": f"{k} full rounds over {G} groups x {R} replicas (oracle = C++ port of the "
+                                       f"Java path; reference JVM unavailable in this image), {dt:.1f} s"},
+            "e2e": {"value": v, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import gigapaxos_b200
+    from gigapaxos_b200 import abi
+    from gigapaxos_b200.abi import DevRoundBufs, Engine, KernelTimes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the gpx engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    lib = gigapaxos_b200.load_library()
+    eng = Engine(lib, engine_config(lib, G, R, P, local_rank))
+    names = shard_names(G, rank, world)
+    eng.create_groups(make_descs(abi, names, R))
+
+    NB = 4  # distinct synthetic request batches, cycled
+    host_batches = [make_batch(abi, G, P, 1000 * rank + b) for b in range(NB)]
+    d_reqs = [torch.from_numpy(b[0].view(np.uint8).copy()).to(dev) for b in host_batches]
+    d_pay = [torch.from_numpy(b[1].copy()).to(dev) for b in host_batches]
+    d_status = torch.zeros(G, dtype=torch.int32, device=dev)
+    d_exec = torch.zeros(G * R * 24, dtype=torch.uint8, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    round_dev = lib.fn("round_device")
+
+    def dev_round(b):
+        bufs = DevRoundBufs(d_reqs[b].data_ptr(), d_pay[b].data_ptr(), d_pay[b].numel(), G, d_status.data_ptr(),
+                            d_exec.data_ptr())
+        rc = round_dev(eng.handle, C.byref(bufs), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(lib.last_error())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident rounds ------------------------------------------------
+    for w in range(max(W, 3)):
+        dev_round(w % NB)
+    c0 = eng.counters()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        if not args.no_flush:
+            flush_buf.zero_()
+        ev_s[k].record()
+        dev_round(k % NB)
+        ev_e[k].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = np.array([ev_s[k].elapsed_time(ev_e[k]) for k in range(K)])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    c1 = eng.counters()
+    decided = c1["decisions_made"] - c0["decisions_made"]
+    assert decided == G * K, f"expected {G * K} decisions in the timed region, engine made {decided}"
+    assert c1["executed"] - c0["executed"] == G * K * R
+    value = world * G * K / (total_ms / 1e3)
+
+    # ---- roofline: per-kernel CUDA events inside the engine (same launches, same stream) ----
+    lib.fn("enable_kernel_timing")(eng.handle, C.c_int(1))
+    kt = KernelTimes()
+    lib.fn("get_kernel_times")(eng.handle, C.byref(kt), C.c_int(1))
+    K2 = min(K, 20)
+    for k in range(K2):
+        if not args.no_flush:
+            flush_buf.zero_()
+        dev_round(k % NB)
+    torch.cuda.synchronize()
+    lib.fn("get_kernel_times")(eng.handle, C.byref(kt), C.c_int(1))
+    lib.fn("enable_kernel_timing")(eng.handle, C.c_int(0))
+    acc_ms = kt.accept_ms / max(kt.launches, 1)
+    peak, peak_src = hbm_peak()
+    alg_bytes = G * R * b_acc(P)
+    achieved = alg_bytes / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else 0.0
+    roofline = {
+        "kernel": "k_accept (accept-batch: handleAccept at R acceptors + log append)", "bound": "hbm",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_accept": b_acc(P),
+        "accepts_per_launch": G * R, "kernel_ms": acc_ms,
+        "kernel_ms_all": {"propose": kt.propose_ms / max(kt.launches, 1), "accept": acc_ms,
+                          "tally": kt.tally_ms / max(kt.launches, 1), "commit": kt.commit_ms / max(kt.launches, 1)},
+        "round_frac": (G * b_slot(R, P) / (float(np.median(step_ms)) / 1e3) / 1e9) / peak,
+    }
+
+    # ---- e2e: public C-ABI call with host (pinned) buffers ---------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        fn = lib.fn("round")
+        h_reqs = [torch.from_numpy(b[0].view(np.uint8).copy()).pin_memory() for b in host_batches]
+        h_pay = [torch.from_numpy(b[1].copy()).pin_memory() for b in host_batches]
+        h_status = torch.zeros(G, dtype=torch.int32).pin_memory()
+        h_exec = torch.zeros(G * R * 24, dtype=torch.uint8).pin_memory()
+        h_extra = torch.zeros(64 * 24, dtype=torch.uint8).pin_memory()
+        ns, nx = C.c_uint32(0), C.c_uint32(0)
+
+        def host_round(b):
+            rc = fn(eng.handle, C.c_uint32(G), C.c_void_p(h_reqs[b].data_ptr()), C.c_void_p(h_pay[b].data_ptr()),
+                    C.c_uint64(h_pay[b].numel()), C.c_void_p(h_status.data_ptr()), C.c_void_p(h_exec.data_ptr()),
+                    C.byref(ns), C.c_void_p(h_extra.data_ptr()), C.c_uint32(64), C.byref(nx))
+            if rc != 0:
+                raise RuntimeError(lib.last_error())
+
+        for w in range(3):
+            host_round(w % NB)
+        K3 = min(K, 30)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K3):
+            host_round(k % NB)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert ns.value == G * R
+        ex = h_exec.numpy().view(abi.exec_dtype)
+        assert int((ex["flags"] & abi.F_VOID).sum()) == 0, "e2e round left VOID exec records"
+        e2e = {"value": world * G * K3 / dt, "unit": "decisions/s",
+               "h2d_bytes_per_step": int(G * 32 + h_pay[0].numel()),
+               "d2h_bytes_per_step": int(G * 4 + 32 + G * R * 24), "steps": K3,
+               "ms_per_step": 1e3 * dt / K3,
+               "api": "gpx_round (include/gpx.h): pinned host request/payload buffers in, status + EXEC records out"}
+
+    # ---- cpu baseline (rank 0, N=1 only) --------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        v, k, dt, T = cpu_decisions_per_sec(G, R, P, args.cpu_budget, threads)
+        cpu = {"value": v, "unit": "decisions/s", "cores": T, "kind": "port",
+               "sample": f"{k} full rounds over the same {G} groups x {R} replicas, oracle (C++ port of the Java "
+                         f"path; no JVM in this image) sharded over {T} threads, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": config, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 5 * K,
+            "p50_decide_latency_ms": float(np.median(step_ms)),
+            "requests_per_sec": value, "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,332 @@
+"""ctypes / numpy mirror of include/gpx.h (the C ABI of the engine).
+
+Everything here is plumbing: record dtypes, the config/row structs and a thin `Engine`
+wrapper whose methods are 1:1 with the C entry points.  The library path and symbol
+prefix are parameters so that the test-suite can drive its CPU checker (own prefix)
+through the very same wrapper; nothing in this package ever loads the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+GPX_ABI_VERSION = 1
+GPX_MAX_GROUP_SIZE = 16
+GPX_MAX_LANES = 8
+GPX_MAX_WINDOW = 8
+
+# return codes
+GPX_OK, GPX_EINVAL, GPX_ENOMEM, GPX_ECUDA, GPX_ENOGPU, GPX_ERANGE, GPX_EIO = 0, -1, -2, -3, -4, -5, -6
+# PaxosAcceptor.STATES ordinals
+ST_RECOVERY, ST_ACTIVE_1, ST_ACTIVE_2, ST_STOPPED, ST_FREE = 0, 1, 2, 3, 255
+# record flags
+F_STOP, F_VOID, F_ACCEPT, F_DECISION, F_META, F_CKPT, F_LOGGED, F_NACK, F_EXTRA = (
+    0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80, 0x100)
+# request status codes
+RS_BATCHED, RS_FORWARD, RS_REFUSED_STOP, RS_BACKPRESSURE, RS_DROPPED, RS_PREACTIVE, RS_NOCOORD = (
+    -1, -2, -3, -4, -5, -6, -7)
+INIT_BATCH, INIT_DEFAULT = 0, 1
+PATCH_SET_BALLOT, PATCH_JUMP_SLOT, PATCH_SET_STATE, PATCH_INSTALL_COORD, PATCH_RESIGN_COORD, PATCH_SET_GC = (
+    1, 2, 3, 4, 5, 6)
+SEG_MAGIC = 0x53585047
+
+request_dtype = np.dtype([("gid", "<u4"), ("flags", "<u4"), ("req_id", "<i8"), ("payload_off", "<u4"),
+                          ("payload_len", "<u4"), ("entry_node", "<i4"), ("client", "<u4")])
+pvalue_fields = [("gid", "<u4"), ("slot", "<i4"), ("bnum", "<i4"), ("bcoord", "<i4"), ("median_cp", "<i4"),
+                 ("flags", "<u2"), ("dst_mask", "<u2"), ("req_id", "<i8")]
+decision_dtype = np.dtype(pvalue_fields)
+accept_dtype = np.dtype(pvalue_fields + [("payload_off", "<u4"), ("payload_len", "<u4"), ("nreq", "<u4"),
+                                         ("sender", "<i4")])
+reply_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("bnum", "<i4"), ("bcoord", "<i4"), ("max_cp", "<i4"),
+                        ("who", "<u4"), ("req_id", "<i8")])
+exec_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("req_id", "<i8"), ("payload_off", "<u4"), ("flags", "<u4")])
+batch_ent_dtype = np.dtype([("req_id", "<i8"), ("len", "<u4"), ("flags", "<u4")])
+seg_hdr_dtype = np.dtype([("magic", "<u4"), ("type", "<u2"), ("lane", "<u2"), ("n_slots", "<u4"), ("n_valid", "<u4"),
+                          ("payload_bytes", "<u8"), ("seq", "<u8"), ("ring_off", "<u8"), ("rec_bytes", "<u4"),
+                          ("reserved", "<u4", (5,))])
+row_dtype = np.dtype([("gid", "<u4"), ("lane", "<u4"), ("version", "<i4"), ("acc_slot", "<i4"), ("acc_bnum", "<i4"),
+                      ("acc_bcoord", "<i4"), ("acc_gc_slot", "<i4"), ("state", "<i4"), ("coord_exists", "<i4"),
+                      ("coord_active", "<i4"), ("coord_bnum", "<i4"), ("coord_bcoord", "<i4"),
+                      ("next_proposal_slot", "<i4"), ("n_members", "<i4"), ("members", "<i4", (16,)),
+                      ("node_slots", "<i4", (16,))])
+group_desc_dtype = np.dtype([("gid", "<u4"), ("version", "<i4"), ("name_hash", "<i4"), ("n_members", "<i4"),
+                             ("members", "<i4", (16,)), ("init_mode", "<i4")])
+patch_dtype = np.dtype([("gid", "<u4"), ("lane", "<u4"), ("op", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"),
+                        ("d", "<i4"), ("reserved", "<i4")])
+
+assert request_dtype.itemsize == 32 and decision_dtype.itemsize == 32 and accept_dtype.itemsize == 48
+assert reply_dtype.itemsize == 32 and exec_dtype.itemsize == 24 and seg_hdr_dtype.itemsize == 64
+assert row_dtype.itemsize == 56 + 128 and group_desc_dtype.itemsize == 84 and patch_dtype.itemsize == 32
+
+COUNTER_NAMES = ["accepts_handled", "accepts_acked", "accepts_nacked", "accepts_logged", "accepts_dropped",
+                 "replies_handled", "replies_ignored", "preempted", "coordinators_resigned", "decisions_made",
+                 "decisions_handled", "decisions_dropped", "placeholders", "executed", "stops_executed",
+                 "checkpoints_due", "proposals", "requests_batched", "requests_rejected", "window_overflow",
+                 "kernel_launches"]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("device", C.c_int32), ("max_groups", C.c_uint32), ("n_lanes", C.c_uint32),
+        ("lane_node", C.c_int32 * GPX_MAX_LANES), ("window", C.c_uint32), ("max_group_size", C.c_uint32),
+        ("log_ring_bytes", C.c_uint64), ("max_batch_recs", C.c_uint32), ("max_batch_payload", C.c_uint64),
+        ("batching_enabled", C.c_int32), ("max_batch_size", C.c_int32), ("max_batch_bytes", C.c_int64),
+        ("request_size_estimate", C.c_int32), ("checkpoint_interval", C.c_int32), ("cpi_noise", C.c_double),
+        ("gc_majority_executed", C.c_int32), ("log_meta_decisions", C.c_int32), ("journaling_enabled", C.c_int32),
+        ("batched_accept_replies", C.c_int32), ("batched_commits", C.c_int32), ("short_circuit_local", C.c_int32),
+        ("min_pp_batch_size", C.c_int32), ("digest_requests", C.c_int32), ("reserved", C.c_int32 * 8),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in COUNTER_NAMES] + [("reserved", C.c_uint64 * 7)]
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [("propose_ms", C.c_double), ("accept_ms", C.c_double), ("tally_ms", C.c_double),
+                ("commit_ms", C.c_double), ("launches", C.c_uint64)]
+
+
+class DevRoundBufs(C.Structure):
+    _fields_ = [("reqs", C.c_void_p), ("payload", C.c_void_p), ("payload_bytes", C.c_uint64), ("n", C.c_uint32),
+                ("status", C.c_void_p), ("exec", C.c_void_p)]
+
+
+class GpxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gpx error {code}: {msg}")
+        self.code = code
+
+
+def who(acc_idx: int, dst_idx: int, flags: int = 0) -> int:
+    return (acc_idx & 0xFF) | ((dst_idx & 0xFF) << 8) | ((flags & 0xFFFF) << 16)
+
+
+def who_acc(w):
+    return w & 0xFF
+
+
+def who_dst(w):
+    return (w >> 8) & 0xFF
+
+
+def who_flags(w):
+    return w >> 16
+
+
+def java_string_hash(s: str) -> int:
+    """java.lang.String.hashCode() for ISO-8859-1 / BMP strings."""
+    h = 0
+    for ch in s:
+        h = (31 * h + ord(ch)) & 0xFFFFFFFF
+    return h - (1 << 32) if h >= (1 << 31) else h
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Library:
+    """A loaded C-ABI library (CUDA engine or, in tests, the oracle) with a symbol prefix."""
+
+    def __init__(self, path: str, prefix: str = "gpx_"):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build it with `python -m gigapaxos_b200.build` (there is no CPU fallback)")
+        self.path, self.prefix = path, prefix
+        self.lib = C.CDLL(path)
+        self.fn("last_error").restype = C.c_char_p
+        self.fn("build_info").restype = C.c_char_p
+
+    def fn(self, name: str):
+        return getattr(self.lib, self.prefix + name)
+
+    def has(self, name: str) -> bool:
+        return hasattr(self.lib, self.prefix + name)
+
+    def last_error(self) -> str:
+        return (self.fn("last_error")() or b"").decode()
+
+    def build_info(self) -> str:
+        return self.fn("build_info")().decode()
+
+    def config_defaults(self) -> Config:
+        cfg = Config()
+        self.fn("config_defaults")(C.byref(cfg))
+        return cfg
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise GpxError(rc, self.last_error())
+
+
+class Engine:
+    """1:1 wrapper over the gpx_* entry points.  Arrays are numpy structured arrays."""
+
+    def __init__(self, library: Library, cfg: Config):
+        self.L = library
+        self.cfg = cfg
+        self.n_lanes = int(cfg.n_lanes)
+        self._h = C.c_void_p()
+        library.check(library.fn("engine_create")(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self.L.fn("engine_destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ---- groups -------------------------------------------------------------------
+    def create_groups(self, descs: np.ndarray):
+        descs = np.ascontiguousarray(descs, dtype=group_desc_dtype)
+        self.L.check(self.L.fn("create_groups")(self._h, C.c_uint32(len(descs)), _ptr(descs)))
+
+    def destroy_groups(self, gids):
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        self.L.check(self.L.fn("destroy_groups")(self._h, C.c_uint32(len(gids)), _ptr(gids)))
+
+    def dump_rows(self, gids, lane: int) -> np.ndarray:
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        out = np.zeros(len(gids), dtype=row_dtype)
+        self.L.check(self.L.fn("dump_rows")(self._h, C.c_uint32(len(gids)), _ptr(gids), C.c_uint32(lane), _ptr(out)))
+        return out
+
+    def load_rows(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=row_dtype)
+        self.L.check(self.L.fn("load_rows")(self._h, C.c_uint32(len(rows)), _ptr(rows)))
+
+    def patch(self, patches: np.ndarray):
+        patches = np.ascontiguousarray(patches, dtype=patch_dtype)
+        self.L.check(self.L.fn("patch")(self._h, C.c_uint32(len(patches)), _ptr(patches)))
+
+    def group_flags(self, gids, lane: int) -> np.ndarray:
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        out = np.zeros(len(gids), dtype=np.uint8)
+        self.L.check(self.L.fn("get_group_flags")(self._h, C.c_uint32(lane), C.c_uint32(len(gids)), _ptr(gids),
+                                                  _ptr(out)))
+        return out
+
+    # ---- data path ------------------------------------------------------------------
+    def propose(self, reqs: np.ndarray, payload: np.ndarray):
+        reqs = np.ascontiguousarray(reqs, dtype=request_dtype)
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        n = len(reqs)
+        pal = (payload.size + 15) & ~15
+        accepts = np.zeros(max(n, 1), dtype=accept_dtype)
+        blob = np.zeros(2 * pal + 16 * n + 64, dtype=np.uint8)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        na, bb = C.c_uint32(0), C.c_uint64(0)
+        self.L.check(self.L.fn("propose")(self._h, C.c_uint32(n), _ptr(reqs), _ptr(payload),
+                                          C.c_uint64(payload.size), _ptr(accepts), C.byref(na), _ptr(blob),
+                                          C.c_uint64(blob.size), C.byref(bb), _ptr(status)))
+        return accepts[: na.value].copy(), blob[: bb.value].copy(), status[:n].copy()
+
+    def handle_accepts(self, accepts: np.ndarray, blob: np.ndarray, extra_cap: int = 4096):
+        accepts = np.ascontiguousarray(accepts, dtype=accept_dtype)
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        if blob.size & 15:
+            blob = np.concatenate([blob, np.zeros(16 - (blob.size & 15), dtype=np.uint8)])
+        n = len(accepts)
+        replies = np.zeros(max(n * self.n_lanes, 1), dtype=reply_dtype)
+        extra = np.zeros(max(extra_cap, 1), dtype=exec_dtype)
+        nx = C.c_uint32(0)
+        self.L.check(self.L.fn("handle_accepts")(self._h, C.c_uint32(n), _ptr(accepts), _ptr(blob),
+                                                 C.c_uint64(blob.size), _ptr(replies), _ptr(extra),
+                                                 C.c_uint32(extra_cap), C.byref(nx)))
+        return replies[: n * self.n_lanes].copy(), extra[: min(nx.value, extra_cap)].copy()
+
+    def handle_accept_replies(self, replies: np.ndarray) -> np.ndarray:
+        replies = np.ascontiguousarray(replies, dtype=reply_dtype)
+        n = len(replies)
+        dec = np.zeros(max(n, 1), dtype=decision_dtype)
+        nd = C.c_uint32(0)
+        self.L.check(self.L.fn("handle_accept_replies")(self._h, C.c_uint32(n), _ptr(replies), _ptr(dec),
+                                                        C.byref(nd)))
+        return dec[: nd.value].copy()
+
+    def handle_decisions(self, decisions: np.ndarray, extra_cap: int = 4096):
+        decisions = np.ascontiguousarray(decisions, dtype=decision_dtype)
+        n = len(decisions)
+        ex = np.zeros(max(n * self.n_lanes, 1), dtype=exec_dtype)
+        extra = np.zeros(max(extra_cap, 1), dtype=exec_dtype)
+        nx = C.c_uint32(0)
+        self.L.check(self.L.fn("handle_decisions")(self._h, C.c_uint32(n), _ptr(decisions), _ptr(ex), _ptr(extra),
+                                                   C.c_uint32(extra_cap), C.byref(nx)))
+        return ex[: n * self.n_lanes].copy(), extra[: min(nx.value, extra_cap)].copy()
+
+    def round(self, reqs: np.ndarray, payload: np.ndarray, extra_cap: int = 4096):
+        reqs = np.ascontiguousarray(reqs, dtype=request_dtype)
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        n = len(reqs)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        ex = np.zeros(max(n * self.n_lanes, 1), dtype=exec_dtype)
+        extra = np.zeros(max(extra_cap, 1), dtype=exec_dtype)
+        ns, nx = C.c_uint32(0), C.c_uint32(0)
+        self.L.check(self.L.fn("round")(self._h, C.c_uint32(n), _ptr(reqs), _ptr(payload), C.c_uint64(payload.size),
+                                        _ptr(status), _ptr(ex), C.byref(ns), _ptr(extra), C.c_uint32(extra_cap),
+                                        C.byref(nx)))
+        return status[:n].copy(), ex[: ns.value].copy(), extra[: min(nx.value, extra_cap)].copy()
+
+    # ---- log / counters --------------------------------------------------------------
+    def log_head(self, lane: int) -> int:
+        head = C.c_uint64(0)
+        self.L.check(self.L.fn("log_read")(self._h, C.c_uint32(lane), C.c_uint64(0), None, C.c_uint64(0), None,
+                                           C.byref(head)))
+        return head.value
+
+    def log_read(self, lane: int, start: int = 0, nbytes: Optional[int] = None) -> np.ndarray:
+        head = self.log_head(lane)
+        if nbytes is None:
+            nbytes = max(head - start, 0)
+        buf = np.zeros(max(nbytes, 1), dtype=np.uint8)
+        got = C.c_uint64(0)
+        self.L.check(self.L.fn("log_read")(self._h, C.c_uint32(lane), C.c_uint64(start), _ptr(buf),
+                                           C.c_uint64(nbytes), C.byref(got), None))
+        return buf[: got.value]
+
+    def counters(self) -> dict:
+        c = Counters()
+        self.L.check(self.L.fn("get_counters")(self._h, C.byref(c)))
+        return {n: int(getattr(c, n)) for n in COUNTER_NAMES}
+
+    def reset_counters(self):
+        self.L.check(self.L.fn("reset_counters")(self._h))
+
+
+def parse_log(buf: np.ndarray, ring_cap: Optional[int] = None):
+    """Walk the segments of a log ring image.  Yields (hdr, images, payload_area, payload_ring_off)."""
+    out = []
+    off = 0
+    n = buf.size
+    while off + 64 <= n:
+        hdr = buf[off: off + 64].view(seg_hdr_dtype)[0]
+        if int(hdr["magic"]) != SEG_MAGIC:
+            if ring_cap:  # wrap padding: skip to the next ring boundary
+                nxt = (off // ring_cap + 1) * ring_cap
+                if nxt <= off or nxt + 64 > n:
+                    break
+                off = nxt
+                continue
+            break
+        rec = int(hdr["rec_bytes"])
+        ns = int(hdr["n_slots"])
+        pb = int(hdr["payload_bytes"])
+        dt = accept_dtype if rec == 48 else decision_dtype
+        imgs = buf[off + 64: off + 64 + ns * rec].view(dt)[: int(hdr["n_valid"])]
+        pay_off = off + 64 + ns * rec
+        payload = buf[pay_off: pay_off + pb]
+        out.append((hdr, imgs, payload, pay_off))
+        off = pay_off + ((pb + 15) & ~15)
+    return out

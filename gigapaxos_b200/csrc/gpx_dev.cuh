@@ -1,0 +1,321 @@
+/*
+ * gpx_dev.cuh -- HBM state layout and per-record protocol transitions (device side).
+ *
+ * State is structure-of-arrays over a dense group index `gid`, one copy per co-located
+ * replica ("lane").  Window arrays are laid out [lane][w][gid] so that groups advancing
+ * in lockstep touch consecutive 32-byte entries (coalesced), and a straggling group
+ * still costs exactly one 32-byte sector.
+ *
+ *   acc_row   int4  [L][G]      {_slot, ballotNum, ballotCoord, acceptedGCSlot}   PaxosAcceptor.java:94-99
+ *   acc_aux   u32   [L][G]      state | committed-present mask | committed-valued mask | flags
+ *   acc_win   2xint4[L][W][G]   accepted pvalue {slot,bnum,bcoord,frame_ref | reqID,plen,fl}  (acceptedProposals :108)
+ *   com_win   2xint4[L][W][G]   committed decision {bnum,bcoord,medianCP,frame_ref | reqID,plen,fl} (committedRequests :109)
+ *   coord_row int4  [L][G]      {myBallotNum, myBallotCoord, nextProposalSlotNumber, flags|outstanding<<8}
+ *   node_slots i32  [L][R][G]   PaxosCoordinatorState.nodeSlotNumbers
+ *   prop_win  int4  [L][W][G]   proposal {slot, votes|present|stop, reqID}  (myProposals + WaitforUtility bitmask)
+ *   grp_meta  u32   [G]         member-set id | R | live
+ *
+ * All slot / ballot comparisons use Java's wrapping int subtraction (Ballot.java:60-66,
+ * PaxosAcceptor.java:288,315,341,484).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gpx.h"
+
+#define GPX_AUX_STATE(a) ((a) & 0xffu)
+#define GPX_AUX_PRESENT(a) (((a) >> 8) & 0xffu)
+#define GPX_AUX_VALUED(a) (((a) >> 16) & 0xffu)
+#define GPX_AUX_FLAGS(a) ((a) >> 24)
+#define GPX_GF_OVERFLOW 1u
+#define GPX_GF_NEEDS_SYNC 2u
+
+#define GPX_ENT_VALID 1u
+#define GPX_ENT_STOP 2u
+
+#define GPX_CF_EXISTS 1u
+#define GPX_CF_ACTIVE 2u
+
+#define GPX_PV_PRESENT (1u << 16)
+#define GPX_PV_STOP (1u << 17)
+
+#define GPX_META_LIVE (1u << 24)
+
+/* counter indices == field order of gpx_counters */
+enum {
+  C_ACCEPTS_HANDLED = 0,
+  C_ACCEPTS_ACKED,
+  C_ACCEPTS_NACKED,
+  C_ACCEPTS_LOGGED,
+  C_ACCEPTS_DROPPED,
+  C_REPLIES_HANDLED,
+  C_REPLIES_IGNORED,
+  C_PREEMPTED,
+  C_COORD_RESIGNED,
+  C_DECISIONS_MADE,
+  C_DECISIONS_HANDLED,
+  C_DECISIONS_DROPPED,
+  C_PLACEHOLDERS,
+  C_EXECUTED,
+  C_STOPS_EXECUTED,
+  C_CKPTS_DUE,
+  C_PROPOSALS,
+  C_REQS_BATCHED,
+  C_REQS_REJECTED,
+  C_WINDOW_OVERFLOW,
+  C_KERNEL_LAUNCHES,
+  C_NCTR = 24
+};
+
+struct MsetInfo { /* one sorted member set (PISM.groupMembers :205), 96 B */
+  int32_t nodes[GPX_MAX_GROUP_SIZE];
+  uint8_t lane_of_idx[GPX_MAX_GROUP_SIZE]; /* local lane hosting member idx, 0xff if remote */
+  uint8_t idx_of_lane[GPX_MAX_LANES];      /* member idx served by lane, 0xff if lane not a member */
+  uint16_t lane_mask;
+  uint8_t R;
+  uint8_t pad;
+  uint32_t pad2;
+};
+
+struct DevState {
+  uint32_t G, L, W, Rcap;
+  int4* acc_row;
+  uint32_t* acc_aux;
+  int4* acc_win;
+  int4* com_win;
+  int4* coord_row;
+  int32_t* node_slots;
+  int4* prop_win;
+  uint32_t* grp_meta;
+  int32_t* grp_cpi;
+  const MsetInfo* msets;
+  uint8_t* ring[GPX_MAX_LANES];
+  uint64_t ring_cap;
+  unsigned long long* ring_head; /* [L] absolute byte offsets */
+  unsigned long long* seg_seq;   /* [L] */
+  unsigned long long* ctr;       /* [C_NCTR] */
+  unsigned int* tickets;         /* [8] last-block tickets, one per kernel kind */
+  int32_t lane_node[GPX_MAX_LANES];
+  int32_t cpi_const;
+  int32_t cpi_per_group; /* CPI_NOISE != 0 */
+  int32_t gc_majority_executed;
+  int32_t log_meta;
+  int32_t journaling;
+  int32_t batching;
+  int32_t max_batch_size;
+  int32_t size_est;
+  long long max_batch_bytes;
+};
+
+__device__ __forceinline__ int jsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+/* Ballot.compareTo paxosutil/Ballot.java:60-66 */
+__device__ __forceinline__ int bcmp(int an, int ac, int bn, int bc) { return an != bn ? jsub(an, bn) : jsub(ac, bc); }
+
+__device__ __forceinline__ size_t row_idx(const DevState& S, uint32_t l, uint32_t gid) { return (size_t)l * S.G + gid; }
+__device__ __forceinline__ size_t win_idx(const DevState& S, uint32_t l, uint32_t w, uint32_t gid) {
+  return ((size_t)l * S.W + w) * S.G + gid;
+}
+__device__ __forceinline__ size_t ns_idx(const DevState& S, uint32_t l, uint32_t r, uint32_t gid) {
+  return ((size_t)l * S.Rcap + r) * S.G + gid;
+}
+
+__device__ __forceinline__ int4 ldg4(const void* p) { return *reinterpret_cast<const int4*>(p); }
+__device__ __forceinline__ void stg4(void* p, int4 v) { *reinterpret_cast<int4*>(p) = v; }
+/* streaming (read-once) 128-bit load: records and payloads are consumed exactly once */
+__device__ __forceinline__ int4 ld_stream4(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+/* streaming 128-bit store (outputs are read by a later kernel / the host, never by this one) */
+__device__ __forceinline__ void st_stream4(void* p, int4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+/* a pvalue in registers */
+struct DPValue {
+  int slot, bnum, bcoord, median_cp;
+  long long req_id;
+  unsigned frame_ref, plen, fl; /* fl: GPX_ENT_STOP | nreq<<16 */
+  bool valued;
+};
+
+/* segment base of this launch for one lane: skip to the ring start if it would wrap */
+__device__ __forceinline__ unsigned long long seg_base(const DevState& S, uint32_t l, unsigned long long reserved) {
+  unsigned long long head = S.ring_head[l];
+  unsigned long long pos = head & (S.ring_cap - 1);
+  if (pos + reserved > S.ring_cap) head += S.ring_cap - pos;
+  return head;
+}
+__device__ __forceinline__ uint8_t* ring_ptr(const DevState& S, uint32_t l, unsigned long long abs_off) {
+  return S.ring[l] + (abs_off & (S.ring_cap - 1));
+}
+
+/* PaxosCoordinatorState.getMedianMinus :867-875 over node_slots[lane][0..R)[gid] */
+__device__ __forceinline__ int median_minus(const DevState& S, uint32_t lane, uint32_t gid, uint32_t R) {
+  if (R == 3) {
+    int a = S.node_slots[ns_idx(S, lane, 0, gid)], b = S.node_slots[ns_idx(S, lane, 1, gid)],
+        c = S.node_slots[ns_idx(S, lane, 2, gid)];
+    return max(min(a, b), min(max(a, b), c));
+  }
+  int v[GPX_MAX_GROUP_SIZE];
+  for (uint32_t k = 0; k < R; k++) v[k] = S.node_slots[ns_idx(S, lane, k, gid)];
+  for (uint32_t k = 1; k < R; k++) { /* insertion sort, R <= 16 */
+    int x = v[k];
+    int m = (int)k - 1;
+    while (m >= 0 && v[m] > x) {
+      v[m + 1] = v[m];
+      m--;
+    }
+    v[m + 1] = x;
+  }
+  return v[(R % 2 == 0) ? R / 2 - 1 : R / 2];
+}
+
+/* PaxosAcceptor.garbageCollectAccepted :476-494.  Entries <= gc die implicitly (an
+ * accepted entry is alive iff valid && slot - gc > 0); garbageCollectDecisions :496-506
+ * is a no-op here because committed entries only ever live in [_slot, _slot + W). */
+__device__ __forceinline__ void gc_step(int4& row, int gcSlot) {
+  if (jsub(row.x, gcSlot) <= 0) gcSlot = row.x - 1;
+  if (jsub(gcSlot, row.w) > 0) row.w = gcSlot;
+}
+
+__device__ __forceinline__ gpx_exec_rec make_exec(const DevState& S, uint32_t gid, uint32_t lane, const DPValue& x,
+                                                  bool extra) {
+  int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
+  bool stop = (x.fl & GPX_ENT_STOP) != 0;
+  bool ckpt = (x.slot % cpi == 0) || stop; /* PISM.shouldCheckpoint :2037-2041 */
+  gpx_exec_rec r;
+  r.gid = gid;
+  r.slot = x.slot;
+  r.req_id = x.req_id;
+  r.payload_off = x.frame_ref;
+  r.flags = (stop ? GPX_F_STOP : 0u) | (ckpt ? GPX_F_CKPT : 0u) | (extra ? GPX_F_EXTRA : 0u) | (lane << 8) |
+            (x.fl & 0xffff0000u);
+  return r;
+}
+
+__device__ __forceinline__ void store_exec(gpx_exec_rec* dst, const gpx_exec_rec& r) {
+  /* 24 B = 3 x 8 B */
+  const long long* s = reinterpret_cast<const long long*>(&r);
+  long long* d = reinterpret_cast<long long*>(dst);
+  d[0] = s[0];
+  d[1] = s[1];
+  d[2] = s[2];
+}
+
+/*
+ * PISM.extractExecuteAndCheckpoint :1619-1701 around PaxosAcceptor.putAndRemoveNextExecutable
+ * :325-366 / reconstructDecision :369-385 / executed :462-474, on register-resident row/aux.
+ * The first execution goes to *primary (if non-null), further ones to the extra queue.
+ * `acc_hint` may carry the already loaded accepted entry of d.slot (q0,q1) to skip a reload.
+ */
+__device__ __noinline__ void eec(const DevState& S, uint32_t lane, uint32_t gid, int4& row, uint32_t& aux,
+                                 const DPValue& d, gpx_exec_rec* primary, gpx_exec_rec* extra, uint32_t extra_cap,
+                                 uint32_t* n_extra, unsigned int* s_ctr, bool all_extra) {
+  const uint32_t Wm = S.W - 1;
+  bool first = true;
+  while (true) {
+    if (GPX_AUX_STATE(aux) == GPX_ST_STOPPED) break;
+    gc_step(row, d.median_cp); /* :340 */
+    bool direct = false; /* d is next-in-line and valued: execute it without a com_win round trip */
+    if (jsub(d.slot, row.x) >= 0) { /* :343 put decision unless a valued one is present */
+      uint32_t w = (uint32_t)d.slot & Wm;
+      bool present = (GPX_AUX_PRESENT(aux) >> w) & 1u, valued = (GPX_AUX_VALUED(aux) >> w) & 1u;
+      if (!present || !valued) {
+        if (d.slot == row.x && d.valued) {
+          direct = true;
+          aux |= (1u << (8 + w)) | (1u << (16 + w));
+        } else {
+          size_t ci = 2 * win_idx(S, lane, w, gid);
+          S.com_win[ci] = make_int4(d.bnum, d.bcoord, d.median_cp, (int)d.frame_ref);
+          S.com_win[ci + 1] = make_int4((int)(unsigned)(d.req_id & 0xffffffffll), (int)(d.req_id >> 32), (int)d.plen,
+                                        (int)d.fl);
+          aux |= (1u << (8 + w));
+          if (d.valued)
+            aux |= (1u << (16 + w));
+          else
+            aux &= ~(1u << (16 + w));
+        }
+      }
+    }
+    uint32_t w0 = (uint32_t)row.x & Wm;
+    bool have = false;
+    DPValue nx;
+    if (direct) {
+      nx = d;
+      nx.fl = d.fl & ~GPX_ENT_VALID;
+      have = true;
+    } else if ((GPX_AUX_PRESENT(aux) >> w0) & 1u) { /* :352 */
+      size_t ci = 2 * win_idx(S, lane, w0, gid);
+      int4 c0 = S.com_win[ci], c1 = S.com_win[ci + 1];
+      if ((GPX_AUX_VALUED(aux) >> w0) & 1u) {
+        nx.slot = row.x;
+        nx.bnum = c0.x;
+        nx.bcoord = c0.y;
+        nx.median_cp = c0.z;
+        nx.frame_ref = (unsigned)c0.w;
+        nx.req_id = ((long long)c1.y << 32) | (unsigned)c1.x;
+        nx.plen = (unsigned)c1.z;
+        nx.fl = (unsigned)c1.w;
+        nx.valued = true;
+        have = true;
+      } else { /* reconstruct from the accept with an equal ballot :373-383 */
+        size_t ai = 2 * win_idx(S, lane, w0, gid);
+        int4 a0 = S.acc_win[ai], a1 = S.acc_win[ai + 1];
+        bool alive = ((unsigned)a1.w & GPX_ENT_VALID) && jsub(a0.x, row.w) > 0 && a0.x == row.x;
+        if (alive && a0.y == c0.x && a0.z == c0.y) {
+          nx.slot = row.x;
+          nx.bnum = a0.y;
+          nx.bcoord = a0.z;
+          nx.median_cp = c0.z;
+          nx.frame_ref = (unsigned)a0.w;
+          nx.req_id = ((long long)a1.y << 32) | (unsigned)a1.x;
+          nx.plen = (unsigned)a1.z;
+          nx.fl = (unsigned)a1.w & ~GPX_ENT_VALID;
+          nx.valued = true;
+          have = true;
+        }
+      }
+    }
+    {
+      if (have) {
+        aux &= ~((1u << (8 + w0)) | (1u << (16 + w0))); /* committedRequests.remove(slot) */
+        row.x = (int)((unsigned)row.x + 1u);            /* executed(): _slot++ */
+        if (nx.fl & GPX_ENT_STOP) {
+          aux = (aux & ~0xffu) | GPX_ST_STOPPED; /* stop() */
+          aux &= ~0x00ffff00u;                   /* committedRequests.clear() */
+        }
+        if (S.journaling) { /* acceptedProposals.remove(slot) :360-362 */
+          size_t ai = 2 * win_idx(S, lane, w0, gid);
+          int4 a0 = S.acc_win[ai];
+          int4 a1 = S.acc_win[ai + 1];
+          if (((unsigned)a1.w & GPX_ENT_VALID) && a0.x == nx.slot) {
+            a1.w = (int)((unsigned)a1.w & ~GPX_ENT_VALID);
+            S.acc_win[ai + 1] = a1;
+          }
+        }
+      }
+    }
+    if (!have) break;
+    atomicAdd(&s_ctr[C_EXECUTED], 1u);
+    gpx_exec_rec er = make_exec(S, gid, lane, nx, all_extra || !first);
+    if (er.flags & GPX_F_CKPT) atomicAdd(&s_ctr[C_CKPTS_DUE], 1u);
+    if (first && !all_extra && primary) {
+      store_exec(primary, er);
+    } else if (n_extra) {
+      uint32_t k = atomicAdd(n_extra, 1u);
+      if (k < extra_cap) store_exec(extra + k, er);
+    }
+    first = false;
+    if (nx.fl & GPX_ENT_STOP) {
+      atomicAdd(&s_ctr[C_STOPS_EXECUTED], 1u);
+      break;
+    }
+  }
+}

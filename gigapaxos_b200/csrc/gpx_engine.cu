@@ -1,0 +1,790 @@
+/*
+ * gpx_engine.cu -- host side of the engine and the C ABI of include/gpx.h.
+ *
+ * One engine == one GPU == one process (scale-out is one engine per rank, groups
+ * sharded by paxosID hash; see gigapaxos_b200/shard.py).  The engine owns the SoA
+ * state in HBM, the per-lane log rings and scratch streams; every entry point is a
+ * thin marshalling layer around the kernels in gpx_kernels.cuh.  There is no CPU
+ * fallback: without a CUDA device gpx_engine_create fails with GPX_ENOGPU.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gpx_kernels.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return fail(GPX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
+
+static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+struct gpx_engine {
+  gpx_config cfg;
+  DevState S;
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;
+  /* member sets */
+  std::vector<MsetInfo> msets;
+  std::map<std::vector<int32_t>, uint32_t> mset_ids;
+  MsetInfo* d_msets = nullptr;
+  /* host-side per-group info (name hash, version) for dump/load */
+  std::vector<int32_t> h_version, h_name_hash;
+  /* scratch streams */
+  gpx_request_rec* d_reqs = nullptr;
+  uint8_t* d_payload = nullptr;
+  uint8_t* d_blob1 = nullptr;
+  uint64_t blob1_cap = 0;
+  gpx_accept_rec* d_accepts = nullptr;
+  gpx_accept_reply_rec* d_replies = nullptr;
+  gpx_decision_rec* d_decisions = nullptr;
+  gpx_exec_rec* d_exec = nullptr;
+  gpx_exec_rec* d_extra = nullptr;
+  uint32_t extra_cap = 0;
+  int32_t* d_status = nullptr;
+  uint32_t* d_copy_tab = nullptr;
+  uint32_t* d_copy_dst = nullptr;
+  RoundCtl* d_ctl = nullptr;
+  RoundCtl* h_ctl = nullptr; /* pinned */
+  void* d_misc = nullptr;    /* group-management staging */
+  size_t misc_bytes = 0;
+  /* timing */
+  bool timing = false;
+  cudaEvent_t ev[5];
+  gpx_kernel_times kt;
+
+  template <typename T>
+  int dalloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 16);
+    if (e != cudaSuccess) return fail(GPX_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    allocs.push_back(q);
+    *p = (T*)q;
+    return GPX_OK;
+  }
+  int ensure_misc(size_t bytes) {
+    if (bytes <= misc_bytes) return GPX_OK;
+    if (d_misc) cudaFree(d_misc);
+    misc_bytes = bytes + (bytes >> 2) + 4096;
+    cudaError_t e = cudaMalloc(&d_misc, misc_bytes);
+    if (e != cudaSuccess) {
+      d_misc = nullptr;
+      misc_bytes = 0;
+      return fail(GPX_ENOMEM, "cudaMalloc(misc)");
+    }
+    return GPX_OK;
+  }
+};
+
+extern "C" {
+
+const char* gpx_last_error(void) { return g_err.c_str(); }
+const char* gpx_build_info(void) {
+  return "gpx CUDA engine: hand-written kernels for sm_100a (compute_100a), nvcc " __DATE__;
+}
+
+void gpx_config_defaults(gpx_config* c) {
+  memset(c, 0, sizeof *c);
+  c->abi_version = GPX_ABI_VERSION;
+  c->device = 0;
+  c->max_groups = 1024;
+  c->n_lanes = 3;
+  c->lane_node[0] = 100; /* TC.TEST_START_NODE_ID testing/TESTPaxosConfig.java:100 */
+  c->lane_node[1] = 101;
+  c->lane_node[2] = 102;
+  c->window = 8;
+  c->max_group_size = 3;
+  c->log_ring_bytes = 1ull << 26;
+  c->max_batch_recs = 1u << 16;
+  c->max_batch_payload = 1ull << 24;
+  c->batching_enabled = 1;         /* PaxosConfig.java:309 */
+  c->max_batch_size = 2000;        /* :403 */
+  c->max_batch_bytes = 4 * 1024 * 1024; /* min(NIOTransport.MAX_PAYLOAD_SIZE, MAX_LOG_MESSAGE_SIZE) */
+  c->request_size_estimate = 512;
+  c->checkpoint_interval = 400;    /* :410 */
+  c->cpi_noise = 0;                /* :746 */
+  c->gc_majority_executed = 1;     /* :882 */
+  c->log_meta_decisions = 1;       /* :588 */
+  c->journaling_enabled = 1;       /* :240 */
+  c->batched_accept_replies = 1;   /* :458 */
+  c->batched_commits = 1;          /* :466 */
+  c->short_circuit_local = 1;      /* :834 */
+  c->min_pp_batch_size = 3;        /* :860 */
+  c->digest_requests = 0;          /* :788 */
+}
+
+/* ---- Java helpers (String.hashCode, Math.abs, PISM.roundRobinCoordinator, getCPI) ---- */
+int32_t gpx_java_string_hash(const char* s, size_t len) {
+  uint32_t h = 0;
+  for (size_t i = 0; i < len; i++) h = 31u * h + (uint32_t)(unsigned char)s[i];
+  return (int32_t)h;
+}
+static int32_t java_abs(int32_t v) { return v < 0 ? (int32_t)(0u - (uint32_t)v) : v; }
+int32_t gpx_round_robin_coordinator(int32_t name_hash, const int32_t* m, int32_t n, int32_t ballotnum) {
+  int32_t idx = java_abs((int32_t)((uint32_t)ballotnum + (uint32_t)name_hash)) % n;
+  if (idx < 0) idx = -idx;
+  return m[idx];
+}
+int32_t gpx_get_cpi(int32_t cpi, double noise, int32_t name_hash) {
+  return (int32_t)(cpi * (1 - noise) + (java_abs(name_hash) % cpi) * 2 * noise);
+}
+
+/* ---- lifecycle -------------------------------------------------------------------- */
+int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
+  if (!cfg || !out) return fail(GPX_EINVAL, "null argument");
+  if (cfg->abi_version != GPX_ABI_VERSION) return fail(GPX_EINVAL, "abi_version mismatch");
+  if (cfg->n_lanes == 0 || cfg->n_lanes > GPX_MAX_LANES) return fail(GPX_EINVAL, "n_lanes out of range");
+  if (cfg->window == 0 || cfg->window > GPX_MAX_WINDOW || (cfg->window & (cfg->window - 1)))
+    return fail(GPX_EINVAL, "window must be 1,2,4 or 8");
+  if (cfg->max_group_size == 0 || cfg->max_group_size > GPX_MAX_GROUP_SIZE)
+    return fail(GPX_EINVAL, "max_group_size out of range");
+  if (cfg->log_ring_bytes < (1u << 16) || (cfg->log_ring_bytes & (cfg->log_ring_bytes - 1)))
+    return fail(GPX_EINVAL, "log_ring_bytes must be a power of two >= 64 KiB");
+  if (cfg->max_groups == 0 || cfg->max_batch_recs == 0) return fail(GPX_EINVAL, "zero capacity");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(GPX_ENOGPU, "no CUDA device: the gpx engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(GPX_EINVAL, "bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+  gpx_engine* e = new gpx_engine();
+  e->cfg = *cfg;
+  memset(&e->kt, 0, sizeof e->kt);
+  DevState& S = e->S;
+  memset(&S, 0, sizeof S);
+  const size_t G = cfg->max_groups, L = cfg->n_lanes, W = cfg->window, R = cfg->max_group_size;
+  S.G = (uint32_t)G;
+  S.L = (uint32_t)L;
+  S.W = (uint32_t)W;
+  S.Rcap = (uint32_t)R;
+  int rc;
+#define TRY(x)            \
+  if ((rc = (x)) != 0) {  \
+    gpx_engine_destroy(e);\
+    return rc;            \
+  }
+  TRY(e->dalloc(&S.acc_row, L * G));
+  TRY(e->dalloc(&S.acc_aux, L * G));
+  TRY(e->dalloc(&S.acc_win, 2 * L * W * G));
+  TRY(e->dalloc(&S.com_win, 2 * L * W * G));
+  TRY(e->dalloc(&S.coord_row, L * G));
+  TRY(e->dalloc(&S.node_slots, L * R * G));
+  TRY(e->dalloc(&S.prop_win, L * W * G));
+  TRY(e->dalloc(&S.grp_meta, G));
+  TRY(e->dalloc(&S.grp_cpi, G));
+  TRY(e->dalloc(&e->d_msets, (size_t)GPX_MAX_MSETS));
+  S.msets = e->d_msets;
+  S.ring_cap = cfg->log_ring_bytes;
+  for (size_t l = 0; l < L; l++) {
+    TRY(e->dalloc(&S.ring[l], (size_t)cfg->log_ring_bytes));
+    cudaMemset(S.ring[l], 0, cfg->log_ring_bytes);
+  }
+  TRY(e->dalloc(&S.ring_head, (size_t)GPX_MAX_LANES));
+  TRY(e->dalloc(&S.seg_seq, (size_t)GPX_MAX_LANES));
+  TRY(e->dalloc(&S.ctr, (size_t)C_NCTR));
+  TRY(e->dalloc(&S.tickets, (size_t)8));
+  cudaMemset(S.ring_head, 0, GPX_MAX_LANES * 8);
+  cudaMemset(S.seg_seq, 0, GPX_MAX_LANES * 8);
+  cudaMemset(S.ctr, 0, C_NCTR * 8);
+  cudaMemset(S.tickets, 0, 8 * 4);
+  cudaMemset(S.grp_meta, 0, G * 4);
+  {
+    /* every row starts FREE */
+    std::vector<uint32_t> aux(L * G, (uint32_t)GPX_ST_FREE);
+    cudaMemcpy(S.acc_aux, aux.data(), L * G * 4, cudaMemcpyHostToDevice);
+    cudaMemset(S.coord_row, 0, L * G * sizeof(int4));
+    cudaMemset(S.acc_win, 0, 2 * L * W * G * sizeof(int4));
+    cudaMemset(S.com_win, 0, 2 * L * W * G * sizeof(int4));
+    cudaMemset(S.prop_win, 0, L * W * G * sizeof(int4));
+  }
+  for (size_t l = 0; l < GPX_MAX_LANES; l++) S.lane_node[l] = l < L ? cfg->lane_node[l] : INT32_MIN;
+  S.cpi_const = cfg->checkpoint_interval;
+  S.cpi_per_group = cfg->cpi_noise != 0.0;
+  S.gc_majority_executed = cfg->gc_majority_executed;
+  S.log_meta = cfg->log_meta_decisions;
+  S.journaling = cfg->journaling_enabled;
+  S.batching = cfg->batching_enabled;
+  S.max_batch_size = cfg->max_batch_size;
+  S.size_est = cfg->request_size_estimate;
+  S.max_batch_bytes = cfg->max_batch_bytes;
+  /* scratch */
+  const size_t N = cfg->max_batch_recs;
+  const uint64_t P = (cfg->max_batch_payload + 15) & ~15ull;
+  TRY(e->dalloc(&e->d_reqs, N));
+  TRY(e->dalloc(&e->d_payload, (size_t)P));
+  e->blob1_cap = P + 16ull * N;
+  TRY(e->dalloc(&e->d_blob1, (size_t)e->blob1_cap));
+  TRY(e->dalloc(&e->d_accepts, N));
+  TRY(e->dalloc(&e->d_replies, N * L));
+  TRY(e->dalloc(&e->d_decisions, N * L));
+  TRY(e->dalloc(&e->d_exec, N * L));
+  e->extra_cap = (uint32_t)N;
+  TRY(e->dalloc(&e->d_extra, N));
+  TRY(e->dalloc(&e->d_status, N));
+  TRY(e->dalloc(&e->d_copy_tab, N));
+  TRY(e->dalloc(&e->d_copy_dst, N));
+  TRY(e->dalloc(&e->d_ctl, (size_t)1));
+#undef TRY
+  if (cudaHostAlloc((void**)&e->h_ctl, sizeof(RoundCtl), cudaHostAllocDefault) != cudaSuccess) {
+    gpx_engine_destroy(e);
+    return fail(GPX_ENOMEM, "cudaHostAlloc");
+  }
+  cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 5; i++) cudaEventCreate(&e->ev[i]);
+  e->h_version.assign(G, 0);
+  e->h_name_hash.assign(G, 0);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    gpx_engine_destroy(e);
+    return fail(GPX_ECUDA, cudaGetErrorString(err));
+  }
+  *out = e;
+  return GPX_OK;
+}
+
+void gpx_engine_destroy(gpx_engine* e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->d_misc) cudaFree(e->d_misc);
+  if (e->h_ctl) cudaFreeHost(e->h_ctl);
+  if (e->stream) {
+    cudaStreamDestroy(e->stream);
+    for (int i = 0; i < 5; i++) cudaEventDestroy(e->ev[i]);
+  }
+  delete e;
+}
+
+/* ---- groups ----------------------------------------------------------------------- */
+static int intern_mset(gpx_engine* e, std::vector<int32_t> m, uint32_t* id, bool* added) {
+  std::sort(m.begin(), m.end()); /* PISM ctor sorts groupMembers :205 */
+  auto it = e->mset_ids.find(m);
+  if (it != e->mset_ids.end()) {
+    *id = it->second;
+    return GPX_OK;
+  }
+  if (e->msets.size() >= GPX_MAX_MSETS) return fail(GPX_ERANGE, "too many distinct member sets");
+  MsetInfo mi;
+  memset(&mi, 0xff, sizeof mi);
+  mi.R = (uint8_t)m.size();
+  mi.lane_mask = 0;
+  mi.pad = 0;
+  mi.pad2 = 0;
+  for (size_t i = 0; i < GPX_MAX_GROUP_SIZE; i++) mi.nodes[i] = i < m.size() ? m[i] : INT32_MIN;
+  for (uint32_t l = 0; l < e->cfg.n_lanes; l++)
+    for (size_t i = 0; i < m.size(); i++)
+      if (m[i] == e->cfg.lane_node[l]) {
+        mi.lane_of_idx[i] = (uint8_t)l;
+        mi.idx_of_lane[l] = (uint8_t)i;
+        mi.lane_mask |= (uint16_t)(1u << l);
+      }
+  *id = (uint32_t)e->msets.size();
+  e->msets.push_back(mi);
+  e->mset_ids[m] = *id;
+  *added = true;
+  return GPX_OK;
+}
+static int push_msets(gpx_engine* e) {
+  CK(cudaMemcpyAsync(e->d_msets, e->msets.data(), e->msets.size() * sizeof(MsetInfo), cudaMemcpyHostToDevice,
+                     e->stream));
+  return GPX_OK;
+}
+
+int gpx_create_groups(gpx_engine* e, uint32_t n, const gpx_group_desc* d) {
+  if (!e || (!d && n)) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  std::vector<InitRec> recs(n);
+  bool added = false;
+  for (uint32_t k = 0; k < n; k++) {
+    if (d[k].gid >= e->cfg.max_groups) return fail(GPX_ERANGE, "gid >= max_groups");
+    if (d[k].n_members <= 0 || d[k].n_members > (int)e->cfg.max_group_size)
+      return fail(GPX_ERANGE, "group size exceeds max_group_size");
+    std::vector<int32_t> m(d[k].members, d[k].members + d[k].n_members);
+    std::sort(m.begin(), m.end());
+    uint32_t id;
+    int rc = intern_mset(e, m, &id, &added);
+    if (rc) return rc;
+    recs[k].gid = d[k].gid;
+    recs[k].mset = id;
+    recs[k].coord0 = gpx_round_robin_coordinator(d[k].name_hash, m.data(), (int32_t)m.size(), 0);
+    recs[k].cpi = gpx_get_cpi(e->cfg.checkpoint_interval, e->cfg.cpi_noise, d[k].name_hash);
+    recs[k].init_mode = d[k].init_mode;
+    recs[k].R = (uint32_t)m.size();
+    e->h_version[d[k].gid] = d[k].version;
+    e->h_name_hash[d[k].gid] = d[k].name_hash;
+  }
+  if (added) {
+    int rc = push_msets(e);
+    if (rc) return rc;
+  }
+  int rc = e->ensure_misc(n * sizeof(InitRec));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->d_misc, recs.data(), n * sizeof(InitRec), cudaMemcpyHostToDevice, e->stream));
+  k_init_groups<<<cdiv(n, 256), 256, 0, e->stream>>>(e->S, (const InitRec*)e->d_misc, n);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return GPX_OK;
+}
+
+int gpx_destroy_groups(gpx_engine* e, uint32_t n, const uint32_t* gids) {
+  if (!e || (!gids && n)) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  int rc = e->ensure_misc(n * 4ull);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->d_misc, gids, n * 4ull, cudaMemcpyHostToDevice, e->stream));
+  k_destroy_groups<<<cdiv(n, 256), 256, 0, e->stream>>>(e->S, (const uint32_t*)e->d_misc, n);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return GPX_OK;
+}
+
+int gpx_dump_rows(gpx_engine* e, uint32_t n, const uint32_t* gids, uint32_t lane, gpx_row* out) {
+  if (!e || !gids || !out) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  if (n == 0) return GPX_OK;
+  size_t goff = (n * sizeof(gpx_row) + 255) & ~(size_t)255;
+  int rc = e->ensure_misc(goff + n * 4ull);
+  if (rc) return rc;
+  uint32_t* d_g = (uint32_t*)((uint8_t*)e->d_misc + goff);
+  CK(cudaMemcpyAsync(d_g, gids, n * 4ull, cudaMemcpyHostToDevice, e->stream));
+  k_dump_rows<<<cdiv(n, 128), 128, 0, e->stream>>>(e->S, d_g, n, lane, (gpx_row*)e->d_misc);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, e->d_misc, n * sizeof(gpx_row), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (uint32_t k = 0; k < n; k++)
+    if (gids[k] < e->cfg.max_groups) out[k].version = e->h_version[gids[k]];
+  return GPX_OK;
+}
+
+int gpx_load_rows(gpx_engine* e, uint32_t n, const gpx_row* rows) {
+  if (!e || (!rows && n)) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  std::vector<LoadRec> recs(n);
+  bool added = false;
+  for (uint32_t k = 0; k < n; k++) {
+    const gpx_row& r = rows[k];
+    if (r.gid >= e->cfg.max_groups || r.lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "gid/lane");
+    if (r.n_members <= 0 || r.n_members > (int)e->cfg.max_group_size) return fail(GPX_ERANGE, "n_members");
+    std::vector<int32_t> m(r.members, r.members + r.n_members);
+    uint32_t id;
+    int rc = intern_mset(e, m, &id, &added);
+    if (rc) return rc;
+    recs[k].row = r;
+    recs[k].mset = id;
+    recs[k].cpi = gpx_get_cpi(e->cfg.checkpoint_interval, e->cfg.cpi_noise, e->h_name_hash[r.gid]);
+    e->h_version[r.gid] = r.version;
+  }
+  if (added) {
+    int rc = push_msets(e);
+    if (rc) return rc;
+  }
+  int rc = e->ensure_misc(n * sizeof(LoadRec));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->d_misc, recs.data(), n * sizeof(LoadRec), cudaMemcpyHostToDevice, e->stream));
+  k_load_rows<<<cdiv(n, 128), 128, 0, e->stream>>>(e->S, (const LoadRec*)e->d_misc, n);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return GPX_OK;
+}
+
+int gpx_patch(gpx_engine* e, uint32_t n, const gpx_patch_rec* p) {
+  if (!e || (!p && n)) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  for (uint32_t k = 0; k < n; k++) {
+    if (p[k].gid >= e->cfg.max_groups || p[k].lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "gid/lane");
+    if (p[k].op < GPX_PATCH_SET_BALLOT || p[k].op > GPX_PATCH_SET_GC) return fail(GPX_EINVAL, "bad patch op");
+  }
+  int rc = e->ensure_misc(n * sizeof(gpx_patch_rec));
+  if (rc) return rc;
+  /* patches to the same (gid,lane) must apply in order: launch them one wave at a time */
+  std::vector<gpx_patch_rec> wave;
+  std::vector<uint8_t> done(n, 0);
+  uint32_t left = n;
+  while (left) {
+    wave.clear();
+    std::map<std::pair<uint32_t, uint32_t>, int> seen;
+    for (uint32_t k = 0; k < n; k++) {
+      if (done[k]) continue;
+      auto key = std::make_pair(p[k].gid, p[k].lane);
+      if (seen.count(key)) continue;
+      seen[key] = 1;
+      wave.push_back(p[k]);
+      done[k] = 1;
+      left--;
+    }
+    CK(cudaMemcpyAsync(e->d_misc, wave.data(), wave.size() * sizeof(gpx_patch_rec), cudaMemcpyHostToDevice,
+                       e->stream));
+    k_patch<<<cdiv(wave.size(), 128), 128, 0, e->stream>>>(e->S, (const gpx_patch_rec*)e->d_misc,
+                                                            (uint32_t)wave.size());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return GPX_OK;
+}
+
+/* ---- kernel launch helpers (device pointers) ------------------------------------- */
+static int launch_propose(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload,
+                          uint64_t payload_al, uint32_t n, int32_t* d_status, cudaStream_t st) {
+  ProposeArgs A;
+  A.reqs = d_reqs;
+  A.n = n;
+  A.payload_bytes_al = payload_al;
+  A.accepts = e->d_accepts;
+  A.status = d_status;
+  A.copy_tab = e->d_copy_tab;
+  A.copy_dst = e->d_copy_dst;
+  A.ctl = e->d_ctl;
+  k_propose<<<cdiv(n, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
+  k_build_blobs<<<cdiv(n, GPX_BLOCK), GPX_BLOCK, 0, st>>>(A, d_payload, e->d_blob1);
+  CK(cudaGetLastError());
+  return GPX_OK;
+}
+
+static int launch_accept(gpx_engine* e, const gpx_accept_rec* d_recs, const uint32_t* n_ptr, uint32_t n_max,
+                         const uint8_t* blob0, uint64_t blob0_bytes, const uint8_t* blob1, uint64_t blob1_bytes,
+                         const unsigned long long* blob1_used_ptr, gpx_accept_reply_rec* d_replies, cudaStream_t st) {
+  AcceptArgs A;
+  A.recs = d_recs;
+  A.n_ptr = n_ptr;
+  A.n_max = n_max;
+  A.blob0 = blob0;
+  A.blob0_bytes = blob0_bytes;
+  A.blob1 = blob1;
+  A.blob1_bytes = blob1_bytes;
+  A.blob1_used_ptr = blob1_used_ptr;
+  A.replies = d_replies;
+  A.extra = e->d_extra;
+  A.extra_cap = e->extra_cap;
+  A.n_extra = &e->d_ctl->n_extra;
+  k_accept<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  return GPX_OK;
+}
+
+static int launch_tally(gpx_engine* e, const gpx_accept_reply_rec* d_replies, const uint32_t* n_ptr, uint32_t mult,
+                        uint32_t n_max, gpx_decision_rec* d_dec, cudaStream_t st) {
+  TallyArgs A;
+  A.replies = d_replies;
+  A.n_ptr = n_ptr;
+  A.mult = mult;
+  A.n_max = n_max;
+  A.decisions = d_dec;
+  A.n_decisions = &e->d_ctl->n_decisions;
+  k_tally<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  return GPX_OK;
+}
+
+static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uint32_t* n_ptr, uint32_t n_max,
+                         gpx_exec_rec* d_exec, cudaStream_t st) {
+  CommitArgs A;
+  A.decisions = d_dec;
+  A.n_ptr = n_ptr;
+  A.n_max = n_max;
+  A.exec = d_exec;
+  A.extra = e->d_extra;
+  A.extra_cap = e->extra_cap;
+  A.n_extra = &e->d_ctl->n_extra;
+  k_commit<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  return GPX_OK;
+}
+
+static int ring_fits(gpx_engine* e, uint64_t reserved) {
+  if (reserved > e->cfg.log_ring_bytes) return fail(GPX_ERANGE, "batch does not fit the log ring; raise log_ring_bytes");
+  return GPX_OK;
+}
+static int check_batch(gpx_engine* e, uint32_t n, uint64_t payload_bytes) {
+  if (n > e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
+  if (payload_bytes > e->cfg.max_batch_payload) return fail(GPX_ERANGE, "payload_bytes > max_batch_payload");
+  return GPX_OK;
+}
+static int fetch_ctl(gpx_engine* e) {
+  CK(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return GPX_OK;
+}
+
+/* ---- data path: host buffers -------------------------------------------------------- */
+int gpx_propose(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                uint64_t payload_bytes, gpx_accept_rec* out_accepts, uint32_t* n_accepts, uint8_t* out_blob,
+                uint64_t blob_cap, uint64_t* blob_bytes, int32_t* status) {
+  if (!e || !n_accepts || !blob_bytes) return fail(GPX_EINVAL, "null argument");
+  *n_accepts = 0;
+  *blob_bytes = 0;
+  if (n == 0) return GPX_OK;
+  if (!reqs || !out_accepts || !status || (!payload && payload_bytes)) return fail(GPX_EINVAL, "null argument");
+  int rc = check_batch(e, n, payload_bytes);
+  if (rc) return rc;
+  const uint64_t pal = (payload_bytes + 15) & ~15ull;
+  cudaStream_t st = e->stream;
+  CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
+  CK(cudaMemcpyAsync(e->d_reqs, reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, st));
+  if (payload_bytes) CK(cudaMemcpyAsync(e->d_payload, payload, payload_bytes, cudaMemcpyHostToDevice, st));
+  rc = launch_propose(e, e->d_reqs, e->d_payload, pal, n, e->d_status, st);
+  if (rc) return rc;
+  rc = fetch_ctl(e);
+  if (rc) return rc;
+  const uint32_t na = e->h_ctl->n_accepts;
+  const uint64_t b1 = e->h_ctl->blob1_used;
+  if (pal + b1 > blob_cap) return fail(GPX_ERANGE, "out_blob too small");
+  CK(cudaMemcpyAsync(out_accepts, e->d_accepts, na * sizeof(gpx_accept_rec), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, e->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (out_blob) {
+    if (payload_bytes) memcpy(out_blob, payload, payload_bytes);
+    if (pal > payload_bytes) memset(out_blob + payload_bytes, 0, pal - payload_bytes);
+    if (b1) CK(cudaMemcpyAsync(out_blob + pal, e->d_blob1, b1, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  *n_accepts = na;
+  *blob_bytes = pal + b1;
+  return GPX_OK;
+}
+
+int gpx_handle_accepts(gpx_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
+                       uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra_exec,
+                       uint32_t extra_cap, uint32_t* n_extra) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n_extra) *n_extra = 0;
+  if (n == 0) return GPX_OK;
+  if (!accepts || !out_replies || (!blob && blob_bytes)) return fail(GPX_EINVAL, "null argument");
+  if (blob_bytes & 15) return fail(GPX_EINVAL, "blob_bytes must be a multiple of 16");
+  if (n > e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
+  if (blob_bytes > e->blob1_cap) return fail(GPX_ERANGE, "blob too large");
+  int rc = ring_fits(e, 64ull + 48ull * n + blob_bytes);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  const uint32_t L = e->cfg.n_lanes;
+  CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
+  CK(cudaMemcpyAsync(e->d_accepts, accepts, n * sizeof(gpx_accept_rec), cudaMemcpyHostToDevice, st));
+  if (blob_bytes) CK(cudaMemcpyAsync(e->d_blob1, blob, blob_bytes, cudaMemcpyHostToDevice, st));
+  rc = launch_accept(e, e->d_accepts, nullptr, n, e->d_blob1, blob_bytes, nullptr, 0, nullptr, e->d_replies, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_replies, e->d_replies, (size_t)n * L * sizeof(gpx_accept_reply_rec), cudaMemcpyDeviceToHost,
+                     st));
+  rc = fetch_ctl(e);
+  if (rc) return rc;
+  uint32_t nx = e->h_ctl->n_extra;
+  if (n_extra) *n_extra = nx;
+  uint32_t cp = std::min(std::min(nx, extra_cap), e->extra_cap);
+  if (cp && out_extra_exec) {
+    CK(cudaMemcpyAsync(out_extra_exec, e->d_extra, cp * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return GPX_OK;
+}
+
+int gpx_handle_accept_replies(gpx_engine* e, uint32_t n, const gpx_accept_reply_rec* replies,
+                              gpx_decision_rec* out_decisions, uint32_t* n_decisions) {
+  if (!e || !n_decisions) return fail(GPX_EINVAL, "null argument");
+  *n_decisions = 0;
+  if (n == 0) return GPX_OK;
+  if (!replies || !out_decisions) return fail(GPX_EINVAL, "null argument");
+  if (n > (uint64_t)e->cfg.max_batch_recs * e->cfg.n_lanes) return fail(GPX_ERANGE, "n > max_batch_recs * n_lanes");
+  cudaStream_t st = e->stream;
+  CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
+  CK(cudaMemcpyAsync(e->d_replies, replies, n * sizeof(gpx_accept_reply_rec), cudaMemcpyHostToDevice, st));
+  int rc = launch_tally(e, e->d_replies, nullptr, 1, n, e->d_decisions, st);
+  if (rc) return rc;
+  rc = fetch_ctl(e);
+  if (rc) return rc;
+  uint32_t nd = e->h_ctl->n_decisions;
+  if (nd) {
+    CK(cudaMemcpyAsync(out_decisions, e->d_decisions, nd * sizeof(gpx_decision_rec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  *n_decisions = nd;
+  return GPX_OK;
+}
+
+int gpx_handle_decisions(gpx_engine* e, uint32_t n, const gpx_decision_rec* decisions, gpx_exec_rec* out_exec,
+                         gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n_extra) *n_extra = 0;
+  if (n == 0) return GPX_OK;
+  if (!decisions || !out_exec) return fail(GPX_EINVAL, "null argument");
+  if (n > (uint64_t)e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
+  int rc = ring_fits(e, 64ull + 32ull * n);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  const uint32_t L = e->cfg.n_lanes;
+  CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
+  CK(cudaMemcpyAsync(e->d_decisions, decisions, n * sizeof(gpx_decision_rec), cudaMemcpyHostToDevice, st));
+  rc = launch_commit(e, e->d_decisions, nullptr, n, e->d_exec, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_exec, e->d_exec, (size_t)n * L * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+  rc = fetch_ctl(e);
+  if (rc) return rc;
+  uint32_t nx = e->h_ctl->n_extra;
+  if (n_extra) *n_extra = nx;
+  uint32_t cp = std::min(std::min(nx, extra_cap), e->extra_cap);
+  if (cp && out_extra_exec) {
+    CK(cudaMemcpyAsync(out_extra_exec, e->d_extra, cp * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return GPX_OK;
+}
+
+/* the fused round on device pointers; all inter-replica records stay in HBM */
+static int round_on_stream(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload,
+                           uint64_t payload_bytes, uint32_t n, int32_t* d_status, gpx_exec_rec* d_exec,
+                           cudaStream_t st) {
+  const uint64_t pal = (payload_bytes + 15) & ~15ull;
+  const uint32_t L = e->cfg.n_lanes;
+  const bool tm = e->timing;
+  CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
+  if (tm) cudaEventRecord(e->ev[0], st);
+  int rc = launch_propose(e, d_reqs, d_payload, pal, n, d_status, st);
+  if (rc) return rc;
+  if (tm) cudaEventRecord(e->ev[1], st);
+  /* the ACCEPT segment mirrors the payload arena plus the constructed blobs actually used */
+  rc = launch_accept(e, e->d_accepts, &e->d_ctl->n_accepts, n, d_payload, pal, e->d_blob1, 0, &e->d_ctl->blob1_used,
+                     e->d_replies, st);
+  if (rc) return rc;
+  if (tm) cudaEventRecord(e->ev[2], st);
+  rc = launch_tally(e, e->d_replies, &e->d_ctl->n_accepts, L, n * L, e->d_decisions, st);
+  if (rc) return rc;
+  if (tm) cudaEventRecord(e->ev[3], st);
+  rc = launch_commit(e, e->d_decisions, &e->d_ctl->n_decisions, n, d_exec, st);
+  if (rc) return rc;
+  if (tm) {
+    cudaEventRecord(e->ev[4], st);
+    cudaEventSynchronize(e->ev[4]);
+    float ms;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+    e->kt.propose_ms += ms;
+    cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]);
+    e->kt.accept_ms += ms;
+    cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]);
+    e->kt.tally_ms += ms;
+    cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]);
+    e->kt.commit_ms += ms;
+    e->kt.launches++;
+  }
+  return GPX_OK;
+}
+
+int gpx_round(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload, uint64_t payload_bytes,
+              int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots, gpx_exec_rec* out_extra_exec,
+              uint32_t extra_cap, uint32_t* n_extra) {
+  if (!e || !n_exec_slots) return fail(GPX_EINVAL, "null argument");
+  *n_exec_slots = 0;
+  if (n_extra) *n_extra = 0;
+  if (n == 0) return GPX_OK;
+  if (!reqs || !status || !out_exec || (!payload && payload_bytes)) return fail(GPX_EINVAL, "null argument");
+  int rc = check_batch(e, n, payload_bytes);
+  if (rc) return rc;
+  const uint64_t pal = (payload_bytes + 15) & ~15ull;
+  const uint64_t b1 = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
+  rc = ring_fits(e, 64ull + 48ull * n + pal + b1);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  const uint32_t L = e->cfg.n_lanes;
+  CK(cudaMemcpyAsync(e->d_reqs, reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, st));
+  if (payload_bytes) CK(cudaMemcpyAsync(e->d_payload, payload, payload_bytes, cudaMemcpyHostToDevice, st));
+  rc = round_on_stream(e, e->d_reqs, e->d_payload, payload_bytes, n, e->d_status, e->d_exec, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(status, e->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  rc = fetch_ctl(e);
+  if (rc) return rc;
+  const uint32_t nd = e->h_ctl->n_decisions, nx = e->h_ctl->n_extra;
+  if (nd) CK(cudaMemcpyAsync(out_exec, e->d_exec, (size_t)nd * L * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+  uint32_t cp = std::min(std::min(nx, extra_cap), e->extra_cap);
+  if (cp && out_extra_exec)
+    CK(cudaMemcpyAsync(out_extra_exec, e->d_extra, cp * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_exec_slots = nd * L;
+  if (n_extra) *n_extra = nx;
+  return GPX_OK;
+}
+
+int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream) {
+  if (!e || !b) return fail(GPX_EINVAL, "null argument");
+  if (b->n == 0) return GPX_OK;
+  int rc = check_batch(e, b->n, b->payload_bytes);
+  if (rc) return rc;
+  return round_on_stream(e, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
+                         stream ? (cudaStream_t)stream : e->stream);
+}
+
+int gpx_enable_kernel_timing(gpx_engine* e, int on) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  e->timing = on != 0;
+  return GPX_OK;
+}
+int gpx_get_kernel_times(gpx_engine* e, gpx_kernel_times* out, int reset) {
+  if (!e || !out) return fail(GPX_EINVAL, "null argument");
+  *out = e->kt;
+  if (reset) memset(&e->kt, 0, sizeof e->kt);
+  return GPX_OK;
+}
+
+/* ---- log ring ----------------------------------------------------------------------- */
+int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_t cap, uint64_t* n_copied,
+                 uint64_t* head) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  CK(cudaStreamSynchronize(e->stream));
+  unsigned long long heads[GPX_MAX_LANES];
+  CK(cudaMemcpy(heads, e->S.ring_head, sizeof heads, cudaMemcpyDeviceToHost));
+  const uint64_t h = heads[lane], rc = e->S.ring_cap;
+  if (head) *head = h;
+  uint64_t nb = 0;
+  if (dst && from < h) {
+    nb = std::min<uint64_t>(cap, h - from);
+    if (h - from > rc) return fail(GPX_ERANGE, "requested bytes were already overwritten");
+    uint64_t pos = from & (rc - 1);
+    uint64_t first = std::min<uint64_t>(nb, rc - pos);
+    CK(cudaMemcpy(dst, e->S.ring[lane] + pos, first, cudaMemcpyDeviceToHost));
+    if (nb > first) CK(cudaMemcpy((uint8_t*)dst + first, e->S.ring[lane], nb - first, cudaMemcpyDeviceToHost));
+  }
+  if (n_copied) *n_copied = nb;
+  return GPX_OK;
+}
+
+/* ---- introspection ------------------------------------------------------------------- */
+int gpx_get_counters(gpx_engine* e, gpx_counters* out) {
+  if (!e || !out) return fail(GPX_EINVAL, "null argument");
+  CK(cudaStreamSynchronize(e->stream));
+  unsigned long long c[C_NCTR];
+  CK(cudaMemcpy(c, e->S.ctr, sizeof c, cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof *out);
+  uint64_t* o = (uint64_t*)out;
+  for (int i = 0; i < C_NCTR && i < (int)(sizeof(gpx_counters) / 8); i++) o[i] = c[i];
+  return GPX_OK;
+}
+int gpx_reset_counters(gpx_engine* e) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  CK(cudaMemset(e->S.ctr, 0, C_NCTR * 8));
+  return GPX_OK;
+}
+int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out) {
+  if (!e || !gids || !out) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  if (n == 0) return GPX_OK;
+  size_t goff = ((size_t)n + 255) & ~(size_t)255;
+  int rc = e->ensure_misc(goff + n * 4ull);
+  if (rc) return rc;
+  uint32_t* d_g = (uint32_t*)((uint8_t*)e->d_misc + goff);
+  CK(cudaMemcpyAsync(d_g, gids, n * 4ull, cudaMemcpyHostToDevice, e->stream));
+  k_get_flags<<<cdiv(n, 256), 256, 0, e->stream>>>(e->S, lane, d_g, n, (uint8_t*)e->d_misc);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, e->d_misc, n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return GPX_OK;
+}
+
+} /* extern "C" */

@@ -347,6 +347,15 @@ int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_
 /* ---- introspection ---------------------------------------------------------------- */
 int gpx_get_counters(gpx_engine* e, gpx_counters* out);
 int gpx_reset_counters(gpx_engine* e);
+/* slow-path list: per-group flag byte of one lane (bit0 window overflow: a record beyond the
+ * in-flight window W was dropped; bit1 needs sync: a commit could not be resolved locally ->
+ * host runs PISM.syncLongDecisionGaps :1550 / requestMissingDecisions) */
+#define GPX_GF_OVERFLOW_BIT 1u
+#define GPX_GF_NEEDS_SYNC_BIT 2u
+int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out);
+/* `active.<name>=host:port` entries (PaxosConfig.getActives :156-170) of the last
+ * gpx_config_from_properties call, as "name=host:port\n" lines */
+int gpx_properties_actives(char* out, size_t cap);
 
 /* ---- device-resident API (bench `value`, multi-GPU shards): all pointers are device
  * pointers owned by the caller, `stream` is a cudaStream_t ------------------------------ */

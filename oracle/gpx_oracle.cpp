@@ -610,12 +610,13 @@ struct gpxo_engine {
   }
 
   /* PISM.extractExecuteAndCheckpoint :1619-1701 (execution itself is the host app's) */
-  void EEC(Acceptor& A, const PValue& loggedDecision, std::vector<PValue>& out) {
+  void EEC(const Group& g, Acceptor& A, const PValue& loggedDecision, std::vector<PValue>& out) {
     if (A.isStopped()) return;
     PValue nx;
     while (A.putAndRemoveNextExecutable(loggedDecision, &nx)) {
       out.push_back(nx);
       ctr.executed++;
+      if (shouldCheckpoint(g, nx)) ctr.checkpoints_due++;
       if (nx.stop) {
         ctr.stops_executed++;
         break;
@@ -858,9 +859,14 @@ int gpxo_patch(gpxo_engine* e, uint32_t n, const gpx_patch_rec* p) {
 int gpxo_propose(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
                  uint64_t payload_bytes, gpx_accept_rec* out_accepts, uint32_t* n_accepts, uint8_t* out_blob,
                  uint64_t blob_cap, uint64_t* blob_bytes, int32_t* status) {
-  (void)payload_bytes;
+  /* blob layout (same as the device engine): [payload arena, 16-B padded][constructed blobs of
+   * batched slots]; an unbatched slot's blob is the request's own payload (zero copy) */
+  const u64 pal = (payload_bytes + 15) & ~(u64)15;
+  if (pal > blob_cap) return GPX_ERANGE;
+  if (payload_bytes) memcpy(out_blob, payload, payload_bytes);
+  if (pal > payload_bytes) memset(out_blob + payload_bytes, 0, pal - payload_bytes);
   u32 na = 0;
-  u64 bb = 0;
+  u64 bb = pal;
   u32 i = 0;
   while (i < n) {
     u32 gid = reqs[i].gid;
@@ -951,9 +957,7 @@ int gpxo_propose(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const 
       u32 plen;
       if (nreq == 1) {
         plen = reqs[k].payload_len;
-        if (bb + ((plen + 15) & ~15u) > blob_cap) return GPX_ERANGE;
-        memcpy(out_blob + bb, payload + reqs[k].payload_off, plen);
-        if (plen & 15) memset(out_blob + bb + plen, 0, 16 - (plen & 15));
+        boff = reqs[k].payload_off;
       } else {
         u64 total = (u64)nreq * 16;
         for (u32 q = k; q < b; q++) total += reqs[q].payload_len;
@@ -973,8 +977,8 @@ int gpxo_propose(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const 
           w += reqs[q].payload_len;
         }
         if (w & 15) memset(out_blob + w, 0, 16 - (w & 15));
+        bb += ((u64)plen + 15) & ~(u64)15;
       }
-      bb += ((u64)plen + 15) & ~(u64)15;
       gpx_accept_rec& a = out_accepts[na++];
       a.h.gid = gid;
       a.h.slot = acc.slot;
@@ -1099,7 +1103,7 @@ int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accept
          * its placeholder was logged on arrival and replay of {placeholder, accept} is
          * idempotent (DESIGN.md "Deliberate omissions") */
         std::vector<PValue> ex;
-        e->EEC(A, rd, ex);
+        e->EEC(g, A, rd, ex);
         for (auto& x : ex) put_event_exec(extras, e->makeExec(r.h.gid, l, g, x, true));
       }
     }
@@ -1222,13 +1226,12 @@ int gpxo_handle_decisions(gpxo_engine* e, uint32_t n, const gpx_decision_rec* de
       }
       writeImg();
       std::vector<PValue> xs;
-      e->EEC(A, d, xs);
+      e->EEC(g, A, d, xs);
       for (size_t k = 0; k < xs.size(); k++) {
         if (k == 0)
           ex = e->makeExec(r.gid, l, g, xs[k], false);
         else
           extras.push_back(e->makeExec(r.gid, l, g, xs[k], true));
-        if (e->shouldCheckpoint(g, xs[k])) e->ctr.checkpoints_due++;
       }
       if (!A.isStopped() && !d.has_value && jsub(d.slot, A._slot) >= 0 && xs.empty()) A.flags |= GF_NEEDS_SYNC;
     }
@@ -1246,7 +1249,7 @@ int gpxo_round(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const ui
                gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
   u32 L = e->L();
   std::vector<gpx_accept_rec> acc(n);
-  std::vector<uint8_t> blob(payload_bytes + 32ull * n + 64);
+  std::vector<uint8_t> blob(2 * ((payload_bytes + 15) & ~15ull) + 32ull * n + 64);
   u32 na = 0;
   u64 bb = 0;
   int rc = gpxo_propose(e, n, reqs, payload, payload_bytes, acc.data(), &na, blob.data(), blob.size(), &bb, status);
