@@ -330,11 +330,17 @@ def main():
     d_exec = torch.zeros(G * R * 24, dtype=torch.uint8, device=dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     round_dev = lib.fn("round_device")
+    # everything below is issued on ONE explicit stream: the engine launches its kernels on the
+    # stream handed to gpx_round_device and torch.cuda.Event only sees torch's current stream
+    bench_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(bench_stream)
 
     def dev_round(b):
         bufs = DevRoundBufs(d_reqs[b].data_ptr(), d_pay[b].data_ptr(), d_pay[b].numel(), G, d_status.data_ptr(),
                             d_exec.data_ptr())
-        rc = round_dev(eng.handle, C.byref(bufs), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        st = torch.cuda.current_stream().cuda_stream
+        assert st != 0, "bench must run on an explicit stream"
+        rc = round_dev(eng.handle, C.byref(bufs), C.c_void_p(st))
         if rc != 0:
             raise RuntimeError(lib.last_error())
 

@@ -195,7 +195,7 @@ __device__ __forceinline__ gpx_exec_rec make_exec(const DevState& S, uint32_t gi
   r.slot = x.slot;
   r.req_id = x.req_id;
   r.payload_off = x.frame_ref;
-  r.flags = (stop ? GPX_F_STOP : 0u) | (ckpt ? GPX_F_CKPT : 0u) | (extra ? GPX_F_EXTRA : 0u) | (lane << 8) |
+  r.flags = (stop ? GPX_F_STOP : 0u) | (ckpt ? GPX_F_CKPT : 0u) | (extra ? GPX_F_EXTRA : 0u) | (lane << 12) |
             (x.fl & 0xffff0000u);
   return r;
 }

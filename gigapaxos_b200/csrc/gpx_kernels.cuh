@@ -739,7 +739,7 @@ __device__ __forceinline__ void commit_one(const DevState& S, const CommitArgs& 
     vx.slot = slot;
     vx.req_id = 0;
     vx.payload_off = 0;
-    vx.flags = GPX_F_VOID | (l << 8);
+    vx.flags = GPX_F_VOID | (l << 12);
     store_exec(ex, vx);
     int4 img0 = q0, img1 = make_int4(q1.x, (int)(GPX_F_VOID | (dst_mask << 16)), q1.z, q1.w);
     do {

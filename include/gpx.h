@@ -169,7 +169,7 @@ typedef struct gpx_exec_rec {
   int32_t slot;
   int64_t req_id;
   uint32_t payload_off; /* (byte offset of the blob in the lane's log ring) / 16 */
-  uint32_t flags;       /* GPX_F_STOP|VOID|CKPT|EXTRA; bits 8..11 lane; bits 16..31 nreq */
+  uint32_t flags;       /* bits 0..11 GPX_F_STOP|VOID|CKPT|EXTRA; bits 12..15 lane; bits 16..31 nreq */
 } gpx_exec_rec;
 
 /* ---- log ring ---------------------------------------------------------------

@@ -605,7 +605,7 @@ struct gpxo_engine {
     r.req_id = x.req_id;
     r.payload_off = x.frame_ref;
     u32 f = (x.stop ? GPX_F_STOP : 0) | (shouldCheckpoint(g, x) ? GPX_F_CKPT : 0) | (extra ? GPX_F_EXTRA : 0);
-    r.flags = f | (lane << 8) | (x.nreq << 16);
+    r.flags = f | (lane << 12) | (x.nreq << 16);
     return r;
   }
 
@@ -1184,7 +1184,7 @@ int gpxo_handle_decisions(gpxo_engine* e, uint32_t n, const gpx_decision_rec* de
       memset(&ex, 0, sizeof ex);
       ex.gid = r.gid;
       ex.slot = r.slot;
-      ex.flags = GPX_F_VOID | (l << 8);
+      ex.flags = GPX_F_VOID | (l << 12);
       gpx_decision_rec img = r;
       img.flags = GPX_F_VOID;
       auto writeImg = [&]() { memcpy(&e->lanes[l].ring[seg[l] + 64 + (u64)i * 32], &img, 32); };

@@ -107,7 +107,7 @@ def canon(recs: np.ndarray, keys=("gid",)) -> np.ndarray:
 
 
 def exec_by_lane(ex: np.ndarray, n_lanes: int) -> list[np.ndarray]:
-    lanes = (ex["flags"] >> 8) & 0xF
+    lanes = (ex["flags"] >> 12) & 0xF
     out = []
     for l in range(n_lanes):
         e = ex[(lanes == l) & ((ex["flags"] & abi.F_VOID) == 0)]

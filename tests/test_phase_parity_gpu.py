@@ -1,0 +1,39 @@
+"""GPU parity of the per-phase C-ABI calls (gpx_propose / gpx_handle_accepts /
+gpx_handle_accept_replies / gpx_handle_decisions / gpx_patch) against the oracle under
+adversarial schedules: every output record, every state row, every counter and every log byte
+is compared (tests/fuzz.py)."""
+import numpy as np
+import pytest
+
+from fuzz import Fuzzer
+from test_round_parity_gpu import compare_logs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed,R,W", [(1, 3, 8), (2, 3, 8), (3, 5, 8), (4, 3, 4), (5, 5, 2), (6, 3, 1)])
+def test_fuzz_parity(oracle_lib, cuda_lib, seed, R, W):
+    f = Fuzzer([oracle_lib, cuda_lib], G=64, R=R, W=W, seed=seed)
+    decided = f.run(steps=60, check_every=5)
+    assert decided > 50
+    c = f.engines[1].counters()
+    assert c["accepts_nacked"] > 0 and c["placeholders"] > 0
+    compare_logs(f.engines[0], f.engines[1], R)
+    f.close()
+
+
+def test_fuzz_parity_no_faults_many_groups(oracle_lib, cuda_lib):
+    f = Fuzzer([oracle_lib, cuda_lib], G=3000, R=3, W=8, seed=9)
+    decided = f.run(steps=12, rival=False, view_changes=False, stop_prob=0.002, check_every=4)
+    assert decided > 3000
+    f.close()
+
+
+def test_fuzz_parity_gc_modes(oracle_lib, cuda_lib):
+    """GC_MAJORITY_EXECUTED=false (maxCheckpointedSlot = lastCheckpointSlot), LOG_META_DECISIONS=false,
+    ENABLE_JOURNALING=false (accepts stay in memory after execution) and a small CPI."""
+    f = Fuzzer([oracle_lib, cuda_lib], G=64, R=3, W=8, seed=21, gc_majority_executed=0, log_meta_decisions=0,
+               journaling_enabled=0, checkpoint_interval=3)
+    f.run(steps=40, check_every=5)
+    compare_logs(f.engines[0], f.engines[1], 3)
+    f.close()
