@@ -2,15 +2,17 @@
 """bench.py -- Paxos decisions/sec of the B200 engine on BASELINE.json's metric.
 
 A *step* is one full Paxos round over every group of the workload: one client request per
-group enters the RequestBatcher, the coordinator proposes (k_propose), all R co-located
-replicas accept + log (k_accept), the coordinator tallies the replies (k_tally) and all
-replicas commit + emit in-order EXEC records (k_commit).  One step decides one slot per group.
+group enters the RequestBatcher and the coordinator proposes (k_propose); then, per ACCEPT,
+all R co-located replicas accept + log, the coordinator tallies the replies and all replicas
+commit + emit in-order EXEC records (k_act, the fused loopback path; the phase-by-phase kernels
+k_accept / k_tally / k_commit are timed beside it).  One step decides one slot per group.
 
   value  : decisions/s with the request batch already resident in HBM (gpx_round_device)
   e2e    : the same metric through the public C-ABI call gpx_round with HOST buffers
            (pinned), H2D of the requests and D2H of status + EXEC records inside the timing
-  roofline: accept-batch kernel, algorithmic bytes (193+2P per ACCEPT at one acceptor,
-           SURVEY.md 8d) / CUDA-event duration, vs the measured HBM copy peak
+  roofline: the dominant kernel of the timed path (k_act), algorithmic bytes / CUDA-event duration
+           vs the measured HBM copy peak; roofline_accept: the stand-alone accept-batch kernel
+           (193+2P per ACCEPT at one acceptor)
   cpu_baseline: the CPU oracle (a port of the Java path, reference JVM unavailable) on the
            host cores, groups sharded over threads
 
@@ -51,6 +53,14 @@ def b_acc(P: int) -> int:
 
 def b_slot(R: int, P: int) -> int:
     return R * (193 + 2 * P) + R * (64 + 8 * R) + 32 + R * 153
+
+
+def b_act(R: int, P: int) -> int:
+    """Algorithmic bytes per decided slot of the fused k_act kernel with all R replicas co-located
+    (DESIGN.md 4): ACCEPT record 48 + blob P + reply mask 1 + decision record 32; per replica aux 4 +
+    row 16 in + 16 out + window entry 32 in + ACCEPT log image 48 + blob P + DECISION log image 32 +
+    EXEC 24; coordinator row 16+16, proposal entry 16+16, nodeSlots 4R in + 4R out."""
+    return (48 + P + 1 + 32) + R * (4 + 16 + 16 + 32 + 48 + P + 32 + 24) + (64 + 8 * R)
 
 
 def hbm_peak():
@@ -227,10 +237,14 @@ def cpu_decisions_per_sec(G, R, P, budget_s, threads):
 
     workers = [Worker(e, b) for e, b in zip(engines, batches)]
 
+    trunc = lib.fn("log_truncate")
+
     def run_rounds(k):
         def body(w):
-            for _ in range(k):
+            for it in range(k):
                 w.round()
+                if it % 8 == 7:  # the oracle's journal is an in-memory vector: drop it like a drained log
+                    trunc(w.e.handle)
         ts = [threading.Thread(target=body, args=(w,)) for w in workers]
         t0 = time.perf_counter()
         for t in ts:
@@ -241,10 +255,12 @@ def cpu_decisions_per_sec(G, R, P, budget_s, threads):
 
     run_rounds(1)  # warm-up (page faults, allocator)
     t1 = run_rounds(1)
-    k = int(max(1, min(200, budget_s / max(t1, 1e-6))))
-    # the oracle's log is an ever-growing vector: bound the rounds so memory stays small
-    k = min(k, max(1, int(2e9 / max(1, G * (48 + 16 + 32) * R))))
+    k = int(max(1, min(20000, 0.25 * budget_s / max(t1, 1e-6))))
     dt = run_rounds(k)
+    while dt < 0.8 * budget_s and k < 200000:  # the first estimate is cold: extend until the budget is used
+        k2 = int(max(1, min(200000, (budget_s - dt) / max(dt / k, 1e-9))))
+        dt += run_rounds(k2)
+        k += k2
     for e in engines:
         e.close()
     return G * k / dt, k, dt, T
@@ -382,30 +398,52 @@ def main():
     value = world * G * K / (total_ms / 1e3)
 
     # ---- roofline: per-kernel CUDA events inside the engine (same launches, same stream) ----
-    lib.fn("enable_kernel_timing")(eng.handle, C.c_int(1))
-    kt = KernelTimes()
-    lib.fn("get_kernel_times")(eng.handle, C.byref(kt), C.c_int(1))
-    K2 = min(K, 20)
-    for k in range(K2):
-        if not args.no_flush:
-            flush_buf.zero_()
-        dev_round(k % NB)
-    torch.cuda.synchronize()
-    lib.fn("get_kernel_times")(eng.handle, C.byref(kt), C.c_int(1))
-    lib.fn("enable_kernel_timing")(eng.handle, C.c_int(0))
-    acc_ms = kt.accept_ms / max(kt.launches, 1)
+    def kernel_times(fn_name, K2):
+        f = lib.fn(fn_name)
+        lib.fn("enable_kernel_timing")(eng.handle, C.c_int(1))
+        kt = KernelTimes()
+        lib.fn("get_kernel_times")(eng.handle, C.byref(kt), C.c_int(1))
+        for k in range(K2):
+            if not args.no_flush:
+                flush_buf.zero_()
+            b = k % NB
+            bufs = DevRoundBufs(d_reqs[b].data_ptr(), d_pay[b].data_ptr(), d_pay[b].numel(), G, d_status.data_ptr(),
+                                d_exec.data_ptr())
+            rc = f(eng.handle, C.byref(bufs), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc != 0:
+                raise RuntimeError(lib.last_error())
+        torch.cuda.synchronize()
+        lib.fn("get_kernel_times")(eng.handle, C.byref(kt), C.c_int(1))
+        lib.fn("enable_kernel_timing")(eng.handle, C.c_int(0))
+        nl = max(kt.launches, 1)
+        return {"propose": kt.propose_ms / nl, "accept": kt.accept_ms / nl, "tally": kt.tally_ms / nl,
+                "commit": kt.commit_ms / nl}
+
     peak, peak_src = hbm_peak()
-    alg_bytes = G * R * b_acc(P)
-    achieved = alg_bytes / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else 0.0
+    kf = kernel_times("round_device", min(K, 20))          # fused: "accept" is k_act
+    kp = kernel_times("round_device_phases", min(K, 20))   # phase by phase: the standalone kernels
+    act_ms, acc_ms = kf["accept"], kp["accept"]
+    act_bytes = G * b_act(R, P)
+    acc_bytes = G * R * b_acc(P)
     roofline = {
-        "kernel": "k_accept (accept-batch: handleAccept at R acceptors + log append)", "bound": "hbm",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_accept": b_acc(P),
-        "accepts_per_launch": G * R, "kernel_ms": acc_ms,
-        "kernel_ms_all": {"propose": kt.propose_ms / max(kt.launches, 1), "accept": acc_ms,
-                          "tally": kt.tally_ms / max(kt.launches, 1), "commit": kt.commit_ms / max(kt.launches, 1)},
-        "round_frac": (G * b_slot(R, P) / (float(np.median(step_ms)) / 1e3) / 1e9) / peak,
+        "kernel": "k_act (fused accept -> tally -> commit per ACCEPT at R co-located replicas + log append)",
+        "bound": "hbm", "achieved": act_bytes / (act_ms / 1e3) / 1e9 if act_ms > 0 else 0.0, "peak": peak,
+        "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": act_bytes, "bytes_per_decided_slot": b_act(R, P),
+        "decided_slots_per_launch": G, "kernel_ms": act_ms,
+        "kernel_ms_all": {"k_propose+k_build_blobs": kf["propose"], "k_act": act_ms},
     }
+    roofline["frac"] = roofline["achieved"] / peak
+    roofline_accept = {
+        "kernel": "k_accept (stand-alone accept-batch kernel of the phase-by-phase pipeline, north_star kernel)",
+        "bound": "hbm", "achieved": acc_bytes / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else 0.0, "peak": peak,
+        "unit": "GB/s", "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": acc_bytes,
+        "bytes_per_accept": b_acc(P), "accepts_per_launch": G * R, "kernel_ms": acc_ms,
+        "kernel_ms_all": {"k_propose+k_build_blobs": kp["propose"], "k_accept": acc_ms, "k_tally": kp["tally"],
+                          "k_commit": kp["commit"]},
+        "phase_pipeline_decisions_per_sec": G / ((kp["propose"] + acc_ms + kp["tally"] + kp["commit"]) / 1e3),
+    }
+    roofline_accept["frac"] = roofline_accept["achieved"] / peak
 
     # ---- e2e: public C-ABI call with host (pinned) buffers ---------------------------------
     e2e = None
@@ -461,7 +499,8 @@ def main():
             "metric": metric, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": config, "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 5 * K,
+            "roofline_accept": roofline_accept,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 3 * K,
             "p50_decide_latency_ms": float(np.median(step_ms)),
             "requests_per_sec": value, "wall_s_timed_region": t_wall,
         }

@@ -266,7 +266,27 @@ class Engine:
                                                    C.c_uint32(extra_cap), C.byref(nx)))
         return ex[: n * self.n_lanes].copy(), extra[: min(nx.value, extra_cap)].copy()
 
-    def round(self, reqs: np.ndarray, payload: np.ndarray, extra_cap: int = 4096):
+    def handle_accepts_fused(self, accepts: np.ndarray, blob: np.ndarray, extra_cap: int = 4096):
+        accepts = np.ascontiguousarray(accepts, dtype=accept_dtype)
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        if blob.size & 15:
+            blob = np.concatenate([blob, np.zeros(16 - (blob.size & 15), dtype=np.uint8)])
+        n = len(accepts)
+        replies = np.zeros(max(n * self.n_lanes, 1), dtype=reply_dtype)
+        dec = np.zeros(max(n, 1), dtype=decision_dtype)
+        ex = np.zeros(max(n * self.n_lanes, 1), dtype=exec_dtype)
+        extra = np.zeros(max(extra_cap, 1), dtype=exec_dtype)
+        nx = C.c_uint32(0)
+        self.L.check(self.L.fn("handle_accepts_fused")(self._h, C.c_uint32(n), _ptr(accepts), _ptr(blob),
+                                                       C.c_uint64(blob.size), _ptr(replies), _ptr(dec), _ptr(ex),
+                                                       _ptr(extra), C.c_uint32(extra_cap), C.byref(nx)))
+        return (replies[: n * self.n_lanes].copy(), dec[:n].copy(), ex[: n * self.n_lanes].copy(),
+                extra[: min(nx.value, extra_cap)].copy())
+
+    def round_phases(self, reqs: np.ndarray, payload: np.ndarray, extra_cap: int = 4096):
+        return self.round(reqs, payload, extra_cap, fn="round_phases")
+
+    def round(self, reqs: np.ndarray, payload: np.ndarray, extra_cap: int = 4096, fn: str = "round"):
         reqs = np.ascontiguousarray(reqs, dtype=request_dtype)
         payload = np.ascontiguousarray(payload, dtype=np.uint8)
         n = len(reqs)
@@ -274,7 +294,7 @@ class Engine:
         ex = np.zeros(max(n * self.n_lanes, 1), dtype=exec_dtype)
         extra = np.zeros(max(extra_cap, 1), dtype=exec_dtype)
         ns, nx = C.c_uint32(0), C.c_uint32(0)
-        self.L.check(self.L.fn("round")(self._h, C.c_uint32(n), _ptr(reqs), _ptr(payload), C.c_uint64(payload.size),
+        self.L.check(self.L.fn(fn)(self._h, C.c_uint32(n), _ptr(reqs), _ptr(payload), C.c_uint64(payload.size),
                                         _ptr(status), _ptr(ex), C.byref(ns), _ptr(extra), C.c_uint32(extra_cap),
                                         C.byref(nx)))
         return status[:n].copy(), ex[: ns.value].copy(), extra[: min(nx.value, extra_cap)].copy()
@@ -322,11 +342,21 @@ def parse_log(buf: np.ndarray, ring_cap: Optional[int] = None):
             break
         rec = int(hdr["rec_bytes"])
         ns = int(hdr["n_slots"])
+        nv = int(hdr["n_valid"])
         pb = int(hdr["payload_bytes"])
-        dt = accept_dtype if rec == 48 else decision_dtype
-        imgs = buf[off + 64: off + 64 + ns * rec].view(dt)[: int(hdr["n_valid"])]
+        if rec == 48:  # two planes: ns x 32 B pvalue headers, then ns x 16 B extensions
+            imgs = np.zeros(nv, dtype=accept_dtype)
+            hp = buf[off + 64: off + 64 + ns * 32].view(decision_dtype)[:nv]
+            xp = buf[off + 64 + ns * 32: off + 64 + ns * 48].view(
+                np.dtype([("payload_off", "<u4"), ("payload_len", "<u4"), ("nreq", "<u4"), ("sender", "<i4")]))[:nv]
+            for f in decision_dtype.names:
+                imgs[f] = hp[f]
+            for f in xp.dtype.names:
+                imgs[f] = xp[f]
+        else:
+            imgs = buf[off + 64: off + 64 + ns * rec].view(decision_dtype)[:nv]
         pay_off = off + 64 + ns * rec
         payload = buf[pay_off: pay_off + pb]
         out.append((hdr, imgs, payload, pay_off))
-        off = pay_off + ((pb + 15) & ~15)
+        off = (pay_off + ((pb + 15) & ~15) + 31) & ~31
     return out

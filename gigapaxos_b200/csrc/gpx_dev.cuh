@@ -137,6 +137,30 @@ __device__ __forceinline__ void st_stream4(void* p, int4 v) {
                : "memory");
 }
 
+/* 256-bit (one full 32-byte sector) loads / stores: LDG.E.256 / STG.E.256 on sm_100a.  32-byte records
+ * and window entries move in ONE instruction, so every store fills a sector instead of half of one. */
+__device__ __forceinline__ void ld256(const void* p, int4& a, int4& b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void ld256_stream(const void* p, int4& a, int4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const int4 a, const int4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void st256_stream(void* p, const int4 a, const int4 b) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y),
+               "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 /* a pvalue in registers */
 struct DPValue {
   int slot, bnum, bcoord, median_cp;
@@ -215,9 +239,9 @@ __device__ __forceinline__ void store_exec(gpx_exec_rec* dst, const gpx_exec_rec
  * The first execution goes to *primary (if non-null), further ones to the extra queue.
  * `acc_hint` may carry the already loaded accepted entry of d.slot (q0,q1) to skip a reload.
  */
-__device__ __noinline__ void eec(const DevState& S, uint32_t lane, uint32_t gid, int4& row, uint32_t& aux,
-                                 const DPValue& d, gpx_exec_rec* primary, gpx_exec_rec* extra, uint32_t extra_cap,
-                                 uint32_t* n_extra, unsigned int* s_ctr, bool all_extra) {
+__device__ __noinline__ void eec_impl(const DevState& S, uint32_t lane, uint32_t gid, int4& row, uint32_t& aux,
+                                      const DPValue& d, gpx_exec_rec* primary, gpx_exec_rec* extra,
+                                      uint32_t extra_cap, uint32_t* n_extra, unsigned int* s_ctr, bool all_extra) {
   const uint32_t Wm = S.W - 1;
   bool first = true;
   while (true) {
@@ -318,4 +342,16 @@ __device__ __noinline__ void eec(const DevState& S, uint32_t lane, uint32_t gid,
       break;
     }
   }
+}
+
+/* call wrapper: only temporaries have their address taken, so the caller's row/aux stay in registers */
+__device__ __forceinline__ void eec(const DevState& S, uint32_t lane, uint32_t gid, int4& row, uint32_t& aux,
+                                    const DPValue& d, gpx_exec_rec* primary, gpx_exec_rec* extra, uint32_t extra_cap,
+                                    uint32_t* n_extra, unsigned int* s_ctr, bool all_extra) {
+  int4 r = row;
+  uint32_t a = aux;
+  DPValue dd = d;
+  eec_impl(S, lane, gid, r, a, dd, primary, extra, extra_cap, n_extra, s_ctr, all_extra);
+  row = r;
+  aux = a;
 }

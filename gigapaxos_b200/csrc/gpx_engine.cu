@@ -58,6 +58,8 @@ struct gpx_engine {
   int32_t* d_status = nullptr;
   uint32_t* d_copy_tab = nullptr;
   uint32_t* d_copy_dst = nullptr;
+  uint8_t* d_out_mask = nullptr;
+  std::vector<uint8_t> h_out_mask;
   RoundCtl* d_ctl = nullptr;
   RoundCtl* h_ctl = nullptr; /* pinned */
   void* d_misc = nullptr;    /* group-management staging */
@@ -236,6 +238,7 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   TRY(e->dalloc(&e->d_status, N));
   TRY(e->dalloc(&e->d_copy_tab, N));
   TRY(e->dalloc(&e->d_copy_dst, N));
+  TRY(e->dalloc(&e->d_out_mask, N));
   TRY(e->dalloc(&e->d_ctl, (size_t)1));
 #undef TRY
   if (cudaHostAlloc((void**)&e->h_ctl, sizeof(RoundCtl), cudaHostAllocDefault) != cudaSuccess) {
@@ -453,9 +456,24 @@ static int launch_propose(gpx_engine* e, const gpx_request_rec* d_reqs, const ui
   return GPX_OK;
 }
 
-static int launch_accept(gpx_engine* e, const gpx_accept_rec* d_recs, const uint32_t* n_ptr, uint32_t n_max,
-                         const uint8_t* blob0, uint64_t blob0_bytes, const uint8_t* blob1, uint64_t blob1_bytes,
-                         const unsigned long long* blob1_used_ptr, gpx_accept_reply_rec* d_replies, cudaStream_t st) {
+/* kernels are templated on the lane count so that per-lane state stays in registers */
+#define GPX_DISPATCH_L(lanes, KERNEL, grid, st, ...)                                   \
+  switch (lanes) {                                                                     \
+    case 1: KERNEL<1><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                 \
+    case 2: KERNEL<2><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                 \
+    case 3: KERNEL<3><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                 \
+    case 4: KERNEL<4><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                 \
+    case 5: KERNEL<5><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                 \
+    case 6: KERNEL<6><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                 \
+    case 7: KERNEL<7><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                 \
+    default: KERNEL<8><<<grid, GPX_BLOCK, 0, st>>>(__VA_ARGS__); break;                \
+  }
+
+static int launch_accept(gpx_engine* e, bool fused, const gpx_accept_rec* d_recs, const uint32_t* n_ptr,
+                         uint32_t n_max, const uint8_t* blob0, uint64_t blob0_bytes, const uint8_t* blob1,
+                         uint64_t blob1_bytes, const unsigned long long* blob1_used_ptr,
+                         gpx_accept_reply_rec* d_replies, gpx_decision_rec* d_dec, gpx_exec_rec* d_exec,
+                         cudaStream_t st) {
   AcceptArgs A;
   A.recs = d_recs;
   A.n_ptr = n_ptr;
@@ -466,10 +484,18 @@ static int launch_accept(gpx_engine* e, const gpx_accept_rec* d_recs, const uint
   A.blob1_bytes = blob1_bytes;
   A.blob1_used_ptr = blob1_used_ptr;
   A.replies = d_replies;
+  A.decisions = d_dec;
+  A.out_mask = e->d_out_mask;
+  A.exec = d_exec;
   A.extra = e->d_extra;
   A.extra_cap = e->extra_cap;
   A.n_extra = &e->d_ctl->n_extra;
-  k_accept<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
+  const uint32_t grid = cdiv(n_max, GPX_BLOCK);
+  if (fused) {
+    GPX_DISPATCH_L(e->cfg.n_lanes, k_act, grid, st, e->S, A);
+  } else {
+    GPX_DISPATCH_L(e->cfg.n_lanes, k_accept, grid, st, e->S, A);
+  }
   CK(cudaGetLastError());
   return GPX_OK;
 }
@@ -498,7 +524,7 @@ static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uin
   A.extra = e->d_extra;
   A.extra_cap = e->extra_cap;
   A.n_extra = &e->d_ctl->n_extra;
-  k_commit<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
+  GPX_DISPATCH_L(e->cfg.n_lanes, k_commit, cdiv(n_max, GPX_BLOCK), st, e->S, A);
   CK(cudaGetLastError());
   return GPX_OK;
 }
@@ -564,14 +590,15 @@ int gpx_handle_accepts(gpx_engine* e, uint32_t n, const gpx_accept_rec* accepts,
   if (blob_bytes & 15) return fail(GPX_EINVAL, "blob_bytes must be a multiple of 16");
   if (n > e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
   if (blob_bytes > e->blob1_cap) return fail(GPX_ERANGE, "blob too large");
-  int rc = ring_fits(e, 64ull + 48ull * n + blob_bytes);
+  int rc = ring_fits(e, 96ull + 48ull * n + blob_bytes);
   if (rc) return rc;
   cudaStream_t st = e->stream;
   const uint32_t L = e->cfg.n_lanes;
   CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
   CK(cudaMemcpyAsync(e->d_accepts, accepts, n * sizeof(gpx_accept_rec), cudaMemcpyHostToDevice, st));
   if (blob_bytes) CK(cudaMemcpyAsync(e->d_blob1, blob, blob_bytes, cudaMemcpyHostToDevice, st));
-  rc = launch_accept(e, e->d_accepts, nullptr, n, e->d_blob1, blob_bytes, nullptr, 0, nullptr, e->d_replies, st);
+  rc = launch_accept(e, false, e->d_accepts, nullptr, n, e->d_blob1, blob_bytes, nullptr, 0, nullptr, e->d_replies,
+                     nullptr, nullptr, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out_replies, e->d_replies, (size_t)n * L * sizeof(gpx_accept_reply_rec), cudaMemcpyDeviceToHost,
                      st));
@@ -638,8 +665,64 @@ int gpx_handle_decisions(gpx_engine* e, uint32_t n, const gpx_decision_rec* deci
   return GPX_OK;
 }
 
-/* the fused round on device pointers; all inter-replica records stay in HBM */
-static int round_on_stream(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload,
+/* handleAccept + loopback tally + commit per ACCEPT (k_act), host buffers */
+int gpx_handle_accepts_fused(gpx_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
+                             uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_decision_rec* out_decisions,
+                             gpx_exec_rec* out_exec, gpx_exec_rec* out_extra_exec, uint32_t extra_cap,
+                             uint32_t* n_extra) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n_extra) *n_extra = 0;
+  if (n == 0) return GPX_OK;
+  if (!accepts || !out_replies || !out_decisions || !out_exec || (!blob && blob_bytes))
+    return fail(GPX_EINVAL, "null argument");
+  if (blob_bytes & 15) return fail(GPX_EINVAL, "blob_bytes must be a multiple of 16");
+  if (n > e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
+  if (blob_bytes > e->blob1_cap) return fail(GPX_ERANGE, "blob too large");
+  int rc = ring_fits(e, 160ull + 80ull * n + blob_bytes);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  const uint32_t L = e->cfg.n_lanes;
+  CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
+  CK(cudaMemcpyAsync(e->d_accepts, accepts, n * sizeof(gpx_accept_rec), cudaMemcpyHostToDevice, st));
+  if (blob_bytes) CK(cudaMemcpyAsync(e->d_blob1, blob, blob_bytes, cudaMemcpyHostToDevice, st));
+  rc = launch_accept(e, true, e->d_accepts, nullptr, n, e->d_blob1, blob_bytes, nullptr, 0, nullptr, e->d_replies,
+                     e->d_decisions, e->d_exec, st);
+  if (rc) return rc;
+  /* replies consumed by a local coordinator never reach HBM: out_mask says which reply slots were written */
+  e->h_out_mask.resize(n);
+  CK(cudaMemcpyAsync(e->h_out_mask.data(), e->d_out_mask, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  bool any_out = false;
+  for (uint32_t i = 0; i < n; i++) any_out = any_out || e->h_out_mask[i];
+  if (any_out)
+    CK(cudaMemcpyAsync(out_replies, e->d_replies, (size_t)n * L * sizeof(gpx_accept_reply_rec), cudaMemcpyDeviceToHost,
+                       st));
+  CK(cudaMemcpyAsync(out_decisions, e->d_decisions, (size_t)n * sizeof(gpx_decision_rec), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_exec, e->d_exec, (size_t)n * L * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+  rc = fetch_ctl(e);
+  if (rc) return rc;
+  for (uint32_t i = 0; i < n; i++) /* VOID where the reply was consumed locally or never produced */
+    for (uint32_t l = 0; l < L; l++)
+      if (!((e->h_out_mask[i] >> l) & 1u)) {
+        gpx_accept_reply_rec& r = out_replies[(size_t)i * L + l];
+        memset(&r, 0, sizeof r);
+        r.gid = accepts[i].h.gid;
+        r.slot = accepts[i].h.slot;
+        r.who = GPX_WHO(0xffu, 0xffu, GPX_F_VOID);
+      }
+  uint32_t nx = e->h_ctl->n_extra;
+  if (n_extra) *n_extra = nx;
+  uint32_t cp = std::min(std::min(nx, extra_cap), e->extra_cap);
+  if (cp && out_extra_exec) {
+    CK(cudaMemcpyAsync(out_extra_exec, e->d_extra, cp * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return GPX_OK;
+}
+
+/* one round on device pointers.  fused: k_propose -> k_act (replies, decisions and rows stay in registers);
+ * phases: k_propose -> k_accept -> k_tally -> k_commit (inter-replica records go through HBM) */
+static int round_on_stream(gpx_engine* e, bool fused, const gpx_request_rec* d_reqs, const uint8_t* d_payload,
                            uint64_t payload_bytes, uint32_t n, int32_t* d_status, gpx_exec_rec* d_exec,
                            cudaStream_t st) {
   const uint64_t pal = (payload_bytes + 15) & ~15ull;
@@ -651,15 +734,19 @@ static int round_on_stream(gpx_engine* e, const gpx_request_rec* d_reqs, const u
   if (rc) return rc;
   if (tm) cudaEventRecord(e->ev[1], st);
   /* the ACCEPT segment mirrors the payload arena plus the constructed blobs actually used */
-  rc = launch_accept(e, e->d_accepts, &e->d_ctl->n_accepts, n, d_payload, pal, e->d_blob1, 0, &e->d_ctl->blob1_used,
-                     e->d_replies, st);
+  rc = launch_accept(e, fused, e->d_accepts, &e->d_ctl->n_accepts, n, d_payload, pal, e->d_blob1, 0,
+                     &e->d_ctl->blob1_used, e->d_replies, e->d_decisions, d_exec, st);
   if (rc) return rc;
   if (tm) cudaEventRecord(e->ev[2], st);
-  rc = launch_tally(e, e->d_replies, &e->d_ctl->n_accepts, L, n * L, e->d_decisions, st);
-  if (rc) return rc;
+  if (!fused) {
+    rc = launch_tally(e, e->d_replies, &e->d_ctl->n_accepts, L, n * L, e->d_decisions, st);
+    if (rc) return rc;
+  }
   if (tm) cudaEventRecord(e->ev[3], st);
-  rc = launch_commit(e, e->d_decisions, &e->d_ctl->n_decisions, n, d_exec, st);
-  if (rc) return rc;
+  if (!fused) {
+    rc = launch_commit(e, e->d_decisions, &e->d_ctl->n_decisions, n, d_exec, st);
+    if (rc) return rc;
+  }
   if (tm) {
     cudaEventRecord(e->ev[4], st);
     cudaEventSynchronize(e->ev[4]);
@@ -677,9 +764,9 @@ static int round_on_stream(gpx_engine* e, const gpx_request_rec* d_reqs, const u
   return GPX_OK;
 }
 
-int gpx_round(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload, uint64_t payload_bytes,
-              int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots, gpx_exec_rec* out_extra_exec,
-              uint32_t extra_cap, uint32_t* n_extra) {
+static int round_host(gpx_engine* e, bool fused, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                      uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
+                      gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
   if (!e || !n_exec_slots) return fail(GPX_EINVAL, "null argument");
   *n_exec_slots = 0;
   if (n_extra) *n_extra = 0;
@@ -689,26 +776,41 @@ int gpx_round(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint
   if (rc) return rc;
   const uint64_t pal = (payload_bytes + 15) & ~15ull;
   const uint64_t b1 = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
-  rc = ring_fits(e, 64ull + 48ull * n + pal + b1);
+  rc = ring_fits(e, 160ull + 80ull * n + pal + b1);
   if (rc) return rc;
   cudaStream_t st = e->stream;
   const uint32_t L = e->cfg.n_lanes;
   CK(cudaMemcpyAsync(e->d_reqs, reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, st));
   if (payload_bytes) CK(cudaMemcpyAsync(e->d_payload, payload, payload_bytes, cudaMemcpyHostToDevice, st));
-  rc = round_on_stream(e, e->d_reqs, e->d_payload, payload_bytes, n, e->d_status, e->d_exec, st);
+  rc = round_on_stream(e, fused, e->d_reqs, e->d_payload, payload_bytes, n, e->d_status, e->d_exec, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(status, e->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   rc = fetch_ctl(e);
   if (rc) return rc;
-  const uint32_t nd = e->h_ctl->n_decisions, nx = e->h_ctl->n_extra;
-  if (nd) CK(cudaMemcpyAsync(out_exec, e->d_exec, (size_t)nd * L * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
+  /* fused: one EXEC row per ACCEPT; phases: one per DECISION */
+  const uint32_t rows = fused ? e->h_ctl->n_accepts : e->h_ctl->n_decisions;
+  const uint32_t nx = e->h_ctl->n_extra;
+  if (rows) CK(cudaMemcpyAsync(out_exec, e->d_exec, (size_t)rows * L * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
   uint32_t cp = std::min(std::min(nx, extra_cap), e->extra_cap);
   if (cp && out_extra_exec)
     CK(cudaMemcpyAsync(out_extra_exec, e->d_extra, cp * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  *n_exec_slots = nd * L;
+  *n_exec_slots = rows * L;
   if (n_extra) *n_extra = nx;
   return GPX_OK;
+}
+
+int gpx_round(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload, uint64_t payload_bytes,
+              int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots, gpx_exec_rec* out_extra_exec,
+              uint32_t extra_cap, uint32_t* n_extra) {
+  return round_host(e, true, n, reqs, payload, payload_bytes, status, out_exec, n_exec_slots, out_extra_exec,
+                    extra_cap, n_extra);
+}
+int gpx_round_phases(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                     uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
+                     gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  return round_host(e, false, n, reqs, payload, payload_bytes, status, out_exec, n_exec_slots, out_extra_exec,
+                    extra_cap, n_extra);
 }
 
 int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream) {
@@ -716,7 +818,15 @@ int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream) {
   if (b->n == 0) return GPX_OK;
   int rc = check_batch(e, b->n, b->payload_bytes);
   if (rc) return rc;
-  return round_on_stream(e, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
+  return round_on_stream(e, true, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
+                         stream ? (cudaStream_t)stream : e->stream);
+}
+int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream) {
+  if (!e || !b) return fail(GPX_EINVAL, "null argument");
+  if (b->n == 0) return GPX_OK;
+  int rc = check_batch(e, b->n, b->payload_bytes);
+  if (rc) return rc;
+  return round_on_stream(e, false, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
                          stream ? (cudaStream_t)stream : e->stream);
 }
 

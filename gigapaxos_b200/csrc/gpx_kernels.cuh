@@ -9,14 +9,20 @@
  *   k_commit   PISM.handleBatchedCommit (:1480-1528) / handleCommittedRequest (:1432-1478) /
  *              extractExecuteAndCheckpoint (:1619-1701)
  *
+ *   k_act      accept -> tally -> commit fused per ACCEPT for co-located replicas: the reference's
+ *              loopback path (PaxosManager.sendOrLoopback :2116-2128) with every inter-replica
+ *              record kept in registers instead of HBM
+ *
  * Work mapping: one thread per record; records of one group are adjacent in every stream
  * ("grouped by gid"), and the thread of the first record of a run processes the whole run
  * in order, which reproduces the per-instance `synchronized` of the reference
  * (PaxosAcceptor.java:302,325; PaxosCoordinator.java:210).  Different groups never share
- * state, so runs are independent.  All traffic is 128-bit: 48-byte ACCEPTs are 3 x LDG.128,
- * rows are one LDG.128, window entries two.  Fixed-position outputs (reply i*L+lane, log
- * image i, exec i*L+lane) need no atomics; variable outputs (ACCEPTs, DECISIONs) are
- * compacted with one atomic per block.
+ * state, so runs are independent.  Kernels are templated on the number of lanes so the
+ * per-lane state of a record lives in registers and all of its independent loads
+ * (L x {aux, row, window entry}) are issued before the first use.  32-byte records and window
+ * entries move with ONE 256-bit LDG/STG (a full sector per thread per instruction), rows with
+ * 128-bit ones.  Fixed-position outputs (reply i*L+lane, log image i, exec i*L+lane) need no
+ * atomics; variable outputs (ACCEPTs, DECISIONs) are compacted with one atomic per block.
  */
 #pragma once
 #include "gpx_dev.cuh"
@@ -67,11 +73,14 @@ __device__ __forceinline__ void flush_counters(const DevState& S, unsigned int* 
   }
 }
 
+__device__ __forceinline__ bool st_usable(uint32_t aux) {
+  uint32_t st = GPX_AUX_STATE(aux);
+  return st == GPX_ST_ACTIVE_1 || st == GPX_ST_ACTIVE_2;
+}
 __device__ __forceinline__ bool usable(const DevState& S, uint32_t gid, uint32_t lane, uint32_t* aux_out) {
   uint32_t aux = S.acc_aux[row_idx(S, lane, gid)];
   *aux_out = aux;
-  uint32_t st = GPX_AUX_STATE(aux);
-  return st == GPX_ST_ACTIVE_1 || st == GPX_ST_ACTIVE_2;
+  return st_usable(aux);
 }
 
 /* ============================== k_propose ===================================== */
@@ -165,19 +174,17 @@ __device__ __noinline__ void propose_run(const DevState& S, const ProposeArgs& A
       uint32_t b = batch_end(S, reqs, A.n, k, gid);
       if (b > run_end) b = run_end;
       uint32_t nreq = b - k;
-      /* PCS.propose :235-239 refuse after a STOP that is still outstanding */
-      {
+      const uint32_t w = (uint32_t)crow.z & Wm;
+      if (((unsigned)crow.w >> 8) != 0) { /* proposals outstanding: only then can the window refuse */
+        /* PCS.propose :235-239 refuse after a STOP that is still outstanding */
         int prev = (int)((unsigned)crow.z - 1u);
         int4 pe = S.prop_win[win_idx(S, clane, (uint32_t)prev & Wm, gid)];
         if (((unsigned)pe.y & GPX_PV_PRESENT) && pe.x == prev && ((unsigned)pe.y & GPX_PV_STOP)) {
           code = GPX_RS_REFUSED_STOP;
           break;
         }
-      }
-      uint32_t w = (uint32_t)crow.z & Wm;
-      {
-        int4 pe = S.prop_win[win_idx(S, clane, w, gid)];
-        if ((unsigned)pe.y & GPX_PV_PRESENT) { /* window full: W proposals in flight */
+        int4 pw = S.prop_win[win_idx(S, clane, w, gid)];
+        if ((unsigned)pw.y & GPX_PV_PRESENT) { /* window full: W proposals in flight */
           code = GPX_RS_BACKPRESSURE;
           break;
         }
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_build_blobs(const __grid_constant
   for (uint32_t b = 0; b < r.payload_len; b++) d[b] = s[b];
 }
 
-/* ============================== k_accept ====================================== */
+/* ============================== shared per-lane steps ============================== */
 struct AcceptArgs {
   const gpx_accept_rec* recs;
   const uint32_t* n_ptr; /* device count, or null */
@@ -321,7 +328,10 @@ struct AcceptArgs {
   const uint8_t* blob1; /* constructed blobs: offsets [blob0_bytes, blob0_bytes+blob1_bytes) */
   unsigned long long blob1_bytes;
   const unsigned long long* blob1_used_ptr; /* device: bytes of blob1 actually used (overrides blob1_bytes) */
-  gpx_accept_reply_rec* replies; /* [n_max][L] */
+  gpx_accept_reply_rec* replies;            /* [n_max][L] */
+  gpx_decision_rec* decisions;              /* k_act: [n_max], fixed position */
+  uint8_t* out_mask;                        /* k_act: [n_max] lanes whose reply was NOT consumed locally (written) */
+  gpx_exec_rec* exec;                       /* k_act: [n_max][L] */
   gpx_exec_rec* extra;
   uint32_t extra_cap;
   uint32_t* n_extra;
@@ -331,165 +341,356 @@ __device__ __forceinline__ const uint8_t* blob_ptr(const AcceptArgs& A, unsigned
   return off < A.blob0_bytes ? A.blob0 + off : A.blob1 + (off - A.blob0_bytes);
 }
 
-/* one ACCEPT at every addressed lane; returns the mask of lanes that log it */
-__device__ __forceinline__ uint32_t accept_one(const DevState& S, const AcceptArgs& A, const int4 q0, const int4 q1,
-                                               const int4 q2, uint32_t j, const unsigned long long* segb,
-                                               unsigned long long pay_rel, unsigned int* s_ctr) {
-  const uint32_t gid = (uint32_t)q0.x;
-  const int slot = q0.y, bnum = q0.z, bcoord = q0.w;
-  const int median_cp = q1.x;
-  const uint32_t fl_dm = (uint32_t)q1.y; /* flags | dst_mask<<16 */
-  const uint32_t rflags = fl_dm & 0xffffu, dst_mask = fl_dm >> 16;
-  const uint32_t payload_off = (uint32_t)q2.x, plen = (uint32_t)q2.y, nreq = (uint32_t)q2.z;
-  const int sender = q2.w;
-  const uint32_t Wm = S.W - 1;
-  uint32_t logmask = 0;
-  uint32_t meta = 0;
-  const MsetInfo* ms = nullptr;
-  bool gid_ok = gid < S.G;
-  if (gid_ok) {
-    meta = S.grp_meta[gid];
-    ms = &S.msets[meta & 0xffffu];
-  }
-  const bool live = gid_ok && (meta & GPX_META_LIVE);
-  uint32_t dstIdx = 0xffu;
-  if (live) {
-    const uint32_t R = (meta >> 16) & 0xffu;
-    for (uint32_t m = 0; m < R; m++)
-      if (ms->nodes[m] == sender) dstIdx = m;
-  }
-  for (uint32_t l = 0; l < S.L; l++) {
-    /* default: VOID reply, VOID image */
-    int4 rep0 = make_int4((int)gid, slot, 0, 0);
-    int4 rep1 = make_int4(0, (int)GPX_WHO(0xffu, 0xffu, GPX_F_VOID), 0, 0);
-    uint32_t img_flags = GPX_F_VOID, img_dm = dst_mask;
-    do {
-      if (!((dst_mask >> l) & 1u) || (rflags & GPX_F_VOID)) break;
-      uint32_t aux;
-      if (!live || !usable(S, gid, l, &aux)) { /* PISM :456-460 */
-        atomicAdd(&s_ctr[C_ACCEPTS_DROPPED], 1u);
-        break;
-      }
-      const uint32_t myIdx = ms->idx_of_lane[l];
-      if (myIdx == 0xffu) {
-        atomicAdd(&s_ctr[C_ACCEPTS_DROPPED], 1u);
-        break;
-      }
-      const size_t ri = row_idx(S, l, gid);
-      int4 row = S.acc_row[ri];
-      if (jsub(slot, row.x) >= (int)S.W) { /* beyond the in-flight window: drop + flag for the host */
-        S.acc_aux[ri] = aux | (GPX_GF_OVERFLOW << 24);
-        atomicAdd(&s_ctr[C_WINDOW_OVERFLOW], 1u);
-        atomicAdd(&s_ctr[C_ACCEPTS_DROPPED], 1u);
-        break;
-      }
-      atomicAdd(&s_ctr[C_ACCEPTS_HANDLED], 1u);
-      const int4 row_in = row;
-      /* prev = paxosState.getAccept(slot) :1123 */
-      const size_t ai = 2 * win_idx(S, l, (uint32_t)slot & Wm, gid);
-      const int4 e0 = S.acc_win[ai], e1 = S.acc_win[ai + 1];
-      const bool ent_alive = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, row.w) > 0;
-      const bool hasPrev = ent_alive && e0.x == slot;
-      unsigned frame_ref = (unsigned)(((segb[l] + pay_rel + payload_off) & (S.ring_cap - 1)) >> 4);
-      if (hasPrev && e0.y == bnum && e0.z == bcoord) frame_ref = (unsigned)e0.w; /* duplicate keeps its frame */
-      /* acceptAndUpdateBallot :302-322 */
-      bool store = false;
-      if (bcmp(bnum, bcoord, row.y, row.z) >= 0) {
-        row.y = bnum;
-        row.z = bcoord;
-        if (jsub(slot, row.w) > 0) {
-          store = true;
-          if (ent_alive && e0.x != slot) { /* ring conflict: never evict a live entry for a stale accept */
-            bool staleNew = jsub(slot, row.x) < 0, occStale = jsub(e0.x, row.x) < 0;
-            if (staleNew && !occStale) store = false;
-          }
-        }
-      }
-      gc_step(row, median_cp); /* :320 */
-      /* AcceptReplyPacket :1139-1143 */
-      int max_cp = row.x - 1;
-      if (!S.gc_majority_executed) {
-        int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
-        int s1 = row.x - 1;
-        int lcp = s1 - s1 % cpi;
-        if (lcp < 0) {
-          lcp = jsub(lcp, cpi);
-          if (lcp > 0) lcp = 2147483647 - 2147483647 % cpi;
-        }
-        max_cp = lcp;
-      }
-      /* toLog :1146-1149 */
-      const bool toLog = bcmp(bnum, bcoord, row.y, row.z) >= 0 && jsub(slot, row.w) > 0 &&
-                         (!hasPrev || bcmp(e0.y, e0.z, bnum, bcoord) < 0);
-      const bool nack = bcmp(row.y, row.z, bnum, bcoord) > 0;
-      rep0 = make_int4((int)gid, slot, row.y, row.z);
-      rep1 = make_int4(max_cp, (int)GPX_WHO(myIdx, dstIdx, (toLog ? GPX_F_LOGGED : 0u) | (nack ? GPX_F_NACK : 0u)),
-                       q1.z, q1.w);
-      atomicAdd(&s_ctr[nack ? C_ACCEPTS_NACKED : C_ACCEPTS_ACKED], 1u);
-      if (toLog) {
-        atomicAdd(&s_ctr[C_ACCEPTS_LOGGED], 1u);
-        logmask |= 1u << l;
-        img_flags = rflags;
-        img_dm = 1u << l;
-      }
-      if (store) {
-        S.acc_win[ai] = make_int4(slot, bnum, bcoord, (int)frame_ref);
-        S.acc_win[ai + 1] = make_int4(q1.z, q1.w, (int)plen,
-                                      (int)(GPX_ENT_VALID | ((rflags & GPX_F_STOP) ? GPX_ENT_STOP : 0u) | (nreq << 16)));
-      }
-      /* reconstructDecision(slot) -> handleCommittedRequest :1158-1161 (rare: a commit overtook its accept) */
-      const int dslot = jsub(slot, row.x);
-      if (dslot >= 0 && dslot < (int)S.W && ((GPX_AUX_PRESENT(aux) >> ((uint32_t)slot & Wm)) & 1u)) {
-        const uint32_t w = (uint32_t)slot & Wm;
-        const size_t ci = 2 * win_idx(S, l, w, gid);
-        const int4 c0 = S.com_win[ci], c1 = S.com_win[ci + 1];
-        DPValue d;
-        bool ok = false;
-        if ((GPX_AUX_VALUED(aux) >> w) & 1u) {
-          d.slot = slot;
-          d.bnum = c0.x;
-          d.bcoord = c0.y;
-          d.median_cp = c0.z;
-          d.frame_ref = (unsigned)c0.w;
-          d.req_id = ((long long)c1.y << 32) | (unsigned)c1.x;
-          d.plen = (unsigned)c1.z;
-          d.fl = (unsigned)c1.w;
-          d.valued = true;
-          ok = true;
-        } else {
-          const int4 n0 = S.acc_win[ai], n1 = S.acc_win[ai + 1];
-          const bool alive = ((unsigned)n1.w & GPX_ENT_VALID) && jsub(n0.x, row.w) > 0 && n0.x == slot;
-          if (alive && n0.y == c0.x && n0.z == c0.y) {
-            d.slot = slot;
-            d.bnum = n0.y;
-            d.bcoord = n0.z;
-            d.median_cp = c0.z;
-            d.frame_ref = (unsigned)n0.w;
-            d.req_id = ((long long)n1.y << 32) | (unsigned)n1.x;
-            d.plen = (unsigned)n1.z;
-            d.fl = (unsigned)n1.w;
-            d.valued = true;
-            ok = true;
-          }
-        }
-        if (ok) eec(S, l, gid, row, aux, d, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
-        S.acc_aux[ri] = aux;
-      }
-      if (row.x != row_in.x || row.y != row_in.y || row.z != row_in.z || row.w != row_in.w) S.acc_row[ri] = row;
-    } while (false);
-    /* reply (fixed position) */
-    int4* rp = reinterpret_cast<int4*>(&A.replies[(size_t)j * S.L + l]);
-    st_stream4(rp, rep0);
-    st_stream4(rp + 1, rep1);
-    /* log image (fixed position in this launch's ACCEPT segment of lane l) */
-    int4* ip = reinterpret_cast<int4*>(ring_ptr(S, l, segb[l] + 64 + (unsigned long long)j * 48));
-    st_stream4(ip, q0);
-    st_stream4(ip + 1, make_int4(q1.x, (int)(img_flags | (img_dm << 16)), q1.z, q1.w));
-    st_stream4(ip + 2, q2);
-  }
-  return logmask;
+/* per-lane state of one record, kept in registers across accept -> tally -> commit */
+#define LS_HANDLED 1u   /* the acceptor processed the ACCEPT (row/aux may have changed) */
+#define LS_STORE 2u     /* the accepted window entry still has to be written */
+#define LS_LOGGED 4u    /* toLog: image + blob go to the log ring */
+#define LS_RARE 8u      /* reconstructDecision path ran: window memory was touched */
+#define LS_OCCVALID 16u /* the ring position held an entry with its valid bit set */
+#define LS_ROWDIRTY 32u
+#define LS_AUXDIRTY 64u
+struct LaneSt {
+  int4 row;
+  uint32_t aux;
+  int rbn, rbc, rmaxcp; /* ACCEPT_REPLY: acceptor ballot after the accept, maxCheckpointedSlot */
+  uint32_t rwho;
+  uint32_t frame_ref;
+  uint32_t fl;
+  uint32_t img_flags; /* flags | dst_mask<<16 of the ACCEPT log image */
+};
+
+__device__ __forceinline__ void make_entry(const int4 q0, const int4 q1, const int4 q2, uint32_t frame_ref, int4& n0,
+                                           int4& n1) {
+  const uint32_t rflags = (uint32_t)q1.y & 0xffffu;
+  n0 = make_int4(q0.y, q0.z, q0.w, (int)frame_ref);
+  n1 = make_int4(q1.z, q1.w, q2.y,
+                 (int)(GPX_ENT_VALID | ((rflags & GPX_F_STOP) ? GPX_ENT_STOP : 0u) | ((uint32_t)q2.z << 16)));
 }
 
+/* PISM.handleAccept :1080-1166 for one ACCEPT at one lane, on register-resident state.  (e0,e1) is the
+ * window entry at slot mod W as loaded.  The caller writes row/aux/entry back; if a commit had overtaken
+ * this ACCEPT the reconstructDecision path runs here (rare) after the entry has been stored. */
+__device__ __forceinline__ void accept_lane(const DevState& S, const AcceptArgs& A, uint32_t l, bool live,
+                                            const MsetInfo* ms, uint32_t dstIdx, const int4 q0, const int4 q1,
+                                            const int4 q2, const int4 e0, const int4 e1, unsigned frame_ref_new,
+                                            LaneSt& st, unsigned int* s_ctr) {
+  const uint32_t gid = (uint32_t)q0.x;
+  const int slot = q0.y, bnum = q0.z, bcoord = q0.w, median_cp = q1.x;
+  const uint32_t rflags = (uint32_t)q1.y & 0xffffu, dst_mask = (uint32_t)q1.y >> 16;
+  const uint32_t Wm = S.W - 1;
+  st.rbn = 0;
+  st.rbc = 0;
+  st.rmaxcp = 0;
+  st.rwho = GPX_WHO(0xffu, 0xffu, GPX_F_VOID);
+  st.img_flags = GPX_F_VOID | (dst_mask << 16);
+  st.frame_ref = frame_ref_new;
+  st.fl = ((unsigned)e1.w & GPX_ENT_VALID) ? LS_OCCVALID : 0u;
+  if (!((dst_mask >> l) & 1u) || (rflags & GPX_F_VOID)) return;
+  if (!live || !st_usable(st.aux)) { /* PISM :456-460 */
+    atomicAdd(&s_ctr[C_ACCEPTS_DROPPED], 1u);
+    return;
+  }
+  const uint32_t myIdx = ms->idx_of_lane[l];
+  if (myIdx == 0xffu) {
+    atomicAdd(&s_ctr[C_ACCEPTS_DROPPED], 1u);
+    return;
+  }
+  int4& row = st.row;
+  if (jsub(slot, row.x) >= (int)S.W) { /* beyond the in-flight window: drop + flag for the host */
+    st.aux |= (GPX_GF_OVERFLOW << 24);
+    st.fl |= LS_AUXDIRTY;
+    atomicAdd(&s_ctr[C_WINDOW_OVERFLOW], 1u);
+    atomicAdd(&s_ctr[C_ACCEPTS_DROPPED], 1u);
+    return;
+  }
+  st.fl |= LS_HANDLED;
+  atomicAdd(&s_ctr[C_ACCEPTS_HANDLED], 1u);
+  const int4 row_in = row;
+  /* prev = paxosState.getAccept(slot) :1123 */
+  const bool ent_alive = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, row.w) > 0;
+  const bool hasPrev = ent_alive && e0.x == slot;
+  if (hasPrev && e0.y == bnum && e0.z == bcoord) st.frame_ref = (unsigned)e0.w; /* duplicate keeps its frame */
+  /* acceptAndUpdateBallot :302-322 */
+  bool store = false;
+  if (bcmp(bnum, bcoord, row.y, row.z) >= 0) {
+    row.y = bnum;
+    row.z = bcoord;
+    if (jsub(slot, row.w) > 0) {
+      store = true;
+      if (ent_alive && e0.x != slot) { /* ring conflict: never evict a live entry for a stale accept */
+        bool staleNew = jsub(slot, row.x) < 0, occStale = jsub(e0.x, row.x) < 0;
+        if (staleNew && !occStale) store = false;
+      }
+    }
+  }
+  gc_step(row, median_cp); /* :320 */
+  /* AcceptReplyPacket :1139-1143 */
+  int max_cp = row.x - 1;
+  if (!S.gc_majority_executed) {
+    int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
+    int s1 = row.x - 1;
+    int lcp = s1 - s1 % cpi;
+    if (lcp < 0) {
+      lcp = jsub(lcp, cpi);
+      if (lcp > 0) lcp = 2147483647 - 2147483647 % cpi;
+    }
+    max_cp = lcp;
+  }
+  /* toLog :1146-1149 */
+  const bool toLog = bcmp(bnum, bcoord, row.y, row.z) >= 0 && jsub(slot, row.w) > 0 &&
+                     (!hasPrev || bcmp(e0.y, e0.z, bnum, bcoord) < 0);
+  const bool nack = bcmp(row.y, row.z, bnum, bcoord) > 0;
+  st.rbn = row.y;
+  st.rbc = row.z;
+  st.rmaxcp = max_cp;
+  st.rwho = GPX_WHO(myIdx, dstIdx, (toLog ? GPX_F_LOGGED : 0u) | (nack ? GPX_F_NACK : 0u));
+  atomicAdd(&s_ctr[nack ? C_ACCEPTS_NACKED : C_ACCEPTS_ACKED], 1u);
+  if (toLog) {
+    atomicAdd(&s_ctr[C_ACCEPTS_LOGGED], 1u);
+    st.fl |= LS_LOGGED;
+    st.img_flags = rflags | ((1u << l) << 16);
+  }
+  if (store) st.fl |= LS_STORE;
+  /* reconstructDecision(slot) -> handleCommittedRequest :1158-1161 (rare: a commit overtook its accept) */
+  const int dslot = jsub(slot, row.x);
+  if (dslot >= 0 && dslot < (int)S.W && ((GPX_AUX_PRESENT(st.aux) >> ((uint32_t)slot & Wm)) & 1u)) {
+    const uint32_t w = (uint32_t)slot & Wm;
+    const size_t ai = 2 * win_idx(S, l, w, gid);
+    st.fl |= LS_RARE;
+    if (store) { /* the entry must be visible to the commit path */
+      int4 n0, n1;
+      make_entry(q0, q1, q2, st.frame_ref, n0, n1);
+      st256(&S.acc_win[ai], n0, n1);
+      st.fl &= ~LS_STORE;
+    }
+    int4 c0, c1;
+    ld256(&S.com_win[ai], c0, c1);
+    DPValue d;
+    bool ok = false;
+    if ((GPX_AUX_VALUED(st.aux) >> w) & 1u) {
+      d.slot = slot;
+      d.bnum = c0.x;
+      d.bcoord = c0.y;
+      d.median_cp = c0.z;
+      d.frame_ref = (unsigned)c0.w;
+      d.req_id = ((long long)c1.y << 32) | (unsigned)c1.x;
+      d.plen = (unsigned)c1.z;
+      d.fl = (unsigned)c1.w;
+      d.valued = true;
+      ok = true;
+    } else {
+      int4 n0, n1;
+      ld256(&S.acc_win[ai], n0, n1);
+      const bool alive = ((unsigned)n1.w & GPX_ENT_VALID) && jsub(n0.x, row.w) > 0 && n0.x == slot;
+      if (alive && n0.y == c0.x && n0.z == c0.y) {
+        d.slot = slot;
+        d.bnum = n0.y;
+        d.bcoord = n0.z;
+        d.median_cp = c0.z;
+        d.frame_ref = (unsigned)n0.w;
+        d.req_id = ((long long)n1.y << 32) | (unsigned)n1.x;
+        d.plen = (unsigned)n1.z;
+        d.fl = (unsigned)n1.w;
+        d.valued = true;
+        ok = true;
+      }
+    }
+    const uint32_t aux_b = st.aux;
+    if (ok) eec(S, l, gid, row, st.aux, d, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
+    if (st.aux != aux_b) st.fl |= LS_AUXDIRTY;
+  }
+  if (row.x != row_in.x || row.y != row_in.y || row.z != row_in.z || row.w != row_in.w) st.fl |= LS_ROWDIRTY;
+}
+
+/* PISM.handleAcceptReply :1248-1365 for one reply at the coordinator lane `cl` (row cached in `crow`) */
+__device__ __forceinline__ bool tally_reply(const DevState& S, uint32_t cl, uint32_t gid, uint32_t R,
+                                            const MsetInfo* ms, int4& crow, bool& dirty, int slot, int rb, int rc,
+                                            int max_cp, uint32_t accIdx, gpx_decision_rec& d, unsigned int* s_ctr) {
+  const uint32_t Wm = S.W - 1;
+  bool decided = false;
+  atomicAdd(&s_ctr[C_REPLIES_HANDLED], 1u);
+  const uint32_t cf = (unsigned)crow.w & 0xffu;
+  if ((cf & GPX_CF_EXISTS) && (cf & GPX_CF_ACTIVE)) { /* PaxosCoordinator.handleAcceptReply :212 */
+    const int c = bcmp(rb, rc, crow.x, crow.y);
+    const size_t pi = win_idx(S, cl, (uint32_t)slot & Wm, gid);
+    if (c > 0) { /* handleAcceptReplyHigherBallot :661-675 */
+      int4 pe = S.prop_win[pi];
+      if (((unsigned)pe.y & GPX_PV_PRESENT) && pe.x == slot) {
+        pe.y = (int)((unsigned)pe.y & ~GPX_PV_PRESENT);
+        S.prop_win[pi] = pe;
+        crow.w = (int)((unsigned)crow.w - (1u << 8));
+        dirty = true;
+        atomicAdd(&s_ctr[C_PREEMPTED], 1u);
+      }
+    } else if (c == 0) { /* handleAcceptReplyMyBallot :597-640 */
+      if (accIdx < R) {  /* recordSlotNumber :809-825 (plain <) */
+        const size_t ni = ns_idx(S, cl, accIdx, gid);
+        if (S.node_slots[ni] < max_cp) S.node_slots[ni] = max_cp;
+      }
+      int4 pe = S.prop_win[pi];
+      if (((unsigned)pe.y & GPX_PV_PRESENT) && pe.x == slot) {
+        uint32_t vf = (unsigned)pe.y;
+        if (accIdx < R) vf |= (1u << accIdx);      /* WaitforUtility.updateHeardFrom :51-62 */
+        if (__popc(vf & 0xffffu) > (int)(R / 2)) { /* heardFromMajority :64-68 */
+          d.gid = gid;
+          d.slot = slot;
+          d.bnum = crow.x;
+          d.bcoord = crow.y;
+          d.median_cp = median_minus(S, cl, gid, R); /* makeDecision(getMajorityCommittedSlot()) :630 */
+          d.flags = (uint16_t)(GPX_F_DECISION | ((vf & GPX_PV_STOP) ? GPX_F_STOP : 0u));
+          d.dst_mask = ms->lane_mask;
+          d.req_id = ((long long)pe.w << 32) | (unsigned)pe.z;
+          decided = true;
+          pe.y = (int)(vf & ~GPX_PV_PRESENT);
+          crow.w = (int)((unsigned)crow.w - (1u << 8));
+          dirty = true;
+          atomicAdd(&s_ctr[C_DECISIONS_MADE], 1u);
+        } else
+          pe.y = (int)vf;
+        S.prop_win[pi] = pe;
+      }
+    }
+  }
+  /* nullifyCoordinatorIfPreemptedFully :1353-1356 */
+  if ((((unsigned)crow.w) & GPX_CF_EXISTS) && bcmp(rb, rc, crow.x, crow.y) > 0 && (((unsigned)crow.w) >> 8) == 0) {
+    crow = make_int4(0, 0, 0, 0);
+    dirty = true;
+    atomicAdd(&s_ctr[C_COORD_RESIGNED], 1u);
+  }
+  return decided;
+}
+
+/* PISM.handleBatchedCommit :1480-1528 (one slot) at one lane on register-resident row/aux; (a0,a1) is the
+ * accepted window entry at slot mod W as currently in memory.  Produces the log image. */
+__device__ __forceinline__ void commit_lane(const DevState& S, uint32_t l, uint32_t gid, int slot, int bnum,
+                                            int bcoord, int median_cp, int4& row, uint32_t& aux, const int4 a0,
+                                            const int4 a1, gpx_exec_rec* ex, gpx_exec_rec* extra, uint32_t extra_cap,
+                                            uint32_t* n_extra, int4& img0, int4& img1, unsigned int* s_ctr) {
+  if (jsub(slot, row.x) >= (int)S.W) {
+    aux |= ((GPX_GF_OVERFLOW | GPX_GF_NEEDS_SYNC) << 24);
+    atomicAdd(&s_ctr[C_WINDOW_OVERFLOW], 1u);
+    atomicAdd(&s_ctr[C_DECISIONS_DROPPED], 1u);
+    return;
+  }
+  atomicAdd(&s_ctr[C_DECISIONS_HANDLED], 1u);
+  const bool a_alive = ((unsigned)a1.w & GPX_ENT_VALID) && jsub(a0.x, row.w) > 0 && a0.x == slot;
+  DPValue d;
+  d.slot = slot;
+  d.bnum = bnum;
+  d.bcoord = bcoord;
+  d.median_cp = median_cp;
+  if (a_alive && a0.y == bnum && a0.z == bcoord) { /* :1488 decision := the accept we hold */
+    d.req_id = ((long long)a1.y << 32) | (unsigned)a1.x;
+    d.frame_ref = (unsigned)a0.w;
+    d.plen = (unsigned)a1.z;
+    d.fl = (unsigned)a1.w & ~GPX_ENT_VALID;
+    d.valued = true;
+  } else { /* placeholder :1514-1522 */
+    d.req_id = 0;
+    d.frame_ref = 0;
+    d.plen = 0;
+    d.fl = 0;
+    d.valued = false;
+    atomicAdd(&s_ctr[C_PLACEHOLDERS], 1u);
+  }
+  /* logDecision :1446-1466 */
+  if (d.valued || S.log_meta) {
+    const bool meta = S.log_meta && a_alive && bcmp(a0.y, a0.z, d.bnum, d.bcoord) >= 0;
+    const uint32_t lf = GPX_F_DECISION | (meta ? GPX_F_META : 0u) | ((d.fl & GPX_ENT_STOP) ? GPX_F_STOP : 0u);
+    img0 = make_int4((int)gid, slot, d.bnum, d.bcoord);
+    img1 = make_int4(meta ? -1 : d.median_cp, (int)(lf | ((1u << l) << 16)), (int)(unsigned)(d.req_id & 0xffffffffll),
+                     (int)(d.req_id >> 32));
+  }
+  const int slot_before = row.x;
+  eec(S, l, gid, row, aux, d, ex, extra, extra_cap, n_extra, s_ctr, false);
+  if (GPX_AUX_STATE(aux) != GPX_ST_STOPPED && !d.valued && jsub(slot, row.x) >= 0 && row.x == slot_before)
+    aux |= (GPX_GF_NEEDS_SYNC << 24);
+}
+
+__device__ __forceinline__ void write_seg_hdr(const DevState& S, uint32_t l, unsigned long long base, uint16_t type,
+                                              uint32_t n_slots, uint32_t n_valid, unsigned long long pay_bytes,
+                                              uint32_t rec_bytes, unsigned long long seq) {
+  gpx_log_seg_hdr h;
+  memset(&h, 0, sizeof h);
+  h.magic = GPX_SEG_MAGIC;
+  h.type = type;
+  h.lane = (uint16_t)l;
+  h.n_slots = n_slots;
+  h.n_valid = n_valid;
+  h.payload_bytes = pay_bytes;
+  h.seq = seq;
+  h.ring_off = base;
+  h.rec_bytes = rec_bytes;
+  int4* hp = reinterpret_cast<int4*>(ring_ptr(S, l, base));
+  const int4* sp = reinterpret_cast<const int4*>(&h);
+  hp[0] = sp[0];
+  hp[1] = sp[1];
+  hp[2] = sp[2];
+  hp[3] = sp[3];
+}
+
+/* copy one blob into the payload area of every logging lane (read once, written up to L times) */
+template <int L>
+__device__ __forceinline__ void copy_blob(const DevState& S, const AcceptArgs& A, uint32_t off, uint32_t plen,
+                                          uint32_t logmask, const unsigned long long* payb) {
+  const uint8_t* src = blob_ptr(A, off);
+  if (((off | (uint32_t)(uintptr_t)src) & 15u) == 0) {
+    for (uint32_t b = 0; b < plen; b += 16) {
+      int4 v = ld_stream4(src + b);
+#pragma unroll
+      for (int l = 0; l < L; l++)
+        if ((logmask >> l) & 1u) st_stream4(ring_ptr(S, l, payb[l] + off + b), v);
+    }
+  } else {
+    for (uint32_t b = 0; b < plen; b++) {
+      uint8_t v = src[b];
+#pragma unroll
+      for (int l = 0; l < L; l++)
+        if ((logmask >> l) & 1u) *ring_ptr(S, l, payb[l] + off + b) = v;
+    }
+  }
+}
+
+/* ACCEPT segment: [64 B hdr][n x 32 B pvalue-header plane][n x 16 B extension plane][payload area];
+ * the two planes let every image move as one 256-bit plus one 128-bit aligned store */
+__device__ __forceinline__ void write_accept_image(const DevState& S, uint32_t l, unsigned long long segb,
+                                                   uint32_t n_max, uint32_t j, const int4 q0, const int4 q1,
+                                                   const int4 q2, uint32_t img_flags) {
+  st256_stream(ring_ptr(S, l, segb + 64 + (unsigned long long)j * 32), q0, make_int4(q1.x, (int)img_flags, q1.z, q1.w));
+  st_stream4(ring_ptr(S, l, segb + 64 + (unsigned long long)n_max * 32 + (unsigned long long)j * 16), q2);
+}
+
+__device__ __forceinline__ void store_void_exec(gpx_exec_rec* ex, uint32_t gid, int slot, uint32_t l) {
+  gpx_exec_rec vx;
+  vx.gid = gid;
+  vx.slot = slot;
+  vx.req_id = 0;
+  vx.payload_off = 0;
+  vx.flags = GPX_F_VOID | (l << 12);
+  store_exec(ex, vx);
+}
+
+struct GroupCtx {
+  uint32_t R;
+  const MsetInfo* ms;
+  bool live;
+};
+__device__ __forceinline__ GroupCtx group_ctx(const DevState& S, uint32_t gid) {
+  GroupCtx g;
+  g.R = 0;
+  g.ms = nullptr;
+  g.live = false;
+  if (gid < S.G) {
+    const uint32_t meta = S.grp_meta[gid];
+    g.ms = &S.msets[meta & 0xffffu];
+    g.R = (meta >> 16) & 0xffu;
+    g.live = (meta & GPX_META_LIVE) != 0;
+  }
+  return g;
+}
+
+/* ============================== k_accept ====================================== */
+template <int L>
 __global__ void __launch_bounds__(GPX_BLOCK) k_accept(const __grid_constant__ DevState S,
                                                       const __grid_constant__ AcceptArgs A) {
   __shared__ unsigned int s_ctr[C_NCTR];
@@ -498,32 +699,19 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_accept(const __grid_constant__ De
   uint32_t n = A.n_ptr ? *A.n_ptr : A.n_max;
   if (n > A.n_max) n = A.n_max;
   const uint32_t i = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  const uint32_t Wm = S.W - 1;
   const unsigned long long pay_bytes = A.blob0_bytes + (A.blob1_used_ptr ? *A.blob1_used_ptr : A.blob1_bytes);
-  const unsigned long long reserved = 64ull + (unsigned long long)A.n_max * 48ull + pay_bytes;
   const unsigned long long pay_rel = 64ull + (unsigned long long)A.n_max * 48ull;
-  unsigned long long segb[GPX_MAX_LANES];
+  const unsigned long long reserved = (pay_rel + pay_bytes + 31ull) & ~31ull; /* images need 32-B alignment */
+  unsigned long long segb[L], payb[L];
 #pragma unroll
-  for (uint32_t l = 0; l < GPX_MAX_LANES; l++) segb[l] = l < S.L ? seg_base(S, l, reserved) : 0ull;
+  for (int l = 0; l < L; l++) {
+    segb[l] = seg_base(S, l, reserved);
+    payb[l] = segb[l] + pay_rel;
+  }
   if (i == 0) {
-    for (uint32_t l = 0; l < S.L; l++) {
-      gpx_log_seg_hdr h;
-      memset(&h, 0, sizeof h);
-      h.magic = GPX_SEG_MAGIC;
-      h.type = GPX_F_ACCEPT;
-      h.lane = (uint16_t)l;
-      h.n_slots = A.n_max;
-      h.n_valid = n;
-      h.payload_bytes = pay_bytes;
-      h.seq = S.seg_seq[l];
-      h.ring_off = segb[l];
-      h.rec_bytes = 48;
-      int4* hp = reinterpret_cast<int4*>(ring_ptr(S, l, segb[l]));
-      const int4* sp = reinterpret_cast<const int4*>(&h);
-      hp[0] = sp[0];
-      hp[1] = sp[1];
-      hp[2] = sp[2];
-      hp[3] = sp[3];
-    }
+#pragma unroll
+    for (int l = 0; l < L; l++) write_seg_hdr(S, l, segb[l], GPX_F_ACCEPT, A.n_max, n, pay_bytes, 48, S.seg_seq[l]);
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
   if (i < n) {
@@ -532,26 +720,49 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_accept(const __grid_constant__ De
     const uint32_t gid = (uint32_t)q0.x;
     const bool head = (i == 0) || (A.recs[i - 1].h.gid != gid);
     if (head) {
+      const GroupCtx g = group_ctx(S, gid);
       uint32_t j = i;
       while (true) {
-        uint32_t logmask = accept_one(S, A, q0, q1, q2, j, segb, pay_rel, s_ctr);
-        if (logmask) { /* append the blob to the payload area of every logging lane */
-          const uint32_t off = (uint32_t)q2.x, plen = (uint32_t)q2.y;
-          const uint8_t* src = blob_ptr(A, off);
-          if (((off | (uint32_t)(uintptr_t)src) & 15u) == 0) {
-            for (uint32_t b = 0; b < plen; b += 16) {
-              int4 v = ld_stream4(src + b);
-              for (uint32_t l = 0; l < S.L; l++)
-                if ((logmask >> l) & 1u) st_stream4(ring_ptr(S, l, segb[l] + pay_rel + off + b), v);
-            }
-          } else {
-            for (uint32_t b = 0; b < plen; b++) {
-              uint8_t v = src[b];
-              for (uint32_t l = 0; l < S.L; l++)
-                if ((logmask >> l) & 1u) *ring_ptr(S, l, segb[l] + pay_rel + off + b) = v;
-            }
+        const int slot = q0.y;
+        const uint32_t payload_off = (uint32_t)q2.x;
+        LaneSt st[L];
+        int4 e0[L], e1[L];
+#pragma unroll
+        for (int l = 0; l < L; l++) { /* all independent loads first */
+          st[l].aux = 0;
+          st[l].row = make_int4(0, 0, 0, 0);
+          e0[l] = e1[l] = make_int4(0, 0, 0, 0);
+          if (g.live) {
+            const size_t ri = row_idx(S, l, gid);
+            st[l].aux = S.acc_aux[ri];
+            st[l].row = S.acc_row[ri];
+            ld256(&S.acc_win[2 * win_idx(S, l, (uint32_t)slot & Wm, gid)], e0[l], e1[l]);
           }
         }
+        uint32_t dstIdx = 0xffu;
+        if (g.live)
+          for (uint32_t m = 0; m < g.R; m++)
+            if (g.ms->nodes[m] == q2.w) dstIdx = m;
+        uint32_t logmask = 0;
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          const unsigned fr = (unsigned)(((payb[l] + payload_off) & (S.ring_cap - 1)) >> 4);
+          accept_lane(S, A, l, g.live, g.ms, dstIdx, q0, q1, q2, e0[l], e1[l], fr, st[l], s_ctr);
+          const size_t ri = row_idx(S, l, gid);
+          if (st[l].fl & LS_STORE) {
+            int4 n0, n1;
+            make_entry(q0, q1, q2, st[l].frame_ref, n0, n1);
+            st256(&S.acc_win[2 * win_idx(S, l, (uint32_t)slot & Wm, gid)], n0, n1);
+          }
+          if (st[l].fl & LS_ROWDIRTY) S.acc_row[ri] = st[l].row;
+          if (st[l].fl & LS_AUXDIRTY) S.acc_aux[ri] = st[l].aux;
+          if (st[l].fl & LS_LOGGED) logmask |= 1u << l;
+          st256_stream(&A.replies[(size_t)j * L + l], make_int4((int)gid, slot, st[l].rbn, st[l].rbc),
+                       (GPX_WHO_FLAGS(st[l].rwho) & GPX_F_VOID) ? make_int4(0, (int)st[l].rwho, 0, 0)
+                                                                : make_int4(st[l].rmaxcp, (int)st[l].rwho, q1.z, q1.w));
+          write_accept_image(S, l, segb[l], A.n_max, j, q0, q1, q2, st[l].img_flags);
+        }
+        if (logmask) copy_blob<L>(S, A, payload_off, (uint32_t)q2.y, logmask, payb);
         j++;
         if (j >= n) break;
         rp = reinterpret_cast<const int4*>(&A.recs[j]);
@@ -569,10 +780,13 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_accept(const __grid_constant__ De
   __threadfence();
   if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[1], 1u) == gridDim.x - 1);
   __syncthreads();
-  if (s_last && threadIdx.x < S.L) {
-    S.ring_head[threadIdx.x] = segb[threadIdx.x] + ((reserved + 15ull) & ~15ull);
-    S.seg_seq[threadIdx.x] += 1ull;
-    if (threadIdx.x == 0) S.tickets[1] = 0;
+  if (s_last && threadIdx.x == 0) {
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      S.ring_head[l] = segb[l] + reserved;
+      S.seg_seq[l] += 1ull;
+    }
+    S.tickets[1] = 0;
   }
 }
 
@@ -595,109 +809,53 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_tally(const __grid_constant__ Dev
   uint32_t n = A.n_ptr ? (*A.n_ptr) * A.mult : A.n_max;
   if (n > A.n_max) n = A.n_max;
   const uint32_t i = blockIdx.x * GPX_BLOCK + threadIdx.x;
-  const uint32_t Wm = S.W - 1;
   gpx_decision_rec dbuf[GPX_MAX_WINDOW];
   uint32_t nd = 0;
   if (i == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   if (i < n) {
-    const int4* rp = reinterpret_cast<const int4*>(&A.replies[i]);
-    int4 q0 = ld_stream4(rp), q1 = ld_stream4(rp + 1);
+    int4 q0, q1;
+    ld256_stream(&A.replies[i], q0, q1);
     const uint32_t gid = (uint32_t)q0.x;
     const bool head = (i == 0) || (A.replies[i - 1].gid != gid);
     if (head) {
-      /* coordinator rows touched by this run are cached in registers per lane */
       int cl = -1;
       int4 crow = make_int4(0, 0, 0, 0);
       bool dirty = false;
-      uint32_t meta = 0, R = 0;
-      const MsetInfo* ms = nullptr;
-      const bool gid_ok = gid < S.G;
-      if (gid_ok) {
-        meta = S.grp_meta[gid];
-        ms = &S.msets[meta & 0xffffu];
-        R = (meta >> 16) & 0xffu;
-      }
-      const bool live = gid_ok && (meta & GPX_META_LIVE);
+      const GroupCtx g = group_ctx(S, gid);
       uint32_t j = i;
       while (true) {
         const uint32_t who = (uint32_t)q1.y;
-        const uint32_t wf = GPX_WHO_FLAGS(who);
-        if (!(wf & GPX_F_VOID)) {
-          const uint32_t dstIdx = GPX_WHO_DST(who), accIdx = GPX_WHO_ACC(who);
+        if (!(GPX_WHO_FLAGS(who) & GPX_F_VOID)) {
+          const uint32_t dstIdx = GPX_WHO_DST(who);
           int lane = -1;
           uint32_t aux;
-          if (live && dstIdx < R && ms->lane_of_idx[dstIdx] != 0xffu && usable(S, gid, ms->lane_of_idx[dstIdx], &aux))
-            lane = ms->lane_of_idx[dstIdx];
+          if (g.live && dstIdx < g.R && g.ms->lane_of_idx[dstIdx] != 0xffu &&
+              usable(S, gid, g.ms->lane_of_idx[dstIdx], &aux))
+            lane = g.ms->lane_of_idx[dstIdx];
           if (lane < 0) {
             atomicAdd(&s_ctr[C_REPLIES_IGNORED], 1u);
           } else {
-            atomicAdd(&s_ctr[C_REPLIES_HANDLED], 1u);
             if (lane != cl) {
               if (dirty) S.coord_row[row_idx(S, cl, gid)] = crow;
               cl = lane;
               crow = S.coord_row[row_idx(S, cl, gid)];
               dirty = false;
             }
-            const int slot = q0.y, rb = q0.z, rc = q0.w, max_cp = q1.x;
-            const uint32_t cf = (unsigned)crow.w & 0xffu;
-            if ((cf & GPX_CF_EXISTS) && (cf & GPX_CF_ACTIVE)) { /* PaxosCoordinator.handleAcceptReply :212 */
-              const int c = bcmp(rb, rc, crow.x, crow.y);
-              const size_t pi = win_idx(S, cl, (uint32_t)slot & Wm, gid);
-              if (c > 0) { /* handleAcceptReplyHigherBallot :661-675 */
-                int4 pe = S.prop_win[pi];
-                if (((unsigned)pe.y & GPX_PV_PRESENT) && pe.x == slot) {
-                  pe.y = (int)((unsigned)pe.y & ~GPX_PV_PRESENT);
-                  S.prop_win[pi] = pe;
-                  crow.w = (int)((unsigned)crow.w - (1u << 8));
-                  dirty = true;
-                  atomicAdd(&s_ctr[C_PREEMPTED], 1u);
-                }
-              } else if (c == 0) { /* handleAcceptReplyMyBallot :597-640 */
-                if (accIdx < R) { /* recordSlotNumber :809-825 (plain <) */
-                  const size_t ni = ns_idx(S, cl, accIdx, gid);
-                  if (S.node_slots[ni] < max_cp) S.node_slots[ni] = max_cp;
-                }
-                int4 pe = S.prop_win[pi];
-                if (((unsigned)pe.y & GPX_PV_PRESENT) && pe.x == slot) {
-                  uint32_t vf = (unsigned)pe.y;
-                  if (accIdx < R) vf |= (1u << accIdx); /* WaitforUtility.updateHeardFrom :51-62 */
-                  if (__popc(vf & 0xffffu) > (int)(R / 2)) { /* heardFromMajority :64-68 */
-                    gpx_decision_rec d;
-                    d.gid = gid;
-                    d.slot = slot;
-                    d.bnum = crow.x;
-                    d.bcoord = crow.y;
-                    d.median_cp = median_minus(S, cl, gid, R); /* makeDecision(getMajorityCommittedSlot()) */
-                    d.flags = (uint16_t)(GPX_F_DECISION | ((vf & GPX_PV_STOP) ? GPX_F_STOP : 0u));
-                    d.dst_mask = ms->lane_mask;
-                    d.req_id = ((long long)pe.w << 32) | (unsigned)pe.z;
-                    if (nd < GPX_MAX_WINDOW) dbuf[nd] = d;
-                    nd++;
-                    pe.y = (int)(vf & ~GPX_PV_PRESENT);
-                    crow.w = (int)((unsigned)crow.w - (1u << 8));
-                    dirty = true;
-                    atomicAdd(&s_ctr[C_DECISIONS_MADE], 1u);
-                  } else
-                    pe.y = (int)vf;
-                  S.prop_win[pi] = pe;
-                }
-              }
-            }
-            /* nullifyCoordinatorIfPreemptedFully :1353-1356 */
-            if ((((unsigned)crow.w) & GPX_CF_EXISTS) && bcmp(rb, rc, crow.x, crow.y) > 0 && (((unsigned)crow.w) >> 8) == 0) {
-              crow = make_int4(0, 0, 0, 0);
-              dirty = true;
-              atomicAdd(&s_ctr[C_COORD_RESIGNED], 1u);
+            gpx_decision_rec d;
+            if (tally_reply(S, (uint32_t)cl, gid, g.R, g.ms, crow, dirty, q0.y, q0.z, q0.w, q1.x, GPX_WHO_ACC(who), d,
+                            s_ctr)) {
+              if (nd < GPX_MAX_WINDOW) dbuf[nd] = d;
+              nd++;
             }
           }
         }
         j++;
         if (j >= n) break;
-        rp = reinterpret_cast<const int4*>(&A.replies[j]);
-        int4 t0 = ld_stream4(rp);
+        int4 t0, t1;
+        ld256_stream(&A.replies[j], t0, t1);
         if ((uint32_t)t0.x != gid) break;
         q0 = t0;
-        q1 = ld_stream4(rp + 1);
+        q1 = t1;
       }
       if (dirty) S.coord_row[row_idx(S, cl, gid)] = crow;
     }
@@ -705,10 +863,8 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_tally(const __grid_constant__ Dev
   if (nd > GPX_MAX_WINDOW) nd = GPX_MAX_WINDOW; /* cannot happen: <= W proposals outstanding */
   uint32_t base = block_reserve(nd, A.n_decisions, s_scan);
   for (uint32_t k = 0; k < nd; k++) {
-    int4* dp = reinterpret_cast<int4*>(&A.decisions[base + k]);
     const int4* sp = reinterpret_cast<const int4*>(&dbuf[k]);
-    st_stream4(dp, sp[0]);
-    st_stream4(dp + 1, sp[1]);
+    st256_stream(&A.decisions[base + k], sp[0], sp[1]);
   }
   flush_counters(S, s_ctr);
 }
@@ -724,85 +880,7 @@ struct CommitArgs {
   uint32_t* n_extra;
 };
 
-__device__ __forceinline__ void commit_one(const DevState& S, const CommitArgs& A, const int4 q0, const int4 q1,
-                                           uint32_t j, const unsigned long long* segb, unsigned int* s_ctr) {
-  const uint32_t gid = (uint32_t)q0.x;
-  const int slot = q0.y, bnum = q0.z, bcoord = q0.w, median_cp = q1.x;
-  const uint32_t rflags = (uint32_t)q1.y & 0xffffu, dst_mask = (uint32_t)q1.y >> 16;
-  const uint32_t Wm = S.W - 1;
-  const bool gid_ok = gid < S.G;
-  const bool live = gid_ok && (S.grp_meta[gid] & GPX_META_LIVE);
-  for (uint32_t l = 0; l < S.L; l++) {
-    gpx_exec_rec* ex = &A.exec[(size_t)j * S.L + l];
-    gpx_exec_rec vx;
-    vx.gid = gid;
-    vx.slot = slot;
-    vx.req_id = 0;
-    vx.payload_off = 0;
-    vx.flags = GPX_F_VOID | (l << 12);
-    store_exec(ex, vx);
-    int4 img0 = q0, img1 = make_int4(q1.x, (int)(GPX_F_VOID | (dst_mask << 16)), q1.z, q1.w);
-    do {
-      if (!((dst_mask >> l) & 1u) || (rflags & GPX_F_VOID)) break;
-      uint32_t aux;
-      if (!live || !usable(S, gid, l, &aux)) {
-        atomicAdd(&s_ctr[C_DECISIONS_DROPPED], 1u);
-        break;
-      }
-      const size_t ri = row_idx(S, l, gid);
-      int4 row = S.acc_row[ri];
-      if (jsub(slot, row.x) >= (int)S.W) {
-        S.acc_aux[ri] = aux | ((GPX_GF_OVERFLOW | GPX_GF_NEEDS_SYNC) << 24);
-        atomicAdd(&s_ctr[C_WINDOW_OVERFLOW], 1u);
-        atomicAdd(&s_ctr[C_DECISIONS_DROPPED], 1u);
-        break;
-      }
-      atomicAdd(&s_ctr[C_DECISIONS_HANDLED], 1u);
-      const int4 row_in = row;
-      const uint32_t aux_in = aux;
-      const size_t ai = 2 * win_idx(S, l, (uint32_t)slot & Wm, gid);
-      const int4 a0 = S.acc_win[ai], a1 = S.acc_win[ai + 1];
-      const bool a_alive = ((unsigned)a1.w & GPX_ENT_VALID) && jsub(a0.x, row.w) > 0 && a0.x == slot;
-      DPValue d;
-      d.slot = slot;
-      d.bnum = bnum;
-      d.bcoord = bcoord;
-      d.median_cp = median_cp;
-      if (a_alive && a0.y == bnum && a0.z == bcoord) { /* :1488 decision := the accept we hold */
-        d.req_id = ((long long)a1.y << 32) | (unsigned)a1.x;
-        d.frame_ref = (unsigned)a0.w;
-        d.plen = (unsigned)a1.z;
-        d.fl = (unsigned)a1.w & ~GPX_ENT_VALID;
-        d.valued = true;
-      } else { /* placeholder :1514-1522 */
-        d.req_id = 0;
-        d.frame_ref = 0;
-        d.plen = 0;
-        d.fl = 0;
-        d.valued = false;
-        atomicAdd(&s_ctr[C_PLACEHOLDERS], 1u);
-      }
-      /* logDecision :1446-1466 */
-      if (d.valued || S.log_meta) {
-        const bool meta = S.log_meta && a_alive && bcmp(a0.y, a0.z, d.bnum, d.bcoord) >= 0;
-        const uint32_t lf = GPX_F_DECISION | (meta ? GPX_F_META : 0u) | ((d.fl & GPX_ENT_STOP) ? GPX_F_STOP : 0u);
-        img0 = make_int4((int)gid, slot, d.bnum, d.bcoord);
-        img1 = make_int4(meta ? -1 : d.median_cp, (int)(lf | ((1u << l) << 16)), (int)(unsigned)(d.req_id & 0xffffffffll),
-                         (int)(d.req_id >> 32));
-      }
-      const int slot_before = row.x;
-      eec(S, l, gid, row, aux, d, ex, A.extra, A.extra_cap, A.n_extra, s_ctr, false);
-      if (GPX_AUX_STATE(aux) != GPX_ST_STOPPED && !d.valued && jsub(slot, row.x) >= 0 && row.x == slot_before)
-        aux |= (GPX_GF_NEEDS_SYNC << 24);
-      if (aux != aux_in) S.acc_aux[ri] = aux;
-      if (row.x != row_in.x || row.y != row_in.y || row.z != row_in.z || row.w != row_in.w) S.acc_row[ri] = row;
-    } while (false);
-    int4* ip = reinterpret_cast<int4*>(ring_ptr(S, l, segb[l] + 64 + (unsigned long long)j * 32));
-    st_stream4(ip, img0);
-    st_stream4(ip + 1, img1);
-  }
-}
-
+template <int L>
 __global__ void __launch_bounds__(GPX_BLOCK) k_commit(const __grid_constant__ DevState S,
                                                       const __grid_constant__ CommitArgs A) {
   __shared__ unsigned int s_ctr[C_NCTR];
@@ -811,48 +889,68 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_commit(const __grid_constant__ De
   uint32_t n = A.n_ptr ? *A.n_ptr : A.n_max;
   if (n > A.n_max) n = A.n_max;
   const uint32_t i = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  const uint32_t Wm = S.W - 1;
   const unsigned long long reserved = 64ull + (unsigned long long)A.n_max * 32ull;
-  unsigned long long segb[GPX_MAX_LANES];
+  unsigned long long segb[L];
 #pragma unroll
-  for (uint32_t l = 0; l < GPX_MAX_LANES; l++) segb[l] = l < S.L ? seg_base(S, l, reserved) : 0ull;
+  for (int l = 0; l < L; l++) segb[l] = seg_base(S, l, reserved);
   if (i == 0) {
-    for (uint32_t l = 0; l < S.L; l++) {
-      gpx_log_seg_hdr h;
-      memset(&h, 0, sizeof h);
-      h.magic = GPX_SEG_MAGIC;
-      h.type = GPX_F_DECISION;
-      h.lane = (uint16_t)l;
-      h.n_slots = A.n_max;
-      h.n_valid = n;
-      h.payload_bytes = 0;
-      h.seq = S.seg_seq[l];
-      h.ring_off = segb[l];
-      h.rec_bytes = 32;
-      int4* hp = reinterpret_cast<int4*>(ring_ptr(S, l, segb[l]));
-      const int4* sp = reinterpret_cast<const int4*>(&h);
-      hp[0] = sp[0];
-      hp[1] = sp[1];
-      hp[2] = sp[2];
-      hp[3] = sp[3];
-    }
+#pragma unroll
+    for (int l = 0; l < L; l++) write_seg_hdr(S, l, segb[l], GPX_F_DECISION, A.n_max, n, 0, 32, S.seg_seq[l]);
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
   if (i < n) {
-    const int4* rp = reinterpret_cast<const int4*>(&A.decisions[i]);
-    int4 q0 = ld_stream4(rp), q1 = ld_stream4(rp + 1);
+    int4 q0, q1;
+    ld256_stream(&A.decisions[i], q0, q1);
     const uint32_t gid = (uint32_t)q0.x;
     const bool head = (i == 0) || (A.decisions[i - 1].gid != gid);
     if (head) {
+      const GroupCtx g = group_ctx(S, gid);
       uint32_t j = i;
       while (true) {
-        commit_one(S, A, q0, q1, j, segb, s_ctr);
+        const int slot = q0.y;
+        const uint32_t rflags = (uint32_t)q1.y & 0xffffu, dst_mask = (uint32_t)q1.y >> 16;
+        uint32_t aux[L];
+        int4 row[L], e0[L], e1[L];
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          aux[l] = 0;
+          row[l] = e0[l] = e1[l] = make_int4(0, 0, 0, 0);
+          if (g.live) {
+            const size_t ri = row_idx(S, l, gid);
+            aux[l] = S.acc_aux[ri];
+            row[l] = S.acc_row[ri];
+            ld256(&S.acc_win[2 * win_idx(S, l, (uint32_t)slot & Wm, gid)], e0[l], e1[l]);
+          }
+        }
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          gpx_exec_rec* ex = &A.exec[(size_t)j * L + l];
+          store_void_exec(ex, gid, slot, l);
+          int4 img0 = q0, img1 = make_int4(q1.x, (int)(GPX_F_VOID | (dst_mask << 16)), q1.z, q1.w);
+          if (((dst_mask >> l) & 1u) && !(rflags & GPX_F_VOID)) {
+            if (!g.live || !st_usable(aux[l])) {
+              atomicAdd(&s_ctr[C_DECISIONS_DROPPED], 1u);
+            } else {
+              const size_t ri = row_idx(S, l, gid);
+              const int4 row_in = row[l];
+              const uint32_t aux_in = aux[l];
+              commit_lane(S, l, gid, slot, q0.z, q0.w, q1.x, row[l], aux[l], e0[l], e1[l], ex, A.extra, A.extra_cap,
+                          A.n_extra, img0, img1, s_ctr);
+              const int4 r2 = row[l];
+              if (aux[l] != aux_in) S.acc_aux[ri] = aux[l];
+              if (r2.x != row_in.x || r2.y != row_in.y || r2.z != row_in.z || r2.w != row_in.w) S.acc_row[ri] = r2;
+            }
+          }
+          st256_stream(ring_ptr(S, l, segb[l] + 64 + (unsigned long long)j * 32), img0, img1);
+        }
         j++;
         if (j >= n) break;
-        rp = reinterpret_cast<const int4*>(&A.decisions[j]);
-        int4 t0 = ld_stream4(rp);
+        int4 t0, t1;
+        ld256_stream(&A.decisions[j], t0, t1);
         if ((uint32_t)t0.x != gid) break;
         q0 = t0;
-        q1 = ld_stream4(rp + 1);
+        q1 = t1;
       }
     }
   }
@@ -861,10 +959,255 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_commit(const __grid_constant__ De
   __threadfence();
   if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[3], 1u) == gridDim.x - 1);
   __syncthreads();
-  if (s_last && threadIdx.x < S.L) {
-    S.ring_head[threadIdx.x] = segb[threadIdx.x] + reserved;
-    S.seg_seq[threadIdx.x] += 1ull;
-    if (threadIdx.x == 0) S.tickets[3] = 0;
+  if (s_last && threadIdx.x == 0) {
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      S.ring_head[l] = segb[l] + reserved;
+      S.seg_seq[l] += 1ull;
+    }
+    S.tickets[3] = 0;
+  }
+}
+
+/* ============================== k_act (fused) ================================== */
+/* Per ACCEPT, in batch order: handleAccept at every addressed lane; replies addressed to a usable LOCAL
+ * coordinator lane are tallied at once (the others are written to A.replies for the host); a resulting
+ * DECISION is committed at every local lane before the next ACCEPT of the run.  Per lane it appends an
+ * ACCEPT segment followed by a DECISION segment (image index = ACCEPT index).  On the fast path (the
+ * in-order case) rows are read and written once, replies and the decision never touch HBM, and an entry
+ * that is accepted and executed in the same pass is not written at all. */
+template <int L>
+__global__ void __launch_bounds__(GPX_BLOCK) k_act(const __grid_constant__ DevState S,
+                                                   const __grid_constant__ AcceptArgs A) {
+  __shared__ unsigned int s_ctr[C_NCTR];
+  if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t n = A.n_ptr ? *A.n_ptr : A.n_max;
+  if (n > A.n_max) n = A.n_max;
+  const uint32_t i = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  const uint32_t Wm = S.W - 1;
+  const unsigned long long pay_bytes = A.blob0_bytes + (A.blob1_used_ptr ? *A.blob1_used_ptr : A.blob1_bytes);
+  const unsigned long long pay_rel = 64ull + (unsigned long long)A.n_max * 48ull;
+  const unsigned long long res_a = (pay_rel + pay_bytes + 31ull) & ~31ull;
+  const unsigned long long res_d = 64ull + (unsigned long long)A.n_max * 32ull;
+  unsigned long long segb[L], payb[L], dsegb[L];
+#pragma unroll
+  for (int l = 0; l < L; l++) {
+    segb[l] = seg_base(S, l, res_a + res_d); /* both segments on one side of the ring wrap */
+    payb[l] = segb[l] + pay_rel;
+    dsegb[l] = segb[l] + res_a;
+  }
+  if (i == 0) {
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      write_seg_hdr(S, l, segb[l], GPX_F_ACCEPT, A.n_max, n, pay_bytes, 48, S.seg_seq[l]);
+      write_seg_hdr(S, l, dsegb[l], GPX_F_DECISION, A.n_max, n, 0, 32, S.seg_seq[l] + 1ull);
+    }
+    atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
+  }
+  if (i < n) {
+    const int4* rp = reinterpret_cast<const int4*>(&A.recs[i]);
+    int4 q0 = ld_stream4(rp), q1 = ld_stream4(rp + 1), q2 = ld_stream4(rp + 2);
+    const uint32_t gid = (uint32_t)q0.x;
+    const bool head = (i == 0) || (A.recs[i - 1].h.gid != gid);
+    if (head) {
+      const GroupCtx g = group_ctx(S, gid);
+      uint32_t j = i;
+      while (true) {
+        const int slot = q0.y;
+        const uint32_t payload_off = (uint32_t)q2.x;
+        /* ---- all independent loads of this ACCEPT ---- */
+        LaneSt st[L];
+        int4 e0[L], e1[L];
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          st[l].aux = 0;
+          st[l].row = make_int4(0, 0, 0, 0);
+          e0[l] = e1[l] = make_int4(0, 0, 0, 0);
+          if (g.live) {
+            const size_t ri = row_idx(S, l, gid);
+            st[l].aux = S.acc_aux[ri];
+            st[l].row = S.acc_row[ri];
+            ld256(&S.acc_win[2 * win_idx(S, l, (uint32_t)slot & Wm, gid)], e0[l], e1[l]);
+          }
+        }
+        uint32_t dstIdx = 0xffu;
+        if (g.live)
+          for (uint32_t m = 0; m < g.R; m++)
+            if (g.ms->nodes[m] == q2.w) dstIdx = m;
+        int cl = -1; /* the coordinator that issued this ACCEPT, if it is a local lane */
+        if (g.live && dstIdx < g.R && g.ms->lane_of_idx[dstIdx] != 0xffu) cl = g.ms->lane_of_idx[dstIdx];
+        int4 crow = make_int4(0, 0, 0, 0);
+        if (cl >= 0) crow = S.coord_row[row_idx(S, cl, gid)];
+        /* ---- accept at every lane ---- */
+        uint32_t logmask = 0;
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          const unsigned fr = (unsigned)(((payb[l] + payload_off) & (S.ring_cap - 1)) >> 4);
+          accept_lane(S, A, l, g.live, g.ms, dstIdx, q0, q1, q2, e0[l], e1[l], fr, st[l], s_ctr);
+          if (st[l].fl & LS_LOGGED) logmask |= 1u << l;
+          write_accept_image(S, l, segb[l], A.n_max, j, q0, q1, q2, st[l].img_flags);
+        }
+        if (logmask) copy_blob<L>(S, A, payload_off, (uint32_t)q2.y, logmask, payb);
+        /* ---- tally the replies addressed to a usable local coordinator (PISM drop rule :456-460) ---- */
+        uint32_t caux = 0;
+#pragma unroll
+        for (int l = 0; l < L; l++)
+          if (l == cl) caux = st[l].aux;
+        const bool tally_here = cl >= 0 && st_usable(caux);
+        gpx_decision_rec d;
+        d.gid = gid;
+        d.slot = slot;
+        d.bnum = 0;
+        d.bcoord = 0;
+        d.median_cp = 0;
+        d.flags = GPX_F_VOID;
+        d.dst_mask = 0;
+        d.req_id = 0;
+        bool decided = false, cdirty = false;
+        uint32_t omask = 0; /* replies that leave this engine (remote or unusable coordinator) */
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          const bool is_void = (GPX_WHO_FLAGS(st[l].rwho) & GPX_F_VOID) != 0;
+          if (is_void) continue;
+          if (tally_here) { /* consumed locally: the reply never touches HBM */
+            gpx_decision_rec dd;
+            if (tally_reply(S, (uint32_t)cl, gid, g.R, g.ms, crow, cdirty, slot, st[l].rbn, st[l].rbc, st[l].rmaxcp,
+                            GPX_WHO_ACC(st[l].rwho), dd, s_ctr) &&
+                !decided) {
+              d = dd;
+              decided = true;
+            }
+          } else {
+            omask |= 1u << l;
+            st256_stream(&A.replies[(size_t)j * L + l], make_int4((int)gid, slot, st[l].rbn, st[l].rbc),
+                         make_int4(st[l].rmaxcp, (int)st[l].rwho, q1.z, q1.w));
+          }
+        }
+        A.out_mask[j] = (uint8_t)omask;
+        if (cdirty) S.coord_row[row_idx(S, cl, gid)] = crow;
+        {
+          const int4* sp = reinterpret_cast<const int4*>(&d);
+          st256_stream(&A.decisions[j], sp[0], sp[1]);
+        }
+        /* ---- commit the decision at every lane ---- */
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          gpx_exec_rec* ex = &A.exec[(size_t)j * L + l];
+          int4 img0 = make_int4((int)gid, slot, d.bnum, d.bcoord);
+          int4 img1 = make_int4(d.median_cp, (int)(GPX_F_VOID | ((uint32_t)d.dst_mask << 16)),
+                                (int)(unsigned)(d.req_id & 0xffffffffll), (int)(d.req_id >> 32));
+          const size_t ai = 2 * win_idx(S, l, (uint32_t)slot & Wm, gid);
+          const size_t ri = row_idx(S, l, gid);
+          int4& row = st[l].row;
+          uint32_t& aux = st[l].aux;
+          if (!(decided && ((d.dst_mask >> l) & 1u))) {
+            store_void_exec(ex, gid, slot, l);
+          } else if (!g.live || !st_usable(aux)) {
+            store_void_exec(ex, gid, slot, l);
+            atomicAdd(&s_ctr[C_DECISIONS_DROPPED], 1u);
+          } else {
+            const int4 row_b = row;
+            const uint32_t aux_b = aux;
+            const bool fast = (st[l].fl & LS_STORE) && q0.z == d.bnum && q0.w == d.bcoord && slot == row.x &&
+                              !((GPX_AUX_PRESENT(aux) >> ((uint32_t)slot & Wm)) & 1u);
+            if (fast) {
+              /* the accept stored a moment ago is the decided value and it is next in line:
+               * handleBatchedCommit :1488-1501 + the first iteration of extractExecuteAndCheckpoint */
+              atomicAdd(&s_ctr[C_DECISIONS_HANDLED], 1u);
+              int4 n0, n1;
+              make_entry(q0, q1, q2, st[l].frame_ref, n0, n1);
+              const unsigned efl = (unsigned)n1.w;
+              const bool metaf = S.log_meta != 0;
+              const uint32_t lf = GPX_F_DECISION | (metaf ? GPX_F_META : 0u) | ((efl & GPX_ENT_STOP) ? GPX_F_STOP : 0u);
+              img0 = make_int4((int)gid, slot, d.bnum, d.bcoord);
+              img1 = make_int4(metaf ? -1 : d.median_cp, (int)(lf | ((1u << l) << 16)), n1.x, n1.y);
+              gc_step(row, d.median_cp);
+              DPValue x;
+              x.slot = slot;
+              x.bnum = d.bnum;
+              x.bcoord = d.bcoord;
+              x.median_cp = d.median_cp;
+              x.req_id = ((long long)n1.y << 32) | (unsigned)n1.x;
+              x.frame_ref = st[l].frame_ref;
+              x.plen = (unsigned)n1.z;
+              x.fl = efl & ~GPX_ENT_VALID;
+              x.valued = true;
+              row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
+              atomicAdd(&s_ctr[C_EXECUTED], 1u);
+              gpx_exec_rec er = make_exec(S, gid, l, x, false);
+              if (er.flags & GPX_F_CKPT) atomicAdd(&s_ctr[C_CKPTS_DUE], 1u);
+              store_exec(ex, er);
+              bool more = true;
+              if (efl & GPX_ENT_STOP) {
+                aux = (aux & ~0xffu) | GPX_ST_STOPPED; /* stop() + committedRequests.clear() */
+                aux &= ~0x00ffff00u;
+                atomicAdd(&s_ctr[C_STOPS_EXECUTED], 1u);
+                more = false;
+              }
+              if (S.journaling) {
+                /* acceptedProposals.remove(slot): the entry only has to reach HBM (invalidated) when it must
+                 * hide an occupant of the ring position whose valid bit is set */
+                if (st[l].fl & LS_OCCVALID) {
+                  n1.w = (int)((unsigned)n1.w & ~GPX_ENT_VALID);
+                  st256(&S.acc_win[ai], n0, n1);
+                }
+              } else
+                st256(&S.acc_win[ai], n0, n1);
+              st[l].fl &= ~LS_STORE;
+              if (more) { /* second iteration: GC with the advanced slot, then any queued commits */
+                gc_step(row, d.median_cp);
+                if ((GPX_AUX_PRESENT(aux) >> ((uint32_t)row.x & Wm)) & 1u)
+                  eec(S, l, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
+              }
+            } else {
+              /* general path through memory: make the accepted entry visible, then commit */
+              int4 a0 = e0[l], a1 = e1[l];
+              if (st[l].fl & LS_STORE) {
+                make_entry(q0, q1, q2, st[l].frame_ref, a0, a1);
+                st256(&S.acc_win[ai], a0, a1);
+                st[l].fl &= ~LS_STORE;
+              } else if (st[l].fl & LS_RARE)
+                ld256(&S.acc_win[ai], a0, a1);
+              store_void_exec(ex, gid, slot, l);
+              commit_lane(S, l, gid, slot, d.bnum, d.bcoord, d.median_cp, row, aux, a0, a1, ex, A.extra, A.extra_cap,
+                          A.n_extra, img0, img1, s_ctr);
+            }
+            if (aux != aux_b) st[l].fl |= LS_AUXDIRTY;
+            if (row.x != row_b.x || row.y != row_b.y || row.z != row_b.z || row.w != row_b.w) st[l].fl |= LS_ROWDIRTY;
+          }
+          if (st[l].fl & LS_STORE) {
+            int4 n0, n1;
+            make_entry(q0, q1, q2, st[l].frame_ref, n0, n1);
+            st256(&S.acc_win[ai], n0, n1);
+          }
+          if (st[l].fl & LS_ROWDIRTY) S.acc_row[ri] = row;
+          if (st[l].fl & LS_AUXDIRTY) S.acc_aux[ri] = aux;
+          st256_stream(ring_ptr(S, l, dsegb[l] + 64 + (unsigned long long)j * 32), img0, img1);
+        }
+        j++;
+        if (j >= n) break;
+        rp = reinterpret_cast<const int4*>(&A.recs[j]);
+        int4 t0 = ld_stream4(rp);
+        if ((uint32_t)t0.x != gid) break;
+        q0 = t0;
+        q1 = ld_stream4(rp + 1);
+        q2 = ld_stream4(rp + 2);
+      }
+    }
+  }
+  flush_counters(S, s_ctr);
+  __shared__ unsigned int s_last;
+  __threadfence();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[4], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      S.ring_head[l] = segb[l] + res_a + res_d;
+      S.seg_seq[l] += 2ull;
+    }
+    S.tickets[4] = 0;
   }
 }
 

@@ -1,0 +1,308 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+`PaxosManager` mirrors the calls of gigapaxos/PaxosManager.java that feed and drain the
+phase-2 path -- createPaxosInstance (:632, batch form :664-691), propose (:1214) /
+proposeStop, executed (:311-330), kill (:2162) -- on top of the engine's C ABI, and
+`Replicable` / `NoopPaxosApp` mirror gigapaxos/interfaces/Replicable.java and
+gigapaxos/examples/noop/NoopPaxosApp.java:19-72.  The reference's host language is Java; no
+JVM exists in this image, so this mirror is Python (INTEGRATION.md shows the JNI binding).
+
+One manager serves all co-located replicas ("lanes") of its groups, the way the reference's
+TESTPaxosMain runs several PaxosManagers in one JVM (testing/TESTPaxosMain.java:51-64).
+Requests are queued per call like RequestBatcher.enqueue (RequestBatcher.java:112) and one
+`run_round()` is one pass of the hot path: batch + propose, then accept -> tally -> commit on
+the device; the EXEC records come back in per-group slot order and are applied to the app of
+every replica (PISM.execute :1755-1842).
+"""
+from __future__ import annotations
+
+import hashlib
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from .abi import Engine
+
+
+class Replicable:
+    """gigapaxos/interfaces/Replicable.java: execute / checkpoint / restore."""
+
+    def execute(self, name: str, request: "RequestPacket", do_not_reply_to_client: bool) -> bool:
+        raise NotImplementedError
+
+    def checkpoint(self, name: str) -> Optional[str]:
+        return None
+
+    def restore(self, name: str, state: Optional[str]) -> bool:
+        return True
+
+
+class NoopPaxosApp(Replicable):
+    """gigapaxos/examples/noop/NoopPaxosApp.java:19-72: echoes the request, null checkpoints."""
+
+    def __init__(self):
+        self.executed = 0
+
+    def execute(self, name, request, do_not_reply_to_client):
+        request.response_value = b"echoing [" + request.request_value + b"]"  # :26-28
+        self.executed += 1
+        return True
+
+
+class HashChainApp(Replicable):
+    """The invariant app of the reference's tests (testing/TESTPaxosApp.java:143-232):
+    state = requestValue + SHA(state) and seqnum == slot (in-order, gap-free execution)."""
+
+    def __init__(self):
+        self.state: Dict[str, bytes] = {}
+        self.seqnum: Dict[str, int] = {}
+
+    def execute(self, name, request, do_not_reply_to_client):
+        cur = self.state.get(name, b"")
+        self.state[name] = request.request_value + hashlib.sha1(cur).digest()  # TESTPaxosApp.java:179-180
+        expect = self.seqnum.get(name, 1)
+        if request.slot is not None and request.batch_index == 0:
+            assert request.slot == expect, f"{name}: executing slot {request.slot}, expected {expect}"  # :190
+            self.seqnum[name] = expect + 1
+        request.response_value = b"ok"
+        return True
+
+    def checkpoint(self, name):
+        return self.state.get(name, b"").hex()
+
+    def restore(self, name, state):
+        self.state[name] = bytes.fromhex(state) if state else b""
+        return True
+
+
+@dataclass
+class RequestPacket:
+    """paxospackets/RequestPacket.java essentials."""
+    paxos_id: str
+    request_id: int
+    request_value: bytes
+    stop: bool = False
+    entry_replica: int = -1
+    entry_time: float = 0.0
+    response_value: Optional[bytes] = None
+    slot: Optional[int] = None
+    batch_index: int = 0
+    callback: Optional[Callable[["RequestPacket", bool], None]] = field(default=None, repr=False)
+
+
+@dataclass
+class _Instance:
+    gid: int
+    version: int
+    members: Sequence[int]
+    stopped: bool = False
+
+
+class PaxosManager:
+    """Mirror of the PaxosManager calls on the hot path, for co-located replicas."""
+
+    def __init__(self, engine: Engine, apps: Sequence[Replicable], nodes: Sequence[int]):
+        if len(apps) != engine.n_lanes or len(nodes) != engine.n_lanes:
+            raise ValueError("one app and one node id per lane")
+        self.engine = engine
+        self.apps = list(apps)
+        self.nodes = list(nodes)
+        self.instances: Dict[str, _Instance] = {}
+        self.gid_name: Dict[int, str] = {}
+        self.free_gids: List[int] = []
+        self.next_gid = 0
+        self.queue: Dict[str, List[RequestPacket]] = {}  # RequestBatcher.batched :49
+        self.outstanding: Dict[int, RequestPacket] = {}  # PaxosManager.outstanding
+        self.next_request_id = 1
+        self.checkpoints: List[tuple] = []
+        self.num_decisions = 0
+        self.slow_path: List[tuple] = []
+
+    # ---- instance management ------------------------------------------------------------
+    def _alloc_gid(self) -> int:
+        if self.free_gids:
+            return self.free_gids.pop()
+        g = self.next_gid
+        if g >= int(self.engine.cfg.max_groups):
+            raise RuntimeError("PINSTANCES_CAPACITY exceeded")
+        self.next_gid += 1
+        return g
+
+    def createPaxosInstance(self, paxosID: str, version: int, gms: Sequence[int], initialState: Optional[str] = None,
+                            batch: bool = False) -> bool:
+        """PaxosManager.createPaxosInstance :632-662: refuses an existing (paxosID, version' >= version);
+        a higher version replaces a stopped lower one (reconfiguration: stop at e, create at e+1)."""
+        return self.createPaxosInstanceBatch({paxosID: initialState}, gms, version=version, batch=batch)
+
+    def createPaxosInstanceBatch(self, nameStates: Dict[str, Optional[str]], gms: Sequence[int], version: int = 0,
+                                 batch: bool = True) -> bool:
+        """PaxosManager.createPaxosInstance(Map, Set) :664-691 (HotRestoreInfo.createHRI initial rows)."""
+        descs = np.zeros(len(nameStates), dtype=abi.group_desc_dtype)
+        created = True
+        k = 0
+        for name, state in nameStates.items():
+            old = self.instances.get(name)
+            if old is not None:
+                if old.version >= version or not old.stopped:
+                    created = False  # :646-652 "paxos instance already exists"
+                    continue
+                self._release(name)
+            gid = self._alloc_gid()
+            self.instances[name] = _Instance(gid, version, sorted(gms))
+            self.gid_name[gid] = name
+            d = descs[k]
+            d["gid"], d["version"], d["name_hash"], d["n_members"] = gid, version, abi.java_string_hash(name), len(gms)
+            d["members"][: len(gms)] = sorted(gms)
+            d["init_mode"] = abi.INIT_BATCH if batch else abi.INIT_DEFAULT
+            k += 1
+            for app in self.apps:
+                app.restore(name, state)  # PISM ctor :213-217 / putInitialState :692
+        if k:
+            self.engine.create_groups(descs[:k])
+        return created
+
+    def _release(self, name: str):
+        inst = self.instances.pop(name)
+        self.gid_name.pop(inst.gid, None)
+        self.engine.destroy_groups([inst.gid])
+        self.free_gids.append(inst.gid)
+
+    def kill(self, paxosID: str) -> bool:
+        """PaxosManager.kill :2162."""
+        if paxosID not in self.instances:
+            return False
+        self._release(paxosID)
+        return True
+
+    def isStopped(self, paxosID: str) -> bool:
+        inst = self.instances.get(paxosID)
+        return inst is None or inst.stopped
+
+    def getVersion(self, paxosID: str) -> Optional[int]:
+        inst = self.instances.get(paxosID)
+        return None if inst is None else inst.version
+
+    # ---- proposing ----------------------------------------------------------------------------
+    def propose(self, paxosID: str, requestValue: bytes, callback=None, entry_node: Optional[int] = None,
+                stop: bool = False, version: Optional[int] = None) -> Optional[int]:
+        """PaxosManager.propose :1214-1243: returns the request id, or None when the instance does not
+        exist (or the version does not match, PISM :441-447)."""
+        inst = self.instances.get(paxosID)
+        if inst is None or (version is not None and version != inst.version):
+            return None
+        rid = self.next_request_id
+        self.next_request_id += 1
+        req = RequestPacket(paxosID, rid, bytes(requestValue), stop=stop,
+                            entry_replica=self.nodes[0] if entry_node is None else entry_node,
+                            entry_time=time.time(), callback=callback)
+        self.queue.setdefault(paxosID, []).append(req)  # RequestBatcher.enqueueImpl :112-129
+        self.outstanding[rid] = req
+        return rid
+
+    def proposeStop(self, paxosID: str, version: int, requestValue: bytes, callback=None) -> Optional[int]:
+        """PaxosManager.proposeStop: a STOP request for epoch `version`."""
+        return self.propose(paxosID, requestValue, callback, stop=True, version=version)
+
+    # ---- one pass of the hot path -----------------------------------------------------------------
+    def run_round(self) -> int:
+        """Drain the request queues through the engine; returns the number of executed slots."""
+        names = [n for n in self.queue if self.queue[n]]
+        if not names:
+            return 0
+        reqs_l: List[RequestPacket] = []
+        for n in sorted(names, key=lambda x: self.instances[x].gid if x in self.instances else -1):
+            if n not in self.instances:
+                for r in self.queue[n]:
+                    self.outstanding.pop(r.request_id, None)
+                continue
+            reqs_l.extend(self.queue[n])
+        self.queue = {}
+        if not reqs_l:
+            return 0
+        n = len(reqs_l)
+        reqs = np.zeros(n, dtype=abi.request_dtype)
+        offs, off = [], 0
+        for r in reqs_l:
+            offs.append(off)
+            off += (len(r.request_value) + 15) // 16 * 16
+        payload = np.zeros(off, dtype=np.uint8)
+        for i, r in enumerate(reqs_l):
+            inst = self.instances[r.paxos_id]
+            lane = self.nodes.index(r.entry_replica) if r.entry_replica in self.nodes else 0
+            reqs[i]["gid"] = inst.gid
+            reqs[i]["flags"] = (abi.F_STOP if r.stop else 0) | (lane << 8)
+            reqs[i]["req_id"] = r.request_id
+            reqs[i]["payload_off"], reqs[i]["payload_len"] = offs[i], len(r.request_value)
+            reqs[i]["entry_node"] = r.entry_replica
+            payload[offs[i]: offs[i] + len(r.request_value)] = np.frombuffer(r.request_value, dtype=np.uint8)
+        status, ex, extra = self.engine.round(reqs, payload)
+        # requests the engine could not propose go back to the host slow path (retry / forward / prepare)
+        for i, st in enumerate(status):
+            if st in (abi.RS_BACKPRESSURE,):
+                self.queue.setdefault(reqs_l[i].paxos_id, []).append(reqs_l[i])
+            elif st < 0 and st != abi.RS_BATCHED:
+                self.slow_path.append((reqs_l[i].paxos_id, reqs_l[i].request_id, int(st)))
+                self.outstanding.pop(reqs_l[i].request_id, None)
+        # batches: a positive status starts a slot, RS_BATCHED entries follow it (RequestPacket.batched)
+        batches: Dict[int, List[RequestPacket]] = {}
+        cur = None
+        for i, st in enumerate(status):
+            if st > 0:
+                cur = reqs_l[i].request_id
+                batches[cur] = [reqs_l[i]]
+            elif st == abi.RS_BATCHED and cur is not None:
+                batches[cur].append(reqs_l[i])
+        return self._apply(np.concatenate([ex, extra]), batches)
+
+    def _apply(self, ex: np.ndarray, batches: Dict[int, List[RequestPacket]]) -> int:
+        """PISM.execute :1755-1842 + PaxosManager.executed :311-330 for every EXEC record, per group in
+        slot order (primary and extra records of one call interleave)."""
+        ex = ex[(ex["flags"] & abi.F_VOID) == 0]
+        if len(ex) == 0:
+            return 0
+        lanes = (ex["flags"] >> 12) & 0xF
+        ex = ex[np.lexsort((ex["slot"], ex["gid"], lanes))]
+        executed = 0
+        for x in ex:
+            lane = int((x["flags"] >> 12) & 0xF)
+            name = self.gid_name.get(int(x["gid"]))
+            if name is None:
+                continue
+            batch = batches.get(int(x["req_id"]))
+            if batch is None:  # decided elsewhere / earlier round: only the id is known here
+                first = self.outstanding.get(int(x["req_id"]))
+                batch = [first] if first is not None else []
+            is_stop = bool(x["flags"] & abi.F_STOP)
+            for bi, req in enumerate(batch):
+                view = RequestPacket(req.paxos_id, req.request_id, req.request_value, req.stop, req.entry_replica,
+                                     req.entry_time, slot=int(x["slot"]), batch_index=bi, callback=req.callback)
+                entry = req.entry_replica == self.nodes[lane]
+                self.apps[lane].execute(name, view, do_not_reply_to_client=not entry)  # :1802-1806
+                if entry:  # PaxosManager.executed: callback / response from the entry replica only
+                    req.response_value, req.slot = view.response_value, view.slot
+                    self.outstanding.pop(req.request_id, None)
+                    if req.callback is not None:
+                        req.callback(req, True)
+                # PISM.execute :1813-1815: the acceptor is already STOPPED when a stop batch executes,
+                # so only the first request of a stop batch is executed
+                if is_stop:
+                    break
+            if x["flags"] & abi.F_CKPT:  # PISM.shouldCheckpoint :2037 -> consistentCheckpoint :1711-1723
+                self.checkpoints.append((name, lane, int(x["slot"]), self.apps[lane].checkpoint(name)))
+            if is_stop:
+                self.instances[name].stopped = True
+            if lane == 0:
+                self.num_decisions += 1
+            executed += 1
+        return executed
+
+    def flush(self, max_rounds: int = 64) -> int:
+        total = 0
+        for _ in range(max_rounds):
+            if not any(self.queue.values()):
+                break
+            total += self.run_round()
+        return total

@@ -175,8 +175,10 @@ typedef struct gpx_exec_rec {
 /* ---- log ring ---------------------------------------------------------------
  * One ring per lane.  A ring is a sequence of segments, one per kernel launch
  * that logs: [gpx_log_seg_hdr 64 B][n_slots record images][payload area].
- * ACCEPT segment: images are gpx_accept_rec (48 B); image.payload_off is relative
- * to the segment's payload area; unlogged records have GPX_F_VOID.
+ * ACCEPT segment (rec_bytes 48): the images are stored as two planes, n_slots x 32 B pvalue
+ * headers followed by n_slots x 16 B {payload_off,payload_len,nreq,sender}, so that every image
+ * moves as one 256-bit plus one 128-bit aligned store; image.payload_off is relative to the
+ * segment's payload area; unlogged records have GPX_F_VOID.  Segments are 32-byte multiples.
  * DECISION segment: images are gpx_decision_rec (32 B), no payload area.
  * (SQLPaxosLogger.journal frames {int32 len}{packet bytes}, :1000-1003; gpx_wire_*
  * re-frames segments into that byte format.) */
@@ -332,12 +334,28 @@ int gpx_handle_decisions(gpx_engine* e, uint32_t n, const gpx_decision_rec* deci
                          gpx_exec_rec* out_exec, gpx_exec_rec* out_extra_exec, uint32_t extra_cap,
                          uint32_t* n_extra);
 
-/* One full round for co-located replicas: propose -> accept -> tally -> commit, all
- * inter-replica records staying in HBM.  Host request buffers in, EXEC records out
- * (out_exec[n * n_lanes], extras appended to out_extra_exec). */
+/* Fused co-located path (PaxosManager.sendOrLoopback :2116-2128): per ACCEPT, in batch order,
+ * handleAccept at every addressed lane; replies addressed to a usable LOCAL coordinator lane are
+ * handled at once (the others are returned in out_replies, VOID where consumed); a resulting
+ * DECISION (out_decisions[n], VOID where none) is handled at every local lane before the next
+ * ACCEPT.  out_exec[n * n_lanes].  EXEC records of one call are applied per group in slot order
+ * (primary and extra records interleave). */
+int gpx_handle_accepts_fused(gpx_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
+                             uint64_t blob_bytes, gpx_accept_reply_rec* out_replies,
+                             gpx_decision_rec* out_decisions, gpx_exec_rec* out_exec,
+                             gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
+
+/* One full round for co-located replicas.  gpx_round: RequestBatcher + propose, then the fused
+ * accept -> tally -> commit per ACCEPT with replies, decisions and rows kept in registers.
+ * gpx_round_phases: the same round phase by phase (all ACCEPTs, then all replies, then all
+ * DECISIONs), inter-replica records going through HBM.  Host request buffers in, EXEC records out
+ * (out_exec[*n_exec_slots], extras appended to out_extra_exec). */
 int gpx_round(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
               uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
               gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
+int gpx_round_phases(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                     uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
+                     gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
 
 /* ---- log ring ------------------------------------------------------------------- */
 /* copy ring bytes [from, min(head, from+cap)) of `lane` into dst; *head receives the ring head */
@@ -367,7 +385,8 @@ typedef struct gpx_dev_round_bufs {
   int32_t* status;             /* [n] device */
   gpx_exec_rec* exec;          /* [n * n_lanes] device */
 } gpx_dev_round_bufs;
-int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream);
+int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream);        /* fused */
+int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream); /* phase by phase */
 /* per-kernel CUDA-event timing of the last gpx_round_device calls (ms, accumulated) */
 typedef struct gpx_kernel_times {
   double propose_ms, accept_ms, tally_ms, commit_ms;

@@ -578,7 +578,7 @@ struct gpxo_engine {
   u64 segBegin(u32 lane, uint16_t type, u32 n_slots, u32 rec_bytes, u64 payload_bytes) {
     Lane& ln = lanes[lane];
     u64 off = ln.ring.size();
-    u64 total = 64 + (u64)n_slots * rec_bytes + ((payload_bytes + 15) & ~(u64)15);
+    u64 total = (64 + (u64)n_slots * rec_bytes + ((payload_bytes + 15) & ~(u64)15) + 31) & ~(u64)31;
     ln.ring.resize(off + total, 0);
     gpx_log_seg_hdr h;
     memset(&h, 0, sizeof h);
@@ -1005,6 +1005,218 @@ int gpxo_propose(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const 
   return GPX_OK;
 }
 
+/* ---- per-record bodies (shared by the phase-by-phase and the fused entry points) ---------- */
+
+/* PISM.handleAccept :1080-1166 for ACCEPT i at lane l */
+static void acceptAtLane(gpxo_engine* e, u32 i, u32 l, const gpx_accept_rec& r, const uint8_t* blob, u64 seg, u64 pay,
+                         gpx_accept_reply_rec& rep, std::vector<gpx_exec_rec>& extras) {
+  memset(&rep, 0, sizeof rep);
+  rep.gid = r.h.gid;
+  rep.slot = r.h.slot;
+  rep.who = GPX_WHO(0xff, 0xff, GPX_F_VOID);
+  gpx_accept_rec img = r;
+  img.h.flags = GPX_F_VOID;
+  /* ACCEPT segment: [hdr][n x 32 B pvalue-header plane][n x 16 B extension plane][payload] */
+  const u32 nslots = ((const gpx_log_seg_hdr*)&e->lanes[l].ring[seg])->n_slots;
+  auto writeImg = [&]() {
+    memcpy(&e->lanes[l].ring[seg + 64 + (u64)i * 32], &img, 32);
+    memcpy(&e->lanes[l].ring[seg + 64 + (u64)nslots * 32 + (u64)i * 16], (const uint8_t*)&img + 32, 16);
+  };
+  if (!(r.h.dst_mask & (1u << l)) || (r.h.flags & GPX_F_VOID)) {
+    writeImg();
+    return;
+  }
+  if (!e->usable(r.h.gid, l)) { /* PISM :456-460 stopped / no instance -> dropped */
+    e->ctr.accepts_dropped++;
+    writeImg();
+    return;
+  }
+  Group& g = e->groups[r.h.gid];
+  Acceptor& A = e->lanes[l].acc[r.h.gid];
+  int myIdx = e->memberIdx(g, e->lanes[l].node);
+  if (myIdx < 0) {
+    e->ctr.accepts_dropped++;
+    writeImg();
+    return;
+  }
+  if (e->W() > 0 && jsub(r.h.slot, A._slot) >= e->W()) { /* device window rule */
+    A.flags |= GF_OVERFLOW;
+    e->ctr.window_overflow++;
+    e->ctr.accepts_dropped++;
+    writeImg();
+    return;
+  }
+  e->ctr.accepts_handled++;
+  PValue accept;
+  accept.slot = r.h.slot;
+  accept.bal = Ballot{r.h.bnum, r.h.bcoord};
+  accept.req_id = r.h.req_id;
+  accept.stop = (r.h.flags & GPX_F_STOP) != 0;
+  accept.has_value = true;
+  accept.median_cp = r.h.median_cp;
+  accept.nreq = r.nreq;
+  accept.plen = r.payload_len;
+  accept.frame_ref = (u32)((pay + r.payload_off) / 16);
+  /* prev = paxosState.getAccept(accept.slot) :1123 */
+  bool hasPrev = A.acceptedProposals.count(accept.slot) != 0;
+  PValue prev;
+  if (hasPrev) prev = A.acceptedProposals[accept.slot];
+  /* a duplicate of an already accepted pvalue keeps the frame it was logged in */
+  if (hasPrev && prev.bal.equals(accept.bal)) accept.frame_ref = prev.frame_ref;
+  Ballot ballot;
+  if (!A.acceptAndUpdateBallot(accept, &ballot)) {
+    writeImg();
+    return;
+  }
+  /* AcceptReplyPacket :1139-1143 */
+  rep.bnum = ballot.num;
+  rep.bcoord = ballot.coord;
+  rep.max_cp = e->cfg.gc_majority_executed ? A._slot - 1 : lastCheckpointSlot(A._slot - 1, g.cpi);
+  rep.req_id = r.h.req_id;
+  int dstIdx = e->memberIdx(g, r.sender);
+  /* toLog :1146-1149 */
+  bool toLog = accept.bal.compareTo(ballot) >= 0 && jsub(accept.slot, A.acceptedGCSlot) > 0 &&
+               (!hasPrev || prev.bal.compareTo(accept.bal) < 0);
+  bool nack = ballot.compareTo(accept.bal) > 0;
+  u32 rf = (toLog ? GPX_F_LOGGED : 0) | (nack ? GPX_F_NACK : 0);
+  rep.who = GPX_WHO(myIdx, dstIdx < 0 ? 0xff : dstIdx, rf);
+  if (nack)
+    e->ctr.accepts_nacked++;
+  else
+    e->ctr.accepts_acked++;
+  if (toLog) {
+    e->ctr.accepts_logged++;
+    img = r;
+    img.h.dst_mask = (uint16_t)(1u << l);
+    memcpy(&e->lanes[l].ring[pay + r.payload_off], blob + r.payload_off, r.payload_len);
+  }
+  writeImg();
+  /* reconstructDecision(accept.slot) -> handleCommittedRequest :1158-1161 */
+  PValue rd;
+  if (A.reconstructDecision(accept.slot, &rd)) {
+    /* the re-log of the reconstructed decision (logDecision :1446) is deliberately omitted:
+     * its placeholder was logged on arrival and replay of {placeholder, accept} is
+     * idempotent (DESIGN.md "Deliberate omissions") */
+    std::vector<PValue> ex;
+    e->EEC(g, A, rd, ex);
+    for (auto& x : ex) put_event_exec(extras, e->makeExec(r.h.gid, l, g, x, true));
+  }
+}
+
+/* the local lane that must tally this reply, or -1 (void / unknown group / remote or unusable coordinator) */
+static int replyLane(gpxo_engine* e, const gpx_accept_reply_rec& r, bool count) {
+  u32 wf = GPX_WHO_FLAGS(r.who);
+  if (wf & GPX_F_VOID) return -1;
+  int lane = -1;
+  if (r.gid < e->cfg.max_groups && e->groups[r.gid].live) {
+    Group& g = e->groups[r.gid];
+    u32 dstIdx = GPX_WHO_DST(r.who);
+    if (dstIdx < g.members.size()) {
+      lane = e->laneOfNode(g.members[dstIdx]);
+      if (lane >= 0 && !e->usable(r.gid, (u32)lane)) lane = -1;
+    }
+  }
+  if (lane < 0 && count) e->ctr.replies_ignored++;
+  return lane;
+}
+
+/* PISM.handleAcceptReply :1248-1365 for one reply at coordinator lane `lane`; true iff a DECISION results */
+static bool replyAtLane(gpxo_engine* e, int lane, const gpx_accept_reply_rec& r, gpx_decision_rec* d) {
+  Group& g = e->groups[r.gid];
+  u32 accIdx = GPX_WHO_ACC(r.who);
+  e->ctr.replies_handled++;
+  Coordinator& C = e->lanes[lane].coord[r.gid];
+  i32 acceptorNode = accIdx < g.members.size() ? g.members[accIdx] : INT32_MIN;
+  Ballot rb{r.bnum, r.bcoord};
+  PValue pv;
+  int t = C.handleAcceptReply(g.members, acceptorNode, rb, r.slot, r.max_cp, &pv);
+  /* nullifyCoordinatorIfPreemptedFully :1353-1356 / PaxosCoordinator.isPreemptedFully :109-114 */
+  if (C.exists && rb.compareTo(C.getBallot()) > 0 && C.preemptedFully()) {
+    C = Coordinator();
+    C.W = e->W();
+    e->ctr.coordinators_resigned++;
+  }
+  if (t == PT_DECISION) {
+    d->gid = r.gid;
+    d->slot = pv.slot;
+    d->bnum = pv.bal.num;
+    d->bcoord = pv.bal.coord;
+    d->median_cp = pv.median_cp;
+    d->flags = (uint16_t)(GPX_F_DECISION | (pv.stop ? GPX_F_STOP : 0));
+    d->dst_mask = (uint16_t)e->localMask(g);
+    d->req_id = pv.req_id;
+    e->ctr.decisions_made++;
+    return true;
+  }
+  if (t == PT_PREEMPTED) e->ctr.preempted++; /* dropped: FORWARD_PREEMPTED_REQUESTS=false PaxosConfig.java:927 */
+  return false;
+}
+
+/* PISM.handleBatchedCommit :1480-1528 (one slot) -> handleCommittedRequest :1432-1478 ->
+ * extractExecuteAndCheckpoint :1619-1701, for DECISION i at lane l */
+static void decisionAtLane(gpxo_engine* e, u32 i, u32 l, const gpx_decision_rec& r, u64 seg, gpx_exec_rec& ex,
+                           std::vector<gpx_exec_rec>& extras) {
+  memset(&ex, 0, sizeof ex);
+  ex.gid = r.gid;
+  ex.slot = r.slot;
+  ex.flags = GPX_F_VOID | (l << 12);
+  gpx_decision_rec img = r;
+  img.flags = GPX_F_VOID;
+  auto writeImg = [&]() { memcpy(&e->lanes[l].ring[seg + 64 + (u64)i * 32], &img, 32); };
+  if (!(r.dst_mask & (1u << l)) || (r.flags & GPX_F_VOID)) {
+    writeImg();
+    return;
+  }
+  if (!e->usable(r.gid, l)) {
+    e->ctr.decisions_dropped++;
+    writeImg();
+    return;
+  }
+  Group& g = e->groups[r.gid];
+  Acceptor& A = e->lanes[l].acc[r.gid];
+  if (e->W() > 0 && jsub(r.slot, A._slot) >= e->W()) {
+    A.flags |= GF_OVERFLOW | GF_NEEDS_SYNC;
+    e->ctr.window_overflow++;
+    e->ctr.decisions_dropped++;
+    writeImg();
+    return;
+  }
+  e->ctr.decisions_handled++;
+  Ballot cb{r.bnum, r.bcoord};
+  PValue d;
+  auto a = A.acceptedProposals.find(r.slot);
+  if (a != A.acceptedProposals.end() && a->second.bal.equals(cb)) { /* :1488 */
+    d = a->second;
+    d.median_cp = r.median_cp;
+    d.has_value = true;
+  } else { /* placeholder :1514-1522 */
+    d = PValue();
+    d.slot = r.slot;
+    d.bal = cb;
+    d.median_cp = r.median_cp;
+    d.has_value = false;
+    e->ctr.placeholders++;
+  }
+  (void)e->decisionLogImage(A, r.gid, l, d, &img); /* logDecision :1446-1466 (img stays VOID when not logged) */
+  writeImg();
+  std::vector<PValue> xs;
+  e->EEC(g, A, d, xs);
+  for (size_t k = 0; k < xs.size(); k++) {
+    if (k == 0)
+      ex = e->makeExec(r.gid, l, g, xs[k], false);
+    else
+      extras.push_back(e->makeExec(r.gid, l, g, xs[k], true));
+  }
+  if (!A.isStopped() && !d.has_value && jsub(d.slot, A._slot) >= 0 && xs.empty()) A.flags |= GF_NEEDS_SYNC;
+}
+
+static void emitExtras(const std::vector<gpx_exec_rec>& extras, gpx_exec_rec* out, uint32_t cap, uint32_t* n_extra) {
+  u32 ne = 0;
+  for (auto& x : extras)
+    if (ne < cap && out) out[ne++] = x;
+  if (n_extra) *n_extra = (u32)extras.size();
+}
+
 /* PISM.handleAccept :1080-1166 at every addressed local lane */
 int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
                         uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra_exec,
@@ -1016,102 +1228,10 @@ int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accept
     pay[l] = seg[l] + 64 + (u64)n * 48;
   }
   std::vector<gpx_exec_rec> extras;
-  for (u32 i = 0; i < n; i++) {
-    const gpx_accept_rec& r = accepts[i];
-    for (u32 l = 0; l < L; l++) {
-      gpx_accept_reply_rec& rep = out_replies[(u64)i * L + l];
-      memset(&rep, 0, sizeof rep);
-      rep.gid = r.h.gid;
-      rep.slot = r.h.slot;
-      rep.who = GPX_WHO(0xff, 0xff, GPX_F_VOID);
-      gpx_accept_rec img = r;
-      img.h.flags = GPX_F_VOID;
-      auto writeImg = [&]() { memcpy(&e->lanes[l].ring[seg[l] + 64 + (u64)i * 48], &img, 48); };
-      if (!(r.h.dst_mask & (1u << l)) || (r.h.flags & GPX_F_VOID)) {
-        writeImg();
-        continue;
-      }
-      if (!e->usable(r.h.gid, l)) { /* PISM :456-460 stopped / no instance -> dropped */
-        e->ctr.accepts_dropped++;
-        writeImg();
-        continue;
-      }
-      Group& g = e->groups[r.h.gid];
-      Acceptor& A = e->lanes[l].acc[r.h.gid];
-      int myIdx = e->memberIdx(g, e->lanes[l].node);
-      if (myIdx < 0) {
-        e->ctr.accepts_dropped++;
-        writeImg();
-        continue;
-      }
-      if (e->W() > 0 && jsub(r.h.slot, A._slot) >= e->W()) { /* device window rule */
-        A.flags |= GF_OVERFLOW;
-        e->ctr.window_overflow++;
-        e->ctr.accepts_dropped++;
-        writeImg();
-        continue;
-      }
-      e->ctr.accepts_handled++;
-      PValue accept;
-      accept.slot = r.h.slot;
-      accept.bal = Ballot{r.h.bnum, r.h.bcoord};
-      accept.req_id = r.h.req_id;
-      accept.stop = (r.h.flags & GPX_F_STOP) != 0;
-      accept.has_value = true;
-      accept.median_cp = r.h.median_cp;
-      accept.nreq = r.nreq;
-      accept.plen = r.payload_len;
-      accept.frame_ref = (u32)((pay[l] + r.payload_off) / 16);
-      /* prev = paxosState.getAccept(accept.slot) :1123 */
-      bool hasPrev = A.acceptedProposals.count(accept.slot) != 0;
-      PValue prev;
-      if (hasPrev) prev = A.acceptedProposals[accept.slot];
-      /* a duplicate of an already accepted pvalue keeps the frame it was logged in */
-      if (hasPrev && prev.bal.equals(accept.bal)) accept.frame_ref = prev.frame_ref;
-      Ballot ballot;
-      if (!A.acceptAndUpdateBallot(accept, &ballot)) {
-        writeImg();
-        continue;
-      }
-      /* AcceptReplyPacket :1139-1143 */
-      rep.bnum = ballot.num;
-      rep.bcoord = ballot.coord;
-      rep.max_cp = e->cfg.gc_majority_executed ? A._slot - 1 : lastCheckpointSlot(A._slot - 1, g.cpi);
-      rep.req_id = r.h.req_id;
-      int dstIdx = e->memberIdx(g, r.sender);
-      /* toLog :1146-1149 */
-      bool toLog = accept.bal.compareTo(ballot) >= 0 && jsub(accept.slot, A.acceptedGCSlot) > 0 &&
-                   (!hasPrev || prev.bal.compareTo(accept.bal) < 0);
-      bool nack = ballot.compareTo(accept.bal) > 0;
-      u32 rf = (toLog ? GPX_F_LOGGED : 0) | (nack ? GPX_F_NACK : 0);
-      rep.who = GPX_WHO(myIdx, dstIdx < 0 ? 0xff : dstIdx, rf);
-      if (nack)
-        e->ctr.accepts_nacked++;
-      else
-        e->ctr.accepts_acked++;
-      if (toLog) {
-        e->ctr.accepts_logged++;
-        img = r;
-        img.h.dst_mask = (uint16_t)(1u << l);
-        memcpy(&e->lanes[l].ring[pay[l] + r.payload_off], blob + r.payload_off, r.payload_len);
-      }
-      writeImg();
-      /* reconstructDecision(accept.slot) -> handleCommittedRequest :1158-1161 */
-      PValue rd;
-      if (A.reconstructDecision(accept.slot, &rd)) {
-        /* the re-log of the reconstructed decision (logDecision :1446) is deliberately omitted:
-         * its placeholder was logged on arrival and replay of {placeholder, accept} is
-         * idempotent (DESIGN.md "Deliberate omissions") */
-        std::vector<PValue> ex;
-        e->EEC(g, A, rd, ex);
-        for (auto& x : ex) put_event_exec(extras, e->makeExec(r.h.gid, l, g, x, true));
-      }
-    }
-  }
-  u32 ne = 0;
-  for (auto& x : extras)
-    if (ne < extra_cap) out_extra_exec[ne++] = x;
-  if (n_extra) *n_extra = (u32)extras.size();
+  for (u32 i = 0; i < n; i++)
+    for (u32 l = 0; l < L; l++)
+      acceptAtLane(e, i, l, accepts[i], blob, seg[l], pay[l], out_replies[(u64)i * L + l], extras);
+  emitExtras(extras, out_extra_exec, extra_cap, n_extra);
   return GPX_OK;
 }
 
@@ -1120,133 +1240,77 @@ int gpxo_handle_accept_replies(gpxo_engine* e, uint32_t n, const gpx_accept_repl
                                gpx_decision_rec* out_decisions, uint32_t* n_decisions) {
   u32 nd = 0;
   for (u32 i = 0; i < n; i++) {
-    const gpx_accept_reply_rec& r = replies[i];
-    u32 wf = GPX_WHO_FLAGS(r.who);
-    if (wf & GPX_F_VOID) continue;
-    if (r.gid >= e->cfg.max_groups || !e->groups[r.gid].live) {
-      e->ctr.replies_ignored++;
-      continue;
-    }
-    Group& g = e->groups[r.gid];
-    u32 dstIdx = GPX_WHO_DST(r.who), accIdx = GPX_WHO_ACC(r.who);
-    if (dstIdx >= g.members.size()) {
-      e->ctr.replies_ignored++;
-      continue;
-    }
-    int lane = e->laneOfNode(g.members[dstIdx]);
-    if (lane < 0 || !e->usable(r.gid, (u32)lane)) {
-      e->ctr.replies_ignored++;
-      continue;
-    }
-    e->ctr.replies_handled++;
-    Coordinator& C = e->lanes[lane].coord[r.gid];
-    i32 acceptorNode = accIdx < g.members.size() ? g.members[accIdx] : INT32_MIN;
-    Ballot rb{r.bnum, r.bcoord};
-    PValue pv;
-    int t = C.handleAcceptReply(g.members, acceptorNode, rb, r.slot, r.max_cp, &pv);
-    /* nullifyCoordinatorIfPreemptedFully :1353-1356 / PaxosCoordinator.isPreemptedFully :109-114 */
-    if (C.exists && rb.compareTo(C.getBallot()) > 0 && C.preemptedFully()) {
-      C = Coordinator();
-      C.W = e->W();
-      e->ctr.coordinators_resigned++;
-    }
-    if (t == PT_DECISION) {
-      gpx_decision_rec& d = out_decisions[nd++];
-      d.gid = r.gid;
-      d.slot = pv.slot;
-      d.bnum = pv.bal.num;
-      d.bcoord = pv.bal.coord;
-      d.median_cp = pv.median_cp;
-      d.flags = (uint16_t)(GPX_F_DECISION | (pv.stop ? GPX_F_STOP : 0));
-      d.dst_mask = (uint16_t)e->localMask(g);
-      d.req_id = pv.req_id;
-      e->ctr.decisions_made++;
-    } else if (t == PT_PREEMPTED) {
-      e->ctr.preempted++; /* dropped: FORWARD_PREEMPTED_REQUESTS=false PaxosConfig.java:927 */
-    }
+    int lane = replyLane(e, replies[i], true);
+    if (lane < 0) continue;
+    if (replyAtLane(e, lane, replies[i], &out_decisions[nd])) nd++;
   }
   *n_decisions = nd;
   return GPX_OK;
 }
 
-/* PISM.handleBatchedCommit :1480-1528 per slot -> handleCommittedRequest :1432-1478 ->
- * extractExecuteAndCheckpoint :1619-1701 */
+/* PISM.handleBatchedCommit :1480-1528 per slot -> handleCommittedRequest -> extractExecuteAndCheckpoint */
 int gpxo_handle_decisions(gpxo_engine* e, uint32_t n, const gpx_decision_rec* decisions, gpx_exec_rec* out_exec,
                           gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
   u32 L = e->L();
   std::vector<u64> seg(L);
   for (u32 l = 0; l < L; l++) seg[l] = e->segBegin(l, GPX_F_DECISION, n, 32, 0);
   std::vector<gpx_exec_rec> extras;
-  for (u32 i = 0; i < n; i++) {
-    const gpx_decision_rec& r = decisions[i];
-    for (u32 l = 0; l < L; l++) {
-      gpx_exec_rec& ex = out_exec[(u64)i * L + l];
-      memset(&ex, 0, sizeof ex);
-      ex.gid = r.gid;
-      ex.slot = r.slot;
-      ex.flags = GPX_F_VOID | (l << 12);
-      gpx_decision_rec img = r;
-      img.flags = GPX_F_VOID;
-      auto writeImg = [&]() { memcpy(&e->lanes[l].ring[seg[l] + 64 + (u64)i * 32], &img, 32); };
-      if (!(r.dst_mask & (1u << l)) || (r.flags & GPX_F_VOID)) {
-        writeImg();
-        continue;
-      }
-      if (!e->usable(r.gid, l)) {
-        e->ctr.decisions_dropped++;
-        writeImg();
-        continue;
-      }
-      Group& g = e->groups[r.gid];
-      Acceptor& A = e->lanes[l].acc[r.gid];
-      if (e->W() > 0 && jsub(r.slot, A._slot) >= e->W()) {
-        A.flags |= GF_OVERFLOW | GF_NEEDS_SYNC;
-        e->ctr.window_overflow++;
-        e->ctr.decisions_dropped++;
-        writeImg();
-        continue;
-      }
-      e->ctr.decisions_handled++;
-      Ballot cb{r.bnum, r.bcoord};
-      PValue d;
-      auto a = A.acceptedProposals.find(r.slot);
-      if (a != A.acceptedProposals.end() && a->second.bal.equals(cb)) { /* :1488 */
-        d = a->second;
-        d.median_cp = r.median_cp;
-        d.has_value = true;
-      } else { /* placeholder :1514-1522 */
-        d = PValue();
-        d.slot = r.slot;
-        d.bal = cb;
-        d.median_cp = r.median_cp;
-        d.has_value = false;
-        e->ctr.placeholders++;
-      }
-      if (e->decisionLogImage(A, r.gid, l, d, &img)) { /* logDecision :1446-1466 */
-      }
-      writeImg();
-      std::vector<PValue> xs;
-      e->EEC(g, A, d, xs);
-      for (size_t k = 0; k < xs.size(); k++) {
-        if (k == 0)
-          ex = e->makeExec(r.gid, l, g, xs[k], false);
-        else
-          extras.push_back(e->makeExec(r.gid, l, g, xs[k], true));
-      }
-      if (!A.isStopped() && !d.has_value && jsub(d.slot, A._slot) >= 0 && xs.empty()) A.flags |= GF_NEEDS_SYNC;
-    }
-  }
-  u32 ne = 0;
-  for (auto& x : extras)
-    if (ne < extra_cap) out_extra_exec[ne++] = x;
-  if (n_extra) *n_extra = (u32)extras.size();
+  for (u32 i = 0; i < n; i++)
+    for (u32 l = 0; l < L; l++) decisionAtLane(e, i, l, decisions[i], seg[l], out_exec[(u64)i * L + l], extras);
+  emitExtras(extras, out_extra_exec, extra_cap, n_extra);
   return GPX_OK;
 }
 
-/* one full round for co-located replicas (PaxosManager.send routing :2098-2128) */
-int gpxo_round(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
-               uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
-               gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+/* Fused co-located path (the order the device's k_act kernel defines): per ACCEPT, in batch order --
+ * handleAccept at every addressed lane; replies whose destination coordinator is a LOCAL lane are handled
+ * at once (PaxosManager.send loopback, PaxosManager.java:2116-2128), the others are returned in
+ * out_replies; a resulting DECISION is handled at every local lane before the next ACCEPT.
+ * out_replies[n*L] (VOID where consumed locally), out_decisions[n] (VOID where none), out_exec[n*L]. */
+int gpxo_handle_accepts_fused(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
+                              uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_decision_rec* out_decisions,
+                              gpx_exec_rec* out_exec, gpx_exec_rec* out_extra_exec, uint32_t extra_cap,
+                              uint32_t* n_extra) {
+  u32 L = e->L();
+  std::vector<u64> seg(L), pay(L), dseg(L);
+  for (u32 l = 0; l < L; l++) {
+    seg[l] = e->segBegin(l, GPX_F_ACCEPT, n, 48, blob_bytes);
+    pay[l] = seg[l] + 64 + (u64)n * 48;
+    dseg[l] = e->segBegin(l, GPX_F_DECISION, n, 32, 0);
+  }
+  std::vector<gpx_exec_rec> extras;
+  for (u32 i = 0; i < n; i++) {
+    for (u32 l = 0; l < L; l++)
+      acceptAtLane(e, i, l, accepts[i], blob, seg[l], pay[l], out_replies[(u64)i * L + l], extras);
+    gpx_decision_rec d;
+    memset(&d, 0, sizeof d);
+    d.gid = accepts[i].h.gid;
+    d.slot = accepts[i].h.slot;
+    d.flags = GPX_F_VOID;
+    bool decided = false;
+    for (u32 l = 0; l < L; l++) {
+      gpx_accept_reply_rec& rep = out_replies[(u64)i * L + l];
+      int lane = replyLane(e, rep, false);
+      if (lane < 0) continue; /* void, or addressed to a remote coordinator: stays in out_replies */
+      gpx_decision_rec dd;
+      if (replyAtLane(e, lane, rep, &dd) && !decided) {
+        d = dd;
+        decided = true;
+      }
+      rep.bnum = rep.bcoord = rep.max_cp = 0; /* consumed locally */
+      rep.req_id = 0;
+      rep.who = GPX_WHO(0xff, 0xff, GPX_F_VOID);
+    }
+    out_decisions[i] = d;
+    for (u32 l = 0; l < L; l++) decisionAtLane(e, i, l, d, dseg[l], out_exec[(u64)i * L + l], extras);
+  }
+  emitExtras(extras, out_extra_exec, extra_cap, n_extra);
+  return GPX_OK;
+}
+
+/* one full round, phase by phase (all ACCEPTs, then all replies, then all DECISIONs) */
+int gpxo_round_phases(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                      uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
+                      gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
   u32 L = e->L();
   std::vector<gpx_accept_rec> acc(n);
   std::vector<uint8_t> blob(2 * ((payload_bytes + 15) & ~15ull) + 32ull * n + 64);
@@ -1270,6 +1334,27 @@ int gpxo_round(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const ui
   return GPX_OK;
 }
 
+/* one full round for co-located replicas in the fused order (PaxosManager.send routing with loopback
+ * :2098-2128): RequestBatcher + propose, then per ACCEPT accept -> tally -> commit */
+int gpxo_round(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+               uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
+               gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  u32 L = e->L();
+  std::vector<gpx_accept_rec> acc(n);
+  std::vector<uint8_t> blob(2 * ((payload_bytes + 15) & ~15ull) + 32ull * n + 64);
+  u32 na = 0;
+  u64 bb = 0;
+  int rc = gpxo_propose(e, n, reqs, payload, payload_bytes, acc.data(), &na, blob.data(), blob.size(), &bb, status);
+  if (rc) return rc;
+  std::vector<gpx_accept_reply_rec> rep((size_t)na * L + 1);
+  std::vector<gpx_decision_rec> dec((size_t)na + 1);
+  rc = gpxo_handle_accepts_fused(e, na, acc.data(), blob.data(), bb, rep.data(), dec.data(), out_exec, out_extra_exec,
+                                 extra_cap, n_extra);
+  if (rc) return rc;
+  *n_exec_slots = na * L;
+  return GPX_OK;
+}
+
 int gpxo_log_read(gpxo_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_t cap, uint64_t* n_copied,
                   uint64_t* head) {
   if (lane >= e->L()) return GPX_ERANGE;
@@ -1279,6 +1364,14 @@ int gpxo_log_read(gpxo_engine* e, uint32_t lane, uint64_t from, void* dst, uint6
   if (nb) memcpy(dst, r.data() + from, nb);
   if (n_copied) *n_copied = nb;
   if (head) *head = h;
+  return GPX_OK;
+}
+
+/* drop the in-memory log (a drained / garbage-collected journal); used by long CPU-baseline runs */
+int gpxo_log_truncate(gpxo_engine* e) {
+  for (auto& ln : e->lanes) {
+    std::vector<uint8_t>().swap(ln.ring);
+  }
   return GPX_OK;
 }
 

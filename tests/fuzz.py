@@ -51,6 +51,7 @@ class Fuzzer:
         self.history = [dict() for _ in range(R)]  # lane -> gid -> [(slot, req_id)]
         self.stopped = set()
         self.rival_bnum = np.zeros(G, dtype=np.int64)
+        self.max_proposed = np.zeros(G, dtype=np.int64)  # highest slot any coordinator issued an ACCEPT for
 
     # ---- comparison helpers ----------------------------------------------------------
     def _all(self, fn):
@@ -111,6 +112,7 @@ class Fuzzer:
         for x in canon(acc0):
             o, ln = int(x["payload_off"]), int(x["payload_len"])
             self.acc_pool.append((x.copy(), blob0[o: o + ln].copy()))
+            self.max_proposed[int(x["gid"])] = max(self.max_proposed[int(x["gid"])], int(x["slot"]))
 
     def inject_rival_accepts(self, n=4):
         """A rival coordinator (another member, higher ballot number) re-proposes slots."""
@@ -177,6 +179,35 @@ class Fuzzer:
         for r in canon(rep0):
             self.rep_pool.append(r.copy())
 
+    def step_accepts_fused(self, p_deliver=0.7, p_dup=0.1, p_keep=0.05, lane_loss=0.1):
+        """The loopback path: accept -> tally -> commit per ACCEPT (gpx_handle_accepts_fused / k_act)."""
+        batch = self._take(self.acc_pool, p_deliver, p_dup, p_keep)
+        if not batch:
+            return
+        batch.sort(key=lambda it: int(it[0]["gid"]))
+        recs = np.zeros(len(batch), dtype=abi.accept_dtype)
+        chunks, off = [], 0
+        for i, (r, blob) in enumerate(batch):
+            recs[i] = r
+            recs[i]["payload_off"] = off
+            pad = (-len(blob)) % 16
+            chunks.append(blob)
+            chunks.append(np.zeros(pad, dtype=np.uint8))
+            off += len(blob) + pad
+            if self.rng.random() < lane_loss:
+                recs[i]["dst_mask"] = int(recs[i]["dst_mask"]) & ~(1 << int(self.rng.integers(0, self.R)))
+        arena = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+        outs = self._all(lambda e: e.handle_accepts_fused(recs, arena))
+        rep0, dec0, ex0, ext0 = outs[0]
+        for rep, dec, ex, ext in outs[1:]:
+            _eq(rep0, rep, "fused: leftover replies")
+            _eq(dec0, dec, "fused: decisions")
+            _eq(ex0, ex, "fused: exec")
+            _eq(canon(ext0), canon(ext), "fused: extra exec", skip=("payload_off",))
+        self.record_exec(np.concatenate([ex0, ext0]))
+        for r in canon(rep0):
+            self.rep_pool.append(r.copy())
+
     def step_replies(self, p_deliver=0.7, p_dup=0.15, p_keep=0.05):
         batch = self._take(self.rep_pool, p_deliver, p_dup, p_keep)
         if not batch:
@@ -223,9 +254,10 @@ class Fuzzer:
             new_lane = int(rng.integers(0, self.R))
             new_node = NODES[new_lane]
             # a real view change carries over accepted pvalues (phase 1, host slow path); the fuzzer
-            # stays protocol-respecting by starting the new coordinator beyond every slot the old
-            # one may have proposed
+            # stays protocol-respecting by starting the new coordinator beyond every slot any earlier
+            # coordinator issued an ACCEPT for (a resigned coordinator's row no longer remembers it)
             next_slot = max(int(rows[l][g]["acc_slot"]) for l in range(self.R))
+            next_slot = max(next_slot, int(self.max_proposed[g]) + 1)
             for l in range(self.R):
                 if rows[l][g]["coord_exists"]:
                     next_slot = max(next_slot, int(rows[l][g]["next_proposal_slot"]))
@@ -260,7 +292,7 @@ class Fuzzer:
                         agreed[k] = rid
         return len(agreed)
 
-    def run(self, steps=60, rival=True, view_changes=True, stop_prob=0.01, check_every=10):
+    def run(self, steps=60, rival=True, view_changes=True, stop_prob=0.01, check_every=10, fused_prob=0.0):
         for t in range(steps):
             self.step_propose(frac=0.5, stop_prob=stop_prob)
             if rival and self.rng.random() < 0.3:
@@ -270,7 +302,10 @@ class Fuzzer:
             order = self.rng.permutation(3)
             for o in order:
                 if o == 0:
-                    self.step_accepts()
+                    if self.rng.random() < fused_prob:
+                        self.step_accepts_fused()
+                    else:
+                        self.step_accepts()
                 elif o == 1:
                     self.step_replies()
                 else:

@@ -1,0 +1,91 @@
+"""The host-side mirror of the reference interface (PaxosManager / Replicable) driven like the
+reference's own integration test (testing/TESTPaxosMain.java:154-176 + TESTPaxosClient): create
+groups, send requests through every entry replica, check every request got its response and the
+RSM invariant of testing/TESTPaxosApp.java (seqnum == slot; identical state on every replica).
+Runs against the oracle on CPU and, marked gpu, against the CUDA engine."""
+import numpy as np
+import pytest
+
+from gigapaxos_b200.paxos_manager import HashChainApp, NoopPaxosApp, PaxosManager
+from helpers import Engine, abi, make_config
+
+NODES = [100, 101, 102]
+
+
+def make_pm(lib, app_cls, **kw):
+    eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20, **kw))
+    return PaxosManager(eng, [app_cls() for _ in NODES], NODES)
+
+
+def drive(lib):
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=5)
+    names = [f"TESTPaxosApp{i}" for i in range(10)]
+    assert pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    assert not pm.createPaxosInstance(names[0], 0, NODES)  # already exists (PaxosManager.java:646-652)
+    responses = []
+    rng = np.random.default_rng(1)
+    sent = 0
+    for r in range(12):
+        for n in names:
+            for _ in range(int(rng.integers(1, 4))):
+                val = bytes(rng.integers(97, 123, size=int(rng.integers(1, 20))).astype(np.uint8))
+                rid = pm.propose(n, val, callback=lambda req, ok: responses.append(req.request_id),
+                                 entry_node=NODES[int(rng.integers(0, 3))])
+                assert rid is not None
+                sent += 1
+        pm.run_round()
+    assert pm.propose("nonexistent", b"x") is None
+    assert sorted(responses) == list(range(1, sent + 1))  # every client got its response exactly once
+    assert not pm.outstanding
+    s0 = pm.apps[0].state
+    assert all(a.state == s0 for a in pm.apps) and len(s0) == 10  # RSMInvariant: replicas agree
+    assert all(a.seqnum == pm.apps[0].seqnum for a in pm.apps)
+    cps = [c for c in pm.checkpoints if c[1] == 0]
+    assert cps and all(c[2] % 5 == 0 for c in cps)  # shouldCheckpoint: slot % CPI == 0
+    # reconfiguration churn (BASELINE config 4): stop at epoch 0, re-create at epoch 1
+    assert pm.proposeStop(names[3], 1, b"stop") is None  # wrong version: dropped (PISM :441-447)
+    assert pm.proposeStop(names[3], 0, b"stop") is not None
+    pm.run_round()
+    assert pm.isStopped(names[3]) and not pm.isStopped(names[4])
+    pm.propose(names[3], b"late")
+    pm.run_round()
+    assert any(sp[0] == names[3] and sp[2] == abi.RS_DROPPED for sp in pm.slow_path)  # stopped: dropped
+    assert not pm.createPaxosInstance(names[3], 0, NODES)
+    assert pm.createPaxosInstance(names[3], 1, NODES, initialState=None)
+    assert pm.getVersion(names[3]) == 1
+    for a in pm.apps:
+        a.seqnum[names[3]] = 1
+    got = []
+    pm.propose(names[3], b"fresh", callback=lambda req, ok: got.append(req.slot))
+    pm.run_round()
+    assert got == [1]  # the new epoch starts at slot 1 again (HotRestoreInfo.createHRI)
+    assert pm.kill(names[5]) and pm.propose(names[5], b"x") is None
+    return pm
+
+
+def test_paxos_manager_mirror_cpu(oracle_lib):
+    drive(oracle_lib)
+
+
+def test_noop_app_and_stop_batch_quirk(oracle_lib):
+    """NoopPaxosApp echoes; a batch that contains a STOP executes only its first request because the
+    acceptor is already STOPPED when the batch runs (PISM.execute :1813-1815)."""
+    pm = make_pm(oracle_lib, NoopPaxosApp)
+    pm.createPaxosInstance("NoopPaxosApp0", 0, NODES)
+    out = []
+    pm.propose("NoopPaxosApp0", b"a", callback=lambda r, ok: out.append(r.response_value))
+    pm.run_round()
+    assert out == [b"echoing [a]"]
+    pm.propose("NoopPaxosApp0", b"x", stop=True, callback=lambda r, ok: out.append(r.response_value))
+    pm.propose("NoopPaxosApp0", b"y", callback=lambda r, ok: out.append(r.response_value))
+    pm.run_round()
+    assert out == [b"echoing [a]", b"echoing [x]"] and pm.isStopped("NoopPaxosApp0")
+    assert all(a.executed == 2 for a in pm.apps)
+
+
+@pytest.mark.gpu
+def test_paxos_manager_mirror_gpu(cuda_lib, oracle_lib):
+    pg = drive(cuda_lib)
+    po = drive(oracle_lib)
+    assert pg.apps[0].state == po.apps[0].state and pg.checkpoints == po.checkpoints
+    assert pg.num_decisions == po.num_decisions

@@ -42,10 +42,12 @@ def compare_logs(eo, eg, n_lanes):
                     assert np.array_equal(po[ao: ao + ln], pg[bo: bo + ln])
 
 
+@pytest.mark.parametrize("mode", ["round", "round_phases"])
 @pytest.mark.parametrize("G,P,rounds,init", [(1000, 1, 6, abi.INIT_BATCH), (777, 64, 5, abi.INIT_DEFAULT),
                                              (300, 200, 4, abi.INIT_BATCH)])
-def test_round_parity(oracle_lib, cuda_lib, G, P, rounds, init):
+def test_round_parity(oracle_lib, cuda_lib, G, P, rounds, init, mode):
     eo, eg = both(oracle_lib, cuda_lib, max_groups=G + 5, max_batch_recs=4096, max_batch_payload=1 << 20)
+    assert eg.L.has("round_phases") and eo.L.has("round_phases")
     d = group_descs(G, init_mode=init)
     eo.create_groups(d)
     eg.create_groups(d)
@@ -53,8 +55,8 @@ def test_round_parity(oracle_lib, cuda_lib, G, P, rounds, init):
     compare_state(eo, eg, gids, 3)
     for r in range(rounds):
         reqs, pay = make_requests(gids, payload_len=P, seed=3, round_no=r, entry_lane=r % 3)
-        so, xo, eo_x = eo.round(reqs, pay)
-        sg, xg, eg_x = eg.round(reqs, pay)
+        so, xo, eo_x = getattr(eo, mode)(reqs, pay)
+        sg, xg, eg_x = getattr(eg, mode)(reqs, pay)
         assert np.array_equal(so, sg)
         assert len(eo_x) == len(eg_x) == 0
         for a, b in zip(exec_by_lane(xo, 3), exec_by_lane(xg, 3)):
@@ -71,7 +73,8 @@ def test_round_parity(oracle_lib, cuda_lib, G, P, rounds, init):
     assert np.all(rows["acc_slot"] == rounds + 1)
 
 
-def test_batched_requests_parity(oracle_lib, cuda_lib):
+@pytest.mark.parametrize("mode", ["round", "round_phases"])
+def test_batched_requests_parity(oracle_lib, cuda_lib, mode):
     """RequestBatcher: several requests of one group in a call share one slot."""
     G = 50
     eo, eg = both(oracle_lib, cuda_lib, max_groups=G, max_batch_recs=4096, max_batch_payload=1 << 20)
@@ -84,8 +87,8 @@ def test_batched_requests_parity(oracle_lib, cuda_lib):
         gids = np.repeat(np.arange(G), counts)
         lens = rng.integers(1, 40, size=len(gids))
         reqs, pay = make_requests(gids, payload_len=lens, seed=9, round_no=r)
-        so, xo, _ = eo.round(reqs, pay)
-        sg, xg, _ = eg.round(reqs, pay)
+        so, xo, _ = getattr(eo, mode)(reqs, pay)
+        sg, xg, _ = getattr(eg, mode)(reqs, pay)
         assert np.array_equal(so, sg)
         for a, b in zip(exec_by_lane(xo, 3), exec_by_lane(xg, 3)):
             assert len(a) == G
