@@ -369,9 +369,9 @@ def main():
     # ---- value: device-resident rounds ------------------------------------------------
     for w in range(max(W, 3)):
         dev_round(w % NB)
-    c0 = eng.counters()
     sampler = ClockSampler(local_rank)
     barrier()
+    c0 = eng.counters()
     sampler.start()
     ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]

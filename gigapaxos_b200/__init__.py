@@ -19,8 +19,9 @@ _lib = None
 
 def load_library() -> Library:
     """Load the CUDA engine library (built in-tree by ``gigapaxos_b200.build``)."""
-    global _lib
+    global _lib, LIB_PATH
     if _lib is None:
+        LIB_PATH = os.environ.get("GPX_LIB", LIB_PATH)  # alternative builds of the same CUDA library (tuning)
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: run `python -m gigapaxos_b200.build` (nvcc, sm_100a). "

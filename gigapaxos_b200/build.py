@@ -46,12 +46,13 @@ def nvcc_path() -> str:
     return p
 
 
-def build_engine(force: bool = False, verbose: bool = False) -> str:
+def build_engine(force: bool = False, verbose: bool = False, out: str = LIB, defines: tuple = ()) -> str:
     srcs = _sources()
-    if not force and _newer(LIB, srcs):
-        return LIB
+    if not force and _newer(out, srcs):
+        return out
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cpp"))]
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB, *units]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           "-o", out, *units]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -61,7 +62,7 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout + r.stderr)
-    return LIB
+    return out
 
 
 def build_oracle(force: bool = False) -> str:

@@ -847,7 +847,7 @@ int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_
                  uint64_t* head) {
   if (!e) return fail(GPX_EINVAL, "null argument");
   if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaDeviceSynchronize());
   unsigned long long heads[GPX_MAX_LANES];
   CK(cudaMemcpy(heads, e->S.ring_head, sizeof heads, cudaMemcpyDeviceToHost));
   const uint64_t h = heads[lane], rc = e->S.ring_cap;
@@ -868,7 +868,7 @@ int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_
 /* ---- introspection ------------------------------------------------------------------- */
 int gpx_get_counters(gpx_engine* e, gpx_counters* out) {
   if (!e || !out) return fail(GPX_EINVAL, "null argument");
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaDeviceSynchronize()); /* rounds may have been issued on a caller's stream (gpx_round_device) */
   unsigned long long c[C_NCTR];
   CK(cudaMemcpy(c, e->S.ctr, sizeof c, cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof *out);

@@ -28,6 +28,12 @@
 #include "gpx_dev.cuh"
 
 #define GPX_BLOCK 256
+#ifndef GPX_ACT_MINB
+#define GPX_ACT_MINB 2 /* resident CTAs per SM the fused kernel is compiled for (register cap = 64K/(256*MINB)) */
+#endif
+#ifndef GPX_PHASE_MINB
+#define GPX_PHASE_MINB 3
+#endif
 
 struct RoundCtl { /* device-resident per-round counters */
   uint32_t n_accepts;
@@ -691,7 +697,7 @@ __device__ __forceinline__ GroupCtx group_ctx(const DevState& S, uint32_t gid) {
 
 /* ============================== k_accept ====================================== */
 template <int L>
-__global__ void __launch_bounds__(GPX_BLOCK) k_accept(const __grid_constant__ DevState S,
+__global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_accept(const __grid_constant__ DevState S,
                                                       const __grid_constant__ AcceptArgs A) {
   __shared__ unsigned int s_ctr[C_NCTR];
   if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
@@ -881,7 +887,7 @@ struct CommitArgs {
 };
 
 template <int L>
-__global__ void __launch_bounds__(GPX_BLOCK) k_commit(const __grid_constant__ DevState S,
+__global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_commit(const __grid_constant__ DevState S,
                                                       const __grid_constant__ CommitArgs A) {
   __shared__ unsigned int s_ctr[C_NCTR];
   if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
@@ -977,7 +983,7 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_commit(const __grid_constant__ De
  * in-order case) rows are read and written once, replies and the decision never touch HBM, and an entry
  * that is accepted and executed in the same pass is not written at all. */
 template <int L>
-__global__ void __launch_bounds__(GPX_BLOCK) k_act(const __grid_constant__ DevState S,
+__global__ void __launch_bounds__(GPX_BLOCK, GPX_ACT_MINB) k_act(const __grid_constant__ DevState S,
                                                    const __grid_constant__ AcceptArgs A) {
   __shared__ unsigned int s_ctr[C_NCTR];
   if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
@@ -1162,12 +1168,12 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_act(const __grid_constant__ DevSt
               }
             } else {
               /* general path through memory: make the accepted entry visible, then commit */
-              int4 a0 = e0[l], a1 = e1[l];
+              int4 a0, a1; /* rare path: re-read the entry instead of keeping L x 32 B of registers alive */
               if (st[l].fl & LS_STORE) {
                 make_entry(q0, q1, q2, st[l].frame_ref, a0, a1);
                 st256(&S.acc_win[ai], a0, a1);
                 st[l].fl &= ~LS_STORE;
-              } else if (st[l].fl & LS_RARE)
+              } else
                 ld256(&S.acc_win[ai], a0, a1);
               store_void_exec(ex, gid, slot, l);
               commit_lane(S, l, gid, slot, d.bnum, d.bcoord, d.median_cp, row, aux, a0, a1, ex, A.extra, A.extra_cap,

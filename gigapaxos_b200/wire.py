@@ -125,11 +125,15 @@ def decode_accept(b: bytes) -> dict:
     rc = L.gpx_wire_decode_accept(b, C.c_size_t(len(b)), C.byref(v))
     if rc != 0:
         raise ValueError("malformed ACCEPT")
-    base = C.addressof(C.c_char.from_buffer_copy(b[:1]))  # noqa: F841 (views are offsets into b)
     out = {k: getattr(v, k) for k in ("packet_type", "version", "request_id", "stop", "entry_replica", "entry_time",
                                       "value_len", "n_batched", "request_bytes", "slot", "bnum", "bcoord",
                                       "median_cp", "sender", "recovery")}
     out["paxos_id"] = b[13: 13 + v.paxos_id_len].decode("iso-8859-1")
+    # requestValue: after the header and the 39 fixed bytes comes {int digestLen, digest}{int valueLen, value}
+    off = 13 + v.paxos_id_len + 39
+    dl = int.from_bytes(b[off: off + 4], "big")
+    off += 4 + dl
+    out["value"] = b[off + 4: off + 4 + v.value_len]
     return out
 
 
