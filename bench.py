@@ -2,15 +2,15 @@
 """bench.py -- Paxos decisions/sec of the B200 engine on BASELINE.json's metric.
 
 A *step* is one full Paxos round over every group of the workload: one client request per
-group enters the RequestBatcher and the coordinator proposes (k_propose); then, per ACCEPT,
-all R co-located replicas accept + log, the coordinator tallies the replies and all replicas
-commit + emit in-order EXEC records (k_act, the fused loopback path; the phase-by-phase kernels
-k_accept / k_tally / k_commit are timed beside it).  One step decides one slot per group.
+group enters the RequestBatcher, the coordinator proposes, all R co-located replicas accept +
+log, the coordinator tallies the replies and all replicas commit + emit in-order EXEC records --
+ONE kernel (k_round, the fused loopback path; the phase-by-phase kernels k_propose / k_accept /
+k_tally / k_commit are timed beside it).  One step decides one slot per group.
 
   value  : decisions/s with the request batch already resident in HBM (gpx_round_device)
   e2e    : the same metric through the public C-ABI call gpx_round with HOST buffers
            (pinned), H2D of the requests and D2H of status + EXEC records inside the timing
-  roofline: the dominant kernel of the timed path (k_act), algorithmic bytes / CUDA-event duration
+  roofline: the kernel of the timed path (k_round), algorithmic bytes / CUDA-event duration
            vs the measured HBM copy peak; roofline_accept: the stand-alone accept-batch kernel
            (193+2P per ACCEPT at one acceptor)
   cpu_baseline: the CPU oracle (a port of the Java path, reference JVM unavailable) on the
@@ -56,11 +56,11 @@ def b_slot(R: int, P: int) -> int:
 
 
 def b_act(R: int, P: int) -> int:
-    """Algorithmic bytes per decided slot of the fused k_act kernel with all R replicas co-located
-    (DESIGN.md 4): ACCEPT record 48 + blob P + reply mask 1 + decision record 32; per replica aux 4 +
+    """Algorithmic bytes per decided slot of the fused k_round kernel with all R replicas co-located
+    (DESIGN.md 4): request 32 + blob P + status 4 + reply mask 1 + decision record 32; per replica aux 4 +
     row 16 in + 16 out + window entry 32 in + ACCEPT log image 48 + blob P + DECISION log image 32 +
-    EXEC 24; coordinator row 16+16, proposal entry 16+16, nodeSlots 4R in + 4R out."""
-    return (48 + P + 1 + 32) + R * (4 + 16 + 16 + 32 + 48 + P + 32 + 24) + (64 + 8 * R)
+    EXEC 24; coordinator row 16 in + 16 out, nodeSlots 4R in + 4R out."""
+    return (32 + P + 4 + 1 + 32) + R * (4 + 16 + 16 + 32 + 48 + P + 32 + 24) + (32 + 8 * R)
 
 
 def hbm_peak():
@@ -320,6 +320,7 @@ def main():
         print(json.dumps(line))
         return
 
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
 
@@ -426,12 +427,12 @@ def main():
     act_bytes = G * b_act(R, P)
     acc_bytes = G * R * b_acc(P)
     roofline = {
-        "kernel": "k_act (fused accept -> tally -> commit per ACCEPT at R co-located replicas + log append)",
+        "kernel": "k_round (the whole round in one kernel: batch + propose, accept x R + log append, tally, commit x R)",
         "bound": "hbm", "achieved": act_bytes / (act_ms / 1e3) / 1e9 if act_ms > 0 else 0.0, "peak": peak,
         "unit": "GB/s", "peak_source": peak_src, "traffic": None,
         "algorithmic_bytes_per_launch": act_bytes, "bytes_per_decided_slot": b_act(R, P),
         "decided_slots_per_launch": G, "kernel_ms": act_ms,
-        "kernel_ms_all": {"k_propose+k_build_blobs": kf["propose"], "k_act": act_ms},
+        "kernel_ms_all": {"k_round": act_ms},
     }
     roofline["frac"] = roofline["achieved"] / peak
     roofline_accept = {
@@ -500,7 +501,7 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": config, "roofline": roofline,
             "roofline_accept": roofline_accept,
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 3 * K,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 1 * K,
             "p50_decide_latency_ms": float(np.median(step_ms)),
             "requests_per_sec": value, "wall_s_timed_region": t_wall,
         }

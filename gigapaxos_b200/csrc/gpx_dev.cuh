@@ -41,6 +41,7 @@
 #define GPX_PV_STOP (1u << 17)
 
 #define GPX_META_LIVE (1u << 24)
+#define GPX_META_IDENT (1u << 25) /* all R members are local lanes and lane l serves member index l */
 
 /* counter indices == field order of gpx_counters */
 enum {
@@ -74,7 +75,7 @@ struct MsetInfo { /* one sorted member set (PISM.groupMembers :205), 96 B */
   uint8_t idx_of_lane[GPX_MAX_LANES];      /* member idx served by lane, 0xff if lane not a member */
   uint16_t lane_mask;
   uint8_t R;
-  uint8_t pad;
+  uint8_t ident; /* lane l <-> member idx l for all l < R, R == n_lanes */
   uint32_t pad2;
 };
 

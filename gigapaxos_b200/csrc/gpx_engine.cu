@@ -17,7 +17,7 @@
 #include <string>
 #include <vector>
 
-#include "gpx_kernels.cuh"
+#include "gpx_round.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -65,6 +65,7 @@ struct gpx_engine {
   void* d_misc = nullptr;    /* group-management staging */
   size_t misc_bytes = 0;
   /* timing */
+  int n_sms = 148;
   bool timing = false;
   cudaEvent_t ev[5];
   gpx_kernel_times kt;
@@ -245,6 +246,11 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
     gpx_engine_destroy(e);
     return fail(GPX_ENOMEM, "cudaHostAlloc");
   }
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess && prop.multiProcessorCount > 0)
+      e->n_sms = prop.multiProcessorCount;
+  }
   cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 5; i++) cudaEventCreate(&e->ev[i]);
   e->h_version.assign(G, 0);
@@ -284,7 +290,7 @@ static int intern_mset(gpx_engine* e, std::vector<int32_t> m, uint32_t* id, bool
   memset(&mi, 0xff, sizeof mi);
   mi.R = (uint8_t)m.size();
   mi.lane_mask = 0;
-  mi.pad = 0;
+  mi.ident = 0;
   mi.pad2 = 0;
   for (size_t i = 0; i < GPX_MAX_GROUP_SIZE; i++) mi.nodes[i] = i < m.size() ? m[i] : INT32_MIN;
   for (uint32_t l = 0; l < e->cfg.n_lanes; l++)
@@ -294,6 +300,9 @@ static int intern_mset(gpx_engine* e, std::vector<int32_t> m, uint32_t* id, bool
         mi.idx_of_lane[l] = (uint8_t)i;
         mi.lane_mask |= (uint16_t)(1u << l);
       }
+  bool ident = m.size() == e->cfg.n_lanes;
+  for (uint32_t l = 0; ident && l < e->cfg.n_lanes; l++) ident = mi.idx_of_lane[l] == l && mi.lane_of_idx[l] == l;
+  mi.ident = ident ? 1 : 0;
   *id = (uint32_t)e->msets.size();
   e->msets.push_back(mi);
   e->mset_ids[m] = *id;
@@ -529,6 +538,60 @@ static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uin
   return GPX_OK;
 }
 
+/* k_round<L, LP>: LP = lanes padded to a power of two (team width) */
+extern "C++" {
+template <int L, int LP>
+static void launch_round_t(uint32_t grid, uint32_t slow_grid, cudaStream_t st, const DevState& S, const RoundArgs& RA) {
+  k_round<L, LP, true><<<grid, GPX_BLOCK, 0, st>>>(S, RA);
+  k_round_slow<L, LP><<<slow_grid, GPX_BLOCK, 0, st>>>(S, RA);
+}
+}
+static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload, uint64_t pal,
+                        uint32_t n, int32_t* d_status, gpx_exec_rec* d_exec, cudaStream_t st) {
+  RoundArgs RA;
+  memset(&RA, 0, sizeof RA);
+  RA.P.reqs = d_reqs;
+  RA.P.n = n;
+  RA.P.payload_bytes_al = pal;
+  RA.P.accepts = e->d_accepts;
+  RA.P.status = d_status;
+  RA.P.copy_tab = e->d_copy_tab;
+  RA.P.copy_dst = e->d_copy_dst;
+  RA.P.ctl = e->d_ctl;
+  RA.A.n_max = n;
+  RA.A.blob0 = d_payload;
+  RA.A.blob0_bytes = pal;
+  RA.A.blob1 = e->d_blob1;
+  RA.A.replies = e->d_replies;
+  RA.A.decisions = e->d_decisions;
+  RA.A.out_mask = e->d_out_mask;
+  RA.A.exec = d_exec;
+  RA.A.extra = e->d_extra;
+  RA.A.extra_cap = e->extra_cap;
+  RA.A.n_extra = &e->d_ctl->n_extra;
+  RA.blob1w = e->d_blob1;
+  RA.todo = e->d_copy_tab; /* scratch reused: k_round does not build blobs through copy_tab */
+  RA.n_todo = &e->d_ctl->n_todo;
+  RA.blob1_res = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
+  RA.A.blob1_bytes = RA.blob1_res;
+  const uint32_t L = e->cfg.n_lanes;
+  const uint32_t LP = L <= 1 ? 1 : L <= 2 ? 2 : L <= 4 ? 4 : 8;
+  const uint32_t grid = cdiv((uint64_t)n * LP, GPX_BLOCK);
+  const uint32_t slow_grid = std::min<uint32_t>(grid, 2u * (uint32_t)e->n_sms);
+  switch (L) {
+    case 1: launch_round_t<1, 1>(grid, slow_grid, st, e->S, RA); break;
+    case 2: launch_round_t<2, 2>(grid, slow_grid, st, e->S, RA); break;
+    case 3: launch_round_t<3, 4>(grid, slow_grid, st, e->S, RA); break;
+    case 4: launch_round_t<4, 4>(grid, slow_grid, st, e->S, RA); break;
+    case 5: launch_round_t<5, 8>(grid, slow_grid, st, e->S, RA); break;
+    case 6: launch_round_t<6, 8>(grid, slow_grid, st, e->S, RA); break;
+    case 7: launch_round_t<7, 8>(grid, slow_grid, st, e->S, RA); break;
+    default: launch_round_t<8, 8>(grid, slow_grid, st, e->S, RA); break;
+  }
+  CK(cudaGetLastError());
+  return GPX_OK;
+}
+
 static int ring_fits(gpx_engine* e, uint64_t reserved) {
   if (reserved > e->cfg.log_ring_bytes) return fail(GPX_ERANGE, "batch does not fit the log ring; raise log_ring_bytes");
   return GPX_OK;
@@ -730,6 +793,19 @@ static int round_on_stream(gpx_engine* e, bool fused, const gpx_request_rec* d_r
   const bool tm = e->timing;
   CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
   if (tm) cudaEventRecord(e->ev[0], st);
+  if (fused) { /* the whole round is ONE kernel */
+    int rc1 = launch_round(e, d_reqs, d_payload, pal, n, d_status, d_exec, st);
+    if (rc1) return rc1;
+    if (tm) {
+      cudaEventRecord(e->ev[1], st);
+      cudaEventSynchronize(e->ev[1]);
+      float ms;
+      cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+      e->kt.accept_ms += ms; /* reported as the dominant kernel of the fused path */
+      e->kt.launches++;
+    }
+    return GPX_OK;
+  }
   int rc = launch_propose(e, d_reqs, d_payload, pal, n, d_status, st);
   if (rc) return rc;
   if (tm) cudaEventRecord(e->ev[1], st);
@@ -776,7 +852,7 @@ static int round_host(gpx_engine* e, bool fused, uint32_t n, const gpx_request_r
   if (rc) return rc;
   const uint64_t pal = (payload_bytes + 15) & ~15ull;
   const uint64_t b1 = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
-  rc = ring_fits(e, 160ull + 80ull * n + pal + b1);
+  rc = ring_fits(e, 192ull + 80ull * n + pal + b1);
   if (rc) return rc;
   cudaStream_t st = e->stream;
   const uint32_t L = e->cfg.n_lanes;
@@ -787,8 +863,8 @@ static int round_host(gpx_engine* e, bool fused, uint32_t n, const gpx_request_r
   CK(cudaMemcpyAsync(status, e->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   rc = fetch_ctl(e);
   if (rc) return rc;
-  /* fused: one EXEC row per ACCEPT; phases: one per DECISION */
-  const uint32_t rows = fused ? e->h_ctl->n_accepts : e->h_ctl->n_decisions;
+  /* fused: one EXEC row per REQUEST index (VOID where the request carries no ACCEPT); phases: one per DECISION */
+  const uint32_t rows = fused ? n : e->h_ctl->n_decisions;
   const uint32_t nx = e->h_ctl->n_extra;
   if (rows) CK(cudaMemcpyAsync(out_exec, e->d_exec, (size_t)rows * L * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
   uint32_t cp = std::min(std::min(nx, extra_cap), e->extra_cap);

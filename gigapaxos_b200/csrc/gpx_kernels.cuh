@@ -41,7 +41,8 @@ struct RoundCtl { /* device-resident per-round counters */
   uint32_t n_extra;
   uint32_t any_batched;
   unsigned long long blob1_used;
-  uint32_t pad[2];
+  uint32_t n_todo;
+  uint32_t pad[1];
 };
 
 /* every thread of the block calls; returns the first index reserved for this thread */
@@ -117,8 +118,10 @@ __device__ __forceinline__ uint32_t batch_end(const DevState& S, const gpx_reque
   return b;
 }
 
+/* `indexed`: the ACCEPT of the batch that starts at request k is written to A.accepts[k] (k_round) instead of
+ * the compacted position base+emitted (k_propose) */
 __device__ __noinline__ void propose_run(const DevState& S, const ProposeArgs& A, uint32_t i, uint32_t run_end,
-                                         uint32_t nb, uint32_t base, unsigned int* s_ctr) {
+                                         uint32_t nb, uint32_t base, unsigned int* s_ctr, bool indexed = false) {
   const gpx_request_rec* reqs = A.reqs;
   const uint32_t gid = reqs[i].gid;
   const uint32_t Wm = S.W - 1;
@@ -260,7 +263,7 @@ __device__ __noinline__ void propose_run(const DevState& S, const ProposeArgs& A
     for (uint32_t q = k; q < run_end; q++) A.status[q] = code;
     atomicAdd(&s_ctr[C_REQS_REJECTED], run_end - k);
   }
-  for (; emitted < nb; emitted++) { /* reserved but unused: VOID keeps the run adjacent */
+  for (; !indexed && emitted < nb; emitted++) { /* reserved but unused: VOID keeps the run adjacent */
     gpx_accept_rec a;
     memset(&a, 0, sizeof a);
     a.h.gid = gid;
@@ -1234,7 +1237,7 @@ __global__ void k_init_groups(const __grid_constant__ DevState S, const InitRec*
   if (i >= n) return;
   const InitRec r = recs[i];
   const MsetInfo* ms = &S.msets[r.mset];
-  S.grp_meta[r.gid] = r.mset | (r.R << 16) | GPX_META_LIVE;
+  S.grp_meta[r.gid] = r.mset | (r.R << 16) | GPX_META_LIVE | (ms->ident ? GPX_META_IDENT : 0u);
   S.grp_cpi[r.gid] = r.cpi;
   for (uint32_t l = 0; l < S.L; l++) {
     const size_t ri = row_idx(S, l, r.gid);
@@ -1324,7 +1327,8 @@ __global__ void k_load_rows(const __grid_constant__ DevState S, const LoadRec* r
   if (i >= n) return;
   const gpx_row& r = recs[i].row;
   const uint32_t gid = r.gid, l = r.lane;
-  S.grp_meta[gid] = recs[i].mset | ((uint32_t)r.n_members << 16) | GPX_META_LIVE;
+  S.grp_meta[gid] = recs[i].mset | ((uint32_t)r.n_members << 16) | GPX_META_LIVE |
+                    (S.msets[recs[i].mset].ident ? GPX_META_IDENT : 0u);
   S.grp_cpi[gid] = recs[i].cpi;
   const size_t ri = row_idx(S, l, gid);
   S.acc_row[ri] = make_int4(r.acc_slot, r.acc_bnum, r.acc_bcoord, r.acc_gc_slot);

@@ -1,0 +1,596 @@
+/*
+ * gpx_round.cuh -- k_round: one launch advances every group of a request batch through a whole Paxos
+ * round (RequestBatcher -> propose -> accept x R -> tally -> commit x R) for co-located replicas.
+ *
+ * Work mapping: a TEAM of LP threads (LP = lanes padded to 1/2/4/8, adjacent lanes of one warp) owns one
+ * request index; team thread `sub` < L is replica lane `sub` of the group.  The team of the first request of
+ * a run of equal gids processes the run (the reference's per-instance `synchronized`).
+ *   propose  computed redundantly by every team thread from the same loads (broadcast loads, no shuffles):
+ *            PISM.handleProposal :818-888, PCS.propose :233-263, getMedianMinus :867-875
+ *   accept   thread `sub` runs PISM.handleAccept :1080-1166 for its own lane (accept_lane), writes its lane's
+ *            log image and copies the blob into its lane's log ring
+ *   tally    the L ACCEPT_REPLYs are exchanged with __shfl_sync inside the team; every thread runs
+ *            PaxosCoordinator.handleAcceptReply :210-250 on register copies of the coordinator row, the
+ *            proposal and nodeSlotNumbers (vote set = bitmask, majority = __popc), so the DECISION is known
+ *            to all lanes without touching memory; thread 0 of the team writes the coordinator state back
+ *   commit   thread `sub` runs handleBatchedCommit :1480 / extractExecuteAndCheckpoint :1619 for its lane
+ * In this fast path the ACCEPT record, the replies, the DECISION and the proposal never touch HBM; each
+ * acceptor row is read and written once.  Anything unusual (several requests of a group in the batch,
+ * outstanding proposals, a pre-active or missing coordinator, remote members) takes the general path:
+ * thread 0 runs propose_run / tally_reply against memory and broadcasts the decision to the team.
+ *
+ * Semantics are those of gpx_propose followed by gpx_handle_accepts_fused (checked by the test-suite); record,
+ * image and EXEC indices are REQUEST indices (holes are VOID).
+ */
+#pragma once
+#include "gpx_kernels.cuh"
+
+struct RoundArgs {
+  ProposeArgs P;  /* reqs, n, payload_bytes_al, accepts (scratch, indexed by request), status, copy_*, ctl */
+  AcceptArgs A;   /* blob0/blob1, replies, decisions, out_mask, exec, extra ... (recs/n_ptr unused) */
+  uint8_t* blob1w; /* writable alias of A.blob1 (constructed blobs of batched slots) */
+  unsigned long long blob1_res; /* payload-area bytes reserved for constructed blobs */
+  uint32_t* todo;               /* split mode: request indices of the runs left to k_round_slow */
+  uint32_t* n_todo;
+};
+
+#ifndef GPX_ROUND_MINB
+#define GPX_ROUND_MINB 5 /* the fast kernel fits 48 registers without spills: 5 CTAs x 256 threads per SM */
+#endif
+
+/* PCS.getMedianMinus :867-875 on a register array (R <= LP <= 8) */
+template <int LP>
+__device__ __forceinline__ int median_regs(const int (&ns)[LP], uint32_t R) {
+  if (R == 1) return ns[0];
+  if (LP >= 4 && R == 3) return max(min(ns[0], ns[1]), min(max(ns[0], ns[1]), ns[2]));
+  int v[LP];
+#pragma unroll
+  for (int k = 0; k < LP; k++) v[k] = (uint32_t)k < R ? ns[k] : 2147483647;
+#pragma unroll
+  for (int a = 0; a < LP; a++) /* odd-even transposition sort, fully unrolled: no dynamic indexing */
+#pragma unroll
+    for (int b = (a & 1); b + 1 < LP; b += 2) {
+      int lo = min(v[b], v[b + 1]), hi = max(v[b], v[b + 1]);
+      v[b] = lo;
+      v[b + 1] = hi;
+    }
+  const uint32_t idx = (R % 2 == 0) ? R / 2 - 1 : R / 2;
+  int out = v[0];
+#pragma unroll
+  for (int k = 1; k < LP; k++)
+    if ((uint32_t)k == idx) out = v[k];
+  return out;
+}
+
+/* commit of decision d at one lane, state in registers (the per-lane part of k_act's commit phase) */
+template <int L>
+__device__ __forceinline__ void commit_team_lane(const DevState& S, const AcceptArgs& A, uint32_t l, uint32_t gid,
+                                                 int slot, bool live, bool decided, const gpx_decision_rec& d,
+                                                 const int4 q0, const int4 q1, const int4 q2, LaneSt& st, uint32_t j,
+                                                 unsigned long long dseg, unsigned int* s_ctr) {
+  const uint32_t Wm = S.W - 1;
+  gpx_exec_rec* ex = &A.exec[(size_t)j * L + l];
+  int4 img0 = make_int4((int)gid, slot, d.bnum, d.bcoord);
+  int4 img1 = make_int4(d.median_cp, (int)(GPX_F_VOID | ((uint32_t)d.dst_mask << 16)),
+                        (int)(unsigned)(d.req_id & 0xffffffffll), (int)(d.req_id >> 32));
+  const size_t ai = 2 * win_idx(S, l, (uint32_t)slot & Wm, gid);
+  const size_t ri = row_idx(S, l, gid);
+  int4& row = st.row;
+  uint32_t& aux = st.aux;
+  if (!(decided && ((d.dst_mask >> l) & 1u))) {
+    store_void_exec(ex, gid, slot, l);
+  } else if (!live || !st_usable(aux)) {
+    store_void_exec(ex, gid, slot, l);
+    atomicAdd(&s_ctr[C_DECISIONS_DROPPED], 1u);
+  } else {
+    const int4 row_b = row;
+    const uint32_t aux_b = aux;
+    const bool fast = (st.fl & LS_STORE) && q0.z == d.bnum && q0.w == d.bcoord && slot == row.x &&
+                      !((GPX_AUX_PRESENT(aux) >> ((uint32_t)slot & Wm)) & 1u);
+    if (fast) {
+      atomicAdd(&s_ctr[C_DECISIONS_HANDLED], 1u);
+      int4 n0, n1;
+      make_entry(q0, q1, q2, st.frame_ref, n0, n1);
+      const unsigned efl = (unsigned)n1.w;
+      const bool metaf = S.log_meta != 0;
+      const uint32_t lf = GPX_F_DECISION | (metaf ? GPX_F_META : 0u) | ((efl & GPX_ENT_STOP) ? GPX_F_STOP : 0u);
+      img0 = make_int4((int)gid, slot, d.bnum, d.bcoord);
+      img1 = make_int4(metaf ? -1 : d.median_cp, (int)(lf | ((1u << l) << 16)), n1.x, n1.y);
+      gc_step(row, d.median_cp);
+      DPValue x;
+      x.slot = slot;
+      x.bnum = d.bnum;
+      x.bcoord = d.bcoord;
+      x.median_cp = d.median_cp;
+      x.req_id = ((long long)n1.y << 32) | (unsigned)n1.x;
+      x.frame_ref = st.frame_ref;
+      x.plen = (unsigned)n1.z;
+      x.fl = efl & ~GPX_ENT_VALID;
+      x.valued = true;
+      row.x = (int)((unsigned)row.x + 1u);
+      atomicAdd(&s_ctr[C_EXECUTED], 1u);
+      gpx_exec_rec er = make_exec(S, gid, l, x, false);
+      if (er.flags & GPX_F_CKPT) atomicAdd(&s_ctr[C_CKPTS_DUE], 1u);
+      store_exec(ex, er);
+      bool more = true;
+      if (efl & GPX_ENT_STOP) {
+        aux = (aux & ~0xffu) | GPX_ST_STOPPED;
+        aux &= ~0x00ffff00u;
+        atomicAdd(&s_ctr[C_STOPS_EXECUTED], 1u);
+        more = false;
+      }
+      if (S.journaling) {
+        if (st.fl & LS_OCCVALID) {
+          n1.w = (int)((unsigned)n1.w & ~GPX_ENT_VALID);
+          st256(&S.acc_win[ai], n0, n1);
+        }
+      } else
+        st256(&S.acc_win[ai], n0, n1);
+      st.fl &= ~LS_STORE;
+      if (more) {
+        gc_step(row, d.median_cp);
+        if ((GPX_AUX_PRESENT(aux) >> ((uint32_t)row.x & Wm)) & 1u)
+          eec(S, l, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
+      }
+    } else {
+      int4 a0, a1;
+      if (st.fl & LS_STORE) {
+        make_entry(q0, q1, q2, st.frame_ref, a0, a1);
+        st256(&S.acc_win[ai], a0, a1);
+        st.fl &= ~LS_STORE;
+      } else
+        ld256(&S.acc_win[ai], a0, a1);
+      store_void_exec(ex, gid, slot, l);
+      commit_lane(S, l, gid, slot, d.bnum, d.bcoord, d.median_cp, row, aux, a0, a1, ex, A.extra, A.extra_cap,
+                  A.n_extra, img0, img1, s_ctr);
+    }
+    if (aux != aux_b) st.fl |= LS_AUXDIRTY;
+    if (row.x != row_b.x || row.y != row_b.y || row.z != row_b.z || row.w != row_b.w) st.fl |= LS_ROWDIRTY;
+  }
+  if (st.fl & LS_STORE) {
+    int4 n0, n1;
+    make_entry(q0, q1, q2, st.frame_ref, n0, n1);
+    st256(&S.acc_win[ai], n0, n1);
+  }
+  if (st.fl & LS_ROWDIRTY) S.acc_row[ri] = row;
+  if (st.fl & LS_AUXDIRTY) S.acc_aux[ri] = aux;
+  st256_stream(ring_ptr(S, l, dseg + 64 + (unsigned long long)j * 32), img0, img1);
+}
+
+/* VOID outputs of a request index that carries no ACCEPT (batched into an earlier one / rejected) */
+template <int L>
+__device__ __forceinline__ void void_outputs(const DevState& S, const RoundArgs& RA, uint32_t sub, uint32_t gid,
+                                             uint32_t j, unsigned long long seg, unsigned long long dseg) {
+  if (sub < (uint32_t)L) {
+    const int4 z0 = make_int4((int)gid, 0, 0, 0), z1 = make_int4(0, (int)GPX_F_VOID, 0, 0);
+    write_accept_image(S, sub, seg, RA.P.n, j, z0, z1, make_int4(0, 0, 0, 0), GPX_F_VOID);
+    st256_stream(ring_ptr(S, sub, dseg + 64 + (unsigned long long)j * 32), z0, z1);
+    store_void_exec(&RA.A.exec[(size_t)j * L + sub], gid, 0, sub);
+  }
+  if (sub == 0) {
+    st256_stream(&RA.A.decisions[j], make_int4((int)gid, 0, 0, 0), make_int4(0, (int)GPX_F_VOID, 0, 0));
+    RA.A.out_mask[j] = 0;
+  }
+}
+
+/* General path for the run that starts at request index i: coordinator work by team thread 0 against memory
+ * (propose_run / tally_reply), decision broadcast to the lanes by shuffles. */
+template <int L, int LP>
+__device__ __forceinline__ void round_general(const DevState& S, const RoundArgs& RA, uint32_t i, uint32_t sub,
+                                              uint32_t tmask, uint32_t tbase, uint32_t gid, unsigned long long seg,
+                                              unsigned long long dseg, unsigned long long payb, unsigned int* s_ctr) {
+  const AcceptArgs& A = RA.A;
+  const gpx_request_rec* reqs = RA.P.reqs;
+  const uint32_t n = RA.P.n;
+  const uint32_t Wm = S.W - 1;
+  const GroupCtx g = group_ctx(S, gid);
+  uint32_t run_end = i + 1;
+  if (sub == 0) {
+    uint32_t nb = 0, k = i;
+    while (k < n && reqs[k].gid == gid) {
+      k = batch_end(S, reqs, n, k, gid);
+      nb++;
+    }
+    run_end = k;
+    propose_run(S, RA.P, i, run_end, nb, i, s_ctr, true);
+    __threadfence_block();
+  }
+  run_end = __shfl_sync(tmask, run_end, tbase);
+  for (uint32_t q = i; q < run_end; q++) {
+    const int stq = RA.P.status[q];
+    if (stq <= 0) {
+      void_outputs<L>(S, RA, sub, gid, q, seg, dseg);
+      continue;
+    }
+    const int4* rp = reinterpret_cast<const int4*>(&RA.P.accepts[q]);
+    const int4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+    const int slot = q0.y;
+    if ((uint32_t)q2.z > 1u) { /* batched slot: build [nreq x gpx_batch_ent][values] (RequestPacket.batched) */
+      if (sub == 0) {
+        const uint32_t nreq = (uint32_t)q2.z;
+        uint8_t* tab = RA.blob1w + ((unsigned long long)(uint32_t)q2.x - A.blob0_bytes);
+        uint8_t* dst = tab + 16ull * nreq;
+        for (uint32_t b = 0; b < nreq; b++) {
+          const gpx_request_rec r = reqs[q + b];
+          gpx_batch_ent be;
+          be.req_id = r.req_id;
+          be.len = r.payload_len;
+          be.flags = r.flags;
+          *reinterpret_cast<int4*>(tab + 16ull * b) = *reinterpret_cast<const int4*>(&be);
+          const uint8_t* src = A.blob0 + r.payload_off;
+          for (uint32_t x = 0; x < r.payload_len; x++) dst[x] = src[x];
+          dst += r.payload_len;
+        }
+        __threadfence_block();
+      }
+      __syncwarp(tmask);
+    }
+    uint32_t dstIdx = 0xffu;
+    if (g.live)
+      for (uint32_t m = 0; m < g.R; m++)
+        if (g.ms->nodes[m] == q2.w) dstIdx = m;
+    int cl2 = -1;
+    if (g.live && dstIdx < g.R && g.ms->lane_of_idx[dstIdx] != 0xffu) cl2 = g.ms->lane_of_idx[dstIdx];
+    LaneSt st;
+    st.aux = 0;
+    st.row = make_int4(0, 0, 0, 0);
+    st.fl = 0;
+    st.rwho = GPX_WHO(0xffu, 0xffu, GPX_F_VOID);
+    st.rbn = st.rbc = st.rmaxcp = 0;
+    if (sub < (uint32_t)L) {
+      int4 e0 = make_int4(0, 0, 0, 0), e1 = e0;
+      if (g.live) {
+        const size_t ri = row_idx(S, sub, gid);
+        st.aux = S.acc_aux[ri];
+        st.row = S.acc_row[ri];
+        ld256(&S.acc_win[2 * win_idx(S, sub, (uint32_t)slot & Wm, gid)], e0, e1);
+      }
+      const unsigned fr = (unsigned)(((payb + (uint32_t)q2.x) & (S.ring_cap - 1)) >> 4);
+      accept_lane(S, A, sub, g.live, g.ms, dstIdx, q0, q1, q2, e0, e1, fr, st, s_ctr);
+      write_accept_image(S, sub, seg, n, q, q0, q1, q2, st.img_flags);
+      if (st.fl & LS_LOGGED) {
+        const uint32_t off = (uint32_t)q2.x, plen = (uint32_t)q2.y;
+        const uint8_t* src = blob_ptr(A, off);
+        if (((off | (uint32_t)(uintptr_t)src) & 15u) == 0) {
+          for (uint32_t b = 0; b < plen; b += 16) st_stream4(ring_ptr(S, sub, payb + off + b), ld_stream4(src + b));
+        } else {
+          for (uint32_t b = 0; b < plen; b++) *ring_ptr(S, sub, payb + off + b) = src[b];
+        }
+      }
+    }
+    uint32_t caux = 0;
+    if (cl2 >= 0) caux = __shfl_sync(tmask, st.aux, tbase + (uint32_t)cl2);
+    const bool tally_here = cl2 >= 0 && st_usable(caux);
+    gpx_decision_rec d;
+    d.gid = gid;
+    d.slot = slot;
+    d.bnum = 0;
+    d.bcoord = 0;
+    d.median_cp = 0;
+    d.flags = GPX_F_VOID;
+    d.dst_mask = 0;
+    d.req_id = 0;
+    int decided_i = 0;
+    uint32_t omask = 0;
+    int4 crow2 = make_int4(0, 0, 0, 0);
+    bool cdirty = false;
+    if (sub == 0 && tally_here) crow2 = S.coord_row[row_idx(S, (uint32_t)cl2, gid)];
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      const uint32_t who = __shfl_sync(tmask, st.rwho, tbase + l);
+      const int rb = __shfl_sync(tmask, st.rbn, tbase + l);
+      const int rc = __shfl_sync(tmask, st.rbc, tbase + l);
+      const int mcp = __shfl_sync(tmask, st.rmaxcp, tbase + l);
+      if (GPX_WHO_FLAGS(who) & GPX_F_VOID) continue;
+      if (!tally_here) {
+        omask |= 1u << l;
+        if (sub == (uint32_t)l)
+          st256_stream(&A.replies[(size_t)q * L + l], make_int4((int)gid, slot, rb, rc),
+                       make_int4(mcp, (int)who, q1.z, q1.w));
+        continue;
+      }
+      if (sub == 0) {
+        gpx_decision_rec dd;
+        if (tally_reply(S, (uint32_t)cl2, gid, g.R, g.ms, crow2, cdirty, slot, rb, rc, mcp, GPX_WHO_ACC(who), dd,
+                        s_ctr) &&
+            !decided_i) {
+          d = dd;
+          decided_i = 1;
+        }
+      }
+    }
+    if (sub == 0) {
+      if (cdirty) S.coord_row[row_idx(S, (uint32_t)cl2, gid)] = crow2;
+      const int4* sp = reinterpret_cast<const int4*>(&d);
+      st256_stream(&A.decisions[q], sp[0], sp[1]);
+      A.out_mask[q] = (uint8_t)omask;
+    }
+    /* broadcast the decision of thread 0 to the lanes */
+    decided_i = __shfl_sync(tmask, decided_i, tbase);
+    {
+      int4* dp = reinterpret_cast<int4*>(&d);
+      dp[0].z = __shfl_sync(tmask, dp[0].z, tbase);
+      dp[0].w = __shfl_sync(tmask, dp[0].w, tbase);
+      dp[1].x = __shfl_sync(tmask, dp[1].x, tbase);
+      dp[1].y = __shfl_sync(tmask, dp[1].y, tbase);
+      dp[1].z = __shfl_sync(tmask, dp[1].z, tbase);
+      dp[1].w = __shfl_sync(tmask, dp[1].w, tbase);
+    }
+    if (sub < (uint32_t)L)
+      commit_team_lane<L>(S, A, sub, gid, slot, g.live, decided_i != 0, d, q0, q1, q2, st, q, dseg, s_ctr);
+    __syncwarp(tmask); /* the next ACCEPT of the run sees this one's coordinator/acceptor writes */
+  }
+}
+
+template <int L, int LP, bool SPLIT>
+__global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __grid_constant__ DevState S,
+                                                                     const __grid_constant__ RoundArgs RA) {
+  __shared__ unsigned int s_ctr[C_NCTR];
+  if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
+  __syncthreads();
+  const AcceptArgs& A = RA.A;
+  const gpx_request_rec* reqs = RA.P.reqs;
+  const uint32_t n = RA.P.n;
+  const uint32_t t = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  const uint32_t sub = t % LP, i = t / LP;
+  const uint32_t lane_id = threadIdx.x & 31u;
+  const uint32_t tbase = lane_id & ~(uint32_t)(LP - 1);
+  const uint32_t tmask = (LP == 32 ? 0xffffffffu : ((1u << LP) - 1u)) << tbase;
+  const uint32_t Wm = S.W - 1;
+  /* per-lane log segments of this launch: [ACCEPT seg (n images + payload area)][DECISION seg] */
+  const unsigned long long pay_bytes = A.blob0_bytes + RA.blob1_res;
+  const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
+  const unsigned long long res_a = (pay_rel + pay_bytes + 31ull) & ~31ull;
+  const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
+  const uint32_t myl = sub < (uint32_t)L ? sub : 0u;
+  const unsigned long long seg = seg_base(S, myl, res_a + res_d);
+  const unsigned long long payb = seg + pay_rel, dseg = seg + res_a;
+  if (t < (uint32_t)L) { /* thread l writes lane l's two segment headers */
+    write_seg_hdr(S, t, seg_base(S, t, res_a + res_d), GPX_F_ACCEPT, n, n, pay_bytes, 48, S.seg_seq[t]);
+    write_seg_hdr(S, t, seg_base(S, t, res_a + res_d) + res_a, GPX_F_DECISION, n, n, 0, 32, S.seg_seq[t] + 1ull);
+  }
+  if (t == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
+
+  /* ---- level A loads: the request record and the neighbour's gid (run-head test) ---- */
+  bool head = false;
+  uint32_t gid = 0;
+  int4 rq0 = make_int4(0, 0, 0, 0), rq1 = rq0;
+  if (i < n) {
+    ld256_stream(&reqs[i], rq0, rq1);
+    gid = (uint32_t)rq0.x;
+    head = (i == 0) || (reqs[i - 1].gid != gid);
+  }
+  uint32_t c_lane = 0, c_team = 0, c_ckpt = 0; /* fast-path event counts, reduced once per warp at the end */
+  if (head) { /* team-uniform */
+    const bool single = !(i + 1 < n && reqs[i + 1].gid == gid);
+    const uint32_t rflags = (uint32_t)rq0.y;
+    const uint32_t entry = (rflags >> 8) & 0xfu;
+    /* ---- level B loads (depend on gid only): group meta, my lane's acceptor + coordinator rows ---- */
+    const bool gid_ok = gid < S.G;
+    uint32_t meta = 0;
+    uint32_t my_aux = 0;
+    int4 my_row = make_int4(0, 0, 0, 0), my_crow = my_row;
+    if (gid_ok) {
+      meta = S.grp_meta[gid];
+      if (sub < (uint32_t)L) {
+        const size_t ri = row_idx(S, sub, gid);
+        my_aux = S.acc_aux[ri];
+        my_row = S.acc_row[ri];
+        my_crow = S.coord_row[ri];
+      }
+    }
+    /* the in-order fast path needs: one request for the group, a live group whose R members are exactly the
+     * L local lanes in member order, no STOP */
+    bool sf = single && gid_ok && ((meta & (GPX_META_LIVE | GPX_META_IDENT)) == (GPX_META_LIVE | GPX_META_IDENT)) &&
+              ((meta >> 16) & 0xffu) == (uint32_t)L && entry < (uint32_t)L && !(rflags & GPX_F_STOP);
+    int cl = 0;
+    int4 crow = make_int4(0, 0, 0, 0);
+    int slot = 0;
+    if (sf) {
+      /* PISM.handleProposal :818-888: who coordinates?  rows of the entry lane come from its thread */
+      const int ae_y = __shfl_sync(tmask, my_row.y, tbase + entry), ae_z = __shfl_sync(tmask, my_row.z, tbase + entry);
+      const int ce_x = __shfl_sync(tmask, my_crow.x, tbase + entry), ce_y = __shfl_sync(tmask, my_crow.y, tbase + entry);
+      const int ce_w = __shfl_sync(tmask, my_crow.w, tbase + entry);
+      cl = (int)entry;
+      if (!(((unsigned)ce_w & GPX_CF_EXISTS) && bcmp(ce_x, ce_y, ae_y, ae_z) >= 0)) {
+        int fl = -1;
+#pragma unroll
+        for (int l = 0; l < L; l++)
+          if (S.lane_node[l] == ae_z) fl = l;
+        sf = fl >= 0 && fl != (int)entry;
+        cl = sf ? fl : 0;
+      }
+      crow.x = __shfl_sync(tmask, my_crow.x, tbase + cl);
+      crow.y = __shfl_sync(tmask, my_crow.y, tbase + cl);
+      crow.z = __shfl_sync(tmask, my_crow.z, tbase + cl);
+      crow.w = __shfl_sync(tmask, my_crow.w, tbase + cl);
+      const int af_y = __shfl_sync(tmask, my_row.y, tbase + cl), af_z = __shfl_sync(tmask, my_row.z, tbase + cl);
+      /* an ACTIVE coordinator whose ballot is not behind its acceptor, with no proposal outstanding */
+      sf = sf && ((unsigned)crow.w == (GPX_CF_EXISTS | GPX_CF_ACTIVE)) && bcmp(crow.x, crow.y, af_y, af_z) >= 0;
+      slot = crow.z;
+    }
+    /* ---- level C loads (depend on the slot / the coordinator lane): window entry, nodeSlotNumbers ---- */
+    int4 e0 = make_int4(0, 0, 0, 0), e1 = e0;
+    int my_ns = 0;
+    if (sf && sub < (uint32_t)L) {
+      ld256(&S.acc_win[2 * win_idx(S, sub, (uint32_t)slot & Wm, gid)], e0, e1);
+      my_ns = S.node_slots[ns_idx(S, (uint32_t)cl, sub, gid)];
+    }
+    if (sf) {
+      /* every lane must be the plain in-order case: usable, same ballot, next slot, nothing already there */
+      bool ok = true;
+      if (sub < (uint32_t)L) {
+        const bool ent_live = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, my_row.w) > 0 && e0.x == slot;
+        ok = st_usable(my_aux) && my_row.y == crow.x && my_row.z == crow.y && my_row.x == slot && !ent_live &&
+             !((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)slot & Wm)) & 1u) && jsub(slot, my_row.w) > 0;
+      }
+      sf = __ballot_sync(tmask, ok) == tmask;
+    }
+    if (sf) {
+      /* ================= in-order fast path: nothing but the durable outputs touches HBM ================= */
+      int ns[LP];
+#pragma unroll
+      for (int k = 0; k < LP; k++) ns[k] = __shfl_sync(tmask, my_ns, tbase + k);
+      const int median = median_regs<LP>(ns, (uint32_t)L); /* AcceptPacket.medianCheckpointedSlot (initCommander) */
+      const uint32_t lane_mask = (1u << L) - 1u;
+      const int4 q0 = make_int4((int)gid, slot, crow.x, crow.y);
+      const int4 q1 = make_int4(median, (int)(GPX_F_ACCEPT | (lane_mask << 16)), rq0.z, rq0.w);
+      const int4 q2 = make_int4(rq1.x, rq1.y, 1, crow.y);
+      /* handleAccept at my lane: ballot equal, slot next-in-line, no previous accept -> ack + log */
+      int4 row = my_row;
+      int max_cp = 0;
+      if (sub < (uint32_t)L) {
+        gc_step(row, median); /* acceptAndUpdateBallot -> garbageCollectAccepted :320 */
+        max_cp = row.x - 1;   /* AcceptReplyPacket.maxCheckpointedSlot :1139-1143 */
+        if (!S.gc_majority_executed) {
+          const int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
+          int lcp = max_cp - max_cp % cpi;
+          if (lcp < 0) {
+            lcp = jsub(lcp, cpi);
+            if (lcp > 0) lcp = 2147483647 - 2147483647 % cpi;
+          }
+          max_cp = lcp;
+        }
+      }
+      /* tally (handleAcceptReplyMyBallot :597-640): replies arrive in lane order, all for my ballot; the decision
+       * is made by reply number L/2 (0-based) with the nodeSlots recorded up to and including it */
+      int nsd[LP];
+#pragma unroll
+      for (int k = 0; k < LP; k++) {
+        const int mcp_k = __shfl_sync(tmask, max_cp, tbase + k);
+        nsd[k] = ns[k];
+        if (k < L && ns[k] < mcp_k) { /* recordSlotNumber :809-825 (plain <) */
+          ns[k] = mcp_k;
+          if (k <= L / 2) nsd[k] = mcp_k;
+        }
+      }
+      const int dmed = median_regs<LP>(nsd, (uint32_t)L); /* makeDecision(getMajorityCommittedSlot()) :630 */
+      const unsigned frame_ref = (unsigned)(((payb + (uint32_t)q2.x) & (S.ring_cap - 1)) >> 4);
+      if (sub < (uint32_t)L) {
+        /* ACCEPT log image + my lane's copy of the blob (AbstractPaxosLogger.logAndMessage) */
+        write_accept_image(S, sub, seg, n, i, q0, q1, q2, GPX_F_ACCEPT | ((1u << sub) << 16));
+        {
+          const uint32_t off = (uint32_t)q2.x, plen = (uint32_t)q2.y;
+          const uint8_t* src = A.blob0 + off;
+          if (((off | (uint32_t)(uintptr_t)src) & 15u) == 0) {
+            for (uint32_t b = 0; b < plen; b += 16) st_stream4(ring_ptr(S, sub, payb + off + b), ld_stream4(src + b));
+          } else {
+            for (uint32_t b = 0; b < plen; b++) *ring_ptr(S, sub, payb + off + b) = src[b];
+          }
+        }
+        /* commit (handleBatchedCommit :1488-1501 + extractExecuteAndCheckpoint): the accept is the decision */
+        const bool metaf = S.log_meta != 0;
+        st256_stream(ring_ptr(S, sub, dseg + 64 + (unsigned long long)i * 32), q0,
+                     make_int4(metaf ? -1 : dmed, (int)((GPX_F_DECISION | (metaf ? GPX_F_META : 0u)) | ((1u << sub) << 16)),
+                               rq0.z, rq0.w));
+        gc_step(row, dmed);
+        DPValue x;
+        x.slot = slot;
+        x.bnum = crow.x;
+        x.bcoord = crow.y;
+        x.median_cp = dmed;
+        x.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
+        x.frame_ref = frame_ref;
+        x.plen = (uint32_t)q2.y;
+        x.fl = (1u << 16);
+        x.valued = true;
+        row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
+        const gpx_exec_rec er = make_exec(S, gid, sub, x, false);
+        if (er.flags & GPX_F_CKPT) c_ckpt++;
+        store_exec(&A.exec[(size_t)i * L + sub], er);
+        const size_t ai = 2 * win_idx(S, sub, (uint32_t)slot & Wm, gid);
+        if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
+          if ((unsigned)e1.w & GPX_ENT_VALID)
+            st256(&S.acc_win[ai], make_int4(slot, crow.x, crow.y, (int)frame_ref), make_int4(rq0.z, rq0.w, q2.y, (int)(1u << 16)));
+        } else
+          st256(&S.acc_win[ai], make_int4(slot, crow.x, crow.y, (int)frame_ref),
+                make_int4(rq0.z, rq0.w, q2.y, (int)(GPX_ENT_VALID | (1u << 16))));
+        gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot */
+        uint32_t aux = my_aux;
+        if ((GPX_AUX_PRESENT(aux) >> ((uint32_t)row.x & Wm)) & 1u) { /* queued commits become executable (rare) */
+          eec(S, sub, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
+          if (aux != my_aux) S.acc_aux[row_idx(S, sub, gid)] = aux;
+        }
+        S.acc_row[row_idx(S, sub, gid)] = row;
+        if (ns[sub] != my_ns) S.node_slots[ns_idx(S, (uint32_t)cl, sub, gid)] = ns[sub];
+        c_lane++;
+      }
+      if (sub == 0) {
+        RA.P.status[i] = slot;
+        crow.z = (int)((unsigned)crow.z + 1u); /* PCS.propose: nextProposalSlotNumber++ (proposal decided at once) */
+        S.coord_row[row_idx(S, (uint32_t)cl, gid)] = crow;
+        st256_stream(&A.decisions[i], q0,
+                     make_int4(dmed, (int)(GPX_F_DECISION | (lane_mask << 16)), rq0.z, rq0.w));
+        A.out_mask[i] = 0;
+        c_team++;
+      }
+    } else {
+      if (SPLIT) { /* hand the run to k_round_slow: the fast kernel stays small (registers, occupancy) */
+        if (sub == 0) RA.todo[atomicAdd(RA.n_todo, 1u)] = i;
+      } else
+        round_general<L, LP>(S, RA, i, sub, tmask, tbase, gid, seg, dseg, payb, s_ctr);
+    }
+  }
+  /* fast-path events, counted in registers: one shared-memory update per warp */
+  {
+    const uint32_t nl = __reduce_add_sync(0xffffffffu, c_lane), nt = __reduce_add_sync(0xffffffffu, c_team);
+    const uint32_t nc = __reduce_add_sync(0xffffffffu, c_ckpt);
+    if (lane_id == 0 && (nl | nt)) {
+      atomicAdd(&s_ctr[C_ACCEPTS_HANDLED], nl);
+      atomicAdd(&s_ctr[C_ACCEPTS_ACKED], nl);
+      atomicAdd(&s_ctr[C_ACCEPTS_LOGGED], nl);
+      atomicAdd(&s_ctr[C_DECISIONS_HANDLED], nl);
+      atomicAdd(&s_ctr[C_EXECUTED], nl);
+      atomicAdd(&s_ctr[C_REPLIES_HANDLED], nl);
+      if (nc) atomicAdd(&s_ctr[C_CKPTS_DUE], nc);
+      atomicAdd(&s_ctr[C_PROPOSALS], nt);
+      atomicAdd(&s_ctr[C_REQS_BATCHED], nt);
+      atomicAdd(&s_ctr[C_DECISIONS_MADE], nt);
+    }
+  }
+  flush_counters(S, s_ctr);
+  __shared__ unsigned int s_last;
+  __threadfence();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[5], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x < (uint32_t)L) {
+    S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
+    S.seg_seq[threadIdx.x] += 2ull;
+  }
+  if (s_last && threadIdx.x == 0) S.tickets[5] = 0;
+}
+
+/* The runs the fast kernel did not take (several requests of a group, STOPs, NACKs, coordinator changes, ...).
+ * A fixed, small grid loops over the todo list; with an empty list the launch costs a few microseconds. */
+template <int L, int LP>
+__global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_constant__ DevState S,
+                                                             const __grid_constant__ RoundArgs RA) {
+  __shared__ unsigned int s_ctr[C_NCTR];
+  if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t ntodo = *RA.n_todo;
+  if (ntodo) {
+    const AcceptArgs& A = RA.A;
+    const uint32_t n = RA.P.n;
+    const uint32_t t = blockIdx.x * GPX_BLOCK + threadIdx.x;
+    const uint32_t sub = t % LP, team = t / LP, nteams = gridDim.x * GPX_BLOCK / LP;
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t tbase = lane_id & ~(uint32_t)(LP - 1);
+    const uint32_t tmask = (LP == 32 ? 0xffffffffu : ((1u << LP) - 1u)) << tbase;
+    const unsigned long long pay_bytes = A.blob0_bytes + RA.blob1_res;
+    const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
+    const unsigned long long res_a = (pay_rel + pay_bytes + 31ull) & ~31ull;
+    const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
+    const uint32_t myl = sub < (uint32_t)L ? sub : 0u;
+    /* the fast kernel already advanced the ring heads past this round's two segments */
+    const unsigned long long seg = S.ring_head[myl] - (res_a + res_d);
+    const unsigned long long payb = seg + pay_rel, dseg = seg + res_a;
+    for (uint32_t k = team; k < ntodo; k += nteams) {
+      const uint32_t i = RA.todo[k];
+      const uint32_t gid = RA.P.reqs[i].gid;
+      round_general<L, LP>(S, RA, i, sub, tmask, tbase, gid, seg, dseg, payb, s_ctr);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
+  flush_counters(S, s_ctr);
+}

@@ -1335,23 +1335,38 @@ int gpxo_round_phases(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, c
 }
 
 /* one full round for co-located replicas in the fused order (PaxosManager.send routing with loopback
- * :2098-2128): RequestBatcher + propose, then per ACCEPT accept -> tally -> commit */
+ * :2098-2128): RequestBatcher + propose, then per ACCEPT accept -> tally -> commit.  Records, log images
+ * and EXEC rows are indexed by REQUEST (the ACCEPT of a batch sits at the index of its first request; the
+ * other indices are VOID), exactly like the device's k_round kernel. */
 int gpxo_round(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
                uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
                gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
   u32 L = e->L();
+  const u64 pal = (payload_bytes + 15) & ~(u64)15;
+  const u64 blob1_res = e->cfg.batching_enabled ? 16ull * n + pal : 0;
   std::vector<gpx_accept_rec> acc(n);
-  std::vector<uint8_t> blob(2 * ((payload_bytes + 15) & ~15ull) + 32ull * n + 64);
+  std::vector<uint8_t> blob(pal + blob1_res + 64);
   u32 na = 0;
   u64 bb = 0;
   int rc = gpxo_propose(e, n, reqs, payload, payload_bytes, acc.data(), &na, blob.data(), blob.size(), &bb, status);
   if (rc) return rc;
-  std::vector<gpx_accept_reply_rec> rep((size_t)na * L + 1);
-  std::vector<gpx_decision_rec> dec((size_t)na + 1);
-  rc = gpxo_handle_accepts_fused(e, na, acc.data(), blob.data(), bb, rep.data(), dec.data(), out_exec, out_extra_exec,
-                                 extra_cap, n_extra);
+  std::vector<gpx_accept_rec> full(n);
+  u32 k = 0;
+  for (u32 i = 0; i < n; i++) {
+    if (status[i] > 0 && k < na)
+      full[i] = acc[k++];
+    else {
+      memset(&full[i], 0, sizeof full[i]);
+      full[i].h.gid = reqs[i].gid;
+      full[i].h.flags = GPX_F_VOID;
+    }
+  }
+  std::vector<gpx_accept_reply_rec> rep((size_t)n * L + 1);
+  std::vector<gpx_decision_rec> dec((size_t)n + 1);
+  rc = gpxo_handle_accepts_fused(e, n, full.data(), blob.data(), pal + blob1_res, rep.data(), dec.data(), out_exec,
+                                 out_extra_exec, extra_cap, n_extra);
   if (rc) return rc;
-  *n_exec_slots = na * L;
+  *n_exec_slots = n * L;
   return GPX_OK;
 }
 
