@@ -299,6 +299,15 @@ class Engine:
                                         C.byref(nx)))
         return status[:n].copy(), ex[: ns.value].copy(), extra[: min(nx.value, extra_cap)].copy()
 
+    def digest_requests(self, reqs: np.ndarray, payload: np.ndarray) -> np.ndarray:
+        """MD5 of every requestValue (RequestPacket.getDigest), shape [n, 16]."""
+        reqs = np.ascontiguousarray(reqs, dtype=request_dtype)
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        out = np.zeros((max(len(reqs), 1), 16), dtype=np.uint8)
+        self.L.check(self.L.fn("digest_requests")(self._h, C.c_uint32(len(reqs)), _ptr(reqs), _ptr(payload),
+                                                  C.c_uint64(payload.size), _ptr(out)))
+        return out[: len(reqs)]
+
     # ---- log / counters --------------------------------------------------------------
     def log_head(self, lane: int) -> int:
         head = C.c_uint64(0)

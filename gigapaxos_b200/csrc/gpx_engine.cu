@@ -158,6 +158,11 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   if (cfg->log_ring_bytes < (1u << 16) || (cfg->log_ring_bytes & (cfg->log_ring_bytes - 1)))
     return fail(GPX_EINVAL, "log_ring_bytes must be a power of two >= 64 KiB");
   if (cfg->max_groups == 0 || cfg->max_batch_recs == 0) return fail(GPX_EINVAL, "zero capacity");
+  { /* the kernels index the state planes with 32-bit element indices */
+    const unsigned long long span = 2ull * cfg->n_lanes * cfg->max_groups *
+                                    (cfg->window > cfg->max_group_size ? cfg->window : cfg->max_group_size);
+    if (span >= (1ull << 32)) return fail(GPX_EINVAL, "max_groups * n_lanes * window too large for one engine");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(GPX_ENOGPU, "no CUDA device: the gpx engine has no CPU fallback");
@@ -575,17 +580,17 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.blob1_res = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
   RA.A.blob1_bytes = RA.blob1_res;
   const uint32_t L = e->cfg.n_lanes;
-  const uint32_t LP = L <= 1 ? 1 : L <= 2 ? 2 : L <= 4 ? 4 : 8;
-  const uint32_t grid = cdiv((uint64_t)n * LP, GPX_BLOCK);
+  const uint32_t teams_per_block = (GPX_BLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
+  const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
   const uint32_t slow_grid = std::min<uint32_t>(grid, 2u * (uint32_t)e->n_sms);
   switch (L) {
     case 1: launch_round_t<1, 1>(grid, slow_grid, st, e->S, RA); break;
     case 2: launch_round_t<2, 2>(grid, slow_grid, st, e->S, RA); break;
-    case 3: launch_round_t<3, 4>(grid, slow_grid, st, e->S, RA); break;
+    case 3: launch_round_t<3, 3>(grid, slow_grid, st, e->S, RA); break;
     case 4: launch_round_t<4, 4>(grid, slow_grid, st, e->S, RA); break;
-    case 5: launch_round_t<5, 8>(grid, slow_grid, st, e->S, RA); break;
-    case 6: launch_round_t<6, 8>(grid, slow_grid, st, e->S, RA); break;
-    case 7: launch_round_t<7, 8>(grid, slow_grid, st, e->S, RA); break;
+    case 5: launch_round_t<5, 5>(grid, slow_grid, st, e->S, RA); break;
+    case 6: launch_round_t<6, 6>(grid, slow_grid, st, e->S, RA); break;
+    case 7: launch_round_t<7, 7>(grid, slow_grid, st, e->S, RA); break;
     default: launch_round_t<8, 8>(grid, slow_grid, st, e->S, RA); break;
   }
   CK(cudaGetLastError());
@@ -904,6 +909,25 @@ int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* st
   if (rc) return rc;
   return round_on_stream(e, false, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
                          stream ? (cudaStream_t)stream : e->stream);
+}
+
+/* RequestPacket.getDigest :1414-1430 for a batch of requests (the digest column of DIGEST_REQUESTS mode) */
+int gpx_digest_requests(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                        uint64_t payload_bytes, uint8_t* out_digests) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!reqs || !out_digests || (!payload && payload_bytes)) return fail(GPX_EINVAL, "null argument");
+  int rc = check_batch(e, n, payload_bytes);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  CK(cudaMemcpyAsync(e->d_reqs, reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, st));
+  if (payload_bytes) CK(cudaMemcpyAsync(e->d_payload, payload, payload_bytes, cudaMemcpyHostToDevice, st));
+  /* digests go to the blob scratch (16 B per request fits: blob1_cap >= 16 * max_batch_recs) */
+  k_md5<<<cdiv(n, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->d_reqs, n, e->d_payload, e->d_blob1);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_digests, e->d_blob1, 16ull * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GPX_OK;
 }
 
 int gpx_enable_kernel_timing(gpx_engine* e, int on) {

@@ -1405,3 +1405,78 @@ __global__ void k_get_flags(const __grid_constant__ DevState S, uint32_t lane, c
   if (i >= n) return;
   out[i] = gids[i] < S.G ? (uint8_t)GPX_AUX_FLAGS(S.acc_aux[row_idx(S, lane, gids[i])]) : 0;
 }
+
+/* ============================== digests (DIGEST_REQUESTS) ============================== */
+/* RequestPacket.getDigest paxospackets/RequestPacket.java:1414-1430: MD5 of the requestValue bytes -- the
+ * "accepted-pvalue digest" column.  One thread per request; RFC 1321. */
+__device__ __forceinline__ uint32_t md5_rotl(uint32_t x, int c) { return (x << c) | (x >> (32 - c)); }
+__constant__ uint32_t c_md5_k[64] = {
+    0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8,
+    0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340,
+    0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87,
+    0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a, 0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c,
+    0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039,
+    0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92,
+    0xffeff47d, 0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb,
+    0xeb86d391};
+__constant__ uint8_t c_md5_s[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9,  14, 20, 5, 9,
+                                    14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
+                                    4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+
+__device__ __forceinline__ uint32_t md5_byte(const uint8_t* msg, uint64_t len, uint64_t padded, uint64_t idx) {
+  if (idx < len) return msg[idx];
+  if (idx == len) return 0x80u;
+  if (idx >= padded - 8) return (uint32_t)(((len * 8ull) >> (8 * (idx - (padded - 8)))) & 0xffu);
+  return 0u;
+}
+
+__global__ void __launch_bounds__(GPX_BLOCK) k_md5(const gpx_request_rec* reqs, uint32_t n, const uint8_t* payload,
+                                                   uint8_t* out /* [n][16] */) {
+  const uint32_t i = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* msg = payload + reqs[i].payload_off;
+  const uint64_t len = reqs[i].payload_len;
+  const uint64_t padded = ((len + 8) / 64 + 1) * 64;
+  uint32_t a0 = 0x67452301u, b0 = 0xefcdab89u, c0 = 0x98badcfeu, d0 = 0x10325476u;
+  for (uint64_t off = 0; off < padded; off += 64) {
+    uint32_t M[16];
+#pragma unroll
+    for (int w = 0; w < 16; w++) {
+      const uint64_t p = off + 4ull * w;
+      if (p + 4 <= len && ((uintptr_t)(msg + p) & 3u) == 0)
+        M[w] = *reinterpret_cast<const uint32_t*>(msg + p);
+      else
+        M[w] = md5_byte(msg, len, padded, p) | (md5_byte(msg, len, padded, p + 1) << 8) |
+               (md5_byte(msg, len, padded, p + 2) << 16) | (md5_byte(msg, len, padded, p + 3) << 24);
+    }
+    uint32_t A = a0, B = b0, Cc = c0, D = d0;
+#pragma unroll
+    for (int r = 0; r < 64; r++) {
+      uint32_t F;
+      int g;
+      if (r < 16) {
+        F = (B & Cc) | (~B & D);
+        g = r;
+      } else if (r < 32) {
+        F = (D & B) | (~D & Cc);
+        g = (5 * r + 1) & 15;
+      } else if (r < 48) {
+        F = B ^ Cc ^ D;
+        g = (3 * r + 5) & 15;
+      } else {
+        F = Cc ^ (B | ~D);
+        g = (7 * r) & 15;
+      }
+      F = F + A + c_md5_k[r] + M[g];
+      A = D;
+      D = Cc;
+      Cc = B;
+      B = B + md5_rotl(F, c_md5_s[r]);
+    }
+    a0 += A;
+    b0 += B;
+    c0 += Cc;
+    d0 += D;
+  }
+  *reinterpret_cast<int4*>(out + 16ull * i) = make_int4((int)a0, (int)b0, (int)c0, (int)d0);
+}

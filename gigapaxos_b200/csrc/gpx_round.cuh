@@ -2,7 +2,7 @@
  * gpx_round.cuh -- k_round: one launch advances every group of a request batch through a whole Paxos
  * round (RequestBatcher -> propose -> accept x R -> tally -> commit x R) for co-located replicas.
  *
- * Work mapping: a TEAM of LP threads (LP = lanes padded to 1/2/4/8, adjacent lanes of one warp) owns one
+ * Work mapping: a TEAM of LP = L threads (adjacent lanes of one warp, 32/LP teams per warp) owns one
  * request index; team thread `sub` < L is replica lane `sub` of the group.  The team of the first request of
  * a run of equal gids processes the run (the reference's per-instance `synchronized`).
  *   propose  computed redundantly by every team thread from the same loads (broadcast loads, no shuffles):
@@ -42,7 +42,7 @@ struct RoundArgs {
 template <int LP>
 __device__ __forceinline__ int median_regs(const int (&ns)[LP], uint32_t R) {
   if (R == 1) return ns[0];
-  if (LP >= 4 && R == 3) return max(min(ns[0], ns[1]), min(max(ns[0], ns[1]), ns[2]));
+  if (LP >= 3 && R == 3) return max(min(ns[0], ns[1]), min(max(ns[0], ns[1]), ns[2]));
   int v[LP];
 #pragma unroll
   for (int k = 0; k < LP; k++) v[k] = (uint32_t)k < R ? ns[k] : 2147483647;
@@ -331,11 +331,16 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
   const AcceptArgs& A = RA.A;
   const gpx_request_rec* reqs = RA.P.reqs;
   const uint32_t n = RA.P.n;
+  /* teams of LP adjacent lanes; 32/LP teams per warp (the 32 mod LP last lanes of a warp idle) */
   const uint32_t t = blockIdx.x * GPX_BLOCK + threadIdx.x;
-  const uint32_t sub = t % LP, i = t / LP;
   const uint32_t lane_id = threadIdx.x & 31u;
-  const uint32_t tbase = lane_id & ~(uint32_t)(LP - 1);
-  const uint32_t tmask = (LP == 32 ? 0xffffffffu : ((1u << LP) - 1u)) << tbase;
+  constexpr uint32_t TPW = 32u / LP;
+  const uint32_t team_in_warp = lane_id / LP;
+  const uint32_t sub = lane_id - team_in_warp * LP;
+  const uint32_t tbase = team_in_warp * LP;
+  const uint32_t tmask = ((1u << LP) - 1u) << tbase;
+  const uint32_t i = team_in_warp < TPW ? (blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5)) * TPW + team_in_warp
+                                        : 0xffffffffu;
   const uint32_t Wm = S.W - 1;
   /* per-lane log segments of this launch: [ACCEPT seg (n images + payload area)][DECISION seg] */
   const unsigned long long pay_bytes = A.blob0_bytes + RA.blob1_res;
@@ -351,33 +356,35 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
   }
   if (t == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
 
-  /* ---- level A loads: the request record and the neighbour's gid (run-head test) ---- */
-  bool head = false;
+  /* ---- level A loads: the request record and the neighbours' gids (run-head / single tests) ---- */
+  static_assert(LP == L, "teams are exactly the L lanes of a group");
+  bool head = false, single = false;
   uint32_t gid = 0;
   int4 rq0 = make_int4(0, 0, 0, 0), rq1 = rq0;
   if (i < n) {
     ld256_stream(&reqs[i], rq0, rq1);
+    const uint32_t gprev = i > 0 ? reqs[i - 1].gid : 0xffffffffu;
+    const uint32_t gnext = i + 1 < n ? reqs[i + 1].gid : 0xffffffffu;
     gid = (uint32_t)rq0.x;
-    head = (i == 0) || (reqs[i - 1].gid != gid);
+    head = (i == 0) || (gprev != gid);
+    single = gnext != gid;
   }
   uint32_t c_lane = 0, c_team = 0, c_ckpt = 0; /* fast-path event counts, reduced once per warp at the end */
   if (head) { /* team-uniform */
-    const bool single = !(i + 1 < n && reqs[i + 1].gid == gid);
     const uint32_t rflags = (uint32_t)rq0.y;
     const uint32_t entry = (rflags >> 8) & 0xfu;
-    /* ---- level B loads (depend on gid only): group meta, my lane's acceptor + coordinator rows ---- */
+    /* ---- level B loads (depend on gid only): group meta, my lane's acceptor + coordinator rows, and --
+     * speculatively -- nodeSlotNumbers of the lane my acceptor believes to coordinate ---- */
     const bool gid_ok = gid < S.G;
-    uint32_t meta = 0;
-    uint32_t my_aux = 0;
+    uint32_t meta = 0, my_aux = 0;
     int4 my_row = make_int4(0, 0, 0, 0), my_crow = my_row;
+    const uint32_t G = S.G;
+    const uint32_t ri = sub * G + gid; /* row index of my lane (32-bit: L*G < 2^32 is checked at engine creation) */
     if (gid_ok) {
       meta = S.grp_meta[gid];
-      if (sub < (uint32_t)L) {
-        const size_t ri = row_idx(S, sub, gid);
-        my_aux = S.acc_aux[ri];
-        my_row = S.acc_row[ri];
-        my_crow = S.coord_row[ri];
-      }
+      my_aux = S.acc_aux[ri];
+      my_row = S.acc_row[ri];
+      my_crow = S.coord_row[ri];
     }
     /* the in-order fast path needs: one request for the group, a live group whose R members are exactly the
      * L local lanes in member order, no STOP */
@@ -412,18 +419,14 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
     /* ---- level C loads (depend on the slot / the coordinator lane): window entry, nodeSlotNumbers ---- */
     int4 e0 = make_int4(0, 0, 0, 0), e1 = e0;
     int my_ns = 0;
-    if (sf && sub < (uint32_t)L) {
-      ld256(&S.acc_win[2 * win_idx(S, sub, (uint32_t)slot & Wm, gid)], e0, e1);
-      my_ns = S.node_slots[ns_idx(S, (uint32_t)cl, sub, gid)];
-    }
+    const uint32_t wi = (sub * S.W + ((uint32_t)slot & Wm)) * G + gid; /* window index of my lane at slot mod W */
     if (sf) {
+      ld256(&S.acc_win[2u * wi], e0, e1);
+      my_ns = S.node_slots[((uint32_t)cl * S.Rcap + sub) * G + gid];
       /* every lane must be the plain in-order case: usable, same ballot, next slot, nothing already there */
-      bool ok = true;
-      if (sub < (uint32_t)L) {
-        const bool ent_live = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, my_row.w) > 0 && e0.x == slot;
-        ok = st_usable(my_aux) && my_row.y == crow.x && my_row.z == crow.y && my_row.x == slot && !ent_live &&
-             !((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)slot & Wm)) & 1u) && jsub(slot, my_row.w) > 0;
-      }
+      const bool ent_live = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, my_row.w) > 0 && e0.x == slot;
+      const bool ok = st_usable(my_aux) && my_row.y == crow.x && my_row.z == crow.y && my_row.x == slot && !ent_live &&
+                      !((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)slot & Wm)) & 1u) && jsub(slot, my_row.w) > 0;
       sf = __ballot_sync(tmask, ok) == tmask;
     }
     if (sf) {
@@ -432,25 +435,20 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
 #pragma unroll
       for (int k = 0; k < LP; k++) ns[k] = __shfl_sync(tmask, my_ns, tbase + k);
       const int median = median_regs<LP>(ns, (uint32_t)L); /* AcceptPacket.medianCheckpointedSlot (initCommander) */
-      const uint32_t lane_mask = (1u << L) - 1u;
+      constexpr uint32_t lane_mask = (1u << L) - 1u;
       const int4 q0 = make_int4((int)gid, slot, crow.x, crow.y);
-      const int4 q1 = make_int4(median, (int)(GPX_F_ACCEPT | (lane_mask << 16)), rq0.z, rq0.w);
-      const int4 q2 = make_int4(rq1.x, rq1.y, 1, crow.y);
       /* handleAccept at my lane: ballot equal, slot next-in-line, no previous accept -> ack + log */
       int4 row = my_row;
-      int max_cp = 0;
-      if (sub < (uint32_t)L) {
-        gc_step(row, median); /* acceptAndUpdateBallot -> garbageCollectAccepted :320 */
-        max_cp = row.x - 1;   /* AcceptReplyPacket.maxCheckpointedSlot :1139-1143 */
-        if (!S.gc_majority_executed) {
-          const int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
-          int lcp = max_cp - max_cp % cpi;
-          if (lcp < 0) {
-            lcp = jsub(lcp, cpi);
-            if (lcp > 0) lcp = 2147483647 - 2147483647 % cpi;
-          }
-          max_cp = lcp;
+      gc_step(row, median);   /* acceptAndUpdateBallot -> garbageCollectAccepted :320 */
+      int max_cp = row.x - 1; /* AcceptReplyPacket.maxCheckpointedSlot :1139-1143 */
+      if (!S.gc_majority_executed) {
+        const int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
+        int lcp = max_cp - max_cp % cpi;
+        if (lcp < 0) {
+          lcp = jsub(lcp, cpi);
+          if (lcp > 0) lcp = 2147483647 - 2147483647 % cpi;
         }
+        max_cp = lcp;
       }
       /* tally (handleAcceptReplyMyBallot :597-640): replies arrive in lane order, all for my ballot; the decision
        * is made by reply number L/2 (0-based) with the nodeSlots recorded up to and including it */
@@ -459,31 +457,58 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
       for (int k = 0; k < LP; k++) {
         const int mcp_k = __shfl_sync(tmask, max_cp, tbase + k);
         nsd[k] = ns[k];
-        if (k < L && ns[k] < mcp_k) { /* recordSlotNumber :809-825 (plain <) */
+        if (ns[k] < mcp_k) { /* recordSlotNumber :809-825 (plain <) */
           ns[k] = mcp_k;
           if (k <= L / 2) nsd[k] = mcp_k;
         }
       }
       const int dmed = median_regs<LP>(nsd, (uint32_t)L); /* makeDecision(getMajorityCommittedSlot()) :630 */
-      const unsigned frame_ref = (unsigned)(((payb + (uint32_t)q2.x) & (S.ring_cap - 1)) >> 4);
-      if (sub < (uint32_t)L) {
-        /* ACCEPT log image + my lane's copy of the blob (AbstractPaxosLogger.logAndMessage) */
-        write_accept_image(S, sub, seg, n, i, q0, q1, q2, GPX_F_ACCEPT | ((1u << sub) << 16));
-        {
-          const uint32_t off = (uint32_t)q2.x, plen = (uint32_t)q2.y;
-          const uint8_t* src = A.blob0 + off;
-          if (((off | (uint32_t)(uintptr_t)src) & 15u) == 0) {
-            for (uint32_t b = 0; b < plen; b += 16) st_stream4(ring_ptr(S, sub, payb + off + b), ld_stream4(src + b));
-          } else {
-            for (uint32_t b = 0; b < plen; b++) *ring_ptr(S, sub, payb + off + b) = src[b];
-          }
+      /* my lane's two log segments are linear inside the ring (a launch never straddles the wrap) */
+      uint8_t* const seg_p = ring_ptr(S, sub, seg);
+      const uint32_t poff = (uint32_t)rq1.x, plen = (uint32_t)rq1.y;
+      const unsigned frame_ref = (unsigned)(((seg + pay_rel + poff) & (S.ring_cap - 1)) >> 4);
+      /* ACCEPT log image + my lane's copy of the blob (AbstractPaxosLogger.logAndMessage) */
+      st256_stream(seg_p + 64 + (size_t)i * 32, q0,
+                   make_int4(median, (int)(GPX_F_ACCEPT | ((1u << sub) << 16)), rq0.z, rq0.w));
+      st_stream4(seg_p + 64 + (size_t)n * 32 + (size_t)i * 16, make_int4((int)poff, (int)plen, 1, crow.y));
+      {
+        const uint8_t* src = A.blob0 + poff;
+        uint8_t* dst = seg_p + pay_rel + poff;
+        if (((poff | (uint32_t)(uintptr_t)src) & 15u) == 0) {
+          for (uint32_t b = 0; b < plen; b += 16) st_stream4(dst + b, ld_stream4(src + b));
+        } else {
+          for (uint32_t b = 0; b < plen; b++) dst[b] = src[b];
         }
-        /* commit (handleBatchedCommit :1488-1501 + extractExecuteAndCheckpoint): the accept is the decision */
-        const bool metaf = S.log_meta != 0;
-        st256_stream(ring_ptr(S, sub, dseg + 64 + (unsigned long long)i * 32), q0,
-                     make_int4(metaf ? -1 : dmed, (int)((GPX_F_DECISION | (metaf ? GPX_F_META : 0u)) | ((1u << sub) << 16)),
-                               rq0.z, rq0.w));
-        gc_step(row, dmed);
+      }
+      /* commit (handleBatchedCommit :1488-1501 + extractExecuteAndCheckpoint): the accept is the decision */
+      const bool metaf = S.log_meta != 0;
+      st256_stream(seg_p + res_a + 64 + (size_t)i * 32, q0,
+                   make_int4(metaf ? -1 : dmed, (int)((GPX_F_DECISION | (metaf ? GPX_F_META : 0u)) | ((1u << sub) << 16)),
+                             rq0.z, rq0.w));
+      gc_step(row, dmed);
+      /* EXEC record (PISM.execute hands the request to the app): checkpoint-due flag = slot % CPI == 0 */
+      {
+        const int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
+        const bool ckpt = (slot % cpi) == 0;
+        if (ckpt) c_ckpt++;
+        gpx_exec_rec er;
+        er.gid = gid;
+        er.slot = slot;
+        er.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
+        er.payload_off = frame_ref;
+        er.flags = (ckpt ? GPX_F_CKPT : 0u) | (sub << 12) | (1u << 16);
+        store_exec(&A.exec[(size_t)i * L + sub], er);
+      }
+      row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
+      if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
+        if ((unsigned)e1.w & GPX_ENT_VALID)
+          st256(&S.acc_win[2u * wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
+                make_int4(rq0.z, rq0.w, (int)plen, (int)(1u << 16)));
+      } else
+        st256(&S.acc_win[2u * wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
+              make_int4(rq0.z, rq0.w, (int)plen, (int)(GPX_ENT_VALID | (1u << 16))));
+      gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot */
+      if ((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)row.x & Wm)) & 1u) { /* queued commits become executable (rare) */
         DPValue x;
         x.slot = slot;
         x.bnum = crow.x;
@@ -491,36 +516,27 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
         x.median_cp = dmed;
         x.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
         x.frame_ref = frame_ref;
-        x.plen = (uint32_t)q2.y;
+        x.plen = plen;
         x.fl = (1u << 16);
         x.valued = true;
-        row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
-        const gpx_exec_rec er = make_exec(S, gid, sub, x, false);
-        if (er.flags & GPX_F_CKPT) c_ckpt++;
-        store_exec(&A.exec[(size_t)i * L + sub], er);
-        const size_t ai = 2 * win_idx(S, sub, (uint32_t)slot & Wm, gid);
-        if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
-          if ((unsigned)e1.w & GPX_ENT_VALID)
-            st256(&S.acc_win[ai], make_int4(slot, crow.x, crow.y, (int)frame_ref), make_int4(rq0.z, rq0.w, q2.y, (int)(1u << 16)));
-        } else
-          st256(&S.acc_win[ai], make_int4(slot, crow.x, crow.y, (int)frame_ref),
-                make_int4(rq0.z, rq0.w, q2.y, (int)(GPX_ENT_VALID | (1u << 16))));
-        gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot */
         uint32_t aux = my_aux;
-        if ((GPX_AUX_PRESENT(aux) >> ((uint32_t)row.x & Wm)) & 1u) { /* queued commits become executable (rare) */
-          eec(S, sub, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
-          if (aux != my_aux) S.acc_aux[row_idx(S, sub, gid)] = aux;
-        }
-        S.acc_row[row_idx(S, sub, gid)] = row;
-        if (ns[sub] != my_ns) S.node_slots[ns_idx(S, (uint32_t)cl, sub, gid)] = ns[sub];
-        c_lane++;
+        eec(S, sub, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
+        if (aux != my_aux) S.acc_aux[ri] = aux;
       }
+      S.acc_row[ri] = row;
+      { /* nodeSlotNumbers[cl][sub] */
+        int mine = ns[0];
+#pragma unroll
+        for (int k = 1; k < LP; k++)
+          if (sub == (uint32_t)k) mine = ns[k];
+        if (mine != my_ns) S.node_slots[((uint32_t)cl * S.Rcap + sub) * G + gid] = mine;
+      }
+      c_lane++;
       if (sub == 0) {
         RA.P.status[i] = slot;
         crow.z = (int)((unsigned)crow.z + 1u); /* PCS.propose: nextProposalSlotNumber++ (proposal decided at once) */
-        S.coord_row[row_idx(S, (uint32_t)cl, gid)] = crow;
-        st256_stream(&A.decisions[i], q0,
-                     make_int4(dmed, (int)(GPX_F_DECISION | (lane_mask << 16)), rq0.z, rq0.w));
+        S.coord_row[(uint32_t)cl * G + gid] = crow;
+        st256_stream(&A.decisions[i], q0, make_int4(dmed, (int)(GPX_F_DECISION | (lane_mask << 16)), rq0.z, rq0.w));
         A.out_mask[i] = 0;
         c_team++;
       }
@@ -572,11 +588,15 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
   if (ntodo) {
     const AcceptArgs& A = RA.A;
     const uint32_t n = RA.P.n;
-    const uint32_t t = blockIdx.x * GPX_BLOCK + threadIdx.x;
-    const uint32_t sub = t % LP, team = t / LP, nteams = gridDim.x * GPX_BLOCK / LP;
     const uint32_t lane_id = threadIdx.x & 31u;
-    const uint32_t tbase = lane_id & ~(uint32_t)(LP - 1);
-    const uint32_t tmask = (LP == 32 ? 0xffffffffu : ((1u << LP) - 1u)) << tbase;
+    constexpr uint32_t TPW = 32u / LP;
+    const uint32_t team_in_warp = lane_id / LP;
+    const uint32_t sub = lane_id - team_in_warp * LP;
+    const uint32_t tbase = team_in_warp * LP;
+    const uint32_t tmask = ((1u << LP) - 1u) << tbase;
+    const uint32_t nteams = gridDim.x * (GPX_BLOCK / 32u) * TPW;
+    const uint32_t team = team_in_warp < TPW ? (blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5)) * TPW + team_in_warp
+                                             : 0xffffffffu;
     const unsigned long long pay_bytes = A.blob0_bytes + RA.blob1_res;
     const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
     const unsigned long long res_a = (pay_rel + pay_bytes + 31ull) & ~31ull;

@@ -357,6 +357,13 @@ int gpx_round_phases(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, con
                      uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
                      gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
 
+/* Digest path (DIGEST_REQUESTS, paxospackets/RequestPacket.java:1414-1430, AcceptPacket.digest :162-170):
+ * MD5 of every request's requestValue, 16 bytes each -- the digest a coordinator puts into an ACCEPT in
+ * place of the request body and an acceptor checks against the body it received by broadcast
+ * (paxosutil/PendingDigests.java:82-145, host side). */
+int gpx_digest_requests(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                        uint64_t payload_bytes, uint8_t* out_digests);
+
 /* ---- log ring ------------------------------------------------------------------- */
 /* copy ring bytes [from, min(head, from+cap)) of `lane` into dst; *head receives the ring head */
 int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_t cap,

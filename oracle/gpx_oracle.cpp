@@ -1412,6 +1412,13 @@ int32_t gpxo_round_robin_coordinator(int32_t name_hash, const int32_t* sorted_me
 int32_t gpxo_get_cpi(int32_t cpi, double noise, int32_t name_hash) { return getCPI(cpi, noise, name_hash); }
 int32_t gpxo_last_checkpoint_slot(int32_t slot, int32_t cpi) { return lastCheckpointSlot(slot, cpi); }
 void gpxo_md5(const uint8_t* msg, size_t len, uint8_t out[16]) { md5(msg, len, out); }
+int gpxo_digest_requests(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
+                         uint64_t payload_bytes, uint8_t* out_digests) {
+  (void)e;
+  (void)payload_bytes;
+  for (u32 i = 0; i < n; i++) md5(payload + reqs[i].payload_off, reqs[i].payload_len, out_digests + 16ull * i);
+  return GPX_OK;
+}
 
 /* HotRestoreInfo string round trip: parse `in`, re-serialise into out (cap bytes) */
 int gpxo_hri_roundtrip(const char* in, char* out, size_t cap) {
