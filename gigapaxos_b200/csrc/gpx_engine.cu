@@ -547,7 +547,7 @@ static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uin
 extern "C++" {
 template <int L, int LP>
 static void launch_round_t(uint32_t grid, uint32_t slow_grid, cudaStream_t st, const DevState& S, const RoundArgs& RA) {
-  k_round<L, LP, true><<<grid, GPX_BLOCK, 0, st>>>(S, RA);
+  k_round<L, LP><<<grid, GPX_BLOCK, 0, st>>>(S, RA);
   k_round_slow<L, LP><<<slow_grid, GPX_BLOCK, 0, st>>>(S, RA);
 }
 }

@@ -322,235 +322,239 @@ __device__ __forceinline__ void round_general(const DevState& S, const RoundArgs
   }
 }
 
-template <int L, int LP, bool SPLIT>
+/*
+ * The fast kernel.  The whole body is straight-line, predicated code: every shuffle and vote is a full-warp
+ * operation outside divergent control flow (no per-team reconvergence bookkeeping), loads are issued in three
+ * dependent levels (request -> rows of the group -> window entry / nodeSlotNumbers), and a team either takes
+ * the in-order fast path or hands its request index to k_round_slow.  The ring heads are advanced by
+ * k_round_slow (always launched behind this kernel on the same stream), so warps retire right after their last
+ * store -- no fence, no ticket.
+ */
+template <int L, int LP>
 __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __grid_constant__ DevState S,
                                                                      const __grid_constant__ RoundArgs RA) {
+  static_assert(LP == L, "teams are exactly the L lanes of a group");
+  constexpr uint32_t FULL = 0xffffffffu;
   __shared__ unsigned int s_ctr[C_NCTR];
   if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
   __syncthreads();
   const AcceptArgs& A = RA.A;
   const gpx_request_rec* reqs = RA.P.reqs;
   const uint32_t n = RA.P.n;
-  /* teams of LP adjacent lanes; 32/LP teams per warp (the 32 mod LP last lanes of a warp idle) */
-  const uint32_t t = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  /* teams of L adjacent lanes; 32/L teams per warp (the 32 mod L last lanes of a warp idle) */
   const uint32_t lane_id = threadIdx.x & 31u;
   constexpr uint32_t TPW = 32u / LP;
   const uint32_t team_in_warp = lane_id / LP;
   const uint32_t sub = lane_id - team_in_warp * LP;
   const uint32_t tbase = team_in_warp * LP;
-  const uint32_t tmask = ((1u << LP) - 1u) << tbase;
+  constexpr uint32_t TEAM = (1u << LP) - 1u;
   const uint32_t i = team_in_warp < TPW ? (blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5)) * TPW + team_in_warp
                                         : 0xffffffffu;
-  const uint32_t Wm = S.W - 1;
+  const uint32_t G = S.G, Wm = S.W - 1;
   /* per-lane log segments of this launch: [ACCEPT seg (n images + payload area)][DECISION seg] */
   const unsigned long long pay_bytes = A.blob0_bytes + RA.blob1_res;
-  const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
-  const unsigned long long res_a = (pay_rel + pay_bytes + 31ull) & ~31ull;
+  const uint32_t pay_rel = 64u + n * 48u;
+  const unsigned long long res_a = ((unsigned long long)pay_rel + pay_bytes + 31ull) & ~31ull;
   const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
-  const uint32_t myl = sub < (uint32_t)L ? sub : 0u;
-  const unsigned long long seg = seg_base(S, myl, res_a + res_d);
-  const unsigned long long payb = seg + pay_rel, dseg = seg + res_a;
-  if (t < (uint32_t)L) { /* thread l writes lane l's two segment headers */
-    write_seg_hdr(S, t, seg_base(S, t, res_a + res_d), GPX_F_ACCEPT, n, n, pay_bytes, 48, S.seg_seq[t]);
-    write_seg_hdr(S, t, seg_base(S, t, res_a + res_d) + res_a, GPX_F_DECISION, n, n, 0, 32, S.seg_seq[t] + 1ull);
+  const unsigned long long seg = seg_base(S, sub, res_a + res_d);
+  if (blockIdx.x == 0 && threadIdx.x < (uint32_t)L) { /* thread l writes lane l's two segment headers */
+    const uint32_t t = threadIdx.x;
+    write_seg_hdr(S, t, seg, GPX_F_ACCEPT, n, n, pay_bytes, 48, S.seg_seq[t]);
+    write_seg_hdr(S, t, seg + res_a, GPX_F_DECISION, n, n, 0, 32, S.seg_seq[t] + 1ull);
+    if (t == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
-  if (t == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
 
-  /* ---- level A loads: the request record and the neighbours' gids (run-head / single tests) ---- */
-  static_assert(LP == L, "teams are exactly the L lanes of a group");
-  bool head = false, single = false;
-  uint32_t gid = 0;
+  /* ---- level A: the request record and the neighbours' gids (run-head / single-request tests) ---- */
+  const bool valid = i < n;
   int4 rq0 = make_int4(0, 0, 0, 0), rq1 = rq0;
-  if (i < n) {
+  uint32_t gprev = 0xffffffffu, gnext = 0xffffffffu;
+  if (valid) {
     ld256_stream(&reqs[i], rq0, rq1);
-    const uint32_t gprev = i > 0 ? reqs[i - 1].gid : 0xffffffffu;
-    const uint32_t gnext = i + 1 < n ? reqs[i + 1].gid : 0xffffffffu;
-    gid = (uint32_t)rq0.x;
-    head = (i == 0) || (gprev != gid);
-    single = gnext != gid;
+    if (i > 0) gprev = reqs[i - 1].gid;
+    if (i + 1 < n) gnext = reqs[i + 1].gid;
   }
+  const uint32_t gid = (uint32_t)rq0.x, rflags = (uint32_t)rq0.y, entry = (rflags >> 8) & 0xfu;
+  const uint32_t poff = (uint32_t)rq1.x, plen = (uint32_t)rq1.y;
+  const bool head = valid && (i == 0 || gprev != gid);
+  /* candidates for the in-order path: the only request of its group in this batch, no STOP */
+  const bool cand = head && gnext != gid && gid < G && entry < (uint32_t)L && !(rflags & GPX_F_STOP);
+
+  /* ---- level B (depends on gid only): group meta, my lane's acceptor + coordinator rows; the first chunk of
+   * the payload rides along ---- */
+  uint32_t meta = 0, my_aux = 0;
+  int4 my_row = make_int4(0, 0, 0, 0), my_crow = my_row, pv = my_row;
+  const uint32_t ri = sub * G + gid; /* 32-bit plane indices: checked against 2^32 at engine creation */
+  const uint8_t* const psrc = A.blob0 + poff;
+  const bool pal = ((poff | (uint32_t)(uintptr_t)A.blob0) & 15u) == 0;
+  if (cand) {
+    meta = S.grp_meta[gid];
+    my_aux = S.acc_aux[ri];
+    my_row = S.acc_row[ri];
+    my_crow = S.coord_row[ri];
+    if (plen) {
+      if (pal)
+        pv = ld_stream4(psrc);
+      else
+        pv.x = psrc[0];
+    }
+  }
+  /* a live group whose R members are exactly the L local lanes in member order */
+  bool sf = cand && ((meta & (GPX_META_LIVE | GPX_META_IDENT)) == (GPX_META_LIVE | GPX_META_IDENT)) &&
+            ((meta >> 16) & 0xffu) == (uint32_t)L;
+  /* PISM.handleProposal :818-888: who coordinates?  the entry lane's rows come from its thread */
+  const uint32_t esrc = tbase + entry;
+  const int ae_y = __shfl_sync(FULL, my_row.y, esrc), ae_z = __shfl_sync(FULL, my_row.z, esrc);
+  const int ce_x = __shfl_sync(FULL, my_crow.x, esrc), ce_y = __shfl_sync(FULL, my_crow.y, esrc);
+  const int ce_w = __shfl_sync(FULL, my_crow.w, esrc);
+  uint32_t cl = entry;
+  if (!(((unsigned)ce_w & GPX_CF_EXISTS) && bcmp(ce_x, ce_y, ae_y, ae_z) >= 0)) {
+    int fl = -1; /* forward to the coordinator of the entry lane's ballot, if it is a local lane */
+#pragma unroll
+    for (int l = 0; l < L; l++)
+      if (S.lane_node[l] == ae_z) fl = l;
+    sf = sf && fl >= 0 && fl != (int)entry;
+    cl = fl >= 0 ? (uint32_t)fl : 0u;
+  }
+  const uint32_t csrc = tbase + cl;
+  int4 crow;
+  crow.x = __shfl_sync(FULL, my_crow.x, csrc);
+  crow.y = __shfl_sync(FULL, my_crow.y, csrc);
+  crow.z = __shfl_sync(FULL, my_crow.z, csrc);
+  crow.w = __shfl_sync(FULL, my_crow.w, csrc);
+  const int af_y = __shfl_sync(FULL, my_row.y, csrc), af_z = __shfl_sync(FULL, my_row.z, csrc);
+  /* an ACTIVE coordinator whose ballot is not behind its acceptor, with no proposal outstanding; my lane must be
+   * the plain in-order case: usable, same ballot, expecting exactly this slot, nothing committed there yet */
+  const int slot = crow.z;
+  sf = sf && ((unsigned)crow.w == (GPX_CF_EXISTS | GPX_CF_ACTIVE)) && bcmp(crow.x, crow.y, af_y, af_z) >= 0 &&
+       st_usable(my_aux) && my_row.y == crow.x && my_row.z == crow.y && my_row.x == slot &&
+       !((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)slot & Wm)) & 1u) && jsub(slot, my_row.w) > 0;
+  sf = ((__ballot_sync(FULL, sf) >> tbase) & TEAM) == TEAM;
+
+  /* ---- level C (depends on the slot / the coordinator lane): window entry, nodeSlotNumbers ---- */
+  int4 e0 = make_int4(0, 0, 0, 0), e1 = e0;
+  int my_ns = 0;
+  const uint32_t wi = 2u * ((sub * S.W + ((uint32_t)slot & Wm)) * G + gid);
+  const uint32_t ni = (cl * S.Rcap + sub) * G + gid;
+  if (sf) {
+    ld256(&S.acc_win[wi], e0, e1);
+    my_ns = S.node_slots[ni];
+  }
+  { /* an accept already sitting at this slot -> general path */
+    const bool ent_live = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, my_row.w) > 0 && e0.x == slot;
+    sf = ((__ballot_sync(FULL, sf && !ent_live) >> tbase) & TEAM) == TEAM;
+  }
+  int ns[LP];
+#pragma unroll
+  for (int k = 0; k < LP; k++) ns[k] = __shfl_sync(FULL, my_ns, tbase + k);
+  const int median = median_regs<LP>(ns, (uint32_t)L); /* AcceptPacket.medianCheckpointedSlot (initCommander) */
+  /* handleAccept at my lane: ballot equal, slot next-in-line, no previous accept -> ack + log */
+  int4 row = my_row;
+  gc_step(row, median);   /* acceptAndUpdateBallot -> garbageCollectAccepted :320 */
+  const int cpi = S.cpi_per_group ? (sf ? S.grp_cpi[gid] : 1) : S.cpi_const;
+  int max_cp = row.x - 1; /* AcceptReplyPacket.maxCheckpointedSlot :1139-1143 */
+  if (!S.gc_majority_executed) {
+    int lcp = max_cp - max_cp % cpi;
+    if (lcp < 0) {
+      lcp = jsub(lcp, cpi);
+      if (lcp > 0) lcp = 2147483647 - 2147483647 % cpi;
+    }
+    max_cp = lcp;
+  }
+  /* tally (handleAcceptReplyMyBallot :597-640): replies arrive in lane order, all for my ballot; the decision is
+   * made by reply number L/2 (0-based) with the nodeSlots recorded up to and including it */
+  int nsd[LP], mine = my_ns;
+#pragma unroll
+  for (int k = 0; k < LP; k++) {
+    const int mcp_k = __shfl_sync(FULL, max_cp, tbase + k);
+    nsd[k] = ns[k];
+    if (ns[k] < mcp_k) { /* recordSlotNumber :809-825 (plain <) */
+      if (k <= L / 2) nsd[k] = mcp_k;
+      if (sub == (uint32_t)k) mine = mcp_k;
+    }
+  }
+  const int dmed = median_regs<LP>(nsd, (uint32_t)L); /* makeDecision(getMajorityCommittedSlot()) :630 */
+
   uint32_t c_lane = 0, c_team = 0, c_ckpt = 0; /* fast-path event counts, reduced once per warp at the end */
-  if (head) { /* team-uniform */
-    const uint32_t rflags = (uint32_t)rq0.y;
-    const uint32_t entry = (rflags >> 8) & 0xfu;
-    /* ---- level B loads (depend on gid only): group meta, my lane's acceptor + coordinator rows, and --
-     * speculatively -- nodeSlotNumbers of the lane my acceptor believes to coordinate ---- */
-    const bool gid_ok = gid < S.G;
-    uint32_t meta = 0, my_aux = 0;
-    int4 my_row = make_int4(0, 0, 0, 0), my_crow = my_row;
-    const uint32_t G = S.G;
-    const uint32_t ri = sub * G + gid; /* row index of my lane (32-bit: L*G < 2^32 is checked at engine creation) */
-    if (gid_ok) {
-      meta = S.grp_meta[gid];
-      my_aux = S.acc_aux[ri];
-      my_row = S.acc_row[ri];
-      my_crow = S.coord_row[ri];
-    }
-    /* the in-order fast path needs: one request for the group, a live group whose R members are exactly the
-     * L local lanes in member order, no STOP */
-    bool sf = single && gid_ok && ((meta & (GPX_META_LIVE | GPX_META_IDENT)) == (GPX_META_LIVE | GPX_META_IDENT)) &&
-              ((meta >> 16) & 0xffu) == (uint32_t)L && entry < (uint32_t)L && !(rflags & GPX_F_STOP);
-    int cl = 0;
-    int4 crow = make_int4(0, 0, 0, 0);
-    int slot = 0;
-    if (sf) {
-      /* PISM.handleProposal :818-888: who coordinates?  rows of the entry lane come from its thread */
-      const int ae_y = __shfl_sync(tmask, my_row.y, tbase + entry), ae_z = __shfl_sync(tmask, my_row.z, tbase + entry);
-      const int ce_x = __shfl_sync(tmask, my_crow.x, tbase + entry), ce_y = __shfl_sync(tmask, my_crow.y, tbase + entry);
-      const int ce_w = __shfl_sync(tmask, my_crow.w, tbase + entry);
-      cl = (int)entry;
-      if (!(((unsigned)ce_w & GPX_CF_EXISTS) && bcmp(ce_x, ce_y, ae_y, ae_z) >= 0)) {
-        int fl = -1;
-#pragma unroll
-        for (int l = 0; l < L; l++)
-          if (S.lane_node[l] == ae_z) fl = l;
-        sf = fl >= 0 && fl != (int)entry;
-        cl = sf ? fl : 0;
+  if (sf) {
+    /* ================= in-order fast path: nothing but the durable outputs touches HBM ================= */
+    const int4 q0 = make_int4((int)gid, slot, crow.x, crow.y);
+    /* my lane's two log segments are linear inside the ring (a launch never straddles the wrap) */
+    uint8_t* const seg_p = ring_ptr(S, sub, seg);
+    const unsigned frame_ref = (unsigned)(((seg + pay_rel + poff) & (S.ring_cap - 1)) >> 4);
+    /* ACCEPT log image + my lane's copy of the blob (AbstractPaxosLogger.logAndMessage) */
+    st256_stream(seg_p + 64 + (size_t)i * 32, q0,
+                 make_int4(median, (int)(GPX_F_ACCEPT | ((1u << sub) << 16)), rq0.z, rq0.w));
+    st_stream4(seg_p + 64 + (size_t)n * 32 + (size_t)i * 16, make_int4((int)poff, (int)plen, 1, crow.y));
+    if (plen) {
+      uint8_t* dst = seg_p + pay_rel + poff;
+      if (pal) {
+        st_stream4(dst, pv);
+        for (uint32_t b = 16; b < plen; b += 16) st_stream4(dst + b, ld_stream4(psrc + b));
+      } else {
+        dst[0] = (uint8_t)pv.x;
+        for (uint32_t b = 1; b < plen; b++) dst[b] = psrc[b];
       }
-      crow.x = __shfl_sync(tmask, my_crow.x, tbase + cl);
-      crow.y = __shfl_sync(tmask, my_crow.y, tbase + cl);
-      crow.z = __shfl_sync(tmask, my_crow.z, tbase + cl);
-      crow.w = __shfl_sync(tmask, my_crow.w, tbase + cl);
-      const int af_y = __shfl_sync(tmask, my_row.y, tbase + cl), af_z = __shfl_sync(tmask, my_row.z, tbase + cl);
-      /* an ACTIVE coordinator whose ballot is not behind its acceptor, with no proposal outstanding */
-      sf = sf && ((unsigned)crow.w == (GPX_CF_EXISTS | GPX_CF_ACTIVE)) && bcmp(crow.x, crow.y, af_y, af_z) >= 0;
-      slot = crow.z;
     }
-    /* ---- level C loads (depend on the slot / the coordinator lane): window entry, nodeSlotNumbers ---- */
-    int4 e0 = make_int4(0, 0, 0, 0), e1 = e0;
-    int my_ns = 0;
-    const uint32_t wi = (sub * S.W + ((uint32_t)slot & Wm)) * G + gid; /* window index of my lane at slot mod W */
-    if (sf) {
-      ld256(&S.acc_win[2u * wi], e0, e1);
-      my_ns = S.node_slots[((uint32_t)cl * S.Rcap + sub) * G + gid];
-      /* every lane must be the plain in-order case: usable, same ballot, next slot, nothing already there */
-      const bool ent_live = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, my_row.w) > 0 && e0.x == slot;
-      const bool ok = st_usable(my_aux) && my_row.y == crow.x && my_row.z == crow.y && my_row.x == slot && !ent_live &&
-                      !((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)slot & Wm)) & 1u) && jsub(slot, my_row.w) > 0;
-      sf = __ballot_sync(tmask, ok) == tmask;
+    /* commit (handleBatchedCommit :1488-1501 + extractExecuteAndCheckpoint): the accept is the decision */
+    const bool metaf = S.log_meta != 0;
+    st256_stream(seg_p + res_a + 64 + (size_t)i * 32, q0,
+                 make_int4(metaf ? -1 : dmed, (int)((GPX_F_DECISION | (metaf ? GPX_F_META : 0u)) | ((1u << sub) << 16)),
+                           rq0.z, rq0.w));
+    gc_step(row, dmed);
+    { /* EXEC record (PISM.execute hands the request to the app); shouldCheckpoint :2037-2041 */
+      const bool ckpt = (slot % cpi) == 0;
+      if (ckpt) c_ckpt++;
+      gpx_exec_rec er;
+      er.gid = gid;
+      er.slot = slot;
+      er.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
+      er.payload_off = frame_ref;
+      er.flags = (ckpt ? GPX_F_CKPT : 0u) | (sub << 12) | (1u << 16);
+      store_exec(&A.exec[(size_t)i * L + sub], er);
     }
-    if (sf) {
-      /* ================= in-order fast path: nothing but the durable outputs touches HBM ================= */
-      int ns[LP];
-#pragma unroll
-      for (int k = 0; k < LP; k++) ns[k] = __shfl_sync(tmask, my_ns, tbase + k);
-      const int median = median_regs<LP>(ns, (uint32_t)L); /* AcceptPacket.medianCheckpointedSlot (initCommander) */
+    row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
+    if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
+      if ((unsigned)e1.w & GPX_ENT_VALID)
+        st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
+              make_int4(rq0.z, rq0.w, (int)plen, (int)(1u << 16)));
+    } else
+      st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
+            make_int4(rq0.z, rq0.w, (int)plen, (int)(GPX_ENT_VALID | (1u << 16))));
+    gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot */
+    if ((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)row.x & Wm)) & 1u) { /* queued commits become executable (rare) */
+      DPValue x;
+      x.slot = slot;
+      x.bnum = crow.x;
+      x.bcoord = crow.y;
+      x.median_cp = dmed;
+      x.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
+      x.frame_ref = frame_ref;
+      x.plen = plen;
+      x.fl = (1u << 16);
+      x.valued = true;
+      uint32_t aux = my_aux;
+      eec(S, sub, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
+      if (aux != my_aux) S.acc_aux[ri] = aux;
+    }
+    S.acc_row[ri] = row;
+    if (mine != my_ns) S.node_slots[ni] = mine; /* nodeSlotNumbers[cl][sub] */
+    c_lane = 1;
+    if (sub == 0) {
       constexpr uint32_t lane_mask = (1u << L) - 1u;
-      const int4 q0 = make_int4((int)gid, slot, crow.x, crow.y);
-      /* handleAccept at my lane: ballot equal, slot next-in-line, no previous accept -> ack + log */
-      int4 row = my_row;
-      gc_step(row, median);   /* acceptAndUpdateBallot -> garbageCollectAccepted :320 */
-      int max_cp = row.x - 1; /* AcceptReplyPacket.maxCheckpointedSlot :1139-1143 */
-      if (!S.gc_majority_executed) {
-        const int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
-        int lcp = max_cp - max_cp % cpi;
-        if (lcp < 0) {
-          lcp = jsub(lcp, cpi);
-          if (lcp > 0) lcp = 2147483647 - 2147483647 % cpi;
-        }
-        max_cp = lcp;
-      }
-      /* tally (handleAcceptReplyMyBallot :597-640): replies arrive in lane order, all for my ballot; the decision
-       * is made by reply number L/2 (0-based) with the nodeSlots recorded up to and including it */
-      int nsd[LP];
-#pragma unroll
-      for (int k = 0; k < LP; k++) {
-        const int mcp_k = __shfl_sync(tmask, max_cp, tbase + k);
-        nsd[k] = ns[k];
-        if (ns[k] < mcp_k) { /* recordSlotNumber :809-825 (plain <) */
-          ns[k] = mcp_k;
-          if (k <= L / 2) nsd[k] = mcp_k;
-        }
-      }
-      const int dmed = median_regs<LP>(nsd, (uint32_t)L); /* makeDecision(getMajorityCommittedSlot()) :630 */
-      /* my lane's two log segments are linear inside the ring (a launch never straddles the wrap) */
-      uint8_t* const seg_p = ring_ptr(S, sub, seg);
-      const uint32_t poff = (uint32_t)rq1.x, plen = (uint32_t)rq1.y;
-      const unsigned frame_ref = (unsigned)(((seg + pay_rel + poff) & (S.ring_cap - 1)) >> 4);
-      /* ACCEPT log image + my lane's copy of the blob (AbstractPaxosLogger.logAndMessage) */
-      st256_stream(seg_p + 64 + (size_t)i * 32, q0,
-                   make_int4(median, (int)(GPX_F_ACCEPT | ((1u << sub) << 16)), rq0.z, rq0.w));
-      st_stream4(seg_p + 64 + (size_t)n * 32 + (size_t)i * 16, make_int4((int)poff, (int)plen, 1, crow.y));
-      {
-        const uint8_t* src = A.blob0 + poff;
-        uint8_t* dst = seg_p + pay_rel + poff;
-        if (((poff | (uint32_t)(uintptr_t)src) & 15u) == 0) {
-          for (uint32_t b = 0; b < plen; b += 16) st_stream4(dst + b, ld_stream4(src + b));
-        } else {
-          for (uint32_t b = 0; b < plen; b++) dst[b] = src[b];
-        }
-      }
-      /* commit (handleBatchedCommit :1488-1501 + extractExecuteAndCheckpoint): the accept is the decision */
-      const bool metaf = S.log_meta != 0;
-      st256_stream(seg_p + res_a + 64 + (size_t)i * 32, q0,
-                   make_int4(metaf ? -1 : dmed, (int)((GPX_F_DECISION | (metaf ? GPX_F_META : 0u)) | ((1u << sub) << 16)),
-                             rq0.z, rq0.w));
-      gc_step(row, dmed);
-      /* EXEC record (PISM.execute hands the request to the app): checkpoint-due flag = slot % CPI == 0 */
-      {
-        const int cpi = S.cpi_per_group ? S.grp_cpi[gid] : S.cpi_const;
-        const bool ckpt = (slot % cpi) == 0;
-        if (ckpt) c_ckpt++;
-        gpx_exec_rec er;
-        er.gid = gid;
-        er.slot = slot;
-        er.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
-        er.payload_off = frame_ref;
-        er.flags = (ckpt ? GPX_F_CKPT : 0u) | (sub << 12) | (1u << 16);
-        store_exec(&A.exec[(size_t)i * L + sub], er);
-      }
-      row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
-      if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
-        if ((unsigned)e1.w & GPX_ENT_VALID)
-          st256(&S.acc_win[2u * wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
-                make_int4(rq0.z, rq0.w, (int)plen, (int)(1u << 16)));
-      } else
-        st256(&S.acc_win[2u * wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
-              make_int4(rq0.z, rq0.w, (int)plen, (int)(GPX_ENT_VALID | (1u << 16))));
-      gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot */
-      if ((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)row.x & Wm)) & 1u) { /* queued commits become executable (rare) */
-        DPValue x;
-        x.slot = slot;
-        x.bnum = crow.x;
-        x.bcoord = crow.y;
-        x.median_cp = dmed;
-        x.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
-        x.frame_ref = frame_ref;
-        x.plen = plen;
-        x.fl = (1u << 16);
-        x.valued = true;
-        uint32_t aux = my_aux;
-        eec(S, sub, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
-        if (aux != my_aux) S.acc_aux[ri] = aux;
-      }
-      S.acc_row[ri] = row;
-      { /* nodeSlotNumbers[cl][sub] */
-        int mine = ns[0];
-#pragma unroll
-        for (int k = 1; k < LP; k++)
-          if (sub == (uint32_t)k) mine = ns[k];
-        if (mine != my_ns) S.node_slots[((uint32_t)cl * S.Rcap + sub) * G + gid] = mine;
-      }
-      c_lane++;
-      if (sub == 0) {
-        RA.P.status[i] = slot;
-        crow.z = (int)((unsigned)crow.z + 1u); /* PCS.propose: nextProposalSlotNumber++ (proposal decided at once) */
-        S.coord_row[(uint32_t)cl * G + gid] = crow;
-        st256_stream(&A.decisions[i], q0, make_int4(dmed, (int)(GPX_F_DECISION | (lane_mask << 16)), rq0.z, rq0.w));
-        A.out_mask[i] = 0;
-        c_team++;
-      }
-    } else {
-      if (SPLIT) { /* hand the run to k_round_slow: the fast kernel stays small (registers, occupancy) */
-        if (sub == 0) RA.todo[atomicAdd(RA.n_todo, 1u)] = i;
-      } else
-        round_general<L, LP>(S, RA, i, sub, tmask, tbase, gid, seg, dseg, payb, s_ctr);
+      RA.P.status[i] = slot;
+      crow.z = (int)((unsigned)crow.z + 1u); /* PCS.propose: nextProposalSlotNumber++ (proposal decided at once) */
+      S.coord_row[cl * G + gid] = crow;
+      st256_stream(&A.decisions[i], q0, make_int4(dmed, (int)(GPX_F_DECISION | (lane_mask << 16)), rq0.z, rq0.w));
+      A.out_mask[i] = 0;
+      c_team = 1;
     }
+  } else if (head && sub == 0) {
+    RA.todo[atomicAdd(RA.n_todo, 1u)] = i; /* the run goes to k_round_slow */
   }
   /* fast-path events, counted in registers: one shared-memory update per warp */
   {
-    const uint32_t nl = __reduce_add_sync(0xffffffffu, c_lane), nt = __reduce_add_sync(0xffffffffu, c_team);
-    const uint32_t nc = __reduce_add_sync(0xffffffffu, c_ckpt);
+    const uint32_t nl = __reduce_add_sync(FULL, c_lane), nt = __reduce_add_sync(FULL, c_team);
+    const uint32_t nc = __reduce_add_sync(FULL, c_ckpt);
     if (lane_id == 0 && (nl | nt)) {
       atomicAdd(&s_ctr[C_ACCEPTS_HANDLED], nl);
       atomicAdd(&s_ctr[C_ACCEPTS_ACKED], nl);
@@ -565,15 +569,6 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
     }
   }
   flush_counters(S, s_ctr);
-  __shared__ unsigned int s_last;
-  __threadfence();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[5], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x < (uint32_t)L) {
-    S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
-    S.seg_seq[threadIdx.x] += 2ull;
-  }
-  if (s_last && threadIdx.x == 0) S.tickets[5] = 0;
 }
 
 /* The runs the fast kernel did not take (several requests of a group, STOPs, NACKs, coordinator changes, ...).
@@ -602,8 +597,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
     const unsigned long long res_a = (pay_rel + pay_bytes + 31ull) & ~31ull;
     const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
     const uint32_t myl = sub < (uint32_t)L ? sub : 0u;
-    /* the fast kernel already advanced the ring heads past this round's two segments */
-    const unsigned long long seg = S.ring_head[myl] - (res_a + res_d);
+    const unsigned long long seg = seg_base(S, myl, res_a + res_d); /* same segments as the fast kernel */
     const unsigned long long payb = seg + pay_rel, dseg = seg + res_a;
     for (uint32_t k = team; k < ntodo; k += nteams) {
       const uint32_t i = RA.todo[k];
@@ -613,4 +607,18 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   flush_counters(S, s_ctr);
+  /* the last block to finish publishes the ring heads of the round (every block has read them by then) */
+  __shared__ unsigned int s_last;
+  __threadfence();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[5], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x < (uint32_t)L) {
+    const uint32_t n = RA.P.n;
+    const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
+    const unsigned long long res_a = (pay_rel + RA.A.blob0_bytes + RA.blob1_res + 31ull) & ~31ull;
+    const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
+    S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
+    S.seg_seq[threadIdx.x] += 2ull;
+  }
+  if (s_last && threadIdx.x == 0) S.tickets[5] = 0;
 }
