@@ -105,7 +105,7 @@ def make_descs(abi, names, R):
 
 def make_batch(abi, G, P, seed):
     rng = np.random.default_rng(seed)
-    stride = (P + 15) // 16 * 16
+    stride = P  # requests packed back to back, as the RequestBatcher concatenates them
     reqs = np.zeros(G, dtype=abi.request_dtype)
     reqs["gid"] = np.arange(G, dtype=np.uint32)
     reqs["flags"] = 0
@@ -130,9 +130,8 @@ def engine_config(lib, G, R, P, device):
     cfg.window = 8
     cfg.max_group_size = R
     cfg.max_batch_recs = G
-    stride = (P + 15) // 16 * 16
-    cfg.max_batch_payload = G * stride
-    per_round = 64 + 48 * G + G * stride + 64 + 32 * G
+    cfg.max_batch_payload = G * P + 16
+    per_round = 64 + 48 * G + G * P + 64 + 32 * G + 64
     ring = 1 << 26
     while ring < 4 * per_round:
         ring <<= 1
@@ -446,9 +445,14 @@ def main():
     }
     roofline_accept["frac"] = roofline_accept["achieved"] / peak
 
-    # ---- e2e: public C-ABI call with host (pinned) buffers ---------------------------------
+    # ---- e2e: public C-ABI calls with host (pinned) buffers -------------------------------
+    # Headline: the pipelined form gpx_round_submit / gpx_round_wait with compact EXEC summaries -- every step
+    # copies its request batch host->device and its result (one 8-byte summary per request + control block)
+    # device->host inside the timed region; up to PIPE_DEPTH steps overlap.  The synchronous gpx_round with
+    # full EXEC records (R x 24 B per decision) is reported beside it.
     e2e = None
     if not args.skip_e2e:
+        from gigapaxos_b200.abi import RoundIO, exec_sum_dtype, PIPE_DEPTH, ROUND_COMPACT
         fn = lib.fn("round")
         h_reqs = [torch.from_numpy(b[0].view(np.uint8).copy()).pin_memory() for b in host_batches]
         h_pay = [torch.from_numpy(b[1].copy()).pin_memory() for b in host_batches]
@@ -464,6 +468,13 @@ def main():
             if rc != 0:
                 raise RuntimeError(lib.last_error())
 
+        def allmax(dt):
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+            return dt
+
         for w in range(3):
             host_round(w % NB)
         K3 = min(K, 30)
@@ -472,19 +483,67 @@ def main():
         for k in range(K3):
             host_round(k % NB)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt_sync = allmax(time.perf_counter() - t0)
         assert ns.value == G * R
         ex = h_exec.numpy().view(abi.exec_dtype)
         assert int((ex["flags"] & abi.F_VOID).sum()) == 0, "e2e round left VOID exec records"
-        e2e = {"value": world * G * K3 / dt, "unit": "decisions/s",
+
+        # pipelined, compact summaries
+        submit, wait = lib.fn("round_submit"), lib.fn("round_wait")
+        h_sum = [torch.zeros(G * 8, dtype=torch.uint8).pin_memory() for _ in range(PIPE_DEPTH)]
+        h_xtra = [torch.zeros(4096 * 24, dtype=torch.uint8).pin_memory() for _ in range(PIPE_DEPTH)]
+        ios = []
+        for d in range(PIPE_DEPTH * NB):
+            b, q = d % NB, d % PIPE_DEPTH
+            ios.append(RoundIO(G, ROUND_COMPACT, h_reqs[b].data_ptr(), h_pay[b].data_ptr(), h_pay[b].numel(), None, None,
+                               h_sum[q].data_ptr(), h_xtra[q].data_ptr(), 4096))
+        tk = C.c_uint64(0)
+        inflight = []
+
+        def pipe_step(k):
+            if len(inflight) == PIPE_DEPTH:
+                pipe_wait()
+            io = ios[k % (PIPE_DEPTH * NB)]
+            rc = submit(eng.handle, C.byref(io), C.byref(tk))
+            if rc != 0:
+                raise RuntimeError(lib.last_error())
+            inflight.append(tk.value)
+
+        def pipe_wait():
+            rc = wait(eng.handle, C.c_uint64(inflight.pop(0)), C.byref(ns), C.byref(nx))
+            if rc != 0:
+                raise RuntimeError(lib.last_error())
+            assert nx.value == 0, "bench workload must stay on the in-order path"
+
+        for w in range(2 * PIPE_DEPTH):
+            pipe_step(w)
+        while inflight:
+            pipe_wait()
+        K4 = max(K, 50)
+        barrier()
+        c0e = eng.counters()
+        t0 = time.perf_counter()
+        for k in range(K4):
+            pipe_step(k)
+        while inflight:
+            pipe_wait()
+        dt_pipe = allmax(time.perf_counter() - t0)
+        c1e = eng.counters()
+        assert c1e["decisions_made"] - c0e["decisions_made"] == G * K4
+        assert c1e["executed"] - c0e["executed"] == G * K4 * R
+        for q in range(PIPE_DEPTH):
+            sm = h_sum[q].numpy().view(exec_sum_dtype)
+            assert np.all(sm["lane_mask"] == (1 << R) - 1) and np.all(sm["slot"] > 0), "summaries incomplete"
+        e2e = {"value": world * G * K4 / dt_pipe, "unit": "decisions/s",
                "h2d_bytes_per_step": int(G * 32 + h_pay[0].numel()),
-               "d2h_bytes_per_step": int(G * 4 + 32 + G * R * 24), "steps": K3,
-               "ms_per_step": 1e3 * dt / K3,
-               "api": "gpx_round (include/gpx.h): pinned host request/payload buffers in, status + EXEC records out"}
+               "d2h_bytes_per_step": int(G * 8 + 32), "steps": K4, "ms_per_step": 1e3 * dt_pipe / K4,
+               "api": "gpx_round_submit / gpx_round_wait (include/gpx.h), GPX_ROUND_COMPACT: pinned host request + "
+                      "payload buffers in, one 8-byte EXEC summary per request out, up to %d rounds in flight; "
+                      "wall clock around submit..wait of all steps" % PIPE_DEPTH,
+               "sync_full": {"value": world * G * K3 / dt_sync, "unit": "decisions/s", "steps": K3,
+                             "ms_per_step": 1e3 * dt_sync / K3, "h2d_bytes_per_step": int(G * 32 + h_pay[0].numel()),
+                             "d2h_bytes_per_step": int(G * 4 + 32 + G * R * 24),
+                             "api": "gpx_round: synchronous call, status + R full EXEC records per decision out"}}
 
     # ---- cpu baseline (rank 0, N=1 only) --------------------------------------------------
     cpu = None
@@ -501,7 +560,7 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": config, "roofline": roofline,
             "roofline_accept": roofline_accept,
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 1 * K,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 2 * K,  # k_round + k_round_slow per step
             "p50_decide_latency_ms": float(np.median(step_ms)),
             "requests_per_sec": value, "wall_s_timed_region": t_wall,
         }

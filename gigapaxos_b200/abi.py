@@ -44,6 +44,9 @@ reply_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("bnum", "<i4"), ("bcoo
                         ("who", "<u4"), ("req_id", "<i8")])
 exec_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("req_id", "<i8"), ("payload_off", "<u4"), ("flags", "<u4")])
 batch_ent_dtype = np.dtype([("req_id", "<i8"), ("len", "<u4"), ("flags", "<u4")])
+exec_sum_dtype = np.dtype([("slot", "<i4"), ("lane_mask", "u1"), ("flags", "u1"), ("nreq", "<u2")])
+ROUND_COMPACT = 1
+PIPE_DEPTH = 4
 seg_hdr_dtype = np.dtype([("magic", "<u4"), ("type", "<u2"), ("lane", "<u2"), ("n_slots", "<u4"), ("n_valid", "<u4"),
                           ("payload_bytes", "<u8"), ("seq", "<u8"), ("ring_off", "<u8"), ("rec_bytes", "<u4"),
                           ("reserved", "<u4", (5,))])
@@ -93,6 +96,12 @@ class KernelTimes(C.Structure):
 class DevRoundBufs(C.Structure):
     _fields_ = [("reqs", C.c_void_p), ("payload", C.c_void_p), ("payload_bytes", C.c_uint64), ("n", C.c_uint32),
                 ("status", C.c_void_p), ("exec", C.c_void_p)]
+
+
+class RoundIO(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("flags", C.c_uint32), ("reqs", C.c_void_p), ("payload", C.c_void_p),
+                ("payload_bytes", C.c_uint64), ("status", C.c_void_p), ("exec", C.c_void_p), ("sum", C.c_void_p),
+                ("extra", C.c_void_p), ("extra_cap", C.c_uint32)]
 
 
 class GpxError(RuntimeError):
@@ -171,6 +180,7 @@ class Engine:
         self.cfg = cfg
         self.n_lanes = int(cfg.n_lanes)
         self._h = C.c_void_p()
+        self._inflight = {}
         library.check(library.fn("engine_create")(C.byref(cfg), C.byref(self._h)))
 
     def close(self):
@@ -298,6 +308,43 @@ class Engine:
                                         _ptr(status), _ptr(ex), C.byref(ns), _ptr(extra), C.c_uint32(extra_cap),
                                         C.byref(nx)))
         return status[:n].copy(), ex[: ns.value].copy(), extra[: min(nx.value, extra_cap)].copy()
+
+    # ---- pipelined rounds (gpx_round_submit / gpx_round_wait) ---------------------------
+    def round_submit(self, reqs: np.ndarray, payload: np.ndarray, compact: bool = False, extra_cap: int = 4096,
+                     bufs: Optional[dict] = None) -> int:
+        """Enqueue one round; returns its ticket.  `bufs` may carry caller-owned (e.g. page-locked) output arrays
+        `status`, `exec`, `sum`, `extra`; otherwise they are allocated here and returned by round_wait."""
+        assert reqs.dtype == request_dtype and reqs.flags.c_contiguous and payload.dtype == np.uint8
+        n = len(reqs)
+        b = dict(bufs or {})
+        if compact:
+            b.setdefault("sum", np.zeros(max(n, 1), dtype=exec_sum_dtype))
+        else:
+            b.setdefault("status", np.zeros(max(n, 1), dtype=np.int32))
+            b.setdefault("exec", np.zeros(max(n * self.n_lanes, 1), dtype=exec_dtype))
+        b.setdefault("extra", np.zeros(max(extra_cap, 1), dtype=exec_dtype))
+        io = RoundIO(n, ROUND_COMPACT if compact else 0, reqs.ctypes.data, payload.ctypes.data if payload.size else None,
+                     payload.size, b["status"].ctypes.data if "status" in b else None,
+                     b["exec"].ctypes.data if "exec" in b else None, b["sum"].ctypes.data if "sum" in b else None,
+                     b["extra"].ctypes.data, len(b["extra"]))
+        t = C.c_uint64(0)
+        self.L.check(self.L.fn("round_submit")(self._h, C.byref(io), C.byref(t)))
+        b["n"], b["compact"], b["reqs"], b["payload"] = n, compact, reqs, payload  # keep the inputs alive
+        self._inflight[t.value] = b
+        return t.value
+
+    def round_wait(self, ticket: int) -> dict:
+        """Block until round `ticket` is done; returns {status, exec | sum, extra (trimmed), n_extra}."""
+        ns, nx = C.c_uint32(0), C.c_uint32(0)
+        self.L.check(self.L.fn("round_wait")(self._h, C.c_uint64(ticket), C.byref(ns), C.byref(nx)))
+        b = self._inflight.pop(ticket)
+        n = b["n"]
+        out = {"n_extra": nx.value, "extra": b["extra"][: min(nx.value, len(b["extra"]))]}
+        if b["compact"]:
+            out["sum"] = b["sum"][:n]
+        else:
+            out["status"], out["exec"] = b["status"][:n], b["exec"][: ns.value]
+        return out
 
     def digest_requests(self, reqs: np.ndarray, payload: np.ndarray) -> np.ndarray:
         """MD5 of every requestValue (RequestPacket.getDigest), shape [n, 16]."""

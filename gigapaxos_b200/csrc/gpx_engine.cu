@@ -64,6 +64,25 @@ struct gpx_engine {
   RoundCtl* h_ctl = nullptr; /* pinned */
   void* d_misc = nullptr;    /* group-management staging */
   size_t misc_bytes = 0;
+  /* pipelined rounds (gpx_round_submit / gpx_round_wait): per-slot staging, three streams */
+  struct PipeSlot {
+    gpx_request_rec* d_reqs = nullptr;
+    uint8_t* d_payload = nullptr;
+    int32_t* d_status = nullptr;
+    gpx_exec_rec* d_exec = nullptr;
+    gpx_exec_sum* d_sum = nullptr;
+    gpx_exec_rec* d_extra = nullptr;
+    RoundCtl* d_ctl = nullptr;
+    RoundCtl* h_ctl = nullptr; /* pinned */
+    cudaEvent_t ev_h2d = nullptr, ev_k = nullptr, ev_d2h = nullptr;
+    bool busy = false;
+    uint64_t ticket = 0;
+    gpx_round_io io;
+  };
+  PipeSlot pipe[GPX_PIPE_DEPTH];
+  bool pipe_ready = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  uint64_t next_ticket = 0, next_wait = 0;
   /* timing */
   int n_sms = 148;
   bool timing = false;
@@ -275,6 +294,14 @@ void gpx_engine_destroy(gpx_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_misc) cudaFree(e->d_misc);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
+  for (auto& ps : e->pipe) {
+    if (ps.h_ctl) cudaFreeHost(ps.h_ctl);
+    if (ps.ev_h2d) cudaEventDestroy(ps.ev_h2d);
+    if (ps.ev_k) cudaEventDestroy(ps.ev_k);
+    if (ps.ev_d2h) cudaEventDestroy(ps.ev_d2h);
+  }
+  if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
   if (e->stream) {
     cudaStreamDestroy(e->stream);
     for (int i = 0; i < 5; i++) cudaEventDestroy(e->ev[i]);
@@ -552,7 +579,14 @@ static void launch_round_t(uint32_t grid, uint32_t slow_grid, cudaStream_t st, c
 }
 }
 static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload, uint64_t pal,
-                        uint32_t n, int32_t* d_status, gpx_exec_rec* d_exec, cudaStream_t st) {
+                        uint32_t n, int32_t* d_status, gpx_exec_rec* d_exec, cudaStream_t st,
+                        RoundCtl* d_ctl = nullptr, gpx_exec_rec* d_extra = nullptr, uint32_t extra_cap = 0,
+                        gpx_exec_sum* d_sum = nullptr) {
+  if (!d_ctl) d_ctl = e->d_ctl;
+  if (!d_extra) {
+    d_extra = e->d_extra;
+    extra_cap = e->extra_cap;
+  }
   RoundArgs RA;
   memset(&RA, 0, sizeof RA);
   RA.P.reqs = d_reqs;
@@ -562,7 +596,8 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.P.status = d_status;
   RA.P.copy_tab = e->d_copy_tab;
   RA.P.copy_dst = e->d_copy_dst;
-  RA.P.ctl = e->d_ctl;
+  RA.P.ctl = d_ctl;
+  RA.sum = d_sum;
   RA.A.n_max = n;
   RA.A.blob0 = d_payload;
   RA.A.blob0_bytes = pal;
@@ -571,12 +606,12 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.A.decisions = e->d_decisions;
   RA.A.out_mask = e->d_out_mask;
   RA.A.exec = d_exec;
-  RA.A.extra = e->d_extra;
-  RA.A.extra_cap = e->extra_cap;
-  RA.A.n_extra = &e->d_ctl->n_extra;
+  RA.A.extra = d_extra;
+  RA.A.extra_cap = extra_cap;
+  RA.A.n_extra = &d_ctl->n_extra;
   RA.blob1w = e->d_blob1;
   RA.todo = e->d_copy_tab; /* scratch reused: k_round does not build blobs through copy_tab */
-  RA.n_todo = &e->d_ctl->n_todo;
+  RA.n_todo = &d_ctl->n_todo;
   RA.blob1_res = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
   RA.A.blob1_bytes = RA.blob1_res;
   const uint32_t L = e->cfg.n_lanes;
@@ -909,6 +944,100 @@ int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* st
   if (rc) return rc;
   return round_on_stream(e, false, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
                          stream ? (cudaStream_t)stream : e->stream);
+}
+
+/* ---- pipelined rounds ---------------------------------------------------------------- */
+static int pipe_init(gpx_engine* e) {
+  if (e->pipe_ready) return GPX_OK;
+  const size_t N = e->cfg.max_batch_recs, L = e->cfg.n_lanes;
+  const uint64_t P = (e->cfg.max_batch_payload + 15) & ~15ull;
+  int rc;
+  for (auto& ps : e->pipe) {
+    if ((rc = e->dalloc(&ps.d_reqs, N)) || (rc = e->dalloc(&ps.d_payload, (size_t)P)) ||
+        (rc = e->dalloc(&ps.d_status, N)) || (rc = e->dalloc(&ps.d_exec, N * L)) || (rc = e->dalloc(&ps.d_sum, N)) ||
+        (rc = e->dalloc(&ps.d_extra, N * (L + 1))) || /* compact mode: the general path reports here */ (rc = e->dalloc(&ps.d_ctl, (size_t)1)))
+      return rc;
+    if (cudaHostAlloc((void**)&ps.h_ctl, sizeof(RoundCtl), cudaHostAllocDefault) != cudaSuccess)
+      return fail(GPX_ENOMEM, "cudaHostAlloc");
+    CK(cudaEventCreateWithFlags(&ps.ev_h2d, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ps.ev_k, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ps.ev_d2h, cudaEventDisableTiming));
+  }
+  CK(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+  e->pipe_ready = true;
+  return GPX_OK;
+}
+
+int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket) {
+  if (!e || !io || !ticket) return fail(GPX_EINVAL, "null argument");
+  const uint32_t n = io->n;
+  const bool compact = (io->flags & GPX_ROUND_COMPACT) != 0;
+  if (io->flags & ~GPX_ROUND_COMPACT) return fail(GPX_EINVAL, "unknown round flags");
+  if (n && (!io->reqs || (!io->payload && io->payload_bytes))) return fail(GPX_EINVAL, "null argument");
+  if (n && (compact ? !io->sum : (!io->status || !io->exec))) return fail(GPX_EINVAL, "null output buffer");
+  int rc = check_batch(e, n, io->payload_bytes);
+  if (rc) return rc;
+  const uint64_t pal = (io->payload_bytes + 15) & ~15ull;
+  const uint64_t b1 = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
+  rc = ring_fits(e, 192ull + 80ull * n + pal + b1);
+  if (rc) return rc;
+  rc = pipe_init(e);
+  if (rc) return rc;
+  gpx_engine::PipeSlot& ps = e->pipe[e->next_ticket % GPX_PIPE_DEPTH];
+  if (ps.busy) return fail(GPX_ERANGE, "GPX_PIPE_DEPTH rounds in flight: call gpx_round_wait first");
+  ps.busy = true;
+  ps.ticket = e->next_ticket;
+  ps.io = *io;
+  *ticket = e->next_ticket++;
+  if (n == 0) return GPX_OK;
+  const uint32_t L = e->cfg.n_lanes;
+  /* stream 1: inputs.  (the slot's previous round was waited for, so its buffers are free) */
+  CK(cudaMemcpyAsync(ps.d_reqs, io->reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, e->s_h2d));
+  if (io->payload_bytes)
+    CK(cudaMemcpyAsync(ps.d_payload, io->payload, io->payload_bytes, cudaMemcpyHostToDevice, e->s_h2d));
+  CK(cudaEventRecord(ps.ev_h2d, e->s_h2d));
+  /* stream 2: the round (serialised with every other engine call on the engine's stream) */
+  CK(cudaStreamWaitEvent(e->stream, ps.ev_h2d, 0));
+  CK(cudaMemsetAsync(ps.d_ctl, 0, sizeof(RoundCtl), e->stream));
+  rc = launch_round(e, ps.d_reqs, ps.d_payload, pal, n, ps.d_status, ps.d_exec, e->stream, ps.d_ctl, ps.d_extra,
+                    (uint32_t)std::min<uint64_t>((uint64_t)e->cfg.max_batch_recs * (L + 1), 0xffffffffull),
+                    compact ? ps.d_sum : nullptr);
+  if (rc) return rc;
+  CK(cudaEventRecord(ps.ev_k, e->stream));
+  /* stream 3: results */
+  CK(cudaStreamWaitEvent(e->s_d2h, ps.ev_k, 0));
+  CK(cudaMemcpyAsync(ps.h_ctl, ps.d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->s_d2h));
+  if (compact) {
+    CK(cudaMemcpyAsync(io->sum, ps.d_sum, n * sizeof(gpx_exec_sum), cudaMemcpyDeviceToHost, e->s_d2h));
+  } else {
+    CK(cudaMemcpyAsync(io->status, ps.d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+    CK(cudaMemcpyAsync(io->exec, ps.d_exec, (size_t)n * L * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, e->s_d2h));
+  }
+  CK(cudaEventRecord(ps.ev_d2h, e->s_d2h));
+  return GPX_OK;
+}
+
+int gpx_round_wait(gpx_engine* e, uint64_t ticket, uint32_t* n_exec_slots, uint32_t* n_extra) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n_exec_slots) *n_exec_slots = 0;
+  if (n_extra) *n_extra = 0;
+  if (ticket != e->next_wait || ticket >= e->next_ticket) return fail(GPX_EINVAL, "rounds are waited for in submission order");
+  gpx_engine::PipeSlot& ps = e->pipe[ticket % GPX_PIPE_DEPTH];
+  e->next_wait++;
+  ps.busy = false;
+  if (ps.io.n == 0) return GPX_OK;
+  CK(cudaEventSynchronize(ps.ev_d2h));
+  const uint32_t nx = ps.h_ctl->n_extra;
+  const uint32_t cp = (uint32_t)std::min<uint64_t>(std::min(nx, ps.io.extra_cap),
+                                                  (uint64_t)e->cfg.max_batch_recs * (e->cfg.n_lanes + 1));
+  if (cp && ps.io.extra) { /* rare: executions beyond the one per (request, lane) */
+    CK(cudaMemcpyAsync(ps.io.extra, ps.d_extra, cp * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, e->s_d2h));
+    CK(cudaStreamSynchronize(e->s_d2h));
+  }
+  if (n_exec_slots) *n_exec_slots = (ps.io.flags & GPX_ROUND_COMPACT) ? 0 : ps.io.n * e->cfg.n_lanes;
+  if (n_extra) *n_extra = nx;
+  return GPX_OK;
 }
 
 /* RequestPacket.getDigest :1414-1430 for a batch of requests (the digest column of DIGEST_REQUESTS mode) */

@@ -30,9 +30,16 @@ struct RoundArgs {
   AcceptArgs A;   /* blob0/blob1, replies, decisions, out_mask, exec, extra ... (recs/n_ptr unused) */
   uint8_t* blob1w; /* writable alias of A.blob1 (constructed blobs of batched slots) */
   unsigned long long blob1_res; /* payload-area bytes reserved for constructed blobs */
-  uint32_t* todo;               /* split mode: request indices of the runs left to k_round_slow */
+  uint32_t* todo;               /* request indices of the runs left to k_round_slow */
   uint32_t* n_todo;
+  gpx_exec_sum* sum;            /* compact output mode (GPX_ROUND_COMPACT): one summary per request index instead of
+                                 * n_lanes EXEC rows; everything that is not the plain in-order case goes to the
+                                 * extra queue.  null = full EXEC rows */
 };
+
+__device__ __forceinline__ void store_sum(gpx_exec_sum* dst, int slot, uint32_t lane_mask, uint32_t flags, uint32_t nreq) {
+  *reinterpret_cast<int2*>(dst) = make_int2(slot, (int)(lane_mask | (flags << 8) | (nreq << 16)));
+}
 
 #ifndef GPX_ROUND_MINB
 #define GPX_ROUND_MINB 5 /* the fast kernel fits 48 registers without spills: 5 CTAs x 256 threads per SM */
@@ -170,6 +177,7 @@ __device__ __forceinline__ void void_outputs(const DevState& S, const RoundArgs&
   if (sub == 0) {
     st256_stream(&RA.A.decisions[j], make_int4((int)gid, 0, 0, 0), make_int4(0, (int)GPX_F_VOID, 0, 0));
     RA.A.out_mask[j] = 0;
+    if (RA.sum) store_sum(&RA.sum[j], RA.P.status[j], 0, 0, 0);
   }
 }
 
@@ -318,6 +326,16 @@ __device__ __forceinline__ void round_general(const DevState& S, const RoundArgs
     }
     if (sub < (uint32_t)L)
       commit_team_lane<L>(S, A, sub, gid, slot, g.live, decided_i != 0, d, q0, q1, q2, st, q, dseg, s_ctr);
+    if (RA.sum) { /* compact mode: the general path reports through the extra queue */
+      if (sub < (uint32_t)L) {
+        const gpx_exec_rec er = A.exec[(size_t)q * L + sub];
+        if (!(er.flags & GPX_F_VOID) && A.n_extra) {
+          const uint32_t k = atomicAdd(A.n_extra, 1u);
+          if (k < A.extra_cap) store_exec(A.extra + k, er);
+        }
+      }
+      if (sub == 0) store_sum(&RA.sum[q], stq, 0, 0, 0);
+    }
     __syncwarp(tmask); /* the next ACCEPT of the run sees this one's coordinator/acceptor writes */
   }
 }
@@ -510,7 +528,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
       er.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
       er.payload_off = frame_ref;
       er.flags = (ckpt ? GPX_F_CKPT : 0u) | (sub << 12) | (1u << 16);
-      store_exec(&A.exec[(size_t)i * L + sub], er);
+      if (!RA.sum) store_exec(&A.exec[(size_t)i * L + sub], er);
     }
     row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
     if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
@@ -541,7 +559,10 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
     c_lane = 1;
     if (sub == 0) {
       constexpr uint32_t lane_mask = (1u << L) - 1u;
-      RA.P.status[i] = slot;
+      if (RA.sum) /* every lane executed request i at `slot`, in order */
+        store_sum(&RA.sum[i], slot, lane_mask, (slot % cpi) == 0 ? GPX_F_CKPT : 0u, 1u);
+      else
+        RA.P.status[i] = slot;
       crow.z = (int)((unsigned)crow.z + 1u); /* PCS.propose: nextProposalSlotNumber++ (proposal decided at once) */
       S.coord_row[cl * G + gid] = crow;
       st256_stream(&A.decisions[i], q0, make_int4(dmed, (int)(GPX_F_DECISION | (lane_mask << 16)), rq0.z, rq0.w));

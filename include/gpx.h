@@ -357,6 +357,48 @@ int gpx_round_phases(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, con
                      uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
                      gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
 
+/* Pipelined form of gpx_round.  The reference's hot path is a pipeline of threads (RequestBatcher ->
+ * PISM -> PaxosPacketBatcher / AbstractPaxosLogger.BatchedLogger -> Messenger): a batch is being collected
+ * while the previous one is logged and the one before is executed.  gpx_round_submit enqueues the
+ * host->device copy of a batch, the round kernels and the device->host copy of its results on three
+ * streams and returns at once; up to GPX_PIPE_DEPTH rounds may be in flight, rounds execute in submission
+ * order.  All host buffers of the io block must stay valid (and should be page-locked for the copies to
+ * overlap) until gpx_round_wait(ticket) returns.
+ *
+ * Output modes:
+ *   full (flags = 0)       status[n], exec[n * n_lanes] as gpx_round.
+ *   GPX_ROUND_COMPACT      sum[n]: one 8-byte summary per REQUEST index.  lane_mask != 0: every lane in the
+ *                          mask executed exactly this request at `slot`, as its next in-order execution
+ *                          (flags: GPX_F_CKPT if PISM.shouldCheckpoint :2037 holds) -- the host runs
+ *                          Replicable.execute from its own copy of the request.  lane_mask == 0: `slot` is
+ *                          the request's status (slot number or GPX_RS_* code) and every execution it caused
+ *                          is a full record in the extra queue.  EXEC records of one call are applied per
+ *                          (lane, group) in slot order. */
+#define GPX_PIPE_DEPTH 4
+#define GPX_ROUND_COMPACT 1u
+typedef struct gpx_exec_sum {
+  int32_t slot;       /* decided slot (lane_mask != 0) or the request's status */
+  uint8_t lane_mask;  /* lanes that executed the request in order */
+  uint8_t flags;      /* GPX_F_CKPT */
+  uint16_t nreq;      /* requests executed with it (1) */
+} gpx_exec_sum;
+typedef struct gpx_round_io {
+  uint32_t n;
+  uint32_t flags;              /* 0 or GPX_ROUND_COMPACT */
+  const gpx_request_rec* reqs; /* [n] host */
+  const uint8_t* payload;      /* host */
+  uint64_t payload_bytes;
+  int32_t* status;             /* [n] out, full mode */
+  gpx_exec_rec* exec;          /* [n * n_lanes] out, full mode */
+  gpx_exec_sum* sum;           /* [n] out, compact mode */
+  gpx_exec_rec* extra;         /* [extra_cap] out: further executions (filled by gpx_round_wait; *n_extra >
+                                * extra_cap = truncated.  compact mode needs up to n * n_lanes + the full mode's) */
+  uint32_t extra_cap;
+} gpx_round_io;
+int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket);
+/* blocks until round `ticket` is complete; rounds must be waited for in submission order */
+int gpx_round_wait(gpx_engine* e, uint64_t ticket, uint32_t* n_exec_slots, uint32_t* n_extra);
+
 /* Digest path (DIGEST_REQUESTS, paxospackets/RequestPacket.java:1414-1430, AcceptPacket.digest :162-170):
  * MD5 of every request's requestValue, 16 bytes each -- the digest a coordinator puts into an ACCEPT in
  * place of the request body and an acceptor checks against the body it received by broadcast
