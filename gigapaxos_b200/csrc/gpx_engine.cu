@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gpx_round.cuh"
+#include "gpx_route.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -944,6 +945,140 @@ int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* st
   if (rc) return rc;
   return round_on_stream(e, false, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
                          stream ? (cudaStream_t)stream : e->stream);
+}
+
+/* ---- device-resident phase calls (spread placement) -------------------------------------- */
+static_assert(sizeof(gpx_dev_ctl) == sizeof(RoundCtl), "gpx_dev_ctl mirrors RoundCtl");
+namespace {
+/* the launch helpers count into / append to engine-owned scratch; point them at the caller's buffers for the
+ * duration of one call (the engine is single-submitter) */
+struct ScratchSwap {
+  gpx_engine* e;
+  RoundCtl* ctl0;
+  gpx_accept_rec* acc0;
+  gpx_exec_rec* ex0;
+  uint32_t cap0;
+  ScratchSwap(gpx_engine* e_, gpx_dev_ctl* ctl, gpx_accept_rec* acc, gpx_exec_rec* extra, uint32_t extra_cap)
+      : e(e_), ctl0(e_->d_ctl), acc0(e_->d_accepts), ex0(e_->d_extra), cap0(e_->extra_cap) {
+    if (ctl) e->d_ctl = reinterpret_cast<RoundCtl*>(ctl);
+    if (acc) e->d_accepts = acc;
+    if (extra) {
+      e->d_extra = extra;
+      e->extra_cap = extra_cap;
+    }
+  }
+  ~ScratchSwap() {
+    e->d_ctl = ctl0;
+    e->d_accepts = acc0;
+    e->d_extra = ex0;
+    e->extra_cap = cap0;
+  }
+};
+}  // namespace
+
+int gpx_propose_device(gpx_engine* e, const gpx_request_rec* reqs, const uint8_t* payload, uint64_t payload_bytes,
+                       uint32_t n, int32_t* status, gpx_accept_rec* out_accepts, gpx_dev_ctl* ctl, void* stream) {
+  if (!e || !ctl) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!reqs || !status || !out_accepts || (!payload && payload_bytes)) return fail(GPX_EINVAL, "null argument");
+  int rc = check_batch(e, n, payload_bytes);
+  if (rc) return rc;
+  ScratchSwap sw(e, ctl, out_accepts, nullptr, 0);
+  return launch_propose(e, reqs, payload, (payload_bytes + 15) & ~15ull, n, status,
+                        stream ? (cudaStream_t)stream : e->stream);
+}
+
+int gpx_route_device(gpx_engine* e, uint32_t kind, const void* recs, const uint32_t* n_ptr, uint32_t n_max,
+                     const uint8_t* payload, uint64_t payload_bytes, uint32_t n_dest, const int32_t* dest_nodes,
+                     void* out_recs, uint32_t cap, uint32_t* out_counts, uint8_t* out_blob, uint64_t blob_cap,
+                     uint32_t* out_blob_units, uint32_t* dropped, void* stream) {
+  if (!e || !recs || !dest_nodes || !out_recs || !out_counts) return fail(GPX_EINVAL, "null argument");
+  if (kind != GPX_F_ACCEPT && kind != GPX_F_DECISION && kind != 0) return fail(GPX_EINVAL, "bad record kind");
+  if (n_dest == 0 || n_dest > GPX_ROUTE_ND) return fail(GPX_EINVAL, "n_dest out of range");
+  if (kind == GPX_F_ACCEPT && (!out_blob || !out_blob_units || (blob_cap & 15))) return fail(GPX_EINVAL, "blob buckets");
+  if (n_max == 0) return GPX_OK;
+  RouteArgs A;
+  memset(&A, 0, sizeof A);
+  A.recs = (const uint8_t*)recs;
+  A.n_ptr = n_ptr;
+  A.n_max = n_max;
+  A.kind = kind;
+  A.n_dest = n_dest;
+  for (uint32_t d = 0; d < n_dest; d++) A.dest_node[d] = dest_nodes[d];
+  A.out_recs = (uint8_t*)out_recs;
+  A.cap = cap;
+  A.out_counts = out_counts;
+  A.blob0 = payload;
+  A.blob0_bytes = (payload_bytes + 15) & ~15ull;
+  A.blob1 = e->d_blob1;
+  A.out_blob = out_blob;
+  A.blob_cap = blob_cap;
+  A.out_blob_units = out_blob_units;
+  A.dropped = dropped;
+  k_route<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, stream ? (cudaStream_t)stream : e->stream>>>(e->S, A);
+  CK(cudaGetLastError());
+  return GPX_OK;
+}
+
+int gpx_accepts_device(gpx_engine* e, gpx_accept_rec* recs, uint32_t n, const uint8_t* blob, uint64_t blob_bytes,
+                       uint32_t n_chunks, const uint32_t* chunk_rec_end, const uint64_t* chunk_blob_base,
+                       gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra, uint32_t extra_cap,
+                       gpx_dev_ctl* ctl, void* stream) {
+  if (!e || !ctl) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!recs || !out_replies || (!blob && blob_bytes)) return fail(GPX_EINVAL, "null argument");
+  if (blob_bytes & 15) return fail(GPX_EINVAL, "blob_bytes must be a multiple of 16");
+  if (n_chunks > GPX_ROUTE_ND || (n_chunks && (!chunk_rec_end || !chunk_blob_base))) return fail(GPX_EINVAL, "chunks");
+  if (n > e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
+  int rc = ring_fits(e, 96ull + 48ull * n + blob_bytes);
+  if (rc) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  {
+    IngestArgs R;
+    memset(&R, 0, sizeof R);
+    R.recs = (uint8_t*)recs;
+    R.rec_bytes = 48;
+    R.n = n;
+    R.n_chunks = n_chunks;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+      R.rec_end[c] = chunk_rec_end[c];
+      R.blob_base[c] = chunk_blob_base[c];
+    }
+    k_ingest<<<cdiv(n, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, R);
+  }
+  ScratchSwap sw(e, ctl, nullptr, out_extra, out_extra ? extra_cap : 0);
+  return launch_accept(e, false, recs, nullptr, n, blob, blob_bytes, nullptr, 0, nullptr, out_replies, nullptr, nullptr,
+                       st);
+}
+
+int gpx_replies_device(gpx_engine* e, const gpx_accept_reply_rec* replies, uint32_t n,
+                       gpx_decision_rec* out_decisions, gpx_dev_ctl* ctl, void* stream) {
+  if (!e || !ctl) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!replies || !out_decisions) return fail(GPX_EINVAL, "null argument");
+  ScratchSwap sw(e, ctl, nullptr, nullptr, 0);
+  return launch_tally(e, replies, nullptr, 1, n, out_decisions, stream ? (cudaStream_t)stream : e->stream);
+}
+
+int gpx_decisions_device(gpx_engine* e, gpx_decision_rec* decisions, uint32_t n, gpx_exec_rec* out_exec,
+                         gpx_exec_rec* out_extra, uint32_t extra_cap, gpx_dev_ctl* ctl, void* stream) {
+  if (!e || !ctl) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!decisions || !out_exec) return fail(GPX_EINVAL, "null argument");
+  if (n > e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
+  int rc = ring_fits(e, 64ull + 32ull * n);
+  if (rc) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  {
+    IngestArgs R;
+    memset(&R, 0, sizeof R);
+    R.recs = (uint8_t*)decisions;
+    R.rec_bytes = 32;
+    R.n = n;
+    k_ingest<<<cdiv(n, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, R);
+  }
+  ScratchSwap sw(e, ctl, nullptr, out_extra, out_extra ? extra_cap : 0);
+  return launch_commit(e, decisions, nullptr, n, out_exec, st);
 }
 
 /* ---- pipelined rounds ---------------------------------------------------------------- */

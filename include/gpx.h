@@ -436,6 +436,51 @@ typedef struct gpx_dev_round_bufs {
 } gpx_dev_round_bufs;
 int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream);        /* fused */
 int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream); /* phase by phase */
+/* ---- device-resident phase calls: replicas of a group in DIFFERENT engines (spread placement:
+ * one engine per GPU hosts one node; ACCEPT / ACCEPT_REPLY / DECISION records travel between engines
+ * over NVLink).  Everything is asynchronous on `stream`; all pointers are device pointers unless
+ * noted.  `ctl` is a caller-owned device block the kernels count into (the caller zeroes it). ---- */
+typedef struct gpx_dev_ctl {
+  uint32_t n_accepts;   /* gpx_propose_device: ACCEPTs written */
+  uint32_t n_decisions; /* gpx_replies_device: DECISIONs appended (accumulates over calls) */
+  uint32_t n_extra;     /* EXEC records appended to the extra queue */
+  uint32_t any_batched;
+  uint64_t blob1_used;  /* bytes of constructed (batched) blobs behind the payload arena */
+  uint32_t n_todo;
+  uint32_t pad;
+} gpx_dev_ctl;
+/* RequestBatcher + PISM.handleProposal / PCS.propose: out_accepts[<= n] (grouped by gid, dst_mask = all
+ * members), payload_off relative to [payload arena | engine-owned batched blobs] */
+int gpx_propose_device(gpx_engine* e, const gpx_request_rec* reqs, const uint8_t* payload, uint64_t payload_bytes,
+                       uint32_t n, int32_t* status, gpx_accept_rec* out_accepts, gpx_dev_ctl* ctl, void* stream);
+/* PaxosPacketBatcher per-destination grouping + PaxosManager.send unicast split (:2098-2128): bucket the
+ * records of one kind (GPX_F_ACCEPT, GPX_F_DECISION, 0 = ACCEPT_REPLY) by destination node.
+ * dest_nodes[n_dest <= 8] (host) lists the nodes served, the local one included (loopback).
+ * out_recs[n_dest][cap], out_counts[n_dest] (zeroed by the caller); ACCEPTs also re-pack their blobs:
+ * out_blob[n_dest][blob_cap], out_blob_units[n_dest] = bytes / 16.  Records of a group stay adjacent
+ * and ordered inside a bucket.  *dropped counts records without a served destination / over capacity. */
+int gpx_route_device(gpx_engine* e, uint32_t kind, const void* recs, const uint32_t* n_ptr, uint32_t n_max,
+                     const uint8_t* payload, uint64_t payload_bytes, uint32_t n_dest, const int32_t* dest_nodes,
+                     void* out_recs, uint32_t cap, uint32_t* out_counts, uint8_t* out_blob, uint64_t blob_cap,
+                     uint32_t* out_blob_units, uint32_t* dropped, void* stream);
+/* PISM.handleAccept at the local lanes for n received ACCEPTs = n_chunks concatenated buckets (chunk c ends
+ * at record chunk_rec_end[c], its blob starts at chunk_blob_base[c] of `blob`; host arrays); payload_off of
+ * the records is rebased in place.  out_replies[n * n_lanes]; executions released by
+ * reconstructDecision go to out_extra[ctl->n_extra++]. */
+int gpx_accepts_device(gpx_engine* e, gpx_accept_rec* recs, uint32_t n, const uint8_t* blob, uint64_t blob_bytes,
+                       uint32_t n_chunks, const uint32_t* chunk_rec_end, const uint64_t* chunk_blob_base,
+                       gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra, uint32_t extra_cap,
+                       gpx_dev_ctl* ctl, void* stream);
+/* PaxosCoordinator.handleAcceptReply for n replies grouped by gid (one bucket of one acceptor at a time keeps
+ * the replies of a group in one run); DECISIONs are appended at out_decisions[ctl->n_decisions++] */
+int gpx_replies_device(gpx_engine* e, const gpx_accept_reply_rec* replies, uint32_t n,
+                       gpx_decision_rec* out_decisions, gpx_dev_ctl* ctl, void* stream);
+/* PISM.handleBatchedCommit + extractExecuteAndCheckpoint: out_exec[n * n_lanes], further executions in
+ * out_extra[ctl->n_extra++].  (Received ACCEPT / DECISION records get their dst_mask -- a LOCAL lane mask --
+ * rewritten in place to this engine's member lanes.) */
+int gpx_decisions_device(gpx_engine* e, gpx_decision_rec* decisions, uint32_t n, gpx_exec_rec* out_exec,
+                         gpx_exec_rec* out_extra, uint32_t extra_cap, gpx_dev_ctl* ctl, void* stream);
+
 /* per-kernel CUDA-event timing of the last gpx_round_device calls (ms, accumulated) */
 typedef struct gpx_kernel_times {
   double propose_ms, accept_ms, tally_ms, commit_ms;
