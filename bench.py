@@ -279,6 +279,11 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--placement", default="packed", choices=["packed", "spread"],
+                    help="packed (default): all replicas of a group on its home GPU, no data-path collective; spread: "
+                         "replica j on GPU (home+j) mod N, ACCEPT/REPLY/DECISION records exchanged over NCCL "
+                         "(needs N >= replicas; with --gpus 1 the nodes are --spread-nodes engines on one GPU)")
+    ap.add_argument("--spread-nodes", type=int, default=4)
     args = ap.parse_args()
 
     wl = dict(WORKLOADS[args.workload])
@@ -334,6 +339,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     lib = gigapaxos_b200.load_library()
+    if args.placement == "spread":
+        run_spread(args, lib, dev, rank, world, G, R, P, K, max(W, 3), metric, config)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     eng = Engine(lib, engine_config(lib, G, R, P, local_rank))
     names = shard_names(G, rank, world)
     eng.create_groups(make_descs(abi, names, R))
@@ -568,6 +578,130 @@ def main():
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_spread(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
+    """Spread placement: one node (single-lane engine) per GPU; every node coordinates G groups and is an acceptor of
+    ~(R-1)*G more.  A step = one request for every group; the records cross GPUs three times (ACCEPT, ACCEPT_REPLY,
+    DECISION) through gigapaxos_b200/spread.py."""
+    import torch
+    import torch.distributed as dist
+
+    from gigapaxos_b200 import abi
+    from gigapaxos_b200.spread import (DistExchange, LocalExchange, SpreadCluster, SpreadNode, coordinator_of,
+                                       members_of)
+    N = world if world > 1 else args.spread_nodes
+    if N < R:
+        raise SystemExit(f"spread placement needs at least {R} nodes")
+    node_ids = [NODES[0] + i for i in range(N)]
+    # group names NoopPaxosApp<i>, i = 0, 1, ...: keep the first G that every node coordinates
+    per, i, total = [[] for _ in range(N)], 0, 0
+    while total < N * G:
+        nm = f"NoopPaxosApp{i}"
+        mem = [node_ids[m] for m in members_of(nm, N, R)]
+        c = coordinator_of(nm, mem) - node_ids[0]
+        if len(per[c]) < G:
+            per[c].append((nm, mem))
+            total += 1
+        i += 1
+    descs = np.zeros(N * G, dtype=abi.group_desc_dtype)
+    member_of = np.zeros((N * G, N), dtype=bool)
+    for c in range(N):
+        for k, (nm, mem) in enumerate(per[c]):
+            g = c * G + k  # global gid: node c coordinates gids [c*G, (c+1)*G)
+            descs[g]["gid"] = g
+            descs[g]["name_hash"] = abi.java_string_hash(nm)
+            descs[g]["n_members"] = R
+            descs[g]["members"][:R] = mem
+            descs[g]["init_mode"] = abi.INIT_BATCH
+            member_of[g, [m - node_ids[0] for m in mem]] = True
+    local = list(range(N)) if world == 1 else [rank]
+    nodes = []
+    for idx in local:
+        n_in = int(member_of[:, idx].sum())
+        ring = 1 << 26
+        while ring < 4 * (128 + 80 * n_in + n_in * (P + 16)):
+            ring <<= 1
+        nd = SpreadNode(lib, idx, node_ids, dev, max_groups=N * G, max_batch=max(n_in, G), max_payload=G * P + 16,
+                        max_group_size=R, window=8, log_ring_bytes=ring)
+        nd.engine.create_groups(descs[member_of[:, idx]])
+        nodes.append(nd)
+    cluster = SpreadCluster(nodes, LocalExchange(N) if world == 1 else DistExchange(), N)
+    NB = 4
+    batches = []
+    for b in range(NB):
+        bb = {}
+        for idx in local:
+            reqs, pay = make_batch(abi, G, P, 1000 * idx + b)
+            reqs["gid"] = np.arange(idx * G, (idx + 1) * G, dtype=np.uint32)
+            reqs["entry_node"] = node_ids[idx]
+            bb[idx] = (torch.from_numpy(reqs.view(np.uint8).copy()).to(dev),
+                       torch.from_numpy(np.concatenate([pay, np.zeros(16, np.uint8)])).to(dev)[: pay.size], G)
+        batches.append(bb)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(W):
+        cluster.round(batches[w % NB])
+    sampler = ClockSampler(dev.index or 0)
+    barrier()
+    c0 = [nd.engine.counters() for nd in nodes]
+    sampler.start()
+    cluster.timing = True
+    step_ms, phase_ms = [], {}
+    for k in range(K):
+        if not args.no_flush:
+            flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = cluster.round(batches[k % NB])
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        for name, ms in res[local[0]].get("ms", {}).items():
+            phase_ms[name] = phase_ms.get(name, 0.0) + ms / K
+    barrier()
+    clocks = sampler.stop()
+    total_ms = float(np.sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    c1 = [nd.engine.counters() for nd in nodes]
+    for nd, a, b in zip(nodes, c0, c1):
+        assert b["decisions_made"] - a["decisions_made"] == G * K, "every coordinated group decides once per step"
+        assert b["executed"] - a["executed"] == int(member_of[:, nd.index].sum()) * K, "every replica executes"
+    value = N * G * K / (total_ms / 1e3)
+    if rank == 0:
+        n_in = int(member_of[:, local[0]].sum())
+        peak, peak_src = hbm_peak()
+        acc_ms = phase_ms.get("accept+route", 0.0)
+        cfg = dict(config)
+        cfg.update({"groups_per_gpu": G, "placement": f"spread: {N} nodes, one single-lane engine per "
+                    + ("GPU (NCCL point-to-point buckets over NVLink)" if world > 1 else "node, all on ONE GPU (device copies)")
+                    + f"; replica j of a group on node (home+j) mod {N}; three record exchanges per round",
+                    "accepts_in_per_node_per_step": n_in})
+        line = {
+            "metric": metric, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": cfg,
+            "roofline": {"kernel": "accept phase of one node: k_ingest + k_accept<1> + k_route(replies)", "bound": "hbm",
+                         "achieved": n_in * b_acc(P) / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else 0.0, "peak": peak,
+                         "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": n_in * b_acc(P), "kernel_ms": acc_ms,
+                         "frac": (n_in * b_acc(P) / (acc_ms / 1e3) / 1e9 / peak) if acc_ms > 0 else 0.0},
+            "phase_ms": phase_ms, "cpu_baseline": None, "e2e": None, "clocks": clocks,
+            "gpu_launches": K * (2 + 3 + 2 + N + 1 + 2) * len(local),
+            "p50_decide_latency_ms": float(np.median(step_ms)),
+        }
+        print(json.dumps(line))
+    for nd in nodes:
+        nd.engine.close()
 
 
 if __name__ == "__main__":

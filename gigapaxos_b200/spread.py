@@ -71,25 +71,50 @@ class LocalExchange:
                     recv[j][i].copy_(send[i][j], non_blocking=True)
 
 
-class NcclExchange:
-    """one process per GPU (torch.distributed, backend nccl): node index == rank"""
+class DistExchange:
+    """one process per node (torch.distributed; backend nccl over NVLink on GPUs, gloo in the CPU tests):
+    node index == rank.  Counts travel by all_gather, the buckets by one batch of point-to-point
+    sends/receives straight out of / into the bucket views (no packing copy)."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.n = dist.get_world_size(group)
-        self.local = [dist.get_rank(group)]
+        self.rank = dist.get_rank(group)
+        self.local = [self.rank]
 
     def counts(self, per_node):
         mine = per_node[0].contiguous()  # [n, k] what I send to each destination
-        got = torch.empty_like(mine)
-        self.dist.all_to_all_single(got, mine, group=self.group)
-        both = torch.stack([mine, got]).cpu().numpy()
-        return [both[1]], [both[0]]
+        allc = [torch.empty_like(mine) for _ in range(self.n)]
+        self.dist.all_gather(allc, mine, group=self.group)
+        host = torch.stack(allc).cpu().numpy()  # [src, dst, k]
+        return [host[:, self.rank, :].copy()], [host[self.rank]]
 
     def all_to_all(self, send, recv):
-        self.dist.all_to_all(recv[0], send[0], group=self.group)
+        dist, me = self.dist, self.rank
+        ops = []
+        for p in range(self.n):
+            if p == me:
+                continue
+            if recv[0][p].numel():
+                ops.append(dist.P2POp(dist.irecv, recv[0][p], p, self.group))
+            if send[0][p].numel():
+                ops.append(dist.P2POp(dist.isend, send[0][p], p, self.group))
+        if recv[0][me].numel():
+            recv[0][me].copy_(send[0][me], non_blocking=True)  # loopback
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+NcclExchange = DistExchange
+
+
+def _on(dev: torch.device):
+    """device context (no-op for the CPU nodes of the test-suite)"""
+    import contextlib
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
 
 
 class SpreadNode:
@@ -173,9 +198,10 @@ class SpreadCluster:
         self.x = exchange
         self.N = n_nodes
         assert [nd.index for nd in nodes] == list(exchange.local)
+        self.timing = False
         self.streams = {}
         for nd in nodes:
-            if nd.device not in self.streams:
+            if nd.device.type == "cuda" and nd.device not in self.streams:
                 self.streams[nd.device] = torch.cuda.Stream(device=nd.device)
 
     def _exchange(self, kind: int, outs: List[torch.Tensor], caps: List[int], blobs=None, blob_caps=None):
@@ -186,8 +212,6 @@ class SpreadCluster:
         send_r, recv_r, send_b, recv_b, res = [], [], [], [], []
         for k, nd in enumerate(self.nodes):
             sc, rc = send_cnt[k], recv_cnt[k]  # [N, 2]
-            if int(nd.dropped.item()) != 0:
-                raise RuntimeError("k_route dropped records: destination not served or buckets too small")
             cap = caps[k]
             send_r.append([outs[k][d * cap * rb: d * cap * rb + int(sc[d, 0]) * rb] for d in range(self.N)])
             tot = int(rc[:, 0].sum())
@@ -230,12 +254,22 @@ class SpreadCluster:
         extra / n_extra, and the intermediate counts."""
         N = self.N
         st = {}
+        marks = {nd.index: [] for nd in self.nodes}
+
+        def mark(nd, name):  # CUDA events at the phase boundaries (only when self.timing)
+            if self.timing and nd.device.type == "cuda":
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(nd.device))
+                marks[nd.index].append((name, ev))
+
+        for nd in self.nodes:
+            mark(nd, "start")
         # ---- propose + route ACCEPTs -------------------------------------------------------------------
         outs, caps, blobs, bcaps = [], [], [], []
         for nd in self.nodes:
             reqs, payload, n = batches.get(nd.index, (None, None, 0))
             dev = nd.device
-            with torch.cuda.device(dev):
+            with _on(dev):
                 nd.ctl.zero_()
                 nd.dropped.zero_()
                 s = {"n": n, "status": torch.zeros(max(n, 1), dtype=torch.int32, device=dev),
@@ -253,14 +287,17 @@ class SpreadCluster:
                 s["_keep"] = (acc, out, ob)
                 st[nd.index] = s
                 outs.append(out), caps.append(max(n, 1)), blobs.append(ob), bcaps.append(bcap)
+                mark(nd, "propose+route")
         got = self._exchange(K_ACCEPT, outs, caps, blobs, bcaps)
+        for nd in self.nodes:
+            mark(nd, "exchange_accepts")
         # ---- handleAccept + route replies ----------------------------------------------------------------
         outs, caps = [], []
         for nd, (abuf, cnts, offs, bbuf, boffs) in zip(self.nodes, got):
             s = st[nd.index]
             na = int(offs[-1])
             s["n_accepts_in"] = na
-            with torch.cuda.device(nd.device):
+            with _on(nd.device):
                 rep = torch.empty(max(na, 1) * 32, dtype=torch.uint8, device=nd.device)
                 out = torch.empty(N * max(na, 1) * 32, dtype=torch.uint8, device=nd.device)
                 if na:
@@ -271,14 +308,17 @@ class SpreadCluster:
                     nd.cnt = torch.zeros((N, 2), dtype=torch.int32, device=nd.device)
                 s["_keep2"] = (abuf, bbuf, rep, out)
                 outs.append(out), caps.append(max(na, 1))
+                mark(nd, "accept+route")
         got = self._exchange(K_REPLY, outs, caps)
+        for nd in self.nodes:
+            mark(nd, "exchange_replies")
         # ---- tally (one acceptor's bucket at a time, node order) + route DECISIONs ----------------------------
         outs, caps = [], []
         for nd, (rbuf, cnts, offs, _, _) in zip(self.nodes, got):
             s = st[nd.index]
             nr = int(offs[-1])
             n = s["n"]
-            with torch.cuda.device(nd.device):
+            with _on(nd.device):
                 dec = torch.empty(max(n, 1) * 32, dtype=torch.uint8, device=nd.device)
                 out = torch.empty(N * max(n, 1) * 32, dtype=torch.uint8, device=nd.device)
                 for src in range(N):
@@ -291,19 +331,29 @@ class SpreadCluster:
                 s["n_replies_in"] = nr
                 s["_keep3"] = (rbuf, dec, out)
                 outs.append(out), caps.append(max(n, 1))
+                mark(nd, "tally+route")
         got = self._exchange(K_DECISION, outs, caps)
+        for nd in self.nodes:
+            mark(nd, "exchange_decisions")
         # ---- commit + execute -------------------------------------------------------------------------------
         for nd, (dbuf, cnts, offs, _, _) in zip(self.nodes, got):
             s = st[nd.index]
             ndec = int(offs[-1])
-            with torch.cuda.device(nd.device):
+            with _on(nd.device):
                 ex = torch.empty(max(ndec, 1) * 24, dtype=torch.uint8, device=nd.device)
                 if ndec:
                     nd.decisions(dbuf, ndec, ex, s["extra"], extra_cap)
                 s["exec"], s["n_exec"], s["_keep4"] = ex, ndec, dbuf
+                mark(nd, "commit")
         for nd in self.nodes:
             s = st[nd.index]
             s["n_extra"] = int(nd.ctl[CTL_N_EXTRA].item())
+            if int(nd.dropped.item()) != 0:
+                raise RuntimeError("k_route dropped records: destination not served or buckets too small")
+            if marks[nd.index]:
+                torch.cuda.synchronize(nd.device)
+                m = marks[nd.index]
+                s["ms"] = {m[k + 1][0]: m[k][1].elapsed_time(m[k + 1][1]) for k in range(len(m) - 1)}
             for k in ("_keep", "_keep2", "_keep3", "_keep4"):
                 s.pop(k, None)
         return st

@@ -154,3 +154,86 @@ def test_spread_round_parity(oracle_lib, cuda_lib, N, G, P):
     for k in ("accepts_handled", "accepts_acked", "accepts_logged", "replies_handled", "decisions_made",
               "decisions_handled", "executed", "checkpoints_due", "proposals", "requests_batched"):
         assert co[k] == tot[k], k
+
+
+# ---- one process per GPU over NCCL (needs >= 3 GPUs: skipped on single-GPU boxes) ------------------------------
+def _nccl_worker(rank, world, port, q, G, rounds):
+    import os
+    import traceback
+    import torch
+    import torch.distributed as dist
+    try:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        os.environ["NCCL_DEBUG"] = "WARN"
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import gigapaxos_b200
+        from gigapaxos_b200.spread import DistExchange
+        from helpers import oracle_library
+        from test_spread_gloo import by_gid as by_gid2, make_groups, node_batch, workload
+        R = 3
+        node_ids, descs, coord, member_of = make_groups(world, G, R)
+        lib = gigapaxos_b200.load_library()
+        nd = SpreadNode(lib, rank, node_ids, dev, max_groups=G, max_batch=8 * G, max_payload=1 << 22, max_group_size=R,
+                        checkpoint_interval=3)
+        nd.engine.create_groups(descs[member_of[:, rank]])
+        cluster = SpreadCluster([nd], DistExchange(), world)
+        olib = oracle_library()
+        ref = Engine(olib, make_config(olib, max_groups=G, n_lanes=world, lane_node=node_ids, max_group_size=R,
+                                       max_batch_recs=8 * G, max_batch_payload=1 << 22, checkpoint_interval=3))
+        ref.create_groups(descs)
+        n_exec = 0
+        for r in range(rounds):
+            gids, reqs, pay = workload(G, coord, r)
+            acc, blob, so = ref.propose(reqs, pay)
+            rep, _ = ref.handle_accepts(acc, blob)
+            dec = ref.handle_accept_replies(rep)
+            xo, _ = ref.handle_decisions(dec)
+            sel = np.nonzero(coord[gids] == rank)[0]
+            batches = {}
+            if len(sel):
+                a, b, n = node_batch(reqs, pay, sel)
+                batches[rank] = (a.to(dev), b.to(dev), n)
+            s = cluster.round(batches)[rank]
+            torch.cuda.synchronize()
+            if len(sel):
+                assert np.array_equal(s["status"].cpu().numpy()[: len(sel)], so[sel])
+            got = by_gid2(s["exec"].cpu().numpy().view(abi.exec_dtype)[: s["n_exec"]])
+            want = by_gid2(xo[((xo["flags"] >> 12) & 0xF) == rank])
+            assert len(got) == len(want)
+            for f in ("gid", "slot", "req_id"):
+                assert np.array_equal(got[f], want[f]), f
+            n_exec += len(got)
+        g = np.nonzero(member_of[:, rank])[0]
+        ro, rg = ref.dump_rows(g, rank), nd.engine.dump_rows(g, 0)
+        for f in ro.dtype.names:
+            if f != "lane":
+                assert np.array_equal(ro[f], rg[f]), f
+        dist.barrier()
+        q.put((rank, "ok", n_exec))
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        q.put((rank, "fail: " + traceback.format_exc(), 0))
+        raise
+
+
+def test_spread_over_nccl():
+    import torch
+    import torch.multiprocessing as mp
+    from test_spread_gloo import free_port
+    world = min(torch.cuda.device_count(), 4)
+    if world < 3:
+        pytest.skip("spread placement over NCCL needs >= 3 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, 500, 4)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, n_exec in res:
+        assert status == "ok", f"rank {rank}: {status}"
+        assert n_exec > 0
