@@ -703,11 +703,19 @@ template <int L>
 __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_accept(const __grid_constant__ DevState S,
                                                       const __grid_constant__ AcceptArgs A) {
   __shared__ unsigned int s_ctr[C_NCTR];
+  /* the block's tile of the incoming ACCEPT batch (its 256 records + the predecessor for the run-head test) is
+   * staged in shared memory by ONE TMA bulk copy, overlapped with the segment bookkeeping below */
+  __shared__ __align__(128) uint8_t s_tile[(GPX_BLOCK + 1) * sizeof(gpx_accept_rec)];
+  __shared__ __align__(8) unsigned long long s_bar;
   if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   uint32_t n = A.n_ptr ? *A.n_ptr : A.n_max;
   if (n > A.n_max) n = A.n_max;
-  const uint32_t i = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  const uint32_t i0 = blockIdx.x * GPX_BLOCK, i = i0 + threadIdx.x;
+  const uint32_t t0 = i0 ? i0 - 1u : 0u, t1 = min(n, i0 + GPX_BLOCK); /* records [t0, t1) are staged */
+  const uint32_t tile_bytes = t1 > t0 ? (t1 - t0) * (uint32_t)sizeof(gpx_accept_rec) : 0u;
+  if (threadIdx.x == 0 && tile_bytes) tma_load_1d(s_tile, &A.recs[t0], tile_bytes, &s_bar);
   const uint32_t Wm = S.W - 1;
   const unsigned long long pay_bytes = A.blob0_bytes + (A.blob1_used_ptr ? *A.blob1_used_ptr : A.blob1_bytes);
   const unsigned long long pay_rel = 64ull + (unsigned long long)A.n_max * 48ull;
@@ -723,11 +731,12 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_accept(const __gr
     for (int l = 0; l < L; l++) write_seg_hdr(S, l, segb[l], GPX_F_ACCEPT, A.n_max, n, pay_bytes, 48, S.seg_seq[l]);
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
+  if (tile_bytes) mbar_wait(&s_bar, 0);
   if (i < n) {
-    const int4* rp = reinterpret_cast<const int4*>(&A.recs[i]);
-    int4 q0 = ld_stream4(rp), q1 = ld_stream4(rp + 1), q2 = ld_stream4(rp + 2);
+    const int4* rp = reinterpret_cast<const int4*>(s_tile + (size_t)(i - t0) * sizeof(gpx_accept_rec));
+    int4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
     const uint32_t gid = (uint32_t)q0.x;
-    const bool head = (i == 0) || (A.recs[i - 1].h.gid != gid);
+    const bool head = (i == 0) || ((uint32_t)rp[-3].x != gid);
     if (head) {
       const GroupCtx g = group_ctx(S, gid);
       uint32_t j = i;
@@ -774,12 +783,14 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_accept(const __gr
         if (logmask) copy_blob<L>(S, A, payload_off, (uint32_t)q2.y, logmask, payb);
         j++;
         if (j >= n) break;
-        rp = reinterpret_cast<const int4*>(&A.recs[j]);
-        int4 t0 = ld_stream4(rp);
-        if ((uint32_t)t0.x != gid) break;
-        q0 = t0;
-        q1 = ld_stream4(rp + 1);
-        q2 = ld_stream4(rp + 2);
+        /* the run continues in the staged tile, or -- across the block boundary -- in global memory */
+        rp = j < t1 ? reinterpret_cast<const int4*>(s_tile + (size_t)(j - t0) * sizeof(gpx_accept_rec))
+                    : reinterpret_cast<const int4*>(&A.recs[j]);
+        const int4 nx = rp[0];
+        if ((uint32_t)nx.x != gid) break;
+        q0 = nx;
+        q1 = rp[1];
+        q2 = rp[2];
       }
     }
   }
