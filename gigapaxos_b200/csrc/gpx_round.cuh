@@ -353,12 +353,22 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
                                                                      const __grid_constant__ RoundArgs RA) {
   static_assert(LP == L, "teams are exactly the L lanes of a group");
   constexpr uint32_t FULL = 0xffffffffu;
+  constexpr uint32_t TPB = (GPX_BLOCK / 32u) * (32u / LP); /* teams (= requests) per block */
   __shared__ unsigned int s_ctr[C_NCTR];
+  /* the block's tile of the request batch (+ one neighbour on each side for the run tests) is staged in shared
+   * memory by ONE TMA bulk copy */
+  __shared__ __align__(128) gpx_request_rec s_req[TPB + 2];
+  __shared__ __align__(8) unsigned long long s_bar;
   if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   const AcceptArgs& A = RA.A;
   const gpx_request_rec* reqs = RA.P.reqs;
   const uint32_t n = RA.P.n;
+  const uint32_t r0 = blockIdx.x * TPB; /* first request of the block; records [t0, t1) are staged */
+  const uint32_t t0 = r0 ? r0 - 1u : 0u, t1 = min(n, r0 + TPB + 1u);
+  const uint32_t tile_bytes = t1 > t0 ? (t1 - t0) * (uint32_t)sizeof(gpx_request_rec) : 0u;
+  if (threadIdx.x == 0 && tile_bytes) tma_load_1d(s_req, &reqs[t0], tile_bytes, &s_bar);
   /* teams of L adjacent lanes; 32/L teams per warp (the 32 mod L last lanes of a warp idle) */
   const uint32_t lane_id = threadIdx.x & 31u;
   constexpr uint32_t TPW = 32u / LP;
@@ -386,10 +396,13 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
   const bool valid = i < n;
   int4 rq0 = make_int4(0, 0, 0, 0), rq1 = rq0;
   uint32_t gprev = 0xffffffffu, gnext = 0xffffffffu;
+  if (tile_bytes) mbar_wait(&s_bar, 0);
   if (valid) {
-    ld256_stream(&reqs[i], rq0, rq1);
-    if (i > 0) gprev = reqs[i - 1].gid;
-    if (i + 1 < n) gnext = reqs[i + 1].gid;
+    const int4* rp = reinterpret_cast<const int4*>(&s_req[i - t0]);
+    rq0 = rp[0];
+    rq1 = rp[1];
+    if (i > 0) gprev = s_req[i - t0 - 1].gid;
+    if (i + 1 < n) gnext = s_req[i - t0 + 1].gid;
   }
   const uint32_t gid = (uint32_t)rq0.x, rflags = (uint32_t)rq0.y, entry = (rflags >> 8) & 0xfu;
   const uint32_t poff = (uint32_t)rq1.x, plen = (uint32_t)rq1.y;
