@@ -84,6 +84,8 @@ struct DevState {
   int4* acc_row;
   uint32_t* acc_aux;
   int4* acc_win;
+  uint8_t* acc_dirty; /* [L][G] journaling mode: 1 once a VALID accepted entry was stored for (lane, gid); while 0 the
+                       * in-order path knows the window holds no accept without reading it */
   int4* com_win;
   int4* coord_row;
   int32_t* node_slots;
@@ -146,6 +148,13 @@ __device__ __forceinline__ void ld256(const void* p, int4& a, int4& b) {
                : "l"(p)
                : "memory");
 }
+/* every store of an accepted-window entry goes through here (keeps acc_dirty conservative) */
+#define ST_ACC(S, lane, gid, idx, n0, n1)                                                    \
+  do {                                                                                       \
+    st256(&(S).acc_win[(idx)], (n0), (n1));                                                  \
+    if ((S).journaling && ((unsigned)(n1).w & GPX_ENT_VALID)) (S).acc_dirty[(size_t)(lane) * (S).G + (gid)] = 1; \
+  } while (0)
+
 /* ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous record tile into shared memory, completion
  * signalled on an mbarrier: one elected thread arms the barrier with the byte count and issues the copy, every
  * thread waits on the phase.  Addresses and size are multiples of 16. ---- */

@@ -207,6 +207,7 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   TRY(e->dalloc(&S.acc_row, L * G));
   TRY(e->dalloc(&S.acc_aux, L * G));
   TRY(e->dalloc(&S.acc_win, 2 * L * W * G));
+  TRY(e->dalloc(&S.acc_dirty, L * G));
   TRY(e->dalloc(&S.com_win, 2 * L * W * G));
   TRY(e->dalloc(&S.coord_row, L * G));
   TRY(e->dalloc(&S.node_slots, L * R * G));
@@ -235,6 +236,7 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
     cudaMemcpy(S.acc_aux, aux.data(), L * G * 4, cudaMemcpyHostToDevice);
     cudaMemset(S.coord_row, 0, L * G * sizeof(int4));
     cudaMemset(S.acc_win, 0, 2 * L * W * G * sizeof(int4));
+    cudaMemset(S.acc_dirty, 0, L * G);
     cudaMemset(S.com_win, 0, 2 * L * W * G * sizeof(int4));
     cudaMemset(S.prop_win, 0, L * W * G * sizeof(int4));
   }

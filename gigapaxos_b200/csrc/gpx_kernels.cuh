@@ -469,7 +469,7 @@ __device__ __forceinline__ void accept_lane(const DevState& S, const AcceptArgs&
     if (store) { /* the entry must be visible to the commit path */
       int4 n0, n1;
       make_entry(q0, q1, q2, st.frame_ref, n0, n1);
-      st256(&S.acc_win[ai], n0, n1);
+      ST_ACC(S, l, gid, ai, n0, n1);
       st.fl &= ~LS_STORE;
     }
     int4 c0, c1;
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_accept(const __gr
           if (st[l].fl & LS_STORE) {
             int4 n0, n1;
             make_entry(q0, q1, q2, st[l].frame_ref, n0, n1);
-            st256(&S.acc_win[2 * win_idx(S, l, (uint32_t)slot & Wm, gid)], n0, n1);
+            ST_ACC(S, l, gid, 2 * win_idx(S, l, (uint32_t)slot & Wm, gid), n0, n1);
           }
           if (st[l].fl & LS_ROWDIRTY) S.acc_row[ri] = st[l].row;
           if (st[l].fl & LS_AUXDIRTY) S.acc_aux[ri] = st[l].aux;
@@ -1170,10 +1170,10 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ACT_MINB) k_act(const __grid_co
                  * hide an occupant of the ring position whose valid bit is set */
                 if (st[l].fl & LS_OCCVALID) {
                   n1.w = (int)((unsigned)n1.w & ~GPX_ENT_VALID);
-                  st256(&S.acc_win[ai], n0, n1);
+                  ST_ACC(S, l, gid, ai, n0, n1);
                 }
               } else
-                st256(&S.acc_win[ai], n0, n1);
+                ST_ACC(S, l, gid, ai, n0, n1);
               st[l].fl &= ~LS_STORE;
               if (more) { /* second iteration: GC with the advanced slot, then any queued commits */
                 gc_step(row, d.median_cp);
@@ -1185,7 +1185,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ACT_MINB) k_act(const __grid_co
               int4 a0, a1; /* rare path: re-read the entry instead of keeping L x 32 B of registers alive */
               if (st[l].fl & LS_STORE) {
                 make_entry(q0, q1, q2, st[l].frame_ref, a0, a1);
-                st256(&S.acc_win[ai], a0, a1);
+                ST_ACC(S, l, gid, ai, a0, a1);
                 st[l].fl &= ~LS_STORE;
               } else
                 ld256(&S.acc_win[ai], a0, a1);
@@ -1199,7 +1199,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ACT_MINB) k_act(const __grid_co
           if (st[l].fl & LS_STORE) {
             int4 n0, n1;
             make_entry(q0, q1, q2, st[l].frame_ref, n0, n1);
-            st256(&S.acc_win[ai], n0, n1);
+            ST_ACC(S, l, gid, ai, n0, n1);
           }
           if (st[l].fl & LS_ROWDIRTY) S.acc_row[ri] = row;
           if (st[l].fl & LS_AUXDIRTY) S.acc_aux[ri] = aux;
@@ -1252,6 +1252,7 @@ __global__ void k_init_groups(const __grid_constant__ DevState S, const InitRec*
   S.grp_cpi[r.gid] = r.cpi;
   for (uint32_t l = 0; l < S.L; l++) {
     const size_t ri = row_idx(S, l, r.gid);
+    S.acc_dirty[ri] = 0;
     for (uint32_t w = 0; w < S.W; w++) {
       const size_t wi = win_idx(S, l, w, r.gid);
       S.acc_win[2 * wi] = make_int4(0, 0, 0, 0);
@@ -1344,6 +1345,7 @@ __global__ void k_load_rows(const __grid_constant__ DevState S, const LoadRec* r
   const size_t ri = row_idx(S, l, gid);
   S.acc_row[ri] = make_int4(r.acc_slot, r.acc_bnum, r.acc_bcoord, r.acc_gc_slot);
   S.acc_aux[ri] = (uint32_t)r.state & 0xffu;
+  S.acc_dirty[ri] = 0; /* every window entry is invalidated below */
   for (uint32_t w = 0; w < S.W; w++) {
     const size_t wi = win_idx(S, l, w, gid);
     S.acc_win[2 * wi + 1] = make_int4(0, 0, 0, 0);

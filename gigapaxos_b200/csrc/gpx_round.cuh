@@ -129,10 +129,10 @@ __device__ __forceinline__ void commit_team_lane(const DevState& S, const Accept
       if (S.journaling) {
         if (st.fl & LS_OCCVALID) {
           n1.w = (int)((unsigned)n1.w & ~GPX_ENT_VALID);
-          st256(&S.acc_win[ai], n0, n1);
+          ST_ACC(S, l, gid, ai, n0, n1);
         }
       } else
-        st256(&S.acc_win[ai], n0, n1);
+        ST_ACC(S, l, gid, ai, n0, n1);
       st.fl &= ~LS_STORE;
       if (more) {
         gc_step(row, d.median_cp);
@@ -143,7 +143,7 @@ __device__ __forceinline__ void commit_team_lane(const DevState& S, const Accept
       int4 a0, a1;
       if (st.fl & LS_STORE) {
         make_entry(q0, q1, q2, st.frame_ref, a0, a1);
-        st256(&S.acc_win[ai], a0, a1);
+        ST_ACC(S, l, gid, ai, a0, a1);
         st.fl &= ~LS_STORE;
       } else
         ld256(&S.acc_win[ai], a0, a1);
@@ -157,7 +157,7 @@ __device__ __forceinline__ void commit_team_lane(const DevState& S, const Accept
   if (st.fl & LS_STORE) {
     int4 n0, n1;
     make_entry(q0, q1, q2, st.frame_ref, n0, n1);
-    st256(&S.acc_win[ai], n0, n1);
+    ST_ACC(S, l, gid, ai, n0, n1);
   }
   if (st.fl & LS_ROWDIRTY) S.acc_row[ri] = row;
   if (st.fl & LS_AUXDIRTY) S.acc_aux[ri] = aux;
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
 
   /* ---- level B (depends on gid only): group meta, my lane's acceptor + coordinator rows; the first chunk of
    * the payload rides along ---- */
-  uint32_t meta = 0, my_aux = 0;
+  uint32_t meta = 0, my_aux = 0, my_dirty = 1;
   int4 my_row = make_int4(0, 0, 0, 0), my_crow = my_row, pv = my_row;
   const uint32_t ri = sub * G + gid; /* 32-bit plane indices: checked against 2^32 at engine creation */
   const uint8_t* const psrc = A.blob0 + poff;
@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
     my_aux = S.acc_aux[ri];
     my_row = S.acc_row[ri];
     my_crow = S.coord_row[ri];
+    if (S.journaling) my_dirty = S.acc_dirty[ri]; /* 0: no accept was ever stored here -> skip the window read */
     if (plen) {
       if (pal)
         pv = ld_stream4(psrc);
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
   const uint32_t wi = 2u * ((sub * S.W + ((uint32_t)slot & Wm)) * G + gid);
   const uint32_t ni = (cl * S.Rcap + sub) * G + gid;
   if (sf) {
-    ld256(&S.acc_win[wi], e0, e1);
+    if (my_dirty) ld256(&S.acc_win[wi], e0, e1);
     my_ns = S.node_slots[ni];
   }
   { /* an accept already sitting at this slot -> general path */
@@ -546,10 +547,10 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ROUND_MINB) k_round(const __gri
     row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
     if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
       if ((unsigned)e1.w & GPX_ENT_VALID)
-        st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
+        st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref), /* VALID cleared: acc_dirty untouched */
               make_int4(rq0.z, rq0.w, (int)plen, (int)(1u << 16)));
     } else
-      st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref),
+      st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref), /* not journaling: acc_dirty unused */
             make_int4(rq0.z, rq0.w, (int)plen, (int)(GPX_ENT_VALID | (1u << 16))));
     gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot */
     if ((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)row.x & Wm)) & 1u) { /* queued commits become executable (rare) */
