@@ -279,6 +279,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-large", action="store_true", help="skip the 1M-group roofline context measurement")
     ap.add_argument("--placement", default="packed", choices=["packed", "spread"],
                     help="packed (default): all replicas of a group on its home GPU, no data-path collective; spread: "
                          "replica j on GPU (home+j) mod N, ACCEPT/REPLY/DECISION records exchanged over NCCL "
@@ -455,6 +456,51 @@ def main():
     }
     roofline_accept["frac"] = roofline_accept["achieved"] / peak
 
+    # ---- the same kernels on a batch that fills the GPU (context for the latency-bound 100K-group step) --------
+    roofline_large = None
+    if args.workload == "cfg2" and not args.groups and world == 1 and not args.skip_large:
+        G2 = 1_000_000
+        eng2 = Engine(lib, engine_config(lib, G2, R, P, local_rank))
+        eng2.create_groups(make_descs(abi, shard_names(G2, rank, world), R))
+        hb = [make_batch(abi, G2, P, 77 + b) for b in range(2)]
+        r2 = [torch.from_numpy(b[0].view(np.uint8).copy()).to(dev) for b in hb]
+        p2 = [torch.from_numpy(b[1].copy()).to(dev) for b in hb]
+        st2 = torch.zeros(G2, dtype=torch.int32, device=dev)
+        ex2 = torch.zeros(G2 * R * 24, dtype=torch.uint8, device=dev)
+        res = {}
+        for name in ("round_device", "round_device_phases"):
+            f = lib.fn(name)
+            lib.fn("enable_kernel_timing")(eng2.handle, C.c_int(0))
+            kt = KernelTimes()
+            for k in range(3 + 10):
+                if k == 3:
+                    torch.cuda.synchronize()
+                    lib.fn("enable_kernel_timing")(eng2.handle, C.c_int(1))
+                    lib.fn("get_kernel_times")(eng2.handle, C.byref(kt), C.c_int(1))
+                if not args.no_flush:
+                    flush_buf.zero_()
+                bufs = DevRoundBufs(r2[k % 2].data_ptr(), p2[k % 2].data_ptr(), p2[k % 2].numel(), G2, st2.data_ptr(),
+                                    ex2.data_ptr())
+                if f(eng2.handle, C.byref(bufs), C.c_void_p(torch.cuda.current_stream().cuda_stream)) != 0:
+                    raise RuntimeError(lib.last_error())
+            torch.cuda.synchronize()
+            lib.fn("get_kernel_times")(eng2.handle, C.byref(kt), C.c_int(1))
+            lib.fn("enable_kernel_timing")(eng2.handle, C.c_int(0))
+            res[name] = kt.accept_ms / max(kt.launches, 1)
+        c2 = eng2.counters()
+        assert c2["decisions_made"] == 2 * 13 * G2
+        eng2.close()
+        del r2, p2, st2, ex2
+        km, ka = res["round_device"], res["round_device_phases"]
+        roofline_large = {
+            "workload": f"{G2} groups x {R} replicas, {P}-byte requests, one GPU (same kernels, batch fills the GPU)",
+            "k_round": {"kernel_ms": km, "decisions_per_sec": G2 / (km / 1e3),
+                        "achieved": G2 * b_act(R, P) / (km / 1e3) / 1e9, "frac": G2 * b_act(R, P) / (km / 1e3) / 1e9 / peak},
+            "k_accept": {"kernel_ms": ka, "achieved": G2 * R * b_acc(P) / (ka / 1e3) / 1e9,
+                         "frac": G2 * R * b_acc(P) / (ka / 1e3) / 1e9 / peak},
+            "unit": "GB/s", "peak": peak,
+        }
+
     # ---- e2e: public C-ABI calls with host (pinned) buffers -------------------------------
     # Headline: the pipelined form gpx_round_submit / gpx_round_wait with compact EXEC summaries -- every step
     # copies its request batch host->device and its result (one 8-byte summary per request + control block)
@@ -569,7 +615,7 @@ def main():
             "metric": metric, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": config, "roofline": roofline,
-            "roofline_accept": roofline_accept,
+            "roofline_accept": roofline_accept, "roofline_1m_groups": roofline_large,
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 2 * K,  # k_round + k_round_slow per step
             "p50_decide_latency_ms": float(np.median(step_ms)),
             "requests_per_sec": value, "wall_s_timed_region": t_wall,
