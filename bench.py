@@ -508,7 +508,8 @@ def main():
     # full EXEC records (R x 24 B per decision) is reported beside it.
     e2e = None
     if not args.skip_e2e:
-        from gigapaxos_b200.abi import RoundIO, exec_sum_dtype, PIPE_DEPTH, ROUND_COMPACT
+        from gigapaxos_b200.abi import (RoundIO, exec_sum_dtype, request_packed_dtype, PIPE_DEPTH, ROUND_COMPACT,
+                                        ROUND_PACKED_REQS)
         fn = lib.fn("round")
         h_reqs = [torch.from_numpy(b[0].view(np.uint8).copy()).pin_memory() for b in host_batches]
         h_pay = [torch.from_numpy(b[1].copy()).pin_memory() for b in host_batches]
@@ -548,11 +549,19 @@ def main():
         submit, wait = lib.fn("round_submit"), lib.fn("round_wait")
         h_sum = [torch.zeros(G * 8, dtype=torch.uint8).pin_memory() for _ in range(PIPE_DEPTH)]
         h_xtra = [torch.zeros(4096 * 24, dtype=torch.uint8).pin_memory() for _ in range(PIPE_DEPTH)]
+        # 16-byte packed requests (GPX_ROUND_PACKED_REQS): gid, payload_len, flags, req_id; payloads back to back
+        h_pk = []
+        for b in range(NB):
+            rq = host_batches[b][0]
+            pk = np.zeros(G, dtype=request_packed_dtype)
+            pk["gid"], pk["payload_len"], pk["flags"], pk["req_id"] = rq["gid"], rq["payload_len"], rq["flags"], rq["req_id"]
+            assert np.array_equal(rq["payload_off"], np.arange(G, dtype=np.uint32) * P)
+            h_pk.append(torch.from_numpy(pk.view(np.uint8).copy()).pin_memory())
         ios = []
         for d in range(PIPE_DEPTH * NB):
             b, q = d % NB, d % PIPE_DEPTH
-            ios.append(RoundIO(G, ROUND_COMPACT, h_reqs[b].data_ptr(), h_pay[b].data_ptr(), h_pay[b].numel(), None, None,
-                               h_sum[q].data_ptr(), h_xtra[q].data_ptr(), 4096))
+            ios.append(RoundIO(G, ROUND_COMPACT | ROUND_PACKED_REQS, h_pk[b].data_ptr(), h_pay[b].data_ptr(),
+                               h_pay[b].numel(), None, None, h_sum[q].data_ptr(), h_xtra[q].data_ptr(), 4096))
         tk = C.c_uint64(0)
         inflight = []
 
@@ -591,10 +600,11 @@ def main():
             sm = h_sum[q].numpy().view(exec_sum_dtype)
             assert np.all(sm["lane_mask"] == (1 << R) - 1) and np.all(sm["slot"] > 0), "summaries incomplete"
         e2e = {"value": world * G * K4 / dt_pipe, "unit": "decisions/s",
-               "h2d_bytes_per_step": int(G * 32 + h_pay[0].numel()),
+               "h2d_bytes_per_step": int(G * 16 + h_pay[0].numel()),
                "d2h_bytes_per_step": int(G * 8 + 32), "steps": K4, "ms_per_step": 1e3 * dt_pipe / K4,
-               "api": "gpx_round_submit / gpx_round_wait (include/gpx.h), GPX_ROUND_COMPACT: pinned host request + "
-                      "payload buffers in, one 8-byte EXEC summary per request out, up to %d rounds in flight; "
+               "api": "gpx_round_submit / gpx_round_wait (include/gpx.h), GPX_ROUND_PACKED_REQS | GPX_ROUND_COMPACT: "
+                      "pinned host buffers of 16-byte requests + payload in, one 8-byte EXEC summary per request out, "
+                      "up to %d rounds in flight; "
                       "wall clock around submit..wait of all steps" % PIPE_DEPTH,
                "sync_full": {"value": world * G * K3 / dt_sync, "unit": "decisions/s", "steps": K3,
                              "ms_per_step": 1e3 * dt_sync / K3, "h2d_bytes_per_step": int(G * 32 + h_pay[0].numel()),

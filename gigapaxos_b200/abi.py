@@ -46,6 +46,8 @@ exec_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("req_id", "<i8"), ("pay
 batch_ent_dtype = np.dtype([("req_id", "<i8"), ("len", "<u4"), ("flags", "<u4")])
 exec_sum_dtype = np.dtype([("slot", "<i4"), ("lane_mask", "u1"), ("flags", "u1"), ("nreq", "<u2")])
 ROUND_COMPACT = 1
+ROUND_PACKED_REQS = 2
+request_packed_dtype = np.dtype([("gid", "<u4"), ("payload_len", "<u2"), ("flags", "<u2"), ("req_id", "<i8")])
 PIPE_DEPTH = 4
 seg_hdr_dtype = np.dtype([("magic", "<u4"), ("type", "<u2"), ("lane", "<u2"), ("n_slots", "<u4"), ("n_valid", "<u4"),
                           ("payload_bytes", "<u8"), ("seq", "<u8"), ("ring_off", "<u8"), ("rec_bytes", "<u4"),
@@ -311,10 +313,11 @@ class Engine:
 
     # ---- pipelined rounds (gpx_round_submit / gpx_round_wait) ---------------------------
     def round_submit(self, reqs: np.ndarray, payload: np.ndarray, compact: bool = False, extra_cap: int = 4096,
-                     bufs: Optional[dict] = None) -> int:
+                     bufs: Optional[dict] = None, packed: bool = False) -> int:
         """Enqueue one round; returns its ticket.  `bufs` may carry caller-owned (e.g. page-locked) output arrays
         `status`, `exec`, `sum`, `extra`; otherwise they are allocated here and returned by round_wait."""
-        assert reqs.dtype == request_dtype and reqs.flags.c_contiguous and payload.dtype == np.uint8
+        assert reqs.dtype == (request_packed_dtype if packed else request_dtype)
+        assert reqs.flags.c_contiguous and payload.dtype == np.uint8
         n = len(reqs)
         b = dict(bufs or {})
         if compact:
@@ -323,7 +326,7 @@ class Engine:
             b.setdefault("status", np.zeros(max(n, 1), dtype=np.int32))
             b.setdefault("exec", np.zeros(max(n * self.n_lanes, 1), dtype=exec_dtype))
         b.setdefault("extra", np.zeros(max(extra_cap, 1), dtype=exec_dtype))
-        io = RoundIO(n, ROUND_COMPACT if compact else 0, reqs.ctypes.data, payload.ctypes.data if payload.size else None,
+        io = RoundIO(n, (ROUND_COMPACT if compact else 0) | (ROUND_PACKED_REQS if packed else 0), reqs.ctypes.data, payload.ctypes.data if payload.size else None,
                      payload.size, b["status"].ctypes.data if "status" in b else None,
                      b["exec"].ctypes.data if "exec" in b else None, b["sum"].ctypes.data if "sum" in b else None,
                      b["extra"].ctypes.data, len(b["extra"]))

@@ -72,6 +72,8 @@ struct gpx_engine {
     int32_t* d_status = nullptr;
     gpx_exec_rec* d_exec = nullptr;
     gpx_exec_sum* d_sum = nullptr;
+    gpx_request_packed* d_packed = nullptr;
+    uint32_t* d_bsum = nullptr;
     gpx_exec_rec* d_extra = nullptr;
     RoundCtl* d_ctl = nullptr;
     RoundCtl* h_ctl = nullptr; /* pinned */
@@ -1092,6 +1094,7 @@ static int pipe_init(gpx_engine* e) {
   for (auto& ps : e->pipe) {
     if ((rc = e->dalloc(&ps.d_reqs, N)) || (rc = e->dalloc(&ps.d_payload, (size_t)P)) ||
         (rc = e->dalloc(&ps.d_status, N)) || (rc = e->dalloc(&ps.d_exec, N * L)) || (rc = e->dalloc(&ps.d_sum, N)) ||
+        (rc = e->dalloc(&ps.d_packed, N)) || (rc = e->dalloc(&ps.d_bsum, N / GPX_UNPACK_PER_BLOCK + 2)) ||
         (rc = e->dalloc(&ps.d_extra, N * (L + 1))) || /* compact mode: the general path reports here */ (rc = e->dalloc(&ps.d_ctl, (size_t)1)))
       return rc;
     if (cudaHostAlloc((void**)&ps.h_ctl, sizeof(RoundCtl), cudaHostAllocDefault) != cudaSuccess)
@@ -1110,7 +1113,8 @@ int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket) {
   if (!e || !io || !ticket) return fail(GPX_EINVAL, "null argument");
   const uint32_t n = io->n;
   const bool compact = (io->flags & GPX_ROUND_COMPACT) != 0;
-  if (io->flags & ~GPX_ROUND_COMPACT) return fail(GPX_EINVAL, "unknown round flags");
+  const bool packed = (io->flags & GPX_ROUND_PACKED_REQS) != 0;
+  if (io->flags & ~(GPX_ROUND_COMPACT | GPX_ROUND_PACKED_REQS)) return fail(GPX_EINVAL, "unknown round flags");
   if (n && (!io->reqs || (!io->payload && io->payload_bytes))) return fail(GPX_EINVAL, "null argument");
   if (n && (compact ? !io->sum : (!io->status || !io->exec))) return fail(GPX_EINVAL, "null output buffer");
   int rc = check_batch(e, n, io->payload_bytes);
@@ -1130,13 +1134,23 @@ int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket) {
   if (n == 0) return GPX_OK;
   const uint32_t L = e->cfg.n_lanes;
   /* stream 1: inputs.  (the slot's previous round was waited for, so its buffers are free) */
-  CK(cudaMemcpyAsync(ps.d_reqs, io->reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, e->s_h2d));
+  if (packed)
+    CK(cudaMemcpyAsync(ps.d_packed, io->reqs, n * sizeof(gpx_request_packed), cudaMemcpyHostToDevice, e->s_h2d));
+  else
+    CK(cudaMemcpyAsync(ps.d_reqs, io->reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, e->s_h2d));
   if (io->payload_bytes)
     CK(cudaMemcpyAsync(ps.d_payload, io->payload, io->payload_bytes, cudaMemcpyHostToDevice, e->s_h2d));
   CK(cudaEventRecord(ps.ev_h2d, e->s_h2d));
   /* stream 2: the round (serialised with every other engine call on the engine's stream) */
   CK(cudaStreamWaitEvent(e->stream, ps.ev_h2d, 0));
   CK(cudaMemsetAsync(ps.d_ctl, 0, sizeof(RoundCtl), e->stream));
+  if (packed) { /* expand the 16-byte requests: payload_off = running sum of payload_len */
+    const uint32_t nb = cdiv(n, GPX_UNPACK_PER_BLOCK);
+    k_unpack_sums<<<nb, GPX_BLOCK, 0, e->stream>>>(ps.d_packed, n, ps.d_bsum);
+    k_unpack_scan<<<1, GPX_BLOCK, 0, e->stream>>>(ps.d_bsum, nb);
+    k_unpack_expand<<<nb, GPX_BLOCK, 0, e->stream>>>(e->S, ps.d_packed, n, ps.d_bsum, ps.d_reqs);
+    CK(cudaGetLastError());
+  }
   rc = launch_round(e, ps.d_reqs, ps.d_payload, pal, n, ps.d_status, ps.d_exec, e->stream, ps.d_ctl, ps.d_extra,
                     (uint32_t)std::min<uint64_t>((uint64_t)e->cfg.max_batch_recs * (L + 1), 0xffffffffull),
                     compact ? ps.d_sum : nullptr);

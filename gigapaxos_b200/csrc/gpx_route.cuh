@@ -181,3 +181,86 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_ingest(const __grid_constant__ De
     if (A.blob_base[c]) reinterpret_cast<gpx_accept_rec*>(r)->payload_off += (uint32_t)A.blob_base[c];
   }
 }
+
+/* ---- k_unpack: expand packed 16-byte requests (GPX_ROUND_PACKED_REQS) into gpx_request_rec; payload_off is the
+ * exclusive prefix sum of payload_len.  Three small launches: per-block sums, scan of the block sums, expand. ---- */
+#define GPX_UNPACK_PER_BLOCK 1024u /* requests per block: 256 threads x 4 */
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_w /*[GPX_BLOCK/32]*/, uint32_t* total) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) s_w[wid] = incl;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < GPX_BLOCK / 32; w++) {
+    const uint32_t x = s_w[w];
+    if (w < wid) base += x;
+    tot += x;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(GPX_BLOCK) k_unpack_sums(const gpx_request_packed* in, uint32_t n, uint32_t* bsum) {
+  __shared__ uint32_t s_w[GPX_BLOCK / 32];
+  const uint32_t b0 = blockIdx.x * GPX_UNPACK_PER_BLOCK + threadIdx.x * 4u;
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++)
+    if (b0 + k < n) v += in[b0 + k].payload_len;
+  uint32_t tot;
+  block_exclusive_scan(v, s_w, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(GPX_BLOCK) k_unpack_scan(uint32_t* bsum, uint32_t nb) {
+  __shared__ uint32_t s_w[GPX_BLOCK / 32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nb; base += GPX_BLOCK) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nb ? bsum[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan(v, s_w, &tot);
+    if (i < nb) bsum[i] = carry + ex;
+    carry += tot;
+  }
+}
+__global__ void __launch_bounds__(GPX_BLOCK) k_unpack_expand(const __grid_constant__ DevState S, const gpx_request_packed* in,
+                                                             uint32_t n, const uint32_t* bsum, gpx_request_rec* out) {
+  __shared__ uint32_t s_w[GPX_BLOCK / 32];
+  const uint32_t b0 = blockIdx.x * GPX_UNPACK_PER_BLOCK + threadIdx.x * 4u;
+  gpx_request_packed r[4];
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    r[k].payload_len = 0;
+    if (b0 + k < n) {
+      r[k] = in[b0 + k];
+      v += r[k].payload_len;
+    }
+  }
+  uint32_t tot;
+  uint32_t off = bsum[blockIdx.x] + block_exclusive_scan(v, s_w, &tot);
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++)
+    if (b0 + k < n) {
+      const uint32_t lane = (r[k].flags >> 8) & 0xfu;
+      gpx_request_rec q;
+      q.gid = r[k].gid;
+      q.flags = r[k].flags;
+      q.req_id = r[k].req_id;
+      q.payload_off = off;
+      q.payload_len = r[k].payload_len;
+      q.entry_node = lane < S.L ? S.lane_node[lane] : S.lane_node[0];
+      q.client = b0 + k;
+      const int4* qp = reinterpret_cast<const int4*>(&q);
+      st256(&out[b0 + k], qp[0], qp[1]);
+      off += r[k].payload_len;
+    }
+}

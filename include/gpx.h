@@ -373,9 +373,21 @@ int gpx_round_phases(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, con
  *                          Replicable.execute from its own copy of the request.  lane_mask == 0: `slot` is
  *                          the request's status (slot number or GPX_RS_* code) and every execution it caused
  *                          is a full record in the extra queue.  EXEC records of one call are applied per
- *                          (lane, group) in slot order. */
+ *                          (lane, group) in slot order.
+ *   GPX_ROUND_PACKED_REQS  (input) `reqs` holds n gpx_request_packed (16 B) instead of gpx_request_rec (32 B):
+ *                          the payloads lie back to back in request order (payload_off = running sum of
+ *                          payload_len), entry_node = the node of the entry lane, client = the request
+ *                          index.  Halves the host->device bytes of a batch; the engine expands the records
+ *                          on the device (k_unpack: block sums, scan, expand). */
 #define GPX_PIPE_DEPTH 4
 #define GPX_ROUND_COMPACT 1u
+#define GPX_ROUND_PACKED_REQS 2u
+typedef struct gpx_request_packed {
+  uint32_t gid;
+  uint16_t payload_len;
+  uint16_t flags;  /* as gpx_request_rec.flags: bit0 GPX_F_STOP, bits 8..11 entry lane */
+  int64_t req_id;
+} gpx_request_packed;
 typedef struct gpx_exec_sum {
   int32_t slot;       /* decided slot (lane_mask != 0) or the request's status */
   uint8_t lane_mask;  /* lanes that executed the request in order */
@@ -384,8 +396,8 @@ typedef struct gpx_exec_sum {
 } gpx_exec_sum;
 typedef struct gpx_round_io {
   uint32_t n;
-  uint32_t flags;              /* 0 or GPX_ROUND_COMPACT */
-  const gpx_request_rec* reqs; /* [n] host */
+  uint32_t flags;              /* GPX_ROUND_COMPACT | GPX_ROUND_PACKED_REQS */
+  const gpx_request_rec* reqs; /* [n] host (gpx_request_packed[n] with GPX_ROUND_PACKED_REQS) */
   const uint8_t* payload;      /* host */
   uint64_t payload_bytes;
   int32_t* status;             /* [n] out, full mode */

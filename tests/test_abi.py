@@ -53,10 +53,10 @@ def test_struct_sizes_match_header():
     code = r"""
     #include "gpx.h"
     #include <stdio.h>
-    int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(gpx_request_rec), sizeof(gpx_accept_rec),
+    int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(gpx_request_rec), sizeof(gpx_accept_rec),
       sizeof(gpx_decision_rec), sizeof(gpx_accept_reply_rec), sizeof(gpx_exec_rec), sizeof(gpx_log_seg_hdr),
       sizeof(gpx_row), sizeof(gpx_group_desc), sizeof(gpx_patch_rec), sizeof(gpx_config), sizeof(gpx_counters),
-      sizeof(gpx_exec_sum), sizeof(gpx_round_io));}
+      sizeof(gpx_exec_sum), sizeof(gpx_round_io), sizeof(gpx_request_packed));}
     """
     import subprocess
     import tempfile
@@ -69,6 +69,7 @@ def test_struct_sizes_match_header():
     assert sizes[:9] == [32, 48, 32, 32, 24, 64, abi.row_dtype.itemsize, abi.group_desc_dtype.itemsize, 32]
     assert sizes[9] == C.sizeof(abi.Config) and sizes[10] == C.sizeof(abi.Counters)
     assert sizes[11] == abi.exec_sum_dtype.itemsize == 8 and sizes[12] == C.sizeof(abi.RoundIO)
+    assert sizes[13] == abi.request_packed_dtype.itemsize == 16
 
 
 def test_config_defaults_match_reference_defaults(cuda_lib, oracle_lib):

@@ -129,3 +129,38 @@ def test_pipeline_depth_and_order_are_enforced(cuda_lib):
         first = int(st[0]) if first is None else first
         assert np.all(st == first + k)  # rounds run in submission order
     assert eg.dump_rows(np.arange(64), 0)["acc_slot"].tolist() == [first + abi.PIPE_DEPTH] * 64
+
+
+def test_packed_requests(oracle_lib, cuda_lib):
+    """GPX_ROUND_PACKED_REQS: 16-byte requests, payloads back to back; the device expands them (k_unpack) to the
+    records the oracle is given explicitly"""
+    G, rounds = 700, 6
+    eo, eg = both(oracle_lib, cuda_lib, max_groups=G, max_batch_recs=8192, max_batch_payload=1 << 20,
+                  checkpoint_interval=5)
+    d = group_descs(G)
+    eo.create_groups(d)
+    eg.create_groups(d)
+    rng = np.random.default_rng(29)
+    nodes = [100, 101, 102]
+    for r in range(rounds):
+        counts = rng.choice([0, 1, 1, 1, 2, 5], size=G)
+        gids = np.repeat(np.arange(G), counts).astype(np.uint32)
+        n = len(gids)  # > 1024 so the scan crosses unpack blocks
+        lens = rng.integers(0, 70, size=n).astype(np.uint32)
+        lane = int(rng.integers(0, 3))
+        packed = np.zeros(n, dtype=abi.request_packed_dtype)
+        packed["gid"], packed["payload_len"] = gids, lens
+        packed["flags"] = (lane << 8) | np.where(rng.random(n) < (0.01 if r > 2 else 0), abi.F_STOP, 0)
+        packed["req_id"] = rng.integers(1, 1 << 62, size=n)
+        pay = rng.integers(48, 123, size=int(lens.sum()), dtype=np.uint8)
+        full = np.zeros(n, dtype=abi.request_dtype)
+        full["gid"], full["flags"], full["req_id"], full["payload_len"] = gids, packed["flags"], packed["req_id"], lens
+        full["payload_off"] = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+        full["entry_node"] = nodes[lane]
+        full["client"] = np.arange(n, dtype=np.uint32)
+        so, xo, ex_o = eo.round(full, pay, extra_cap=3 * n + 64)
+        res = eg.round_wait(eg.round_submit(packed, pay, packed=True, extra_cap=3 * n + 64))
+        assert np.array_equal(so, res["status"])
+        assert sorted(exec_tuples(xo) + exec_tuples(ex_o)) == sorted(exec_tuples(res["exec"]) + exec_tuples(res["extra"]))
+    compare_state(eo, eg, np.arange(G), 3)
+    compare_logs(eo, eg, 3)
