@@ -580,7 +580,19 @@ extern "C++" {
 template <int L, int LP>
 static void launch_round_t(uint32_t grid, uint32_t slow_grid, cudaStream_t st, const DevState& S, const RoundArgs& RA) {
   k_round<L, LP><<<grid, GPX_BLOCK, 0, st>>>(S, RA);
-  k_round_slow<L, LP><<<slow_grid, GPX_BLOCK, 0, st>>>(S, RA);
+  { /* programmatic dependent launch: k_round_slow's launch latency hides behind k_round */
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(slow_grid);
+    cfg.blockDim = dim3(GPX_BLOCK);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_round_slow<L, LP>, S, RA);
+  }
 }
 }
 static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload, uint64_t pal,
