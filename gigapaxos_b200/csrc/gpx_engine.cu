@@ -62,6 +62,7 @@ struct gpx_engine {
   uint8_t* d_out_mask = nullptr;
   std::vector<uint8_t> h_out_mask;
   RoundCtl* d_ctl = nullptr;
+  RoundCtl* d_rctl = nullptr; /* [2] the round kernels' own block: [0] working (zero between rounds), [1] published */
   RoundCtl* h_ctl = nullptr; /* pinned */
   void* d_misc = nullptr;    /* group-management staging */
   size_t misc_bytes = 0;
@@ -270,6 +271,8 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   TRY(e->dalloc(&e->d_copy_dst, N));
   TRY(e->dalloc(&e->d_out_mask, N));
   TRY(e->dalloc(&e->d_ctl, (size_t)1));
+  TRY(e->dalloc(&e->d_rctl, (size_t)2));
+  cudaMemset(e->d_rctl, 0, 2 * sizeof(RoundCtl));
 #undef TRY
   if (cudaHostAlloc((void**)&e->h_ctl, sizeof(RoundCtl), cudaHostAllocDefault) != cudaSuccess) {
     gpx_engine_destroy(e);
@@ -599,7 +602,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
                         uint32_t n, int32_t* d_status, gpx_exec_rec* d_exec, cudaStream_t st,
                         RoundCtl* d_ctl = nullptr, gpx_exec_rec* d_extra = nullptr, uint32_t extra_cap = 0,
                         gpx_exec_sum* d_sum = nullptr) {
-  if (!d_ctl) d_ctl = e->d_ctl;
+  if (!d_ctl) d_ctl = e->d_rctl; /* [0] working block (zero on entry, re-zeroed by k_round_slow), [1] published */
   if (!d_extra) {
     d_extra = e->d_extra;
     extra_cap = e->extra_cap;
@@ -614,6 +617,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.P.copy_tab = e->d_copy_tab;
   RA.P.copy_dst = e->d_copy_dst;
   RA.P.ctl = d_ctl;
+  RA.ctl_out = d_ctl + 1;
   RA.sum = d_sum;
   RA.A.n_max = n;
   RA.A.blob0 = d_payload;
@@ -658,8 +662,8 @@ static int check_batch(gpx_engine* e, uint32_t n, uint64_t payload_bytes) {
   if (payload_bytes > e->cfg.max_batch_payload) return fail(GPX_ERANGE, "payload_bytes > max_batch_payload");
   return GPX_OK;
 }
-static int fetch_ctl(gpx_engine* e) {
-  CK(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->stream));
+static int fetch_ctl(gpx_engine* e, const RoundCtl* src = nullptr) {
+  CK(cudaMemcpyAsync(e->h_ctl, src ? src : e->d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return GPX_OK;
 }
@@ -848,7 +852,7 @@ static int round_on_stream(gpx_engine* e, bool fused, const gpx_request_rec* d_r
   const uint64_t pal = (payload_bytes + 15) & ~15ull;
   const uint32_t L = e->cfg.n_lanes;
   const bool tm = e->timing;
-  CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st));
+  if (!fused) CK(cudaMemsetAsync(e->d_ctl, 0, sizeof(RoundCtl), st)); /* the fused kernels keep their own block zero */
   if (tm) cudaEventRecord(e->ev[0], st);
   if (fused) { /* the whole round is ONE kernel */
     int rc1 = launch_round(e, d_reqs, d_payload, pal, n, d_status, d_exec, st);
@@ -918,7 +922,7 @@ static int round_host(gpx_engine* e, bool fused, uint32_t n, const gpx_request_r
   rc = round_on_stream(e, fused, e->d_reqs, e->d_payload, payload_bytes, n, e->d_status, e->d_exec, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(status, e->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  rc = fetch_ctl(e);
+  rc = fetch_ctl(e, fused ? e->d_rctl + 1 : nullptr);
   if (rc) return rc;
   /* fused: one EXEC row per REQUEST index (VOID where the request carries no ACCEPT); phases: one per DECISION */
   const uint32_t rows = fused ? n : e->h_ctl->n_decisions;
@@ -1107,10 +1111,11 @@ static int pipe_init(gpx_engine* e) {
     if ((rc = e->dalloc(&ps.d_reqs, N)) || (rc = e->dalloc(&ps.d_payload, (size_t)P)) ||
         (rc = e->dalloc(&ps.d_status, N)) || (rc = e->dalloc(&ps.d_exec, N * L)) || (rc = e->dalloc(&ps.d_sum, N)) ||
         (rc = e->dalloc(&ps.d_packed, N)) || (rc = e->dalloc(&ps.d_bsum, N / GPX_UNPACK_PER_BLOCK + 2)) ||
-        (rc = e->dalloc(&ps.d_extra, N * (L + 1))) || /* compact mode: the general path reports here */ (rc = e->dalloc(&ps.d_ctl, (size_t)1)))
+        (rc = e->dalloc(&ps.d_extra, N * (L + 1))) || /* compact mode: the general path reports here */ (rc = e->dalloc(&ps.d_ctl, (size_t)2)))
       return rc;
     if (cudaHostAlloc((void**)&ps.h_ctl, sizeof(RoundCtl), cudaHostAllocDefault) != cudaSuccess)
       return fail(GPX_ENOMEM, "cudaHostAlloc");
+    CK(cudaMemset(ps.d_ctl, 0, 2 * sizeof(RoundCtl))); /* [0] working, [1] published by k_round_slow */
     CK(cudaEventCreateWithFlags(&ps.ev_h2d, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ps.ev_k, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ps.ev_d2h, cudaEventDisableTiming));
@@ -1155,7 +1160,6 @@ int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket) {
   CK(cudaEventRecord(ps.ev_h2d, e->s_h2d));
   /* stream 2: the round (serialised with every other engine call on the engine's stream) */
   CK(cudaStreamWaitEvent(e->stream, ps.ev_h2d, 0));
-  CK(cudaMemsetAsync(ps.d_ctl, 0, sizeof(RoundCtl), e->stream));
   if (packed) { /* expand the 16-byte requests: payload_off = running sum of payload_len */
     const uint32_t nb = cdiv(n, GPX_UNPACK_PER_BLOCK);
     k_unpack_sums<<<nb, GPX_BLOCK, 0, e->stream>>>(ps.d_packed, n, ps.d_bsum);
@@ -1170,7 +1174,7 @@ int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket) {
   CK(cudaEventRecord(ps.ev_k, e->stream));
   /* stream 3: results */
   CK(cudaStreamWaitEvent(e->s_d2h, ps.ev_k, 0));
-  CK(cudaMemcpyAsync(ps.h_ctl, ps.d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->s_d2h));
+  CK(cudaMemcpyAsync(ps.h_ctl, ps.d_ctl + 1, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->s_d2h));
   if (compact) {
     CK(cudaMemcpyAsync(io->sum, ps.d_sum, n * sizeof(gpx_exec_sum), cudaMemcpyDeviceToHost, e->s_d2h));
   } else {

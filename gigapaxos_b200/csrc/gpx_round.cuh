@@ -32,10 +32,22 @@ struct RoundArgs {
   unsigned long long blob1_res; /* payload-area bytes reserved for constructed blobs */
   uint32_t* todo;               /* request indices of the runs left to k_round_slow */
   uint32_t* n_todo;
+  RoundCtl* ctl_out;            /* k_round_slow publishes the round's counters here and re-zeroes P.ctl for the next
+                                 * round (no memset between rounds) */
   gpx_exec_sum* sum;            /* compact output mode (GPX_ROUND_COMPACT): one summary per request index instead of
                                  * n_lanes EXEC rows; everything that is not the plain in-order case goes to the
                                  * extra queue.  null = full EXEC rows */
 };
+
+__device__ __forceinline__ void publish_ctl(const RoundArgs& RA) {
+  int4* w = reinterpret_cast<int4*>(RA.P.ctl);
+  int4* o = reinterpret_cast<int4*>(RA.ctl_out);
+  static_assert(sizeof(RoundCtl) == 32, "two int4");
+  o[0] = w[0];
+  o[1] = w[1];
+  w[0] = make_int4(0, 0, 0, 0);
+  w[1] = make_int4(0, 0, 0, 0);
+}
 
 __device__ __forceinline__ void store_sum(gpx_exec_sum* dst, int slot, uint32_t lane_mask, uint32_t flags, uint32_t nreq) {
   *reinterpret_cast<int2*>(dst) = make_int2(slot, (int)(lane_mask | (flags << 8) | (nreq << 16)));
@@ -626,7 +638,10 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
       const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
       S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
       S.seg_seq[threadIdx.x] += 2ull;
-      if (threadIdx.x == 0) atomicAdd(&S.ctr[C_KERNEL_LAUNCHES], 1ull);
+      if (threadIdx.x == 0) {
+        atomicAdd(&S.ctr[C_KERNEL_LAUNCHES], 1ull);
+        publish_ctl(RA); /* n_todo is 0 and stays 0: the other blocks only read that */
+      }
     }
     return;
   }
@@ -670,5 +685,8 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
     S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
     S.seg_seq[threadIdx.x] += 2ull;
   }
-  if (s_last && threadIdx.x == 0) S.tickets[5] = 0;
+  if (s_last && threadIdx.x == 0) {
+    S.tickets[5] = 0;
+    publish_ctl(RA);
+  }
 }
