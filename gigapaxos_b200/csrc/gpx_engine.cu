@@ -582,7 +582,7 @@ static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uin
 extern "C++" {
 template <int L, int LP>
 static void launch_round_t(uint32_t grid, uint32_t slow_grid, cudaStream_t st, const DevState& S, const RoundArgs& RA) {
-  k_round<L, LP><<<grid, GPX_BLOCK, 0, st>>>(S, RA);
+  k_round<L, LP><<<grid, GPX_RBLOCK, 0, st>>>(S, RA);
   { /* programmatic dependent launch: k_round_slow's launch latency hides behind k_round */
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -636,7 +636,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.blob1_res = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
   RA.A.blob1_bytes = RA.blob1_res;
   const uint32_t L = e->cfg.n_lanes;
-  const uint32_t teams_per_block = (GPX_BLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
+  const uint32_t teams_per_block = (GPX_RBLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
   const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
   const uint32_t slow_grid = std::min<uint32_t>(grid, 2u * (uint32_t)e->n_sms);
   switch (L) {
