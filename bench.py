@@ -445,6 +445,12 @@ def main():
         "kernel_ms_all": {"k_round": act_ms},
     }
     roofline["frac"] = roofline["achieved"] / peak
+    # dram__bytes_read.sum + dram__bytes_write.sum of one k_round launch, from the committed `ncu --set full` captures
+    # (profiles/r1f_k_round_*_ncu_full_summary.txt); a number measured under ncu, so it is a constant here
+    ncu_traffic = {("cfg2", 100_000, 1): 18_508_800 + 4_371_456, ("1m1b", 1_000_000, 1): 184_884_992 + 430_979_328}
+    roofline["traffic"] = ncu_traffic.get((args.workload, G, P))
+    roofline["traffic_source"] = ("profiles/r1f_k_round_%s_ncu_full_summary.txt" % ("cfg2" if G == 100_000 else "1m")
+                                  if roofline["traffic"] else None)
     roofline_accept = {
         "kernel": "k_accept (stand-alone accept-batch kernel of the phase-by-phase pipeline, north_star kernel)",
         "bound": "hbm", "achieved": acc_bytes / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else 0.0, "peak": peak,
