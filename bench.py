@@ -266,7 +266,21 @@ def cpu_decisions_per_sec(G, R, P, budget_s, threads):
 
 
 # --------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line of the contract goes to the real stdout; everything else that libraries write to fd 1
+    (e.g. NCCL's version banner) has been diverted to stderr"""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -322,10 +336,10 @@ def main():
                                        f"Java path; reference JVM unavailable in this image), {dt:.1f} s"},
             "e2e": {"value": v, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    os.environ.pop("NCCL_DEBUG", None)  # (stdout is diverted anyway: rank 0 prints ONE JSON line)
     import torch
     import torch.distributed as dist
 
@@ -636,7 +650,7 @@ def main():
             "p50_decide_latency_ms": float(np.median(step_ms)),
             "requests_per_sec": value, "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -761,7 +775,7 @@ def run_spread(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
             "gpu_launches": K * (2 + 3 + 2 + N + 1 + 2) * len(local),
             "p50_decide_latency_ms": float(np.median(step_ms)),
         }
-        print(json.dumps(line))
+        emit(line)
     for nd in nodes:
         nd.engine.close()
 
