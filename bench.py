@@ -475,6 +475,10 @@ def main():
         "phase_pipeline_decisions_per_sec": G / ((kp["propose"] + acc_ms + kp["tally"] + kp["commit"]) / 1e3),
     }
     roofline_accept["frac"] = roofline_accept["achieved"] / peak
+    roofline_accept["traffic"] = {("cfg2", 100_000, 1): 20_956_416 + 2_864_384,
+                                  ("1m1b", 1_000_000, 1): 209_124_608 + 301_923_328}.get((args.workload, G, P))
+    roofline_accept["traffic_source"] = ("profiles/r1f_k_accept_%s_ncu_full_summary.txt" % ("cfg2" if G == 100_000 else "1m")
+                                         if roofline_accept["traffic"] else None)
 
     # ---- the same kernels on a batch that fills the GPU (context for the latency-bound 100K-group step) --------
     roofline_large = None
