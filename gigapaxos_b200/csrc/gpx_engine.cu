@@ -638,7 +638,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   const uint32_t L = e->cfg.n_lanes;
   const uint32_t teams_per_block = (GPX_RBLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
   const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
-  const uint32_t slow_grid = std::min<uint32_t>(grid, 2u * (uint32_t)e->n_sms);
+  const uint32_t slow_grid = std::min<uint32_t>(grid, (uint32_t)e->n_sms); /* grid-stride over the todo list */
   switch (L) {
     case 1: launch_round_t<1, 1>(grid, slow_grid, st, e->S, RA); break;
     case 2: launch_round_t<2, 2>(grid, slow_grid, st, e->S, RA); break;
