@@ -29,6 +29,7 @@ F_STOP, F_VOID, F_ACCEPT, F_DECISION, F_META, F_CKPT, F_LOGGED, F_NACK, F_EXTRA 
 RS_BATCHED, RS_FORWARD, RS_REFUSED_STOP, RS_BACKPRESSURE, RS_DROPPED, RS_PREACTIVE, RS_NOCOORD = (
     -1, -2, -3, -4, -5, -6, -7)
 INIT_BATCH, INIT_DEFAULT = 0, 1
+GF_OVERFLOW, GF_NEEDS_SYNC, GF_NOT_CAUGHT_UP = 1, 2, 4  # gpx_get_group_flags bits
 PATCH_SET_BALLOT, PATCH_JUMP_SLOT, PATCH_SET_STATE, PATCH_INSTALL_COORD, PATCH_RESIGN_COORD, PATCH_SET_GC = (
     1, 2, 3, 4, 5, 6)
 SEG_MAGIC = 0x53585047

@@ -1416,7 +1416,26 @@ __global__ void k_get_flags(const __grid_constant__ DevState S, uint32_t lane, c
                             uint8_t* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = gids[i] < S.G ? (uint8_t)GPX_AUX_FLAGS(S.acc_aux[row_idx(S, lane, gids[i])]) : 0;
+  if (gids[i] >= S.G) {
+    out[i] = 0;
+    return;
+  }
+  const uint32_t gid = gids[i];
+  const size_t ri = row_idx(S, lane, gid);
+  const uint32_t aux = S.acc_aux[ri];
+  /* PaxosAcceptor.caughtUp :452-459 / PCS.caughtUp :758 */
+  bool busy = GPX_AUX_PRESENT(aux) != 0; /* committedRequests not empty */
+  const int4 crow = S.coord_row[ri];
+  if (((unsigned)crow.w & GPX_CF_EXISTS) && ((unsigned)crow.w >> 8)) busy = true; /* myProposals not empty */
+  if (!S.journaling) { /* acceptedProposals not empty (journaling: accepted pvalues come from the log) */
+    const int gc = S.acc_row[ri].w;
+    for (uint32_t w = 0; w < S.W; w++) {
+      const size_t ai = 2 * win_idx(S, lane, w, gid);
+      const int4 a0 = S.acc_win[ai], a1 = S.acc_win[ai + 1];
+      if (((unsigned)a1.w & GPX_ENT_VALID) && jsub(a0.x, gc) > 0) busy = true;
+    }
+  }
+  out[i] = (uint8_t)(GPX_AUX_FLAGS(aux) | (busy ? GPX_GF_NOT_CAUGHT_UP_BIT : 0u));
 }
 
 /* ============================== digests (DIGEST_REQUESTS) ============================== */

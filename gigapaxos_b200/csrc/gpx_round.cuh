@@ -2,22 +2,26 @@
  * gpx_round.cuh -- k_round: one launch advances every group of a request batch through a whole Paxos
  * round (RequestBatcher -> propose -> accept x R -> tally -> commit x R) for co-located replicas.
  *
- * Work mapping: a TEAM of LP = L threads (adjacent lanes of one warp, 32/LP teams per warp) owns one
- * request index; team thread `sub` < L is replica lane `sub` of the group.  The team of the first request of
- * a run of equal gids processes the run (the reference's per-instance `synchronized`).
- *   propose  computed redundantly by every team thread from the same loads (broadcast loads, no shuffles):
- *            PISM.handleProposal :818-888, PCS.propose :233-263, getMedianMinus :867-875
- *   accept   thread `sub` runs PISM.handleAccept :1080-1166 for its own lane (accept_lane), writes its lane's
- *            log image and copies the blob into its lane's log ring
- *   tally    the L ACCEPT_REPLYs are exchanged with __shfl_sync inside the team; every thread runs
- *            PaxosCoordinator.handleAcceptReply :210-250 on register copies of the coordinator row, the
- *            proposal and nodeSlotNumbers (vote set = bitmask, majority = __popc), so the DECISION is known
- *            to all lanes without touching memory; thread 0 of the team writes the coordinator state back
- *   commit   thread `sub` runs handleBatchedCommit :1480 / extractExecuteAndCheckpoint :1619 for its lane
- * In this fast path the ACCEPT record, the replies, the DECISION and the proposal never touch HBM; each
- * acceptor row is read and written once.  Anything unusual (several requests of a group in the batch,
- * outstanding proposals, a pre-active or missing coordinator, remote members) takes the general path:
- * thread 0 runs propose_run / tally_reply against memory and broadcasts the decision to the team.
+ * Work mapping: a TEAM of L threads (adjacent lanes of one warp, 32/L teams per warp) owns one request index;
+ * team thread `sub` is replica lane `sub` of the group.  Two kernels:
+ *
+ *   k_round       the in-order case, straight-line predicated code.  Every thread loads ITS lane's acceptor row,
+ *                 aux word and coordinator row (+ the group's meta word and the first payload chunk); the entry
+ *                 lane's and the coordinator lane's rows reach the team by full-warp __shfl_sync
+ *                 (PISM.handleProposal :818-888, PCS.propose :233-263); a team vote (__ballot_sync) checks that every
+ *                 lane is the plain case of PISM.handleAccept :1080-1166 (same ballot, next slot, nothing there);
+ *                 the L ACCEPT_REPLYs (maxCheckpointedSlot :1139-1143) are exchanged by shuffles and tallied in
+ *                 registers (recordSlotNumber :809-825, getMedianMinus :867-875, majority at reply L/2); each thread
+ *                 then writes only the durable outputs of its lane (log image + blob, decision image, EXEC record or
+ *                 summary, window entry, acceptor row) and thread 0 the status, coordinator row and DECISION.
+ *                 The ACCEPT record, the replies and the proposal never exist in memory.
+ *   k_round_slow  everything else (several requests of a group in the batch -> one batched slot, STOP, outstanding
+ *                 proposals, a pre-active / missing / remote coordinator, an occupied window entry, NACKs): teams
+ *                 that cannot take the in-order path append their request index to a todo list; this kernel runs
+ *                 the general code over it (thread 0 of the team: propose_run / tally_reply against memory, decision
+ *                 broadcast to the lanes by shuffles, accept_lane / commit per lane), publishes the ring heads and
+ *                 the round's control block.  It is launched behind k_round with programmatic stream
+ *                 serialization and returns at once when the list is empty.
  *
  * Semantics are those of gpx_propose followed by gpx_handle_accepts_fused (checked by the test-suite); record,
  * image and EXEC indices are REQUEST indices (holes are VOID).
@@ -57,7 +61,7 @@ __device__ __forceinline__ void store_sum(gpx_exec_sum* dst, int slot, uint32_t 
 #define GPX_RBLOCK 128 /* threads per block of the fast round kernel: finer-grained waves than 256 (measured +3%) */
 #endif
 #ifndef GPX_ROUND_MINB
-#define GPX_ROUND_MINB 5 /* the fast kernel fits 48 registers without spills: 5 CTAs x 256 threads per SM */
+#define GPX_ROUND_MINB 5 /* 48 registers per thread = 1,280 resident threads per SM; measured optimum (40 and 64 are slower) */
 #endif
 
 /* PCS.getMedianMinus :867-875 on a register array (R <= LP <= 8) */

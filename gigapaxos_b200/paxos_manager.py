@@ -94,6 +94,67 @@ class RequestPacket:
 
 
 @dataclass
+class HotRestoreInfo:
+    """paxosutil/HotRestoreInfo.java:40-120: the state a paused instance is rebuilt from, and its '|'-separated
+    string form (the value of the pause table, SQLPaxosLogger.pause)."""
+    paxosID: str
+    version: int
+    members: List[int]
+    accSlot: int
+    accBallot: tuple  # (ballotNumber, coordinatorID)
+    accGCSlot: int
+    coordBallot: Optional[tuple]  # None unless this node is an ACTIVE coordinator (getBallotIfActive :400)
+    nextProposalSlot: int  # -1 unless active (getNextProposalSlotIfActive :375)
+    nodeSlots: Optional[List[int]]
+
+    @staticmethod
+    def _ints(a) -> str:  # Util.arrayOfIntToString :241-248
+        return "[" + ",".join(str(int(x)) for x in a) + "]"
+
+    def __str__(self) -> str:  # HotRestoreInfo.toString :88-107
+        b = lambda t: f"{t[0]}:{t[1]}"  # Ballot.toString :105
+        return "|".join([self.paxosID, str(self.version), self._ints(self.members), str(self.accSlot),
+                         b(self.accBallot), str(self.accGCSlot), b(self.coordBallot) if self.coordBallot else "null",
+                         str(self.nextProposalSlot), self._ints(self.nodeSlots) if self.nodeSlots is not None else "null"])
+
+    @classmethod
+    def parse(cls, ser: str) -> "HotRestoreInfo":  # HotRestoreInfo(String) :71-85
+        t = ser.split("|")
+        ints = lambda x: [int(v) for v in x.replace("[", "").replace("]", "").replace(" ", "").split(",")]
+        bal = lambda x: tuple(int(v) for v in x.split(":"))
+        return cls(t[0], int(t[1]), ints(t[2]), int(t[3]), bal(t[4]), int(t[5]), bal(t[6]) if t[6] != "null" else None,
+                   int(t[7]), ints(t[8]) if t[8] != "null" else None)
+
+    @classmethod
+    def from_row(cls, paxosID: str, row) -> "HotRestoreInfo":
+        """PISM.tryPause :2004-2025 from one dumped engine row (gpx_row)"""
+        n = int(row["n_members"])
+        active = bool(row["coord_exists"]) and bool(row["coord_active"])
+        return cls(paxosID, int(row["version"]), [int(x) for x in row["members"][:n]], int(row["acc_slot"]),
+                   (int(row["acc_bnum"]), int(row["acc_bcoord"])), int(row["acc_gc_slot"]),
+                   (int(row["coord_bnum"]), int(row["coord_bcoord"])) if active else None,
+                   int(row["next_proposal_slot"]) if active else -1,
+                   [int(x) for x in row["node_slots"][:n]] if active else None)
+
+    def to_row(self, gid: int, lane: int, my_node: int) -> np.ndarray:
+        """PISM.hotRestore :677-690: the acceptor comes back ACTIVE; the coordinator only at the node it names"""
+        r = np.zeros(1, dtype=abi.row_dtype)
+        n = len(self.members)
+        r["gid"], r["lane"], r["version"] = gid, lane, self.version
+        r["acc_slot"], r["acc_bnum"], r["acc_bcoord"], r["acc_gc_slot"] = (self.accSlot, self.accBallot[0],
+                                                                            self.accBallot[1], self.accGCSlot)
+        r["state"] = abi.ST_ACTIVE_1  # paxosState.setActive(): no recovery
+        r["n_members"] = n
+        r["members"][0, :n] = self.members
+        if self.coordBallot is not None and self.coordBallot[1] == my_node:
+            r["coord_exists"], r["coord_active"] = 1, 1
+            r["coord_bnum"], r["coord_bcoord"] = self.coordBallot
+            r["next_proposal_slot"] = self.nextProposalSlot
+            r["node_slots"][0, :n] = self.nodeSlots
+        return r
+
+
+@dataclass
 class _Instance:
     gid: int
     version: int
@@ -120,6 +181,7 @@ class PaxosManager:
         self.checkpoints: List[tuple] = []
         self.num_decisions = 0
         self.slow_path: List[tuple] = []
+        self.paused: Dict[str, List[str]] = {}  # paxosID -> HotRestoreInfo string per lane (the pause table)
 
     # ---- instance management ------------------------------------------------------------
     def _alloc_gid(self) -> int:
@@ -177,6 +239,40 @@ class PaxosManager:
         self._release(paxosID)
         return True
 
+    # ---- pause / unpause (PaxosManager.pause :2284-2330, unpause :2370-2437) ------------------------------
+    def pause(self, paxosID: str) -> bool:
+        """Move an idle instance out of the engine: PISM.tryPause :2004-2035 succeeds only when every replica is
+        caught up (nothing committed-but-unexecuted, no outstanding proposal); the rows are kept as
+        HotRestoreInfo strings (the pause table) and the gid is freed."""
+        inst = self.instances.get(paxosID)
+        if inst is None or inst.stopped or self.queue.get(paxosID):
+            return False
+        gids = np.array([inst.gid], dtype=np.uint32)
+        for lane in range(self.engine.n_lanes):
+            if int(self.engine.group_flags(gids, lane)[0]) & abi.GF_NOT_CAUGHT_UP:
+                return False
+        hris = [str(HotRestoreInfo.from_row(paxosID, self.engine.dump_rows(gids, lane)[0]))
+                for lane in range(self.engine.n_lanes)]
+        self.paused[paxosID] = hris
+        self._release(paxosID)  # forceStop + removal from pinstances
+        return True
+
+    def unpause(self, paxosID: str) -> bool:
+        """PaxosManager.unpause :2370: rebuild the instance from its HotRestoreInfo (PISM.hotRestore :677-690)."""
+        hris = self.paused.pop(paxosID, None)
+        if hris is None or paxosID in self.instances:
+            return False
+        infos = [HotRestoreInfo.parse(h) for h in hris]
+        gid = self._alloc_gid()
+        self.instances[paxosID] = _Instance(gid, infos[0].version, list(infos[0].members))
+        self.gid_name[gid] = paxosID
+        rows = np.concatenate([h.to_row(gid, lane, self.nodes[lane]) for lane, h in enumerate(infos)])
+        self.engine.load_rows(rows)
+        return True
+
+    def isPaused(self, paxosID: str) -> bool:
+        return paxosID in self.paused
+
     def isStopped(self, paxosID: str) -> bool:
         inst = self.instances.get(paxosID)
         return inst is None or inst.stopped
@@ -191,6 +287,8 @@ class PaxosManager:
         """PaxosManager.propose :1214-1243: returns the request id, or None when the instance does not
         exist (or the version does not match, PISM :441-447)."""
         inst = self.instances.get(paxosID)
+        if inst is None and paxosID in self.paused and self.unpause(paxosID):  # PaxosManager.getInstance :2453 -> unpause
+            inst = self.instances.get(paxosID)
         if inst is None or (version is not None and version != inst.version):
             return None
         rid = self.next_request_id

@@ -431,6 +431,10 @@ int gpx_reset_counters(gpx_engine* e);
  * host runs PISM.syncLongDecisionGaps :1550 / requestMissingDecisions) */
 #define GPX_GF_OVERFLOW_BIT 1u
 #define GPX_GF_NEEDS_SYNC_BIT 2u
+/* computed on the fly: the lane is NOT caught up -- PaxosAcceptor.caughtUp :452-459 (committedRequests empty, and
+ * acceptedProposals empty unless journaling serves accepted pvalues from disk) or PCS.caughtUp :758 (myProposals
+ * empty) is false.  PISM.tryPause :2004-2035 pauses an instance only when this bit is clear on every lane. */
+#define GPX_GF_NOT_CAUGHT_UP_BIT 4u
 int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out);
 /* `active.<name>=host:port` entries (PaxosConfig.getActives :156-170) of the last
  * gpx_config_from_properties call, as "name=host:port\n" lines */

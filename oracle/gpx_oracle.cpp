@@ -447,13 +447,13 @@ static void md5(const uint8_t* msg, size_t len, uint8_t out[16]) {
 
 /* ------------------------------------------------------------------------------
  * paxosutil/HotRestoreInfo.java:60-120 string form ('|' separated)
- * Util.arrayOfIntToString -> "[a, b, c]"
+ * Util.arrayOfIntToString (utils/Util.java:241-248) -> "[a,b,c]" (no blanks; stringToIntArray :184-193 strips any)
  * ---------------------------------------------------------------------------- */
 static std::string arrayOfIntToString(const std::vector<i32>& a) {
   std::string s = "[";
   for (size_t i = 0; i < a.size(); i++) {
     s += std::to_string(a[i]);
-    if (i + 1 < a.size()) s += ", ";
+    if (i + 1 < a.size()) s += ",";
   }
   return s + "]";
 }
@@ -1401,7 +1401,16 @@ int gpxo_reset_counters(gpxo_engine* e) {
 /* group flags (GF_*) of one lane, for the host slow-path list */
 int gpxo_get_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out) {
   if (lane >= e->L()) return GPX_ERANGE;
-  for (u32 k = 0; k < n; k++) out[k] = gids[k] < e->cfg.max_groups ? e->lanes[lane].acc[gids[k]].flags : 0;
+  for (u32 k = 0; k < n; k++) {
+    out[k] = 0;
+    if (gids[k] >= e->cfg.max_groups) continue;
+    const Acceptor& A = e->lanes[lane].acc[gids[k]];
+    const Coordinator& C = e->lanes[lane].coord[gids[k]];
+    /* PaxosAcceptor.caughtUp :452-459, PaxosCoordinator.caughtUp :369-371 / PCS.caughtUp :758-761 */
+    bool caughtUp = A.committedRequests.empty() && (A.acceptedProposals.empty() || A.journaling);
+    if (C.exists && !C.myProposals.empty()) caughtUp = false;
+    out[k] = (uint8_t)(A.flags | (caughtUp ? 0u : GPX_GF_NOT_CAUGHT_UP_BIT));
+  }
   return GPX_OK;
 }
 
@@ -1436,10 +1445,13 @@ int gpxo_hri_from_row(const char* paxosID, const gpx_row* r, char* out, size_t c
   h.accSlot = r->acc_slot;
   h.accBallot = Ballot{r->acc_bnum, r->acc_bcoord};
   h.accGCSlot = r->acc_gc_slot;
-  h.hasCoord = r->coord_exists != 0;
+  /* PISM.tryPause :2004-2025: getBallotIfActive / getNextProposalSlotIfActive / getNodeSlotsIfActive
+   * (PaxosCoordinator.java:375-402): null, -1, null unless the coordinator is ACTIVE */
+  const bool active = r->coord_exists != 0 && r->coord_active != 0;
+  h.hasCoord = active;
   h.coordBallot = Ballot{r->coord_bnum, r->coord_bcoord};
-  h.nextProposalSlot = r->next_proposal_slot;
-  h.hasNodeSlots = r->coord_exists != 0;
+  h.nextProposalSlot = active ? r->next_proposal_slot : -1;
+  h.hasNodeSlots = active;
   h.nodeSlots.assign(r->node_slots, r->node_slots + r->n_members);
   std::string s = h.toString();
   if (s.size() + 1 > cap) return GPX_ERANGE;
@@ -1576,7 +1588,7 @@ int gpxo_selftest(uint64_t seed) {
     h.hasNodeSlots = true;
     h.nodeSlots = {1, 3, 5};
     std::string s1 = h.toString();
-    CHECK(50, s1 == "paxos0|2|[1, 4, 67]|5|3:4|3|45:67|34|[1, 3, 5]");
+    CHECK(50, s1 == "paxos0|2|[1,4,67]|5|3:4|3|45:67|34|[1,3,5]"); /* Util.arrayOfIntToString: no blanks */
     CHECK(51, HotRestoreInfo::parse(s1).toString() == s1);
   }
   /* 6. medianMinus :867-875, roundRobinCoordinator :2251-2256, String.hashCode */

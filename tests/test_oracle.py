@@ -22,12 +22,15 @@ def test_reference_selftests(oracle_lib):
 def test_hot_restore_info_literal(oracle_lib):
     """The only literal-valued JUnit test near the path: HotRestoreInfoTest.testToStringAndBack."""
     out = C.create_string_buffer(256)
-    s = b"paxos0|2|[1, 4, 67]|5|3:4|3|45:67|34|[1, 3, 5]"
+    s = b"paxos0|2|[1,4,67]|5|3:4|3|45:67|34|[1,3,5]"  # Util.arrayOfIntToString (utils/Util.java:241-248): no blanks
     assert oracle_lib.fn("hri_roundtrip")(s, out, C.c_size_t(256)) == 0
     assert out.value == s
-    s2 = b"name|0|[100, 101, 102]|1|0:101|-1|null|0|null"
+    s2 = b"name|0|[100,101,102]|1|0:101|-1|null|-1|null"
     assert oracle_lib.fn("hri_roundtrip")(s2, out, C.c_size_t(256)) == 0
     assert out.value == s2
+    # Util.stringToIntArray :184-193 strips brackets and white space: a blank-separated array parses to the same
+    assert oracle_lib.fn("hri_roundtrip")(b"paxos0|2|[1, 4, 67]|5|3:4|3|45:67|34|[1, 3, 5]", out, C.c_size_t(256)) == 0
+    assert out.value == s
 
 
 def test_java_helpers(oracle_lib):

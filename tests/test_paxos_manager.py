@@ -89,3 +89,72 @@ def test_paxos_manager_mirror_gpu(cuda_lib, oracle_lib):
     po = drive(oracle_lib)
     assert pg.apps[0].state == po.apps[0].state and pg.checkpoints == po.checkpoints
     assert pg.num_decisions == po.num_decisions
+
+
+# ---- pause / unpause (PaxosManager.pause :2284, unpause :2370; HotRestoreInfo) ---------------------------------
+def test_hot_restore_info_string_is_the_reference_format():
+    """the one literal-valued JUnit test near this path: paxosutil/HotRestoreInfo.java:159-175"""
+    from gigapaxos_b200.paxos_manager import HotRestoreInfo
+    h = HotRestoreInfo("paxos0", 2, [1, 4, 67], 5, (3, 4), 3, (45, 67), 34, [1, 3, 5])
+    s = str(h)
+    assert s == "paxos0|2|[1,4,67]|5|3:4|3|45:67|34|[1,3,5]"
+    assert str(HotRestoreInfo.parse(s)) == s
+    n = HotRestoreInfo("g", 0, [100, 101, 102], 1, (0, 101), -1, None, -1, None)
+    assert str(n) == "g|0|[100,101,102]|1|0:101|-1|null|-1|null" and HotRestoreInfo.parse(str(n)) == n
+
+
+def drive_pausing(lib, pause: bool):
+    """the same request schedule with and without pausing idle instances in between: the replicated state
+    machines must end in the same state, paused instances come back on demand (propose -> unpause)"""
+    import ctypes as C
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=4)
+    names = [f"TESTPaxosApp{i}" for i in range(12)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    rng = np.random.default_rng(3)
+    hri_seen = []
+    for r in range(10):
+        active = [n for n in names if rng.random() < 0.6]
+        for n in active:
+            pm.propose(n, f"{n}:{r}".encode(), entry_node=NODES[int(rng.integers(0, 3))])
+        if r == 4:
+            pm.propose(names[0], b"queued")
+            if pause:
+                assert not pm.pause(names[0])  # a request is queued: not idle
+        pm.run_round()
+        if pause and r % 3 == 0:
+            for n in names[::2]:
+                if n in pm.instances:
+                    gid = pm.instances[n].gid
+                    row = pm.engine.dump_rows(np.array([gid], dtype=np.uint32), 1)
+                    assert pm.pause(n) and pm.isPaused(n) and n not in pm.instances
+                    hri_seen.append((pm.paused[n][1], row))
+    if pause:
+        assert hri_seen and pm.paused  # some instances are still paused at the end
+        if lib.has("hri_from_row"):  # cross-check the string against the oracle's C++ formatter
+            for s, row in hri_seen:
+                out = C.create_string_buffer(512)
+                name = s.split("|")[0].encode()
+                assert lib.fn("hri_from_row")(name, row.ctypes.data_as(C.c_void_p), out, C.c_size_t(512)) == 0
+                assert out.value.decode() == s
+        for n in list(pm.paused):
+            assert pm.unpause(n)
+    return pm
+
+
+def test_pause_unpause_cpu(oracle_lib):
+    a, b = drive_pausing(oracle_lib, True), drive_pausing(oracle_lib, False)
+    assert a.apps[0].state == b.apps[0].state and all(x.state == a.apps[0].state for x in a.apps)
+    assert a.num_decisions == b.num_decisions
+    names = sorted(a.instances)
+    ra = {n: a.engine.dump_rows(np.array([a.instances[n].gid], dtype=np.uint32), 0)[0] for n in names}
+    rb = {n: b.engine.dump_rows(np.array([b.instances[n].gid], dtype=np.uint32), 0)[0] for n in names}
+    for n in names:
+        for f in ("acc_slot", "acc_bnum", "acc_bcoord", "acc_gc_slot", "next_proposal_slot", "coord_active"):
+            assert ra[n][f] == rb[n][f], (n, f)
+
+
+@pytest.mark.gpu
+def test_pause_unpause_gpu(cuda_lib, oracle_lib):
+    g, o = drive_pausing(cuda_lib, True), drive_pausing(oracle_lib, True)
+    assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
+    assert g.checkpoints == o.checkpoints
