@@ -245,7 +245,7 @@ __device__ __noinline__ void propose_run(const DevState& S, const ProposeArgs& A
       a.payload_len = plen;
       a.nreq = nreq;
       a.sender = crow.y;
-      int4* dst = reinterpret_cast<int4*>(&A.accepts[base + emitted]);
+      int4* dst = reinterpret_cast<int4*>(&A.accepts[indexed ? k : base + emitted]);
       const int4* src = reinterpret_cast<const int4*>(&a);
       dst[0] = src[0];
       dst[1] = src[1];

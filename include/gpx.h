@@ -188,7 +188,7 @@ typedef struct gpx_log_seg_hdr {
   uint16_t type; /* GPX_F_ACCEPT or GPX_F_DECISION */
   uint16_t lane;
   uint32_t n_slots;       /* record images reserved */
-  uint32_t n_valid;       /* images actually written (<= n_slots) */
+  uint32_t n_valid;       /* leading image slots in use (<= n_slots); some of them may be VOID holes */
   uint64_t payload_bytes; /* payload area bytes (ACCEPT segments) */
   uint64_t seq;           /* segment sequence number of this lane */
   uint64_t ring_off;      /* absolute ring offset of this header */

@@ -1221,6 +1221,10 @@ static void emitExtras(const std::vector<gpx_exec_rec>& extras, gpx_exec_rec* ou
 int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
                         uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra_exec,
                         uint32_t extra_cap, uint32_t* n_extra) {
+  if (n == 0) { /* an empty batch is a no-op: nothing is logged (the engine's calls return at once, too) */
+    if (n_extra) *n_extra = 0;
+    return GPX_OK;
+  }
   u32 L = e->L();
   std::vector<u64> seg(L), pay(L);
   for (u32 l = 0; l < L; l++) {
@@ -1251,6 +1255,10 @@ int gpxo_handle_accept_replies(gpxo_engine* e, uint32_t n, const gpx_accept_repl
 /* PISM.handleBatchedCommit :1480-1528 per slot -> handleCommittedRequest -> extractExecuteAndCheckpoint */
 int gpxo_handle_decisions(gpxo_engine* e, uint32_t n, const gpx_decision_rec* decisions, gpx_exec_rec* out_exec,
                           gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  if (n == 0) { /* an empty batch is a no-op: nothing is logged (the engine's calls return at once, too) */
+    if (n_extra) *n_extra = 0;
+    return GPX_OK;
+  }
   u32 L = e->L();
   std::vector<u64> seg(L);
   for (u32 l = 0; l < L; l++) seg[l] = e->segBegin(l, GPX_F_DECISION, n, 32, 0);
@@ -1270,6 +1278,10 @@ int gpxo_handle_accepts_fused(gpxo_engine* e, uint32_t n, const gpx_accept_rec* 
                               uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_decision_rec* out_decisions,
                               gpx_exec_rec* out_exec, gpx_exec_rec* out_extra_exec, uint32_t extra_cap,
                               uint32_t* n_extra) {
+  if (n == 0) { /* an empty batch is a no-op: nothing is logged (the engine's calls return at once, too) */
+    if (n_extra) *n_extra = 0;
+    return GPX_OK;
+  }
   u32 L = e->L();
   std::vector<u64> seg(L), pay(L), dseg(L);
   for (u32 l = 0; l < L; l++) {
@@ -1311,6 +1323,11 @@ int gpxo_handle_accepts_fused(gpxo_engine* e, uint32_t n, const gpx_accept_rec* 
 int gpxo_round_phases(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
                       uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
                       gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  if (n == 0) { /* an empty batch is a no-op: nothing is logged (the engine's calls return at once, too) */
+    if (n_exec_slots) *n_exec_slots = 0;
+    if (n_extra) *n_extra = 0;
+    return GPX_OK;
+  }
   u32 L = e->L();
   std::vector<gpx_accept_rec> acc(n);
   std::vector<uint8_t> blob(2 * ((payload_bytes + 15) & ~15ull) + 32ull * n + 64);
@@ -1341,6 +1358,11 @@ int gpxo_round_phases(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, c
 int gpxo_round(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
                uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
                gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
+  if (n == 0) { /* an empty batch is a no-op: nothing is logged (the engine's calls return at once, too) */
+    if (n_exec_slots) *n_exec_slots = 0;
+    if (n_extra) *n_extra = 0;
+    return GPX_OK;
+  }
   u32 L = e->L();
   const u64 pal = (payload_bytes + 15) & ~(u64)15;
   const u64 blob1_res = e->cfg.batching_enabled ? 16ull * n + pal : 0;

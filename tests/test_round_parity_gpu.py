@@ -28,7 +28,9 @@ def compare_logs(eo, eg, n_lanes):
         so, sg = abi.parse_log(eo.log_read(l)), abi.parse_log(eg.log_read(l))
         assert len(so) == len(sg)
         for (ho, io_, po, _), (hg, ig, pg, _) in zip(so, sg):
-            for f in ("type", "lane", "n_valid", "payload_bytes", "seq", "rec_bytes"):
+            # n_valid is an upper bound on the image slots in use (the phase pipeline leaves VOID holes where the
+            # batcher refused a batch, the oracle compacts them): the images themselves are compared below
+            for f in ("type", "lane", "payload_bytes", "seq", "rec_bytes"):
                 assert int(ho[f]) == int(hg[f]), f"lane {l} seg hdr {f}"
             co, cg = canon(io_), canon(ig)
             assert len(co) == len(cg)
