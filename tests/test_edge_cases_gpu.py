@@ -67,7 +67,8 @@ def test_batch_cut_rules_and_backpressure(oracle_lib, cuda_lib, mode, window):
         counts = rng.integers(0, 30, size=G)
         gids = np.repeat(np.arange(G), counts)
         lens = rng.choice([1, 10, 400, 900], size=len(gids))
-        reqs, pay = make_requests(gids, payload_len=lens, seed=12, round_no=r, entry_lane=r % 3)
+        stop = (rng.random(len(gids)) < 0.01) if r >= 2 else None  # a STOP inside a run: later batches are refused
+        reqs, pay = make_requests(gids, payload_len=lens, seed=12, round_no=r, entry_lane=r % 3, stop_mask=stop)
         so = same_round(eo, eg, mode, reqs, pay, extra_cap=8192)
         seen_bp = seen_bp or bool((so == abi.RS_BACKPRESSURE).any())
         compare_state(eo, eg, np.arange(G), 3)
@@ -118,3 +119,42 @@ def test_capacity_errors_are_api_errors(oracle_lib, cuda_lib):
     # nothing happened
     assert eg.counters()["proposals"] == 0
     compare_state(eo, eg, np.arange(8), 3)
+
+
+@pytest.mark.parametrize("window", [2, 8])
+def test_cut_batches_through_the_pipelined_compact_api(oracle_lib, cuda_lib, window):
+    """the same cut / back-pressure / STOP schedules through gpx_round_submit with compact summaries and packed
+    requests: multi-batch runs take the general path and report through the extra queue"""
+    from test_round_pipeline_gpu import exec_tuples, sum_tuples
+    G = 24
+    kw = dict(max_groups=G, max_batch_recs=2048, max_batch_payload=1 << 20, window=window, max_batch_size=5,
+              max_batch_bytes=3000, request_size_estimate=100)
+    eo, eg = both(oracle_lib, cuda_lib, **kw)
+    d = group_descs(G)
+    eo.create_groups(d)
+    eg.create_groups(d)
+    rng = np.random.default_rng(18)
+    nodes = [100, 101, 102]
+    for r in range(5):
+        counts = rng.integers(0, 25, size=G)
+        gids = np.repeat(np.arange(G), counts).astype(np.uint32)
+        n = len(gids)
+        lens = rng.choice([1, 10, 400, 900], size=n).astype(np.uint32)
+        lane = r % 3
+        packed = np.zeros(n, dtype=abi.request_packed_dtype)
+        packed["gid"], packed["payload_len"] = gids, lens
+        packed["flags"] = (lane << 8) | np.where(rng.random(n) < (0.01 if r >= 2 else 0), abi.F_STOP, 0)
+        packed["req_id"] = rng.integers(1, 1 << 62, size=n)
+        pay = rng.integers(48, 123, size=int(lens.sum()), dtype=np.uint8)
+        full = np.zeros(n, dtype=abi.request_dtype)
+        full["gid"], full["flags"], full["req_id"], full["payload_len"] = gids, packed["flags"], packed["req_id"], lens
+        full["payload_off"] = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+        full["entry_node"], full["client"] = nodes[lane], np.arange(n, dtype=np.uint32)
+        so, xo, ex_o = eo.round(full, pay, extra_cap=8192)
+        res = eg.round_wait(eg.round_submit(packed, pay, compact=True, packed=True, extra_cap=8192))
+        assert np.array_equal(res["sum"]["slot"], so)
+        want = sorted(exec_tuples(xo) + exec_tuples(ex_o))
+        got = sorted(sum_tuples(res["sum"], full, 3) + exec_tuples(res["extra"]))
+        assert got == want
+        compare_state(eo, eg, np.arange(G), 3)
+    compare_logs(eo, eg, 3)
