@@ -575,7 +575,7 @@ struct gpxo_engine {
   }
 
   /* ring: append a segment, return offset of header */
-  u64 segBegin(u32 lane, uint16_t type, u32 n_slots, u32 rec_bytes, u64 payload_bytes) {
+  u64 segBegin(u32 lane, uint16_t type, u32 n_slots, u32 rec_bytes, u64 payload_bytes, u32 n_valid = 0xffffffffu) {
     Lane& ln = lanes[lane];
     u64 off = ln.ring.size();
     u64 total = (64 + (u64)n_slots * rec_bytes + ((payload_bytes + 15) & ~(u64)15) + 31) & ~(u64)31;
@@ -586,7 +586,7 @@ struct gpxo_engine {
     h.type = type;
     h.lane = (uint16_t)lane;
     h.n_slots = n_slots;
-    h.n_valid = n_slots;
+    h.n_valid = n_valid == 0xffffffffu ? n_slots : n_valid;
     h.payload_bytes = (payload_bytes + 15) & ~(u64)15;
     h.seq = ln.seg_seq++;
     h.ring_off = off;
@@ -1218,18 +1218,16 @@ static void emitExtras(const std::vector<gpx_exec_rec>& extras, gpx_exec_rec* ou
 }
 
 /* PISM.handleAccept :1080-1166 at every addressed local lane */
-int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
-                        uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra_exec,
-                        uint32_t extra_cap, uint32_t* n_extra) {
-  if (n == 0) { /* an empty batch is a no-op: nothing is logged (the engine's calls return at once, too) */
-    if (n_extra) *n_extra = 0;
-    return GPX_OK;
-  }
+/* n ACCEPTs into a segment with n_slots >= n image slots (the phase pipeline of a round reserves one slot per
+ * REQUEST before it knows how many ACCEPTs the batcher emits, like the device) */
+static int acceptsImpl(gpxo_engine* e, u32 n, u32 n_slots, const gpx_accept_rec* accepts, const uint8_t* blob,
+                       u64 blob_bytes, gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra_exec, u32 extra_cap,
+                       u32* n_extra) {
   u32 L = e->L();
   std::vector<u64> seg(L), pay(L);
   for (u32 l = 0; l < L; l++) {
-    seg[l] = e->segBegin(l, GPX_F_ACCEPT, n, 48, blob_bytes);
-    pay[l] = seg[l] + 64 + (u64)n * 48;
+    seg[l] = e->segBegin(l, GPX_F_ACCEPT, n_slots, 48, blob_bytes, n);
+    pay[l] = seg[l] + 64 + (u64)n_slots * 48;
   }
   std::vector<gpx_exec_rec> extras;
   for (u32 i = 0; i < n; i++)
@@ -1237,6 +1235,18 @@ int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accept
       acceptAtLane(e, i, l, accepts[i], blob, seg[l], pay[l], out_replies[(u64)i * L + l], extras);
   emitExtras(extras, out_extra_exec, extra_cap, n_extra);
   return GPX_OK;
+}
+static int decisionsImpl(gpxo_engine* e, u32 n, u32 n_slots, const gpx_decision_rec* decisions, gpx_exec_rec* out_exec,
+                         gpx_exec_rec* out_extra_exec, u32 extra_cap, u32* n_extra);
+
+int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accepts, const uint8_t* blob,
+                        uint64_t blob_bytes, gpx_accept_reply_rec* out_replies, gpx_exec_rec* out_extra_exec,
+                        uint32_t extra_cap, uint32_t* n_extra) {
+  if (n == 0) { /* an empty batch is a no-op: nothing is logged (the engine's calls return at once, too) */
+    if (n_extra) *n_extra = 0;
+    return GPX_OK;
+  }
+  return acceptsImpl(e, n, n, accepts, blob, blob_bytes, out_replies, out_extra_exec, extra_cap, n_extra);
 }
 
 /* PISM.handleBatchedAcceptReply :1370-1419 -> handleAcceptReply :1248-1365 per slot */
@@ -1259,9 +1269,13 @@ int gpxo_handle_decisions(gpxo_engine* e, uint32_t n, const gpx_decision_rec* de
     if (n_extra) *n_extra = 0;
     return GPX_OK;
   }
+  return decisionsImpl(e, n, n, decisions, out_exec, out_extra_exec, extra_cap, n_extra);
+}
+static int decisionsImpl(gpxo_engine* e, u32 n, u32 n_slots, const gpx_decision_rec* decisions, gpx_exec_rec* out_exec,
+                         gpx_exec_rec* out_extra_exec, u32 extra_cap, u32* n_extra) {
   u32 L = e->L();
   std::vector<u64> seg(L);
-  for (u32 l = 0; l < L; l++) seg[l] = e->segBegin(l, GPX_F_DECISION, n, 32, 0);
+  for (u32 l = 0; l < L; l++) seg[l] = e->segBegin(l, GPX_F_DECISION, n_slots, 32, 0, n);
   std::vector<gpx_exec_rec> extras;
   for (u32 i = 0; i < n; i++)
     for (u32 l = 0; l < L; l++) decisionAtLane(e, i, l, decisions[i], seg[l], out_exec[(u64)i * L + l], extras);
@@ -1337,14 +1351,15 @@ int gpxo_round_phases(gpxo_engine* e, uint32_t n, const gpx_request_rec* reqs, c
   if (rc) return rc;
   std::vector<gpx_accept_reply_rec> rep((size_t)na * L + 1);
   u32 nx1 = 0, nx2 = 0;
-  rc = gpxo_handle_accepts(e, na, acc.data(), blob.data(), bb, rep.data(), out_extra_exec, extra_cap, &nx1);
+  /* one image slot per REQUEST in both segments, as the device reserves them before the counts are known */
+  rc = acceptsImpl(e, na, n, acc.data(), blob.data(), bb, rep.data(), out_extra_exec, extra_cap, &nx1);
   if (rc) return rc;
   std::vector<gpx_decision_rec> dec((size_t)na * L + 1);
   u32 nd = 0;
   rc = gpxo_handle_accept_replies(e, na * L, rep.data(), dec.data(), &nd);
   if (rc) return rc;
   u32 used = nx1 < extra_cap ? nx1 : extra_cap;
-  rc = gpxo_handle_decisions(e, nd, dec.data(), out_exec, out_extra_exec + used, extra_cap - used, &nx2);
+  rc = decisionsImpl(e, nd, n, dec.data(), out_exec, out_extra_exec + used, extra_cap - used, &nx2);
   if (rc) return rc;
   *n_exec_slots = nd * L;
   if (n_extra) *n_extra = nx1 + nx2;

@@ -39,3 +39,12 @@ def test_unbounded_and_windowed_oracle_agree(oracle_lib):
         c = f.engines[1].counters()
         assert c["window_overflow"] > 0, str(e)
     f.close()
+
+
+@pytest.mark.parametrize("seed,R,fn", [(31, 3, "round"), (32, 5, "round"), (33, 3, "round_phases")])
+def test_fused_rounds_inside_adversarial_schedules(oracle_lib, seed, R, fn):
+    """whole rounds (gpxo_round) interleaved with lossy / duplicated / reordered phase steps, rival coordinators
+    and view changes: safety holds, and the windowed and the unbounded oracle agree"""
+    f = Fuzzer([oracle_lib], G=48, R=R, W=8, seed=seed)
+    assert f.run(steps=60, fused_prob=0.3, round_prob=0.5, round_fn=fn) > 100
+    f.close()

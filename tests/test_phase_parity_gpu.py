@@ -39,3 +39,24 @@ def test_fuzz_parity_gc_modes(oracle_lib, cuda_lib):
     f.run(steps=40, check_every=5, fused_prob=0.5)
     compare_logs(f.engines[0], f.engines[1], 3)
     f.close()
+
+
+@pytest.mark.parametrize("seed,R,W,fn", [(41, 3, 8, "round"), (42, 3, 2, "round"), (43, 5, 4, "round"), (44, 3, 1, "round"),
+                                         (45, 4, 8, "round"), (46, 3, 8, "round_phases"), (47, 2, 4, "round"),
+                                         (48, 1, 2, "round")])
+def test_fuzz_parity_with_fused_rounds(oracle_lib, cuda_lib, seed, R, W, fn):
+    """gpx_round (k_round / k_round_slow) in the states adversarial schedules leave behind: outstanding proposals,
+    NACKed ballots, resigned and re-installed coordinators, placeholders, duplicates, stopped groups"""
+    f = Fuzzer([oracle_lib, cuda_lib], G=64, R=R, W=W, seed=seed)
+    decided = f.run(steps=60, check_every=5, fused_prob=0.3, round_prob=0.5, round_fn=fn)
+    assert decided > 50
+    compare_logs(f.engines[0], f.engines[1], R)
+    f.close()
+
+
+def test_fuzz_parity_fused_rounds_gc_modes(oracle_lib, cuda_lib):
+    f = Fuzzer([oracle_lib, cuda_lib], G=64, R=3, W=8, seed=51, gc_majority_executed=0, log_meta_decisions=0,
+               journaling_enabled=0, checkpoint_interval=3)
+    f.run(steps=40, check_every=5, fused_prob=0.5, round_prob=0.5)
+    compare_logs(f.engines[0], f.engines[1], 3)
+    f.close()
