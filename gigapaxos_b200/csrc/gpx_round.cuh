@@ -432,6 +432,9 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   /* ---- level B (depends on gid only): group meta, my lane's acceptor + coordinator rows; the first chunk of
    * the payload rides along ---- */
   uint32_t meta = 0, my_aux = 0, my_dirty = 1;
+  int ns_all[L];
+#pragma unroll
+  for (int c = 0; c < L; c++) ns_all[c] = 0;
   int4 my_row = make_int4(0, 0, 0, 0), my_crow = my_row, pv = my_row;
   const uint32_t ri = sub * G + gid; /* 32-bit plane indices: checked against 2^32 at engine creation */
   const uint8_t* const psrc = A.blob0 + poff;
@@ -442,6 +445,9 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
     my_row = S.acc_row[ri];
     my_crow = S.coord_row[ri];
     if (S.journaling) my_dirty = S.acc_dirty[ri]; /* 0: no accept was ever stored here -> skip the window read */
+#pragma unroll
+    for (int c = 0; c < L; c++) /* nodeSlotNumbers[c][sub] of every lane that may turn out to coordinate: 4 B each, */
+      ns_all[c] = S.node_slots[((uint32_t)c * S.Rcap + sub) * G + gid]; /* saves a whole dependent load level   */
     if (plen) {
       if (pal)
         pv = ld_stream4(psrc);
@@ -488,7 +494,9 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   const uint32_t ni = (cl * S.Rcap + sub) * G + gid;
   if (sf) {
     if (my_dirty) ld256(&S.acc_win[wi], e0, e1);
-    my_ns = S.node_slots[ni];
+#pragma unroll
+    for (int c = 0; c < L; c++)
+      if (cl == (uint32_t)c) my_ns = ns_all[c];
   }
   { /* an accept already sitting at this slot -> general path */
     const bool ent_live = ((unsigned)e1.w & GPX_ENT_VALID) && jsub(e0.x, my_row.w) > 0 && e0.x == slot;
