@@ -623,9 +623,17 @@ def main():
         for q in range(PIPE_DEPTH):
             sm = h_sum[q].numpy().view(exec_sum_dtype)
             assert np.all(sm["lane_mask"] == (1 << R) - 1) and np.all(sm["slot"] > 0), "summaries incomplete"
+        # decide latency of ONE batch end to end: submit -> wait with nothing else in flight
+        lat = []
+        for k in range(20):
+            t1 = time.perf_counter()
+            pipe_step(k)
+            pipe_wait()
+            lat.append(time.perf_counter() - t1)
         e2e = {"value": world * G * K4 / dt_pipe, "unit": "decisions/s",
                "h2d_bytes_per_step": int(G * 16 + h_pay[0].numel()),
                "d2h_bytes_per_step": int(G * 8 + 32), "steps": K4, "ms_per_step": 1e3 * dt_pipe / K4,
+               "p50_decide_latency_ms": 1e3 * float(np.median(lat)),
                "api": "gpx_round_submit / gpx_round_wait (include/gpx.h), GPX_ROUND_PACKED_REQS | GPX_ROUND_COMPACT: "
                       "pinned host buffers of 16-byte requests + payload in, one 8-byte EXEC summary per request out, "
                       "up to %d rounds in flight; "
