@@ -109,3 +109,22 @@ def test_fuse_commits_median_is_wraparound_max():
     rs, rm = wire.fuse_commits(d)
     assert rs.tolist() == [0, 2, 3, 5]
     assert rm.tolist() == [3, 1, -(2**31) + 5, 0]
+
+
+def test_reference_main_request_packet_with_25_batched():
+    """RequestPacket.main (paxospackets/RequestPacket.java:1531-1563): a STOP request "asd999" with 25 STOP requests
+    "asd0".."asd24" latched to it survives toBytes -> fromBytes.  Here: the product codec encodes it, the layout
+    restatement produces the same bytes, and the ACCEPT that carries it decodes to the same header fields."""
+    subs = [wire.Request("pid", 0, 1000 + i, f"asd{i}".encode(), stop=True, entry_replica=100, entry_time=i)
+            for i in range(25)]
+    req = wire.Request("pid", 0, 999, b"asd999", stop=True, entry_replica=100, entry_time=77, batched=tuple(subs))
+    enc = wire.encode_request(req)
+    kw = lambda r: dict(paxos_id=r.paxos_id, version=r.version, request_id=r.request_id, stop=r.stop, value=r.value,
+                        entry_replica=r.entry_replica, entry_time=r.entry_time)
+    assert enc == wo.request(**kw(req), batched=[kw(s) for s in subs])
+    acc = wire.encode_accept(req, 12, 3, 100, False, 9, 100)
+    v = wire.decode_accept(acc)
+    assert v["n_batched"] == 25 and v["request_id"] == 999 and v["stop"] == 1 and v["value_len"] == 6
+    assert (v["slot"], v["bnum"], v["bcoord"], v["median_cp"]) == (12, 3, 100, 9)
+    # every latched request is length-prefixed inside the parent (RequestPacket.toBytes :935-945)
+    assert enc.count(b"asd") == 26
