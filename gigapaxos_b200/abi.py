@@ -45,6 +45,13 @@ reply_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("bnum", "<i4"), ("bcoo
                         ("who", "<u4"), ("req_id", "<i8")])
 exec_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("req_id", "<i8"), ("payload_off", "<u4"), ("flags", "<u4")])
 batch_ent_dtype = np.dtype([("req_id", "<i8"), ("len", "<u4"), ("flags", "<u4")])
+accepted_pvalue_dtype = np.dtype([("slot", "<i4"), ("bnum", "<i4"), ("bcoord", "<i4"), ("frame_ref", "<u4"),
+                                  ("req_id", "<i8"), ("payload_len", "<u4"), ("flags", "<u4")])
+prepare_reply_dtype = np.dtype([("gid", "<u4"), ("first_slot", "<i4"), ("bnum", "<i4"), ("bcoord", "<i4"), ("who", "<u4"),
+                                ("n_accepted", "<u4"), ("reserved", "<i8"),
+                                ("accepted", accepted_pvalue_dtype, (GPX_MAX_WINDOW,))])
+assert prepare_reply_dtype.itemsize == 32 + 32 * GPX_MAX_WINDOW
+F_PREPARE, F_FROM_LOG = 0x200, 0x400
 exec_sum_dtype = np.dtype([("slot", "<i4"), ("lane_mask", "u1"), ("flags", "u1"), ("nreq", "<u2")])
 ROUND_COMPACT = 1
 ROUND_PACKED_REQS = 2
@@ -278,6 +285,15 @@ class Engine:
         self.L.check(self.L.fn("handle_decisions")(self._h, C.c_uint32(n), _ptr(decisions), _ptr(ex), _ptr(extra),
                                                    C.c_uint32(extra_cap), C.byref(nx)))
         return ex[: n * self.n_lanes].copy(), extra[: min(nx.value, extra_cap)].copy()
+
+    def handle_prepares(self, prepares: np.ndarray) -> np.ndarray:
+        """PISM.handlePrepare at every addressed local lane; `prepares` are pvalue headers (slot = firstUndecidedSlot).
+        Returns prepare_reply records, shape [n * n_lanes]."""
+        prepares = np.ascontiguousarray(prepares, dtype=decision_dtype)
+        n = len(prepares)
+        out = np.zeros(max(n * self.n_lanes, 1), dtype=prepare_reply_dtype)
+        self.L.check(self.L.fn("handle_prepares")(self._h, C.c_uint32(n), _ptr(prepares), _ptr(out)))
+        return out[: n * self.n_lanes]
 
     def handle_accepts_fused(self, accepts: np.ndarray, blob: np.ndarray, extra_cap: int = 4096):
         accepts = np.ascontiguousarray(accepts, dtype=accept_dtype)

@@ -19,6 +19,7 @@
 
 #include "gpx_round.cuh"
 #include "gpx_route.cuh"
+#include "gpx_prepare.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -786,6 +787,31 @@ int gpx_handle_decisions(gpx_engine* e, uint32_t n, const gpx_decision_rec* deci
     CK(cudaMemcpyAsync(out_extra_exec, e->d_extra, cp * sizeof(gpx_exec_rec), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
+  return GPX_OK;
+}
+
+/* phase 1a at the acceptors: PISM.handlePrepare for a batch of PREPAREs, host buffers */
+int gpx_handle_prepares(gpx_engine* e, uint32_t n, const gpx_pvalue_hdr* prepares, gpx_prepare_reply_rec* out_replies) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!prepares || !out_replies) return fail(GPX_EINVAL, "null argument");
+  if (n > e->cfg.max_batch_recs) return fail(GPX_ERANGE, "n > max_batch_recs");
+  int rc = ring_fits(e, 64ull + 32ull * n);
+  if (rc) return rc;
+  const uint32_t L = e->cfg.n_lanes;
+  const size_t out_bytes = (size_t)n * L * sizeof(gpx_prepare_reply_rec);
+  rc = e->ensure_misc(out_bytes);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  CK(cudaMemcpyAsync(e->d_decisions, prepares, n * sizeof(gpx_pvalue_hdr), cudaMemcpyHostToDevice, st));
+  PrepareArgs A;
+  A.recs = e->d_decisions;
+  A.n = n;
+  A.replies = (gpx_prepare_reply_rec*)e->d_misc;
+  GPX_DISPATCH_L(L, k_prepare, cdiv(n, GPX_BLOCK), st, e->S, A);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_replies, e->d_misc, out_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return GPX_OK;
 }
 

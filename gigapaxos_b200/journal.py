@@ -111,7 +111,7 @@ class LogDrainer:
                     self.j.append(self._accept_bytes(a, payload))
                     n += 1
                     self.accepts_written += 1
-            else:
+            else:  # DECISION images and logged PREPAREs (GPX_F_PREPARE: the promised ballot) share the 32-byte form
                 logged = imgs[(imgs["flags"] & abi.F_VOID) == 0]
                 if len(logged):
                     self.j.append_decisions(logged)

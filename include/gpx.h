@@ -90,6 +90,10 @@ enum {
 #define GPX_F_LOGGED 0x0040u     /* accept reply was released by a log append (LogMessagingTask) */
 #define GPX_F_NACK 0x0080u       /* accept reply carries a ballot higher than the accept's */
 #define GPX_F_EXTRA 0x0100u      /* exec/decision came from the reconstructDecision path */
+#define GPX_F_PREPARE 0x0200u    /* log frame / record is a PREPARE (32 B pvalue header, slot = firstUndecidedSlot) */
+#define GPX_F_FROM_LOG 0x0400u   /* prepare reply: journaling serves accepted pvalues from the log (GET_ACCEPTED_
+                                  * PVALUES_FROM_DISK) and the preparer is behind this acceptor -> the host adds the
+                                  * logged accepts of [firstUndecidedSlot, acceptor's slot) from the journal */
 
 /* request status written by gpx_propose (one int32 per request) */
 #define GPX_RS_BATCHED (-1)      /* latched into the batch of an earlier request of the group */
@@ -344,6 +348,38 @@ int gpx_handle_accepts_fused(gpx_engine* e, uint32_t n, const gpx_accept_rec* ac
                              uint64_t blob_bytes, gpx_accept_reply_rec* out_replies,
                              gpx_decision_rec* out_decisions, gpx_exec_rec* out_exec,
                              gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra);
+
+/* ---- phase 1a at the acceptors ------------------------------------------------------------------
+ * PREPARE = a gpx_pvalue_hdr whose `slot` is PreparePacket.firstUndecidedSlot and whose ballot is the would-be
+ * coordinator's.  gpx_handle_prepares runs PISM.handlePrepare :896-955 / PaxosAcceptor.handlePrepare :239-275
+ * at every addressed local lane: a stopped instance drops it; a higher ballot is adopted; the reply carries the
+ * acceptor's ballot after that (NACK if it is higher than the PREPARE's), firstSlot =
+ * getMaxGCSlotFirstUndecidedSlot :277-282 and -- unless NACKing -- the accepted pvalues with slot >=
+ * firstUndecidedSlot in slot order (pruneAcceptedProposals :285-297).  When the ballot was raised the PREPARE is
+ * appended to the lane's log ring before the reply is visible (LogMessagingTask, :940-944; segment type
+ * GPX_F_PREPARE) and the reply is flagged GPX_F_LOGGED.  The coordinator side (PCS.isPrepareAcceptedByMajority,
+ * combinePValuesOntoProposals) stays on the host and installs its result with gpx_patch. */
+typedef struct gpx_accepted_pvalue { /* one accepted pvalue of a PREPARE_REPLY, 32 B (the accepted-window entry) */
+  int32_t slot;
+  int32_t bnum;
+  int32_t bcoord;
+  uint32_t frame_ref;   /* log ring position / 16 of the request blob at this acceptor */
+  int64_t req_id;
+  uint32_t payload_len;
+  uint32_t flags;       /* bit1 STOP, bits 16.. nreq */
+} gpx_accepted_pvalue;
+typedef struct gpx_prepare_reply_rec { /* PrepareReplyPacket, 32 + 32 * GPX_MAX_WINDOW bytes */
+  uint32_t gid;
+  int32_t first_slot;   /* PrepareReplyPacket.firstSlot */
+  int32_t bnum;         /* acceptor's ballot after handling the PREPARE */
+  int32_t bcoord;
+  uint32_t who;         /* GPX_WHO(acceptor idx, preparer idx, GPX_F_VOID | GPX_F_NACK | GPX_F_LOGGED | GPX_F_FROM_LOG) */
+  uint32_t n_accepted;
+  int64_t reserved;
+  gpx_accepted_pvalue accepted[GPX_MAX_WINDOW];
+} gpx_prepare_reply_rec;
+/* out_replies[n * n_lanes] */
+int gpx_handle_prepares(gpx_engine* e, uint32_t n, const gpx_pvalue_hdr* prepares, gpx_prepare_reply_rec* out_replies);
 
 /* One full round for co-located replicas.  gpx_round: RequestBatcher + propose, then the fused
  * accept -> tally -> commit per ACCEPT with replies, decisions and rows kept in registers.

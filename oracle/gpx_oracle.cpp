@@ -114,6 +114,28 @@ struct Acceptor {
     }
   }
 
+  /* handlePrepare :239-275 with pruneAcceptedProposals :285-297 and getMaxGCSlotFirstUndecidedSlot :277-282.
+   * Returns false iff stopped (Java null).  `accepted` comes back in slot order (wrap-aware, relative to the GC
+   * slot); empty when NACKing. */
+  bool handlePrepare(Ballot prepareBallot, i32 firstUndecidedSlot, Ballot* replyBallot, std::vector<PValue>* accepted,
+                     i32* firstSlot) {
+    if (isStopped()) return false;
+    if (prepareBallot.compareTo(getBallot()) > 0) { /* :245-251 */
+      ballotNum = prepareBallot.num;
+      ballotCoord = prepareBallot.coord;
+    }
+    *replyBallot = getBallot();
+    accepted->clear();
+    if (!(getBallot().compareTo(prepareBallot) > 0)) /* send pvalues only if not NACKing :262-270 */
+      for (auto& kv : acceptedProposals)
+        if (jsub(kv.first, firstUndecidedSlot) >= 0) accepted->push_back(kv.second); /* :291-293 */
+    std::sort(accepted->begin(), accepted->end(), [this](const PValue& a, const PValue& b) {
+      return jsub(a.slot, acceptedGCSlot) < jsub(b.slot, acceptedGCSlot);
+    });
+    *firstSlot = jsub(acceptedGCSlot, firstUndecidedSlot - 1) < 0 ? firstUndecidedSlot - 1 : acceptedGCSlot; /* :277-282 */
+    return true;
+  }
+
   /* acceptAndUpdateBallot :302-322; returns false iff stopped (Java null) */
   bool acceptAndUpdateBallot(const PValue& accept, Ballot* out) {
     if (isStopped()) return false;
@@ -1247,6 +1269,73 @@ int gpxo_handle_accepts(gpxo_engine* e, uint32_t n, const gpx_accept_rec* accept
     return GPX_OK;
   }
   return acceptsImpl(e, n, n, accepts, blob, blob_bytes, out_replies, out_extra_exec, extra_cap, n_extra);
+}
+
+/* PISM.handlePrepare :896-955 at every addressed local lane (phase 1a; the coordinator side stays on the host) */
+int gpxo_handle_prepares(gpxo_engine* e, uint32_t n, const gpx_pvalue_hdr* prepares, gpx_prepare_reply_rec* out_replies) {
+  if (n == 0) return GPX_OK;
+  u32 L = e->L();
+  std::vector<u64> seg(L);
+  for (u32 l = 0; l < L; l++) seg[l] = e->segBegin(l, GPX_F_PREPARE, n, 32, 0);
+  for (u32 i = 0; i < n; i++)
+    for (u32 l = 0; l < L; l++) {
+      const gpx_pvalue_hdr& r = prepares[i];
+      gpx_prepare_reply_rec& rep = out_replies[(u64)i * L + l];
+      memset(&rep, 0, sizeof rep);
+      rep.gid = r.gid;
+      rep.who = GPX_WHO(0xff, 0xff, GPX_F_VOID);
+      gpx_pvalue_hdr img = r;
+      img.flags = GPX_F_VOID;
+      auto writeImg = [&]() { memcpy(&e->lanes[l].ring[seg[l] + 64 + (u64)i * 32], &img, 32); };
+      if (!(r.dst_mask & (1u << l)) || (r.flags & GPX_F_VOID) || !e->usable(r.gid, l)) { /* PISM :456-460 */
+        writeImg();
+        continue;
+      }
+      Group& g = e->groups[r.gid];
+      Acceptor& A = e->lanes[l].acc[r.gid];
+      const int myIdx = e->memberIdx(g, e->lanes[l].node);
+      if (myIdx < 0) {
+        writeImg();
+        continue;
+      }
+      const Ballot prev = A.getBallot(), pb{r.bnum, r.bcoord};
+      Ballot rb{0, 0};
+      std::vector<PValue> acc;
+      i32 firstSlot = 0;
+      if (!A.handlePrepare(pb, r.slot, &rb, &acc, &firstSlot)) { /* stopped: null */
+        writeImg();
+        continue;
+      }
+      const int dstIdx = e->memberIdx(g, r.bcoord);
+      u32 fl = 0;
+      if (rb.compareTo(pb) > 0) fl |= GPX_F_NACK;
+      if (prev.compareTo(rb) < 0) { /* the ballot was raised: log the PREPARE, then reply (LogMessagingTask :940-944) */
+        fl |= GPX_F_LOGGED;
+        img.flags = (uint16_t)GPX_F_PREPARE;
+        img.dst_mask = (uint16_t)(1u << l);
+      }
+      /* GET_ACCEPTED_PVALUES_FROM_DISK :927-931: a preparer that is behind also needs the executed slots' accepts */
+      if (!(fl & GPX_F_NACK) && A.journaling && jsub(r.slot, A._slot) < 0) fl |= GPX_F_FROM_LOG;
+      writeImg();
+      rep.first_slot = firstSlot;
+      rep.bnum = rb.num;
+      rep.bcoord = rb.coord;
+      rep.who = GPX_WHO((u32)myIdx, dstIdx < 0 ? 0xffu : (u32)dstIdx, fl);
+      u32 k = 0;
+      for (const PValue& pv : acc) {
+        if (k >= GPX_MAX_WINDOW) break;
+        gpx_accepted_pvalue& o = rep.accepted[k++];
+        o.slot = pv.slot;
+        o.bnum = pv.bal.num;
+        o.bcoord = pv.bal.coord;
+        o.frame_ref = pv.frame_ref;
+        o.req_id = pv.req_id;
+        o.payload_len = pv.plen;
+        o.flags = (pv.stop ? 2u : 0u) | (pv.nreq << 16);
+      }
+      rep.n_accepted = k;
+    }
+  return GPX_OK;
 }
 
 /* PISM.handleBatchedAcceptReply :1370-1419 -> handleAcceptReply :1248-1365 per slot */

@@ -177,6 +177,46 @@ class Fuzzer:
             blob = rng.integers(48, 122, size=ln).astype(np.uint8)
             self.acc_pool.append((rec, blob))
 
+    def step_prepares(self, n=3):
+        """phase 1a: would-be coordinators (any member) send PREPAREs with a fresh ballot -- or a stale one -- and a
+        firstUndecidedSlot around the acceptors' slots, to a subset of the lanes; the replies (ballot, firstSlot,
+        accepted pvalues in slot order, NACK / LOGGED / FROM_LOG flags) and the logged PREPARE images must agree"""
+        rng = self.rng
+        rows = self.engines[0].dump_rows(np.arange(self.G), 0)
+        recs = []
+        for _ in range(n):
+            g = int(rng.integers(0, self.G))
+            node = NODES[int(rng.integers(0, self.R))]
+            if rng.random() < 0.7:
+                self.rival_bnum[g] += 1
+                bn = int(self.rival_bnum[g])
+            else:
+                bn = int(self.rival_bnum[g]) - int(rng.integers(0, 3))  # stale or equal ballot: NACK / plain ack
+            r = np.zeros(1, dtype=abi.decision_dtype)[0]
+            r["gid"], r["slot"], r["bnum"], r["bcoord"] = g, int(rows[g]["acc_slot"]) + int(rng.integers(-3, 3)), bn, node
+            r["flags"] = abi.F_PREPARE
+            mask = (1 << self.R) - 1
+            if rng.random() < 0.3:
+                mask &= ~(1 << int(rng.integers(0, self.R)))  # the multicast loses a destination
+            r["dst_mask"] = mask
+            recs.append(r)
+        recs.sort(key=lambda r: int(r["gid"]))
+        recs = np.array(recs, dtype=abi.decision_dtype)
+        outs = self._all(lambda e: e.handle_prepares(recs))
+        r0 = outs[0]
+        for r1 in outs[1:]:
+            for f in ("gid", "first_slot", "bnum", "bcoord", "who", "n_accepted"):
+                assert np.array_equal(r0[f], r1[f]), f"prepare reply {f}: {r0[f]} vs {r1[f]}"
+            for a, b in zip(r0, r1):
+                k = int(a["n_accepted"])
+                for f in abi.accepted_pvalue_dtype.names:
+                    x, y = a["accepted"][f][:k], b["accepted"][f][:k]
+                    if f == "frame_ref":  # batched blobs: position depends on block scheduling inside a fused round
+                        single = (a["accepted"]["flags"][:k] >> 16) <= 1
+                        x, y = x[single], y[single]
+                    assert np.array_equal(x, y), f"prepare reply accepted.{f}"
+                assert not b["accepted"][k:].view(np.uint8).any(), "entries beyond n_accepted must be zero"
+
     def _take(self, pool, p_deliver, p_dup, p_keep):
         rng = self.rng
         batch, rest = [], []
@@ -334,7 +374,7 @@ class Fuzzer:
         return len(agreed)
 
     def run(self, steps=60, rival=True, view_changes=True, stop_prob=0.01, check_every=10, fused_prob=0.0,
-            round_prob=0.0, round_fn="round"):
+            round_prob=0.0, round_fn="round", prepares=False):
         for t in range(steps):
             if self.rng.random() < round_prob:
                 self.step_round(frac=0.5, stop_prob=stop_prob, fn=round_fn)
@@ -344,6 +384,8 @@ class Fuzzer:
                 self.inject_rival_accepts(int(self.rng.integers(1, 5)))
             if view_changes and self.rng.random() < 0.15:
                 self.patch_view_change(int(self.rng.integers(1, 3)))
+            if prepares and self.rng.random() < 0.3:
+                self.step_prepares(int(self.rng.integers(1, 6)))
             order = self.rng.permutation(3)
             for o in order:
                 if o == 0:

@@ -60,3 +60,20 @@ def test_fuzz_parity_fused_rounds_gc_modes(oracle_lib, cuda_lib):
     f.run(steps=40, check_every=5, fused_prob=0.5, round_prob=0.5)
     compare_logs(f.engines[0], f.engines[1], 3)
     f.close()
+
+
+@pytest.mark.parametrize("seed,R,W,kw", [(71, 3, 8, {}), (72, 5, 4, {}), (73, 3, 2, {}), (74, 3, 8, {"journaling_enabled": 0}),
+                                         (75, 1, 8, {}), (76, 4, 1, {})])
+def test_fuzz_parity_with_prepares(oracle_lib, cuda_lib, seed, R, W, kw):
+    """phase 1a on the device (k_prepare: PISM.handlePrepare / PaxosAcceptor.handlePrepare) inside adversarial
+    schedules with fused rounds: replies, logged PREPARE images, state and ring heads must agree"""
+    f = Fuzzer([oracle_lib, cuda_lib], G=48, R=R, W=W, seed=seed, **kw)
+    decided = f.run(steps=60, check_every=5, fused_prob=0.3, round_prob=0.3, prepares=True)
+    assert decided > 30
+    compare_logs(f.engines[0], f.engines[1], R)
+    f.close()
+
+
+def test_handle_prepare_semantics_gpu(cuda_lib):
+    from test_fuzz_cpu import test_handle_prepare_semantics
+    test_handle_prepare_semantics(cuda_lib)
