@@ -32,6 +32,7 @@ INIT_BATCH, INIT_DEFAULT = 0, 1
 GF_OVERFLOW, GF_NEEDS_SYNC, GF_NOT_CAUGHT_UP = 1, 2, 4  # gpx_get_group_flags bits
 PATCH_SET_BALLOT, PATCH_JUMP_SLOT, PATCH_SET_STATE, PATCH_INSTALL_COORD, PATCH_RESIGN_COORD, PATCH_SET_GC = (
     1, 2, 3, 4, 5, 6)
+PATCH_SET_NODE_SLOT = 7
 SEG_MAGIC = 0x53585047
 
 request_dtype = np.dtype([("gid", "<u4"), ("flags", "<u4"), ("req_id", "<i8"), ("payload_off", "<u4"),

@@ -458,7 +458,7 @@ int gpx_patch(gpx_engine* e, uint32_t n, const gpx_patch_rec* p) {
   if (n == 0) return GPX_OK;
   for (uint32_t k = 0; k < n; k++) {
     if (p[k].gid >= e->cfg.max_groups || p[k].lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "gid/lane");
-    if (p[k].op < GPX_PATCH_SET_BALLOT || p[k].op > GPX_PATCH_SET_GC) return fail(GPX_EINVAL, "bad patch op");
+    if (p[k].op < GPX_PATCH_SET_BALLOT || p[k].op > GPX_PATCH_SET_NODE_SLOT) return fail(GPX_EINVAL, "bad patch op");
   }
   int rc = e->ensure_misc(n * sizeof(gpx_patch_rec));
   if (rc) return rc;

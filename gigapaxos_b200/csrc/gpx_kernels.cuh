@@ -1406,6 +1406,12 @@ __global__ void k_patch(const __grid_constant__ DevState S, const gpx_patch_rec*
       for (uint32_t w = 0; w < S.W; w++) S.prop_win[win_idx(S, r.lane, w, r.gid)] = make_int4(0, 0, 0, 0);
       break;
     case GPX_PATCH_SET_GC: row.w = r.a; break;
+    case GPX_PATCH_SET_NODE_SLOT: /* PCS.recordSlotNumber(PrepareReplyPacket) :786-807 */
+      if ((((unsigned)S.coord_row[ri].w) & GPX_CF_EXISTS) && r.a >= 0 && (uint32_t)r.a < S.Rcap) {
+        const size_t ni = ns_idx(S, r.lane, (uint32_t)r.a, r.gid);
+        if (jsub(S.node_slots[ni], r.b) < 0) S.node_slots[ni] = r.b;
+      }
+      break;
     default: break;
   }
   S.acc_row[ri] = row;

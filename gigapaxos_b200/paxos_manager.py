@@ -154,6 +154,15 @@ class HotRestoreInfo:
         return r
 
 
+NO_OP = b"NO_OP"  # RequestPacket.NO_OP: fills the slot gaps a new coordinator finds (PCS.makeNoopPValue :886-897)
+
+
+def _jsub(a: int, b: int) -> int:
+    """Java's wrap-around int subtraction"""
+    d = (a - b) & 0xFFFFFFFF
+    return d - (1 << 32) if d & 0x80000000 else d
+
+
 @dataclass
 class _Instance:
     gid: int
@@ -239,6 +248,142 @@ class PaxosManager:
         self._release(paxosID)
         return True
 
+    # ---- view change: the host half of phase 1 over the device's phase 1a -----------------------------------
+    def runForCoordinator(self, paxosID: str, lane: int) -> bool:
+        """PISM.checkRunForCoordinator(forceRun) :2090-2150 at the node of `lane`, then PISM.handlePrepareReply
+        :957-990 / PCS.isPrepareAcceptedByMajority :326-391, combinePValuesOntoProposals :393-444, processStop
+        :478-554 and spawnCommandersForProposals :556-575 for the PREPARE_REPLYs of the local lanes.
+
+        The acceptors answer on the device (gpx_handle_prepares); the tally is host logic (rare, variable-size); the
+        result goes back as gpx_patch records (resign the old coordinator, install the new one, recordSlotNumber) and
+        the carried-over pvalues are re-proposed in slot order under the new ballot, their request bodies read from
+        the log ring of the acceptor that reported them.  Returns False when the election was preempted or found no
+        majority."""
+        inst = self.instances.get(paxosID)
+        if inst is None or inst.stopped:
+            return False
+        eng, L = self.engine, self.engine.n_lanes
+        gids = np.array([inst.gid], dtype=np.uint32)
+        members = list(inst.members)
+        R = len(members)
+        me = self.nodes[lane]
+        cur = eng.dump_rows(gids, lane)[0]
+        new_ballot = (int(cur["acc_bnum"]) + 1, me)  # new Ballot(curBallot.ballotNumber + 1, myID) :2143
+        prep = np.zeros(1, dtype=abi.decision_dtype)
+        prep["gid"], prep["slot"] = inst.gid, int(cur["acc_slot"])  # PreparePacket(newBallot, paxosState.getSlot())
+        prep["bnum"], prep["bcoord"] = new_ballot
+        prep["flags"], prep["dst_mask"] = abi.F_PREPARE, (1 << L) - 1
+        replies = eng.handle_prepares(prep)
+        node_slots = [-1] * R  # PCS ctor :169-171
+        heard, carry, majority = set(), {}, False
+        for l, rep in enumerate(replies):  # PISM.handlePrepareReply, in lane order
+            fl = abi.who_flags(int(rep["who"]))
+            if fl & abi.F_VOID:
+                continue
+            rb = (int(rep["bnum"]), int(rep["bcoord"]))
+            c = _jsub(rb[0], new_ballot[0]) or _jsub(rb[1], new_ballot[1])
+            if c > 0:  # isPreemptable :271-278 -> getPreActivesIfPreempted: the election is lost
+                return False
+            idx = abi.who_acc(int(rep["who"]))
+            if c < 0 or idx in heard or idx >= R:  # canIgnorePrepareReply :287-316
+                continue
+            acc = rep["accepted"][: int(rep["n_accepted"])]
+            # recordSlotNumber :786-807 with PrepareReplyPacket.getMinSlot: the lowest accepted slot, else gcSlot + 1
+            min_slot = int(rep["first_slot"]) + 1
+            for pv in acc:
+                if _jsub(int(pv["slot"]), min_slot) < 0:
+                    min_slot = int(pv["slot"])
+            if _jsub(node_slots[idx], min_slot) < 0:
+                node_slots[idx] = min_slot
+            for pv in acc:  # the pvalue of the highest ballot per slot is carried over :347-366
+                ex = carry.get(int(pv["slot"]))
+                if ex is None or (_jsub(int(pv["bnum"]), int(ex[0]["bnum"])) or
+                                  _jsub(int(pv["bcoord"]), int(ex[0]["bcoord"]))) > 0:
+                    carry[int(pv["slot"])] = (pv.copy(), l)
+            heard.add(idx)
+            if len(heard) > R // 2:  # WaitforUtility.heardFromMajority
+                majority = True
+                break
+        if not majority:
+            return False
+        # combinePValuesOntoProposals :393-444 (this mirror keeps no pre-active proposals: requests wait in its queue)
+        next_slot = int(cur["acc_slot"])  # PCS ctor: nextProposalSlotNumber = paxosState.getSlot()
+        plan: List[tuple] = []  # (slot, pvalue | None for a no-op, acceptor lane)
+        if carry:
+            max_carry = max_min = None
+            for sl in carry:
+                max_carry = sl if max_carry is None or _jsub(sl, max_carry) > 0 else max_carry
+            for v in node_slots:
+                max_min = v if max_min is None or _jsub(v, max_min) > 0 else max_min
+            sl = max_min
+            while _jsub(sl, max_carry) <= 0:
+                plan.append((sl,) + (carry[sl] if sl in carry else (None, -1)))
+                sl = (sl + 1) & 0xFFFFFFFF
+                sl = sl - (1 << 32) if sl & 0x80000000 else sl
+            next_slot = max_min
+        plan = self._process_stop(plan, new_ballot)
+        # the old coordinator(s) of this group resign, the new one starts ACTIVE at the first slot it has to fill
+        pts = []
+        for l in range(L):
+            pts.append((inst.gid, l, abi.PATCH_RESIGN_COORD, 0, 0, 0, 0))
+        pts.append((inst.gid, lane, abi.PATCH_INSTALL_COORD, new_ballot[0], new_ballot[1], next_slot, 1))
+        for i, v in enumerate(node_slots):
+            pts.append((inst.gid, lane, abi.PATCH_SET_NODE_SLOT, i, v, 0, 0))
+        p = np.zeros(len(pts), dtype=abi.patch_dtype)
+        for i, t in enumerate(pts):
+            p[i]["gid"], p[i]["lane"], p[i]["op"], p[i]["a"], p[i]["b"], p[i]["c"], p[i]["d"] = t
+        eng.patch(p)
+        # spawnCommandersForProposals :556-575: one ACCEPT per carried-over slot, in slot order, under my ballot
+        for sl, pv, src in plan:
+            if pv is None:
+                reqs = [RequestPacket(paxosID, 0, NO_OP, entry_replica=me)]
+            else:
+                reqs = self._requests_of(paxosID, pv, src, me)
+            self._submit(reqs)
+        return True
+
+    @staticmethod
+    def _process_stop(plan: List[tuple], my_ballot: tuple) -> List[tuple]:
+        """PCS.processStop :478-554: a regular request may never follow a STOP.  For a STOP at slot s1 and a regular
+        request at a higher slot s2: if the STOP's ballot is higher the request is replaced by the STOP, if lower the
+        STOP becomes a no-op."""
+        out = {sl: (pv, src) for sl, pv, src in plan}
+        bal = lambda pv: (int(pv["bnum"]), int(pv["bcoord"]))
+        is_stop = lambda pv: pv is not None and bool(int(pv["flags"]) & 2)
+        for s1, (p1, src1) in list(out.items()):
+            if not is_stop(p1):
+                continue
+            for s2, (p2, src2) in list(out.items()):
+                if p2 is None or is_stop(p2) or _jsub(s1, s2) >= 0:
+                    continue
+                c = _jsub(bal(p1)[0], bal(p2)[0]) or _jsub(bal(p1)[1], bal(p2)[1])
+                if c > 0:
+                    out[s2] = (p1, src1)
+                elif c < 0:
+                    out[s1] = (None, -1)
+        return [(sl,) + out[sl] for sl, _, _ in plan]
+
+    def _requests_of(self, paxosID: str, pv, src_lane: int, entry: int) -> List[RequestPacket]:
+        """the request(s) of an accepted pvalue, read back from the log ring of the acceptor lane that reported it"""
+        n, nreq = int(pv["payload_len"]), int(pv["flags"]) >> 16
+        blob = bytes(self.engine.log_read(src_lane, int(pv["frame_ref"]) * 16, n)) if n else b""
+        stop = bool(int(pv["flags"]) & 2)
+        if nreq <= 1:
+            known = self.outstanding.get(int(pv["req_id"]))
+            return [RequestPacket(paxosID, int(pv["req_id"]), blob, stop=stop,
+                                  entry_replica=known.entry_replica if known else entry,
+                                  callback=known.callback if known else None)]
+        ents = np.frombuffer(blob[: 16 * nreq], dtype=abi.batch_ent_dtype)
+        out, off = [], 16 * nreq
+        for e in ents:
+            known = self.outstanding.get(int(e["req_id"]))
+            out.append(RequestPacket(paxosID, int(e["req_id"]), blob[off: off + int(e["len"])],
+                                     stop=bool(int(e["flags"]) & abi.F_STOP),
+                                     entry_replica=known.entry_replica if known else entry,
+                                     callback=known.callback if known else None))
+            off += int(e["len"])
+        return out
+
     # ---- pause / unpause (PaxosManager.pause :2284-2330, unpause :2370-2437) ------------------------------
     def pause(self, paxosID: str) -> bool:
         """Move an idle instance out of the engine: PISM.tryPause :2004-2035 succeeds only when every replica is
@@ -318,6 +463,10 @@ class PaxosManager:
                 continue
             reqs_l.extend(self.queue[n])
         self.queue = {}
+        return self._submit(reqs_l)
+
+    def _submit(self, reqs_l: List[RequestPacket]) -> int:
+        """one engine round over a list of requests already grouped by paxos instance"""
         if not reqs_l:
             return 0
         n = len(reqs_l)
@@ -375,6 +524,8 @@ class PaxosManager:
                 batch = [first] if first is not None else []
             is_stop = bool(x["flags"] & abi.F_STOP)
             for bi, req in enumerate(batch):
+                if req.request_id == 0 and req.request_value == NO_OP:  # PISM.execute skips no-ops :1786-1790
+                    continue
                 view = RequestPacket(req.paxos_id, req.request_id, req.request_value, req.stop, req.entry_replica,
                                      req.entry_time, slot=int(x["slot"]), batch_index=bi, callback=req.callback)
                 entry = req.entry_replica == self.nodes[lane]

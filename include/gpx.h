@@ -241,7 +241,9 @@ enum {
   GPX_PATCH_SET_STATE = 3,     /* acceptor state <- a (forceStop, setActive) */
   GPX_PATCH_INSTALL_COORD = 4, /* coordinator (bnum=a, bcoord=b, next=c, active=d) */
   GPX_PATCH_RESIGN_COORD = 5,  /* coordinator <- null */
-  GPX_PATCH_SET_GC = 6         /* acceptedGCSlot <- a */
+  GPX_PATCH_SET_GC = 6,        /* acceptedGCSlot <- a */
+  GPX_PATCH_SET_NODE_SLOT = 7  /* coordinator's nodeSlotNumbers[a] <- b if higher (recordSlotNumber :786-807 on a
+                                * PREPARE_REPLY, host side of phase 1) */
 };
 typedef struct gpx_patch_rec {
   uint32_t gid;

@@ -870,6 +870,11 @@ int gpxo_patch(gpxo_engine* e, uint32_t n, const gpx_patch_rec* p) {
         break;
       case GPX_PATCH_RESIGN_COORD: C = Coordinator(); C.W = e->W(); break;
       case GPX_PATCH_SET_GC: A.acceptedGCSlot = p[k].a; break;
+      case GPX_PATCH_SET_NODE_SLOT:
+        if (C.exists && p[k].a >= 0 && (size_t)p[k].a < C.nodeSlotNumbers.size() &&
+            jsub(C.nodeSlotNumbers[p[k].a], p[k].b) < 0)
+          C.nodeSlotNumbers[p[k].a] = p[k].b;
+        break;
       default: return GPX_EINVAL;
     }
   }

@@ -158,3 +158,82 @@ def test_pause_unpause_gpu(cuda_lib, oracle_lib):
     g, o = drive_pausing(cuda_lib, True), drive_pausing(oracle_lib, True)
     assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
     assert g.checkpoints == o.checkpoints
+
+
+# ---- view change: host half of phase 1 over the device's phase 1a (PISM.checkRunForCoordinator :2090,
+#      handlePrepareReply :957, PCS.combinePValuesOntoProposals :393) ------------------------------------------------
+def drive_view_change(lib):
+    from helpers import make_requests
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=100)
+    eng = pm.engine
+    names = [f"TESTPaxosApp{i}" for i in range(9)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    for r in range(3):
+        for n in names:
+            pm.propose(n, f"{n}:{r}".encode())
+        pm.run_round()
+    gids = np.array([pm.instances[n].gid for n in names], dtype=np.uint32)
+    rows0 = eng.dump_rows(gids, 0)
+    old_coord = {n: NODES.index(int(rows0[i]["acc_bcoord"])) for i, n in enumerate(names)}
+    # the old coordinators get two more slots ACCEPTed at a majority / a minority of the lanes and then "die": no
+    # replies are tallied, nothing is decided
+    for k, reach in enumerate((0b011, 0b101, 0b100)):  # third slot: only one acceptor ever sees it
+        reqs, pay = make_requests(gids, payload_len=9 + k, seed=5, round_no=k)
+        reqs["flags"] = [old_coord[n] << 8 for n in names]
+        reqs["entry_node"] = [NODES[old_coord[n]] for n in names]
+        acc, blob, st = eng.propose(reqs, pay)
+        assert np.all(st > 0)
+        acc["dst_mask"] = reach
+        eng.handle_accepts(acc, blob)
+    before = pm.apps[0].seqnum.copy() if hasattr(pm.apps[0].seqnum, "copy") else dict(pm.apps[0].seqnum)
+    # the next node in line runs for coordinator in every group
+    won = []
+    for n in names:
+        new_lane = (old_coord[n] + 1) % 3
+        assert pm.runForCoordinator(n, new_lane)
+        won.append(new_lane)
+    rows = [eng.dump_rows(gids, l) for l in range(3)]
+    for i, n in enumerate(names):
+        nl = won[i]
+        assert rows[nl][i]["coord_exists"] and rows[nl][i]["coord_active"]
+        assert rows[nl][i]["coord_bcoord"] == NODES[nl] and rows[nl][i]["coord_bnum"] == rows0[i]["acc_bnum"] + 1
+        assert all(not rows[l][i]["coord_exists"] for l in range(3) if l != nl)
+        # every replica executed the carried-over slots: at least the two slots a majority had accepted
+        assert all(rows[l][i]["acc_slot"] >= rows0[i]["acc_slot"] + 2 for l in range(3))
+        assert len({int(rows[l][i]["acc_slot"]) for l in range(3)}) == 1
+    s0 = pm.apps[0].state
+    assert all(a.state == s0 for a in pm.apps)  # the carried-over values were executed identically everywhere
+    assert all(pm.apps[0].seqnum[n] > before[n] for n in names)
+    # a stale candidate is preempted: some acceptor has promised a higher ballot
+    g0 = int(gids[0])
+    cand = (won[0] + 2) % 3
+    p = np.zeros(2, dtype=abi.patch_dtype)
+    for k, l in enumerate(x for x in range(3) if x != cand):  # a majority has promised ballot 50 to someone else
+        p[k]["gid"], p[k]["lane"], p[k]["op"], p[k]["a"], p[k]["b"] = g0, l, abi.PATCH_SET_BALLOT, 50, NODES[won[0]]
+    eng.patch(p)
+    assert not pm.runForCoordinator(names[0], cand)
+    # business as usual under the new coordinators
+    got = []
+    for r in range(2):
+        for n in names[1:]:
+            pm.propose(n, f"{n}:after{r}".encode(), entry_node=NODES[won[names.index(n)]],
+                       callback=lambda req, ok: got.append(req.slot))
+        pm.run_round()
+    assert len(got) == 2 * (len(names) - 1) and all(a.state == pm.apps[0].state for a in pm.apps)
+    return pm
+
+
+def test_view_change_cpu(oracle_lib):
+    drive_view_change(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_view_change_gpu(cuda_lib, oracle_lib):
+    g, o = drive_view_change(cuda_lib), drive_view_change(oracle_lib)
+    assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
+    names = sorted(g.instances)
+    for lane in range(3):
+        rg = g.engine.dump_rows(np.array([g.instances[n].gid for n in names], dtype=np.uint32), lane)
+        ro = o.engine.dump_rows(np.array([o.instances[n].gid for n in names], dtype=np.uint32), lane)
+        for f in rg.dtype.names:
+            assert np.array_equal(rg[f], ro[f]), (lane, f)
