@@ -17,7 +17,7 @@ from __future__ import annotations
 import os
 import struct
 import time
-from typing import Callable, Dict, Iterator, List, Optional, Tuple
+from typing import Callable, Dict, Iterator, List, Tuple
 
 import numpy as np
 

@@ -6,7 +6,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from helpers import Engine, abi, make_config, make_requests
+from helpers import Engine, abi, make_config
 
 RFC1321 = {b"": "d41d8cd98f00b204e9800998ecf8427e", b"a": "0cc175b9c0f1b6a831c399e269772661",
            b"abc": "900150983cd24fb0d6963f7d28e17f72", b"message digest": "f96b697d7cb7938d525a2f31aaf161d0",

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from helpers import Engine, abi, canon, exec_by_lane, group_descs, make_config, make_requests
+from helpers import Engine, abi, exec_by_lane, group_descs, make_config, make_requests
 
 
 def test_reference_selftests(oracle_lib):

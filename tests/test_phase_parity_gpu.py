@@ -2,7 +2,6 @@
 gpx_handle_accept_replies / gpx_handle_decisions / gpx_patch) against the oracle under
 adversarial schedules: every output record, every state row, every counter and every log byte
 is compared (tests/fuzz.py)."""
-import numpy as np
 import pytest
 
 from fuzz import Fuzzer
