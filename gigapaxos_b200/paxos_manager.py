@@ -274,54 +274,10 @@ class PaxosManager:
         prep["bnum"], prep["bcoord"] = new_ballot
         prep["flags"], prep["dst_mask"] = abi.F_PREPARE, (1 << L) - 1
         replies = eng.handle_prepares(prep)
-        node_slots = [-1] * R  # PCS ctor :169-171
-        heard, carry, majority = set(), {}, False
-        for l, rep in enumerate(replies):  # PISM.handlePrepareReply, in lane order
-            fl = abi.who_flags(int(rep["who"]))
-            if fl & abi.F_VOID:
-                continue
-            rb = (int(rep["bnum"]), int(rep["bcoord"]))
-            c = _jsub(rb[0], new_ballot[0]) or _jsub(rb[1], new_ballot[1])
-            if c > 0:  # isPreemptable :271-278 -> getPreActivesIfPreempted: the election is lost
-                return False
-            idx = abi.who_acc(int(rep["who"]))
-            if c < 0 or idx in heard or idx >= R:  # canIgnorePrepareReply :287-316
-                continue
-            acc = rep["accepted"][: int(rep["n_accepted"])]
-            # recordSlotNumber :786-807 with PrepareReplyPacket.getMinSlot: the lowest accepted slot, else gcSlot + 1
-            min_slot = int(rep["first_slot"]) + 1
-            for pv in acc:
-                if _jsub(int(pv["slot"]), min_slot) < 0:
-                    min_slot = int(pv["slot"])
-            if _jsub(node_slots[idx], min_slot) < 0:
-                node_slots[idx] = min_slot
-            for pv in acc:  # the pvalue of the highest ballot per slot is carried over :347-366
-                ex = carry.get(int(pv["slot"]))
-                if ex is None or (_jsub(int(pv["bnum"]), int(ex[0]["bnum"])) or
-                                  _jsub(int(pv["bcoord"]), int(ex[0]["bcoord"]))) > 0:
-                    carry[int(pv["slot"])] = (pv.copy(), l)
-            heard.add(idx)
-            if len(heard) > R // 2:  # WaitforUtility.heardFromMajority
-                majority = True
-                break
-        if not majority:
+        verdict, node_slots, carry = self.tally_prepare_replies(replies, R, new_ballot)
+        if verdict != "majority":
             return False
-        # combinePValuesOntoProposals :393-444 (this mirror keeps no pre-active proposals: requests wait in its queue)
-        next_slot = int(cur["acc_slot"])  # PCS ctor: nextProposalSlotNumber = paxosState.getSlot()
-        plan: List[tuple] = []  # (slot, pvalue | None for a no-op, acceptor lane)
-        if carry:
-            max_carry = max_min = None
-            for sl in carry:
-                max_carry = sl if max_carry is None or _jsub(sl, max_carry) > 0 else max_carry
-            for v in node_slots:
-                max_min = v if max_min is None or _jsub(v, max_min) > 0 else max_min
-            sl = max_min
-            while _jsub(sl, max_carry) <= 0:
-                plan.append((sl,) + (carry[sl] if sl in carry else (None, -1)))
-                sl = (sl + 1) & 0xFFFFFFFF
-                sl = sl - (1 << 32) if sl & 0x80000000 else sl
-            next_slot = max_min
-        plan = self._process_stop(plan, new_ballot)
+        plan, next_slot = self.combine_carryover(carry, node_slots, int(cur["acc_slot"]))
         # the old coordinator(s) of this group resign, the new one starts ACTIVE at the first slot it has to fill
         pts = []
         for l in range(L):
@@ -343,7 +299,63 @@ class PaxosManager:
         return True
 
     @staticmethod
-    def _process_stop(plan: List[tuple], my_ballot: tuple) -> List[tuple]:
+    def tally_prepare_replies(replies, R: int, new_ballot: tuple):
+        """PISM.handlePrepareReply :957-990 over a sequence of gpx_prepare_reply records, in order: returns
+        ("preempted" | "majority" | "waiting", nodeSlotNumbers, carryover {slot: (pvalue, reply index)})."""
+        node_slots = [-1] * R  # PCS ctor :169-171
+        heard, carry = set(), {}
+        for l, rep in enumerate(replies):
+            fl = abi.who_flags(int(rep["who"]))
+            if fl & abi.F_VOID:
+                continue
+            rb = (int(rep["bnum"]), int(rep["bcoord"]))
+            c = _jsub(rb[0], new_ballot[0]) or _jsub(rb[1], new_ballot[1])
+            if c > 0:  # isPreemptable :271-278 -> getPreActivesIfPreempted: the election is lost
+                return "preempted", node_slots, carry
+            idx = abi.who_acc(int(rep["who"]))
+            if c < 0 or idx in heard or idx >= R:  # canIgnorePrepareReply :287-316
+                continue
+            acc = rep["accepted"][: int(rep["n_accepted"])]
+            # recordSlotNumber :786-807 with PrepareReplyPacket.getMinSlot: the lowest accepted slot, else gcSlot + 1
+            min_slot = int(rep["first_slot"]) + 1
+            for k, pv in enumerate(acc):
+                if k == 0 or _jsub(int(pv["slot"]), min_slot) < 0:
+                    min_slot = int(pv["slot"])
+            if _jsub(node_slots[idx], min_slot) < 0:
+                node_slots[idx] = min_slot
+            for pv in acc:  # the pvalue of the highest ballot per slot is carried over :347-366
+                ex = carry.get(int(pv["slot"]))
+                if ex is None or (_jsub(int(pv["bnum"]), int(ex[0]["bnum"])) or
+                                  _jsub(int(pv["bcoord"]), int(ex[0]["bcoord"]))) > 0:
+                    carry[int(pv["slot"])] = (pv.copy(), l)
+            heard.add(idx)
+            if len(heard) > R // 2:  # WaitforUtility.heardFromMajority
+                return "majority", node_slots, carry
+        return "waiting", node_slots, carry
+
+    @staticmethod
+    def combine_carryover(carry: dict, node_slots: List[int], acc_slot: int):
+        """PCS.combinePValuesOntoProposals :393-444 (this mirror keeps no pre-active proposals: requests wait in
+        its queue): the slots from getMaxMinCarryoverSlot :921 to getMaxPValueSlot :903, carried-over pvalue or
+        no-op.  Returns (plan [(slot, pvalue | None, reply index)], first slot the new coordinator proposes)."""
+        next_slot = acc_slot  # PCS ctor: nextProposalSlotNumber = paxosState.getSlot()
+        plan: List[tuple] = []
+        if carry:
+            max_carry = max_min = None
+            for sl in carry:
+                max_carry = sl if max_carry is None or _jsub(sl, max_carry) > 0 else max_carry
+            for v in node_slots:
+                max_min = v if max_min is None or _jsub(v, max_min) > 0 else max_min
+            sl = max_min
+            while _jsub(sl, max_carry) <= 0:
+                plan.append((sl,) + (carry[sl] if sl in carry else (None, -1)))
+                sl = (sl + 1) & 0xFFFFFFFF
+                sl = sl - (1 << 32) if sl & 0x80000000 else sl
+            next_slot = max_min
+        return PaxosManager._process_stop(plan), next_slot
+
+    @staticmethod
+    def _process_stop(plan: List[tuple]) -> List[tuple]:
         """PCS.processStop :478-554: a regular request may never follow a STOP.  For a STOP at slot s1 and a regular
         request at a higher slot s2: if the STOP's ballot is higher the request is replaced by the STOP, if lower the
         STOP becomes a no-op."""

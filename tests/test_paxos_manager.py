@@ -237,3 +237,57 @@ def test_view_change_gpu(cuda_lib, oracle_lib):
         ro = o.engine.dump_rows(np.array([o.instances[n].gid for n in names], dtype=np.uint32), lane)
         for f in rg.dtype.names:
             assert np.array_equal(rg[f], ro[f]), (lane, f)
+
+
+def _reply(acc_idx, ballot, accepted=(), gc_slot=-1, flags=0):
+    """a PREPARE_REPLY record as gpx_handle_prepares writes it: accepted = [(slot, bnum, bcoord, stop)]"""
+    r = np.zeros(1, dtype=abi.prepare_reply_dtype)[0]
+    r["bnum"], r["bcoord"], r["first_slot"] = ballot[0], ballot[1], gc_slot
+    r["who"] = abi.who(acc_idx, 0, flags)
+    for k, (slot, bn, bc, stop) in enumerate(sorted(accepted)):
+        a = r["accepted"][k]
+        a["slot"], a["bnum"], a["bcoord"], a["req_id"], a["flags"] = slot, bn, bc, 1000 + slot, (2 if stop else 0) | (1 << 16)
+    r["n_accepted"] = len(accepted)
+    return r
+
+
+def test_prepare_reply_tally_is_the_reference_self_test():
+    """PaxosCoordinatorState.main, phase-1 half (PaxosCoordinatorState.java:1008-1178): 43 members, my ballot (2, 21);
+    carry-overs at slots 2 (two ballots), 6, 7, 8, 9 reported by members[2], members[0], members[4]; then the even
+    members answer with nothing.  After combining: every proposal slot >= maxMinSlot (7), stops are only followed by
+    stops."""
+    from gigapaxos_b200.paxos_manager import PaxosManager
+    R, my = 43, (2, 21)
+    T = PaxosManager.tally_prepare_replies
+    assert T([_reply(0xFF, (29, 42), flags=abi.F_VOID)], R, my)[0] == "waiting"      # not a member: ignored
+    assert T([_reply(3, (1, 21))], R, my) == ("waiting", [-1] * R, {})              # lower ballot: ignored
+    assert T([_reply(3, (2, 20))], R, my)[0] == "waiting"
+    assert T([_reply(3, (2, 22))], R, my)[0] == "preempted"                         # isPreemptable
+    rs = [_reply(2, my, [(2, 1, 20, False)]),                                        # members[2]
+          _reply(2, my, [(2, 1, 20, False)]),                                        # duplicate: ignored
+          _reply(0, my, [(2, 1, 21, False), (6, 1, 21, False)]),                     # members[0]
+          _reply(4, my, [(7, 1, 21, False), (8, 1, 22, False), (9, 1, 20, False)])]  # members[4]
+    rs += [_reply(i, my) for i in range(0, R, 2)]                                    # members 0, 2, 4, ... with nothing
+    for cut in (len(rs) - 1, len(rs)):
+        verdict, ns, carry = T(rs[:cut], R, my)
+        assert verdict == ("majority" if cut == len(rs) else "waiting")            # 22 of 43 heard only at the end
+    assert ns[2] == 2 and ns[0] == 2 and ns[4] == 7 and ns[6] == 0 and ns[1] == -1
+    assert sorted(carry) == [2, 6, 7, 8, 9] and int(carry[2][0]["bcoord"]) == 21    # the higher ballot wins slot 2
+    plan, nxt = PaxosManager.combine_carryover(carry, ns, acc_slot=0)
+    assert nxt == 7 and [sl for sl, _, _ in plan] == [7, 8, 9] and all(pv is not None for _, pv, _ in plan)
+    # processStop: a STOP with the higher ballot swallows a later regular request ...
+    rs[3] = _reply(4, my, [(7, 1, 21, False), (8, 1, 22, True), (9, 1, 20, False)])
+    _, ns, carry = T(rs, R, my)
+    plan, _ = PaxosManager.combine_carryover(carry, ns, 0)
+    stops = [bool(int(pv["flags"]) & 2) for _, pv, _ in plan]
+    assert stops == [False, True, True] and int(plan[2][1]["req_id"]) == 1008
+    # ... and a STOP with the lower ballot becomes a no-op
+    rs[3] = _reply(4, my, [(7, 1, 21, False), (8, 1, 19, True), (9, 1, 20, False)])
+    _, ns, carry = T(rs, R, my)
+    plan, _ = PaxosManager.combine_carryover(carry, ns, 0)
+    assert plan[1][1] is None and not (int(plan[2][1]["flags"]) & 2)
+    # a gap between carried-over slots is filled with a no-op (makeNoopPValue :886)
+    rs[3] = _reply(4, my, [(7, 1, 21, False), (9, 1, 20, False)])
+    _, ns, carry = T(rs, R, my)
+    plan, _ = PaxosManager.combine_carryover(carry, ns, 0)
+    assert [pv is None for _, pv, _ in plan] == [False, True, False]
