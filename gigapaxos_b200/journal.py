@@ -10,7 +10,9 @@ ACCEPTs are written with the reference's byte codec (AcceptPacket.toBytes, what
 SQLPaxosLogger.toBytes :1084-1096 journals for ACCEPT packets).  The reference journals
 DECISIONs as JSON strings (JSON codecs are out of scope); this writer therefore
 produces the journal of the reference's DONT_LOG_DECISIONS mode (:977-978) and keeps the
-decision images in a side file `<journal file>.decisions` (raw 32-byte gpx_decision_rec images).
+decision images in a side file `<journal file>.decisions` (raw 32-byte gpx_decision_rec images; logged
+PREPAREs -- the promised ballots, GPX_F_PREPARE -- share the form and the file, the reference journals
+those as JSON as well).
 """
 from __future__ import annotations
 
