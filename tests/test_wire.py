@@ -128,3 +128,42 @@ def test_reference_main_request_packet_with_25_batched():
     assert (v["slot"], v["bnum"], v["bcoord"], v["median_cp"]) == (12, 3, 100, 9)
     # every latched request is length-prefixed inside the parent (RequestPacket.toBytes :935-945)
     assert enc.count(b"asd") == 26
+
+
+# ---- property tests (hypothesis): encode -> decode is the identity on every field the decoder returns ---------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+i32 = st.integers(-(1 << 31), (1 << 31) - 1)
+i64 = st.integers(-(1 << 63), (1 << 63) - 1)
+pid = st.text(alphabet=st.characters(min_codepoint=33, max_codepoint=126), min_size=1, max_size=60)
+
+
+@settings(max_examples=150, deadline=None)
+@given(pid, st.integers(0, 1 << 20), i64, st.binary(max_size=400), st.booleans(), i32, i32, i32, i32, st.integers(0, 40))
+def test_accept_roundtrip_property(paxos_id, version, rid, value, stop, slot, bnum, bcoord, median, nb):
+    subs = tuple(wire.Request(paxos_id, version, rid ^ (k + 1), value[:k], stop=False, entry_replica=7, entry_time=k)
+                 for k in range(nb))
+    r = wire.Request(paxos_id, version, rid, value, stop=stop, entry_replica=bcoord, entry_time=12345, batched=subs)
+    b = wire.encode_accept(r, slot, bnum, bcoord, False, median, bcoord)
+    v = wire.decode_accept(b)
+    assert (v["paxos_id"], v["version"], v["request_id"], v["slot"], v["bnum"], v["bcoord"], v["median_cp"],
+            v["sender"], v["n_batched"], v["value_len"], bool(v["stop"])) == (
+        paxos_id, version, rid, slot, bnum, bcoord, median, bcoord, nb, len(value), stop)
+    kw = dict(paxos_id=paxos_id, version=version, request_id=rid, stop=stop, value=value, entry_replica=bcoord,
+              entry_time=12345,
+              batched=[dict(paxos_id=s.paxos_id, version=s.version, request_id=s.request_id, stop=s.stop, value=s.value,
+                            entry_replica=s.entry_replica, entry_time=s.entry_time) for s in subs])
+    assert b == wo.accept(kw, slot, bnum, bcoord, False, median, bcoord)
+    j = wire.journal_frame(b)
+    assert int.from_bytes(j[:4], "big", signed=True) == len(b) and j[4:] == b
+
+
+@settings(max_examples=150, deadline=None)
+@given(pid, st.integers(0, 1000), i32, i32, i32, st.lists(i32, min_size=1, max_size=64, unique=True),
+       st.lists(i32, min_size=1, max_size=16, unique=True))
+def test_batched_commit_roundtrip_property(paxos_id, version, bnum, bcoord, median, slots, group):
+    b = wire.encode_batched_commit(paxos_id, version, bnum, bcoord, median, slots, group)
+    d = wire.decode_batched_commit(b)
+    assert sorted(d["slots"]) == sorted(slots) and d["group"] == group
+    assert (d["bnum"], d["bcoord"], d["median_cp"]) == (bnum, bcoord, median)
+    assert b == wo.batched_commit(paxos_id, version, bnum, bcoord, median, slots, group)
