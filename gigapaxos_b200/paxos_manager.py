@@ -377,9 +377,90 @@ class PaxosManager:
 
     def _requests_of(self, paxosID: str, pv, src_lane: int, entry: int) -> List[RequestPacket]:
         """the request(s) of an accepted pvalue, read back from the log ring of the acceptor lane that reported it"""
-        n, nreq = int(pv["payload_len"]), int(pv["flags"]) >> 16
+        n = int(pv["payload_len"])
         blob = bytes(self.engine.log_read(src_lane, int(pv["frame_ref"]) * 16, n)) if n else b""
-        stop = bool(int(pv["flags"]) & 2)
+        return self._requests_from_blob(paxosID, pv, blob, entry)
+
+    # ---- catching up a replica that fell behind (PISM.syncLongDecisionGaps :1550, checkpoint transfer :1852) ----
+    def syncDecisions(self, paxosID: str, lane: int) -> int:
+        """PISM.requestMissingDecisions :2292-2316 at `lane` and handleSyncDecisionsPacket :2426-2500 at the replica
+        that is furthest ahead: the missing slots [my slot, donor's slot) are served from the donor's journal (its log
+        ring): getLoggedDecisions plus getActualDecisions -- the decision images name slot and ballot, the ACCEPT images
+        of that ballot carry the request.  They are replayed at the lagging lane W slots at a time (accept, then
+        commit) and its application executes them.  When that cannot close the gap (the lane has promised a higher
+        ballot, or the donor's ring no longer holds the slots) the replica takes a checkpoint instead
+        (handleCheckpoint :1852-1879: restore the app state, jumpSlot).  Returns the number of slots executed."""
+        inst = self.instances.get(paxosID)
+        if inst is None:
+            return 0
+        eng, L, gid = self.engine, self.engine.n_lanes, inst.gid
+        gids = np.array([gid], dtype=np.uint32)
+        rows = [eng.dump_rows(gids, l)[0] for l in range(L)]
+        donor = max(range(L), key=lambda l: _jsub(int(rows[l]["acc_slot"]), int(rows[lane]["acc_slot"])))
+        lo, hi = int(rows[lane]["acc_slot"]), int(rows[donor]["acc_slot"])
+        if donor == lane or _jsub(hi, lo) <= 0:
+            return 0
+        want = lambda sl: _jsub(sl, lo) >= 0 and _jsub(sl, hi) < 0
+        accepts, decisions = {}, {}
+        for hdr, imgs, payload, _ in abi.parse_log(eng.log_read(donor)):
+            for a in imgs:
+                if (int(a["flags"]) & abi.F_VOID) or int(a["gid"]) != gid or not want(int(a["slot"])):
+                    continue
+                if int(hdr["rec_bytes"]) == 48:
+                    o, n = int(a["payload_off"]), int(a["payload_len"])
+                    accepts[(int(a["slot"]), int(a["bnum"]), int(a["bcoord"]))] = (a.copy(), bytes(payload[o: o + n]))
+                elif int(a["flags"]) & abi.F_DECISION:
+                    decisions[int(a["slot"])] = a.copy()
+        executed, W, sl = 0, int(eng.cfg.window), lo
+        while _jsub(sl, hi) < 0:
+            chunk = []
+            while len(chunk) < W and _jsub(sl, hi) < 0:
+                d = decisions.get(sl)
+                a = accepts.get((sl, int(d["bnum"]), int(d["bcoord"]))) if d is not None else None
+                if a is None:
+                    break  # the donor's journal no longer has this slot
+                chunk.append((d, a))
+                sl += 1
+            if not chunk:
+                break
+            acc = np.zeros(len(chunk), dtype=abi.accept_dtype)
+            dec = np.zeros(len(chunk), dtype=abi.decision_dtype)
+            blob, batches = bytearray(), {}
+            for k, (d, (a, body)) in enumerate(chunk):
+                for f in abi.accept_dtype.names:
+                    acc[k][f] = a[f]
+                acc[k]["flags"], acc[k]["dst_mask"], acc[k]["payload_off"] = int(a["flags"]) & ~0x40, 1 << lane, len(blob)
+                blob += body + bytes(-len(body) % 16)
+                for f in ("gid", "slot", "bnum", "bcoord", "req_id"):
+                    dec[k][f] = a[f]
+                dec[k]["median_cp"] = max(int(d["median_cp"]), -1)
+                dec[k]["flags"] = abi.F_DECISION | (int(a["flags"]) & abi.F_STOP)
+                dec[k]["dst_mask"] = 1 << lane
+                pv = {"req_id": int(a["req_id"]), "flags": (2 if int(a["flags"]) & abi.F_STOP else 0) | (int(a["nreq"]) << 16)}
+                batches[int(a["req_id"])] = self._requests_from_blob(paxosID, pv, body, self.nodes[donor])
+            eng.handle_accepts(acc, np.frombuffer(bytes(blob), dtype=np.uint8))
+            ex, extra = eng.handle_decisions(dec)
+            n = self._apply(np.concatenate([ex, extra]), batches)
+            executed += n
+            if n == 0:
+                break  # e.g. the lane has promised a higher ballot: the accepts were refused
+        now = int(eng.dump_rows(gids, lane)[0]["acc_slot"])
+        if _jsub(hi, now) > 0:
+            executed += self._transfer_checkpoint(paxosID, donor, lane, hi)
+        return executed
+
+    def _transfer_checkpoint(self, paxosID: str, donor: int, lane: int, slot: int) -> int:
+        """PISM.handleCheckpoint :1852-1879: the app state of a replica that is ahead replaces mine and the acceptor
+        jumps to the slot after the checkpoint (PaxosAcceptor.jumpSlot :564-578)."""
+        inst = self.instances[paxosID]
+        self.apps[lane].restore(paxosID, self.apps[donor].checkpoint(paxosID))
+        p = np.zeros(1, dtype=abi.patch_dtype)
+        p["gid"], p["lane"], p["op"], p["a"] = inst.gid, lane, abi.PATCH_JUMP_SLOT, slot
+        self.engine.patch(p)
+        return 1
+
+    def _requests_from_blob(self, paxosID: str, pv, blob: bytes, entry: int) -> List[RequestPacket]:
+        nreq, stop = int(pv["flags"]) >> 16, bool(int(pv["flags"]) & 2)
         if nreq <= 1:
             known = self.outstanding.get(int(pv["req_id"]))
             return [RequestPacket(paxosID, int(pv["req_id"]), blob, stop=stop,

@@ -291,3 +291,81 @@ def test_prepare_reply_tally_is_the_reference_self_test():
     _, ns, carry = T(rs, R, my)
     plan, _ = PaxosManager.combine_carryover(carry, ns, 0)
     assert [pv is None for _, pv, _ in plan] == [False, True, False]
+
+
+# ---- catching up a lagging replica (PISM.syncLongDecisionGaps :1550 / handleSyncDecisionsPacket :2426 / checkpoint
+#      transfer :1852) ------------------------------------------------------------------------------------------------
+def drive_sync(lib):
+    from gigapaxos_b200.paxos_manager import RequestPacket
+    from helpers import make_requests
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=100)
+    eng = pm.engine
+    names = [f"TESTPaxosApp{i}" for i in range(6)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    for r in range(2):
+        for n in names:
+            pm.propose(n, f"{n}:{r}".encode())
+        pm.run_round()
+    gids = np.array([pm.instances[n].gid for n in names], dtype=np.uint32)
+    rows0 = eng.dump_rows(gids, 0)
+    coord = [NODES.index(int(rows0[i]["acc_bcoord"])) for i in range(len(names))]
+
+    def rounds_without_lane2(k0, k1):
+        """lane 2 is partitioned away: lanes 0 and 1 keep deciding (a majority) and executing"""
+        for k in range(k0, k1):
+            reqs, pay = make_requests(gids, payload_len=5 + k % 7, seed=9, round_no=k)
+            reqs["flags"] = [c << 8 for c in coord]
+            reqs["entry_node"] = [NODES[c] for c in coord]
+            acc, blob, st = eng.propose(reqs, pay)
+            assert np.all(st > 0)
+            acc["dst_mask"] = 0b011
+            rep, _ = eng.handle_accepts(acc, blob)
+            dec = eng.handle_accept_replies(rep)
+            assert len(dec) == len(names)
+            dec["dst_mask"] = 0b011
+            ex, extra = eng.handle_decisions(dec)
+            batches = {int(r["req_id"]): [RequestPacket(names[i], int(r["req_id"]),
+                                                        bytes(pay[int(r["payload_off"]): int(r["payload_off"]) + int(r["payload_len"])]),
+                                                        entry_replica=NODES[coord[i]])]
+                       for i, r in enumerate(reqs)}
+            pm._apply(np.concatenate([ex, extra]), batches)
+
+    rounds_without_lane2(0, 11)  # 11 slots: more than the window W = 8
+    assert pm.apps[2].state != pm.apps[0].state and pm.apps[1].state == pm.apps[0].state
+    for n in names:  # getLoggedDecisions + getActualDecisions from the donor's journal, W slots at a time
+        assert pm.syncDecisions(n, 2) == 11
+        assert pm.syncDecisions(n, 2) == 0
+    assert pm.apps[2].state == pm.apps[0].state and pm.apps[2].seqnum == pm.apps[0].seqnum
+    r2, r0 = eng.dump_rows(gids, 2), eng.dump_rows(gids, 0)
+    assert np.array_equal(r2["acc_slot"], r0["acc_slot"])
+    # the lane falls behind again, but now it has promised a higher ballot to someone: the old accepts are refused,
+    # so it catches up by checkpoint transfer (handleCheckpoint -> jumpSlot)
+    # (groups whose coordinator sits on lane 2 are left alone: bumping its acceptor's ballot would depose it)
+    bump = [i for i in range(len(names)) if coord[i] != 2]
+    assert bump
+    p = np.zeros(len(bump), dtype=abi.patch_dtype)
+    p["gid"], p["lane"], p["op"], p["a"], p["b"] = gids[bump], 2, abi.PATCH_SET_BALLOT, 9, NODES[2]
+    eng.patch(p)
+    rounds_without_lane2(11, 14)
+    for i, n in enumerate(names):
+        assert pm.syncDecisions(n, 2) == (1 if i in bump else 3)  # one checkpoint / three replayed slots
+    assert pm.apps[2].state == pm.apps[0].state
+    r2, r0 = eng.dump_rows(gids, 2), eng.dump_rows(gids, 0)
+    assert np.array_equal(r2["acc_slot"], r0["acc_slot"]) and np.all(r2["acc_bnum"][bump] == 9)
+    return pm
+
+
+def test_sync_decisions_cpu(oracle_lib):
+    drive_sync(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_sync_decisions_gpu(cuda_lib, oracle_lib):
+    g, o = drive_sync(cuda_lib), drive_sync(oracle_lib)
+    assert g.apps[2].state == o.apps[2].state and g.apps[0].state == o.apps[0].state
+    names = sorted(g.instances)
+    for lane in range(3):
+        rg = g.engine.dump_rows(np.array([g.instances[n].gid for n in names], dtype=np.uint32), lane)
+        ro = o.engine.dump_rows(np.array([o.instances[n].gid for n in names], dtype=np.uint32), lane)
+        for f in rg.dtype.names:
+            assert np.array_equal(rg[f], ro[f]), (lane, f)
