@@ -49,3 +49,84 @@ def test_digest_oracle(oracle_lib):
 @pytest.mark.gpu
 def test_digest_gpu(cuda_lib, oracle_lib):
     assert np.array_equal(check(cuda_lib), check(oracle_lib))
+
+
+# ---- digest mode end to end: AcceptPacket.digest / undigest + PendingDigests -------------------------
+def drive_digest_mode(lib, digest: bool):
+    from gigapaxos_b200.digests import PendingDigests, assemble, digest_accepts
+    from helpers import group_descs, make_requests
+    G, L = 40, 3
+    e = Engine(lib, make_config(lib, max_groups=G, max_batch_recs=4096, max_batch_payload=1 << 20, batching_enabled=0))
+    e.create_groups(group_descs(G))
+    pend = [PendingDigests() for _ in range(L)]  # one per acceptor node
+    rng = np.random.default_rng(7)
+    executed = 0
+    for r in range(5):
+        reqs, pay = make_requests(np.arange(G), payload_len=rng.integers(1, 90, size=G), seed=3, round_no=r)
+        acc, blob, st = e.propose(reqs, pay)
+        assert np.all(st > 0)
+        if not digest:
+            rep, _ = e.handle_accepts(acc, blob)
+        else:
+            bodies = {int(q["req_id"]): (int(q["gid"]), bytes(pay[int(q["payload_off"]): int(q["payload_off"]) + int(q["payload_len"])]))
+                      for q in reqs}
+            dacc = digest_accepts(e, acc, blob)  # MD5 on the device: the ACCEPTs travel without their bodies
+            assert all(int(d.rec["payload_len"]) == 0 and len(d.digest) == 16 for d in dacc)
+            rep = np.zeros(len(acc) * L, dtype=abi.reply_dtype)
+            rep["who"] = abi.who(0xFF, 0xFF, abi.F_VOID)
+            for l in range(L):
+                pairs = []
+                order = rng.permutation(len(dacc))
+                for k in order:  # the broadcast body and the digested ACCEPT race each other
+                    d = dacc[k]
+                    rid = int(d.rec["req_id"])
+                    gid, value = bodies[rid]
+                    if rng.random() < 0.5:
+                        pend[l].enqueue(gid, rid, value)
+                        got = pend[l].match(d)
+                    else:
+                        assert pend[l].match(d) is None
+                        pend[l].enqueue(gid, rid, value)
+                        got = pend[l].release(gid, rid, value)
+                    assert got is not None
+                    pairs.append(got)
+                a2, b2 = assemble(pairs)
+                a2["dst_mask"] = 1 << l
+                rl, _ = e.handle_accepts(a2, b2)
+                rl = rl.reshape(len(a2), L)[:, l]
+                # put lane l's replies where the undigested run has them (accept index * L + lane)
+                pos = {int(x["req_id"]): i for i, x in enumerate(acc)}
+                for x in rl:
+                    rep[pos[int(x["req_id"])] * L + l] = x
+            assert not any(p.accepts for p in pend) and all(p.anomalies == 0 for p in pend)
+        dec = e.handle_accept_replies(rep)
+        ex, extra = e.handle_decisions(dec)
+        executed += int(((ex["flags"] & abi.F_VOID) == 0).sum())
+    assert executed == 5 * G * L
+    return e
+
+
+def check_digest_mode(lib):
+    from gigapaxos_b200.digests import DigestedAccept, PendingDigests
+    a, b = drive_digest_mode(lib, True), drive_digest_mode(lib, False)
+    gids = np.arange(40)
+    for l in range(3):
+        ra, rb = a.dump_rows(gids, l), b.dump_rows(gids, l)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), (l, f)
+    # a body that does not hash to the ACCEPT's digest is an anomaly, not an accept (PendingDigests.logAnomaly)
+    p = PendingDigests()
+    rec = np.zeros(1, dtype=abi.accept_dtype)[0]
+    rec["gid"], rec["req_id"] = 3, 77
+    p.enqueue(3, 77, b"the body")
+    assert p.match(DigestedAccept(rec, hashlib.md5(b"another body").digest(), 12)) is None and p.anomalies == 1
+    assert p.match(DigestedAccept(rec, hashlib.md5(b"the body").digest(), 8)) is not None
+
+
+def test_digest_mode_cpu(oracle_lib):
+    check_digest_mode(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_digest_mode_gpu(cuda_lib):
+    check_digest_mode(cuda_lib)
