@@ -199,10 +199,24 @@ class SpreadCluster:
         self.N = n_nodes
         assert [nd.index for nd in nodes] == list(exchange.local)
         self.timing = False
+        self._pool: Dict[tuple, torch.Tensor] = {}  # persistent per-node buffers (grown, never shrunk)
         self.streams = {}
         for nd in nodes:
             if nd.device.type == "cuda" and nd.device not in self.streams:
                 self.streams[nd.device] = torch.cuda.Stream(device=nd.device)
+
+    def _buf(self, nd: "SpreadNode", key: str, nbytes: int, zero: bool = False) -> torch.Tensor:
+        """a byte buffer of the node that lives across rounds: no allocator traffic on the round's critical path.
+        What round() returns (status / exec / extra) points into these buffers and is valid until the next round."""
+        k = (nd.index, key)
+        t = self._pool.get(k)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes * 1.5), 256), dtype=torch.uint8, device=nd.device)
+            self._pool[k] = t
+        v = t[: max(nbytes, 1)]
+        if zero:
+            v.zero_()
+        return v
 
     def _exchange(self, kind: int, outs: List[torch.Tensor], caps: List[int], blobs=None, blob_caps=None):
         """outs[k]: node k's routed buckets [N][cap] (bytes).  Returns per local node (recv records, per-source
@@ -215,7 +229,7 @@ class SpreadCluster:
             cap = caps[k]
             send_r.append([outs[k][d * cap * rb: d * cap * rb + int(sc[d, 0]) * rb] for d in range(self.N)])
             tot = int(rc[:, 0].sum())
-            buf = torch.empty(max(tot, 1) * rb, dtype=torch.uint8, device=nd.device)
+            buf = self._buf(nd, "recv%d" % kind, max(tot, 1) * rb)
             offs = np.concatenate([[0], np.cumsum(rc[:, 0])]).astype(np.int64)
             recv_r.append([buf[offs[s] * rb: offs[s + 1] * rb] for s in range(self.N)])
             bbuf, boffs = None, None
@@ -223,7 +237,7 @@ class SpreadCluster:
                 bc = blob_caps[k]
                 send_b.append([blobs[k][d * bc: d * bc + int(sc[d, 1]) * 16] for d in range(self.N)])
                 btot = int(rc[:, 1].sum()) * 16
-                bbuf = torch.empty(max(btot, 16), dtype=torch.uint8, device=nd.device)
+                bbuf = self._buf(nd, "brecv%d" % kind, max(btot, 16))
                 boffs = np.concatenate([[0], np.cumsum(rc[:, 1].astype(np.int64) * 16)])
                 recv_b.append([bbuf[boffs[s]: boffs[s + 1]] for s in range(self.N)])
             res.append((buf, rc[:, 0].astype(np.int64), offs, bbuf, boffs))
@@ -272,13 +286,13 @@ class SpreadCluster:
             with _on(dev):
                 nd.ctl.zero_()
                 nd.dropped.zero_()
-                s = {"n": n, "status": torch.zeros(max(n, 1), dtype=torch.int32, device=dev),
-                     "extra": torch.zeros(extra_cap * 24, dtype=torch.uint8, device=dev)}
-                acc = torch.empty(max(n, 1) * 48, dtype=torch.uint8, device=dev)
+                s = {"n": n, "status": self._buf(nd, "status", 4 * max(n, 1), zero=True).view(torch.int32),
+                     "extra": self._buf(nd, "extra", extra_cap * 24, zero=True)}
+                acc = self._buf(nd, "acc", max(n, 1) * 48)
                 pbytes = payload.numel() if n else 0
                 bcap = ((pbytes + 15) // 16 * 16) + 32 * max(n, 1)  # payload + batched-blob tables, per bucket
-                out = torch.empty(N * max(n, 1) * 48, dtype=torch.uint8, device=dev)
-                ob = torch.empty(N * bcap, dtype=torch.uint8, device=dev)
+                out = self._buf(nd, "a_out", N * max(n, 1) * 48)
+                ob = self._buf(nd, "a_blob", N * bcap)
                 if n:
                     nd.propose(reqs, payload, n, s["status"], acc)
                     nd.route(K_ACCEPT, acc, nd.ctl.data_ptr() + 4 * CTL_N_ACCEPTS, n, payload, out, max(n, 1), ob, bcap)
@@ -298,8 +312,8 @@ class SpreadCluster:
             na = int(offs[-1])
             s["n_accepts_in"] = na
             with _on(nd.device):
-                rep = torch.empty(max(na, 1) * 32, dtype=torch.uint8, device=nd.device)
-                out = torch.empty(N * max(na, 1) * 32, dtype=torch.uint8, device=nd.device)
+                rep = self._buf(nd, "rep", max(na, 1) * 32)
+                out = self._buf(nd, "r_out", N * max(na, 1) * 32)
                 if na:
                     nd.accepts(abuf, na, bbuf[: int(boffs[-1])], [int(x) for x in offs[1:]], [int(x) for x in boffs[:-1]],
                                rep, s["extra"], extra_cap)
@@ -319,8 +333,8 @@ class SpreadCluster:
             nr = int(offs[-1])
             n = s["n"]
             with _on(nd.device):
-                dec = torch.empty(max(n, 1) * 32, dtype=torch.uint8, device=nd.device)
-                out = torch.empty(N * max(n, 1) * 32, dtype=torch.uint8, device=nd.device)
+                dec = self._buf(nd, "dec", max(n, 1) * 32)
+                out = self._buf(nd, "d_out", N * max(n, 1) * 32)
                 for src in range(N):
                     if cnts[src]:
                         nd.replies(rbuf, int(offs[src]) * 32, int(cnts[src]), dec)
@@ -340,7 +354,7 @@ class SpreadCluster:
             s = st[nd.index]
             ndec = int(offs[-1])
             with _on(nd.device):
-                ex = torch.empty(max(ndec, 1) * 24, dtype=torch.uint8, device=nd.device)
+                ex = self._buf(nd, "exec", max(ndec, 1) * 24)
                 if ndec:
                     nd.decisions(dbuf, ndec, ex, s["extra"], extra_cap)
                 s["exec"], s["n_exec"], s["_keep4"] = ex, ndec, dbuf
