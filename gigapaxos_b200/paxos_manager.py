@@ -190,6 +190,8 @@ class PaxosManager:
         self.checkpoints: List[tuple] = []
         self.num_decisions = 0
         self.slow_path: List[tuple] = []
+        self.auto_elect = True  # run for coordinator when a proposal finds none (PISM.handleProposal :862-885)
+        self._elect: Dict[str, int] = {}
         self.paused: Dict[str, List[str]] = {}  # paxosID -> HotRestoreInfo string per lane (the pause table)
 
     # ---- instance management ------------------------------------------------------------
@@ -580,12 +582,20 @@ class PaxosManager:
             payload[offs[i]: offs[i] + len(r.request_value)] = np.frombuffer(r.request_value, dtype=np.uint8)
         status, ex, extra = self.engine.round(reqs, payload)
         # requests the engine could not propose go back to the host slow path (retry / forward / prepare)
+        elect: Dict[str, int] = {}
         for i, st in enumerate(status):
             if st in (abi.RS_BACKPRESSURE,):
                 self.queue.setdefault(reqs_l[i].paxos_id, []).append(reqs_l[i])
+            elif st == abi.RS_NOCOORD and self.auto_elect:
+                # PISM.handleProposal :862-885: no coordinator for my acceptor's ballot -> checkRunForCoordinator(true)
+                # at the entry replica; the request waits in the queue and is proposed by the new coordinator
+                r = reqs_l[i]
+                elect.setdefault(r.paxos_id, self.nodes.index(r.entry_replica) if r.entry_replica in self.nodes else 0)
+                self.queue.setdefault(r.paxos_id, []).append(r)
             elif st < 0 and st != abi.RS_BATCHED:
                 self.slow_path.append((reqs_l[i].paxos_id, reqs_l[i].request_id, int(st)))
                 self.outstanding.pop(reqs_l[i].request_id, None)
+        self._elect = elect
         # batches: a positive status starts a slot, RS_BATCHED entries follow it (RequestPacket.batched)
         batches: Dict[int, List[RequestPacket]] = {}
         cur = None
@@ -595,7 +605,14 @@ class PaxosManager:
                 batches[cur] = [reqs_l[i]]
             elif st == abi.RS_BATCHED and cur is not None:
                 batches[cur].append(reqs_l[i])
-        return self._apply(np.concatenate([ex, extra]), batches)
+        done = self._apply(np.concatenate([ex, extra]), batches)
+        for name, lane in self._elect.items():
+            if not self.runForCoordinator(name, lane):  # preempted / no majority: give the requests back
+                for r in self.queue.pop(name, []):
+                    self.slow_path.append((name, r.request_id, abi.RS_NOCOORD))
+                    self.outstanding.pop(r.request_id, None)
+        self._elect = {}
+        return done
 
     def _apply(self, ex: np.ndarray, batches: Dict[int, List[RequestPacket]]) -> int:
         """PISM.execute :1755-1842 + PaxosManager.executed :311-330 for every EXEC record, per group in

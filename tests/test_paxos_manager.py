@@ -369,3 +369,41 @@ def test_sync_decisions_gpu(cuda_lib, oracle_lib):
         ro = o.engine.dump_rows(np.array([o.instances[n].gid for n in names], dtype=np.uint32), lane)
         for f in rg.dtype.names:
             assert np.array_equal(rg[f], ro[f]), (lane, f)
+
+
+def drive_auto_election(lib):
+    """a proposal that finds no coordinator makes its entry replica run for coordinator (PISM.handleProposal :862-885
+    -> checkRunForCoordinator(true)); the request is decided by the new coordinator in the next round"""
+    pm = make_pm(lib, HashChainApp)
+    names = [f"TESTPaxosApp{i}" for i in range(5)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    for n in names:
+        pm.propose(n, b"first")
+    pm.run_round()
+    gids = np.array([pm.instances[n].gid for n in names], dtype=np.uint32)
+    rows = pm.engine.dump_rows(gids, 0)
+    # every coordinator crashes: its row is gone (the acceptors keep their ballots)
+    p = np.zeros(3 * len(names), dtype=abi.patch_dtype)
+    for k in range(len(p)):
+        p[k]["gid"], p[k]["lane"], p[k]["op"] = gids[k // 3], k % 3, abi.PATCH_RESIGN_COORD
+    pm.engine.patch(p)
+    got = []
+    for i, n in enumerate(names):
+        entry = (NODES.index(int(rows[i]["acc_bcoord"])) + 1) % 3  # a surviving replica receives the request
+        pm.propose(n, b"second", entry_node=NODES[entry], callback=lambda req, ok: got.append((req.paxos_id, req.slot)))
+    assert pm.run_round() == 0 and not got   # nobody could propose; elections ran instead
+    assert pm.run_round() == 3 * len(names)  # the new coordinators decide the waiting requests
+    assert sorted(got) == sorted((n, 2) for n in names)
+    rows2 = pm.engine.dump_rows(gids, 0)
+    assert np.all(rows2["acc_bnum"] == rows["acc_bnum"] + 1) and all(a.state == pm.apps[0].state for a in pm.apps)
+    return pm
+
+
+def test_auto_election_cpu(oracle_lib):
+    drive_auto_election(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_auto_election_gpu(cuda_lib, oracle_lib):
+    g, o = drive_auto_election(cuda_lib), drive_auto_election(oracle_lib)
+    assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
