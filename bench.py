@@ -57,10 +57,11 @@ def b_slot(R: int, P: int) -> int:
 
 def b_act(R: int, P: int) -> int:
     """Algorithmic bytes per decided slot of the fused k_round kernel with all R replicas co-located
-    (DESIGN.md 4): request 32 + blob P + status 4 + reply mask 1 + decision record 32; per replica aux 4 +
-    row 16 in + 16 out + window entry 32 in + ACCEPT log image 48 + blob P + DECISION log image 32 +
-    EXEC 24; coordinator row 16 in + 16 out, nodeSlots 4R in + 4R out."""
-    return (32 + P + 4 + 1 + 32) + R * (4 + 16 + 16 + 32 + 48 + P + 32 + 24) + (32 + 8 * R)
+    (DESIGN.md 4): request 32 + blob P + status 4; per replica aux 4 + row 16 in + 16 out + window entry 32 in +
+    ACCEPT log image 48 + blob P + DECISION log image 32 + EXEC 24; coordinator row 16 in + 16 out, nodeSlots
+    4R in + 4R out.  (The DECISION record and the reply out-mask are no longer written by the fast path: every
+    member is a local lane, nobody reads them.)"""
+    return (32 + P + 4) + R * (4 + 16 + 16 + 32 + 48 + P + 32 + 24) + (32 + 8 * R)
 
 
 def hbm_peak():

@@ -66,8 +66,17 @@ enum {
   C_REQS_REJECTED,
   C_WINDOW_OVERFLOW,
   C_KERNEL_LAUNCHES,
-  C_NCTR = 24
+  /* aggregates of k_round's in-order fast path (folded into the public counters by gpx_get_counters): every lane
+   * of a fast team handled + acked + logged one ACCEPT, handled one reply and one DECISION and executed once; every
+   * team made one proposal (one request batched) and one decision */
+  C_FAST_LANES = 24,
+  C_FAST_TEAMS = 25,
+  C_FAST_CKPT = 26,
+  C_NCTR = 32
 };
+/* the global counter block is striped: block b adds into stripe b mod GPX_CTR_STRIPES (256 B apart), so the
+ * per-block counter flushes of a large grid do not serialise on one L2 line */
+#define GPX_CTR_STRIPES 64
 
 struct MsetInfo { /* one sorted member set (PISM.groupMembers :205), 96 B */
   int32_t nodes[GPX_MAX_GROUP_SIZE];
@@ -97,7 +106,7 @@ struct DevState {
   uint64_t ring_cap;
   unsigned long long* ring_head; /* [L] absolute byte offsets */
   unsigned long long* seg_seq;   /* [L] */
-  unsigned long long* ctr;       /* [C_NCTR] */
+  unsigned long long* ctr;       /* [GPX_CTR_STRIPES][C_NCTR] */
   unsigned int* tickets;         /* [8] last-block tickets, one per kernel kind */
   int32_t lane_node[GPX_MAX_LANES];
   int32_t cpi_const;

@@ -227,11 +227,11 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   }
   TRY(e->dalloc(&S.ring_head, (size_t)GPX_MAX_LANES));
   TRY(e->dalloc(&S.seg_seq, (size_t)GPX_MAX_LANES));
-  TRY(e->dalloc(&S.ctr, (size_t)C_NCTR));
+  TRY(e->dalloc(&S.ctr, (size_t)C_NCTR * GPX_CTR_STRIPES));
   TRY(e->dalloc(&S.tickets, (size_t)8));
   cudaMemset(S.ring_head, 0, GPX_MAX_LANES * 8);
   cudaMemset(S.seg_seq, 0, GPX_MAX_LANES * 8);
-  cudaMemset(S.ctr, 0, C_NCTR * 8);
+  cudaMemset(S.ctr, 0, C_NCTR * GPX_CTR_STRIPES * 8);
   cudaMemset(S.tickets, 0, 8 * 4);
   cudaMemset(S.grp_meta, 0, G * 4);
   {
@@ -583,7 +583,11 @@ static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uin
 extern "C++" {
 template <int L, int LP>
 static void launch_round_t(uint32_t grid, uint32_t slow_grid, cudaStream_t st, const DevState& S, const RoundArgs& RA) {
-  k_round<L, LP><<<grid, GPX_RBLOCK, 0, st>>>(S, RA);
+  /* the reference's default configuration gets the kernel with the flags folded at compile time */
+  if (S.journaling && S.gc_majority_executed && S.log_meta && !S.cpi_per_group)
+    k_round<L, LP, true><<<grid, GPX_RBLOCK, 0, st>>>(S, RA);
+  else
+    k_round<L, LP, false><<<grid, GPX_RBLOCK, 0, st>>>(S, RA);
   { /* programmatic dependent launch: k_round_slow's launch latency hides behind k_round */
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -636,6 +640,10 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.n_todo = &d_ctl->n_todo;
   RA.blob1_res = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
   RA.A.blob1_bytes = RA.blob1_res;
+  RA.pay_bytes = pal + RA.blob1_res;
+  RA.pay_rel = 64u + n * 48u;
+  RA.res_a = ((unsigned long long)RA.pay_rel + RA.pay_bytes + 31ull) & ~31ull;
+  RA.res_d = 64ull + (unsigned long long)n * 32ull;
   const uint32_t L = e->cfg.n_lanes;
   const uint32_t teams_per_block = (GPX_RBLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
   const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
@@ -1291,16 +1299,35 @@ int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_
 int gpx_get_counters(gpx_engine* e, gpx_counters* out) {
   if (!e || !out) return fail(GPX_EINVAL, "null argument");
   CK(cudaDeviceSynchronize()); /* rounds may have been issued on a caller's stream (gpx_round_device) */
+  std::vector<unsigned long long> rawv((size_t)C_NCTR * GPX_CTR_STRIPES);
+  unsigned long long* raw = rawv.data();
   unsigned long long c[C_NCTR];
-  CK(cudaMemcpy(c, e->S.ctr, sizeof c, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(raw, e->S.ctr, rawv.size() * 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < C_NCTR; i++) {
+    c[i] = 0;
+    for (int s = 0; s < GPX_CTR_STRIPES; s++) c[i] += raw[s * C_NCTR + i];
+  }
+  { /* fold the fast-path aggregates of k_round (gpx_dev.cuh) */
+    const unsigned long long fl = c[C_FAST_LANES], ft = c[C_FAST_TEAMS], fc = c[C_FAST_CKPT];
+    c[C_ACCEPTS_HANDLED] += fl;
+    c[C_ACCEPTS_ACKED] += fl;
+    c[C_ACCEPTS_LOGGED] += fl;
+    c[C_REPLIES_HANDLED] += fl;
+    c[C_DECISIONS_HANDLED] += fl;
+    c[C_EXECUTED] += fl;
+    c[C_CKPTS_DUE] += fc;
+    c[C_PROPOSALS] += ft;
+    c[C_REQS_BATCHED] += ft;
+    c[C_DECISIONS_MADE] += ft;
+  }
   memset(out, 0, sizeof *out);
   uint64_t* o = (uint64_t*)out;
-  for (int i = 0; i < C_NCTR && i < (int)(sizeof(gpx_counters) / 8); i++) o[i] = c[i];
+  for (int i = 0; i < 24 && i < (int)(sizeof(gpx_counters) / 8); i++) o[i] = c[i];
   return GPX_OK;
 }
 int gpx_reset_counters(gpx_engine* e) {
   if (!e) return fail(GPX_EINVAL, "null argument");
-  CK(cudaMemset(e->S.ctr, 0, C_NCTR * 8));
+  CK(cudaMemset(e->S.ctr, 0, C_NCTR * GPX_CTR_STRIPES * 8));
   return GPX_OK;
 }
 int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out) {

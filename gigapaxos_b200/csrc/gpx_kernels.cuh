@@ -76,7 +76,7 @@ __device__ __forceinline__ void flush_counters(const DevState& S, unsigned int* 
   __syncthreads();
   if (threadIdx.x < C_NCTR) {
     unsigned int v = s_ctr[threadIdx.x];
-    if (v) atomicAdd(&S.ctr[threadIdx.x], (unsigned long long)v);
+    if (v) atomicAdd(&S.ctr[(blockIdx.x & (GPX_CTR_STRIPES - 1)) * C_NCTR + threadIdx.x], (unsigned long long)v);
   }
 }
 

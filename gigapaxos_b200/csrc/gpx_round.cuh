@@ -38,6 +38,11 @@ struct RoundArgs {
   uint32_t* n_todo;
   RoundCtl* ctl_out;            /* k_round_slow publishes the round's counters here and re-zeroes P.ctl for the next
                                  * round (no memset between rounds) */
+  /* launch constants of the two log segments of a lane (host-computed: no 64-bit arithmetic in the kernels) */
+  unsigned long long pay_bytes; /* payload area of the ACCEPT segment = blob0_bytes + blob1_res */
+  unsigned long long res_a;     /* ACCEPT segment bytes  = align32(64 + 48 n + pay_bytes) */
+  unsigned long long res_d;     /* DECISION segment bytes = 64 + 32 n */
+  uint32_t pay_rel;             /* payload area offset inside the ACCEPT segment = 64 + 48 n */
   gpx_exec_sum* sum;            /* compact output mode (GPX_ROUND_COMPACT): one summary per request index instead of
                                  * n_lanes EXEC rows; everything that is not the plain in-order case goes to the
                                  * extra queue.  null = full EXEC rows */
@@ -367,10 +372,19 @@ __device__ __forceinline__ void round_general(const DevState& S, const RoundArgs
  * k_round_slow (always launched behind this kernel on the same stream), so warps retire right after their last
  * store -- no fence, no ticket.
  */
-template <int L, int LP>
+template <int L, int LP, bool DEF>
 __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK)) k_round(const __grid_constant__ DevState S,
                                                                      const __grid_constant__ RoundArgs RA) {
   static_assert(LP == L, "teams are exactly the L lanes of a group");
+  /* DEF: the engine runs the reference's default configuration (ENABLE_JOURNALING, GC_MAJORITY_EXECUTED, LOG_META_DECISIONS
+   * on, CPI_NOISE 0) -- the flags are compile-time constants and their branches fold away */
+  const bool cf_journaling = DEF ? true : (S.journaling != 0);
+  const bool cf_gcme = DEF ? true : (S.gc_majority_executed != 0);
+  const bool cf_logmeta = DEF ? true : (S.log_meta != 0);
+  const bool cf_cpi_pg = DEF ? false : (S.cpi_per_group != 0);
+#ifdef GPX_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); /* k_round_slow's blocks take their seats early */
+#endif
   constexpr uint32_t FULL = 0xffffffffu;
   constexpr uint32_t TPB = (GPX_RBLOCK / 32u) * (32u / LP); /* teams (= requests) per block */
   __shared__ unsigned int s_ctr[C_NCTR];
@@ -399,10 +413,8 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
                                         : 0xffffffffu;
   const uint32_t G = S.G, Wm = S.W - 1;
   /* per-lane log segments of this launch: [ACCEPT seg (n images + payload area)][DECISION seg] */
-  const unsigned long long pay_bytes = A.blob0_bytes + RA.blob1_res;
-  const uint32_t pay_rel = 64u + n * 48u;
-  const unsigned long long res_a = ((unsigned long long)pay_rel + pay_bytes + 31ull) & ~31ull;
-  const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
+  const unsigned long long pay_bytes = RA.pay_bytes, res_a = RA.res_a, res_d = RA.res_d;
+  const uint32_t pay_rel = RA.pay_rel;
   const unsigned long long seg = seg_base(S, sub, res_a + res_d);
   if (blockIdx.x == 0 && threadIdx.x < (uint32_t)L) { /* thread l writes lane l's two segment headers */
     const uint32_t t = threadIdx.x;
@@ -444,7 +456,7 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
     my_aux = S.acc_aux[ri];
     my_row = S.acc_row[ri];
     my_crow = S.coord_row[ri];
-    if (S.journaling) my_dirty = S.acc_dirty[ri]; /* 0: no accept was ever stored here -> skip the window read */
+    if (cf_journaling) my_dirty = S.acc_dirty[ri]; /* 0: no accept was ever stored here -> skip the window read */
 #pragma unroll
     for (int c = 0; c < L; c++) /* nodeSlotNumbers[c][sub] of every lane that may turn out to coordinate: 4 B each, */
       ns_all[c] = S.node_slots[((uint32_t)c * S.Rcap + sub) * G + gid]; /* saves a whole dependent load level   */
@@ -484,7 +496,8 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   const int slot = crow.z;
   sf = sf && ((unsigned)crow.w == (GPX_CF_EXISTS | GPX_CF_ACTIVE)) && bcmp(crow.x, crow.y, af_y, af_z) >= 0 &&
        st_usable(my_aux) && my_row.y == crow.x && my_row.z == crow.y && my_row.x == slot &&
-       !((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)slot & Wm)) & 1u) && jsub(slot, my_row.w) > 0;
+       GPX_AUX_PRESENT(my_aux) == 0u && jsub(slot, my_row.w) > 0; /* no commit queued anywhere in the window: the
+                                                                     * execution below is the only one (no EEC loop) */
   sf = ((__ballot_sync(FULL, sf) >> tbase) & TEAM) == TEAM;
 
   /* ---- level C (depends on the slot / the coordinator lane): window entry, nodeSlotNumbers ---- */
@@ -509,9 +522,9 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   /* handleAccept at my lane: ballot equal, slot next-in-line, no previous accept -> ack + log */
   int4 row = my_row;
   gc_step(row, median);   /* acceptAndUpdateBallot -> garbageCollectAccepted :320 */
-  const int cpi = S.cpi_per_group ? (sf ? S.grp_cpi[gid] : 1) : S.cpi_const;
+  const int cpi = cf_cpi_pg ? (sf ? S.grp_cpi[gid] : 1) : S.cpi_const;
   int max_cp = row.x - 1; /* AcceptReplyPacket.maxCheckpointedSlot :1139-1143 */
-  if (!S.gc_majority_executed) {
+  if (!cf_gcme) {
     int lcp = max_cp - max_cp % cpi;
     if (lcp < 0) {
       lcp = jsub(lcp, cpi);
@@ -548,14 +561,16 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
       uint8_t* dst = seg_p + pay_rel + poff;
       if (pal) {
         st_stream4(dst, pv);
+#pragma unroll 1
         for (uint32_t b = 16; b < plen; b += 16) st_stream4(dst + b, ld_stream4(psrc + b));
       } else {
         dst[0] = (uint8_t)pv.x;
+#pragma unroll 1
         for (uint32_t b = 1; b < plen; b++) dst[b] = psrc[b];
       }
     }
     /* commit (handleBatchedCommit :1488-1501 + extractExecuteAndCheckpoint): the accept is the decision */
-    const bool metaf = S.log_meta != 0;
+    const bool metaf = cf_logmeta;
     st256_stream(seg_p + res_a + 64 + (size_t)i * 32, q0,
                  make_int4(metaf ? -1 : dmed, (int)((GPX_F_DECISION | (metaf ? GPX_F_META : 0u)) | ((1u << sub) << 16)),
                            rq0.z, rq0.w));
@@ -572,29 +587,14 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
       if (!RA.sum) store_exec(&A.exec[(size_t)i * L + sub], er);
     }
     row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
-    if (S.journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
+    if (cf_journaling) { /* acceptedProposals.remove(slot): only written to hide a valid occupant */
       if ((unsigned)e1.w & GPX_ENT_VALID)
         st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref), /* VALID cleared: acc_dirty untouched */
               make_int4(rq0.z, rq0.w, (int)plen, (int)(1u << 16)));
     } else
       st256(&S.acc_win[wi], make_int4(slot, crow.x, crow.y, (int)frame_ref), /* not journaling: acc_dirty unused */
             make_int4(rq0.z, rq0.w, (int)plen, (int)(GPX_ENT_VALID | (1u << 16))));
-    gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot */
-    if ((GPX_AUX_PRESENT(my_aux) >> ((uint32_t)row.x & Wm)) & 1u) { /* queued commits become executable (rare) */
-      DPValue x;
-      x.slot = slot;
-      x.bnum = crow.x;
-      x.bcoord = crow.y;
-      x.median_cp = dmed;
-      x.req_id = ((long long)rq0.w << 32) | (unsigned)rq0.z;
-      x.frame_ref = frame_ref;
-      x.plen = plen;
-      x.fl = (1u << 16);
-      x.valued = true;
-      uint32_t aux = my_aux;
-      eec(S, sub, gid, row, aux, x, nullptr, A.extra, A.extra_cap, A.n_extra, s_ctr, true);
-      if (aux != my_aux) S.acc_aux[ri] = aux;
-    }
+    gc_step(row, dmed); /* second EEC iteration: GC with the advanced slot; nothing is queued (checked above) */
     S.acc_row[ri] = row;
     if (mine != my_ns) S.node_slots[ni] = mine; /* nodeSlotNumbers[cl][sub] */
     c_lane = 1;
@@ -606,8 +606,8 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
         RA.P.status[i] = slot;
       crow.z = (int)((unsigned)crow.z + 1u); /* PCS.propose: nextProposalSlotNumber++ (proposal decided at once) */
       S.coord_row[cl * G + gid] = crow;
-      st256_stream(&A.decisions[i], q0, make_int4(dmed, (int)(GPX_F_DECISION | (lane_mask << 16)), rq0.z, rq0.w));
-      A.out_mask[i] = 0;
+      /* the DECISION record and the reply out-mask are not written: every member is a local lane (IDENT), the
+       * decision was committed above and gpx_round hands neither to the caller */
       c_team = 1;
     }
   } else if (head && sub == 0) {
@@ -617,17 +617,10 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   {
     const uint32_t nl = __reduce_add_sync(FULL, c_lane), nt = __reduce_add_sync(FULL, c_team);
     const uint32_t nc = __reduce_add_sync(FULL, c_ckpt);
-    if (lane_id == 0 && (nl | nt)) {
-      atomicAdd(&s_ctr[C_ACCEPTS_HANDLED], nl);
-      atomicAdd(&s_ctr[C_ACCEPTS_ACKED], nl);
-      atomicAdd(&s_ctr[C_ACCEPTS_LOGGED], nl);
-      atomicAdd(&s_ctr[C_DECISIONS_HANDLED], nl);
-      atomicAdd(&s_ctr[C_EXECUTED], nl);
-      atomicAdd(&s_ctr[C_REPLIES_HANDLED], nl);
-      if (nc) atomicAdd(&s_ctr[C_CKPTS_DUE], nc);
-      atomicAdd(&s_ctr[C_PROPOSALS], nt);
-      atomicAdd(&s_ctr[C_REQS_BATCHED], nt);
-      atomicAdd(&s_ctr[C_DECISIONS_MADE], nt);
+    if (lane_id == 0 && (nl | nt)) { /* aggregates, expanded by gpx_get_counters */
+      atomicAdd(&s_ctr[C_FAST_LANES], nl);
+      atomicAdd(&s_ctr[C_FAST_TEAMS], nt);
+      if (nc) atomicAdd(&s_ctr[C_FAST_CKPT], nc);
     }
   }
   flush_counters(S, s_ctr);
@@ -647,10 +640,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
   const uint32_t ntodo = *RA.n_todo;
   if (ntodo == 0) { /* the common case: nothing left over -- block 0 publishes the ring heads, everyone leaves */
     if (blockIdx.x == 0 && threadIdx.x < (uint32_t)L) {
-      const uint32_t n = RA.P.n;
-      const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
-      const unsigned long long res_a = (pay_rel + RA.A.blob0_bytes + RA.blob1_res + 31ull) & ~31ull;
-      const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
+      const unsigned long long res_a = RA.res_a, res_d = RA.res_d;
       S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
       S.seg_seq[threadIdx.x] += 2ull;
       if (threadIdx.x == 0) {
@@ -672,10 +662,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
     const uint32_t nteams = gridDim.x * (GPX_BLOCK / 32u) * TPW;
     const uint32_t team = team_in_warp < TPW ? (blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5)) * TPW + team_in_warp
                                              : 0xffffffffu;
-    const unsigned long long pay_bytes = A.blob0_bytes + RA.blob1_res;
-    const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
-    const unsigned long long res_a = (pay_rel + pay_bytes + 31ull) & ~31ull;
-    const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
+    const unsigned long long pay_rel = RA.pay_rel, res_a = RA.res_a, res_d = RA.res_d;
     const uint32_t myl = sub < (uint32_t)L ? sub : 0u;
     const unsigned long long seg = seg_base(S, myl, res_a + res_d); /* same segments as the fast kernel */
     const unsigned long long payb = seg + pay_rel, dseg = seg + res_a;
@@ -693,10 +680,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
   if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[5], 1u) == gridDim.x - 1);
   __syncthreads();
   if (s_last && threadIdx.x < (uint32_t)L) {
-    const uint32_t n = RA.P.n;
-    const unsigned long long pay_rel = 64ull + (unsigned long long)n * 48ull;
-    const unsigned long long res_a = (pay_rel + RA.A.blob0_bytes + RA.blob1_res + 31ull) & ~31ull;
-    const unsigned long long res_d = 64ull + (unsigned long long)n * 32ull;
+    const unsigned long long res_a = RA.res_a, res_d = RA.res_d;
     S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
     S.seg_seq[threadIdx.x] += 2ull;
   }
