@@ -115,6 +115,33 @@ class RoundIO(C.Structure):
                 ("extra", C.c_void_p), ("extra_cap", C.c_uint32)]
 
 
+SPREAD_MAX_NODES = 8
+SPREAD_GRAPH = 1
+
+
+class SpreadConfig(C.Structure):
+    """gpx_spread_config (include/gpx.h)"""
+    _fields_ = [("n_nodes", C.c_uint32), ("node_ids", C.c_int32 * SPREAD_MAX_NODES),
+                ("cap", (C.c_uint32 * SPREAD_MAX_NODES) * SPREAD_MAX_NODES), ("blob_per_rec", C.c_uint32),
+                ("max_reqs", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32 * 8)]
+
+
+class SpreadPlan(C.Structure):
+    """gpx_spread_plan"""
+    _U64x3 = (C.c_uint64 * SPREAD_MAX_NODES) * 3
+    _fields_ = [("n_nodes", C.c_uint32), ("rank", C.c_uint32), ("send_off", _U64x3), ("send_bytes", _U64x3),
+                ("recv_off", _U64x3), ("recv_bytes", _U64x3), ("vbase", C.c_uint32 * SPREAD_MAX_NODES),
+                ("vtotal", C.c_uint32), ("blob_off", C.c_uint64 * SPREAD_MAX_NODES), ("blob_vtotal", C.c_uint64),
+                ("arena_bytes", C.c_uint64)]
+
+
+class SpreadIO(C.Structure):
+    """gpx_spread_io: device pointers of one node's round"""
+    _fields_ = [("reqs", C.c_void_p), ("payload", C.c_void_p), ("payload_bytes", C.c_uint64), ("n", C.c_uint32),
+                ("reserved", C.c_uint32), ("status", C.c_void_p), ("exec", C.c_void_p), ("extra", C.c_void_p),
+                ("extra_cap", C.c_uint32), ("reserved2", C.c_uint32), ("ctl", C.c_void_p)]
+
+
 class GpxError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"gpx error {code}: {msg}")

@@ -52,7 +52,7 @@ def build_engine(force: bool = False, verbose: bool = False, out: str = LIB, def
         return out
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cpp"))]
     cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", out, *units]
+           "-o", out, *units, "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -8,6 +8,8 @@
  * fallback: without a CUDA device gpx_engine_create fails with GPX_ENOGPU.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> /* types only: libnccl.so.2 is loaded at run time (gpx_spread_host.inc) */
 
 #include <algorithm>
 #include <cstdio>
@@ -19,6 +21,7 @@
 
 #include "gpx_round.cuh"
 #include "gpx_route.cuh"
+#include "gpx_spread.cuh"
 #include "gpx_prepare.cuh"
 
 static thread_local std::string g_err;
@@ -1345,5 +1348,7 @@ int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t
   CK(cudaStreamSynchronize(e->stream));
   return GPX_OK;
 }
+
+#include "gpx_spread_host.inc"
 
 } /* extern "C" */

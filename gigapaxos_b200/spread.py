@@ -371,3 +371,84 @@ class SpreadCluster:
             for k in ("_keep", "_keep2", "_keep3", "_keep4"):
                 s.pop(k, None)
         return st
+
+
+# ======================================================================================================
+# The data plane behind the C ABI (include/gpx.h gpx_spread_*): no Python, no host count reads per round.
+# ======================================================================================================
+def spread_caps(coord: np.ndarray, member_of: np.ndarray, slots_per_round: int = 1, slack: int = 0) -> np.ndarray:
+    """cap[s][d] = groups node s coordinates that node d is a member of (x slots a round may open per group):
+    the bucket capacities every node of the spread group must agree on (gpx_spread_config.cap)."""
+    n = member_of.shape[1]
+    cap = np.zeros((SPREAD_MAX_NODES_PY, SPREAD_MAX_NODES_PY), dtype=np.uint32)
+    for s in range(n):
+        mine = member_of[coord == s]
+        if len(mine):
+            cap[s, :n] = mine.sum(axis=0) * slots_per_round
+    cap[cap > 0] += slack
+    return cap
+
+
+SPREAD_MAX_NODES_PY = abi.SPREAD_MAX_NODES
+
+
+def spread_config(node_ids: Sequence[int], cap: np.ndarray, blob_per_rec: int, max_reqs: int,
+                  graph: bool = False) -> "abi.SpreadConfig":
+    c = abi.SpreadConfig()
+    c.n_nodes = len(node_ids)
+    for i, x in enumerate(node_ids):
+        c.node_ids[i] = int(x)
+    for s in range(abi.SPREAD_MAX_NODES):
+        for d in range(abi.SPREAD_MAX_NODES):
+            c.cap[s][d] = int(cap[s, d])
+    c.blob_per_rec = (int(blob_per_rec) + 15) // 16 * 16
+    c.max_reqs = int(max_reqs)
+    c.flags = abi.SPREAD_GRAPH if graph else 0
+    return c
+
+
+def spread_plan(lib: Library, cfg: "abi.SpreadConfig", rank: int) -> "abi.SpreadPlan":
+    p = abi.SpreadPlan()
+    lib.check(lib.fn("spread_plan_node")(C.byref(cfg), C.c_uint32(rank), C.byref(p)))
+    return p
+
+
+class Spread:
+    """gpx_spread handle: `engines` are this process's nodes (all of them = local mode; exactly one + an NCCL
+    unique id = one process per GPU)."""
+
+    def __init__(self, lib: Library, engines: Sequence[Engine], cfg: "abi.SpreadConfig", rank: Optional[int] = None,
+                 unique_id: Optional[bytes] = None):
+        self.lib, self.cfg, self.engines = lib, cfg, list(engines)
+        self._h = C.c_void_p()
+        if unique_id is None:
+            arr = (C.c_void_p * len(engines))(*[e.handle for e in engines])
+            lib.check(lib.fn("spread_create_local")(arr, C.byref(cfg), C.byref(self._h)))
+            self.ranks = list(range(len(engines)))
+        else:
+            assert len(engines) == 1 and rank is not None and len(unique_id) == 128
+            buf = C.create_string_buffer(unique_id, 128)
+            lib.check(lib.fn("spread_create_nccl")(engines[0].handle, C.byref(cfg), C.c_uint32(rank), buf,
+                                                   C.byref(self._h)))
+            self.ranks = [rank]
+        self.plans = [spread_plan(lib, cfg, r) for r in self.ranks]
+
+    @staticmethod
+    def unique_id(lib: Library) -> bytes:
+        buf = C.create_string_buffer(128)
+        lib.check(lib.fn("spread_unique_id")(buf))
+        return buf.raw
+
+    def round(self, ios: Sequence["abi.SpreadIO"], stream: int):
+        arr = (abi.SpreadIO * len(ios))(*ios)
+        self.lib.check(self.lib.fn("spread_round")(self._h, arr, C.c_void_p(stream)))
+
+    def dropped(self, k: int = 0) -> int:
+        out = C.c_uint32(0)
+        self.lib.check(self.lib.fn("spread_dropped")(self._h, C.c_uint32(k), C.byref(out)))
+        return out.value
+
+    def close(self):
+        if self._h:
+            self.lib.fn("spread_destroy")(self._h)
+            self._h = C.c_void_p()

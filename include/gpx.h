@@ -535,6 +535,80 @@ int gpx_replies_device(gpx_engine* e, const gpx_accept_reply_rec* replies, uint3
 int gpx_decisions_device(gpx_engine* e, gpx_decision_rec* decisions, uint32_t n, gpx_exec_rec* out_exec,
                          gpx_exec_rec* out_extra, uint32_t extra_cap, gpx_dev_ctl* ctl, void* stream);
 
+/* ---- SPREAD placement behind the C ABI: the replicas of a group live in DIFFERENT engines -- one
+ * single-lane engine per node, one node per GPU, replica j of a group on node (home + j) mod N
+ * (PISM.roundRobinCoordinator :2251-2256) -- and the three inter-replica packet types of a round (ACCEPT,
+ * ACCEPT_REPLY, DECISION; unicast fan-out paxosutil/PaxosMessenger.java:175-182, PaxosManager.send :2098-2128,
+ * per-destination batching PaxosPacketBatcher.java:270-303) cross GPUs as fixed-capacity buckets whose record
+ * count travels in-band: no host ever reads a count, a whole round is one asynchronous enqueue (optionally one
+ * CUDA-graph launch) of  k_propose -> k_sp_route -> [exchange] -> k_sp_accept -> [exchange] -> k_sp_tally ->
+ * [exchange] -> k_sp_commit.  The exchange is one ncclGroupStart / ncclSend + ncclRecv per peer / ncclGroupEnd per
+ * packet type over NVLink (one process per GPU; libnccl.so.2 is loaded at run time), or plain device copies
+ * when all nodes are engines of one process ("local" mode: tests on a single GPU).
+ *
+ * A Java PaxosManager would create one engine + one spread handle per GPU process, hand every batch of client
+ * requests for the groups it coordinates to gpx_spread_round and apply the EXEC records it gets back; every
+ * process of the spread group calls gpx_spread_round once per round (an empty batch still takes part in the
+ * exchanges). */
+#define GPX_SPREAD_MAX_NODES 8
+#define GPX_SPREAD_GRAPH 1u /* capture a round into a CUDA graph per distinct io block and replay it */
+typedef struct gpx_spread gpx_spread;
+typedef struct gpx_spread_config {
+  uint32_t n_nodes;                                         /* engines (nodes) of the spread group */
+  int32_t node_ids[GPX_SPREAD_MAX_NODES];                   /* node id served by engine i (its lane 0) */
+  uint32_t cap[GPX_SPREAD_MAX_NODES][GPX_SPREAD_MAX_NODES]; /* cap[s][d]: ACCEPTs node s may send node d in one round
+                                                             * (>= groups s coordinates that d is a member of, times the
+                                                             * slots a round may open per group); cap[s][s] is the
+                                                             * loop-back bucket; 0 = the pair never exchanges.  The same
+                                                             * matrix on every node. */
+  uint32_t blob_per_rec; /* blob bytes a bucket reserves per record slot (multiple of 16): request bodies travel
+                          * with their ACCEPT (AcceptPacket carries the RequestPacket, AcceptPacket.java:95-138) */
+  uint32_t max_reqs;     /* requests one node submits per round (<= the engine's max_batch_recs) */
+  uint32_t flags;        /* GPX_SPREAD_GRAPH */
+  uint32_t reserved[8];
+} gpx_spread_config;
+/* what one node's buffers look like: byte offsets into its bucket arena, transfer sizes (0 = no transfer with that
+ * peer), and the virtual index space of its receive side.  kind 0 = ACCEPT, 1 = ACCEPT_REPLY, 2 = DECISION.
+ * Pure host arithmetic: send_bytes[k][d] of node s equals recv_bytes[k][s] of node d. */
+typedef struct gpx_spread_plan {
+  uint32_t n_nodes, rank;
+  uint64_t send_off[3][GPX_SPREAD_MAX_NODES], send_bytes[3][GPX_SPREAD_MAX_NODES];
+  uint64_t recv_off[3][GPX_SPREAD_MAX_NODES], recv_bytes[3][GPX_SPREAD_MAX_NODES];
+  uint32_t vbase[GPX_SPREAD_MAX_NODES]; /* first virtual record index of the bucket received from node s */
+  uint32_t vtotal;                      /* EXEC slots / log image slots per round at this node */
+  uint64_t blob_off[GPX_SPREAD_MAX_NODES];
+  uint64_t blob_vtotal;
+  uint64_t arena_bytes;
+} gpx_spread_plan;
+int gpx_spread_plan_node(const gpx_spread_config* cfg, uint32_t rank, gpx_spread_plan* out);
+/* per node and round: device pointers owned by the caller */
+typedef struct gpx_spread_io {
+  const gpx_request_rec* reqs; /* [n] requests for groups this node coordinates, grouped by gid (entry lane 0) */
+  const uint8_t* payload;
+  uint64_t payload_bytes;
+  uint32_t n;
+  uint32_t reserved;
+  int32_t* status;    /* [n] */
+  gpx_exec_rec* exec; /* [plan.vtotal]: EXEC record of the DECISION at that virtual index, VOID holes elsewhere */
+  gpx_exec_rec* extra;
+  uint32_t extra_cap;
+  uint32_t reserved2;
+  gpx_dev_ctl* ctl;   /* zeroed by the round; n_accepts / n_extra when it is done */
+} gpx_spread_io;
+/* 128-byte NCCL unique id (ncclGetUniqueId): made by one process, handed to the others by the host's own channel */
+int gpx_spread_unique_id(void* out_id128);
+/* one process per node: `e` is node `rank` of cfg->n_nodes; collective over the spread group (ncclCommInitRank) */
+int gpx_spread_create_nccl(gpx_engine* e, const gpx_spread_config* cfg, uint32_t rank, const void* id128,
+                           gpx_spread** out);
+/* all cfg->n_nodes nodes are engines of this process (same device): the exchange is a set of device copies */
+int gpx_spread_create_local(gpx_engine* const* engines, const gpx_spread_config* cfg, gpx_spread** out);
+void gpx_spread_destroy(gpx_spread* sp);
+/* one round, asynchronous on `stream`.  io[k] belongs to the k-th local node (NCCL mode: one; local mode: n_nodes) */
+int gpx_spread_round(gpx_spread* sp, const gpx_spread_io* io, void* stream);
+/* records k_sp_route could not place since creation (bucket too small / member node not in the spread group);
+ * synchronises the device */
+int gpx_spread_dropped(gpx_spread* sp, uint32_t local_index, uint32_t* out);
+
 /* per-kernel CUDA-event timing of the last gpx_round_device calls (ms, accumulated) */
 typedef struct gpx_kernel_times {
   double propose_ms, accept_ms, tally_ms, commit_ms;
