@@ -295,11 +295,16 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-large", action="store_true", help="skip the 1M-group roofline context measurement")
-    ap.add_argument("--placement", default="packed", choices=["packed", "spread"],
-                    help="packed (default): all replicas of a group on its home GPU, no data-path collective; spread: "
+    ap.add_argument("--placement", default="auto", choices=["auto", "packed", "spread"],
+                    help="auto (default): spread when the job has at least as many GPUs as replicas (SURVEY.md 8e), "
+                         "else packed.  packed: all replicas of a group on its home GPU, no data-path collective; spread: "
                          "replica j on GPU (home+j) mod N, ACCEPT/REPLY/DECISION records exchanged over NCCL "
                          "(needs N >= replicas; with --gpus 1 the nodes are --spread-nodes engines on one GPU)")
     ap.add_argument("--spread-nodes", type=int, default=4)
+    ap.add_argument("--spread-python", action="store_true",
+                    help="spread placement through the host-orchestrated reference path (gigapaxos_b200/spread.py "
+                         "SpreadCluster: torch.distributed exchanges, one host count read per exchange) instead of gpx_spread_*")
+    ap.add_argument("--no-graph", action="store_true", help="spread: plain stream launches instead of one CUDA graph per round")
     args = ap.parse_args()
 
     wl = dict(WORKLOADS[args.workload])
@@ -312,12 +317,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.placement == "auto":
+        args.placement = "spread" if (world >= R and world > 1) else "packed"
     metric = "paxos_decisions_per_sec"
     config = {
         "workload": wl["name"], "groups_per_gpu": G, "replicas": R, "payload_bytes": P, "window": 8,
         "requests_per_group_per_step": 1,
         "placement": "packed: all R replicas of a group on the GPU that owns the group; groups sharded by "
-                     "|String.hashCode(paxosID)| mod n_gpus; no data-path collective",
+                     "|String.hashCode(paxosID)| mod n_gpus; no data-path collective"
+                     + ("" if world >= R or world == 1 else f" (fewer GPUs than replicas: SURVEY.md 8e packs them)"),
         "l2": "none" if args.no_flush else "flushed between timed steps (256 MiB write, outside the timed events)",
         "init": "batch creation (HotRestoreInfo.createHRI)",
     }
@@ -340,7 +348,7 @@ def main():
         emit(line)
         return
 
-    os.environ.pop("NCCL_DEBUG", None)  # (stdout is diverted anyway: rank 0 prints ONE JSON line)
+    # (NCCL_DEBUG is left as the launcher set it: NCCL's log lines go to the diverted stdout = stderr)
     import torch
     import torch.distributed as dist
 
@@ -356,7 +364,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     lib = gigapaxos_b200.load_library()
     if args.placement == "spread":
-        run_spread(args, lib, dev, rank, world, G, R, P, K, max(W, 3), metric, config)
+        (run_spread if args.spread_python else run_spread_c)(args, lib, dev, rank, world, G, R, P, K, max(W, 3), metric,
+                                                              config)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -667,6 +676,245 @@ def main():
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def spread_placement(N, G, R, node_ids):
+    """G groups per coordinator node: names NoopPaxosApp<i>, i = 0, 1, ...; replica j of a group on node
+    (home + j) mod N, coordinator = PISM.roundRobinCoordinator(0).  Node c coordinates the global
+    gids [c*G, (c+1)*G).  Returns (descs, member_of[N*G, N], coord[N*G])."""
+    from gigapaxos_b200 import abi
+    from gigapaxos_b200.spread import coordinator_of, members_of
+    per, i, total = [[] for _ in range(N)], 0, 0
+    while total < N * G:
+        nm = f"NoopPaxosApp{i}"
+        mem = [node_ids[m] for m in members_of(nm, N, R)]
+        c = coordinator_of(nm, mem) - node_ids[0]
+        if len(per[c]) < G:
+            per[c].append((nm, mem))
+            total += 1
+        i += 1
+    descs = np.zeros(N * G, dtype=abi.group_desc_dtype)
+    member_of = np.zeros((N * G, N), dtype=bool)
+    coord = np.repeat(np.arange(N), G)
+    for c in range(N):
+        for k, (nm, mem) in enumerate(per[c]):
+            g = c * G + k
+            descs[g]["gid"] = g
+            descs[g]["name_hash"] = abi.java_string_hash(nm)
+            descs[g]["n_members"] = R
+            descs[g]["members"][:R] = mem
+            descs[g]["init_mode"] = abi.INIT_BATCH
+            member_of[g, [m - node_ids[0] for m in mem]] = True
+    return descs, member_of, coord
+
+
+def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
+    """Spread placement behind the C ABI (gpx_spread_*, gigapaxos_b200/csrc/gpx_spread.cuh): one single-lane engine per
+    GPU, every node coordinates G groups and is an acceptor of (R-1)*G more; a step = one request for every group; the
+    ACCEPT / ACCEPT_REPLY / DECISION records cross GPUs as fixed-capacity buckets through grouped ncclSend/ncclRecv
+    issued by libgpx itself (no Python and no host count read inside a round)."""
+    import torch
+    import torch.distributed as dist
+
+    from gigapaxos_b200 import abi
+    from gigapaxos_b200.abi import Engine
+    from gigapaxos_b200.spread import Spread, spread_caps, spread_config
+    N = world if world > 1 else args.spread_nodes
+    if N < R:
+        raise SystemExit(f"spread placement needs at least {R} nodes")
+    node_ids = [NODES[0] + i for i in range(N)]
+    descs, member_of, coord = spread_placement(N, G, R, node_ids)
+    local = list(range(N)) if world == 1 else [rank]
+    cap = spread_caps(coord, member_of)
+    blob_per_rec = (P + 15) // 16 * 16
+    scfg = spread_config(node_ids, cap, blob_per_rec=blob_per_rec, max_reqs=G, graph=not args.no_graph)
+    engines = []
+    for idx in local:
+        n_in = int(member_of[:, idx].sum())
+        vt = sum(((int(cap[s, idx]) + 255) // 256) * 256 for s in range(N))
+        per_round = 256 + 80 * vt + n_in * blob_per_rec
+        ring = 1 << 26
+        while ring < 4 * per_round:
+            ring <<= 1
+        cfg = lib.config_defaults()
+        cfg.device = dev.index or 0
+        cfg.max_groups = N * G
+        cfg.n_lanes = 1
+        cfg.lane_node[0] = node_ids[idx]
+        cfg.window = 8
+        cfg.max_group_size = R
+        cfg.max_batch_recs = G
+        cfg.max_batch_payload = G * P + 16
+        cfg.log_ring_bytes = ring
+        e = Engine(lib, cfg)
+        e.create_groups(descs[member_of[:, idx]])
+        engines.append(e)
+    if world > 1:
+        ids = [Spread.unique_id(lib) if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=dev)
+        sp = Spread(lib, engines, scfg, rank=rank, unique_id=ids[0])
+    else:
+        sp = Spread(lib, engines, scfg)
+    NB = 4
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    bufs = []  # per local node: device buffers
+    for k, idx in enumerate(local):
+        vt = sp.plans[k].vtotal
+        b = {"status": torch.zeros(G, dtype=torch.int32, device=dev),
+             "exec": torch.zeros(max(vt, 1) * 24, dtype=torch.uint8, device=dev),
+             "extra": torch.zeros(4096 * 24, dtype=torch.uint8, device=dev),
+             "ctl": torch.zeros(8, dtype=torch.int32, device=dev), "reqs": [], "pay": [], "h_reqs": [], "h_pay": []}
+        for nb in range(NB):
+            reqs, pay = make_batch(abi, G, P, 1000 * idx + nb)
+            reqs["gid"] = np.arange(idx * G, (idx + 1) * G, dtype=np.uint32)
+            reqs["entry_node"] = node_ids[idx]
+            pay = np.concatenate([pay, np.zeros(16, np.uint8)])
+            b["h_reqs"].append(torch.from_numpy(reqs.view(np.uint8).copy()).pin_memory())
+            b["h_pay"].append(torch.from_numpy(pay).pin_memory())
+            b["reqs"].append(b["h_reqs"][-1].to(dev))
+            b["pay"].append(b["h_pay"][-1].to(dev))
+        bufs.append(b)
+
+    def make_ios(nb, reqs_key="reqs", pay_key="pay"):
+        ios = []
+        for b in bufs:
+            io = abi.SpreadIO()
+            io.reqs, io.payload, io.payload_bytes, io.n = b[reqs_key][nb].data_ptr(), b[pay_key][nb].data_ptr(), G * P, G
+            io.status, io.exec = b["status"].data_ptr(), b["exec"].data_ptr()
+            io.extra, io.extra_cap, io.ctl = b["extra"].data_ptr(), 4096, b["ctl"].data_ptr()
+            ios.append(io)
+        return ios
+
+    ios = [make_ios(nb) for nb in range(NB)]
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    st = stream.cuda_stream
+    for w in range(max(W, 2 * NB)):
+        sp.round(ios[w % NB], st)
+    sampler = ClockSampler(dev.index or 0)
+    barrier()
+    c0 = [e.counters() for e in engines]
+    sampler.start()
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for k in range(K):
+        if not args.no_flush:
+            flush_buf.zero_()
+        ev_s[k].record()
+        sp.round(ios[k % NB], st)
+        ev_e[k].record()
+    barrier()
+    clocks = sampler.stop()
+    step_ms = np.array([ev_s[k].elapsed_time(ev_e[k]) for k in range(K)])
+    total_ms = allmax(float(step_ms.sum()))
+    c1 = [e.counters() for e in engines]
+    for k, (a, b) in enumerate(zip(c0, c1)):
+        n_in = int(member_of[:, local[k]].sum())
+        assert b["decisions_made"] - a["decisions_made"] == G * K, "every coordinated group decides once per step"
+        assert b["executed"] - a["executed"] == n_in * K, "every replica executes every decision"
+        assert sp.dropped(k) == 0
+    value = N * G * K / (total_ms / 1e3)
+
+    # back-to-back rounds without the L2 flush in between (how a loaded node runs: the next round's kernels start
+    # while nothing else touches the GPU); reported beside the flushed number
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        sp.round(ios[k % NB], st)
+    e1.record()
+    barrier()
+    b2b_ms = allmax(e0.elapsed_time(e1)) / K
+
+    # per-kernel share of a round: CUDA events between the phases cannot be placed inside the C call (and inside a
+    # graph), so a non-graph handle is timed phase by phase through the per-phase wall of the ncu launch list under
+    # profiles/; here only the whole round is timed.
+
+    # ---- e2e: host (pinned) request batches in, status + EXEC records out, copies inside the timed region ----------
+    e2e = None
+    if not args.skip_e2e:
+        h_status = [torch.zeros(G, dtype=torch.int32).pin_memory() for _ in bufs]
+        h_exec = [torch.zeros(b["exec"].numel(), dtype=torch.uint8).pin_memory() for b in bufs]
+        for b in bufs:  # device staging the copies land in (fixed addresses: one graph)
+            b["s_reqs"] = [torch.zeros_like(b["reqs"][0])]
+            b["s_pay"] = [torch.zeros_like(b["pay"][0])]
+        ios_e = make_ios(0, "s_reqs", "s_pay")
+
+        def e2e_step(k):
+            for b in bufs:
+                b["s_reqs"][0].copy_(b["h_reqs"][k % NB], non_blocking=True)
+                b["s_pay"][0].copy_(b["h_pay"][k % NB], non_blocking=True)
+            sp.round(ios_e, st)
+            for j, b in enumerate(bufs):
+                h_status[j].copy_(b["status"], non_blocking=True)
+                h_exec[j].copy_(b["exec"], non_blocking=True)
+
+        for k in range(3):
+            e2e_step(k)
+        K3 = max(10, min(K, 30))
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K3):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        dt = allmax(time.perf_counter() - t0)
+        ex = h_exec[0].numpy().view(abi.exec_dtype)
+        assert int(((ex["flags"] & abi.F_VOID) == 0).sum()) == int(member_of[:, local[0]].sum())
+        assert np.all(h_status[0].numpy() > 0)
+        e2e = {"value": N * G * K3 / dt, "unit": "decisions/s", "steps": K3, "ms_per_step": 1e3 * dt / K3,
+               "h2d_bytes_per_step": int(G * 32 + G * P + 16), "d2h_bytes_per_step": int(G * 4 + h_exec[0].numel()),
+               "api": "gpx_spread_round (include/gpx.h) per GPU process on request batches copied from pinned host "
+                      "memory each step; status + one 24-byte EXEC record per executed (group, replica) copied back; "
+                      "one stream, wall clock around all steps"}
+
+    if rank == 0:
+        n_in = int(member_of[:, local[0]].sum())
+        peak, peak_src = hbm_peak()
+        cfg = dict(config)
+        link_bytes = int(sum(sp.plans[0].send_bytes[k][d] for k in range(3) for d in range(N) if d != local[0]))
+        cfg.update({"groups_per_gpu": G, "accepts_in_per_node_per_step": n_in,
+                    "placement": f"spread: {N} nodes, one single-lane engine per "
+                    + ("GPU; libgpx issues grouped ncclSend/ncclRecv of fixed-capacity buckets over NVLink"
+                       if world > 1 else "node, all on ONE GPU (device copies)")
+                    + f"; replica j of a group on node (home+j) mod {N}; three record exchanges per round; "
+                    + ("one CUDA graph launch per round" if not args.no_graph else "stream launches"),
+                    "nvlink_bytes_sent_per_gpu_per_step": link_bytes})
+        ms = total_ms / K
+        # algorithmic HBM bytes of one node's round: the phase pipeline's B_slot spread over the nodes (SURVEY.md 8d)
+        bytes_round = G * b_slot(R, P)
+        line = {
+            "metric": metric, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": K, "warmup": max(W, 2 * NB),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": cfg,
+            "roofline": {"kernel": "one node's whole spread round (k_propose, k_build_blobs, k_sp_route, k_sp_accept, "
+                                   "k_sp_tally, k_sp_commit + 3 bucket exchanges)", "bound": "hbm",
+                         "achieved": bytes_round / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": bytes_round,
+                         "bytes_per_decided_slot": b_slot(R, P), "kernel_ms": ms,
+                         "frac": bytes_round / (ms / 1e3) / 1e9 / peak,
+                         "nvlink": {"bytes_sent_per_gpu": link_bytes, "min_ms_at_770GBs": link_bytes / 770e9 * 1e3}},
+            "back_to_back_ms_per_step": b2b_ms, "back_to_back_decisions_per_sec": N * G / (b2b_ms / 1e3),
+            "cpu_baseline": None, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": K * 6 * len(local), "p50_decide_latency_ms": float(np.median(step_ms)),
+        }
+        emit(line)
+    sp.close()
+    for e in engines:
+        e.close()
 
 
 def run_spread(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
