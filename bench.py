@@ -42,6 +42,10 @@ WORKLOADS = {
                  P=64),
     "1m1b": dict(name="3-replica, 1M groups, 1-byte requests, single B200 (north_star target size)", G=1_000_000,
                  R=3, P=1),
+    "cfg4": dict(name="5-replica, 1M groups, mixed 1-1024 B requests with reconfiguration churn (0.1% of the groups "
+                      "STOP and are re-created at the next epoch every round)", G=1_000_000, R=5, P=512),
+    "cfg5": dict(name="3-replica, 10M groups resident, accept-batch sweep 1-1024 requests per batch on a 1% active "
+                      "subset", G=10_000_000, R=3, P=1),
 }
 NODES = (100, 101, 102, 103, 104)
 
@@ -62,6 +66,46 @@ def b_act(R: int, P: int) -> int:
     4R in + 4R out.  (The DECISION record and the reply out-mask are no longer written by the fast path: every
     member is a local lane, nobody reads them.)"""
     return (32 + P + 4) + R * (4 + 16 + 16 + 32 + 48 + P + 32 + 24) + (32 + 8 * R)
+
+
+def b_act_batched(R: int, P: int, b: int) -> int:
+    """b_act for a slot that carries b requests of P bytes (replace 2P by 2bP + 16b): b request records
+    + bodies + statuses in, the constructed blob [b x 16 B entries][bodies] written once and logged by every replica."""
+    blob = 16 * b + b * P
+    return (32 * b + b * P + 4 * b) + blob + R * (4 + 16 + 16 + 32 + 48 + blob + 32 + 24) + (32 + 8 * R)
+
+
+def java_hash_numbered(prefix: str, idx: np.ndarray) -> np.ndarray:
+    """String.hashCode() of f"{prefix}{i}" for every i of idx, vectorised"""
+    idx = np.asarray(idx, dtype=np.int64)
+    h0 = np.uint32(java_hash(prefix) & 0xFFFFFFFF)
+    out = np.zeros(len(idx), dtype=np.uint32)
+    ndig = np.ones(len(idx), dtype=np.int64)
+    t = idx // 10
+    while np.any(t > 0):
+        ndig += (t > 0)
+        t //= 10
+    for nd in np.unique(ndig):
+        sel = np.nonzero(ndig == nd)[0]
+        v = idx[sel]
+        h = np.full(len(sel), h0, dtype=np.uint32)
+        for k in range(int(nd) - 1, -1, -1):
+            with np.errstate(over="ignore"):
+                h = h * np.uint32(31) + ((v // (10 ** k)) % 10 + 48).astype(np.uint32)
+        out[sel] = h
+    return out.view(np.int32)
+
+
+def make_descs_fast(abi, G, R, gid0=0, name0=0, prefix="NoopPaxosApp", version=0):
+    d = np.zeros(G, dtype=abi.group_desc_dtype)
+    d["gid"] = np.arange(gid0, gid0 + G, dtype=np.uint32)
+    d["version"] = version
+    d["name_hash"] = java_hash_numbered(prefix, np.arange(name0, name0 + G))
+    d["n_members"] = R
+    for i in range(R):
+        d["members"][:, i] = NODES[i]
+    d["init_mode"] = abi.INIT_BATCH
+    return d
 
 
 def hbm_peak():
@@ -366,6 +410,11 @@ def main():
     if args.placement == "spread":
         (run_spread if args.spread_python else run_spread_c)(args, lib, dev, rank, world, G, R, P, K, max(W, 3), metric,
                                                               config)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if args.workload in ("cfg4", "cfg5"):
+        (run_cfg4 if args.workload == "cfg4" else run_cfg5)(args, lib, dev, rank, world, wl, K, max(W, 3), metric, config)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -676,6 +725,275 @@ def main():
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _bench_common(dev, world):
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+    return barrier, allmax
+
+
+def run_cfg4(args, lib, dev, rank, world, wl, K, W, metric, config):
+    """BASELINE config 4: 5 replicas, request sizes uniform in 1..1024 B (seed 2), and reconfiguration churn INSIDE the
+    timed region: every round 0.1 % of the groups receive a STOP (PISM.handleCommittedRequest stop path, executed in
+    order on all 5 replicas), the stopped groups are killed and re-created at epoch + 1 with fresh state
+    (PaxosManager.kill :2162 + createPaxosInstance :632 -> gpx_destroy_groups + gpx_create_groups; the version drop rule
+    PISM :441-447 is where names map to gids).  Packed placement: groups sharded by paxosID hash, all 5 replicas of a
+    group on its home GPU."""
+    import torch
+    from gigapaxos_b200 import abi
+    from gigapaxos_b200.abi import DevRoundBufs, Engine
+    G = args.groups or wl["G"] // max(world, 1)
+    R = wl["R"]
+    barrier, allmax = _bench_common(dev, world)
+    churn = max(1, G // 1000)
+    NB = 4
+    rng = np.random.default_rng(2 + rank)
+    host = []
+    pay_max = 0
+    for b in range(NB):
+        lens = rng.integers(1, 1025, size=G).astype(np.uint32)
+        stride = (lens + 15) // 16 * 16
+        offs = np.concatenate([[0], np.cumsum(stride)[:-1]]).astype(np.uint32)
+        reqs = np.zeros(G, dtype=abi.request_dtype)
+        reqs["gid"] = np.arange(G, dtype=np.uint32)
+        reqs["req_id"] = rng.integers(1, 1 << 62, size=G, dtype=np.int64)
+        reqs["payload_off"], reqs["payload_len"] = offs, lens
+        reqs["entry_node"] = NODES[0]
+        reqs["client"] = np.arange(G, dtype=np.uint32)
+        stop = rng.choice(G, size=churn, replace=False)
+        reqs["flags"][stop] |= abi.F_STOP
+        total = int(stride.sum())
+        pay = rng.integers(48, 123, size=total, dtype=np.uint8)
+        host.append((reqs, pay, np.sort(stop).astype(np.uint32), int(lens.sum())))
+        pay_max = max(pay_max, total)
+    cfg = lib.config_defaults()
+    cfg.device = dev.index or 0
+    cfg.max_groups, cfg.n_lanes, cfg.window, cfg.max_group_size = G, R, 8, R
+    for i in range(R):
+        cfg.lane_node[i] = NODES[i]
+    cfg.max_batch_recs, cfg.max_batch_payload = G, pay_max + 16
+    per_round = 256 + 80 * G + 2 * pay_max + 16 * G
+    ring = 1 << 26
+    while ring < 3 * per_round:
+        ring <<= 1
+    cfg.log_ring_bytes = ring
+    eng = Engine(lib, cfg)
+    eng.create_groups(make_descs_fast(abi, G, R, name0=rank * G))
+    version = np.zeros(G, dtype=np.int32)
+    name_hash = java_hash_numbered("NoopPaxosApp", np.arange(rank * G, rank * G + G))
+    d_reqs = [torch.from_numpy(h[0].view(np.uint8).copy()).to(dev) for h in host]
+    d_pay = [torch.from_numpy(h[1]).to(dev) for h in host]
+    d_status = torch.zeros(G, dtype=torch.int32, device=dev)
+    d_exec = torch.zeros(G * R * 24, dtype=torch.uint8, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    round_dev = lib.fn("round_device")
+
+    def step(k):
+        b = k % NB
+        bufs = DevRoundBufs(d_reqs[b].data_ptr(), d_pay[b].data_ptr(), d_pay[b].numel(), G, d_status.data_ptr(),
+                            d_exec.data_ptr())
+        if round_dev(eng.handle, C.byref(bufs), C.c_void_p(stream.cuda_stream)) != 0:
+            raise RuntimeError(lib.last_error())
+        # churn: the groups whose STOP was just decided and executed are killed and re-created at the next epoch
+        dead = host[b][2]
+        torch.cuda.current_stream().synchronize()  # the EXEC records of the STOPs are out (the host would apply them)
+        version[dead] += 1
+        nd = np.zeros(len(dead), dtype=abi.group_desc_dtype)
+        nd["gid"], nd["version"], nd["name_hash"], nd["n_members"] = dead, version[dead], name_hash[dead], R
+        for i in range(R):
+            nd["members"][:, i] = NODES[i]
+        nd["init_mode"] = abi.INIT_BATCH
+        eng.destroy_groups(dead)
+        eng.create_groups(nd)
+
+    for w in range(W):
+        step(w)
+    sampler = ClockSampler(dev.index or 0)
+    barrier()
+    c0 = eng.counters()
+    sampler.start()
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_r = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for k in range(K):
+        if not args.no_flush:
+            flush_buf.zero_()
+        ev_s[k].record()
+        b = k % NB
+        bufs = DevRoundBufs(d_reqs[b].data_ptr(), d_pay[b].data_ptr(), d_pay[b].numel(), G, d_status.data_ptr(),
+                            d_exec.data_ptr())
+        if round_dev(eng.handle, C.byref(bufs), C.c_void_p(stream.cuda_stream)) != 0:
+            raise RuntimeError(lib.last_error())
+        ev_r[k].record()
+        dead = host[b][2]
+        stream.synchronize()
+        version[dead] += 1
+        nd = np.zeros(len(dead), dtype=abi.group_desc_dtype)
+        nd["gid"], nd["version"], nd["name_hash"], nd["n_members"] = dead, version[dead], name_hash[dead], R
+        for i in range(R):
+            nd["members"][:, i] = NODES[i]
+        nd["init_mode"] = abi.INIT_BATCH
+        eng.destroy_groups(dead)
+        eng.create_groups(nd)
+        ev_e[k].record()  # the stream is idle: this timestamp is taken when the synchronous churn calls have returned
+    barrier()
+    clocks = sampler.stop()
+    step_ms = np.array([ev_s[k].elapsed_time(ev_e[k]) for k in range(K)])
+    round_ms = np.array([ev_s[k].elapsed_time(ev_r[k]) for k in range(K)])
+    total_ms = allmax(float(step_ms.sum()))
+    c1 = eng.counters()
+    assert c1["decisions_made"] - c0["decisions_made"] == G * K
+    assert c1["executed"] - c0["executed"] == G * K * R
+    assert c1["stops_executed"] - c0["stops_executed"] == churn * K * R
+    value = world * G * K / (total_ms / 1e3)
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        mean_len = float(np.mean([h[3] for h in host])) / G
+        bytes_round = int(G * ((32 + 4) + R * (4 + 16 + 16 + 32 + 48 + 32 + 24) + (32 + 8 * R)) + (1 + R) * G * mean_len)
+        rms = float(round_ms.mean())
+        cfg_out = dict(config)
+        cfg_out.update({"groups_per_gpu": G, "replicas": R, "payload_bytes": "uniform 1..1024 (seed 2)",
+                        "churn": f"{churn} groups per round per GPU: STOP decided + executed on all {R} replicas, then "
+                                 "gpx_destroy_groups + gpx_create_groups at version + 1, inside the timed region"})
+        emit({"metric": metric, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": K, "warmup": W,
+              "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "int32", "data": "synthetic", "config": cfg_out,
+              "roofline": {"kernel": "k_round<5> + k_round_slow<5> (the round without the churn calls)", "bound": "hbm",
+                           "achieved": bytes_round / (rms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": bytes_round,
+                           "kernel_ms": rms, "frac": bytes_round / (rms / 1e3) / 1e9 / peak},
+              "churn_ms_per_step": float((step_ms - round_ms).mean()), "round_ms_per_step": rms,
+              "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": 4 * K,
+              "p50_decide_latency_ms": float(np.median(round_ms))})
+    eng.close()
+
+
+def run_cfg5(args, lib, dev, rank, world, wl, K, W, metric, config):
+    """BASELINE config 5: 10 M groups resident (sharded over the GPUs), each round a 1 % subset is active and every active
+    group receives b requests that the RequestBatcher packs into ONE slot (RequestBatcher.java:198-219); sweep
+    b = 1, 2, 4, ..., 1024.  A round carries at most 4 M requests (active groups = min(1 % of the groups, 4 M / b)).
+    Packed placement (all 3 replicas of a group on its home GPU)."""
+    import torch
+    from gigapaxos_b200 import abi
+    from gigapaxos_b200.abi import DevRoundBufs, Engine
+    GT = args.groups or wl["G"] // max(world, 1)
+    R, P = wl["R"], wl["P"]
+    barrier, allmax = _bench_common(dev, world)
+    A1 = max(GT // 100, 1)
+    MAXREQ = max(A1, min(4_000_000, A1 * 1024))
+    cfg = lib.config_defaults()
+    cfg.device = dev.index or 0
+    cfg.max_groups, cfg.n_lanes, cfg.window, cfg.max_group_size = GT, R, 8, R
+    for i in range(R):
+        cfg.lane_node[i] = NODES[i]
+    cfg.max_batch_recs, cfg.max_batch_payload = MAXREQ, MAXREQ * P + 16
+    per_round = 256 + 80 * MAXREQ + 2 * MAXREQ * P + 16 * MAXREQ
+    ring = 1 << 26
+    while ring < 3 * per_round:
+        ring <<= 1
+    cfg.log_ring_bytes = ring
+    eng = Engine(lib, cfg)
+    t0 = time.perf_counter()
+    for lo in range(0, GT, 2_000_000):
+        n = min(2_000_000, GT - lo)
+        eng.create_groups(make_descs_fast(abi, n, R, gid0=lo, name0=rank * GT + lo))
+    create_s = time.perf_counter() - t0
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    round_dev = lib.fn("round_device")
+    d_status = torch.zeros(MAXREQ, dtype=torch.int32, device=dev)
+    d_exec = torch.zeros(MAXREQ * R * 24, dtype=torch.uint8, device=dev)
+    peak, peak_src = hbm_peak()
+    rng = np.random.default_rng(5 + rank)
+    sweep, clocks_all = [], None
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    NB = 3
+    for b in [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024]:
+        A = max(1, min(A1, MAXREQ // b))
+        n = A * b
+        d_reqs, d_pay = [], []
+        for nb in range(NB):
+            active = np.sort(rng.choice(GT, size=A, replace=False)).astype(np.uint32)
+            reqs = np.zeros(n, dtype=abi.request_dtype)
+            reqs["gid"] = np.repeat(active, b)
+            reqs["req_id"] = rng.integers(1, 1 << 62, size=n, dtype=np.int64)
+            reqs["payload_off"] = np.arange(n, dtype=np.uint32) * P
+            reqs["payload_len"] = P
+            reqs["entry_node"] = NODES[0]
+            reqs["client"] = np.arange(n, dtype=np.uint32)
+            d_reqs.append(torch.from_numpy(reqs.view(np.uint8)).to(dev))
+            d_pay.append(torch.from_numpy(rng.integers(48, 123, size=n * P + 16, dtype=np.uint8)).to(dev))
+
+        def step(k):
+            q = k % NB
+            bufs = DevRoundBufs(d_reqs[q].data_ptr(), d_pay[q].data_ptr(), n * P, n, d_status.data_ptr(), d_exec.data_ptr())
+            if round_dev(eng.handle, C.byref(bufs), C.c_void_p(stream.cuda_stream)) != 0:
+                raise RuntimeError(lib.last_error())
+        for w in range(W):
+            step(w)
+        barrier()
+        c0 = eng.counters()
+        ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        for k in range(K):
+            if not args.no_flush:
+                flush_buf.zero_()
+            ev_s[k].record()
+            step(k)
+            ev_e[k].record()
+        barrier()
+        ms = np.array([ev_s[k].elapsed_time(ev_e[k]) for k in range(K)])
+        total_ms = allmax(float(ms.sum()))
+        c1 = eng.counters()
+        assert c1["decisions_made"] - c0["decisions_made"] == A * K, (b, c1["decisions_made"] - c0["decisions_made"], A * K)
+        assert c1["executed"] - c0["executed"] == A * K * R
+        assert c1["requests_batched"] - c0["requests_batched"] == n * K
+        per = total_ms / K
+        bytes_round = A * b_act_batched(R, P, b)
+        sweep.append({"requests_per_batch": b, "active_groups_per_gpu": A, "requests_per_step_per_gpu": n,
+                      "ms_per_step": per, "decisions_per_sec": world * A / (per / 1e3),
+                      "requests_per_sec": world * n / (per / 1e3), "p50_ms": float(np.median(ms)),
+                      "roofline_frac": bytes_round / (per / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": bytes_round})
+        del d_reqs, d_pay
+    clocks = sampler.stop()
+    if rank == 0:
+        best = max(sweep, key=lambda x: x["requests_per_sec"])
+        head = sweep[0]
+        cfg_out = dict(config)
+        cfg_out.update({"groups_per_gpu": GT, "groups_total": GT * world, "replicas": R, "payload_bytes": P,
+                        "active_fraction": 0.01, "max_requests_per_step": MAXREQ,
+                        "device_memory_used_gb": round((total_b - free_b) / 1e9, 2), "group_creation_s": round(create_s, 2)})
+        emit({"metric": metric, "value": head["decisions_per_sec"], "unit": "decisions/s", "n_gpus": world, "steps": K,
+              "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg_out,
+              "roofline": {"kernel": "k_round + k_round_slow at b = 1 (in-order fast path over the active 1 %)", "bound": "hbm",
+                           "achieved": head["algorithmic_bytes_per_step"] / (head["ms_per_step"] / 1e3) / 1e9,
+                           "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                           "algorithmic_bytes_per_launch": head["algorithmic_bytes_per_step"],
+                           "kernel_ms": head["ms_per_step"], "frac": head["roofline_frac"]},
+              "sweep": sweep, "best_requests_per_sec": best["requests_per_sec"],
+              "best_requests_per_batch": best["requests_per_batch"], "cpu_baseline": None, "e2e": None,
+              "clocks": clocks, "gpu_launches": 2 * K * len(sweep)})
+    eng.close()
 
 
 def spread_placement(N, G, R, node_ids):

@@ -63,6 +63,7 @@ struct gpx_engine {
   int32_t* d_status = nullptr;
   uint32_t* d_copy_tab = nullptr;
   uint32_t* d_copy_dst = nullptr;
+  uint32_t* d_todo = nullptr; /* [2N] k_round's left-over runs: start index, end index */
   uint8_t* d_out_mask = nullptr;
   std::vector<uint8_t> h_out_mask;
   RoundCtl* d_ctl = nullptr;
@@ -273,6 +274,7 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   TRY(e->dalloc(&e->d_status, N));
   TRY(e->dalloc(&e->d_copy_tab, N));
   TRY(e->dalloc(&e->d_copy_dst, N));
+  TRY(e->dalloc(&e->d_todo, 2 * N));
   TRY(e->dalloc(&e->d_out_mask, N));
   TRY(e->dalloc(&e->d_ctl, (size_t)1));
   TRY(e->dalloc(&e->d_rctl, (size_t)2));
@@ -639,7 +641,8 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.A.extra_cap = extra_cap;
   RA.A.n_extra = &d_ctl->n_extra;
   RA.blob1w = e->d_blob1;
-  RA.todo = e->d_copy_tab; /* scratch reused: k_round does not build blobs through copy_tab */
+  RA.todo = e->d_todo;
+  RA.todo_end = e->d_todo + e->cfg.max_batch_recs;
   RA.n_todo = &d_ctl->n_todo;
   RA.blob1_res = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
   RA.A.blob1_bytes = RA.blob1_res;
@@ -650,7 +653,8 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   const uint32_t L = e->cfg.n_lanes;
   const uint32_t teams_per_block = (GPX_RBLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
   const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
-  const uint32_t slow_grid = std::min<uint32_t>(grid, (uint32_t)e->n_sms); /* grid-stride over the todo list */
+  const uint32_t slow_grid = std::min<uint32_t>(grid, (uint32_t)e->n_sms); /* grid-stride over the todo list; all
+                                                                            * blocks resident (grid barriers) */
   switch (L) {
     case 1: launch_round_t<1, 1>(grid, slow_grid, st, e->S, RA); break;
     case 2: launch_round_t<2, 2>(grid, slow_grid, st, e->S, RA); break;

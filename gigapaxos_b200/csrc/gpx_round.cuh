@@ -35,6 +35,7 @@ struct RoundArgs {
   uint8_t* blob1w; /* writable alias of A.blob1 (constructed blobs of batched slots) */
   unsigned long long blob1_res; /* payload-area bytes reserved for constructed blobs */
   uint32_t* todo;               /* request indices of the runs left to k_round_slow */
+  uint32_t* todo_end;           /* [k] one past the last request of run todo[k] (written by k_round_slow's phase 1) */
   uint32_t* n_todo;
   RoundCtl* ctl_out;            /* k_round_slow publishes the round's counters here and re-zeroes P.ctl for the next
                                  * round (no memset between rounds) */
@@ -205,58 +206,62 @@ __device__ __forceinline__ void void_outputs(const DevState& S, const RoundArgs&
   }
 }
 
-/* General path for the run that starts at request index i: coordinator work by team thread 0 against memory
- * (propose_run / tally_reply), decision broadcast to the lanes by shuffles. */
-template <int L, int LP>
-__device__ __forceinline__ void round_general(const DevState& S, const RoundArgs& RA, uint32_t i, uint32_t sub,
-                                              uint32_t tmask, uint32_t tbase, uint32_t gid, unsigned long long seg,
-                                              unsigned long long dseg, unsigned long long payb, unsigned int* s_ctr) {
-  const AcceptArgs& A = RA.A;
+/* General path, phase 1, for the run that starts at request index i: RequestBatcher + PCS.propose by team thread 0
+ * (propose_run writes the ACCEPTs at their request index, the status of every request of the run and, for batched
+ * slots, where each request's table entry and body go).  Returns one past the last request of the run. */
+__device__ __forceinline__ uint32_t round_propose(const DevState& S, const RoundArgs& RA, uint32_t i, uint32_t gid,
+                                                  unsigned int* s_ctr) {
   const gpx_request_rec* reqs = RA.P.reqs;
+  const uint32_t n = RA.P.n;
+  uint32_t nb = 0, k = i;
+  while (k < n && reqs[k].gid == gid) {
+    k = batch_end(S, reqs, n, k, gid);
+    nb++;
+  }
+  propose_run(S, RA.P, i, k, nb, i, s_ctr, true);
+  return k;
+}
+
+/* General path, phase 2: the blobs of the batched slots of one run, [nreq x gpx_batch_ent][values]
+ * (RequestPacket.batched), built by a whole warp -- lane t takes requests t, t + 32, ... of the run */
+__device__ __forceinline__ void round_build_blobs(const RoundArgs& RA, uint32_t i, uint32_t run_end, uint32_t lane_id) {
+  const gpx_request_rec* reqs = RA.P.reqs;
+  for (uint32_t q = i + lane_id; q < run_end; q += 32u) {
+    const int st = RA.P.status[q];
+    const bool batched = (st == GPX_RS_BATCHED) || (st > 0 && q + 1 < run_end && RA.P.status[q + 1] == GPX_RS_BATCHED);
+    if (!batched) continue;
+    const gpx_request_rec r = reqs[q];
+    gpx_batch_ent be;
+    be.req_id = r.req_id;
+    be.len = r.payload_len;
+    be.flags = r.flags;
+    *reinterpret_cast<int4*>(RA.blob1w + (RA.P.copy_tab[q] - RA.A.blob0_bytes)) = *reinterpret_cast<const int4*>(&be);
+    uint8_t* d = RA.blob1w + (RA.P.copy_dst[q] - RA.A.blob0_bytes);
+    const uint8_t* sp = RA.A.blob0 + r.payload_off;
+    uint32_t b = 0;
+    if ((((uint32_t)(uintptr_t)d | (uint32_t)(uintptr_t)sp) & 15u) == 0)
+      for (; b + 16 <= r.payload_len; b += 16) *reinterpret_cast<int4*>(d + b) = ld_stream4(sp + b);
+    for (; b < r.payload_len; b++) d[b] = sp[b];
+  }
+}
+
+/* General path, phase 3, for the run [i, run_end): accept at every lane, coordinator work by team thread 0 against
+ * memory (tally_reply), decision broadcast to the lanes by shuffles, commit at every lane. */
+template <int L, int LP>
+__device__ __forceinline__ void round_general(const DevState& S, const RoundArgs& RA, uint32_t i, uint32_t run_end,
+                                              uint32_t sub, uint32_t tmask, uint32_t tbase, uint32_t gid,
+                                              unsigned long long seg, unsigned long long dseg, unsigned long long payb,
+                                              unsigned int* s_ctr) {
+  const AcceptArgs& A = RA.A;
   const uint32_t n = RA.P.n;
   const uint32_t Wm = S.W - 1;
   const GroupCtx g = group_ctx(S, gid);
-  uint32_t run_end = i + 1;
-  if (sub == 0) {
-    uint32_t nb = 0, k = i;
-    while (k < n && reqs[k].gid == gid) {
-      k = batch_end(S, reqs, n, k, gid);
-      nb++;
-    }
-    run_end = k;
-    propose_run(S, RA.P, i, run_end, nb, i, s_ctr, true);
-    __threadfence_block();
-  }
-  run_end = __shfl_sync(tmask, run_end, tbase);
   for (uint32_t q = i; q < run_end; q++) {
     const int stq = RA.P.status[q];
-    if (stq <= 0) {
-      void_outputs<L>(S, RA, sub, gid, q, seg, dseg);
-      continue;
-    }
+    if (stq <= 0) continue; /* no ACCEPT at this request index: its VOID outputs were written in phase 2 */
     const int4* rp = reinterpret_cast<const int4*>(&RA.P.accepts[q]);
     const int4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
     const int slot = q0.y;
-    if ((uint32_t)q2.z > 1u) { /* batched slot: build [nreq x gpx_batch_ent][values] (RequestPacket.batched) */
-      if (sub == 0) {
-        const uint32_t nreq = (uint32_t)q2.z;
-        uint8_t* tab = RA.blob1w + ((unsigned long long)(uint32_t)q2.x - A.blob0_bytes);
-        uint8_t* dst = tab + 16ull * nreq;
-        for (uint32_t b = 0; b < nreq; b++) {
-          const gpx_request_rec r = reqs[q + b];
-          gpx_batch_ent be;
-          be.req_id = r.req_id;
-          be.len = r.payload_len;
-          be.flags = r.flags;
-          *reinterpret_cast<int4*>(tab + 16ull * b) = *reinterpret_cast<const int4*>(&be);
-          const uint8_t* src = A.blob0 + r.payload_off;
-          for (uint32_t x = 0; x < r.payload_len; x++) dst[x] = src[x];
-          dst += r.payload_len;
-        }
-        __threadfence_block();
-      }
-      __syncwarp(tmask);
-    }
     uint32_t dstIdx = 0xffu;
     if (g.live)
       for (uint32_t m = 0; m < g.R; m++)
@@ -626,8 +631,33 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   flush_counters(S, s_ctr);
 }
 
+/* grid-wide barrier of a grid whose blocks are all resident (k_round_slow: at most 2 blocks per SM, launched behind
+ * k_round): bar[0] counts arrivals, bar[1] is the generation */
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int gen = atomicAdd(&bar[1], 0u);
+    if (atomicAdd(&bar[0], 1u) == nblocks - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      while (atomicAdd(&bar[1], 0u) == gen) __nanosleep(100);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 /* The runs the fast kernel did not take (several requests of a group, STOPs, NACKs, coordinator changes, ...).
- * A fixed, small grid loops over the todo list; with an empty list the launch costs a few microseconds. */
+ * A fixed, small grid loops over the todo list in three phases separated by grid barriers:
+ *   1  RequestBatcher + PCS.propose, one thread per run (propose_run)
+ *   2  one WARP per run: the blobs of batched slots and the VOID outputs of the request indices that carry no ACCEPT,
+ *      lane-parallel over the requests of the run (RequestBatcher.java:198-219 packs up to MAX_BATCH_SIZE requests
+ *      into one slot: a 1,024-request batch is built by 32 lanes, not by one thread)
+ *   3  accept x L, tally, commit x L per ACCEPT of the run, one team of L threads per run
+ * With an empty list the launch costs a few microseconds. */
 template <int L, int LP>
 __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_constant__ DevState S,
                                                              const __grid_constant__ RoundArgs RA) {
@@ -650,10 +680,44 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
     }
     return;
   }
-  if (ntodo) {
-    const AcceptArgs& A = RA.A;
-    const uint32_t n = RA.P.n;
-    const uint32_t lane_id = threadIdx.x & 31u;
+  const AcceptArgs& A = RA.A;
+  const uint32_t n = RA.P.n;
+  const uint32_t lane_id = threadIdx.x & 31u;
+  const unsigned long long pay_rel = RA.pay_rel, res_a = RA.res_a, res_d = RA.res_d;
+  /* ---- phase 1: propose, one thread per run ---- */
+  for (uint32_t k = blockIdx.x * GPX_BLOCK + threadIdx.x; k < ntodo; k += gridDim.x * GPX_BLOCK) {
+    const uint32_t i = RA.todo[k];
+    RA.todo_end[k] = round_propose(S, RA, i, RA.P.reqs[i].gid, s_ctr);
+  }
+  grid_barrier(&S.tickets[6], gridDim.x);
+  /* ---- phase 2: one warp per run ---- */
+  {
+    unsigned long long segl[L];
+#pragma unroll
+    for (int l = 0; l < L; l++) segl[l] = seg_base(S, l, res_a + res_d);
+    const uint32_t nwarps = gridDim.x * (GPX_BLOCK / 32u);
+    for (uint32_t k = blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5); k < ntodo; k += nwarps) {
+      const uint32_t i = RA.todo[k], run_end = RA.todo_end[k];
+      round_build_blobs(RA, i, run_end, lane_id);
+      for (uint32_t q = i + lane_id; q < run_end; q += 32u) {
+        if (RA.P.status[q] > 0) continue;
+        const uint32_t gid = RA.P.reqs[q].gid;
+        const int4 z0 = make_int4((int)gid, 0, 0, 0), z1 = make_int4(0, (int)GPX_F_VOID, 0, 0);
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          write_accept_image(S, l, segl[l], n, q, z0, z1, make_int4(0, 0, 0, 0), GPX_F_VOID);
+          st256_stream(ring_ptr(S, l, segl[l] + res_a + 64 + (unsigned long long)q * 32), z0, z1);
+          store_void_exec(&A.exec[(size_t)q * L + l], gid, 0, l);
+        }
+        st256_stream(&A.decisions[q], z0, z1);
+        A.out_mask[q] = 0;
+        if (RA.sum) store_sum(&RA.sum[q], RA.P.status[q], 0, 0, 0);
+      }
+    }
+  }
+  grid_barrier(&S.tickets[6], gridDim.x);
+  /* ---- phase 3: one team per run ---- */
+  {
     constexpr uint32_t TPW = 32u / LP;
     const uint32_t team_in_warp = lane_id / LP;
     const uint32_t sub = lane_id - team_in_warp * LP;
@@ -662,14 +726,12 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
     const uint32_t nteams = gridDim.x * (GPX_BLOCK / 32u) * TPW;
     const uint32_t team = team_in_warp < TPW ? (blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5)) * TPW + team_in_warp
                                              : 0xffffffffu;
-    const unsigned long long pay_rel = RA.pay_rel, res_a = RA.res_a, res_d = RA.res_d;
     const uint32_t myl = sub < (uint32_t)L ? sub : 0u;
     const unsigned long long seg = seg_base(S, myl, res_a + res_d); /* same segments as the fast kernel */
     const unsigned long long payb = seg + pay_rel, dseg = seg + res_a;
     for (uint32_t k = team; k < ntodo; k += nteams) {
       const uint32_t i = RA.todo[k];
-      const uint32_t gid = RA.P.reqs[i].gid;
-      round_general<L, LP>(S, RA, i, sub, tmask, tbase, gid, seg, dseg, payb, s_ctr);
+      round_general<L, LP>(S, RA, i, RA.todo_end[k], sub, tmask, tbase, RA.P.reqs[i].gid, seg, dseg, payb, s_ctr);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
@@ -680,7 +742,6 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
   if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[5], 1u) == gridDim.x - 1);
   __syncthreads();
   if (s_last && threadIdx.x < (uint32_t)L) {
-    const unsigned long long res_a = RA.res_a, res_d = RA.res_d;
     S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
     S.seg_seq[threadIdx.x] += 2ull;
   }
