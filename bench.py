@@ -943,36 +943,47 @@ def run_cfg5(args, lib, dev, rank, world, wl, K, W, metric, config):
             d_reqs.append(torch.from_numpy(reqs.view(np.uint8)).to(dev))
             d_pay.append(torch.from_numpy(rng.integers(48, 123, size=n * P + 16, dtype=np.uint8)).to(dev))
 
-        def step(k):
-            q = k % NB
-            bufs = DevRoundBufs(d_reqs[q].data_ptr(), d_pay[q].data_ptr(), n * P, n, d_status.data_ptr(), d_exec.data_ptr())
-            if round_dev(eng.handle, C.byref(bufs), C.c_void_p(stream.cuda_stream)) != 0:
-                raise RuntimeError(lib.last_error())
-        for w in range(W):
-            step(w)
-        barrier()
-        c0 = eng.counters()
-        ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        for k in range(K):
-            if not args.no_flush:
-                flush_buf.zero_()
-            ev_s[k].record()
-            step(k)
-            ev_e[k].record()
-        barrier()
-        ms = np.array([ev_s[k].elapsed_time(ev_e[k]) for k in range(K)])
-        total_ms = allmax(float(ms.sum()))
-        c1 = eng.counters()
-        assert c1["decisions_made"] - c0["decisions_made"] == A * K, (b, c1["decisions_made"] - c0["decisions_made"], A * K)
-        assert c1["executed"] - c0["executed"] == A * K * R
-        assert c1["requests_batched"] - c0["requests_batched"] == n * K
-        per = total_ms / K
+        forms = {}
+        for form, fname in (("fused_by_request", "round_device"), ("compact_fused", "round_device_compact"),
+                            ("phases", "round_device_phases")):
+            if form == "fused_by_request" and b > 64:
+                pass  # still timed: it is the headline form's own curve
+            fn = lib.fn(fname)
+
+            def step(k):
+                q = k % NB
+                bufs = DevRoundBufs(d_reqs[q].data_ptr(), d_pay[q].data_ptr(), n * P, n, d_status.data_ptr(),
+                                    d_exec.data_ptr())
+                if fn(eng.handle, C.byref(bufs), C.c_void_p(stream.cuda_stream)) != 0:
+                    raise RuntimeError(lib.last_error())
+            for w in range(W):
+                step(w)
+            barrier()
+            c0 = eng.counters()
+            ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+            ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+            for k in range(K):
+                if not args.no_flush:
+                    flush_buf.zero_()
+                ev_s[k].record()
+                step(k)
+                ev_e[k].record()
+            barrier()
+            ms = np.array([ev_s[k].elapsed_time(ev_e[k]) for k in range(K)])
+            total_ms = allmax(float(ms.sum()))
+            c1 = eng.counters()
+            assert c1["decisions_made"] - c0["decisions_made"] == A * K, (b, form, c1["decisions_made"] - c0["decisions_made"])
+            assert c1["executed"] - c0["executed"] == A * K * R
+            assert c1["requests_batched"] - c0["requests_batched"] == n * K
+            forms[form] = {"ms_per_step": total_ms / K, "p50_ms": float(np.median(ms))}
+        bestf = min(forms, key=lambda f: forms[f]["ms_per_step"])
+        per = forms[bestf]["ms_per_step"]
         bytes_round = A * b_act_batched(R, P, b)
         sweep.append({"requests_per_batch": b, "active_groups_per_gpu": A, "requests_per_step_per_gpu": n,
-                      "ms_per_step": per, "decisions_per_sec": world * A / (per / 1e3),
-                      "requests_per_sec": world * n / (per / 1e3), "p50_ms": float(np.median(ms)),
-                      "roofline_frac": bytes_round / (per / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": bytes_round})
+                      "form": bestf, "ms_per_step": per, "decisions_per_sec": world * A / (per / 1e3),
+                      "requests_per_sec": world * n / (per / 1e3), "p50_ms": forms[bestf]["p50_ms"],
+                      "roofline_frac": bytes_round / (per / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": bytes_round,
+                      "ms_per_step_by_form": {f: v["ms_per_step"] for f, v in forms.items()}})
         del d_reqs, d_pay
     clocks = sampler.stop()
     if rank == 0:
@@ -985,6 +996,9 @@ def run_cfg5(args, lib, dev, rank, world, wl, K, W, metric, config):
         emit({"metric": metric, "value": head["decisions_per_sec"], "unit": "decisions/s", "n_gpus": world, "steps": K,
               "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
               "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg_out,
+              "forms": {"fused_by_request": "gpx_round_device: k_round + k_round_slow, outputs indexed by request",
+                        "compact_fused": "gpx_round_device_compact: k_propose + k_build_blobs + k_act, outputs per ACCEPT",
+                        "phases": "gpx_round_device_phases: k_propose, k_accept, k_tally, k_commit"},
               "roofline": {"kernel": "k_round + k_round_slow at b = 1 (in-order fast path over the active 1 %)", "bound": "hbm",
                            "achieved": head["algorithmic_bytes_per_step"] / (head["ms_per_step"] / 1e3) / 1e9,
                            "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,

@@ -64,6 +64,7 @@ struct gpx_engine {
   uint32_t* d_copy_tab = nullptr;
   uint32_t* d_copy_dst = nullptr;
   uint32_t* d_todo = nullptr; /* [2N] k_round's left-over runs: start index, end index */
+  uint8_t* d_mark = nullptr;  /* [N] request belongs to a left-over run */
   uint8_t* d_out_mask = nullptr;
   std::vector<uint8_t> h_out_mask;
   RoundCtl* d_ctl = nullptr;
@@ -95,6 +96,7 @@ struct gpx_engine {
   /* timing */
   int n_sms = 148;
   bool timing = false;
+  bool compact_fused = false; /* round_on_stream(fused = false): k_propose + k_act instead of the four phase kernels */
   cudaEvent_t ev[5];
   gpx_kernel_times kt;
 
@@ -275,6 +277,7 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   TRY(e->dalloc(&e->d_copy_tab, N));
   TRY(e->dalloc(&e->d_copy_dst, N));
   TRY(e->dalloc(&e->d_todo, 2 * N));
+  TRY(e->dalloc(&e->d_mark, N));
   TRY(e->dalloc(&e->d_out_mask, N));
   TRY(e->dalloc(&e->d_ctl, (size_t)1));
   TRY(e->dalloc(&e->d_rctl, (size_t)2));
@@ -643,6 +646,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.blob1w = e->d_blob1;
   RA.todo = e->d_todo;
   RA.todo_end = e->d_todo + e->cfg.max_batch_recs;
+  RA.mark = e->d_mark;
   RA.n_todo = &d_ctl->n_todo;
   RA.blob1_res = e->cfg.batching_enabled ? std::min<uint64_t>(e->blob1_cap, 16ull * n + pal) : 0;
   RA.A.blob1_bytes = RA.blob1_res;
@@ -653,7 +657,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   const uint32_t L = e->cfg.n_lanes;
   const uint32_t teams_per_block = (GPX_RBLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
   const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
-  const uint32_t slow_grid = std::min<uint32_t>(grid, (uint32_t)e->n_sms); /* grid-stride over the todo list; all
+  const uint32_t slow_grid = std::min<uint32_t>(grid, 2u * (uint32_t)e->n_sms); /* grid-stride over the todo list; all
                                                                             * blocks resident (grid barriers) */
   switch (L) {
     case 1: launch_round_t<1, 1>(grid, slow_grid, st, e->S, RA); break;
@@ -912,16 +916,16 @@ static int round_on_stream(gpx_engine* e, bool fused, const gpx_request_rec* d_r
   if (rc) return rc;
   if (tm) cudaEventRecord(e->ev[1], st);
   /* the ACCEPT segment mirrors the payload arena plus the constructed blobs actually used */
-  rc = launch_accept(e, fused, e->d_accepts, &e->d_ctl->n_accepts, n, d_payload, pal, e->d_blob1, 0,
+  rc = launch_accept(e, e->compact_fused, e->d_accepts, &e->d_ctl->n_accepts, n, d_payload, pal, e->d_blob1, 0,
                      &e->d_ctl->blob1_used, e->d_replies, e->d_decisions, d_exec, st);
   if (rc) return rc;
   if (tm) cudaEventRecord(e->ev[2], st);
-  if (!fused) {
+  if (!e->compact_fused) {
     rc = launch_tally(e, e->d_replies, &e->d_ctl->n_accepts, L, n * L, e->d_decisions, st);
     if (rc) return rc;
   }
   if (tm) cudaEventRecord(e->ev[3], st);
-  if (!fused) {
+  if (!e->compact_fused) {
     rc = launch_commit(e, e->d_decisions, &e->d_ctl->n_decisions, n, d_exec, st);
     if (rc) return rc;
   }
@@ -998,6 +1002,20 @@ int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream) {
   if (rc) return rc;
   return round_on_stream(e, true, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
                          stream ? (cudaStream_t)stream : e->stream);
+}
+/* k_propose (ACCEPTs compacted at the front: one record, log image and EXEC row per ACCEPT, no per-request holes) +
+ * k_act (accept -> tally -> commit per ACCEPT in registers): the form for batches in which most requests share a
+ * slot with others (RequestBatcher.java:198-219) */
+int gpx_round_device_compact(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream) {
+  if (!e || !b) return fail(GPX_EINVAL, "null argument");
+  if (b->n == 0) return GPX_OK;
+  int rc = check_batch(e, b->n, b->payload_bytes);
+  if (rc) return rc;
+  e->compact_fused = true;
+  rc = round_on_stream(e, false, b->reqs, b->payload, b->payload_bytes, b->n, b->status, b->exec,
+                       stream ? (cudaStream_t)stream : e->stream);
+  e->compact_fused = false;
+  return rc;
 }
 int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream) {
   if (!e || !b) return fail(GPX_EINVAL, "null argument");

@@ -37,6 +37,8 @@ struct RoundArgs {
   uint32_t* todo;               /* request indices of the runs left to k_round_slow */
   uint32_t* todo_end;           /* [k] one past the last request of run todo[k] (written by k_round_slow's phase 1) */
   uint32_t* n_todo;
+  uint8_t* mark;                /* [n] 1 = the request belongs to a run left to k_round_slow (written by k_round for every
+                                 * request: phase 2 of the slow kernel is one thread per REQUEST) */
   RoundCtl* ctl_out;            /* k_round_slow publishes the round's counters here and re-zeroes P.ctl for the next
                                  * round (no memset between rounds) */
   /* launch constants of the two log segments of a lane (host-computed: no 64-bit arithmetic in the kernels) */
@@ -189,23 +191,6 @@ __device__ __forceinline__ void commit_team_lane(const DevState& S, const Accept
   st256_stream(ring_ptr(S, l, dseg + 64 + (unsigned long long)j * 32), img0, img1);
 }
 
-/* VOID outputs of a request index that carries no ACCEPT (batched into an earlier one / rejected) */
-template <int L>
-__device__ __forceinline__ void void_outputs(const DevState& S, const RoundArgs& RA, uint32_t sub, uint32_t gid,
-                                             uint32_t j, unsigned long long seg, unsigned long long dseg) {
-  if (sub < (uint32_t)L) {
-    const int4 z0 = make_int4((int)gid, 0, 0, 0), z1 = make_int4(0, (int)GPX_F_VOID, 0, 0);
-    write_accept_image(S, sub, seg, RA.P.n, j, z0, z1, make_int4(0, 0, 0, 0), GPX_F_VOID);
-    st256_stream(ring_ptr(S, sub, dseg + 64 + (unsigned long long)j * 32), z0, z1);
-    store_void_exec(&RA.A.exec[(size_t)j * L + sub], gid, 0, sub);
-  }
-  if (sub == 0) {
-    st256_stream(&RA.A.decisions[j], make_int4((int)gid, 0, 0, 0), make_int4(0, (int)GPX_F_VOID, 0, 0));
-    RA.A.out_mask[j] = 0;
-    if (RA.sum) store_sum(&RA.sum[j], RA.P.status[j], 0, 0, 0);
-  }
-}
-
 /* General path, phase 1, for the run that starts at request index i: RequestBatcher + PCS.propose by team thread 0
  * (propose_run writes the ACCEPTs at their request index, the status of every request of the run and, for batched
  * slots, where each request's table entry and body go).  Returns one past the last request of the run. */
@@ -222,27 +207,25 @@ __device__ __forceinline__ uint32_t round_propose(const DevState& S, const Round
   return k;
 }
 
-/* General path, phase 2: the blobs of the batched slots of one run, [nreq x gpx_batch_ent][values]
- * (RequestPacket.batched), built by a whole warp -- lane t takes requests t, t + 32, ... of the run */
-__device__ __forceinline__ void round_build_blobs(const RoundArgs& RA, uint32_t i, uint32_t run_end, uint32_t lane_id) {
+/* General path, phase 2, for ONE request q of a left-over run: its entry and body in the blob of a batched slot,
+ * [nreq x gpx_batch_ent][values] (RequestPacket.batched) */
+__device__ __forceinline__ void round_build_blob(const RoundArgs& RA, uint32_t q, int st) {
   const gpx_request_rec* reqs = RA.P.reqs;
-  for (uint32_t q = i + lane_id; q < run_end; q += 32u) {
-    const int st = RA.P.status[q];
-    const bool batched = (st == GPX_RS_BATCHED) || (st > 0 && q + 1 < run_end && RA.P.status[q + 1] == GPX_RS_BATCHED);
-    if (!batched) continue;
-    const gpx_request_rec r = reqs[q];
-    gpx_batch_ent be;
-    be.req_id = r.req_id;
-    be.len = r.payload_len;
-    be.flags = r.flags;
-    *reinterpret_cast<int4*>(RA.blob1w + (RA.P.copy_tab[q] - RA.A.blob0_bytes)) = *reinterpret_cast<const int4*>(&be);
-    uint8_t* d = RA.blob1w + (RA.P.copy_dst[q] - RA.A.blob0_bytes);
-    const uint8_t* sp = RA.A.blob0 + r.payload_off;
-    uint32_t b = 0;
-    if ((((uint32_t)(uintptr_t)d | (uint32_t)(uintptr_t)sp) & 15u) == 0)
-      for (; b + 16 <= r.payload_len; b += 16) *reinterpret_cast<int4*>(d + b) = ld_stream4(sp + b);
-    for (; b < r.payload_len; b++) d[b] = sp[b];
-  }
+  const gpx_request_rec r = reqs[q];
+  const bool batched = (st == GPX_RS_BATCHED) ||
+                       (st > 0 && q + 1 < RA.P.n && RA.P.status[q + 1] == GPX_RS_BATCHED && reqs[q + 1].gid == r.gid);
+  if (!batched) return;
+  gpx_batch_ent be;
+  be.req_id = r.req_id;
+  be.len = r.payload_len;
+  be.flags = r.flags;
+  *reinterpret_cast<int4*>(RA.blob1w + (RA.P.copy_tab[q] - RA.A.blob0_bytes)) = *reinterpret_cast<const int4*>(&be);
+  uint8_t* d = RA.blob1w + (RA.P.copy_dst[q] - RA.A.blob0_bytes);
+  const uint8_t* sp = RA.A.blob0 + r.payload_off;
+  uint32_t b = 0;
+  if ((((uint32_t)(uintptr_t)d | (uint32_t)(uintptr_t)sp) & 15u) == 0)
+    for (; b + 16 <= r.payload_len; b += 16) *reinterpret_cast<int4*>(d + b) = ld_stream4(sp + b);
+  for (; b < r.payload_len; b++) d[b] = sp[b];
 }
 
 /* General path, phase 3, for the run [i, run_end): accept at every lane, coordinator work by team thread 0 against
@@ -256,11 +239,13 @@ __device__ __forceinline__ void round_general(const DevState& S, const RoundArgs
   const uint32_t n = RA.P.n;
   const uint32_t Wm = S.W - 1;
   const GroupCtx g = group_ctx(S, gid);
-  for (uint32_t q = i; q < run_end; q++) {
+  for (uint32_t q = i; q < run_end;) {
     const int stq = RA.P.status[q];
-    if (stq <= 0) continue; /* no ACCEPT at this request index: its VOID outputs were written in phase 2 */
+    if (stq <= 0) break; /* refused / pre-active from here on (propose_run): no further ACCEPT in this run; the VOID
+                          * outputs of request indices without an ACCEPT were written in phase 2 */
     const int4* rp = reinterpret_cast<const int4*>(&RA.P.accepts[q]);
     const int4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+    const uint32_t q_next = q + max(1u, (uint32_t)q2.z); /* the next batch of the run starts behind this one's requests */
     const int slot = q0.y;
     uint32_t dstIdx = 0xffu;
     if (g.live)
@@ -366,6 +351,7 @@ __device__ __forceinline__ void round_general(const DevState& S, const RoundArgs
       if (sub == 0) store_sum(&RA.sum[q], stq, 0, 0, 0);
     }
     __syncwarp(tmask); /* the next ACCEPT of the run sees this one's coordinator/acceptor writes */
+    q = q_next;
   }
 }
 
@@ -565,9 +551,7 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
     if (plen) {
       uint8_t* dst = seg_p + pay_rel + poff;
       if (pal) {
-        st_stream4(dst, pv);
-#pragma unroll 1
-        for (uint32_t b = 16; b < plen; b += 16) st_stream4(dst + b, ld_stream4(psrc + b));
+        st_stream4(dst, pv); /* the rest of a longer body is copied at the very end of the kernel (few live registers) */
       } else {
         dst[0] = (uint8_t)pv.x;
 #pragma unroll 1
@@ -618,6 +602,22 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   } else if (head && sub == 0) {
     RA.todo[atomicAdd(RA.n_todo, 1u)] = i; /* the run goes to k_round_slow */
   }
+  if (valid && sub == 0) RA.mark[i] = sf ? 0 : 1;
+  if (sf && pal && plen > 16u) { /* bodies longer than one chunk: four independent 128-bit loads in flight */
+    uint8_t* const dst = ring_ptr(S, sub, seg) + pay_rel + poff;
+    uint32_t b = 16;
+#pragma unroll 1
+    for (; b + 64 <= plen; b += 64) {
+      const int4 a0 = ld_stream4(psrc + b), a1 = ld_stream4(psrc + b + 16), a2 = ld_stream4(psrc + b + 32),
+                 a3 = ld_stream4(psrc + b + 48);
+      st_stream4(dst + b, a0);
+      st_stream4(dst + b + 16, a1);
+      st_stream4(dst + b + 32, a2);
+      st_stream4(dst + b + 48, a3);
+    }
+#pragma unroll 1
+    for (; b < plen; b += 16) st_stream4(dst + b, ld_stream4(psrc + b));
+  }
   /* fast-path events, counted in registers: one shared-memory update per warp */
   {
     const uint32_t nl = __reduce_add_sync(FULL, c_lane), nt = __reduce_add_sync(FULL, c_team);
@@ -653,9 +653,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
 /* The runs the fast kernel did not take (several requests of a group, STOPs, NACKs, coordinator changes, ...).
  * A fixed, small grid loops over the todo list in three phases separated by grid barriers:
  *   1  RequestBatcher + PCS.propose, one thread per run (propose_run)
- *   2  one WARP per run: the blobs of batched slots and the VOID outputs of the request indices that carry no ACCEPT,
- *      lane-parallel over the requests of the run (RequestBatcher.java:198-219 packs up to MAX_BATCH_SIZE requests
- *      into one slot: a 1,024-request batch is built by 32 lanes, not by one thread)
+ *   2  one thread per REQUEST of those runs (k_round marked them): its entry + body in the blob of a batched slot
+ *      (RequestBatcher.java:198-219 packs up to MAX_BATCH_SIZE requests into one slot) and the VOID outputs of the
+ *      request indices that carry no ACCEPT
  *   3  accept x L, tally, commit x L per ACCEPT of the run, one team of L threads per run
  * With an empty list the launch costs a few microseconds. */
 template <int L, int LP>
@@ -690,29 +690,27 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
     RA.todo_end[k] = round_propose(S, RA, i, RA.P.reqs[i].gid, s_ctr);
   }
   grid_barrier(&S.tickets[6], gridDim.x);
-  /* ---- phase 2: one warp per run ---- */
+  /* ---- phase 2: one thread per REQUEST of the left-over runs ---- */
   {
     unsigned long long segl[L];
 #pragma unroll
     for (int l = 0; l < L; l++) segl[l] = seg_base(S, l, res_a + res_d);
-    const uint32_t nwarps = gridDim.x * (GPX_BLOCK / 32u);
-    for (uint32_t k = blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5); k < ntodo; k += nwarps) {
-      const uint32_t i = RA.todo[k], run_end = RA.todo_end[k];
-      round_build_blobs(RA, i, run_end, lane_id);
-      for (uint32_t q = i + lane_id; q < run_end; q += 32u) {
-        if (RA.P.status[q] > 0) continue;
-        const uint32_t gid = RA.P.reqs[q].gid;
-        const int4 z0 = make_int4((int)gid, 0, 0, 0), z1 = make_int4(0, (int)GPX_F_VOID, 0, 0);
+    for (uint32_t q = blockIdx.x * GPX_BLOCK + threadIdx.x; q < n; q += gridDim.x * GPX_BLOCK) {
+      if (!RA.mark[q]) continue;
+      const int st = RA.P.status[q];
+      round_build_blob(RA, q, st);
+      if (st > 0) continue;
+      const uint32_t gid = RA.P.reqs[q].gid;
+      const int4 z0 = make_int4((int)gid, 0, 0, 0), z1 = make_int4(0, (int)GPX_F_VOID, 0, 0);
 #pragma unroll
-        for (int l = 0; l < L; l++) {
-          write_accept_image(S, l, segl[l], n, q, z0, z1, make_int4(0, 0, 0, 0), GPX_F_VOID);
-          st256_stream(ring_ptr(S, l, segl[l] + res_a + 64 + (unsigned long long)q * 32), z0, z1);
-          store_void_exec(&A.exec[(size_t)q * L + l], gid, 0, l);
-        }
-        st256_stream(&A.decisions[q], z0, z1);
-        A.out_mask[q] = 0;
-        if (RA.sum) store_sum(&RA.sum[q], RA.P.status[q], 0, 0, 0);
+      for (int l = 0; l < L; l++) {
+        write_accept_image(S, l, segl[l], n, q, z0, z1, make_int4(0, 0, 0, 0), GPX_F_VOID);
+        st256_stream(ring_ptr(S, l, segl[l] + res_a + 64 + (unsigned long long)q * 32), z0, z1);
+        store_void_exec(&A.exec[(size_t)q * L + l], gid, 0, l);
       }
+      st256_stream(&A.decisions[q], z0, z1);
+      A.out_mask[q] = 0;
+      if (RA.sum) store_sum(&RA.sum[q], st, 0, 0, 0);
     }
   }
   grid_barrier(&S.tickets[6], gridDim.x);

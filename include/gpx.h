@@ -490,6 +490,10 @@ typedef struct gpx_dev_round_bufs {
 } gpx_dev_round_bufs;
 int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream);        /* fused */
 int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream); /* phase by phase */
+/* gpx_propose + gpx_handle_accepts_fused on device buffers: ACCEPTs compacted at the front (exec[k * n_lanes + lane]
+ * belongs to the k-th ACCEPT of the batch; the count is gpx_counters.proposals' increment), no per-request holes in
+ * the log segments -- the form for batches in which many requests share a slot (RequestBatcher.java:198-219) */
+int gpx_round_device_compact(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream);
 /* ---- device-resident phase calls: replicas of a group in DIFFERENT engines (spread placement:
  * one engine per GPU hosts one node; ACCEPT / ACCEPT_REPLY / DECISION records travel between engines
  * over NVLink).  Everything is asynchronous on `stream`; all pointers are device pointers unless

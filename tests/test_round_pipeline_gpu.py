@@ -9,7 +9,7 @@ plus state and log equality at the end.
 import numpy as np
 import pytest
 
-from helpers import abi, exec_by_lane, group_descs, make_requests
+from helpers import Engine, abi, exec_by_lane, group_descs, make_config, make_requests
 from test_round_parity_gpu import both, compare_logs, compare_state
 
 pytestmark = pytest.mark.gpu
@@ -164,3 +164,50 @@ def test_packed_requests(oracle_lib, cuda_lib):
         assert sorted(exec_tuples(xo) + exec_tuples(ex_o)) == sorted(exec_tuples(res["exec"]) + exec_tuples(res["extra"]))
     compare_state(eo, eg, np.arange(G), 3)
     compare_logs(eo, eg, 3)
+
+
+def test_round_device_compact_parity(oracle_lib, cuda_lib):
+    """gpx_round_device_compact (k_propose + k_build_blobs + k_act on device buffers) == gpx_propose followed by
+    gpx_handle_accepts_fused on the oracle: status, EXEC per lane, rows, counters -- with batched slots of 1..40 requests"""
+    import ctypes as C
+    import torch
+    from gigapaxos_b200.abi import DevRoundBufs
+    G = 700
+    eo, eg = (Engine(lib, make_config(lib, max_groups=G, max_batch_recs=1 << 15, max_batch_payload=1 << 21))
+              for lib in (oracle_lib, cuda_lib))
+    d = group_descs(G)
+    eo.create_groups(d)
+    eg.create_groups(d)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    rng = np.random.default_rng(21)
+    for r in range(5):
+        counts = rng.choice([0, 1, 1, 2, 7, 40], size=G)
+        gids = np.repeat(np.arange(G), counts)
+        lens = rng.integers(1, 50, size=len(gids))
+        reqs, pay = make_requests(gids, payload_len=lens, seed=13, round_no=r, entry_lane=r % 3)
+        acc, blob, so = eo.propose(reqs, pay)
+        rep, dec, xo, extra_o = eo.handle_accepts_fused(acc, blob)
+        n = len(reqs)
+        d_reqs = torch.from_numpy(reqs.view(np.uint8).copy()).to(dev)
+        d_pay = torch.from_numpy(np.concatenate([pay, np.zeros(16, np.uint8)])).to(dev)
+        d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_exec = torch.zeros(n * 3 * 24, dtype=torch.uint8, device=dev)
+        bufs = DevRoundBufs(d_reqs.data_ptr(), d_pay.data_ptr(), len(pay), n, d_status.data_ptr(), d_exec.data_ptr())
+        torch.cuda.synchronize()
+        cuda_lib.check(cuda_lib.fn("round_device_compact")(eg.handle, C.byref(bufs), C.c_void_p(stream.cuda_stream)))
+        torch.cuda.synchronize()
+        assert np.array_equal(d_status.cpu().numpy(), so)
+        xg = d_exec.cpu().numpy().view(abi.exec_dtype)[: len(acc) * 3]
+        for a, b in zip(exec_by_lane(xo, 3), exec_by_lane(xg, 3)):
+            assert len(a) == len(b) == int((counts > 0).sum())
+            for f in a.dtype.names:
+                if f != "payload_off":
+                    assert np.array_equal(a[f], b[f]), f
+    for l in range(3):
+        ro, rg = eo.dump_rows(np.arange(G), l), eg.dump_rows(np.arange(G), l)
+        for f in ro.dtype.names:
+            assert np.array_equal(ro[f], rg[f]), f
+    co, cg = eo.counters(), eg.counters()
+    co.pop("kernel_launches"), cg.pop("kernel_launches")
+    assert co == cg
