@@ -689,9 +689,79 @@ def main():
             pipe_step(k)
             pipe_wait()
             lat.append(time.perf_counter() - t1)
-        e2e = {"value": world * G * K4 / dt_pipe, "unit": "decisions/s",
+        # ---- the same pipeline WITH the journal: every step's log segments (ACCEPT images + request bodies + DECISION
+        # images of all R lanes) are drained to pinned host memory on the engine's drain stream and released
+        # (AbstractPaxosLogger logs before it messages, SQLPaxosLogger.journal :965-1036 appends to a file; the pinned
+        # buffer stands for the file's write buffer).  The first drain catches up with what the earlier legs left.
+        per_round_log = 256 + 80 * G + 2 * (G * P + 16) + 16 * G
+        dbuf = [[torch.zeros(2 * per_round_log, dtype=torch.uint8).pin_memory() for _ in range(R)]
+                for _ in range(PIPE_DEPTH)]
+        ring_b = int(eng.cfg.log_ring_bytes)
+        drained_bytes = [0]
+
+        def pipe_step_log(k):
+            if len(inflight) == PIPE_DEPTH:
+                pipe_wait_log()
+            io = ios[k % (PIPE_DEPTH * NB)]
+            if submit(eng.handle, C.byref(io), C.byref(tk)) != 0:
+                raise RuntimeError(lib.last_error())
+            q = k % PIPE_DEPTH
+            ups = []
+            for l in range(R):  # enqueue the drain of what this round appends (the copy waits for it on the device)
+                f, nb = eng.log_drain_async(l, dbuf[q][l].data_ptr(), dbuf[q][l].numel())
+                ups.append((l, f + nb))
+                drained_bytes[0] += nb
+            inflight.append((tk.value, ups))
+
+        def pipe_wait_log():
+            t, ups = inflight.pop(0)
+            if wait(eng.handle, C.c_uint64(t), C.byref(ns), C.byref(nx)) != 0:
+                raise RuntimeError(lib.last_error())
+            eng.log_drain_wait()  # the journal bytes of this round are in host memory: release the ring
+            for l, upto in ups:
+                eng.log_release(l, upto)
+
+        e2e_log = None
+        try:
+            # catch up: drop the backlog by re-creating the drain cursor at the current head
+            lib.fn("log_drain_skip")(eng.handle)
+            for w in range(2 * PIPE_DEPTH):
+                pipe_step_log(w)
+            while inflight:
+                pipe_wait_log()
+            barrier()
+            drained_bytes[0] = 0
+            c0l = eng.counters()
+            t0 = time.perf_counter()
+            for k in range(K4):
+                pipe_step_log(k)
+            while inflight:
+                pipe_wait_log()
+            dt_log = allmax(time.perf_counter() - t0)
+            c1l = eng.counters()
+            assert c1l["decisions_made"] - c0l["decisions_made"] == G * K4
+            for l in range(R):
+                f, nb = eng.log_drain_async(l, dbuf[0][l].data_ptr(), dbuf[0][l].numel())
+                assert nb == 0, "every appended log byte was drained"
+            e2e_log = {"value": world * G * K4 / dt_log, "ms_per_step": 1e3 * dt_log / K4,
+                       "log_bytes_drained_per_step": drained_bytes[0] // K4}
+        except Exception as ex:  # pragma: no cover
+            e2e_log = {"error": repr(ex)}
+            inflight.clear()
+
+        e2e_nolog = {"value": world * G * K4 / dt_pipe, "unit": "decisions/s", "ms_per_step": 1e3 * dt_pipe / K4,
+                     "d2h_bytes_per_step": int(G * 8 + 32),
+                     "note": "the same pipeline without draining the log ring (DISABLE_LOGGING analogue on the host side: "
+                             "the log images stay in HBM and are overwritten when the ring wraps)"}
+        with_log = e2e_log is not None and "value" in e2e_log
+        e2e = {"value": e2e_log["value"] if with_log else world * G * K4 / dt_pipe, "unit": "decisions/s",
                "h2d_bytes_per_step": int(G * 16 + h_pay[0].numel()),
-               "d2h_bytes_per_step": int(G * 8 + 32), "steps": K4, "ms_per_step": 1e3 * dt_pipe / K4,
+               "d2h_bytes_per_step": int(G * 8 + 32 + (e2e_log["log_bytes_drained_per_step"] if with_log else 0)),
+               "steps": K4, "ms_per_step": e2e_log["ms_per_step"] if with_log else 1e3 * dt_pipe / K4,
+               "journal": ("drained: every step's log segments of all %d lanes copied to pinned host memory on the drain "
+                           "stream (gpx_log_drain_async) and released (gpx_log_release) inside the timed region" % R)
+               if with_log else "NOT drained (%r)" % (e2e_log,),
+               "no_log": e2e_nolog,
                "p50_decide_latency_ms": 1e3 * float(np.median(lat)),
                "api": "gpx_round_submit / gpx_round_wait (include/gpx.h), GPX_ROUND_PACKED_REQS | GPX_ROUND_COMPACT: "
                       "pinned host buffers of 16-byte requests + payload in, one 8-byte EXEC summary per request out, "

@@ -19,7 +19,7 @@ GPX_MAX_LANES = 8
 GPX_MAX_WINDOW = 8
 
 # return codes
-GPX_OK, GPX_EINVAL, GPX_ENOMEM, GPX_ECUDA, GPX_ENOGPU, GPX_ERANGE, GPX_EIO = 0, -1, -2, -3, -4, -5, -6
+GPX_OK, GPX_EINVAL, GPX_ENOMEM, GPX_ECUDA, GPX_ENOGPU, GPX_ERANGE, GPX_EIO, GPX_EAGAIN = 0, -1, -2, -3, -4, -5, -6, -7
 # PaxosAcceptor.STATES ordinals
 ST_RECOVERY, ST_ACTIVE_1, ST_ACTIVE_2, ST_STOPPED, ST_FREE = 0, 1, 2, 3, 255
 # record flags
@@ -91,7 +91,8 @@ class Config(C.Structure):
         ("request_size_estimate", C.c_int32), ("checkpoint_interval", C.c_int32), ("cpi_noise", C.c_double),
         ("gc_majority_executed", C.c_int32), ("log_meta_decisions", C.c_int32), ("journaling_enabled", C.c_int32),
         ("batched_accept_replies", C.c_int32), ("batched_commits", C.c_int32), ("short_circuit_local", C.c_int32),
-        ("min_pp_batch_size", C.c_int32), ("digest_requests", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("min_pp_batch_size", C.c_int32), ("digest_requests", C.c_int32), ("log_backpressure", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -419,6 +420,19 @@ class Engine:
         self.L.check(self.L.fn("log_read")(self._h, C.c_uint32(lane), C.c_uint64(start), _ptr(buf),
                                            C.c_uint64(nbytes), C.byref(got), None))
         return buf[: got.value]
+
+    def log_drain_async(self, lane: int, dst_ptr: int, cap: int, after_stream: int = 0):
+        """enqueue the copy of the next undrained ring bytes into host memory at dst_ptr; returns (from, n_bytes)"""
+        f, nb = C.c_uint64(0), C.c_uint64(0)
+        self.L.check(self.L.fn("log_drain_async")(self._h, C.c_uint32(lane), C.c_void_p(dst_ptr), C.c_uint64(cap),
+                                                  C.byref(f), C.byref(nb), C.c_void_p(after_stream) if after_stream else None))
+        return f.value, nb.value
+
+    def log_drain_wait(self):
+        self.L.check(self.L.fn("log_drain_wait")(self._h))
+
+    def log_release(self, lane: int, upto: int):
+        self.L.check(self.L.fn("log_release")(self._h, C.c_uint32(lane), C.c_uint64(upto)))
 
     def counters(self) -> dict:
         c = Counters()

@@ -93,6 +93,13 @@ struct gpx_engine {
   bool pipe_ready = false;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   uint64_t next_ticket = 0, next_wait = 0;
+  /* host mirror of the per-lane log ring heads (every launch that logs has a size the host knows: the mirror is
+   * exact and no device read is needed to drain; `head_exact` drops when a phase call sized its segment from a
+   * device-resident count, the next drain / back-pressure check then re-reads the heads) */
+  uint64_t h_head[GPX_MAX_LANES] = {0}, log_tail[GPX_MAX_LANES] = {0}, drain_pos[GPX_MAX_LANES] = {0};
+  bool head_exact = true;
+  cudaStream_t s_drain = nullptr;
+  cudaEvent_t ev_drain = nullptr;
   /* timing */
   int n_sms = 148;
   bool timing = false;
@@ -317,6 +324,8 @@ void gpx_engine_destroy(gpx_engine* e) {
     if (ps.ev_k) cudaEventDestroy(ps.ev_k);
     if (ps.ev_d2h) cudaEventDestroy(ps.ev_d2h);
   }
+  if (e->s_drain) cudaStreamDestroy(e->s_drain);
+  if (e->ev_drain) cudaEventDestroy(e->ev_drain);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
   if (e->stream) {
@@ -496,6 +505,8 @@ int gpx_patch(gpx_engine* e, uint32_t n, const gpx_patch_rec* p) {
   return GPX_OK;
 }
 
+static void log_advance(gpx_engine* e, uint64_t reserved, bool exact);
+
 /* ---- kernel launch helpers (device pointers) ------------------------------------- */
 static int launch_propose(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload,
                           uint64_t payload_al, uint32_t n, int32_t* d_status, cudaStream_t st) {
@@ -549,6 +560,11 @@ static int launch_accept(gpx_engine* e, bool fused, const gpx_accept_rec* d_recs
   A.extra_cap = e->extra_cap;
   A.n_extra = &e->d_ctl->n_extra;
   const uint32_t grid = cdiv(n_max, GPX_BLOCK);
+  { /* host mirror of the ring heads: the kernels' own arithmetic (k_accept: one segment; k_act: two, back to back) */
+    const unsigned long long pay_rel = 64ull + (unsigned long long)n_max * 48ull;
+    const unsigned long long res_a = (pay_rel + blob0_bytes + blob1_bytes + 31ull) & ~31ull;
+    log_advance(e, fused ? res_a + 64ull + (unsigned long long)n_max * 32ull : res_a, blob1_used_ptr == nullptr);
+  }
   if (fused) {
     GPX_DISPATCH_L(e->cfg.n_lanes, k_act, grid, st, e->S, A);
   } else {
@@ -582,6 +598,7 @@ static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uin
   A.extra = e->d_extra;
   A.extra_cap = e->extra_cap;
   A.n_extra = &e->d_ctl->n_extra;
+  log_advance(e, 64ull + (unsigned long long)n_max * 32ull, true);
   GPX_DISPATCH_L(e->cfg.n_lanes, k_commit, cdiv(n_max, GPX_BLOCK), st, e->S, A);
   CK(cudaGetLastError());
   return GPX_OK;
@@ -654,6 +671,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.pay_rel = 64u + n * 48u;
   RA.res_a = ((unsigned long long)RA.pay_rel + RA.pay_bytes + 31ull) & ~31ull;
   RA.res_d = 64ull + (unsigned long long)n * 32ull;
+  log_advance(e, RA.res_a + RA.res_d, true);
   const uint32_t L = e->cfg.n_lanes;
   const uint32_t teams_per_block = (GPX_RBLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
   const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
@@ -673,8 +691,43 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   return GPX_OK;
 }
 
+/* ---- log ring bookkeeping on the host ------------------------------------------------------------------ */
+static int log_resync(gpx_engine* e) { /* the true heads, after everything enqueued so far */
+  if (e->head_exact) return GPX_OK;
+  CK(cudaDeviceSynchronize());
+  unsigned long long heads[GPX_MAX_LANES];
+  CK(cudaMemcpy(heads, e->S.ring_head, sizeof heads, cudaMemcpyDeviceToHost));
+  for (uint32_t l = 0; l < e->cfg.n_lanes; l++) e->h_head[l] = heads[l];
+  e->head_exact = true;
+  return GPX_OK;
+}
+/* what seg_base + the publishing block do on the device, on the mirror: one segment (or one pair of segments laid out
+ * back to back) of `reserved` bytes is appended to every lane; `exact` = the host knows `reserved` */
+static void log_advance(gpx_engine* e, uint64_t reserved, bool exact) {
+  if (!e->cfg.log_ring_bytes) return;
+  if (!exact) e->head_exact = false;
+  if (!e->head_exact) return;
+  const uint64_t cap = e->cfg.log_ring_bytes;
+  for (uint32_t l = 0; l < e->cfg.n_lanes; l++) {
+    uint64_t h = e->h_head[l];
+    const uint64_t pos = h & (cap - 1);
+    if (pos + reserved > cap) h += cap - pos;
+    e->h_head[l] = h + reserved;
+  }
+}
+/* `reserved` = upper bound of what one API call appends per lane.  With log_backpressure the call is refused
+ * (GPX_EAGAIN, nothing has happened yet) when it could overwrite bytes that were not released (gpx_log_release):
+ * AbstractPaxosLogger.logAndMessage :157 logs THEN messages -- an ACCEPT_REPLY may only leave once its ACCEPT is
+ * durable, so the journal must have been drained before the ring position is reused. */
 static int ring_fits(gpx_engine* e, uint64_t reserved) {
   if (reserved > e->cfg.log_ring_bytes) return fail(GPX_ERANGE, "batch does not fit the log ring; raise log_ring_bytes");
+  if (e->cfg.log_backpressure) {
+    int rc = log_resync(e);
+    if (rc) return rc;
+    for (uint32_t l = 0; l < e->cfg.n_lanes; l++) /* 2 x: every segment of the call may first skip to the ring start */
+      if (e->h_head[l] - e->log_tail[l] + 2 * reserved > e->cfg.log_ring_bytes)
+        return fail(GPX_EAGAIN, "log ring full: drain it (gpx_log_drain_async) and release the drained bytes (gpx_log_release)");
+  }
   return GPX_OK;
 }
 static int check_batch(gpx_engine* e, uint32_t n, uint64_t payload_bytes) {
@@ -827,6 +880,7 @@ int gpx_handle_prepares(gpx_engine* e, uint32_t n, const gpx_pvalue_hdr* prepare
   A.recs = e->d_decisions;
   A.n = n;
   A.replies = (gpx_prepare_reply_rec*)e->d_misc;
+  log_advance(e, 64ull + 32ull * n, true);
   GPX_DISPATCH_L(L, k_prepare, cdiv(n, GPX_BLOCK), st, e->S, A);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_replies, e->d_misc, out_bytes, cudaMemcpyDeviceToHost, st));
@@ -1317,6 +1371,57 @@ int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_
     if (nb > first) CK(cudaMemcpy((uint8_t*)dst + first, e->S.ring[lane], nb - first, cudaMemcpyDeviceToHost));
   }
   if (n_copied) *n_copied = nb;
+  return GPX_OK;
+}
+
+/* Asynchronous drain (SQLPaxosLogger.journal :965-1036 appends the batch to the journal file; here the caller's
+ * page-locked buffer stands for the file's write buffer).  Everything is enqueued: the copy runs on the engine's
+ * drain stream behind the work already enqueued on `after_stream` (NULL = the engine's stream) and overlaps later
+ * rounds. */
+int gpx_log_drain_async(gpx_engine* e, uint32_t lane, void* dst, uint64_t cap, uint64_t* from, uint64_t* n_bytes,
+                        void* after_stream) {
+  if (!e || !dst || !from || !n_bytes) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  int rc = log_resync(e);
+  if (rc) return rc;
+  if (!e->s_drain) {
+    CK(cudaStreamCreateWithFlags(&e->s_drain, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_drain, cudaEventDisableTiming));
+  }
+  const uint64_t rc_ = e->S.ring_cap, f = e->drain_pos[lane], h = e->h_head[lane];
+  if (h - f > rc_) return fail(GPX_ERANGE, "undrained bytes were already overwritten (enable log_backpressure)");
+  const uint64_t nb = std::min<uint64_t>(cap, h - f);
+  *from = f;
+  *n_bytes = nb;
+  if (!nb) return GPX_OK;
+  CK(cudaEventRecord(e->ev_drain, after_stream ? (cudaStream_t)after_stream : e->stream));
+  CK(cudaStreamWaitEvent(e->s_drain, e->ev_drain, 0));
+  const uint64_t pos = f & (rc_ - 1), first = std::min<uint64_t>(nb, rc_ - pos);
+  CK(cudaMemcpyAsync(dst, e->S.ring[lane] + pos, first, cudaMemcpyDeviceToHost, e->s_drain));
+  if (nb > first)
+    CK(cudaMemcpyAsync((uint8_t*)dst + first, e->S.ring[lane], nb - first, cudaMemcpyDeviceToHost, e->s_drain));
+  e->drain_pos[lane] = f + nb;
+  return GPX_OK;
+}
+/* forget the undrained backlog: the drain cursor and the tail jump to the current heads (a caller that ran with the
+ * journal disabled and now turns it on) */
+int gpx_log_drain_skip(gpx_engine* e) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  int rc = log_resync(e);
+  if (rc) return rc;
+  for (uint32_t l = 0; l < e->cfg.n_lanes; l++) e->drain_pos[l] = e->log_tail[l] = e->h_head[l];
+  return GPX_OK;
+}
+int gpx_log_drain_wait(gpx_engine* e) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (e->s_drain) CK(cudaStreamSynchronize(e->s_drain));
+  return GPX_OK;
+}
+int gpx_log_release(gpx_engine* e, uint32_t lane, uint64_t upto) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  if (upto > e->drain_pos[lane]) return fail(GPX_EINVAL, "release beyond the drained position");
+  if (upto > e->log_tail[lane]) e->log_tail[lane] = upto;
   return GPX_OK;
 }
 

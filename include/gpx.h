@@ -68,7 +68,8 @@ enum {
   GPX_ECUDA = -3,
   GPX_ENOGPU = -4,
   GPX_ERANGE = -5,
-  GPX_EIO = -6
+  GPX_EIO = -6,
+  GPX_EAGAIN = -7 /* log ring full (log_backpressure): drain + release, then repeat the call; nothing was done */
 };
 
 /* PaxosAcceptor.STATES ordinals (PaxosAcceptor.java:87-92); FREE = no instance */
@@ -281,7 +282,11 @@ typedef struct gpx_config {
   int32_t short_circuit_local;     /* SHORT_CIRCUIT_LOCAL :834 */
   int32_t min_pp_batch_size;       /* MIN_PP_BATCH_SIZE :860 */
   int32_t digest_requests;         /* DIGEST_REQUESTS :788 (false) */
-  int32_t reserved[8];
+  int32_t log_backpressure;        /* 1: a call that could overwrite log bytes not yet released by gpx_log_release is
+                                    * refused with GPX_EAGAIN (log-then-message, AbstractPaxosLogger.java:691-716: the
+                                    * journal must be drained before a ring position is reused); 0 (default): the ring
+                                    * overwrites the oldest bytes */
+  int32_t reserved[7];
 } gpx_config;
 
 typedef struct gpx_counters {
@@ -460,6 +465,21 @@ int gpx_digest_requests(gpx_engine* e, uint32_t n, const gpx_request_rec* reqs, 
 /* copy ring bytes [from, min(head, from+cap)) of `lane` into dst; *head receives the ring head */
 int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_t cap,
                  uint64_t* n_copied, uint64_t* head);
+
+/* Drain without stopping the rounds (AbstractPaxosLogger.BatchedLogger :691-716 is a thread beside the protocol
+ * threads; SQLPaxosLogger.journal :965-1036 / Journaler.appendToLogFile :814-826 append to the journal file).
+ * gpx_log_drain_async enqueues, on the engine's own drain stream and behind the work already enqueued on
+ * `after_stream` (a cudaStream_t; NULL = the engine's stream), the copy of the next undrained ring bytes of `lane`
+ * -- [*from, *from + *n_bytes), at most cap, in ring order -- into dst (host memory; page-locked to overlap) and
+ * returns at once.  The host tracks the ring heads itself (every logging call has a host-known size), so no device
+ * read is involved.  gpx_log_drain_wait blocks until the enqueued copies are done; gpx_log_release(lane, upto) tells
+ * the engine that everything before `upto` is durable elsewhere: with gpx_config.log_backpressure set, a call
+ * that would overwrite unreleased bytes is refused with GPX_EAGAIN before it does anything. */
+int gpx_log_drain_async(gpx_engine* e, uint32_t lane, void* dst, uint64_t cap, uint64_t* from, uint64_t* n_bytes,
+                        void* after_stream);
+int gpx_log_drain_wait(gpx_engine* e);
+int gpx_log_drain_skip(gpx_engine* e); /* drop the backlog: drain cursor and tail <- current heads */
+int gpx_log_release(gpx_engine* e, uint32_t lane, uint64_t upto);
 
 /* ---- introspection ---------------------------------------------------------------- */
 int gpx_get_counters(gpx_engine* e, gpx_counters* out);

@@ -12,6 +12,7 @@ if ROOT not in sys.path:
 
 from gigapaxos_b200 import abi  # noqa: E402
 from gigapaxos_b200.abi import Engine, Library  # noqa: E402
+from gigapaxos_b200.abi import GpxError as GpxErrorT  # noqa: E402
 
 ORACLE_PATH = os.path.join(ROOT, "oracle", "libgpx_oracle.so")
 _oracle = None
