@@ -184,6 +184,31 @@ def engine_config(lib, G, R, P, device):
     return cfg
 
 
+class L2Flush:
+    """Flush the 126 MB L2 between timed steps, outside the timed events: a 256 MiB write (everything the previous step
+    left is evicted) followed by a 256 MiB READ, so that the cache ends up full of CLEAN lines.  After a write-only
+    flush the timed kernel would have to write back ~100 MB of the flush's own dirty lines before it can allocate
+    anything -- a cost that belongs to the flush, not to the kernel (`--flush write` keeps that behaviour)."""
+
+    def __init__(self, dev, mode="clean"):
+        import torch
+        self.torch, self.mode = torch, mode
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.rd = torch.zeros(64 << 20, dtype=torch.int32, device=dev)  # 256 MiB
+        self.acc = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def zero_(self):  # the call sites' name
+        self.buf.zero_()
+        if self.mode == "clean":
+            self.torch.sum(self.rd, dim=0, keepdim=True, dtype=self.torch.int64, out=self.acc)
+
+    def describe(self):
+        return ("flushed between timed steps, outside the timed events: 256 MiB write then 256 MiB read (cold and clean)"
+                if self.mode == "clean" else
+                "flushed between timed steps (256 MiB write, outside the timed events; the flush's dirty lines are "
+                "written back during the timed kernel)")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -335,6 +360,8 @@ def main():
     ap.add_argument("--groups", type=int, default=0, help="override groups per GPU")
     ap.add_argument("--payload", type=int, default=0, help="override request payload bytes")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--flush", default="clean", choices=["clean", "write"],
+                    help="clean (default): 256 MiB write + 256 MiB read between timed steps; write: the write only")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -370,7 +397,7 @@ def main():
         "placement": "packed: all R replicas of a group on the GPU that owns the group; groups sharded by "
                      "|String.hashCode(paxosID)| mod n_gpus; no data-path collective"
                      + ("" if world >= R or world == 1 else f" (fewer GPUs than replicas: SURVEY.md 8e packs them)"),
-        "l2": "none" if args.no_flush else "flushed between timed steps (256 MiB write, outside the timed events)",
+        "l2": "none" if args.no_flush else L2Flush.describe(type("x", (), {"mode": args.flush})()),
         "init": "batch creation (HotRestoreInfo.createHRI)",
     }
 
@@ -428,7 +455,7 @@ def main():
     d_pay = [torch.from_numpy(b[1].copy()).to(dev) for b in host_batches]
     d_status = torch.zeros(G, dtype=torch.int32, device=dev)
     d_exec = torch.zeros(G * R * 24, dtype=torch.uint8, device=dev)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = L2Flush(dev, args.flush)
     round_dev = lib.fn("round_device")
     # everything below is issued on ONE explicit stream: the engine launches its kernels on the
     # stream handed to gpx_round_device and torch.cuda.Event only sees torch's current stream
@@ -869,7 +896,7 @@ def run_cfg4(args, lib, dev, rank, world, wl, K, W, metric, config):
     d_pay = [torch.from_numpy(h[1]).to(dev) for h in host]
     d_status = torch.zeros(G, dtype=torch.int32, device=dev)
     d_exec = torch.zeros(G * R * 24, dtype=torch.uint8, device=dev)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = L2Flush(dev, args.flush)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     round_dev = lib.fn("round_device")
@@ -985,7 +1012,7 @@ def run_cfg5(args, lib, dev, rank, world, wl, K, W, metric, config):
         eng.create_groups(make_descs_fast(abi, n, R, gid0=lo, name0=rank * GT + lo))
     create_s = time.perf_counter() - t0
     free_b, total_b = torch.cuda.mem_get_info(dev)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = L2Flush(dev, args.flush)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     round_dev = lib.fn("round_device")
@@ -1189,7 +1216,7 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
         return ios
 
     ios = [make_ios(nb) for nb in range(NB)]
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = L2Flush(dev, args.flush)
 
     def barrier():
         torch.cuda.synchronize()
@@ -1377,7 +1404,7 @@ def run_spread(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
             bb[idx] = (torch.from_numpy(reqs.view(np.uint8).copy()).to(dev),
                        torch.from_numpy(np.concatenate([pay, np.zeros(16, np.uint8)])).to(dev)[: pay.size], G)
         batches.append(bb)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = L2Flush(dev, args.flush)
 
     def barrier():
         torch.cuda.synchronize()

@@ -20,6 +20,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "libgpx_oracle.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    "-rdc=true",  # k_round launches k_round_slow from the device (tail launch): relocatable device code + cudadevrt
     "-Xcompiler", "-fPIC,-O2,-Wall",
     "-shared",
 ]
@@ -52,7 +53,7 @@ def build_engine(force: bool = False, verbose: bool = False, out: str = LIB, def
         return out
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cpp"))]
     cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", out, *units, "-ldl"]
+           "-o", out, *units, "-ldl", "-lcudadevrt"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -104,8 +104,12 @@ struct DevState {
   const MsetInfo* msets;
   uint8_t* ring[GPX_MAX_LANES];
   uint64_t ring_cap;
-  unsigned long long* ring_head; /* [L] absolute byte offsets */
-  unsigned long long* seg_seq;   /* [L] */
+  /* log position of every lane, {ring head (absolute byte offset), next segment sequence number}, kept TWICE:
+   * a launch that logs reads copy `lp` and its block 0 writes copy `lp ^ 1` (the host flips `lp` with every such
+   * launch), so nobody needs to know when the other blocks have read -- no ticket, no fence, no trailing kernel */
+  unsigned long long* log_pos;   /* [2][GPX_MAX_LANES][2] */
+  uint32_t lp;                   /* which copy this launch reads */
+  unsigned long long* cur_seg;   /* [L] segment bases of the round in flight (k_round -> k_round_slow) */
   unsigned long long* ctr;       /* [GPX_CTR_STRIPES][C_NCTR] */
   unsigned int* tickets;         /* [8] last-block tickets, one per kernel kind */
   int32_t lane_node[GPX_MAX_LANES];
@@ -217,10 +221,20 @@ struct DPValue {
 
 /* segment base of this launch for one lane: skip to the ring start if it would wrap */
 __device__ __forceinline__ unsigned long long seg_base(const DevState& S, uint32_t l, unsigned long long reserved) {
-  unsigned long long head = S.ring_head[l];
+  unsigned long long head = S.log_pos[((size_t)S.lp * GPX_MAX_LANES + l) * 2];
   unsigned long long pos = head & (S.ring_cap - 1);
   if (pos + reserved > S.ring_cap) head += S.ring_cap - pos;
   return head;
+}
+__device__ __forceinline__ unsigned long long seg_seq_of(const DevState& S, uint32_t l) {
+  return S.log_pos[((size_t)S.lp * GPX_MAX_LANES + l) * 2 + 1];
+}
+/* block 0 of a logging launch: where the NEXT launch starts (written into the other copy) */
+__device__ __forceinline__ void log_publish(const DevState& S, uint32_t l, unsigned long long new_head,
+                                            unsigned long long new_seq) {
+  unsigned long long* q = &S.log_pos[((size_t)(S.lp ^ 1u) * GPX_MAX_LANES + l) * 2];
+  q[0] = new_head;
+  q[1] = new_seq;
 }
 __device__ __forceinline__ uint8_t* ring_ptr(const DevState& S, uint32_t l, unsigned long long abs_off) {
   return S.ring[l] + (abs_off & (S.ring_cap - 1));

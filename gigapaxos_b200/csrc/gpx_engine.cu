@@ -68,7 +68,11 @@ struct gpx_engine {
   uint8_t* d_out_mask = nullptr;
   std::vector<uint8_t> h_out_mask;
   RoundCtl* d_ctl = nullptr;
-  RoundCtl* d_rctl = nullptr; /* [2] the round kernels' own block: [0] working (zero between rounds), [1] published */
+  RoundCtl* d_rctl = nullptr; /* [2] the round kernels' own control blocks: they alternate as the working block, each
+                               * round zeroes the one the next round counts into */
+  const RoundCtl* last_ctl = nullptr; /* where the last round left its counters */
+  int round_mode = 0;         /* gpx_set_round_mode: 0 / 1 device tail launch of k_round_slow, 2 host-launched pair */
+  uint32_t rparity = 0;
   RoundCtl* h_ctl = nullptr; /* pinned */
   void* d_misc = nullptr;    /* group-management staging */
   size_t misc_bytes = 0;
@@ -238,12 +242,13 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
     TRY(e->dalloc(&S.ring[l], (size_t)cfg->log_ring_bytes));
     cudaMemset(S.ring[l], 0, cfg->log_ring_bytes);
   }
-  TRY(e->dalloc(&S.ring_head, (size_t)GPX_MAX_LANES));
-  TRY(e->dalloc(&S.seg_seq, (size_t)GPX_MAX_LANES));
+  TRY(e->dalloc(&S.log_pos, (size_t)4 * GPX_MAX_LANES));
+  TRY(e->dalloc(&S.cur_seg, (size_t)GPX_MAX_LANES));
   TRY(e->dalloc(&S.ctr, (size_t)C_NCTR * GPX_CTR_STRIPES));
   TRY(e->dalloc(&S.tickets, (size_t)8));
-  cudaMemset(S.ring_head, 0, GPX_MAX_LANES * 8);
-  cudaMemset(S.seg_seq, 0, GPX_MAX_LANES * 8);
+  cudaMemset(S.log_pos, 0, 4 * GPX_MAX_LANES * 8);
+  S.lp = 0;
+  cudaMemset(S.cur_seg, 0, GPX_MAX_LANES * 8);
   cudaMemset(S.ctr, 0, C_NCTR * GPX_CTR_STRIPES * 8);
   cudaMemset(S.tickets, 0, 8 * 4);
   cudaMemset(S.grp_meta, 0, G * 4);
@@ -301,6 +306,7 @@ int gpx_engine_create(const gpx_config* cfg, gpx_engine** out) {
   }
   cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 5; i++) cudaEventCreate(&e->ev[i]);
+  if (const char* rm = getenv("GPX_ROUND_MODE")) e->round_mode = atoi(rm) >= 0 && atoi(rm) <= 2 ? atoi(rm) : 0; /* tuning / tests */
   e->h_version.assign(G, 0);
   e->h_name_hash.assign(G, 0);
   cudaError_t err = cudaDeviceSynchronize();
@@ -506,6 +512,8 @@ int gpx_patch(gpx_engine* e, uint32_t n, const gpx_patch_rec* p) {
 }
 
 static void log_advance(gpx_engine* e, uint64_t reserved, bool exact);
+/* every launch that appends to the log reads log_pos[lp] and writes log_pos[lp ^ 1]: flip after the launch */
+static inline void log_flip(gpx_engine* e) { e->S.lp ^= 1u; }
 
 /* ---- kernel launch helpers (device pointers) ------------------------------------- */
 static int launch_propose(gpx_engine* e, const gpx_request_rec* d_reqs, const uint8_t* d_payload,
@@ -570,6 +578,7 @@ static int launch_accept(gpx_engine* e, bool fused, const gpx_accept_rec* d_recs
   } else {
     GPX_DISPATCH_L(e->cfg.n_lanes, k_accept, grid, st, e->S, A);
   }
+  log_flip(e);
   CK(cudaGetLastError());
   return GPX_OK;
 }
@@ -600,23 +609,23 @@ static int launch_commit(gpx_engine* e, const gpx_decision_rec* d_dec, const uin
   A.n_extra = &e->d_ctl->n_extra;
   log_advance(e, 64ull + (unsigned long long)n_max * 32ull, true);
   GPX_DISPATCH_L(e->cfg.n_lanes, k_commit, cdiv(n_max, GPX_BLOCK), st, e->S, A);
+  log_flip(e);
   CK(cudaGetLastError());
   return GPX_OK;
 }
 
-/* k_round<L, LP>: LP = lanes padded to a power of two (team width) */
+/* k_round<L, LP, DEF>: LP = L (team width); DEF = the reference's default configuration folded at compile time */
 extern "C++" {
 template <int L, int LP>
-static void launch_round_t(uint32_t grid, uint32_t slow_grid, cudaStream_t st, const DevState& S, const RoundArgs& RA) {
-  /* the reference's default configuration gets the kernel with the flags folded at compile time */
+static void launch_round_t(uint32_t grid, cudaStream_t st, const DevState& S, const RoundArgs& RA) {
   if (S.journaling && S.gc_majority_executed && S.log_meta && !S.cpi_per_group)
     k_round<L, LP, true><<<grid, GPX_RBLOCK, 0, st>>>(S, RA);
   else
     k_round<L, LP, false><<<grid, GPX_RBLOCK, 0, st>>>(S, RA);
-  { /* programmatic dependent launch: k_round_slow's launch latency hides behind k_round */
+  if (!RA.tail_launch) { /* host-launched pair; programmatic dependent launch hides k_round_slow's launch latency */
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(slow_grid);
+    cfg.gridDim = dim3(RA.slow_grid);
     cfg.blockDim = dim3(GPX_BLOCK);
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -632,7 +641,15 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
                         uint32_t n, int32_t* d_status, gpx_exec_rec* d_exec, cudaStream_t st,
                         RoundCtl* d_ctl = nullptr, gpx_exec_rec* d_extra = nullptr, uint32_t extra_cap = 0,
                         gpx_exec_sum* d_sum = nullptr) {
-  if (!d_ctl) d_ctl = e->d_rctl; /* [0] working block (zero on entry, re-zeroed by k_round_slow), [1] published */
+  /* the round counts into `working`: the engine's own blocks [0] / [1] alternate (each round zeroes the one the next
+   * round uses); a caller-provided block is zeroed by the caller */
+  RoundCtl* ctl_zero = nullptr;
+  if (!d_ctl) {
+    d_ctl = e->d_rctl + e->rparity;
+    ctl_zero = e->d_rctl + (e->rparity ^ 1u);
+    e->rparity ^= 1u;
+  }
+  e->last_ctl = d_ctl;
   if (!d_extra) {
     d_extra = e->d_extra;
     extra_cap = e->extra_cap;
@@ -647,7 +664,7 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   RA.P.copy_tab = e->d_copy_tab;
   RA.P.copy_dst = e->d_copy_dst;
   RA.P.ctl = d_ctl;
-  RA.ctl_out = d_ctl + 1;
+  RA.ctl_zero = ctl_zero;
   RA.sum = d_sum;
   RA.A.n_max = n;
   RA.A.blob0 = d_payload;
@@ -675,18 +692,20 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
   const uint32_t L = e->cfg.n_lanes;
   const uint32_t teams_per_block = (GPX_RBLOCK / 32u) * (32u / L); /* teams of L adjacent lanes */
   const uint32_t grid = cdiv((uint64_t)n, teams_per_block);
-  const uint32_t slow_grid = std::min<uint32_t>(grid, 2u * (uint32_t)e->n_sms); /* grid-stride over the todo list; all
+  RA.slow_grid = std::min<uint32_t>(grid, 2u * (uint32_t)e->n_sms);
+  RA.tail_launch = e->round_mode == 2 ? 0u : 1u; /* grid-stride over the todo list; all
                                                                             * blocks resident (grid barriers) */
   switch (L) {
-    case 1: launch_round_t<1, 1>(grid, slow_grid, st, e->S, RA); break;
-    case 2: launch_round_t<2, 2>(grid, slow_grid, st, e->S, RA); break;
-    case 3: launch_round_t<3, 3>(grid, slow_grid, st, e->S, RA); break;
-    case 4: launch_round_t<4, 4>(grid, slow_grid, st, e->S, RA); break;
-    case 5: launch_round_t<5, 5>(grid, slow_grid, st, e->S, RA); break;
-    case 6: launch_round_t<6, 6>(grid, slow_grid, st, e->S, RA); break;
-    case 7: launch_round_t<7, 7>(grid, slow_grid, st, e->S, RA); break;
-    default: launch_round_t<8, 8>(grid, slow_grid, st, e->S, RA); break;
+    case 1: launch_round_t<1, 1>(grid, st, e->S, RA); break;
+    case 2: launch_round_t<2, 2>(grid, st, e->S, RA); break;
+    case 3: launch_round_t<3, 3>(grid, st, e->S, RA); break;
+    case 4: launch_round_t<4, 4>(grid, st, e->S, RA); break;
+    case 5: launch_round_t<5, 5>(grid, st, e->S, RA); break;
+    case 6: launch_round_t<6, 6>(grid, st, e->S, RA); break;
+    case 7: launch_round_t<7, 7>(grid, st, e->S, RA); break;
+    default: launch_round_t<8, 8>(grid, st, e->S, RA); break;
   }
+  log_flip(e);
   CK(cudaGetLastError());
   return GPX_OK;
 }
@@ -695,9 +714,9 @@ static int launch_round(gpx_engine* e, const gpx_request_rec* d_reqs, const uint
 static int log_resync(gpx_engine* e) { /* the true heads, after everything enqueued so far */
   if (e->head_exact) return GPX_OK;
   CK(cudaDeviceSynchronize());
-  unsigned long long heads[GPX_MAX_LANES];
-  CK(cudaMemcpy(heads, e->S.ring_head, sizeof heads, cudaMemcpyDeviceToHost));
-  for (uint32_t l = 0; l < e->cfg.n_lanes; l++) e->h_head[l] = heads[l];
+  unsigned long long pos[2 * GPX_MAX_LANES]; /* the copy the next launch will read: {head, seq} per lane */
+  CK(cudaMemcpy(pos, e->S.log_pos + (size_t)e->S.lp * 2 * GPX_MAX_LANES, sizeof pos, cudaMemcpyDeviceToHost));
+  for (uint32_t l = 0; l < e->cfg.n_lanes; l++) e->h_head[l] = pos[2 * l];
   e->head_exact = true;
   return GPX_OK;
 }
@@ -882,6 +901,7 @@ int gpx_handle_prepares(gpx_engine* e, uint32_t n, const gpx_pvalue_hdr* prepare
   A.replies = (gpx_prepare_reply_rec*)e->d_misc;
   log_advance(e, 64ull + 32ull * n, true);
   GPX_DISPATCH_L(L, k_prepare, cdiv(n, GPX_BLOCK), st, e->S, A);
+  log_flip(e);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_replies, e->d_misc, out_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1000,6 +1020,13 @@ static int round_on_stream(gpx_engine* e, bool fused, const gpx_request_rec* d_r
   return GPX_OK;
 }
 
+int gpx_set_round_mode(gpx_engine* e, int mode) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (mode < 0 || mode > 2) return fail(GPX_EINVAL, "round mode: 0 / 1 device tail launch, 2 host-launched pair");
+  e->round_mode = mode;
+  return GPX_OK;
+}
+
 static int round_host(gpx_engine* e, bool fused, uint32_t n, const gpx_request_rec* reqs, const uint8_t* payload,
                       uint64_t payload_bytes, int32_t* status, gpx_exec_rec* out_exec, uint32_t* n_exec_slots,
                       gpx_exec_rec* out_extra_exec, uint32_t extra_cap, uint32_t* n_extra) {
@@ -1021,7 +1048,7 @@ static int round_host(gpx_engine* e, bool fused, uint32_t n, const gpx_request_r
   rc = round_on_stream(e, fused, e->d_reqs, e->d_payload, payload_bytes, n, e->d_status, e->d_exec, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(status, e->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  rc = fetch_ctl(e, fused ? e->d_rctl + 1 : nullptr);
+  rc = fetch_ctl(e, fused ? e->last_ctl : nullptr);
   if (rc) return rc;
   /* fused: one EXEC row per REQUEST index (VOID where the request carries no ACCEPT); phases: one per DECISION */
   const uint32_t rows = fused ? n : e->h_ctl->n_decisions;
@@ -1228,7 +1255,7 @@ static int pipe_init(gpx_engine* e) {
       return rc;
     if (cudaHostAlloc((void**)&ps.h_ctl, sizeof(RoundCtl), cudaHostAllocDefault) != cudaSuccess)
       return fail(GPX_ENOMEM, "cudaHostAlloc");
-    CK(cudaMemset(ps.d_ctl, 0, 2 * sizeof(RoundCtl))); /* [0] working, [1] published by k_round_slow */
+    CK(cudaMemset(ps.d_ctl, 0, 2 * sizeof(RoundCtl)));
     CK(cudaEventCreateWithFlags(&ps.ev_h2d, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ps.ev_k, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ps.ev_d2h, cudaEventDisableTiming));
@@ -1270,6 +1297,7 @@ int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket) {
     CK(cudaMemcpyAsync(ps.d_reqs, io->reqs, n * sizeof(gpx_request_rec), cudaMemcpyHostToDevice, e->s_h2d));
   if (io->payload_bytes)
     CK(cudaMemcpyAsync(ps.d_payload, io->payload, io->payload_bytes, cudaMemcpyHostToDevice, e->s_h2d));
+  CK(cudaMemsetAsync(ps.d_ctl, 0, sizeof(RoundCtl), e->s_h2d)); /* the slot's control block: the round counts into it */
   CK(cudaEventRecord(ps.ev_h2d, e->s_h2d));
   /* stream 2: the round (serialised with every other engine call on the engine's stream) */
   CK(cudaStreamWaitEvent(e->stream, ps.ev_h2d, 0));
@@ -1287,7 +1315,7 @@ int gpx_round_submit(gpx_engine* e, const gpx_round_io* io, uint64_t* ticket) {
   CK(cudaEventRecord(ps.ev_k, e->stream));
   /* stream 3: results */
   CK(cudaStreamWaitEvent(e->s_d2h, ps.ev_k, 0));
-  CK(cudaMemcpyAsync(ps.h_ctl, ps.d_ctl + 1, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->s_d2h));
+  CK(cudaMemcpyAsync(ps.h_ctl, e->last_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, e->s_d2h));
   if (compact) {
     CK(cudaMemcpyAsync(io->sum, ps.d_sum, n * sizeof(gpx_exec_sum), cudaMemcpyDeviceToHost, e->s_d2h));
   } else {
@@ -1357,9 +1385,9 @@ int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_
   if (!e) return fail(GPX_EINVAL, "null argument");
   if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
   CK(cudaDeviceSynchronize());
-  unsigned long long heads[GPX_MAX_LANES];
-  CK(cudaMemcpy(heads, e->S.ring_head, sizeof heads, cudaMemcpyDeviceToHost));
-  const uint64_t h = heads[lane], rc = e->S.ring_cap;
+  unsigned long long pos[2 * GPX_MAX_LANES];
+  CK(cudaMemcpy(pos, e->S.log_pos + (size_t)e->S.lp * 2 * GPX_MAX_LANES, sizeof pos, cudaMemcpyDeviceToHost));
+  const uint64_t h = pos[2 * lane], rc = e->S.ring_cap;
   if (head) *head = h;
   uint64_t nb = 0;
   if (dst && from < h) {

@@ -728,7 +728,11 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_accept(const __gr
   }
   if (i == 0) {
 #pragma unroll
-    for (int l = 0; l < L; l++) write_seg_hdr(S, l, segb[l], GPX_F_ACCEPT, A.n_max, n, pay_bytes, 48, S.seg_seq[l]);
+    for (int l = 0; l < L; l++) {
+      const unsigned long long sq = seg_seq_of(S, l);
+      write_seg_hdr(S, l, segb[l], GPX_F_ACCEPT, A.n_max, n, pay_bytes, 48, sq);
+      log_publish(S, l, segb[l] + reserved, sq + 1ull);
+    }
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
   if (tile_bytes) mbar_wait(&s_bar, 0);
@@ -795,19 +799,6 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_accept(const __gr
     }
   }
   flush_counters(S, s_ctr);
-  /* last block publishes the new ring heads */
-  __shared__ unsigned int s_last;
-  __threadfence();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[1], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-      S.ring_head[l] = segb[l] + reserved;
-      S.seg_seq[l] += 1ull;
-    }
-    S.tickets[1] = 0;
-  }
 }
 
 /* ============================== k_tally ======================================= */
@@ -916,7 +907,11 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_commit(const __gr
   for (int l = 0; l < L; l++) segb[l] = seg_base(S, l, reserved);
   if (i == 0) {
 #pragma unroll
-    for (int l = 0; l < L; l++) write_seg_hdr(S, l, segb[l], GPX_F_DECISION, A.n_max, n, 0, 32, S.seg_seq[l]);
+    for (int l = 0; l < L; l++) {
+      const unsigned long long sq = seg_seq_of(S, l);
+      write_seg_hdr(S, l, segb[l], GPX_F_DECISION, A.n_max, n, 0, 32, sq);
+      log_publish(S, l, segb[l] + reserved, sq + 1ull);
+    }
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
   if (i < n) {
@@ -975,18 +970,6 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_commit(const __gr
     }
   }
   flush_counters(S, s_ctr);
-  __shared__ unsigned int s_last;
-  __threadfence();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[3], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-      S.ring_head[l] = segb[l] + reserved;
-      S.seg_seq[l] += 1ull;
-    }
-    S.tickets[3] = 0;
-  }
 }
 
 /* ============================== k_act (fused) ================================== */
@@ -1020,8 +1003,10 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ACT_MINB) k_act(const __grid_co
   if (i == 0) {
 #pragma unroll
     for (int l = 0; l < L; l++) {
-      write_seg_hdr(S, l, segb[l], GPX_F_ACCEPT, A.n_max, n, pay_bytes, 48, S.seg_seq[l]);
-      write_seg_hdr(S, l, dsegb[l], GPX_F_DECISION, A.n_max, n, 0, 32, S.seg_seq[l] + 1ull);
+      const unsigned long long sq = seg_seq_of(S, l);
+      write_seg_hdr(S, l, segb[l], GPX_F_ACCEPT, A.n_max, n, pay_bytes, 48, sq);
+      write_seg_hdr(S, l, dsegb[l], GPX_F_DECISION, A.n_max, n, 0, 32, sq + 1ull);
+      log_publish(S, l, segb[l] + res_a + res_d, sq + 2ull);
     }
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
@@ -1217,18 +1202,6 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_ACT_MINB) k_act(const __grid_co
     }
   }
   flush_counters(S, s_ctr);
-  __shared__ unsigned int s_last;
-  __threadfence();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[4], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-      S.ring_head[l] = segb[l] + res_a + res_d;
-      S.seg_seq[l] += 2ull;
-    }
-    S.tickets[4] = 0;
-  }
 }
 
 /* ============================== state maintenance ============================== */

@@ -29,7 +29,11 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_prepare(const __grid_constant__ D
   for (int l = 0; l < L; l++) segb[l] = seg_base(S, l, reserved);
   if (i == 0) {
 #pragma unroll
-    for (int l = 0; l < L; l++) write_seg_hdr(S, l, segb[l], GPX_F_PREPARE, n, n, 0, 32, S.seg_seq[l]);
+    for (int l = 0; l < L; l++) {
+      const unsigned long long sq = seg_seq_of(S, l);
+      write_seg_hdr(S, l, segb[l], GPX_F_PREPARE, n, n, 0, 32, sq);
+      log_publish(S, l, segb[l] + reserved, sq + 1ull);
+    }
     atomicAdd(&S.ctr[C_KERNEL_LAUNCHES], 1ull);
   }
   if (i < n) {
@@ -113,19 +117,5 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_prepare(const __grid_constant__ D
         }
       }
     }
-  }
-  /* last block publishes the new ring heads */
-  __shared__ unsigned int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[6], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-      S.ring_head[l] = segb[l] + reserved;
-      S.seg_seq[l] += 1ull;
-    }
-    S.tickets[6] = 0;
   }
 }

@@ -39,8 +39,12 @@ struct RoundArgs {
   uint32_t* n_todo;
   uint8_t* mark;                /* [n] 1 = the request belongs to a run left to k_round_slow (written by k_round for every
                                  * request: phase 2 of the slow kernel is one thread per REQUEST) */
-  RoundCtl* ctl_out;            /* k_round_slow publishes the round's counters here and re-zeroes P.ctl for the next
-                                 * round (no memset between rounds) */
+  RoundCtl* ctl_zero;           /* the control block the NEXT round will count into, zeroed by block 0 of k_round (null: the
+                                 * host zeroes it) */
+  uint32_t slow_grid;           /* grid of k_round_slow (all blocks resident: its phases are separated by grid barriers) */
+  uint32_t tail_launch;         /* 1: the first team that leaves a run to k_round_slow launches it from the device as a
+                                 * tail launch (runs when k_round has completed, before anything else on the stream);
+                                 * 0: the host launches k_round_slow behind every k_round */
   /* launch constants of the two log segments of a lane (host-computed: no 64-bit arithmetic in the kernels) */
   unsigned long long pay_bytes; /* payload area of the ACCEPT segment = blob0_bytes + blob1_res */
   unsigned long long res_a;     /* ACCEPT segment bytes  = align32(64 + 48 n + pay_bytes) */
@@ -50,16 +54,6 @@ struct RoundArgs {
                                  * n_lanes EXEC rows; everything that is not the plain in-order case goes to the
                                  * extra queue.  null = full EXEC rows */
 };
-
-__device__ __forceinline__ void publish_ctl(const RoundArgs& RA) {
-  int4* w = reinterpret_cast<int4*>(RA.P.ctl);
-  int4* o = reinterpret_cast<int4*>(RA.ctl_out);
-  static_assert(sizeof(RoundCtl) == 32, "two int4");
-  o[0] = w[0];
-  o[1] = w[1];
-  w[0] = make_int4(0, 0, 0, 0);
-  w[1] = make_int4(0, 0, 0, 0);
-}
 
 __device__ __forceinline__ void store_sum(gpx_exec_sum* dst, int slot, uint32_t lane_mask, uint32_t flags, uint32_t nreq) {
   *reinterpret_cast<int2*>(dst) = make_int2(slot, (int)(lane_mask | (flags << 8) | (nreq << 16)));
@@ -355,13 +349,16 @@ __device__ __forceinline__ void round_general(const DevState& S, const RoundArgs
   }
 }
 
+template <int L, int LP>
+__global__ void k_round_slow(const __grid_constant__ DevState S, const __grid_constant__ RoundArgs RA);
+
 /*
  * The fast kernel.  The whole body is straight-line, predicated code: every shuffle and vote is a full-warp
  * operation outside divergent control flow (no per-team reconvergence bookkeeping), loads are issued in three
  * dependent levels (request -> rows of the group -> window entry / nodeSlotNumbers), and a team either takes
- * the in-order fast path or hands its request index to k_round_slow.  The ring heads are advanced by
- * k_round_slow (always launched behind this kernel on the same stream), so warps retire right after their last
- * store -- no fence, no ticket.
+ * the in-order fast path or hands its request index to k_round_slow -- which the first such team launches from the
+ * device as a tail launch, so that a round without left-over runs is ONE launch on the stream.  The ring heads are
+ * advanced by the block that draws the last ARRIVAL ticket: warps retire right after their last store, no fence.
  */
 template <int L, int LP, bool DEF>
 __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK)) k_round(const __grid_constant__ DevState S,
@@ -373,9 +370,6 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   const bool cf_gcme = DEF ? true : (S.gc_majority_executed != 0);
   const bool cf_logmeta = DEF ? true : (S.log_meta != 0);
   const bool cf_cpi_pg = DEF ? false : (S.cpi_per_group != 0);
-#ifdef GPX_PDL_EARLY
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); /* k_round_slow's blocks take their seats early */
-#endif
   constexpr uint32_t FULL = 0xffffffffu;
   constexpr uint32_t TPB = (GPX_RBLOCK / 32u) * (32u / LP); /* teams (= requests) per block */
   __shared__ unsigned int s_ctr[C_NCTR];
@@ -406,12 +400,25 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
   /* per-lane log segments of this launch: [ACCEPT seg (n images + payload area)][DECISION seg] */
   const unsigned long long pay_bytes = RA.pay_bytes, res_a = RA.res_a, res_d = RA.res_d;
   const uint32_t pay_rel = RA.pay_rel;
+  /* my lane's log position is read from the copy this launch owns (DevState.lp); block 0 writes the next launch's
+   * position into the other copy and leaves the segment bases for k_round_slow -- the round needs neither a ticket
+   * nor a fence nor a trailing kernel to finish */
   const unsigned long long seg = seg_base(S, sub, res_a + res_d);
   if (blockIdx.x == 0 && threadIdx.x < (uint32_t)L) { /* thread l writes lane l's two segment headers */
     const uint32_t t = threadIdx.x;
-    write_seg_hdr(S, t, seg, GPX_F_ACCEPT, n, n, pay_bytes, 48, S.seg_seq[t]);
-    write_seg_hdr(S, t, seg + res_a, GPX_F_DECISION, n, n, 0, 32, S.seg_seq[t] + 1ull);
-    if (t == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
+    const unsigned long long sq = seg_seq_of(S, t);
+    write_seg_hdr(S, t, seg, GPX_F_ACCEPT, n, n, pay_bytes, 48, sq);
+    write_seg_hdr(S, t, seg + res_a, GPX_F_DECISION, n, n, 0, 32, sq + 1ull);
+    log_publish(S, t, seg + res_a + res_d, sq + 2ull);
+    S.cur_seg[t] = seg;
+    if (t == 0) {
+      atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
+      if (RA.ctl_zero) { /* the control block the next round counts into */
+        int4* z = reinterpret_cast<int4*>(RA.ctl_zero);
+        z[0] = make_int4(0, 0, 0, 0);
+        z[1] = make_int4(0, 0, 0, 0);
+      }
+    }
   }
 
   /* ---- level A: the request record and the neighbours' gids (run-head / single-request tests) ---- */
@@ -600,7 +607,10 @@ __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK
       c_team = 1;
     }
   } else if (head && sub == 0) {
-    RA.todo[atomicAdd(RA.n_todo, 1u)] = i; /* the run goes to k_round_slow */
+    const uint32_t k = atomicAdd(RA.n_todo, 1u);
+    RA.todo[k] = i; /* the run goes to k_round_slow */
+    if (k == 0 && RA.tail_launch) /* the first left-over run of the round brings the second kernel in */
+      k_round_slow<L, LP><<<RA.slow_grid, GPX_BLOCK, 0, cudaStreamTailLaunch>>>(S, RA);
   }
   if (valid && sub == 0) RA.mark[i] = sf ? 0 : 1;
   if (sf && pal && plen > 16u) { /* bodies longer than one chunk: four independent 128-bit loads in flight */
@@ -668,18 +678,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
    * completion (and memory flush) before looking at anything it wrote */
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t ntodo = *RA.n_todo;
-  if (ntodo == 0) { /* the common case: nothing left over -- block 0 publishes the ring heads, everyone leaves */
-    if (blockIdx.x == 0 && threadIdx.x < (uint32_t)L) {
-      const unsigned long long res_a = RA.res_a, res_d = RA.res_d;
-      S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
-      S.seg_seq[threadIdx.x] += 2ull;
-      if (threadIdx.x == 0) {
-        atomicAdd(&S.ctr[C_KERNEL_LAUNCHES], 1ull);
-        publish_ctl(RA); /* n_todo is 0 and stays 0: the other blocks only read that */
-      }
-    }
-    return;
-  }
+  if (ntodo == 0) return; /* host-launched form: nothing was left over */
   const AcceptArgs& A = RA.A;
   const uint32_t n = RA.P.n;
   const uint32_t lane_id = threadIdx.x & 31u;
@@ -694,7 +693,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
   {
     unsigned long long segl[L];
 #pragma unroll
-    for (int l = 0; l < L; l++) segl[l] = seg_base(S, l, res_a + res_d);
+    for (int l = 0; l < L; l++) segl[l] = S.cur_seg[l]; /* k_round has moved the ring heads on already */
     for (uint32_t q = blockIdx.x * GPX_BLOCK + threadIdx.x; q < n; q += gridDim.x * GPX_BLOCK) {
       if (!RA.mark[q]) continue;
       const int st = RA.P.status[q];
@@ -725,7 +724,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
     const uint32_t team = team_in_warp < TPW ? (blockIdx.x * (GPX_BLOCK / 32u) + (threadIdx.x >> 5)) * TPW + team_in_warp
                                              : 0xffffffffu;
     const uint32_t myl = sub < (uint32_t)L ? sub : 0u;
-    const unsigned long long seg = seg_base(S, myl, res_a + res_d); /* same segments as the fast kernel */
+    const unsigned long long seg = S.cur_seg[myl]; /* same segments as the fast kernel */
     const unsigned long long payb = seg + pay_rel, dseg = seg + res_a;
     for (uint32_t k = team; k < ntodo; k += nteams) {
       const uint32_t i = RA.todo[k];
@@ -734,17 +733,4 @@ __global__ void __launch_bounds__(GPX_BLOCK, 2) k_round_slow(const __grid_consta
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   flush_counters(S, s_ctr);
-  /* the last block to finish publishes the ring heads of the round (every block has read them by then) */
-  __shared__ unsigned int s_last;
-  __threadfence();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[5], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x < (uint32_t)L) {
-    S.ring_head[threadIdx.x] = seg_base(S, threadIdx.x, res_a + res_d) + res_a + res_d;
-    S.seg_seq[threadIdx.x] += 2ull;
-  }
-  if (s_last && threadIdx.x == 0) {
-    S.tickets[5] = 0;
-    publish_ctl(RA);
-  }
 }

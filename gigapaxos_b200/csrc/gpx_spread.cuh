@@ -239,7 +239,9 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_sp_accept(const _
   const unsigned long long segb = seg_base(S, 0, reserved);
   const unsigned long long payb = segb + pay_rel + B.blob_off;
   if (v == 0) {
-    write_seg_hdr(S, 0, segb, GPX_F_ACCEPT, A.vtotal, A.vtotal, A.blob_vtotal, 48, S.seg_seq[0]);
+    const unsigned long long sq = seg_seq_of(S, 0);
+    write_seg_hdr(S, 0, segb, GPX_F_ACCEPT, A.vtotal, A.vtotal, A.blob_vtotal, 48, sq);
+    log_publish(S, 0, segb + reserved, sq + 1ull);
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
   const uint32_t j = j0 + threadIdx.x;
@@ -324,15 +326,6 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_sp_accept(const _
     }
   }
   flush_counters(S, s_ctr);
-  __shared__ unsigned int s_last;
-  __threadfence();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[1], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    S.ring_head[0] = segb + reserved;
-    S.seg_seq[0] += 1ull;
-    S.tickets[1] = 0;
-  }
 }
 
 /* ============================== k_sp_tally ============================== */
@@ -444,7 +437,9 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_sp_commit(const _
   const unsigned long long reserved = 64ull + (unsigned long long)A.vtotal * 32ull;
   const unsigned long long segb = seg_base(S, 0, reserved);
   if (v == 0) {
-    write_seg_hdr(S, 0, segb, GPX_F_DECISION, A.vtotal, A.vtotal, 0, 32, S.seg_seq[0]);
+    const unsigned long long sq = seg_seq_of(S, 0);
+    write_seg_hdr(S, 0, segb, GPX_F_DECISION, A.vtotal, A.vtotal, 0, 32, sq);
+    log_publish(S, 0, segb + reserved, sq + 1ull);
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
   if (blockIdx.x == 0 && threadIdx.x < A.N && A.sendA[threadIdx.x].cap) { /* next round's k_sp_route counts from zero */
@@ -502,13 +497,4 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_sp_commit(const _
     }
   }
   flush_counters(S, s_ctr);
-  __shared__ unsigned int s_last;
-  __threadfence();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&S.tickets[3], 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    S.ring_head[0] = segb + reserved;
-    S.seg_seq[0] += 1ull;
-    S.tickets[3] = 0;
-  }
 }

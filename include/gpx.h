@@ -509,6 +509,10 @@ typedef struct gpx_dev_round_bufs {
   gpx_exec_rec* exec;          /* [n * n_lanes] device */
 } gpx_dev_round_bufs;
 int gpx_round_device(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream);        /* fused */
+/* Form of the fused round.  0 / 1 (default): k_round_slow -- the general code for runs that are not the plain in-order
+ * case -- is launched from the device, as a tail launch, by the first team that leaves a run over: a round without
+ * such runs is ONE kernel on the stream.  2: the host launches k_round_slow behind every k_round (tuning / fallback). */
+int gpx_set_round_mode(gpx_engine* e, int mode);
 int gpx_round_device_phases(gpx_engine* e, const gpx_dev_round_bufs* b, void* stream); /* phase by phase */
 /* gpx_propose + gpx_handle_accepts_fused on device buffers: ACCEPTs compacted at the front (exec[k * n_lanes + lane]
  * belongs to the k-th ACCEPT of the batch; the count is gpx_counters.proposals' increment), no per-request holes in
