@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-GPX_ABI_VERSION = 1
+GPX_ABI_VERSION = 2
 GPX_MAX_GROUP_SIZE = 16
 GPX_MAX_LANES = 8
 GPX_MAX_WINDOW = 8
@@ -65,7 +65,7 @@ row_dtype = np.dtype([("gid", "<u4"), ("lane", "<u4"), ("version", "<i4"), ("acc
                       ("acc_bcoord", "<i4"), ("acc_gc_slot", "<i4"), ("state", "<i4"), ("coord_exists", "<i4"),
                       ("coord_active", "<i4"), ("coord_bnum", "<i4"), ("coord_bcoord", "<i4"),
                       ("next_proposal_slot", "<i4"), ("n_members", "<i4"), ("members", "<i4", (16,)),
-                      ("node_slots", "<i4", (16,))])
+                      ("node_slots", "<i4", (16,)), ("name_hash", "<i4")])
 group_desc_dtype = np.dtype([("gid", "<u4"), ("version", "<i4"), ("name_hash", "<i4"), ("n_members", "<i4"),
                              ("members", "<i4", (16,)), ("init_mode", "<i4")])
 patch_dtype = np.dtype([("gid", "<u4"), ("lane", "<u4"), ("op", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"),
@@ -73,7 +73,7 @@ patch_dtype = np.dtype([("gid", "<u4"), ("lane", "<u4"), ("op", "<i4"), ("a", "<
 
 assert request_dtype.itemsize == 32 and decision_dtype.itemsize == 32 and accept_dtype.itemsize == 48
 assert reply_dtype.itemsize == 32 and exec_dtype.itemsize == 24 and seg_hdr_dtype.itemsize == 64
-assert row_dtype.itemsize == 56 + 128 and group_desc_dtype.itemsize == 84 and patch_dtype.itemsize == 32
+assert row_dtype.itemsize == 56 + 128 + 4 and group_desc_dtype.itemsize == 84 and patch_dtype.itemsize == 32
 
 COUNTER_NAMES = ["accepts_handled", "accepts_acked", "accepts_nacked", "accepts_logged", "accepts_dropped",
                  "replies_handled", "replies_ignored", "preempted", "coordinators_resigned", "decisions_made",
@@ -90,8 +90,7 @@ class Config(C.Structure):
         ("batching_enabled", C.c_int32), ("max_batch_size", C.c_int32), ("max_batch_bytes", C.c_int64),
         ("request_size_estimate", C.c_int32), ("checkpoint_interval", C.c_int32), ("cpi_noise", C.c_double),
         ("gc_majority_executed", C.c_int32), ("log_meta_decisions", C.c_int32), ("journaling_enabled", C.c_int32),
-        ("batched_accept_replies", C.c_int32), ("batched_commits", C.c_int32), ("short_circuit_local", C.c_int32),
-        ("min_pp_batch_size", C.c_int32), ("digest_requests", C.c_int32), ("log_backpressure", C.c_int32),
+        ("log_backpressure", C.c_int32),
         ("reserved", C.c_int32 * 7),
     ]
 

@@ -164,11 +164,6 @@ void gpx_config_defaults(gpx_config* c) {
   c->gc_majority_executed = 1;     /* :882 */
   c->log_meta_decisions = 1;       /* :588 */
   c->journaling_enabled = 1;       /* :240 */
-  c->batched_accept_replies = 1;   /* :458 */
-  c->batched_commits = 1;          /* :466 */
-  c->short_circuit_local = 1;      /* :834 */
-  c->min_pp_batch_size = 3;        /* :860 */
-  c->digest_requests = 0;          /* :788 */
 }
 
 /* ---- Java helpers (String.hashCode, Math.abs, PISM.roundRobinCoordinator, getCPI) ---- */
@@ -420,6 +415,8 @@ int gpx_destroy_groups(gpx_engine* e, uint32_t n, const uint32_t* gids) {
   if (n == 0) return GPX_OK;
   int rc = e->ensure_misc(n * 4ull);
   if (rc) return rc;
+  for (uint32_t k = 0; k < n; k++)
+    if (gids[k] < e->cfg.max_groups) e->h_name_hash[gids[k]] = e->h_version[gids[k]] = 0;
   CK(cudaMemcpyAsync(e->d_misc, gids, n * 4ull, cudaMemcpyHostToDevice, e->stream));
   k_destroy_groups<<<cdiv(n, 256), 256, 0, e->stream>>>(e->S, (const uint32_t*)e->d_misc, n);
   CK(cudaGetLastError());
@@ -441,7 +438,10 @@ int gpx_dump_rows(gpx_engine* e, uint32_t n, const uint32_t* gids, uint32_t lane
   CK(cudaMemcpyAsync(out, e->d_misc, n * sizeof(gpx_row), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   for (uint32_t k = 0; k < n; k++)
-    if (gids[k] < e->cfg.max_groups) out[k].version = e->h_version[gids[k]];
+    if (gids[k] < e->cfg.max_groups) {
+      out[k].version = e->h_version[gids[k]];
+      out[k].name_hash = e->h_name_hash[gids[k]];
+    }
   return GPX_OK;
 }
 
@@ -460,8 +460,9 @@ int gpx_load_rows(gpx_engine* e, uint32_t n, const gpx_row* rows) {
     if (rc) return rc;
     recs[k].row = r;
     recs[k].mset = id;
-    recs[k].cpi = gpx_get_cpi(e->cfg.checkpoint_interval, e->cfg.cpi_noise, e->h_name_hash[r.gid]);
+    recs[k].cpi = gpx_get_cpi(e->cfg.checkpoint_interval, e->cfg.cpi_noise, r.name_hash); /* getCPI(paxosID) */
     e->h_version[r.gid] = r.version;
+    e->h_name_hash[r.gid] = r.name_hash;
   }
   if (added) {
     int rc = push_msets(e);

@@ -92,11 +92,6 @@ int gpx_config_from_properties(const char* path, gpx_config* cfg) {
   if (has("DISABLE_LOGGING") && as_bool(p["DISABLE_LOGGING"]) && has("ENABLE_JOURNALING") &&
       !as_bool(p["ENABLE_JOURNALING"]))
     cfg->journaling_enabled = 0; /* GET_ACCEPTED_PVALUES_FROM_DISK = logging || journaling */
-  if (has("BATCHED_ACCEPT_REPLIES")) cfg->batched_accept_replies = as_bool(p["BATCHED_ACCEPT_REPLIES"]);
-  if (has("BATCHED_COMMITS")) cfg->batched_commits = as_bool(p["BATCHED_COMMITS"]);
-  if (has("SHORT_CIRCUIT_LOCAL")) cfg->short_circuit_local = as_bool(p["SHORT_CIRCUIT_LOCAL"]);
-  if (has("MIN_PP_BATCH_SIZE")) cfg->min_pp_batch_size = atoi(p["MIN_PP_BATCH_SIZE"].c_str());
-  if (has("DIGEST_REQUESTS")) cfg->digest_requests = as_bool(p["DIGEST_REQUESTS"]);
   if (has("PINSTANCES_CAPACITY")) cfg->max_groups = (uint32_t)strtoul(p["PINSTANCES_CAPACITY"].c_str(), nullptr, 10);
   if (has("MAX_GROUP_SIZE")) {
     int v = atoi(p["MAX_GROUP_SIZE"].c_str());

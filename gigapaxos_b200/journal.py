@@ -6,16 +6,18 @@ Mirrors SQLPaxosLogger.Journaler (gigapaxos/SQLPaxosLogger.java:685-848): files
 bytes}*` (journal() :1000-1003, appendToLogFile :814-826), a new file once the current one
 exceeds MAX_LOG_FILE_SIZE (rollLogFile :789-812, checked after a batch as in journal() :1041).
 
-ACCEPTs are written with the reference's byte codec (AcceptPacket.toBytes, what
-SQLPaxosLogger.toBytes :1084-1096 journals for ACCEPT packets).  The reference journals
-DECISIONs as JSON strings (JSON codecs are out of scope); this writer therefore
-produces the journal of the reference's DONT_LOG_DECISIONS mode (:977-978) and keeps the
-decision images in a side file `<journal file>.decisions` (raw 32-byte gpx_decision_rec images; logged
-PREPAREs -- the promised ballots, GPX_F_PREPARE -- share the form and the file, the reference journals
-those as JSON as well).
+What a frame holds is what SQLPaxosLogger.toBytes :1084-1096 produces: ACCEPT packets in the reference's byte codec
+(AcceptPacket.toBytes -- BYTEIFICATION), every other packet as the JSON string of PaxosPacket.toString() :1095-1098.
+So DECISIONs are journaled as the JSON of the (meta) decision -- PaxosPacket.toJSONObject :478-494 {"type": 90, "PT": 6,
+"ID", "V"} + PValuePacket.toJSONObjectImpl :184-193 {"B": "bnum:coord", "GC_S"} + ProposalPacket :63-67 {"S"} +
+RequestPacket.toJSONObjectImpl :652-692 {"QID", "ET", "E", "STOP"}; PValuePacket.getMetaDecision :212-218 drops the
+request value and sets GC_S = -1 -- and logged PREPAREs as {"type": 90, "PT": 2, "ID", "V", "B", "PREP_MIN"}
+(PreparePacket.toJSONObjectImpl :78-86).  A Java SQLPaxosLogger reading these files gets exactly the packet types it
+wrote itself; key order inside a JSON object is not significant (org.json).
 """
 from __future__ import annotations
 
+import json
 import os
 import struct
 import time
@@ -42,7 +44,6 @@ class Journaler:
         self.files: List[str] = []
         self._seq = 0
         self.fos = None
-        self.dec = None
         self.cur_size = 0
         self._create()
 
@@ -55,10 +56,8 @@ class Journaler:
         if self.fos:
             self.fos.flush()
             self.fos.close()
-            self.dec.close()
         self.cur = self._name()
         self.fos = open(self.cur, "wb")
-        self.dec = open(self.cur + ".decisions", "wb")
         self.files.append(self.cur)
         self.cur_size = 0
 
@@ -67,12 +66,8 @@ class Journaler:
         self.fos.write(frame)
         self.cur_size += len(frame)
 
-    def append_decisions(self, images: np.ndarray):
-        self.dec.write(images.tobytes())
-
     def end_batch(self):
         self.fos.flush()  # FLUSH=true, SYNC=false (PaxosConfig.java:720,725)
-        self.dec.flush()
         if self.cur_size > self.max:
             self._create()
 
@@ -80,8 +75,46 @@ class Journaler:
         if self.fos:
             self.fos.flush()
             self.fos.close()
-            self.dec.close()
             self.fos = None
+
+
+PT_PREPARE, PT_ACCEPT, PT_DECISION, PT_PAXOS_PACKET = 2, 3, 6, 90  # PaxosPacket.PaxosPacketType :206-287
+
+
+def decision_json(paxos_id: str, version: int, slot: int, bnum: int, bcoord: int, median_cp: int, request_id: int,
+                  entry_replica: int, entry_time: int, stop: bool = False) -> bytes:
+    """PaxosPacket.toString() of a (meta) DECISION: what SQLPaxosLogger.toString :1095-1098 journals"""
+    d = {"type": PT_PAXOS_PACKET, "PT": PT_DECISION, "ID": paxos_id, "V": int(version), "B": f"{int(bnum)}:{int(bcoord)}",
+         "GC_S": int(median_cp), "S": int(slot), "QID": int(request_id), "ET": int(entry_time), "E": int(entry_replica)}
+    if stop:
+        d["STOP"] = True
+    return json.dumps(d, separators=(",", ":")).encode("utf-8")
+
+
+def prepare_json(paxos_id: str, version: int, bnum: int, bcoord: int, first_undecided_slot: int) -> bytes:
+    d = {"type": PT_PAXOS_PACKET, "PT": PT_PREPARE, "ID": paxos_id, "V": int(version), "B": f"{int(bnum)}:{int(bcoord)}",
+         "PREP_MIN": int(first_undecided_slot)}
+    return json.dumps(d, separators=(",", ":")).encode("utf-8")
+
+
+def parse_packet(pkt: bytes) -> dict:
+    """One journaled packet, the way the reference's reader tells them apart (SQLPaxosLogger: a byteified packet starts
+    with the int PAXOS_PACKET type, a stringified one with '{'): {"kind": "ACCEPT" | "DECISION" | "PREPARE", ...}"""
+    if pkt[:1] == b"{":
+        j = json.loads(pkt.decode("utf-8"))
+        assert j["type"] == PT_PAXOS_PACKET
+        bn, bc = (int(x) for x in j["B"].split(":"))
+        if j["PT"] == PT_DECISION:
+            return {"kind": "DECISION", "paxos_id": j["ID"], "version": j["V"], "slot": j["S"], "bnum": bn, "bcoord": bc,
+                    "median_cp": j["GC_S"], "request_id": j["QID"], "stop": bool(j.get("STOP", False)),
+                    "entry_replica": j["E"], "entry_time": j["ET"]}
+        if j["PT"] == PT_PREPARE:
+            return {"kind": "PREPARE", "paxos_id": j["ID"], "version": j["V"], "bnum": bn, "bcoord": bc,
+                    "first_undecided_slot": j["PREP_MIN"]}
+        raise ValueError("unexpected packet type %r" % j["PT"])
+    v = wire.decode_accept(pkt)
+    v["kind"] = "ACCEPT"
+    return v
 
 
 RequestLookup = Callable[[int, int], Tuple[str, int, int, float]]
@@ -114,10 +147,21 @@ class LogDrainer:
                     n += 1
                     self.accepts_written += 1
             else:  # DECISION images and logged PREPAREs (GPX_F_PREPARE: the promised ballot) share the 32-byte form
-                logged = imgs[(imgs["flags"] & abi.F_VOID) == 0]
-                if len(logged):
-                    self.j.append_decisions(logged)
-                    self.decisions_written += len(logged)
+                for dimg in imgs:
+                    fl = int(dimg["flags"])
+                    if fl & abi.F_VOID:
+                        continue
+                    try:
+                        pid, ver, entry, etime = self.lookup(int(dimg["gid"]), int(dimg["req_id"]))
+                    except KeyError:  # a PREPARE carries no request: only (paxosID, version) are needed
+                        pid, ver, entry, etime = self.lookup(int(dimg["gid"]), -1)
+                    if fl & abi.F_PREPARE:  # the image's slot field carries firstUndecidedSlot
+                        self.j.append(prepare_json(pid, ver, int(dimg["bnum"]), int(dimg["bcoord"]), int(dimg["slot"])))
+                    else:
+                        self.j.append(decision_json(pid, ver, int(dimg["slot"]), int(dimg["bnum"]), int(dimg["bcoord"]),
+                                                    int(dimg["median_cp"]), int(dimg["req_id"]), entry, int(etime),
+                                                    stop=bool(fl & abi.F_STOP)))
+                    self.decisions_written += 1
         self.j.end_batch()
         self.offset = head
         return n
@@ -165,8 +209,21 @@ def replay_accepts(files: List[str]) -> Dict[str, Dict[int, dict]]:
     out: Dict[str, Dict[int, dict]] = {}
     for path in files:
         for pkt in read_journal(path):
-            v = wire.decode_accept(pkt)
+            v = parse_packet(pkt)
+            if v["kind"] != "ACCEPT":
+                continue
             cur = out.setdefault(v["paxos_id"], {}).get(v["slot"])
             if cur is None or (v["bnum"], v["bcoord"]) >= (cur["bnum"], cur["bcoord"]):
                 out[v["paxos_id"]][v["slot"]] = v
+    return out
+
+
+def replay_decisions(files: List[str]) -> Dict[str, Dict[int, dict]]:
+    """the DECISION half: per paxosID, slot -> the journaled (meta) decision"""
+    out: Dict[str, Dict[int, dict]] = {}
+    for path in files:
+        for pkt in read_journal(path):
+            v = parse_packet(pkt)
+            if v["kind"] == "DECISION":
+                out.setdefault(v["paxos_id"], {})[v["slot"]] = v
     return out

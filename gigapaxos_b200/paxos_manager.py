@@ -141,6 +141,7 @@ class HotRestoreInfo:
         r = np.zeros(1, dtype=abi.row_dtype)
         n = len(self.members)
         r["gid"], r["lane"], r["version"] = gid, lane, self.version
+        r["name_hash"] = abi.java_string_hash(self.paxosID)  # getCPI :2694-2697 is a function of the paxosID
         r["acc_slot"], r["acc_bnum"], r["acc_bcoord"], r["acc_gc_slot"] = (self.accSlot, self.accBallot[0],
                                                                             self.accBallot[1], self.accGCSlot)
         r["state"] = abi.ST_ACTIVE_1  # paxosState.setActive(): no recovery
@@ -217,6 +218,8 @@ class PaxosManager:
         created = True
         k = 0
         for name, state in nameStates.items():
+            if name in self.paused:  # createPaxosInstance goes through getInstance :2453, which unpauses first: a paused
+                self.unpause(name)   # instance exists -- creating it again must not wipe its state
             old = self.instances.get(name)
             if old is not None:
                 if old.version >= version or not old.stopped:
@@ -245,8 +248,9 @@ class PaxosManager:
 
     def kill(self, paxosID: str) -> bool:
         """PaxosManager.kill :2162."""
+        was_paused = self.paused.pop(paxosID, None) is not None  # a killed instance leaves no pause-table entry behind
         if paxosID not in self.instances:
-            return False
+            return was_paused
         self._release(paxosID)
         return True
 
@@ -275,14 +279,39 @@ class PaxosManager:
         prep["gid"], prep["slot"] = inst.gid, int(cur["acc_slot"])  # PreparePacket(newBallot, paxosState.getSlot())
         prep["bnum"], prep["bcoord"] = new_ballot
         prep["flags"], prep["dst_mask"] = abi.F_PREPARE, (1 << L) - 1
+        # A preparer that is BEHIND some acceptor must hear about the accepts of [my slot, acceptor's slot) as well.
+        # With journaling they have left the acceptor's memory (executed accepts are served from the journal:
+        # PISM.handlePrepare -> getLoggedAccepts, GET_ACCEPTED_PVALUES_FROM_DISK); the acceptor flags its reply
+        # GPX_F_FROM_LOG and the host adds them from the acceptor's log.  When the ring no longer holds them the lane
+        # catches up first (PISM.syncLongDecisionGaps) -- electing it with a stale first slot would let it re-decide a
+        # decided slot with a new value.
+        rows_before = [eng.dump_rows(gids, l)[0] for l in range(L)]
+        logged = {}
+        if any(_jsub(int(r["acc_slot"]), int(cur["acc_slot"])) > 0 for l, r in enumerate(rows_before) if l != lane):
+            logged = self._logged_accepts(inst.gid, int(cur["acc_slot"]), [l for l in range(L) if l != lane])
+            if logged is None:
+                self.syncDecisions(paxosID, lane)
+                cur = eng.dump_rows(gids, lane)[0]
+                if any(_jsub(int(eng.dump_rows(gids, l)[0]["acc_slot"]), int(cur["acc_slot"])) > 0
+                       for l in range(L) if l != lane):
+                    return False  # still behind: no election from here
+                logged = {}
+                new_ballot = (int(cur["acc_bnum"]) + 1, me)
+                prep["slot"], prep["bnum"] = int(cur["acc_slot"]), new_ballot[0]
         replies = eng.handle_prepares(prep)
-        verdict, node_slots, carry = self.tally_prepare_replies(replies, R, new_ballot)
+        # (reply index == lane: gpx_handle_prepares answers at index i * n_lanes + lane and there is one PREPARE)
+        verdict, node_slots, carry = self.tally_prepare_replies(replies, R, new_ballot, logged)
         if verdict != "majority":
             return False
         plan, next_slot = self.combine_carryover(carry, node_slots, int(cur["acc_slot"]))
-        # the old coordinator(s) of this group resign, the new one starts ACTIVE at the first slot it has to fill
+        # coordinators of a LOWER ballot resign (PISM.handlePrepare -> nullifyCoordinatorIfPreempted); the new one starts
+        # ACTIVE at the first slot it has to fill
         pts = []
         for l in range(L):
+            r = eng.dump_rows(gids, l)[0]
+            if l != lane and bool(r["coord_exists"]) and (
+                    _jsub(int(r["coord_bnum"]), new_ballot[0]) or _jsub(int(r["coord_bcoord"]), new_ballot[1])) > 0:
+                continue  # a coordinator with a higher ballot is not ours to remove
             pts.append((inst.gid, l, abi.PATCH_RESIGN_COORD, 0, 0, 0, 0))
         pts.append((inst.gid, lane, abi.PATCH_INSTALL_COORD, new_ballot[0], new_ballot[1], next_slot, 1))
         for i, v in enumerate(node_slots):
@@ -297,13 +326,49 @@ class PaxosManager:
                 reqs = [RequestPacket(paxosID, 0, NO_OP, entry_replica=me)]
             else:
                 reqs = self._requests_of(paxosID, pv, src, me)
-            self._submit(reqs)
+            self._submit(reqs, carryover=True)
         return True
 
+    def _logged_accepts(self, gid: int, first_slot: int, lanes: Sequence[int]):
+        """AbstractPaxosLogger.getLoggedAccepts for the PREPARE path (PISM.handlePrepare :896-955 with
+        GET_ACCEPTED_PVALUES_FROM_DISK): per lane of `lanes`, the logged ACCEPTs of `gid` with slot >= first_slot found
+        in its log ring (the highest ballot per slot), as {lane: [accepted pvalue records in slot order]} -- what that
+        acceptor's PREPARE_REPLY would carry had the accepts still been in memory.  None when a ring has wrapped past
+        what would be needed (the caller then syncs instead)."""
+        out = {}
+        ring = int(self.engine.cfg.log_ring_bytes)
+        for l in lanes:
+            head = self.engine.log_head(l)
+            if head > ring:
+                return None
+            best = {}
+            buf = self.engine.log_read(l, 0, head)
+            for hdr, imgs, payload, pay_off in abi.parse_log(buf):
+                if int(hdr["rec_bytes"]) != 48:
+                    continue
+                sel = imgs[(imgs["gid"] == gid) & ((imgs["flags"] & abi.F_VOID) == 0)]
+                for a in sel:
+                    sl = int(a["slot"])
+                    if _jsub(sl, first_slot) < 0:
+                        continue
+                    pv = np.zeros(1, dtype=abi.accepted_pvalue_dtype)[0]
+                    pv["slot"], pv["bnum"], pv["bcoord"] = sl, int(a["bnum"]), int(a["bcoord"])
+                    pv["frame_ref"] = (pay_off + int(a["payload_off"])) // 16
+                    pv["req_id"], pv["payload_len"] = int(a["req_id"]), int(a["payload_len"])
+                    pv["flags"] = (2 if int(a["flags"]) & abi.F_STOP else 0) | (int(a["nreq"]) << 16)
+                    ex = best.get(sl)
+                    if ex is None or (_jsub(int(pv["bnum"]), int(ex["bnum"])) or
+                                      _jsub(int(pv["bcoord"]), int(ex["bcoord"]))) > 0:
+                        best[sl] = pv
+            out[l] = [best[k] for k in sorted(best)]
+        return out
+
     @staticmethod
-    def tally_prepare_replies(replies, R: int, new_ballot: tuple):
+    def tally_prepare_replies(replies, R: int, new_ballot: tuple, logged=None):
         """PISM.handlePrepareReply :957-990 over a sequence of gpx_prepare_reply records, in order: returns
-        ("preempted" | "majority" | "waiting", nodeSlotNumbers, carryover {slot: (pvalue, reply index)})."""
+        ("preempted" | "majority" | "waiting", nodeSlotNumbers, carryover {slot: (pvalue, reply index)}).
+        logged[l]: accepted pvalues the acceptor behind reply l serves from its journal (GPX_F_FROM_LOG: with
+        journaling the executed accepts have left its memory) -- part of its reply as far as the tally goes."""
         node_slots = [-1] * R  # PCS ctor :169-171
         heard, carry = set(), {}
         for l, rep in enumerate(replies):
@@ -317,7 +382,10 @@ class PaxosManager:
             idx = abi.who_acc(int(rep["who"]))
             if c < 0 or idx in heard or idx >= R:  # canIgnorePrepareReply :287-316
                 continue
-            acc = rep["accepted"][: int(rep["n_accepted"])]
+            acc = list(rep["accepted"][: int(rep["n_accepted"])])
+            if logged and logged.get(l):
+                have = {int(pv["slot"]) for pv in acc}
+                acc = sorted(acc + [pv for pv in logged[l] if int(pv["slot"]) not in have], key=lambda pv: int(pv["slot"]))
             # recordSlotNumber :786-807 with PrepareReplyPacket.getMinSlot: the lowest accepted slot, else gcSlot + 1
             min_slot = int(rep["first_slot"]) + 1
             for k, pv in enumerate(acc):
@@ -375,7 +443,15 @@ class PaxosManager:
                     out[s2] = (p1, src1)
                 elif c < 0:
                     out[s1] = (None, -1)
-        return [(sl,) + out[sl] for sl, _, _ in plan]
+        res = [(sl,) + out[sl] for sl, _, _ in plan]
+        # :548-552: a STOP was among the carried-over pvalues but the last proposal is not one (it lost to a higher
+        # ballot above): the epoch must still end -- the STOP is proposed afresh behind everything else
+        stops = [(pv, src) for _, pv, src in plan if is_stop(pv)]
+        if stops and res and not is_stop(res[-1][1]):
+            last = res[-1][0]
+            nxt = (last + 1) & 0xFFFFFFFF
+            res.append((nxt - (1 << 32) if nxt & 0x80000000 else nxt,) + stops[-1])
+        return res
 
     def _requests_of(self, paxosID: str, pv, src_lane: int, entry: int) -> List[RequestPacket]:
         """the request(s) of an accepted pvalue, read back from the log ring of the acceptor lane that reported it"""
@@ -560,8 +636,10 @@ class PaxosManager:
         self.queue = {}
         return self._submit(reqs_l)
 
-    def _submit(self, reqs_l: List[RequestPacket]) -> int:
-        """one engine round over a list of requests already grouped by paxos instance"""
+    def _submit(self, reqs_l: List[RequestPacket], carryover: bool = False) -> int:
+        """one engine round over a list of requests already grouped by paxos instance.  carryover: the re-proposal of a
+        carried-over pvalue by a new coordinator -- it must take exactly its slot, so a refusal is an error (requeueing
+        it would shift every later carried-over slot)"""
         if not reqs_l:
             return 0
         n = len(reqs_l)
@@ -581,6 +659,8 @@ class PaxosManager:
             reqs[i]["entry_node"] = r.entry_replica
             payload[offs[i]: offs[i] + len(r.request_value)] = np.frombuffer(r.request_value, dtype=np.uint8)
         status, ex, extra = self.engine.round(reqs, payload)
+        if carryover and any(int(st) <= 0 and int(st) != abi.RS_BATCHED for st in status):
+            raise RuntimeError(f"carried-over pvalue could not be re-proposed: status {[int(x) for x in status]}")
         # requests the engine could not propose go back to the host slow path (retry / forward / prepare)
         elect: Dict[str, int] = {}
         for i, st in enumerate(status):

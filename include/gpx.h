@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define GPX_ABI_VERSION 1
+#define GPX_ABI_VERSION 2
 
 #define GPX_MAX_GROUP_SIZE 16 /* PC.MAX_GROUP_SIZE, PaxosConfig.java:532 */
 #define GPX_MAX_LANES 8       /* co-located replicas (lanes) per engine */
@@ -221,6 +221,8 @@ typedef struct gpx_row {
   int32_t n_members;
   int32_t members[GPX_MAX_GROUP_SIZE];    /* sorted ascending node ids */
   int32_t node_slots[GPX_MAX_GROUP_SIZE]; /* PaxosCoordinatorState.nodeSlotNumbers */
+  int32_t name_hash;      /* String.hashCode() of the paxosID (HotRestoreInfo.paxosID): getCPI :2694-2697 is a function of
+                           * the paxosID, and a restored instance may get a different gid than it was created under */
 } gpx_row;
 
 #define GPX_INIT_BATCH 0   /* HotRestoreInfo.createHRI path (PaxosManager.java:664-691) */
@@ -277,11 +279,10 @@ typedef struct gpx_config {
   int32_t gc_majority_executed;    /* GC_MAJORITY_EXECUTED :882 (true) */
   int32_t log_meta_decisions;      /* LOG_META_DECISIONS :588 (true) */
   int32_t journaling_enabled;      /* ENABLE_JOURNALING :240 (true): executed accepts leave memory */
-  int32_t batched_accept_replies;  /* BATCHED_ACCEPT_REPLIES :458 */
-  int32_t batched_commits;         /* BATCHED_COMMITS :466 */
-  int32_t short_circuit_local;     /* SHORT_CIRCUIT_LOCAL :834 */
-  int32_t min_pp_batch_size;       /* MIN_PP_BATCH_SIZE :860 */
-  int32_t digest_requests;         /* DIGEST_REQUESTS :788 (false) */
+  /* (BATCHED_ACCEPT_REPLIES :458, BATCHED_COMMITS :466, MIN_PP_BATCH_SIZE :860 shape how PaxosPacketBatcher packs
+   * records into wire packets -- the engine exchanges fixed-size records, packing happens where packets are formed
+   * (gpx_wire_*); SHORT_CIRCUIT_LOCAL :834 and DIGEST_REQUESTS :788 are host-side choices (DESIGN.md 2.3,
+   * gpx_digest_requests): none of them is engine configuration, so none is carried here) */
   int32_t log_backpressure;        /* 1: a call that could overwrite log bytes not yet released by gpx_log_release is
                                     * refused with GPX_EAGAIN (log-then-message, AbstractPaxosLogger.java:691-716: the
                                     * journal must be drained before a ring position is reused); 0 (default): the ring

@@ -696,11 +696,6 @@ void gpxo_config_defaults(gpx_config* c) {
   c->gc_majority_executed = 1;
   c->log_meta_decisions = 1;
   c->journaling_enabled = 1;
-  c->batched_accept_replies = 1;
-  c->batched_commits = 1;
-  c->short_circuit_local = 1;
-  c->min_pp_batch_size = 3;
-  c->digest_requests = 0;
 }
 
 int gpxo_engine_create(const gpx_config* cfg, gpxo_engine** out) {
@@ -799,6 +794,7 @@ int gpxo_dump_rows(gpxo_engine* e, uint32_t n, const uint32_t* gids, uint32_t la
     r.gid = gid;
     r.lane = lane;
     r.version = g.version;
+    r.name_hash = g.name_hash;
     r.acc_slot = A._slot;
     r.acc_bnum = A.ballotNum;
     r.acc_bcoord = A.ballotCoord;
@@ -826,6 +822,8 @@ int gpxo_load_rows(gpxo_engine* e, uint32_t n, const gpx_row* rows) {
     Group& g = e->groups[r.gid];
     g.live = true;
     g.version = r.version;
+    g.name_hash = r.name_hash; /* HotRestoreInfo carries the paxosID: getCPI :2694-2697 follows the name, not the gid */
+    g.cpi = getCPI(e->cfg.checkpoint_interval, e->cfg.cpi_noise, g.name_hash);
     g.members.assign(r.members, r.members + r.n_members);
     std::sort(g.members.begin(), g.members.end());
     Acceptor& A = e->lanes[r.lane].acc[r.gid];

@@ -1,5 +1,6 @@
 """Journal persistence: the log ring drained into Journaler-compatible files
-({int32 BE len}{AcceptPacket bytes}*, SQLPaxosLogger.java:1000-1003) and read back."""
+({int32 BE len}{packet}*, SQLPaxosLogger.java:1000-1003: ACCEPTs byteified, DECISIONs as the JSON string of the meta
+decision, :1084-1098) and read back the way SQLPaxosLogger's reader walks a file (:685-848)."""
 import os
 
 import numpy as np
@@ -49,12 +50,23 @@ def check(pm, drainers, sent):
         assert os.path.basename(os.path.dirname(d.j.files[0])) == f"paxos_journal.{NODES[l]}"
         seen = {}
         slots = {}
+        dslots = {}
         for f in d.j.files:
+            assert not os.path.exists(f + ".decisions")  # one journal, no side file
             for pkt in journal.read_journal(f):
-                assert pkt[3] == 90 and pkt[7] == 3  # PAXOS_PACKET / ACCEPT (SQLPaxosLogger.toBytes :1090)
-                v = wire.decode_accept(pkt)
-                slots.setdefault(v["paxos_id"], []).append(v["slot"])
-                seen[v["request_id"]] = (v["paxos_id"], v["value"])
+                v = journal.parse_packet(pkt)
+                if v["kind"] == "ACCEPT":
+                    assert pkt[3] == 90 and pkt[7] == 3  # PAXOS_PACKET / ACCEPT (SQLPaxosLogger.toBytes :1090)
+                    slots.setdefault(v["paxos_id"], []).append(v["slot"])
+                    seen[v["request_id"]] = (v["paxos_id"], v["value"])
+                else:
+                    assert v["kind"] == "DECISION" and pkt[:1] == b"{"  # the JSON string of the meta decision
+                    assert v["median_cp"] == -1  # PValuePacket.getMetaDecision :212-218
+                    dslots.setdefault(v["paxos_id"], []).append((v["slot"], v["request_id"]))
+        for name, ss in dslots.items():  # every slot's decision is journaled once, in slot order, for the logged request
+            assert [x[0] for x in ss] == list(range(1, len(ss) + 1))
+            assert all(seen[rid][0] == name for _, rid in ss)
+        assert journal.replay_decisions(d.j.files).keys() == dslots.keys()
         # every first request of every decided slot is in every replica's journal, byte-exact
         for rid, (name, val) in seen.items():
             assert sent[rid] == (name, val)
@@ -81,6 +93,9 @@ def test_journal_roundtrip_gpu(cuda_lib, oracle_lib, tmp_path):
         pb = [p for f in b.j.files for p in journal.read_journal(f)]
         assert len(pa) == len(pb)
         for x, y in zip(pa, pb):
-            vx, vy = wire.decode_accept(x), wire.decode_accept(y)
-            for k in ("paxos_id", "request_id", "slot", "bnum", "bcoord", "median_cp", "sender", "value", "n_batched"):
+            vx, vy = journal.parse_packet(x), journal.parse_packet(y)
+            assert vx["kind"] == vy["kind"]
+            keys = (("paxos_id", "request_id", "slot", "bnum", "bcoord", "median_cp", "sender", "value", "n_batched")
+                    if vx["kind"] == "ACCEPT" else ("paxos_id", "request_id", "slot", "bnum", "bcoord", "median_cp", "stop"))
+            for k in keys:
                 assert vx[k] == vy[k]

@@ -407,3 +407,82 @@ def test_auto_election_cpu(oracle_lib):
 def test_auto_election_gpu(cuda_lib, oracle_lib):
     g, o = drive_auto_election(cuda_lib), drive_auto_election(oracle_lib)
     assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
+
+
+# ---- a LAGGING replica runs for coordinator: with journaling the executed accepts have left the
+#      acceptors' memory; the preparer must still learn them (PISM.handlePrepare -> getLoggedAccepts,
+#      GET_ACCEPTED_PVALUES_FROM_DISK) or it would re-decide a decided slot with a new value ------------------------------
+def drive_lagging_election(lib):
+    from gigapaxos_b200.paxos_manager import RequestPacket
+    from helpers import make_requests
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=100)
+    eng = pm.engine
+    names = [f"TESTPaxosApp{i}" for i in range(5)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    for n in names:
+        pm.propose(n, f"{n}:first".encode())
+    pm.run_round()
+    gids = np.array([pm.instances[n].gid for n in names], dtype=np.uint32)
+    rows0 = eng.dump_rows(gids, 0)
+    coord = [NODES.index(int(rows0[i]["acc_bcoord"])) for i in range(len(names))]
+    # lane 0 is partitioned away for three slots: lanes 1 and 2 decide and execute them (only groups they coordinate)
+    lagging = [i for i in range(len(names)) if coord[i] != 0]
+    assert lagging
+    g2 = gids[lagging]
+    for k in range(3):
+        reqs, pay = make_requests(g2, payload_len=6, seed=4, round_no=k)
+        reqs["flags"] = [coord[i] << 8 for i in lagging]
+        reqs["entry_node"] = [NODES[coord[i]] for i in lagging]
+        acc, blob, st = eng.propose(reqs, pay)
+        assert np.all(st > 0)
+        acc["dst_mask"] = 0b110
+        rep, _ = eng.handle_accepts(acc, blob)
+        dec = eng.handle_accept_replies(rep)
+        dec["dst_mask"] = 0b110
+        ex, extra = eng.handle_decisions(dec)
+        batches = {int(r["req_id"]): [RequestPacket(names[lagging[j]], int(r["req_id"]),
+                                                    bytes(pay[int(r["payload_off"]): int(r["payload_off"]) + int(r["payload_len"])]),
+                                                    entry_replica=NODES[coord[lagging[j]]])]
+                   for j, r in enumerate(reqs)}
+        pm._apply(np.concatenate([ex, extra]), batches)
+    assert np.all(eng.dump_rows(g2, 0)["acc_slot"] == 2) and np.all(eng.dump_rows(g2, 1)["acc_slot"] == 5)
+    # the lagging lane 0 runs for coordinator of those groups and then proposes a NEW value
+    for i in lagging:
+        assert pm.runForCoordinator(names[i], 0)
+        pm.propose(names[i], b"NEWVALUE", entry_node=NODES[0])
+    pm.run_round()
+    # every replica executed the same sequence: the old slots 2..4 kept their values, NEWVALUE landed behind them
+    assert pm.apps[0].state == pm.apps[1].state == pm.apps[2].state
+    assert pm.apps[0].seqnum == pm.apps[1].seqnum == pm.apps[2].seqnum
+    for l in range(3):
+        assert np.all(eng.dump_rows(g2, l)["acc_slot"] == 6)
+    return pm
+
+
+def test_lagging_lane_election_cpu(oracle_lib):
+    drive_lagging_election(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_lagging_lane_election_gpu(cuda_lib, oracle_lib):
+    a, b = drive_lagging_election(cuda_lib), drive_lagging_election(oracle_lib)
+    assert a.apps[0].state == b.apps[0].state
+
+
+def test_create_and_kill_respect_the_pause_table(oracle_lib):
+    """createPaxosInstance of a PAUSED name must unpause it and answer 'already exists' (it goes
+    through PaxosManager.getInstance :2453), not wipe its state; kill must drop the pause-table entry."""
+    pm = make_pm(oracle_lib, HashChainApp)
+    pm.createPaxosInstance("p0", 0, NODES)
+    pm.propose("p0", b"x")
+    pm.run_round()
+    state = pm.apps[0].state.get("p0") if isinstance(pm.apps[0].state, dict) else pm.apps[0].state
+    assert pm.pause("p0") and pm.isPaused("p0")
+    assert pm.createPaxosInstance("p0", 0, NODES) is False  # exists (paused): not re-created
+    assert not pm.isPaused("p0") and "p0" in pm.instances
+    after = pm.apps[0].state.get("p0") if isinstance(pm.apps[0].state, dict) else pm.apps[0].state
+    assert after == state
+    rows = pm.engine.dump_rows(np.array([pm.instances["p0"].gid], dtype=np.uint32), 0)
+    assert int(rows[0]["acc_slot"]) == 2  # the restored row, not a fresh one
+    assert pm.pause("p0") and pm.kill("p0") and not pm.isPaused("p0")
+    assert pm.propose("p0", b"y") is None  # gone for good
