@@ -435,6 +435,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     lib = gigapaxos_b200.load_library()
     if args.placement == "spread":
+        if args.workload == "cfg3" and world > 1 and not args.groups:
+            G = wl["G"] // world  # BASELINE config 3 as written: 1 M groups sharded across the GPUs of the job
+            config["groups_per_gpu"] = G
+            config["workload"] = "3-replica, 1M groups, 64-byte requests, groups sharded across %d GPUs" % world
         (run_spread if args.spread_python else run_spread_c)(args, lib, dev, rank, world, G, R, P, K, max(W, 3), metric,
                                                               config)
         if world > 1:
@@ -1238,17 +1242,28 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
     barrier()
     c0 = [e.counters() for e in engines]
     sampler.start()
+    # One round of a node touches every state row, window entry, bucket and log image of the (R x G) group replicas it
+    # hosts: well over the 126 MB of L2 at the benchmark sizes (the line's config.working_set_mb says how much), so
+    # consecutive rounds find nothing of their own in the cache ("inputs larger than L2"): the K steps are timed back to
+    # back, one event per step boundary.  When the working set is smaller the L2 is flushed between steps instead.
+    n_in0 = int(member_of[:, local[0]].sum())
+    ws_mb = (n_in0 * (16 + 4 + 32 + 48 + 32 + 32 + 24 + 80 + 2 * blob_per_rec) + G * (32 + 48 + 16 + 16 + 12 + 32)) / 1e6
+    use_flush = (not args.no_flush) and ws_mb < 160.0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    if not use_flush:
+        ev[0].record()
     for k in range(K):
-        if not args.no_flush:
+        if use_flush:
             flush_buf.zero_()
-        ev_s[k].record()
+            if world > 1:  # the ranks are coupled by the exchanges: start the step together, or one rank's flush would be
+                barrier()  # timed inside its peers' rounds
+            ev_s[k].record()
         sp.round(ios[k % NB], st)
-        ev_e[k].record()
+        ev[k + 1].record()
     barrier()
     clocks = sampler.stop()
-    step_ms = np.array([ev_s[k].elapsed_time(ev_e[k]) for k in range(K)])
+    step_ms = np.array([(ev_s[k] if use_flush else ev[k]).elapsed_time(ev[k + 1]) for k in range(K)])
     total_ms = allmax(float(step_ms.sum()))
     c1 = [e.counters() for e in engines]
     for k, (a, b) in enumerate(zip(c0, c1)):
@@ -1257,17 +1272,7 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
         assert b["executed"] - a["executed"] == n_in * K, "every replica executes every decision"
         assert sp.dropped(k) == 0
     value = N * G * K / (total_ms / 1e3)
-
-    # back-to-back rounds without the L2 flush in between (how a loaded node runs: the next round's kernels start
-    # while nothing else touches the GPU); reported beside the flushed number
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(K):
-        sp.round(ios[k % NB], st)
-    e1.record()
-    barrier()
-    b2b_ms = allmax(e0.elapsed_time(e1)) / K
+    b2b_ms = total_ms / K
 
     # per-kernel share of a round: CUDA events between the phases cannot be placed inside the C call (and inside a
     # graph), so a non-graph handle is timed phase by phase through the per-phase wall of the ncu launch list under
@@ -1315,7 +1320,9 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
         peak, peak_src = hbm_peak()
         cfg = dict(config)
         link_bytes = int(sum(sp.plans[0].send_bytes[k][d] for k in range(3) for d in range(N) if d != local[0]))
-        cfg.update({"groups_per_gpu": G, "accepts_in_per_node_per_step": n_in,
+        cfg.update({"groups_per_gpu": G, "accepts_in_per_node_per_step": n_in, "working_set_mb_per_gpu_per_step": round(ws_mb, 1),
+                    "l2": (flush_buf.describe() if use_flush else
+                           "not flushed: one step's working set (%.0f MB per GPU) exceeds the 126 MB L2, steps run back to back" % ws_mb),
                     "placement": f"spread: {N} nodes, one single-lane engine per "
                     + ("GPU; libgpx issues grouped ncclSend/ncclRecv of fixed-capacity buckets over NVLink"
                        if world > 1 else "node, all on ONE GPU (device copies)")
@@ -1336,7 +1343,6 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
                          "bytes_per_decided_slot": b_slot(R, P), "kernel_ms": ms,
                          "frac": bytes_round / (ms / 1e3) / 1e9 / peak,
                          "nvlink": {"bytes_sent_per_gpu": link_bytes, "min_ms_at_770GBs": link_bytes / 770e9 * 1e3}},
-            "back_to_back_ms_per_step": b2b_ms, "back_to_back_decisions_per_sec": N * G / (b2b_ms / 1e3),
             "cpu_baseline": None, "e2e": e2e, "clocks": clocks,
             "gpu_launches": K * 6 * len(local), "p50_decide_latency_ms": float(np.median(step_ms)),
         }

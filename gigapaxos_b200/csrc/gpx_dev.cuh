@@ -211,6 +211,23 @@ __device__ __forceinline__ void st256_stream(void* p, const int4 a, const int4 b
                : "memory");
 }
 
+/* up to 16 bytes from an arbitrarily aligned address, zero-padded to one 128-bit chunk */
+__device__ __forceinline__ int4 load_chunk16(const uint8_t* src, uint32_t nbytes) {
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (nbytes >= 16u && (((uintptr_t)src) & 3u) == 0) {
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+    w[0] = s4[0];
+    w[1] = s4[1];
+    w[2] = s4[2];
+    w[3] = s4[3];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+      if ((uint32_t)k < nbytes) w[k >> 2] |= (uint32_t)src[k] << (8 * (k & 3));
+  }
+  return make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+}
+
 /* a pvalue in registers */
 struct DPValue {
   int slot, bnum, bcoord, median_cp;
@@ -259,6 +276,30 @@ __device__ __forceinline__ int median_minus(const DevState& S, uint32_t lane, ui
     v[m + 1] = x;
   }
   return v[(R % 2 == 0) ? R / 2 - 1 : R / 2];
+}
+
+/* PCS.getMedianMinus :867-875 on a register array (R <= LP <= 8) */
+template <int LP>
+__device__ __forceinline__ int median_regs(const int (&ns)[LP], uint32_t R) {
+  if (R == 1) return ns[0];
+  if (LP >= 3 && R == 3) return max(min(ns[0], ns[1]), min(max(ns[0], ns[1]), ns[2]));
+  int v[LP];
+#pragma unroll
+  for (int k = 0; k < LP; k++) v[k] = (uint32_t)k < R ? ns[k] : 2147483647;
+#pragma unroll
+  for (int a = 0; a < LP; a++) /* odd-even transposition sort, fully unrolled: no dynamic indexing */
+#pragma unroll
+    for (int b = (a & 1); b + 1 < LP; b += 2) {
+      int lo = min(v[b], v[b + 1]), hi = max(v[b], v[b + 1]);
+      v[b] = lo;
+      v[b + 1] = hi;
+    }
+  const uint32_t idx = (R % 2 == 0) ? R / 2 - 1 : R / 2;
+  int out = v[0];
+#pragma unroll
+  for (int k = 1; k < LP; k++)
+    if ((uint32_t)k == idx) out = v[k];
+  return out;
 }
 
 /* PaxosAcceptor.garbageCollectAccepted :476-494.  Entries <= gc die implicitly (an

@@ -593,7 +593,10 @@ static int launch_tally(gpx_engine* e, const gpx_accept_reply_rec* d_replies, co
   A.n_max = n_max;
   A.decisions = d_dec;
   A.n_decisions = &e->d_ctl->n_decisions;
-  k_tally<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
+  if (mult > 1 && mult == e->cfg.n_lanes) { /* [ACCEPT][lane] layout of the phase pipeline: one thread per slot */
+    GPX_DISPATCH_L(mult, k_tally_slots, cdiv(n_max / mult, GPX_BLOCK), st, e->S, A);
+  } else
+    k_tally<<<cdiv(n_max, GPX_BLOCK), GPX_BLOCK, 0, st>>>(e->S, A);
   CK(cudaGetLastError());
   return GPX_OK;
 }

@@ -569,6 +569,108 @@ __device__ __forceinline__ bool tally_reply(const DevState& S, uint32_t cl, uint
   return decided;
 }
 
+template <int NR>
+__device__ __forceinline__ bool tally_slot_core(const DevState& S, uint32_t cl, uint32_t gid, uint32_t R,
+                                                const MsetInfo* ms, int4& crow, bool& dirty, int slot,
+                                                const int4 (&r0)[NR], const int4 (&r1)[NR], uint32_t nrep, const int4 pe0,
+                                                const int (&ns0)[8], gpx_decision_rec& d, unsigned int* s_ctr);
+
+/* The replies to ONE ACCEPT (one slot) at the coordinator lane `cl`, with the coordinator row, the slot's proposal
+ * entry and nodeSlotNumbers held in registers: what tally_reply does reply by reply against memory -- same order, same
+ * effects -- with one load and at most one store per touched word (the R replies of a slot arrive together in the
+ * batched exchange, PaxosPacketBatcher.java:270-303 / BatchedAcceptReply).  r0[k] = {gid, slot, bnum, bcoord},
+ * r1[k] = {maxCheckpointedSlot, who, ...}; VOID replies are skipped.  R <= 8. */
+template <int NR>
+__device__ __forceinline__ bool tally_slot_regs(const DevState& S, uint32_t cl, uint32_t gid, uint32_t R,
+                                                const MsetInfo* ms, int4& crow, bool& dirty, int slot,
+                                                const int4 (&r0)[NR], const int4 (&r1)[NR], uint32_t nrep,
+                                                gpx_decision_rec& d, unsigned int* s_ctr) {
+  const uint32_t Wm = S.W - 1;
+  const size_t pi = win_idx(S, cl, (uint32_t)slot & Wm, gid);
+  const int4 pe0 = S.prop_win[pi];
+  int ns0[8];
+#pragma unroll
+  for (int m = 0; m < 8; m++) ns0[m] = (uint32_t)m < R ? S.node_slots[ns_idx(S, cl, (uint32_t)m, gid)] : 2147483647;
+  return tally_slot_core<NR>(S, cl, gid, R, ms, crow, dirty, slot, r0, r1, nrep, pe0, ns0, d, s_ctr);
+}
+
+/* the same with the proposal entry and nodeSlotNumbers already loaded (ns0[m] for m >= R is ignored) */
+template <int NR>
+__device__ __forceinline__ bool tally_slot_core(const DevState& S, uint32_t cl, uint32_t gid, uint32_t R,
+                                                const MsetInfo* ms, int4& crow, bool& dirty, int slot,
+                                                const int4 (&r0)[NR], const int4 (&r1)[NR], uint32_t nrep, const int4 pe0,
+                                                const int (&ns0)[8], gpx_decision_rec& d, unsigned int* s_ctr) {
+  const uint32_t Wm = S.W - 1;
+  const size_t pi = win_idx(S, cl, (uint32_t)slot & Wm, gid);
+  int4 pe = pe0;
+  const int4 pe_in = pe;
+  int ns[8], ns_in[8];
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    ns[m] = (uint32_t)m < R ? ns0[m] : 2147483647;
+    ns_in[m] = ns[m];
+  }
+  bool decided = false;
+  uint32_t handled = 0;
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+    if ((uint32_t)k >= nrep) continue;
+    const uint32_t who = (uint32_t)r1[k].y;
+    if (GPX_WHO_FLAGS(who) & GPX_F_VOID) continue;
+    handled++;
+    const int rb = r0[k].z, rc = r0[k].w, max_cp = r1[k].x;
+    const uint32_t accIdx = GPX_WHO_ACC(who);
+    const uint32_t cf = (unsigned)crow.w & 0xffu;
+    if ((cf & GPX_CF_EXISTS) && (cf & GPX_CF_ACTIVE)) { /* PaxosCoordinator.handleAcceptReply :212 */
+      const int c = bcmp(rb, rc, crow.x, crow.y);
+      if (c > 0) { /* handleAcceptReplyHigherBallot :661-675 */
+        if (((unsigned)pe.y & GPX_PV_PRESENT) && pe.x == slot) {
+          pe.y = (int)((unsigned)pe.y & ~GPX_PV_PRESENT);
+          crow.w = (int)((unsigned)crow.w - (1u << 8));
+          dirty = true;
+          atomicAdd(&s_ctr[C_PREEMPTED], 1u);
+        }
+      } else if (c == 0) { /* handleAcceptReplyMyBallot :597-640 */
+#pragma unroll
+        for (int m = 0; m < 8; m++) /* recordSlotNumber :809-825 (plain <) */
+          if ((uint32_t)m == accIdx && accIdx < R && ns[m] < max_cp) ns[m] = max_cp;
+        if (((unsigned)pe.y & GPX_PV_PRESENT) && pe.x == slot) {
+          uint32_t vf = (unsigned)pe.y;
+          if (accIdx < R) vf |= (1u << accIdx);      /* WaitforUtility.updateHeardFrom :51-62 */
+          if (__popc(vf & 0xffffu) > (int)(R / 2)) { /* heardFromMajority :64-68 */
+            d.gid = gid;
+            d.slot = slot;
+            d.bnum = crow.x;
+            d.bcoord = crow.y;
+            d.median_cp = median_regs<8>(ns, R); /* makeDecision(getMajorityCommittedSlot()) :630 */
+            d.flags = (uint16_t)(GPX_F_DECISION | ((vf & GPX_PV_STOP) ? GPX_F_STOP : 0u));
+            d.dst_mask = ms->lane_mask;
+            d.req_id = ((long long)pe.w << 32) | (unsigned)pe.z;
+            decided = true;
+            pe.y = (int)(vf & ~GPX_PV_PRESENT);
+            crow.w = (int)((unsigned)crow.w - (1u << 8));
+            dirty = true;
+            atomicAdd(&s_ctr[C_DECISIONS_MADE], 1u);
+          } else
+            pe.y = (int)vf;
+        }
+      }
+    }
+    /* nullifyCoordinatorIfPreemptedFully :1353-1356 */
+    if ((((unsigned)crow.w) & GPX_CF_EXISTS) && bcmp(rb, rc, crow.x, crow.y) > 0 && (((unsigned)crow.w) >> 8) == 0) {
+      crow = make_int4(0, 0, 0, 0);
+      dirty = true;
+      atomicAdd(&s_ctr[C_COORD_RESIGNED], 1u);
+    }
+  }
+  if (handled) atomicAdd(&s_ctr[C_REPLIES_HANDLED], handled);
+  if (pe.y != pe_in.y) S.prop_win[pi] = pe;
+#pragma unroll
+  for (int m = 0; m < 8; m++)
+    if ((uint32_t)m < R && ns[m] != ns_in[m]) S.node_slots[ns_idx(S, cl, (uint32_t)m, gid)] = ns[m];
+  return decided;
+}
+
 /* PISM.handleBatchedCommit :1480-1528 (one slot) at one lane on register-resident row/aux; (a0,a1) is the
  * accepted window entry at slot mod W as currently in memory.  Produces the log image. */
 __device__ __forceinline__ void commit_lane(const DevState& S, uint32_t l, uint32_t gid, int slot, int bnum,
@@ -609,6 +711,36 @@ __device__ __forceinline__ void commit_lane(const DevState& S, uint32_t l, uint3
     img0 = make_int4((int)gid, slot, d.bnum, d.bcoord);
     img1 = make_int4(meta ? -1 : d.median_cp, (int)(lf | ((1u << l) << 16)), (int)(unsigned)(d.req_id & 0xffffffffll),
                      (int)(d.req_id >> 32));
+  }
+  if (d.valued && slot == row.x && GPX_AUX_PRESENT(aux) == 0u) {
+    /* the common case, in line: the decision is the accept we hold, it is next in line and nothing else is queued --
+     * extractExecuteAndCheckpoint :1619-1701 runs exactly one execution (what eec_impl does in two loop iterations:
+     * GC, execute, advance, drop the accept from memory when journaling, GC again) without the call and its frame */
+    gc_step(row, d.median_cp);
+    row.x = (int)((unsigned)row.x + 1u); /* executed(): _slot++ */
+    const bool stop = (d.fl & GPX_ENT_STOP) != 0;
+    if (stop) {
+      aux = (aux & ~0xffu) | GPX_ST_STOPPED; /* stop() + committedRequests.clear() */
+      aux &= ~0x00ffff00u;
+    }
+    if (S.journaling) { /* acceptedProposals.remove(slot) :360-362 */
+      const size_t ai = 2 * win_idx(S, l, (uint32_t)slot & (S.W - 1), gid);
+      S.acc_win[ai + 1] = make_int4(a1.x, a1.y, a1.z, (int)((unsigned)a1.w & ~GPX_ENT_VALID));
+    }
+    atomicAdd(&s_ctr[C_EXECUTED], 1u);
+    const gpx_exec_rec er = make_exec(S, gid, l, d, false);
+    if (er.flags & GPX_F_CKPT) atomicAdd(&s_ctr[C_CKPTS_DUE], 1u);
+    if (ex) {
+      store_exec(ex, er);
+    } else if (n_extra) {
+      const uint32_t k = atomicAdd(n_extra, 1u);
+      if (k < extra_cap) store_exec(extra + k, er);
+    }
+    if (stop)
+      atomicAdd(&s_ctr[C_STOPS_EXECUTED], 1u);
+    else
+      gc_step(row, d.median_cp);
+    return;
   }
   const int slot_before = row.x;
   eec(S, l, gid, row, aux, d, ex, extra, extra_cap, n_extra, s_ctr, false);
@@ -880,6 +1012,159 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_tally(const __grid_constant__ Dev
   flush_counters(S, s_ctr);
 }
 
+/* k_tally_slots<L>: the replies of the phase pipeline lie as [ACCEPT j][lane l] (index j * L + l): one thread per
+ * ACCEPT takes the L replies of its slot at once and tallies them in registers (tally_slot_regs); the thread of the
+ * first ACCEPT of a group's run walks the run.  Replies addressed to different coordinator lanes inside one slot, or
+ * groups of more than 8 members, take the reply-by-reply path. */
+template <int L>
+__global__ void __launch_bounds__(GPX_BLOCK) k_tally_slots(const __grid_constant__ DevState S,
+                                                           const __grid_constant__ TallyArgs A) {
+  __shared__ unsigned int s_ctr[C_NCTR];
+  __shared__ uint32_t s_scan[GPX_BLOCK / 32 + 1];
+  if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t n = A.n_ptr ? *A.n_ptr : A.n_max / (uint32_t)L; /* ACCEPTs */
+  if (n > A.n_max / (uint32_t)L) n = A.n_max / (uint32_t)L;
+  const uint32_t i = blockIdx.x * GPX_BLOCK + threadIdx.x;
+  gpx_decision_rec dbuf[GPX_MAX_WINDOW];
+  uint32_t nd = 0;
+  if (i == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
+  if (i < n) {
+    const gpx_accept_reply_rec* rp = &A.replies[(size_t)i * L];
+    int4 r0[L], r1[L];
+#pragma unroll
+    for (int l = 0; l < L; l++) ld256_stream(&rp[l], r0[l], r1[l]);
+    const uint32_t gid = (uint32_t)r0[0].x;
+    const uint32_t gprev = i ? A.replies[(size_t)(i - 1) * L].gid : 0xffffffffu;
+    const uint32_t gnext = i + 1 < n ? A.replies[(size_t)(i + 1) * L].gid : 0xffffffffu;
+    const bool head = (i == 0) || (gprev != gid);
+    /* ---- the plain case in two load levels: ONE ACCEPT of the group in the batch, every reply addressed to the
+     * same coordinator, and member index == lane (GPX_META_IDENT) so that the lane follows from the reply alone: the
+     * group's meta word, the coordinator's aux / row, the slot's proposal entry and nodeSlotNumbers are all fetched
+     * together, validated, and the slot is tallied in registers ---- */
+    bool done = false;
+    if (head && gnext != gid && gid < S.G) {
+      uint32_t dst = 0xffu, nvalid = 0;
+      bool same = true;
+#pragma unroll
+      for (int l = 0; l < L; l++) {
+        const uint32_t who = (uint32_t)r1[l].y;
+        if (GPX_WHO_FLAGS(who) & GPX_F_VOID) continue;
+        if (nvalid++ == 0)
+          dst = GPX_WHO_DST(who);
+        else
+          same = same && GPX_WHO_DST(who) == dst;
+      }
+      if (nvalid && same && dst < (uint32_t)L) {
+        const int slot = r0[0].y;
+        const uint32_t meta = S.grp_meta[gid];
+        const size_t ri = row_idx(S, dst, gid);
+        const uint32_t aux = S.acc_aux[ri];
+        int4 crow = S.coord_row[ri];
+        const int4 pe0 = S.prop_win[win_idx(S, dst, (uint32_t)slot & (S.W - 1), gid)];
+        int ns0[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) ns0[m] = (uint32_t)m < S.Rcap ? S.node_slots[ns_idx(S, dst, (uint32_t)m, gid)] : 0;
+        const uint32_t R = (meta >> 16) & 0xffu;
+        if ((meta & (GPX_META_LIVE | GPX_META_IDENT)) == (GPX_META_LIVE | GPX_META_IDENT) && R <= 8u && st_usable(aux)) {
+          bool dirty = false;
+          gpx_decision_rec d;
+          if (tally_slot_core<L>(S, dst, gid, R, &S.msets[meta & 0xffffu], crow, dirty, slot, r0, r1, (uint32_t)L, pe0, ns0,
+                                 d, s_ctr)) {
+            dbuf[0] = d;
+            nd = 1;
+          }
+          if (dirty) S.coord_row[ri] = crow;
+          done = true;
+        }
+      }
+    }
+    if (head && !done) {
+      const GroupCtx g = group_ctx(S, gid);
+      int cl = -1;
+      int4 crow = make_int4(0, 0, 0, 0);
+      bool dirty = false;
+      uint32_t j = i;
+      while (true) {
+        /* the coordinator lane the slot's replies are addressed to (PISM drop rule :456-460: it must be usable) */
+        int lane = -1;
+        bool uniform = g.live && g.R <= 8u;
+        uint32_t nvalid = 0;
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          const uint32_t who = (uint32_t)r1[l].y;
+          if (GPX_WHO_FLAGS(who) & GPX_F_VOID) continue;
+          nvalid++;
+          const uint32_t dstIdx = GPX_WHO_DST(who);
+          const int ln = (g.live && dstIdx < g.R && g.ms->lane_of_idx[dstIdx] != 0xffu) ? (int)g.ms->lane_of_idx[dstIdx] : -1;
+          if (lane == -1 && nvalid == 1)
+            lane = ln;
+          else if (ln != lane)
+            uniform = false;
+        }
+        uint32_t aux;
+        if (nvalid && uniform && lane >= 0 && usable(S, gid, (uint32_t)lane, &aux)) {
+          if (lane != cl) {
+            if (dirty) S.coord_row[row_idx(S, cl, gid)] = crow;
+            cl = lane;
+            crow = S.coord_row[row_idx(S, cl, gid)];
+            dirty = false;
+          }
+          gpx_decision_rec d;
+          if (tally_slot_regs<L>(S, (uint32_t)cl, gid, g.R, g.ms, crow, dirty, r0[0].y, r0, r1, (uint32_t)L, d, s_ctr)) {
+            if (nd < GPX_MAX_WINDOW) dbuf[nd] = d;
+            nd++;
+          }
+        } else if (nvalid) { /* reply by reply, against memory */
+#pragma unroll
+          for (int l = 0; l < L; l++) {
+            const uint32_t who = (uint32_t)r1[l].y;
+            if (GPX_WHO_FLAGS(who) & GPX_F_VOID) continue;
+            const uint32_t dstIdx = GPX_WHO_DST(who);
+            int ln = -1;
+            if (g.live && dstIdx < g.R && g.ms->lane_of_idx[dstIdx] != 0xffu && usable(S, gid, g.ms->lane_of_idx[dstIdx], &aux))
+              ln = g.ms->lane_of_idx[dstIdx];
+            if (ln < 0) {
+              atomicAdd(&s_ctr[C_REPLIES_IGNORED], 1u);
+              continue;
+            }
+            if (ln != cl) {
+              if (dirty) S.coord_row[row_idx(S, cl, gid)] = crow;
+              cl = ln;
+              crow = S.coord_row[row_idx(S, cl, gid)];
+              dirty = false;
+            }
+            gpx_decision_rec d;
+            if (tally_reply(S, (uint32_t)cl, gid, g.R, g.ms, crow, dirty, r0[l].y, r0[l].z, r0[l].w, r1[l].x,
+                            GPX_WHO_ACC(who), d, s_ctr)) {
+              if (nd < GPX_MAX_WINDOW) dbuf[nd] = d;
+              nd++;
+            }
+          }
+        }
+        j++;
+        if (j >= n) break;
+        rp = &A.replies[(size_t)j * L];
+        int4 t0, t1;
+        ld256_stream(&rp[0], t0, t1);
+        if ((uint32_t)t0.x != gid) break;
+        r0[0] = t0;
+        r1[0] = t1;
+#pragma unroll
+        for (int l = 1; l < L; l++) ld256_stream(&rp[l], r0[l], r1[l]);
+      }
+      if (dirty) S.coord_row[row_idx(S, cl, gid)] = crow;
+    }
+  }
+  if (nd > GPX_MAX_WINDOW) nd = GPX_MAX_WINDOW; /* cannot happen: <= W proposals outstanding */
+  uint32_t base = block_reserve(nd, A.n_decisions, s_scan);
+  for (uint32_t k = 0; k < nd; k++) {
+    const int4* sp = reinterpret_cast<const int4*>(&dbuf[k]);
+    st256_stream(&A.decisions[base + k], sp[0], sp[1]);
+  }
+  flush_counters(S, s_ctr);
+}
+
 /* ============================== k_commit ====================================== */
 struct CommitArgs {
   const gpx_decision_rec* decisions;
@@ -892,7 +1177,7 @@ struct CommitArgs {
 };
 
 template <int L>
-__global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_commit(const __grid_constant__ DevState S,
+__global__ void __launch_bounds__(GPX_BLOCK, 2) k_commit(const __grid_constant__ DevState S,
                                                       const __grid_constant__ CommitArgs A) {
   __shared__ unsigned int s_ctr[C_NCTR];
   if (threadIdx.x < C_NCTR) s_ctr[threadIdx.x] = 0;

@@ -66,30 +66,6 @@ __device__ __forceinline__ void store_sum(gpx_exec_sum* dst, int slot, uint32_t 
 #define GPX_ROUND_MINB 5 /* 48 registers per thread = 1,280 resident threads per SM; measured optimum (40 and 64 are slower) */
 #endif
 
-/* PCS.getMedianMinus :867-875 on a register array (R <= LP <= 8) */
-template <int LP>
-__device__ __forceinline__ int median_regs(const int (&ns)[LP], uint32_t R) {
-  if (R == 1) return ns[0];
-  if (LP >= 3 && R == 3) return max(min(ns[0], ns[1]), min(max(ns[0], ns[1]), ns[2]));
-  int v[LP];
-#pragma unroll
-  for (int k = 0; k < LP; k++) v[k] = (uint32_t)k < R ? ns[k] : 2147483647;
-#pragma unroll
-  for (int a = 0; a < LP; a++) /* odd-even transposition sort, fully unrolled: no dynamic indexing */
-#pragma unroll
-    for (int b = (a & 1); b + 1 < LP; b += 2) {
-      int lo = min(v[b], v[b + 1]), hi = max(v[b], v[b + 1]);
-      v[b] = lo;
-      v[b + 1] = hi;
-    }
-  const uint32_t idx = (R % 2 == 0) ? R / 2 - 1 : R / 2;
-  int out = v[0];
-#pragma unroll
-  for (int k = 1; k < LP; k++)
-    if ((uint32_t)k == idx) out = v[k];
-  return out;
-}
-
 /* commit of decision d at one lane, state in registers (the per-lane part of k_act's commit phase) */
 template <int L>
 __device__ __forceinline__ void commit_team_lane(const DevState& S, const AcceptArgs& A, uint32_t l, uint32_t gid,

@@ -182,12 +182,11 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_sp_route(const __grid_constant__ 
           op[0] = q0;
           op[1] = q1;
           op[2] = make_int4((int)(uint32_t)boff, q2.y, q2.z, q2.w);
-          uint8_t* dst = sp_blob(b) + boff;
+          uint8_t* dst = sp_blob(b) + boff; /* 16-byte aligned: whole chunks are stored, the tail zero-padded */
           uint32_t x = 0;
           if (al)
             for (; x + 16 <= plen; x += 16) st_stream4(dst + x, ld_stream4(src + x));
-          for (; x < plen; x++) dst[x] = src[x];
-          for (; x < (u << 4); x++) dst[x] = 0; /* deterministic padding */
+          for (; x < plen; x += 16) st_stream4(dst + x, load_chunk16(src + x, plen - x));
           p = ((uint32_t)d << GPX_SP_POS_BITS) | pos;
         }
       }
@@ -375,26 +374,33 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_sp_tally(const __grid_constant__ 
         d.req_id = 0;
         bool decided = false;
         const bool is_void = ((uint32_t)q1.y & GPX_F_VOID) != 0;
-        if (!is_void)
-          for (uint32_t m = 0; m < Rcap && m < GPX_SP_ND; m++) {
-            const uint32_t p = A.pos[(size_t)j * Rcap + m];
-            if (p == GPX_SP_NONE) continue;
-            const SpBucket& rb = A.recvR[p >> GPX_SP_POS_BITS];
-            int4 r0, r1;
-            ld256_stream(sp_recs(rb) + (size_t)(p & ((1u << GPX_SP_POS_BITS) - 1u)) * 32, r0, r1);
-            const uint32_t who = (uint32_t)r1.y;
-            if (GPX_WHO_FLAGS(who) & GPX_F_VOID) continue;
-            if (!can || GPX_WHO_DST(who) >= g.R || g.ms->lane_of_idx[GPX_WHO_DST(who)] != 0) {
-              atomicAdd(&s_ctr[C_REPLIES_IGNORED], 1u); /* not addressed to a usable coordinator here */
-              continue;
+        if (!is_void) { /* gather the R replies of the slot (member order), then tally them in registers */
+          int4 r0[GPX_SP_ND], r1[GPX_SP_ND];
+          uint32_t pp[GPX_SP_ND];
+#pragma unroll
+          for (int m = 0; m < GPX_SP_ND; m++) {
+            pp[m] = (uint32_t)m < Rcap ? A.pos[(size_t)j * Rcap + m] : GPX_SP_NONE;
+            r0[m] = make_int4(0, 0, 0, 0);
+            r1[m] = make_int4(0, (int)GPX_WHO(0xffu, 0xffu, GPX_F_VOID), 0, 0);
+            if (pp[m] != GPX_SP_NONE) {
+              const SpBucket& rb = A.recvR[pp[m] >> GPX_SP_POS_BITS];
+              ld256_stream(sp_recs(rb) + (size_t)(pp[m] & ((1u << GPX_SP_POS_BITS) - 1u)) * 32, r0[m], r1[m]);
+              const uint32_t who = (uint32_t)r1[m].y;
+              if (!(GPX_WHO_FLAGS(who) & GPX_F_VOID) &&
+                  (!can || GPX_WHO_DST(who) >= g.R || g.ms->lane_of_idx[GPX_WHO_DST(who)] != 0)) {
+                atomicAdd(&s_ctr[C_REPLIES_IGNORED], 1u); /* not addressed to a usable coordinator here */
+                r1[m].y = (int)GPX_WHO(0xffu, 0xffu, GPX_F_VOID);
+              }
             }
+          }
+          if (can && g.R <= 8u) {
             gpx_decision_rec dd;
-            if (tally_reply(S, 0, gid, g.R, g.ms, crow, dirty, r0.y, r0.z, r0.w, r1.x, GPX_WHO_ACC(who), dd, s_ctr) &&
-                !decided) {
+            if (tally_slot_regs<GPX_SP_ND>(S, 0, gid, g.R, g.ms, crow, dirty, q0.y, r0, r1, (uint32_t)GPX_SP_ND, dd, s_ctr)) {
               d = dd;
               decided = true;
             }
           }
+        }
         if (!is_void) {
           const int4* sp = reinterpret_cast<const int4*>(&d);
           for (uint32_t m = 0; m < Rcap && m < GPX_SP_ND; m++) {
