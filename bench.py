@@ -195,12 +195,12 @@ class L2Flush:
         self.torch, self.mode = torch, mode
         self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         self.rd = torch.zeros(64 << 20, dtype=torch.int32, device=dev)  # 256 MiB
-        self.acc = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.acc = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def zero_(self):  # the call sites' name
         self.buf.zero_()
         if self.mode == "clean":
-            self.torch.sum(self.rd, dim=0, keepdim=True, dtype=self.torch.int64, out=self.acc)
+            self.torch.amax(self.rd, dim=0, keepdim=True, out=self.acc)  # a plain 256 MiB read
 
     def describe(self):
         return ("flushed between timed steps, outside the timed events: 256 MiB write then 256 MiB read (cold and clean)"
@@ -549,26 +549,33 @@ def main():
         "kernel_ms_all": {"k_round": act_ms},
     }
     roofline["frac"] = roofline["achieved"] / peak
-    # dram__bytes_read.sum + dram__bytes_write.sum of one k_round launch, from the committed `ncu --set full` captures
-    # (profiles/r1f_k_round_*_ncu_full_summary.txt); a number measured under ncu, so it is a constant here
-    ncu_traffic = {("cfg2", 100_000, 1): 18_508_800 + 4_371_456, ("1m1b", 1_000_000, 1): 184_884_992 + 430_979_328}
-    roofline["traffic"] = ncu_traffic.get((args.workload, G, P))
-    roofline["traffic_source"] = ("profiles/r1f_k_round_%s_ncu_full_summary.txt" % ("cfg2" if G == 100_000 else "1m")
-                                  if roofline["traffic"] else None)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch: measured with ncu on this very command by
+    # tools/measure_traffic.py (profiles/traffic.json); null when no measurement of this workload is on file
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    wkey = args.workload if not (args.groups or args.payload) else None
+    tr = traffic.get(f"{wkey}:k_round")
+    roofline["traffic"] = tr["traffic"] if tr else None
+    roofline["traffic_source"] = "profiles/traffic.json (tools/measure_traffic.py: ncu dram__bytes_read.sum + dram__bytes_write.sum)" if tr else None
     roofline_accept = {
         "kernel": "k_accept (stand-alone accept-batch kernel of the phase-by-phase pipeline, north_star kernel)",
         "bound": "hbm", "achieved": acc_bytes / (acc_ms / 1e3) / 1e9 if acc_ms > 0 else 0.0, "peak": peak,
         "unit": "GB/s", "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": acc_bytes,
         "bytes_per_accept": b_acc(P), "accepts_per_launch": G * R, "kernel_ms": acc_ms,
-        "kernel_ms_all": {"k_propose+k_build_blobs": kp["propose"], "k_accept": acc_ms, "k_tally": kp["tally"],
+        "kernel_ms_all": {"k_propose+k_build_blobs": kp["propose"], "k_accept": acc_ms, "k_tally_slots": kp["tally"],
                           "k_commit": kp["commit"]},
+        "frac_all": {"k_accept": acc_bytes / (acc_ms / 1e3) / 1e9 / peak if acc_ms > 0 else 0.0,
+                     "k_tally_slots (64 + 8R B per reply)": G * R * (64 + 8 * R) / (kp["tally"] / 1e3) / 1e9 / peak if kp["tally"] > 0 else 0.0,
+                     "k_commit (153 B per decision per replica)": G * R * 153 / (kp["commit"] / 1e3) / 1e9 / peak if kp["commit"] > 0 else 0.0},
         "phase_pipeline_decisions_per_sec": G / ((kp["propose"] + acc_ms + kp["tally"] + kp["commit"]) / 1e3),
     }
     roofline_accept["frac"] = roofline_accept["achieved"] / peak
-    roofline_accept["traffic"] = {("cfg2", 100_000, 1): 20_956_416 + 2_864_384,
-                                  ("1m1b", 1_000_000, 1): 209_124_608 + 301_923_328}.get((args.workload, G, P))
-    roofline_accept["traffic_source"] = ("profiles/r1f_k_accept_%s_ncu_full_summary.txt" % ("cfg2" if G == 100_000 else "1m")
-                                         if roofline_accept["traffic"] else None)
+    tra = traffic.get(f"{wkey}:k_accept")
+    roofline_accept["traffic"] = tra["traffic"] if tra else None
+    roofline_accept["traffic_source"] = roofline["traffic_source"] if tra else None
 
     # ---- the same kernels on a batch that fills the GPU (context for the latency-bound 100K-group step) --------
     roofline_large = None
@@ -818,7 +825,7 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": config, "roofline": roofline,
             "roofline_accept": roofline_accept, "roofline_1m_groups": roofline_large,
-            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 2 * K,  # k_round + k_round_slow per step
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": K,  # one k_round per step (k_round_slow only when a run is left over)
             "p50_decide_latency_ms": float(np.median(step_ms)),
             "requests_per_sec": value, "wall_s_timed_region": t_wall,
         }
