@@ -376,6 +376,9 @@ def main():
                     help="spread placement through the host-orchestrated reference path (gigapaxos_b200/spread.py "
                          "SpreadCluster: torch.distributed exchanges, one host count read per exchange) instead of gpx_spread_*")
     ap.add_argument("--no-graph", action="store_true", help="spread: plain stream launches instead of one CUDA graph per round")
+    ap.add_argument("--no-p2p", action="store_true",
+                    help="spread: exchange the buckets with grouped ncclSend/ncclRecv instead of storing them straight into "
+                         "the peers' receive buckets over NVLink (GPX_SPREAD_P2P)")
     args = ap.parse_args()
 
     wl = dict(WORKLOADS[args.workload])
@@ -1167,7 +1170,7 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
     local = list(range(N)) if world == 1 else [rank]
     cap = spread_caps(coord, member_of)
     blob_per_rec = (P + 15) // 16 * 16
-    scfg = spread_config(node_ids, cap, blob_per_rec=blob_per_rec, max_reqs=G, graph=not args.no_graph)
+    scfg = spread_config(node_ids, cap, blob_per_rec=blob_per_rec, max_reqs=G, graph=not args.no_graph, p2p=not args.no_p2p)
     engines = []
     for idx in local:
         n_in = int(member_of[:, idx].sum())
@@ -1331,8 +1334,10 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
                     "l2": (flush_buf.describe() if use_flush else
                            "not flushed: one step's working set (%.0f MB per GPU) exceeds the 126 MB L2, steps run back to back" % ws_mb),
                     "placement": f"spread: {N} nodes, one single-lane engine per "
-                    + ("GPU; libgpx issues grouped ncclSend/ncclRecv of fixed-capacity buckets over NVLink"
-                       if world > 1 else "node, all on ONE GPU (device copies)")
+                    + (("GPU; the kernels store records straight into the peers' fixed-capacity receive buckets over NVLink "
+                        "(CUDA IPC; handles exchanged over NCCL), flag exchange per packet type" if not args.no_p2p else
+                        "GPU; libgpx issues grouped ncclSend/ncclRecv of fixed-capacity buckets over NVLink")
+                       if world > 1 else "node, all on ONE GPU")
                     + f"; replica j of a group on node (home+j) mod {N}; three record exchanges per round; "
                     + ("one CUDA graph launch per round" if not args.no_graph else "stream launches"),
                     "nvlink_bytes_sent_per_gpu_per_step": link_bytes})

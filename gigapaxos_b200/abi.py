@@ -117,6 +117,7 @@ class RoundIO(C.Structure):
 
 SPREAD_MAX_NODES = 8
 SPREAD_GRAPH = 1
+SPREAD_P2P = 2
 
 
 class SpreadConfig(C.Structure):

@@ -58,6 +58,13 @@ struct SpArgs {
   SpBucket sendA[GPX_SP_ND], recvA[GPX_SP_ND]; /* ACCEPT: me -> d, s -> me */
   SpBucket sendR[GPX_SP_ND], recvR[GPX_SP_ND]; /* ACCEPT_REPLY: me (acceptor) -> coordinator s; acceptor d -> me */
   SpBucket sendD[GPX_SP_ND], recvD[GPX_SP_ND]; /* DECISION: me -> d, s -> me */
+  /* where k_sp_route counts the records of destination d: the header of the send bucket itself, or -- peer-memory
+   * transport, where that header lives on another GPU -- a local scratch header that k_sp_signal copies over */
+  SpHdr* cntA[GPX_SP_ND];
+  uint32_t p2p;                     /* 1: send buckets ARE the peers' receive buckets (NVLink stores), see k_sp_signal */
+  uint32_t* flags_local;            /* [3][GPX_SP_ND] round numbers signalled by the source nodes, per packet type */
+  uint32_t* flags_peer[GPX_SP_ND];  /* node d's flags_local (mapped peer memory) */
+  uint32_t* seq;                    /* [6] rounds signalled / awaited so far per packet type (device-resident: graph replay) */
   uint32_t vtotal;                  /* virtual record slots of the receive side (sum of 256-aligned caps) */
   unsigned long long blob_vtotal;   /* bytes of all received blob areas */
   uint32_t blob_per_rec;
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_sp_route(const __grid_constant__ 
   }
   __syncthreads();
   if (threadIdx.x < GPX_SP_ND && threadIdx.x < A.N && s_cnt[threadIdx.x]) { /* one reservation per block + destination */
-    SpHdr* h = sp_hdr(A.sendA[threadIdx.x]);
+    SpHdr* h = A.cntA[threadIdx.x];
     s_base[threadIdx.x] = atomicAdd(&h->count, s_cnt[threadIdx.x]);
     s_ubase[threadIdx.x] = atomicAdd(&h->blob_units, s_units[threadIdx.x]);
   }
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(GPX_BLOCK) k_sp_tally(const __grid_constant__ 
   if (i == 0) atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   if (blockIdx.x == 0 && threadIdx.x < A.N && A.sendD[threadIdx.x].cap) { /* DECISION buckets mirror the ACCEPT ones */
     SpHdr* h = sp_hdr(A.sendD[threadIdx.x]);
-    uint32_t c = sp_hdr(A.sendA[threadIdx.x])->count;
+    uint32_t c = A.cntA[threadIdx.x]->count;
     if (c > A.sendA[threadIdx.x].cap) c = A.sendA[threadIdx.x].cap;
     h->count = c;
     h->blob_units = 0;
@@ -449,7 +456,7 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_sp_commit(const _
     atomicAdd(&s_ctr[C_KERNEL_LAUNCHES], 1u);
   }
   if (blockIdx.x == 0 && threadIdx.x < A.N && A.sendA[threadIdx.x].cap) { /* next round's k_sp_route counts from zero */
-    SpHdr* h = sp_hdr(A.sendA[threadIdx.x]);
+    SpHdr* h = A.cntA[threadIdx.x];
     h->count = 0;
     h->blob_units = 0;
   }
@@ -503,4 +510,58 @@ __global__ void __launch_bounds__(GPX_BLOCK, GPX_PHASE_MINB) k_sp_commit(const _
     }
   }
   flush_counters(S, s_ctr);
+}
+
+/* ============================== peer-memory transport: k_sp_signal / k_sp_wait ============================== */
+/* With GPX_SPREAD_P2P the send buckets of a node ARE the receive buckets of its peers (mapped peer memory: CUDA IPC
+ * between the per-GPU processes, plain pointers between engines of one process): k_sp_route / k_sp_accept / k_sp_tally
+ * store records, blobs, replies and decisions straight into the destination GPU over NVLink, and the "exchange" that
+ * remains is a flag.  k_sp_signal runs behind the producing kernel (whose stores are complete and visible system-wide
+ * when it has finished): it copies the ACCEPT counts into the peers' bucket headers, fences, and writes this round's
+ * number into flag [kind][me] of every peer it sends to.  k_sp_wait runs in front of the consuming kernel and spins
+ * until every source it receives from has signalled this round.  The round numbers live in device memory, so a
+ * captured round replays unchanged.  Re-use of a bucket is safe without credits: a node writes the ACCEPT bucket of
+ * round r+1 only after its tally of round r, i.e. after the peer's replies of round r, which the peer sent after it
+ * had consumed the ACCEPT bucket of round r (and likewise for the other two kinds). */
+__global__ void k_sp_signal(const __grid_constant__ SpArgs A, uint32_t kind) {
+  const uint32_t t = threadIdx.x;
+  const uint32_t round = A.seq[kind] + 1u;
+  bool to = false;
+  if (t < A.N) {
+    const SpBucket& sb = kind == 0 ? A.sendA[t] : kind == 1 ? A.sendR[t] : A.sendD[t];
+    to = sb.cap != 0;
+    if (to && kind == 0) { /* the ACCEPT counts were taken in local scratch: into the (remote) bucket header */
+      SpHdr* h = sp_hdr(sb);
+      uint32_t c = A.cntA[t]->count;
+      if (c > sb.cap) c = sb.cap;
+      h->count = c;
+      h->blob_units = A.cntA[t]->blob_units;
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (to) {
+    volatile uint32_t* f = A.flags_peer[t] + kind * GPX_SP_ND + A.me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"((uint32_t*)f), "r"(round) : "memory");
+  }
+  __syncwarp();
+  if (t == 0) A.seq[kind] = round;
+}
+
+__global__ void k_sp_wait(const __grid_constant__ SpArgs A, uint32_t kind) {
+  const uint32_t t = threadIdx.x;
+  const uint32_t round = A.seq[3 + kind] + 1u;
+  if (t < A.N) {
+    const SpBucket& rb = kind == 0 ? A.recvA[t] : kind == 1 ? A.recvR[t] : A.recvD[t];
+    if (rb.cap) {
+      const uint32_t* f = A.flags_local + kind * GPX_SP_ND + t;
+      uint32_t seen;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+        if ((int32_t)(seen - round) < 0) __nanosleep(100);
+      } while ((int32_t)(seen - round) < 0);
+    }
+  }
+  __syncwarp();
+  if (t == 0) A.seq[3 + kind] = round;
 }

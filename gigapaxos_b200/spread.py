@@ -393,7 +393,7 @@ SPREAD_MAX_NODES_PY = abi.SPREAD_MAX_NODES
 
 
 def spread_config(node_ids: Sequence[int], cap: np.ndarray, blob_per_rec: int, max_reqs: int,
-                  graph: bool = False) -> "abi.SpreadConfig":
+                  graph: bool = False, p2p: bool = False) -> "abi.SpreadConfig":
     c = abi.SpreadConfig()
     c.n_nodes = len(node_ids)
     for i, x in enumerate(node_ids):
@@ -403,7 +403,7 @@ def spread_config(node_ids: Sequence[int], cap: np.ndarray, blob_per_rec: int, m
             c.cap[s][d] = int(cap[s, d])
     c.blob_per_rec = (int(blob_per_rec) + 15) // 16 * 16
     c.max_reqs = int(max_reqs)
-    c.flags = abi.SPREAD_GRAPH if graph else 0
+    c.flags = (abi.SPREAD_GRAPH if graph else 0) | (abi.SPREAD_P2P if p2p else 0)
     return c
 
 

@@ -581,6 +581,9 @@ int gpx_decisions_device(gpx_engine* e, gpx_decision_rec* decisions, uint32_t n,
  * exchanges). */
 #define GPX_SPREAD_MAX_NODES 8
 #define GPX_SPREAD_GRAPH 1u /* capture a round into a CUDA graph per distinct io block and replay it */
+#define GPX_SPREAD_P2P 2u   /* peer-memory transport: a node's send buckets ARE its peers' receive buckets (CUDA IPC between
+                             * the per-GPU processes): k_sp_route / k_sp_accept / k_sp_tally store over NVLink, the exchange
+                             * is a flag (k_sp_signal / k_sp_wait).  NCCL is then used once, to hand the IPC handles around */
 typedef struct gpx_spread gpx_spread;
 typedef struct gpx_spread_config {
   uint32_t n_nodes;                                         /* engines (nodes) of the spread group */
@@ -593,7 +596,7 @@ typedef struct gpx_spread_config {
   uint32_t blob_per_rec; /* blob bytes a bucket reserves per record slot (multiple of 16): request bodies travel
                           * with their ACCEPT (AcceptPacket carries the RequestPacket, AcceptPacket.java:95-138) */
   uint32_t max_reqs;     /* requests one node submits per round (<= the engine's max_batch_recs) */
-  uint32_t flags;        /* GPX_SPREAD_GRAPH */
+  uint32_t flags;        /* GPX_SPREAD_GRAPH | GPX_SPREAD_P2P */
   uint32_t reserved[8];
 } gpx_spread_config;
 /* what one node's buffers look like: byte offsets into its bucket arena, transfer sizes (0 = no transfer with that

@@ -42,7 +42,7 @@ def make_groups(N, G, R):
 class Cluster:
     """N CUDA nodes + the spread handle + per-node device buffers"""
 
-    def __init__(self, cuda_lib, N, G, R, P, graph=False, slots=1, **cfg):
+    def __init__(self, cuda_lib, N, G, R, P, graph=False, slots=1, p2p=False, **cfg):
         import torch
         self.torch = torch
         self.N, self.G = N, G
@@ -58,7 +58,7 @@ class Cluster:
         cap = spread_caps(self.coord, self.member_of, slots_per_round=slots, slack=3)
         # a batched slot carries 16 B per request + the bodies
         self.scfg = spread_config(self.node_ids, cap, blob_per_rec=4 * (16 + ((P + 15) // 16) * 16), max_reqs=4 * G,
-                                  graph=graph)
+                                  graph=graph, p2p=p2p)
         self.sp = Spread(cuda_lib, self.engines, self.scfg)
         self.stream = torch.cuda.Stream(device=self.dev)
         self.ctl = [torch.zeros(8, dtype=torch.int32, device=self.dev) for _ in range(N)]
@@ -181,11 +181,14 @@ def check_round(cl, res, index, so, xo):
         assert np.array_equal(want["flags"] & ~np.uint32(0xF000), got["flags"] & ~np.uint32(0xF000))
 
 
-@pytest.mark.parametrize("N,G,P,graph", [(4, 600, 1, False), (3, 200, 40, False), (5, 333, 17, False), (8, 900, 5, False),
-                                         (4, 600, 17, True), (5, 100, 17, False)])
-def test_spread_c_round_parity(oracle_lib, cuda_lib, N, G, P, graph):
+@pytest.mark.parametrize("N,G,P,graph,p2p", [(4, 600, 1, False, False), (3, 200, 40, False, False), (5, 333, 17, False, False),
+                                             (8, 900, 5, False, False), (4, 600, 17, True, False), (5, 100, 17, False, False),
+                                             (4, 600, 1, False, True), (8, 900, 5, False, True), (4, 600, 17, True, True)])
+def test_spread_c_round_parity(oracle_lib, cuda_lib, N, G, P, graph, p2p):
+    """p2p: the peer-memory transport (send buckets ARE the peers' receive buckets, k_sp_signal / k_sp_wait); between
+    engines of one process the peers' arenas are plain device pointers, between processes CUDA IPC mappings"""
     R = 3
-    cl = Cluster(cuda_lib, N, G, R, P, graph=graph, checkpoint_interval=3)
+    cl = Cluster(cuda_lib, N, G, R, P, graph=graph, p2p=p2p, checkpoint_interval=3)
     eo = Engine(oracle_lib, make_config(oracle_lib, max_groups=G, n_lanes=N, lane_node=cl.node_ids, max_group_size=R,
                                         max_batch_recs=4 * G, max_batch_payload=1 << 22, checkpoint_interval=3))
     eo.create_groups(cl.descs)
@@ -248,7 +251,7 @@ def test_spread_c_five_replicas_and_stops(oracle_lib, cuda_lib):
 
 
 # ---- one process per GPU over NCCL inside libgpx (needs >= 3 GPUs: skipped on single-GPU boxes) -----------------
-def _nccl_worker(rank, world, port, q, G, rounds, graph):
+def _nccl_worker(rank, world, port, q, G, rounds, graph, p2p=False):
     import os
     import traceback
     import torch
@@ -269,7 +272,7 @@ def _nccl_worker(rank, world, port, q, G, rounds, graph):
                                     checkpoint_interval=3))
         e.create_groups(descs[member_of[:, rank]])
         scfg = spread_config(node_ids, spread_caps(coord, member_of, slack=2), blob_per_rec=4 * (16 + 32),
-                             max_reqs=4 * G, graph=graph)
+                             max_reqs=4 * G, graph=graph, p2p=p2p)
         ids = [Spread.unique_id(lib) if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         sp = Spread(lib, [e], scfg, rank=rank, unique_id=ids[0])
@@ -339,8 +342,8 @@ def _nccl_worker(rank, world, port, q, G, rounds, graph):
         raise
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_spread_c_over_nccl(graph):
+@pytest.mark.parametrize("graph,p2p", [(False, False), (True, False), (False, True), (True, True)])
+def test_spread_c_over_nccl(graph, p2p):
     import torch
     import torch.multiprocessing as mp
     from test_spread_gloo import free_port
@@ -350,7 +353,7 @@ def test_spread_c_over_nccl(graph):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, 500, 5, graph)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, 500, 5, graph, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
