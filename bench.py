@@ -376,9 +376,10 @@ def main():
                     help="spread placement through the host-orchestrated reference path (gigapaxos_b200/spread.py "
                          "SpreadCluster: torch.distributed exchanges, one host count read per exchange) instead of gpx_spread_*")
     ap.add_argument("--no-graph", action="store_true", help="spread: plain stream launches instead of one CUDA graph per round")
-    ap.add_argument("--no-p2p", action="store_true",
-                    help="spread: exchange the buckets with grouped ncclSend/ncclRecv instead of storing them straight into "
-                         "the peers' receive buckets over NVLink (GPX_SPREAD_P2P)")
+    ap.add_argument("--p2p", action="store_true",
+                    help="spread: store the records straight into the peers' receive buckets over NVLink (GPX_SPREAD_P2P, CUDA "
+                         "IPC between the ranks) instead of exchanging the buckets with grouped ncclSend/ncclRecv; falls back "
+                         "to the NCCL exchange when the peer mapping cannot be set up")
     args = ap.parse_args()
 
     wl = dict(WORKLOADS[args.workload])
@@ -1170,7 +1171,7 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
     local = list(range(N)) if world == 1 else [rank]
     cap = spread_caps(coord, member_of)
     blob_per_rec = (P + 15) // 16 * 16
-    scfg = spread_config(node_ids, cap, blob_per_rec=blob_per_rec, max_reqs=G, graph=not args.no_graph, p2p=not args.no_p2p)
+    scfg = spread_config(node_ids, cap, blob_per_rec=blob_per_rec, max_reqs=G, graph=not args.no_graph, p2p=args.p2p)
     engines = []
     for idx in local:
         n_in = int(member_of[:, idx].sum())
@@ -1192,10 +1193,29 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
         e = Engine(lib, cfg)
         e.create_groups(descs[member_of[:, idx]])
         engines.append(e)
+    transport = "p2p" if args.p2p else "nccl"
     if world > 1:
-        ids = [Spread.unique_id(lib) if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0, device=dev)
-        sp = Spread(lib, engines, scfg, rank=rank, unique_id=ids[0])
+        def make(cfg_):
+            ids = [Spread.unique_id(lib) if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0, device=dev)
+            try:
+                return Spread(lib, engines, cfg_, rank=rank, unique_id=ids[0]), 1
+            except Exception as ex:  # e.g. CUDA IPC not permitted on this box
+                print(f"[rank {rank}] spread group creation failed: {ex}", file=sys.stderr)
+                return None, 0
+        sp, ok = make(scfg)
+        t = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0 and args.p2p:  # every rank falls back to the NCCL bucket exchange together
+            if sp is not None:
+                sp.close()
+            transport = "nccl (peer-memory transport unavailable: fell back)"
+            scfg = spread_config(node_ids, cap, blob_per_rec=blob_per_rec, max_reqs=G, graph=not args.no_graph, p2p=False)
+            sp, ok = make(scfg)
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            raise SystemExit("could not create the spread group")
     else:
         sp = Spread(lib, engines, scfg)
     NB = 4
@@ -1335,12 +1355,12 @@ def run_spread_c(args, lib, dev, rank, world, G, R, P, K, W, metric, config):
                            "not flushed: one step's working set (%.0f MB per GPU) exceeds the 126 MB L2, steps run back to back" % ws_mb),
                     "placement": f"spread: {N} nodes, one single-lane engine per "
                     + (("GPU; the kernels store records straight into the peers' fixed-capacity receive buckets over NVLink "
-                        "(CUDA IPC; handles exchanged over NCCL), flag exchange per packet type" if not args.no_p2p else
+                        "(CUDA IPC; handles exchanged over NCCL), flag exchange per packet type" if transport == "p2p" else
                         "GPU; libgpx issues grouped ncclSend/ncclRecv of fixed-capacity buckets over NVLink")
                        if world > 1 else "node, all on ONE GPU")
                     + f"; replica j of a group on node (home+j) mod {N}; three record exchanges per round; "
                     + ("one CUDA graph launch per round" if not args.no_graph else "stream launches"),
-                    "nvlink_bytes_sent_per_gpu_per_step": link_bytes})
+                    "nvlink_bytes_sent_per_gpu_per_step": link_bytes, "transport": transport})
         ms = total_ms / K
         # algorithmic HBM bytes of one node's round: the phase pipeline's B_slot spread over the nodes
         bytes_round = G * b_slot(R, P)
