@@ -13,15 +13,19 @@
  *                 the L ACCEPT_REPLYs (maxCheckpointedSlot :1139-1143) are exchanged by shuffles and tallied in
  *                 registers (recordSlotNumber :809-825, getMedianMinus :867-875, majority at reply L/2); each thread
  *                 then writes only the durable outputs of its lane (log image + blob, decision image, EXEC record or
- *                 summary, window entry, acceptor row) and thread 0 the status, coordinator row and DECISION.
- *                 The ACCEPT record, the replies and the proposal never exist in memory.
+ *                 summary, window entry, acceptor row) and thread 0 the status and the coordinator row.
+ *                 The ACCEPT record, the replies, the DECISION and the proposal never exist in memory.  Block 0 writes
+ *                 the segment headers and the NEXT launch's log positions (double-buffered by launch parity,
+ *                 gpx_dev.cuh): no ticket, no fence, no publisher behind the kernel.
  *   k_round_slow  everything else (several requests of a group in the batch -> one batched slot, STOP, outstanding
- *                 proposals, a pre-active / missing / remote coordinator, an occupied window entry, NACKs): teams
- *                 that cannot take the in-order path append their request index to a todo list; this kernel runs
- *                 the general code over it (thread 0 of the team: propose_run / tally_reply against memory, decision
- *                 broadcast to the lanes by shuffles, accept_lane / commit per lane), publishes the ring heads and
- *                 the round's control block.  It is launched behind k_round with programmatic stream
- *                 serialization and returns at once when the list is empty.
+ *                 proposals, a pre-active / missing / remote coordinator, an occupied window entry, a queued commit,
+ *                 NACKs): teams that cannot take the in-order path append their request index to a todo list, and the
+ *                 FIRST of them launches this kernel from the device as a tail launch (it starts when k_round has
+ *                 completed and before anything else on the stream) -- a round without such runs is a single kernel;
+ *                 gpx_set_round_mode(2) makes the host launch it behind every k_round instead.  Three grid-wide
+ *                 phases separated by grid barriers: propose (one thread per run), blobs of batched slots + VOID
+ *                 outputs (one thread per request of those runs), accept x L / tally / commit x L (one team per run:
+ *                 propose_run / tally_reply against memory, decision broadcast to the lanes by shuffles).
  *
  * Semantics are those of gpx_propose followed by gpx_handle_accepts_fused (checked by the test-suite); record,
  * image and EXEC indices are REQUEST indices (holes are VOID).

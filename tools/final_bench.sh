@@ -1,23 +1,24 @@
 #!/bin/bash
-# default bench line, the reference arm and the 1M-group workloads; summaries on stdout, JSON lines under gpurun_out/
+# round-2 bench lines on ONE GPU (under gpurun): default (cfg2), the reference arm, 1 M groups, cfg4, cfg5, spread with
+# four nodes on one GPU; JSON lines under gpurun_out/, a one-line summary each on stdout.  Multi-GPU lines:
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29500 \
+#       bench.py --gpus N [--workload cfg3] [--p2p] [--placement packed]
 mkdir -p gpurun_out
-timeout 500 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-tail -2 gpurun_out/bench_default.err | cut -c1-300
-timeout 300 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-for w in 1m1b cfg3; do timeout 300 python bench.py --workload $w --skip-cpu > gpurun_out/bench_$w.json 2>/dev/null; done
-python - <<'PY'
-import json
-d = json.load(open("gpurun_out/bench_default.json"))
-print("cfg2", d["value"] / 1e9, d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["kernel_ms"], d["roofline_accept"]["frac"])
-l = d["roofline_1m_groups"]
-print("1m ctx", l["k_round"], l["k_accept"]["frac"])
-e = d["e2e"]
-print("e2e", e["value"] / 1e9, e["ms_per_step"], e["p50_decide_latency_ms"], e["sync_full"]["value"] / 1e9)
-print("cpu", d["cpu_baseline"]["value"] / 1e6, d["clocks"], d["gpu_launches"], d["p50_decide_latency_ms"])
-r = json.load(open("gpurun_out/bench_ref.json"))
-print("ref", r["value"] / 1e6, r["cpu_baseline"]["cores"])
-for w in ("1m1b", "cfg3"):
-    d = json.load(open("gpurun_out/bench_%s.json" % w))
-    print(w, d["value"] / 1e9, d["ms_per_step"], d["roofline"]["frac"], d["roofline_accept"]["frac"], d["e2e"]["value"] / 1e9,
-          d["roofline_accept"]["phase_pipeline_decisions_per_sec"] / 1e9)
+run() { name=$1; shift; timeout 400 python bench.py "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; python - "$name" <<'PY'
+import json, sys
+n = sys.argv[1]
+try:
+    d = json.load(open(f"gpurun_out/bench_{n}.json"))
+    e = d.get("e2e") or {}
+    print(n, "value %.3f G" % (d["value"] / 1e9), "ms %.4f" % d["ms_per_step"], "frac %.3f" % (d.get("roofline") or {}).get("frac", 0),
+          "e2e %.3f G" % (e.get("value", 0) / 1e9))
+except Exception as ex:
+    print(n, "FAILED", ex)
 PY
+}
+run default
+run ref --impl reference
+run 1m1b --workload 1m1b --skip-cpu
+run cfg4 --workload cfg4 --skip-cpu --steps 10
+run cfg5 --workload cfg5 --skip-cpu --steps 10
+run spread_local --placement spread --skip-cpu --steps 10
