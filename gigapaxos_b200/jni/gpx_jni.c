@@ -103,6 +103,62 @@ JNIEXPORT jint JNICALL GPX_JNI(logRelease)(JNIEnv* env, jclass cls, jlong h, jin
   return gpx_log_release((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint64_t)upto);
 }
 
+/* The per-packet-type entry points: what PaxosInstanceStateMachine.handlePaxosMessage :423 (switch :498-558)
+ * dispatches to, one call per batch of same-type packets (PaxosPacketBatcher / PaxosManager.handleIncomingPacket hand
+ * them over demuxed).  An adapter that keeps the reference's messenger between replicas uses these, not roundSubmit.
+ *   REQUEST / PROPOSAL -> propose            (PISM.handleProposal :818, PaxosCoordinatorState.propose :233)
+ *   ACCEPT             -> handleAccepts      (PISM.handleAccept :1080, PaxosAcceptor.acceptAndUpdateBallot :302)
+ *   ACCEPT_REPLY       -> handleAcceptReplies(PISM.handleAcceptReply :1248, PaxosCoordinatorState.handleAcceptReplyMyBallot :597)
+ *   DECISION           -> handleDecisions    (PISM.handleCommittedRequest :1432, extractExecuteAndCheckpoint :1619)
+ *   PREPARE            -> handlePrepares     (PISM.handlePrepare :900, PaxosAcceptor.handlePrepare :239)
+ * counts come back through a direct IntBuffer / LongBuffer of one element. */
+JNIEXPORT jint JNICALL GPX_JNI(propose)(JNIEnv* env, jclass cls, jlong h, jint n, jobject reqs, jobject payload,
+                                        jlong payload_bytes, jobject out_accepts, jobject n_accepts, jobject out_blob,
+                                        jobject blob_bytes, jobject status) {
+  jlong cap = out_blob ? (*env)->GetDirectBufferCapacity(env, out_blob) : 0;
+  return gpx_propose((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_request_rec*)buf(env, reqs),
+                     (const uint8_t*)buf(env, payload), (uint64_t)payload_bytes, (gpx_accept_rec*)buf(env, out_accepts),
+                     (uint32_t*)buf(env, n_accepts), (uint8_t*)buf(env, out_blob), (uint64_t)cap,
+                     (uint64_t*)buf(env, blob_bytes), (int32_t*)buf(env, status));
+}
+JNIEXPORT jint JNICALL GPX_JNI(handleAccepts)(JNIEnv* env, jclass cls, jlong h, jint n, jobject accepts, jobject blob,
+                                              jlong blob_bytes, jobject out_replies, jobject out_extra, jint extra_cap,
+                                              jobject n_extra) {
+  return gpx_handle_accepts((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_accept_rec*)buf(env, accepts),
+                            (const uint8_t*)buf(env, blob), (uint64_t)blob_bytes, (gpx_accept_reply_rec*)buf(env, out_replies),
+                            (gpx_exec_rec*)buf(env, out_extra), (uint32_t)extra_cap, (uint32_t*)buf(env, n_extra));
+}
+JNIEXPORT jint JNICALL GPX_JNI(handleAcceptReplies)(JNIEnv* env, jclass cls, jlong h, jint n, jobject replies,
+                                                    jobject out_decisions, jobject n_decisions) {
+  return gpx_handle_accept_replies((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_accept_reply_rec*)buf(env, replies),
+                                   (gpx_decision_rec*)buf(env, out_decisions), (uint32_t*)buf(env, n_decisions));
+}
+JNIEXPORT jint JNICALL GPX_JNI(handleDecisions)(JNIEnv* env, jclass cls, jlong h, jint n, jobject decisions,
+                                                jobject out_exec, jobject out_extra, jint extra_cap, jobject n_extra) {
+  return gpx_handle_decisions((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_decision_rec*)buf(env, decisions),
+                              (gpx_exec_rec*)buf(env, out_exec), (gpx_exec_rec*)buf(env, out_extra), (uint32_t)extra_cap,
+                              (uint32_t*)buf(env, n_extra));
+}
+JNIEXPORT jint JNICALL GPX_JNI(handlePrepares)(JNIEnv* env, jclass cls, jlong h, jint n, jobject prepares, jobject out_replies) {
+  return gpx_handle_prepares((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_pvalue_hdr*)buf(env, prepares),
+                             (gpx_prepare_reply_rec*)buf(env, out_replies));
+}
+/* long logRead(long h, int lane, long from, ByteBuffer dst, long[] out {nCopied, head}): the synchronous journal read
+ * (recovery / tests); the steady state uses logDrainAsync */
+JNIEXPORT jint JNICALL GPX_JNI(logRead)(JNIEnv* env, jclass cls, jlong h, jint lane, jlong from, jobject dst, jlongArray out) {
+  uint64_t nc = 0, head = 0;
+  jlong cap = dst ? (*env)->GetDirectBufferCapacity(env, dst) : 0;
+  int rc = gpx_log_read((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint64_t)from, buf(env, dst), (uint64_t)cap, &nc, &head);
+  jlong v[2] = {(jlong)nc, (jlong)head};
+  (*env)->SetLongArrayRegion(env, out, 0, 2, v);
+  return rc;
+}
+/* PaxosInstanceStateMachine.getCPI / roundRobinCoordinator and String.hashCode, for an adapter that wants the engine's
+ * arithmetic rather than its own (they are bit-identical: tests/test_oracle.py) */
+JNIEXPORT jint JNICALL GPX_JNI(getCpi)(JNIEnv* env, jclass cls, jint cpi, jdouble noise, jint name_hash) {
+  return gpx_get_cpi(cpi, noise, name_hash);
+}
+
 /* spread placement (one JVM per GPU): long spreadCreate(long h, ByteBuffer cfg, int rank, ByteBuffer ncclId128) */
 JNIEXPORT jint JNICALL GPX_JNI(spreadUniqueId)(JNIEnv* env, jclass cls, jobject id128) { return gpx_spread_unique_id(buf(env, id128)); }
 JNIEXPORT jlong JNICALL GPX_JNI(spreadCreate)(JNIEnv* env, jclass cls, jlong h, jobject cfg, jint rank, jobject id128) {
@@ -115,6 +171,15 @@ JNIEXPORT jlong JNICALL GPX_JNI(spreadCreate)(JNIEnv* env, jclass cls, jlong h, 
  * request staging and result buffers in device memory and moves them with its own cudaMemcpyAsync calls) */
 JNIEXPORT jint JNICALL GPX_JNI(spreadRound)(JNIEnv* env, jclass cls, jlong sp, jobject io, jlong stream) {
   return gpx_spread_round((gpx_spread*)(intptr_t)sp, (const gpx_spread_io*)buf(env, io), (void*)(intptr_t)stream);
+}
+JNIEXPORT jint JNICALL GPX_JNI(spreadPlanNode)(JNIEnv* env, jclass cls, jobject cfg, jint rank, jobject out_plan) {
+  return gpx_spread_plan_node((const gpx_spread_config*)buf(env, cfg), (uint32_t)rank, (gpx_spread_plan*)buf(env, out_plan));
+}
+/* long spreadDropped(long sp, int localIndex): records a bucket could not hold (0 in a correctly sized plan) */
+JNIEXPORT jlong JNICALL GPX_JNI(spreadDropped)(JNIEnv* env, jclass cls, jlong sp, jint local_index) {
+  uint32_t d = 0;
+  int rc = gpx_spread_dropped((gpx_spread*)(intptr_t)sp, (uint32_t)local_index, &d);
+  return rc == GPX_OK ? (jlong)d : (jlong)rc;
 }
 JNIEXPORT void JNICALL GPX_JNI(spreadDestroy)(JNIEnv* env, jclass cls, jlong sp) { gpx_spread_destroy((gpx_spread*)(intptr_t)sp); }
 
