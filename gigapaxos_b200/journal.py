@@ -88,20 +88,20 @@ def decision_json(paxos_id: str, version: int, slot: int, bnum: int, bcoord: int
          "GC_S": int(median_cp), "S": int(slot), "QID": int(request_id), "ET": int(entry_time), "E": int(entry_replica)}
     if stop:
         d["STOP"] = True
-    return json.dumps(d, separators=(",", ":")).encode("utf-8")
+    return json.dumps(d, separators=(",", ":")).encode("ascii")  # non-ASCII as \uXXXX escapes: charset-neutral
 
 
 def prepare_json(paxos_id: str, version: int, bnum: int, bcoord: int, first_undecided_slot: int) -> bytes:
     d = {"type": PT_PAXOS_PACKET, "PT": PT_PREPARE, "ID": paxos_id, "V": int(version), "B": f"{int(bnum)}:{int(bcoord)}",
          "PREP_MIN": int(first_undecided_slot)}
-    return json.dumps(d, separators=(",", ":")).encode("utf-8")
+    return json.dumps(d, separators=(",", ":")).encode("ascii")  # non-ASCII as \uXXXX escapes: charset-neutral
 
 
 def parse_packet(pkt: bytes) -> dict:
     """One journaled packet, the way the reference's reader tells them apart (SQLPaxosLogger: a byteified packet starts
     with the int PAXOS_PACKET type, a stringified one with '{'): {"kind": "ACCEPT" | "DECISION" | "PREPARE", ...}"""
     if pkt[:1] == b"{":
-        j = json.loads(pkt.decode("utf-8"))
+        j = json.loads(pkt.decode("iso-8859-1"))  # SQLPaxosLogger.CHARSET :1313 (a Java-written frame may hold raw bytes)
         assert j["type"] == PT_PAXOS_PACKET
         bn, bc = (int(x) for x in j["B"].split(":"))
         if j["PT"] == PT_DECISION:

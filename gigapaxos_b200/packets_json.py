@@ -1,0 +1,246 @@
+"""The inter-replica packets the reference sends STRINGIFIED, and the cross-group packet batcher.
+
+Four packet types travel byteified (REQUEST, ACCEPT, BATCHED_ACCEPT_REPLY, BATCHED_COMMIT: include/gpx_wire.h,
+paxosutil/PaxosMessenger.java:126-132, paxosutil/PaxosPacketDemultiplexerFast.java:82-95); everything else a gpx-backed
+node exchanges with a Java peer is the JSON string of PaxosPacket.toJSONObject() (paxospackets/PaxosPacket.java:478-494:
+{"type": 90, "PT": <type>, "ID": paxosID, "V": version} + the subclass's toJSONObjectImpl()).  Node ids are integers
+(IntegerMap.allInt(), which byteification requires as well: PaxosMessenger.java:127, :187).  This module holds the ones
+the phase-2 path produces besides the DECISION / PREPARE forms of journal.py:
+
+  ACCEPT_REPLY (8), singleton   a NACK (higher ballot) or an undigest request is never coalesced into a
+                                BatchedAcceptReply (PaxosPacketBatcher.allPositiveAcceptReplies :423-430); AcceptReplyPacket
+                                .toJSONObjectImpl :196-206
+  BATCHED_ACCEPT (36)           digest mode: the coordinator's ACCEPTs of one (paxosID, ballot) as slot -> digest and
+                                slot -> requestID maps; BatchedAccept.toJSONObjectImpl :99-146, merge rule addBatchedAccept
+                                :194-209 (wrap-aware max of medianCheckpointedSlot, TreeMap.putAll)
+  BATCHED_PAXOS_PACKET (37)     PaxosPacketBatcher.batch :280-303: the messaging tasks of one batcher sweep grouped by
+                                recipient set (first-seen order: LinkedHashMap), each group's packets in one
+                                {"PP": [...]} wrapper; BatchedPaxosPacket.toJSONObjectImpl :77-84.  process() :270-277 does
+                                this only when BATCH_ACROSS_GROUPS and more than MIN_PP_BATCH_SIZE (3) tasks are pending;
+                                the receiver unwraps (PaxosManager.java:1087-1090).
+
+Key order inside a JSON object is not significant (org.json / json-smart objects are hash maps).
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, Iterable, List, Sequence, Tuple, Union
+
+PT_PREPARE, PT_ACCEPT, PT_DECISION, PT_ACCEPT_REPLY = 2, 3, 6, 8
+PT_BATCHED_ACCEPT, PT_BATCHED_PAXOS_PACKET, PT_PAXOS_PACKET = 36, 37, 90  # PaxosPacket.PaxosPacketType :202-291
+CHARSET = "iso-8859-1"  # PaxosPacket.CHARSET :439, BatchedAccept.CHARSET :36
+
+BATCH_ACROSS_GROUPS = True  # PaxosConfig.java:807
+MIN_PP_BATCH_SIZE = 3  # PaxosConfig.java:860
+
+
+def _dumps(d: dict) -> bytes:
+    """Strings leave a Java node as String.getBytes("ISO-8859-1") (nio/MessageNIOTransport.java:524, JSONMessenger.java:463;
+    the journal: SQLPaxosLogger.java:1094, CHARSET :1313).  Every non-ASCII character is written as a \\uXXXX escape here,
+    so the bytes are the same under any charset and every JSON parser reads back the same characters; frames a Java node
+    wrote may hold raw ISO-8859-1 bytes, so the reading side decodes with that charset."""
+    return json.dumps(d, separators=(",", ":")).encode("ascii")
+
+
+def _loads(b: bytes) -> dict:
+    return json.loads(b.decode(CHARSET))
+
+
+def _base(pt: int, paxos_id, version: int) -> dict:
+    d = {"type": PT_PAXOS_PACKET, "PT": pt}
+    if paxos_id is not None:  # JSONObject.put(key, null) removes the key
+        d["ID"] = paxos_id
+    d["V"] = int(version)
+    return d
+
+
+def _i32(x: int) -> int:
+    return ((int(x) + (1 << 31)) & 0xFFFFFFFF) - (1 << 31)
+
+
+# ---- ACCEPT_REPLY ---------------------------------------------------------------------------------------------------
+def accept_reply_json(paxos_id: str, version: int, acceptor: int, bnum: int, bcoord: int, slot_number: int,
+                      max_checkpointed_slot: int, request_id: int, undigest_request: bool = False) -> bytes:
+    d = _base(PT_ACCEPT_REPLY, paxos_id, version)
+    d.update({"SNDR": int(acceptor), "B": f"{int(bnum)}:{int(bcoord)}", "S": int(slot_number),
+              "CP_S": int(max_checkpointed_slot), "QID": int(request_id)})
+    if undigest_request:
+        d["NACK"] = True
+    return _dumps(d)
+
+
+def accept_replies_to_packets(replies, names: Dict[int, Tuple[str, int]], node_of_lane: Sequence[int]) -> List[bytes]:
+    """The singleton ACCEPT_REPLYs among engine reply records (abi.reply_dtype): the NACKs, i.e. replies whose ballot is
+    above the ACCEPT's own (PISM.handleAccept :1139-1142 answers with the acceptor's ballot).  Positive replies go into
+    gpx_wire_encode_batched_accept_reply instead.  names: gid -> (paxosID, version)."""
+    from . import abi
+    out = []
+    for r in replies:
+        who = int(r["who"])
+        if (who >> 16) & abi.F_VOID or not (who >> 16) & abi.F_NACK:
+            continue
+        pid, ver = names[int(r["gid"])]
+        out.append(accept_reply_json(pid, ver, node_of_lane[who & 0xFF], int(r["bnum"]), int(r["bcoord"]),
+                                     int(r["slot"]), int(r["max_cp"]), int(r["req_id"])))
+    return out
+
+
+# ---- BATCHED_ACCEPT -------------------------------------------------------------------------------------------------
+class BatchedAccept:
+    """paxospackets/BatchedAccept.java: the digested ACCEPTs of one (paxosID, version, ballot) to one group"""
+
+    def __init__(self, paxos_id: str, version: int, bnum: int, bcoord: int, median_cp: int, group: Iterable[int]):
+        self.paxos_id, self.version, self.bnum, self.bcoord = paxos_id, int(version), int(bnum), int(bcoord)
+        self.median_cp = int(median_cp)
+        self.group = sorted(set(int(g) for g in group))
+        self.slot_digests: Dict[int, bytes] = {}
+        self.slot_request_ids: Dict[int, int] = {}
+
+    def add_accept(self, slot: int, digest: bytes, request_id: int, median_cp: int, bnum=None, bcoord=None,
+                   paxos_id=None):  # addAccept :229-241
+        if (bnum is not None and (int(bnum), int(bcoord)) != (self.bnum, self.bcoord)) or \
+                (paxos_id is not None and paxos_id != self.paxos_id):
+            raise RuntimeError("Unable to combine accepts of different ballots / groups")
+        if _i32(int(median_cp) - self.median_cp) > 0:  # wrap-aware max
+            self.median_cp = int(median_cp)
+        self.slot_digests[int(slot)] = bytes(digest)
+        self.slot_request_ids[int(slot)] = int(request_id)
+        return self
+
+    def add_batched_accept(self, other: "BatchedAccept") -> bool:  # addBatchedAccept :194-209
+        if (other.bnum, other.bcoord) != (self.bnum, self.bcoord) or other.paxos_id != self.paxos_id:
+            raise RuntimeError("Unable to combine batched accepts of different ballots / groups")
+        if _i32(other.median_cp - self.median_cp) > 0:
+            self.median_cp = other.median_cp
+        self.slot_digests.update(other.slot_digests)
+        self.slot_request_ids.update(other.slot_request_ids)
+        return True
+
+    def slots(self) -> List[int]:  # TreeMap<Integer,..>: natural (signed) order
+        return sorted(self.slot_digests)
+
+    def to_json(self) -> bytes:
+        d = _base(PT_BATCHED_ACCEPT, self.paxos_id, self.version)
+        d.update({"B": f"{self.bnum}:{self.bcoord}", "GC_S": self.median_cp, "GROUP": list(self.group),
+                  "S_DIGS": [[s, self.slot_digests[s].decode(CHARSET)] for s in self.slots()],
+                  "S_QIDS": [[s, self.slot_request_ids[s]] for s in sorted(self.slot_request_ids)]})
+        return _dumps(d)
+
+    @staticmethod
+    def from_json(j: Union[bytes, dict]) -> "BatchedAccept":
+        if not isinstance(j, dict):
+            j = _loads(j)
+        assert j["type"] == PT_PAXOS_PACKET and j["PT"] == PT_BATCHED_ACCEPT
+        bn, bc = (int(x) for x in j["B"].split(":"))
+        b = BatchedAccept(j["ID"], j["V"], bn, bc, j["GC_S"], j["GROUP"])
+        for s, dig in j["S_DIGS"]:
+            b.slot_digests[int(s)] = dig.encode(CHARSET)
+        for s, q in j["S_QIDS"]:
+            b.slot_request_ids[int(s)] = int(q)
+        return b
+
+    def to_digested_accepts(self, gid: int, sender_lane: int, value_len: int = 0):
+        """the engine-side form: one digests.DigestedAccept per slot (PISM.handleBatchedAccept :1183-1210 unrolls a
+        BatchedAccept into per-slot ACCEPTs that PendingDigests.match joins with the request bodies)"""
+        import numpy as np
+        from . import abi
+        from .digests import DigestedAccept
+        out = []
+        for s in self.slots():
+            r = np.zeros((), dtype=abi.accept_dtype)
+            r["gid"], r["slot"], r["bnum"], r["bcoord"] = gid, s, self.bnum, self.bcoord
+            r["median_cp"], r["req_id"], r["nreq"], r["sender"] = self.median_cp, self.slot_request_ids[s], 1, sender_lane
+            out.append(DigestedAccept(r, self.slot_digests[s], value_len))
+        return out
+
+
+def batch_digested_accepts(accs, names: Dict[int, Tuple[str, int]], groups: Dict[int, Sequence[int]]) -> List[BatchedAccept]:
+    """PaxosPacketBatcher.enqueueImpl(BatchedAccept) :158-173: digested ACCEPTs (digests.DigestedAccept) of a sweep merged
+    per (paxosID, ballot), first-seen order"""
+    merged: Dict[Tuple[str, int, int], BatchedAccept] = {}
+    for a in accs:
+        r = a.rec
+        pid, ver = names[int(r["gid"])]
+        key = (pid, int(r["bnum"]), int(r["bcoord"]))
+        if key not in merged:
+            merged[key] = BatchedAccept(pid, ver, key[1], key[2], int(r["median_cp"]), groups[int(r["gid"])])
+        merged[key].add_accept(int(r["slot"]), a.digest, int(r["req_id"]), int(r["median_cp"]))
+    return list(merged.values())
+
+
+# ---- BATCHED_PAXOS_PACKET ------------------------------------------------------------------------------------------
+Packet = Union[bytes, dict]
+"""a packet on its way out: byteified (bytes not starting with '{'), a JSON string (bytes starting with '{') or a dict"""
+
+
+def _as_obj(p: Packet):
+    if isinstance(p, dict):
+        return p
+    if p[:1] == b"{":
+        return _loads(p)
+    raise ValueError("a BatchedPaxosPacket holds JSON packets: byteified packets are sent on their own "
+                     "(BatchedPaxosPacket.toJSONObjectImpl calls toJSONObject on every member)")
+
+
+def batched_paxos_packet_json(packets: Sequence[Packet]) -> bytes:
+    """BatchedPaxosPacket: paxosID null (the key is absent), version -1 (PaxosPacket((PaxosPacket) null) :399-405)"""
+    assert len(packets) > 0
+    d = _base(PT_BATCHED_PAXOS_PACKET, None, -1)
+    d["PP"] = [_as_obj(p) for p in packets]
+    return _dumps(d)
+
+
+def unbatch(packet: bytes) -> List[dict]:
+    """PaxosManager.handleIncomingPacket :1087-1090: the member packets of a BATCHED_PAXOS_PACKET (any other JSON packet:
+    itself)"""
+    j = _loads(packet)
+    assert j["type"] == PT_PAXOS_PACKET
+    return list(j["PP"]) if j["PT"] == PT_BATCHED_PAXOS_PACKET else [j]
+
+
+MessagingTask = Tuple[Sequence[int], Sequence[Packet]]
+"""(recipients, msgs) -- paxosutil/MessagingTask"""
+
+
+def batch_messaging_tasks(tasks: Sequence[MessagingTask], batch_across_groups: bool = BATCH_ACROSS_GROUPS,
+                          min_pp_batch_size: int = MIN_PP_BATCH_SIZE) -> List[Tuple[List[int], List[bytes]]]:
+    """PaxosPacketBatcher.process :270-277 + batch :280-303.  Returns (recipients, [wire messages]) per send.  Byteified
+    members of a group of tasks cannot ride in the JSON wrapper; they are sent beside it, as the messenger does for a
+    MessagingTask whose packets are Byteable (PaxosMessenger.toObjects :156-166)."""
+    live = [(list(r), list(m)) for r, m in tasks if r is not None and len(r) and m is not None and len(m)]
+    if not (batch_across_groups and len(tasks) > min_pp_batch_size):
+        return [(r, [p if isinstance(p, bytes) else _dumps(p) for p in m]) for r, m in live]
+    grouped: Dict[frozenset, List[Packet]] = {}
+    for r, m in live:  # dict preserves first-seen order like the LinkedHashMap
+        grouped.setdefault(frozenset(int(x) for x in r), []).extend(m)
+    out = []
+    for group, msgs in grouped.items():
+        js = [p for p in msgs if isinstance(p, dict) or p[:1] == b"{"]
+        raw = [p for p in msgs if not (isinstance(p, dict) or p[:1] == b"{")]
+        wire = list(raw)
+        if js:
+            wire.append(batched_paxos_packet_json(js))
+        out.append((sorted(group), wire))
+    return out
+
+
+def parse_packet(pkt: bytes) -> dict:
+    """journal.parse_packet extended by the types above: {"kind": ...}"""
+    from . import journal
+    if pkt[:1] != b"{":
+        return journal.parse_packet(pkt)
+    j = _loads(pkt)
+    pt = j["PT"]
+    if pt == PT_ACCEPT_REPLY:
+        bn, bc = (int(x) for x in j["B"].split(":"))
+        return {"kind": "ACCEPT_REPLY", "paxos_id": j["ID"], "version": j["V"], "acceptor": j["SNDR"], "bnum": bn,
+                "bcoord": bc, "slot_number": j["S"], "max_checkpointed_slot": j["CP_S"], "request_id": j["QID"],
+                "undigest_request": bool(j.get("NACK", False))}
+    if pt == PT_BATCHED_ACCEPT:
+        b = BatchedAccept.from_json(j)
+        return {"kind": "BATCHED_ACCEPT", "paxos_id": b.paxos_id, "version": b.version, "bnum": b.bnum, "bcoord": b.bcoord,
+                "median_cp": b.median_cp, "group": b.group, "slot_digests": dict(b.slot_digests),
+                "slot_request_ids": dict(b.slot_request_ids)}
+    if pt == PT_BATCHED_PAXOS_PACKET:
+        return {"kind": "BATCHED_PAXOS_PACKET", "packets": [parse_packet(_dumps(p)) for p in j["PP"]]}
+    return journal.parse_packet(pkt)
