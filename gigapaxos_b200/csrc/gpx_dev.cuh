@@ -111,7 +111,7 @@ struct DevState {
   uint32_t lp;                   /* which copy this launch reads */
   unsigned long long* cur_seg;   /* [L] segment bases of the round in flight (k_round -> k_round_slow) */
   unsigned long long* ctr;       /* [GPX_CTR_STRIPES][C_NCTR] */
-  unsigned int* tickets;         /* [8] last-block tickets, one per kernel kind */
+  unsigned int* tickets;         /* [8] words 6..7: the grid barrier of k_round_slow (the rest is unused since log_pos) */
   int32_t lane_node[GPX_MAX_LANES];
   int32_t cpi_const;
   int32_t cpi_per_group; /* CPI_NOISE != 0 */

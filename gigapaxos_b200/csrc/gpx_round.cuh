@@ -338,7 +338,8 @@ __global__ void k_round_slow(const __grid_constant__ DevState S, const __grid_co
  * dependent levels (request -> rows of the group -> window entry / nodeSlotNumbers), and a team either takes
  * the in-order fast path or hands its request index to k_round_slow -- which the first such team launches from the
  * device as a tail launch, so that a round without left-over runs is ONE launch on the stream.  The ring heads are
- * advanced by the block that draws the last ARRIVAL ticket: warps retire right after their last store, no fence.
+ * published by block 0 into the other copy of log_pos (see DevState): warps retire right after their last store, no
+ * fence, no arrival count.
  */
 template <int L, int LP, bool DEF>
 __global__ void __launch_bounds__(GPX_RBLOCK, GPX_ROUND_MINB * (256 / GPX_RBLOCK)) k_round(const __grid_constant__ DevState S,
