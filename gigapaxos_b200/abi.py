@@ -52,7 +52,20 @@ prepare_reply_dtype = np.dtype([("gid", "<u4"), ("first_slot", "<i4"), ("bnum", 
                                 ("n_accepted", "<u4"), ("reserved", "<i8"),
                                 ("accepted", accepted_pvalue_dtype, (GPX_MAX_WINDOW,))])
 assert prepare_reply_dtype.itemsize == 32 + 32 * GPX_MAX_WINDOW
-F_PREPARE, F_FROM_LOG = 0x200, 0x400
+F_PREPARE, F_FROM_LOG, F_MORE = 0x200, 0x400, 0x800
+# phase 1b (gpx_handle_prepare_replies)
+GPX_MAX_CARRY, GPX_MAX_PLAN = 32, 16
+EL_WAITING, EL_MAJORITY, EL_PREEMPTED, EL_DROPPED, EL_OVERFLOW = 0, 1, 2, 3, 4
+CO_NOOP, CO_PVALUE, CO_STOP_NEW = 0, 1, 2
+ELF_STOP_ORDER = 1
+election_dtype = np.dtype([("gid", "<u4"), ("lane", "<u4"), ("bnum", "<i4"), ("bcoord", "<i4"), ("slot", "<i4"),
+                           ("first_reply", "<u4"), ("n_replies", "<u4"), ("reserved", "<u4")])
+carryover_dtype = np.dtype([("slot", "<i4"), ("kind", "<u4"), ("src_reply", "<u4"), ("reserved", "<u4"),
+                            ("pv", accepted_pvalue_dtype)])
+election_out_dtype = np.dtype([("gid", "<u4"), ("verdict", "<i4"), ("next_slot", "<i4"), ("n_plan", "<u2"),
+                               ("flags", "<u2"), ("node_slots", "<i4", (GPX_MAX_GROUP_SIZE,)),
+                               ("plan", carryover_dtype, (GPX_MAX_PLAN + 1,))])
+assert election_dtype.itemsize == 32 and carryover_dtype.itemsize == 48 and election_out_dtype.itemsize == 896
 exec_sum_dtype = np.dtype([("slot", "<i4"), ("lane_mask", "u1"), ("flags", "u1"), ("nreq", "<u2")])
 ROUND_COMPACT = 1
 ROUND_PACKED_REQS = 2
@@ -323,6 +336,17 @@ class Engine:
         out = np.zeros(max(n * self.n_lanes, 1), dtype=prepare_reply_dtype)
         self.L.check(self.L.fn("handle_prepares")(self._h, C.c_uint32(n), _ptr(prepares), _ptr(out)))
         return out[: n * self.n_lanes]
+
+    def handle_prepare_replies(self, elections: np.ndarray, replies: np.ndarray) -> np.ndarray:
+        """Phase 1b for a batch of elections (PISM.handlePrepareReply :1017-1068 and what follows a majority:
+        carry-over, no-op fill, processStop, the coordinator installed ACTIVE).  Returns election_out records."""
+        elections = np.ascontiguousarray(elections, dtype=election_dtype)
+        replies = np.ascontiguousarray(replies, dtype=prepare_reply_dtype)
+        n = len(elections)
+        out = np.zeros(max(n, 1), dtype=election_out_dtype)
+        self.L.check(self.L.fn("handle_prepare_replies")(self._h, C.c_uint32(n), _ptr(elections), C.c_uint32(len(replies)),
+                                                         _ptr(replies), _ptr(out)))
+        return out[:n]
 
     def handle_accepts_fused(self, accepts: np.ndarray, blob: np.ndarray, extra_cap: int = 4096):
         accepts = np.ascontiguousarray(accepts, dtype=accept_dtype)

@@ -136,6 +136,32 @@ __device__ __forceinline__ size_t ns_idx(const DevState& S, uint32_t l, uint32_t
   return ((size_t)l * S.Rcap + r) * S.G + gid;
 }
 
+/* PISM :456-460: only an ACTIVE acceptor handles packets */
+__device__ __forceinline__ bool st_usable(uint32_t aux) {
+  uint32_t st = GPX_AUX_STATE(aux);
+  return st == GPX_ST_ACTIVE_1 || st == GPX_ST_ACTIVE_2;
+}
+
+/* member set, replica count and liveness of one group */
+struct GroupCtx {
+  uint32_t R;
+  const MsetInfo* ms;
+  bool live;
+};
+__device__ __forceinline__ GroupCtx group_ctx(const DevState& S, uint32_t gid) {
+  GroupCtx g;
+  g.R = 0;
+  g.ms = nullptr;
+  g.live = false;
+  if (gid < S.G) {
+    const uint32_t meta = S.grp_meta[gid];
+    g.ms = &S.msets[meta & 0xffffu];
+    g.R = (meta >> 16) & 0xffu;
+    g.live = (meta & GPX_META_LIVE) != 0;
+  }
+  return g;
+}
+
 __device__ __forceinline__ int4 ldg4(const void* p) { return *reinterpret_cast<const int4*>(p); }
 __device__ __forceinline__ void stg4(void* p, int4 v) { *reinterpret_cast<int4*>(p) = v; }
 /* streaming (read-once) 128-bit load: records and payloads are consumed exactly once */

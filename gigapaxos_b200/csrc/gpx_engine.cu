@@ -23,6 +23,7 @@
 #include "gpx_route.cuh"
 #include "gpx_spread.cuh"
 #include "gpx_prepare.cuh"
+#include "gpx_phase1b.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -908,6 +909,44 @@ int gpx_handle_prepares(gpx_engine* e, uint32_t n, const gpx_pvalue_hdr* prepare
   log_flip(e);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_replies, e->d_misc, out_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GPX_OK;
+}
+
+/* phase 1b for a batch of elections: one launch of k_prepare_tally (gpx_phase1b.cuh) */
+int gpx_handle_prepare_replies(gpx_engine* e, uint32_t n, const gpx_election_rec* elections, uint32_t n_reply_recs,
+                               const gpx_prepare_reply_rec* replies, gpx_election_out* out) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!elections || !out || (!replies && n_reply_recs)) return fail(GPX_EINVAL, "null argument");
+  {
+    std::vector<uint32_t> gids(n);
+    for (uint32_t i = 0; i < n; i++) {
+      if ((uint64_t)elections[i].first_reply + elections[i].n_replies > n_reply_recs)
+        return fail(GPX_ERANGE, "election refers to replies beyond n_reply_recs");
+      gids[i] = elections[i].gid;
+    }
+    std::sort(gids.begin(), gids.end());
+    if (std::adjacent_find(gids.begin(), gids.end()) != gids.end())
+      return fail(GPX_EINVAL, "more than one election for a group in one call");
+  }
+  const size_t el_bytes = (size_t)n * sizeof(gpx_election_rec);
+  const size_t rep_bytes = (size_t)n_reply_recs * sizeof(gpx_prepare_reply_rec);
+  const size_t out_bytes = (size_t)n * sizeof(gpx_election_out);
+  int rc = e->ensure_misc(el_bytes + rep_bytes + out_bytes);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  uint8_t* base = (uint8_t*)e->d_misc;
+  CK(cudaMemcpyAsync(base, elections, el_bytes, cudaMemcpyHostToDevice, st));
+  if (rep_bytes) CK(cudaMemcpyAsync(base + el_bytes, replies, rep_bytes, cudaMemcpyHostToDevice, st));
+  Phase1bArgs A;
+  A.els = (const gpx_election_rec*)base;
+  A.n = n;
+  A.replies = (const gpx_prepare_reply_rec*)(base + el_bytes);
+  A.out = (gpx_election_out*)(base + el_bytes + rep_bytes);
+  k_prepare_tally<<<cdiv(n, GPX_P1B_BLOCK), GPX_P1B_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, A.out, out_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return GPX_OK;
 }

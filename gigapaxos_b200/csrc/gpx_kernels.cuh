@@ -80,10 +80,6 @@ __device__ __forceinline__ void flush_counters(const DevState& S, unsigned int* 
   }
 }
 
-__device__ __forceinline__ bool st_usable(uint32_t aux) {
-  uint32_t st = GPX_AUX_STATE(aux);
-  return st == GPX_ST_ACTIVE_1 || st == GPX_ST_ACTIVE_2;
-}
 __device__ __forceinline__ bool usable(const DevState& S, uint32_t gid, uint32_t lane, uint32_t* aux_out) {
   uint32_t aux = S.acc_aux[row_idx(S, lane, gid)];
   *aux_out = aux;
@@ -875,25 +871,6 @@ __device__ __forceinline__ void store_void_exec(gpx_exec_rec* ex, uint32_t gid, 
   vx.payload_off = 0;
   vx.flags = GPX_F_VOID | (l << 12);
   store_exec(ex, vx);
-}
-
-struct GroupCtx {
-  uint32_t R;
-  const MsetInfo* ms;
-  bool live;
-};
-__device__ __forceinline__ GroupCtx group_ctx(const DevState& S, uint32_t gid) {
-  GroupCtx g;
-  g.R = 0;
-  g.ms = nullptr;
-  g.live = false;
-  if (gid < S.G) {
-    const uint32_t meta = S.grp_meta[gid];
-    g.ms = &S.msets[meta & 0xffffu];
-    g.R = (meta >> 16) & 0xffu;
-    g.live = (meta & GPX_META_LIVE) != 0;
-  }
-  return g;
 }
 
 /* ============================== k_accept ====================================== */

@@ -164,6 +164,11 @@ def _jsub(a: int, b: int) -> int:
     return d - (1 << 32) if d & 0x80000000 else d
 
 
+def _jadd(a: int, b: int) -> int:
+    """Java's wrap-around int addition"""
+    return _jsub(a, -b)
+
+
 @dataclass
 class _Instance:
     gid: int
@@ -175,7 +180,7 @@ class _Instance:
 class PaxosManager:
     """Mirror of the PaxosManager calls on the hot path, for co-located replicas."""
 
-    def __init__(self, engine: Engine, apps: Sequence[Replicable], nodes: Sequence[int]):
+    def __init__(self, engine: Engine, apps: Sequence[Replicable], nodes: Sequence[int], device_phase1b: bool = False):
         if len(apps) != engine.n_lanes or len(nodes) != engine.n_lanes:
             raise ValueError("one app and one node id per lane")
         self.engine = engine
@@ -194,6 +199,9 @@ class PaxosManager:
         self.auto_elect = True  # run for coordinator when a proposal finds none (PISM.handleProposal :862-885)
         self._elect: Dict[str, int] = {}
         self.paused: Dict[str, List[str]] = {}  # paxosID -> HotRestoreInfo string per lane (the pause table)
+        # phase 1b (tally of PREPARE_REPLYs, carry-over, no-op fill, install): inside the engine
+        # (gpx_handle_prepare_replies) or by the host-language twin below + gpx_patch
+        self.device_phase1b = device_phase1b
 
     # ---- instance management ------------------------------------------------------------
     def _alloc_gid(self) -> int:
@@ -300,10 +308,36 @@ class PaxosManager:
                 prep["slot"], prep["bnum"] = int(cur["acc_slot"]), new_ballot[0]
         replies = eng.handle_prepares(prep)
         # (reply index == lane: gpx_handle_prepares answers at index i * n_lanes + lane and there is one PREPARE)
+        if self.device_phase1b:
+            res = self._phase1b_engine(inst.gid, lane, new_ballot, int(cur["acc_slot"]), replies, logged)
+        else:
+            res = self._phase1b_host(inst.gid, lane, R, new_ballot, int(cur["acc_slot"]), replies, logged)
+        if res is None:
+            return False
+        plan = res
+        # spawnCommandersForProposals :556-575: one ACCEPT per carried-over slot, in slot order, under my ballot
+        for sl, kind, pv, src in plan:
+            if kind == abi.CO_NOOP:
+                reqs = [RequestPacket(paxosID, 0, NO_OP, entry_replica=me)]
+            elif kind == abi.CO_STOP_NEW:
+                reqs = [RequestPacket(paxosID, 0, b"STOP", stop=True, entry_replica=me)]  # PCS :541
+            else:
+                reqs = self._requests_of(paxosID, pv, src, me)
+            self._submit(reqs, carryover=True)
+        return True
+
+    def _phase1b_host(self, gid, lane, R, new_ballot, acc_slot, replies, logged):
+        """phase 1b in the host language (tally_prepare_replies / combine_carryover), its result installed with
+        gpx_patch records.  Returns the plan [(slot, kind, pvalue, source lane)] or None."""
+        eng, L = self.engine, self.engine.n_lanes
+        gids = np.array([gid], dtype=np.uint32)
         verdict, node_slots, carry = self.tally_prepare_replies(replies, R, new_ballot, logged)
         if verdict != "majority":
-            return False
-        plan, next_slot = self.combine_carryover(carry, node_slots, int(cur["acc_slot"]))
+            return None
+        comb = self.combine_carryover(carry, node_slots, acc_slot)
+        if comb is None:
+            return None
+        plan, next_slot, _ = comb
         # coordinators of a LOWER ballot resign (PISM.handlePrepare -> nullifyCoordinatorIfPreempted); the new one starts
         # ACTIVE at the first slot it has to fill
         pts = []
@@ -312,22 +346,46 @@ class PaxosManager:
             if l != lane and bool(r["coord_exists"]) and (
                     _jsub(int(r["coord_bnum"]), new_ballot[0]) or _jsub(int(r["coord_bcoord"]), new_ballot[1])) > 0:
                 continue  # a coordinator with a higher ballot is not ours to remove
-            pts.append((inst.gid, l, abi.PATCH_RESIGN_COORD, 0, 0, 0, 0))
-        pts.append((inst.gid, lane, abi.PATCH_INSTALL_COORD, new_ballot[0], new_ballot[1], next_slot, 1))
+            pts.append((gid, l, abi.PATCH_RESIGN_COORD, 0, 0, 0, 0))
+        pts.append((gid, lane, abi.PATCH_INSTALL_COORD, new_ballot[0], new_ballot[1], next_slot, 1))
         for i, v in enumerate(node_slots):
-            pts.append((inst.gid, lane, abi.PATCH_SET_NODE_SLOT, i, v, 0, 0))
+            pts.append((gid, lane, abi.PATCH_SET_NODE_SLOT, i, v, 0, 0))
         p = np.zeros(len(pts), dtype=abi.patch_dtype)
         for i, t in enumerate(pts):
             p[i]["gid"], p[i]["lane"], p[i]["op"], p[i]["a"], p[i]["b"], p[i]["c"], p[i]["d"] = t
         eng.patch(p)
-        # spawnCommandersForProposals :556-575: one ACCEPT per carried-over slot, in slot order, under my ballot
-        for sl, pv, src in plan:
-            if pv is None:
-                reqs = [RequestPacket(paxosID, 0, NO_OP, entry_replica=me)]
-            else:
-                reqs = self._requests_of(paxosID, pv, src, me)
-            self._submit(reqs, carryover=True)
-        return True
+        return plan
+
+    def _phase1b_engine(self, gid, lane, new_ballot, acc_slot, replies, logged):
+        """phase 1b inside the engine (gpx_handle_prepare_replies: one kernel tallies, carries over, fills, installs).
+        A reply that grew beyond GPX_MAX_WINDOW pvalues by its logged accepts travels as GPX_F_MORE continuation
+        records.  Returns the plan [(slot, kind, pvalue, source lane)] or None."""
+        recs, rec_lane = [], []
+        for l, rep in enumerate(replies):
+            acc = list(rep["accepted"][: int(rep["n_accepted"])])
+            if logged and logged.get(l):
+                have = {int(pv["slot"]) for pv in acc}
+                acc = sorted(acc + [pv for pv in logged[l] if int(pv["slot"]) not in have], key=lambda pv: int(pv["slot"]))
+            chunks = [acc[k: k + abi.GPX_MAX_WINDOW] for k in range(0, len(acc), abi.GPX_MAX_WINDOW)] or [[]]
+            for ci, ch in enumerate(chunks):
+                r = rep.copy()
+                r["n_accepted"] = len(ch)
+                r["accepted"][:] = 0
+                for k, pv in enumerate(ch):
+                    r["accepted"][k] = pv
+                if ci + 1 < len(chunks):
+                    r["who"] = int(r["who"]) | (abi.F_MORE << 16)
+                recs.append(r)
+                rec_lane.append(l)
+        el = np.zeros(1, dtype=abi.election_dtype)
+        el["gid"], el["lane"], el["bnum"], el["bcoord"], el["slot"] = gid, lane, new_ballot[0], new_ballot[1], acc_slot
+        el["first_reply"], el["n_replies"] = 0, len(recs)
+        out = self.engine.handle_prepare_replies(el, np.array(recs, dtype=abi.prepare_reply_dtype))[0]
+        if int(out["verdict"]) != abi.EL_MAJORITY:
+            return None
+        return [(int(c["slot"]), int(c["kind"]), c["pv"].copy() if int(c["kind"]) == abi.CO_PVALUE else None,
+                 rec_lane[int(c["src_reply"])] if int(c["kind"]) == abi.CO_PVALUE else 0)
+                for c in out["plan"][: int(out["n_plan"])]]
 
     def _logged_accepts(self, gid: int, first_slot: int, lanes: Sequence[int]):
         """AbstractPaxosLogger.getLoggedAccepts for the PREPARE path (PISM.handlePrepare :896-955 with
@@ -365,10 +423,12 @@ class PaxosManager:
 
     @staticmethod
     def tally_prepare_replies(replies, R: int, new_ballot: tuple, logged=None):
-        """PISM.handlePrepareReply :957-990 over a sequence of gpx_prepare_reply records, in order: returns
-        ("preempted" | "majority" | "waiting", nodeSlotNumbers, carryover {slot: (pvalue, reply index)}).
+        """PISM.handlePrepareReply :1017-1068 over a sequence of gpx_prepare_reply records, in order: returns
+        ("preempted" | "majority" | "waiting" | "overflow", nodeSlotNumbers, carryover {slot: (pvalue, reply index)}).
         logged[l]: accepted pvalues the acceptor behind reply l serves from its journal (GPX_F_FROM_LOG: with
-        journaling the executed accepts have left its memory) -- part of its reply as far as the tally goes."""
+        journaling the executed accepts have left its memory) -- part of its reply as far as the tally goes.
+        The host-language twin of gpx_handle_prepare_replies (include/gpx.h), kept for engines without it and as a
+        second restatement the CPU tests hold against the oracle's."""
         node_slots = [-1] * R  # PCS ctor :169-171
         heard, carry = set(), {}
         for l, rep in enumerate(replies):
@@ -386,10 +446,11 @@ class PaxosManager:
             if logged and logged.get(l):
                 have = {int(pv["slot"]) for pv in acc}
                 acc = sorted(acc + [pv for pv in logged[l] if int(pv["slot"]) not in have], key=lambda pv: int(pv["slot"]))
-            # recordSlotNumber :786-807 with PrepareReplyPacket.getMinSlot: the lowest accepted slot, else gcSlot + 1
-            min_slot = int(rep["first_slot"]) + 1
-            for k, pv in enumerate(acc):
-                if k == 0 or _jsub(int(pv["slot"]), min_slot) < 0:
+            # recordSlotNumber :786-807 with PrepareReplyPacket.getMinSlot() :151-164: it starts at firstSlot (= gcSlot + 1;
+            # the record holds gcSlot) and takes the wrap-aware minimum with the accepted slots
+            min_slot = _jadd(int(rep["first_slot"]), 1)
+            for pv in acc:
+                if _jsub(int(pv["slot"]), min_slot) < 0:
                     min_slot = int(pv["slot"])
             if _jsub(node_slots[idx], min_slot) < 0:
                 node_slots[idx] = min_slot
@@ -398,6 +459,8 @@ class PaxosManager:
                 if ex is None or (_jsub(int(pv["bnum"]), int(ex[0]["bnum"])) or
                                   _jsub(int(pv["bcoord"]), int(ex[0]["bcoord"]))) > 0:
                     carry[int(pv["slot"])] = (pv.copy(), l)
+                    if len(carry) > abi.GPX_MAX_CARRY:  # device rule
+                        return "overflow", node_slots, carry
             heard.add(idx)
             if len(heard) > R // 2:  # WaitforUtility.heardFromMajority
                 return "majority", node_slots, carry
@@ -407,51 +470,43 @@ class PaxosManager:
     def combine_carryover(carry: dict, node_slots: List[int], acc_slot: int):
         """PCS.combinePValuesOntoProposals :393-444 (this mirror keeps no pre-active proposals: requests wait in
         its queue): the slots from getMaxMinCarryoverSlot :921 to getMaxPValueSlot :903, carried-over pvalue or
-        no-op.  Returns (plan [(slot, pvalue | None, reply index)], first slot the new coordinator proposes)."""
-        next_slot = acc_slot  # PCS ctor: nextProposalSlotNumber = paxosState.getSlot()
+        no-op, then processStop :478-554.  Returns (plan [(slot, kind, pvalue | None, reply index)], the first slot
+        the new coordinator proposes, flags) or None when the range exceeds GPX_MAX_PLAN (device rule)."""
+        if not carry:
+            return [], acc_slot, 0  # PCS ctor: nextProposalSlotNumber = paxosState.getSlot()
+        max_carry = max_min = None
+        for sl in carry:
+            max_carry = sl if max_carry is None or _jsub(sl, max_carry) > 0 else max_carry
+        for v in node_slots:
+            max_min = v if max_min is None or _jsub(v, max_min) > 0 else max_min
+        if _jsub(max_carry, max_min) >= abi.GPX_MAX_PLAN:
+            return None
         plan: List[tuple] = []
-        if carry:
-            max_carry = max_min = None
-            for sl in carry:
-                max_carry = sl if max_carry is None or _jsub(sl, max_carry) > 0 else max_carry
-            for v in node_slots:
-                max_min = v if max_min is None or _jsub(v, max_min) > 0 else max_min
-            sl = max_min
-            while _jsub(sl, max_carry) <= 0:
-                plan.append((sl,) + (carry[sl] if sl in carry else (None, -1)))
-                sl = (sl + 1) & 0xFFFFFFFF
-                sl = sl - (1 << 32) if sl & 0x80000000 else sl
-            next_slot = max_min
-        return PaxosManager._process_stop(plan), next_slot
+        sl = max_min
+        while _jsub(sl, max_carry) <= 0:
+            plan.append((sl, abi.CO_PVALUE) + carry[sl] if sl in carry else (sl, abi.CO_NOOP, None, 0))
+            sl = _jadd(sl, 1)
+        plan, flags = PaxosManager._process_stop(plan, _jadd(max_carry, 1))
+        return plan, (plan[0][0] if plan else _jadd(max_carry, 1)), flags
 
     @staticmethod
-    def _process_stop(plan: List[tuple]) -> List[tuple]:
-        """PCS.processStop :478-554: a regular request may never follow a STOP.  For a STOP at slot s1 and a regular
-        request at a higher slot s2: if the STOP's ballot is higher the request is replaced by the STOP, if lower the
-        STOP becomes a no-op."""
-        out = {sl: (pv, src) for sl, pv, src in plan}
-        bal = lambda pv: (int(pv["bnum"]), int(pv["bcoord"]))
-        is_stop = lambda pv: pv is not None and bool(int(pv["flags"]) & 2)
-        for s1, (p1, src1) in list(out.items()):
-            if not is_stop(p1):
+    def _process_stop(plan: List[tuple], next_slot: int):
+        """PCS.processStop :478-554.  Every proposal carries the NEW coordinator's ballot here (the constructor of
+        ProposalStateAtCoordinator :153-157 re-stamps it), so neither of its two conversions (request behind a
+        higher-ballot STOP -> STOP :497-511, STOP before a higher-ballot request -> no-op :512-526) can be taken: a
+        regular request behind a STOP is the reference's assert(false) :527, reported as ELF_STOP_ORDER.  What remains
+        is the tail :538-542: a STOP was carried over but the last proposal is not one -> a fresh STOP behind it."""
+        is_stop = lambda e: e[1] == abi.CO_STOP_NEW or (e[1] == abi.CO_PVALUE and bool(int(e[2]["flags"]) & 2))
+        flags = 0
+        for e1 in plan:
+            if not is_stop(e1):
                 continue
-            for s2, (p2, src2) in list(out.items()):
-                if p2 is None or is_stop(p2) or _jsub(s1, s2) >= 0:
-                    continue
-                c = _jsub(bal(p1)[0], bal(p2)[0]) or _jsub(bal(p1)[1], bal(p2)[1])
-                if c > 0:
-                    out[s2] = (p1, src1)
-                elif c < 0:
-                    out[s1] = (None, -1)
-        res = [(sl,) + out[sl] for sl, _, _ in plan]
-        # :548-552: a STOP was among the carried-over pvalues but the last proposal is not one (it lost to a higher
-        # ballot above): the epoch must still end -- the STOP is proposed afresh behind everything else
-        stops = [(pv, src) for _, pv, src in plan if is_stop(pv)]
-        if stops and res and not is_stop(res[-1][1]):
-            last = res[-1][0]
-            nxt = (last + 1) & 0xFFFFFFFF
-            res.append((nxt - (1 << 32) if nxt & 0x80000000 else nxt,) + stops[-1])
-        return res
+            for e2 in plan:
+                if not is_stop(e2) and e2[1] != abi.CO_NOOP and _jsub(e1[0], e2[0]) < 0:
+                    flags |= abi.ELF_STOP_ORDER
+        if plan and any(is_stop(e) for e in plan) and not is_stop(plan[-1]):
+            plan = plan + [(next_slot, abi.CO_STOP_NEW, None, 0)]
+        return plan, flags
 
     def _requests_of(self, paxosID: str, pv, src_lane: int, entry: int) -> List[RequestPacket]:
         """the request(s) of an accepted pvalue, read back from the log ring of the acceptor lane that reported it"""

@@ -389,6 +389,82 @@ typedef struct gpx_prepare_reply_rec { /* PrepareReplyPacket, 32 + 32 * GPX_MAX_
 /* out_replies[n * n_lanes] */
 int gpx_handle_prepares(gpx_engine* e, uint32_t n, const gpx_pvalue_hdr* prepares, gpx_prepare_reply_rec* out_replies);
 
+/* ---- phase 1b at the would-be coordinator -------------------------------------------------------
+ * gpx_handle_prepare_replies runs, for a batch of elections (one candidate coordinator of one group each: the mass
+ * fail-over after a node is lost is many groups electing at once), what PISM.handlePrepareReply :1017-1068 does per
+ * PREPARE_REPLY and what follows a majority:
+ *   PaxosCoordinator.getPreActivesIfPreempted :313-318 / PCS.isPreemptable :271-278   a reply with a higher ballot
+ *       ends the election (GPX_EL_PREEMPTED; nothing is installed);
+ *   PCS.canIgnorePrepareReply :287-316   lower ballot, not a member, already heard: ignored;
+ *   PCS.isPrepareAcceptedByMajority :326-391   recordSlotNumber(PrepareReplyPacket) :786-807 with
+ *       PrepareReplyPacket.getMinSlot :151-164 (= min(firstSlot, the accepted slots), wrap-aware), the pvalue of the
+ *       highest ballot per slot is carried over, WaitforUtility majority;
+ *   PCS.combinePValuesOntoProposals :393-444   the slots getMaxMinCarryoverSlot :921 .. getMaxPValueSlot :903 become
+ *       the new coordinator's first proposals, carried-over pvalue or no-op (makeNoopPValue :886-897);
+ *   PCS.processStop :478-554   every proposal carries the new ballot there (ProposalStateAtCoordinator's constructor
+ *       :153-157 re-stamps it), so its two conversion branches cannot be taken; a regular request behind a STOP is the
+ *       reference's `assert(false)` and is reported as GPX_ELF_STOP_ORDER; when a STOP was carried over and the last
+ *       proposal is not a STOP, a fresh STOP is proposed behind it (:538-542);
+ *   PCS.setCoordinatorActive :577-587   the coordinator is installed ACTIVE at `lane` with the recorded
+ *       nodeSlotNumbers and nextProposalSlotNumber = the first slot of the plan; coordinators of a lower ballot at the
+ *       other local lanes resign (PISM.handlePrepare would have removed them when the PREPARE arrived).
+ * The plan is returned, not proposed: spawnCommandersForProposals :556-575 is the caller re-proposing plan[0..n_plan)
+ * in order through gpx_propose / gpx_round (the request bodies of a carried-over pvalue are in the log ring of the
+ * acceptor that reported it: reply index src_reply, position frame_ref * 16).  The engine keeps no pre-active
+ * proposals (a request that finds a pre-active coordinator gets GPX_RS_PREACTIVE and waits at the host), so
+ * combinePValuesOntoProposals' preActives and reproposePreemptedProposals :460-468 have nothing to do here.
+ *
+ * A PREPARE_REPLY longer than GPX_MAX_WINDOW pvalues (accepts added from the journal, GPX_F_FROM_LOG) is given as
+ * consecutive records of the same acceptor, all but the last flagged GPX_F_MORE in `who`.
+ * Device rules (as for the slot window): more than GPX_MAX_CARRY distinct carried-over slots, or a plan range of more
+ * than GPX_MAX_PLAN slots, gives GPX_EL_OVERFLOW and installs nothing -- the candidate is too far behind and syncs
+ * first (PISM.syncLongDecisionGaps).  At most one election per gid per call (GPX_EINVAL otherwise). */
+#define GPX_F_MORE 0x0800u /* prepare reply record: the same PREPARE_REPLY continues in the next record */
+#define GPX_MAX_CARRY 32
+#define GPX_MAX_PLAN 16
+enum {
+  GPX_EL_WAITING = 0,   /* no majority among the replies given */
+  GPX_EL_MAJORITY = 1,  /* elected and installed */
+  GPX_EL_PREEMPTED = 2, /* a reply carried a higher ballot */
+  GPX_EL_DROPPED = 3,   /* no live instance at that lane / stopped / lane not a member (PISM :456-460) */
+  GPX_EL_OVERFLOW = 4
+};
+enum {
+  GPX_CO_NOOP = 0,     /* RequestPacket(0, NO_OP, false), entry replica = the new coordinator */
+  GPX_CO_PVALUE = 1,   /* the carried-over pvalue's request(s), re-proposed under the new ballot */
+  GPX_CO_STOP_NEW = 2  /* RequestPacket(0, STOP, true) :541 */
+};
+#define GPX_ELF_STOP_ORDER 1u /* a regular request lies behind a STOP in the plan: PCS.processStop's assert(false) */
+typedef struct gpx_election_rec { /* one pre-active coordinator (PISM.checkRunForCoordinator :2090-2150), 32 B */
+  uint32_t gid;
+  uint32_t lane;        /* local lane of the candidate */
+  int32_t bnum;         /* the ballot it sent its PREPARE with */
+  int32_t bcoord;
+  int32_t slot;         /* PCS ctor's nextProposalSlotNumber = paxosState.getSlot() (the PREPARE's firstUndecidedSlot) */
+  uint32_t first_reply; /* replies[first_reply .. first_reply + n_replies) are handled in this order */
+  uint32_t n_replies;
+  uint32_t reserved;
+} gpx_election_rec;
+typedef struct gpx_carryover { /* one proposal of the view change, 48 B */
+  int32_t slot;
+  uint32_t kind;        /* GPX_CO_* */
+  uint32_t src_reply;   /* GPX_CO_PVALUE: index into replies[] of the record that carried it */
+  uint32_t reserved;
+  gpx_accepted_pvalue pv; /* GPX_CO_PVALUE: as reported (its own, lower, ballot) */
+} gpx_carryover;
+typedef struct gpx_election_out { /* 16 + 64 + 17 * 48 = 896 B */
+  uint32_t gid;
+  int32_t verdict;      /* GPX_EL_* */
+  int32_t next_slot;    /* GPX_EL_MAJORITY: the installed nextProposalSlotNumber (plan[0].slot when n_plan > 0) */
+  uint16_t n_plan;
+  uint16_t flags;       /* GPX_ELF_* */
+  int32_t node_slots[GPX_MAX_GROUP_SIZE]; /* nodeSlotNumbers as recorded (-1 = not heard) */
+  gpx_carryover plan[GPX_MAX_PLAN + 1];
+} gpx_election_out;
+/* replies: host array of n_reply_recs records; out[n] */
+int gpx_handle_prepare_replies(gpx_engine* e, uint32_t n, const gpx_election_rec* elections, uint32_t n_reply_recs,
+                               const gpx_prepare_reply_rec* replies, gpx_election_out* out);
+
 /* One full round for co-located replicas.  gpx_round: RequestBatcher + propose, then the fused
  * accept -> tally -> commit per ACCEPT with replies, decisions and rows kept in registers.
  * gpx_round_phases: the same round phase by phase (all ACCEPTs, then all replies, then all

@@ -1341,6 +1341,239 @@ int gpxo_handle_prepares(gpxo_engine* e, uint32_t n, const gpx_pvalue_hdr* prepa
   return GPX_OK;
 }
 
+/* ------------------------------------------------------------------------------
+ * Phase 1b at the would-be coordinator: PISM.handlePrepareReply :1017-1068 ->
+ * PaxosCoordinator.getPreActivesIfPreempted PaxosCoordinator.java:313-318 / handlePrepareReply :281-299 ->
+ * PaxosCoordinatorState.java:264-587.  The pre-active PaxosCoordinatorState lives for the duration of the call.
+ * ---------------------------------------------------------------------------- */
+namespace {
+struct PrepareReplyPacket { /* paxospackets/PrepareReplyPacket.java:36-87 */
+  Ballot ballot{0, 0};
+  i32 acceptor = 0;   /* node id */
+  i32 firstSlot = 0;  /* gcSlot + 1 :80 */
+  std::vector<std::pair<gpx_accepted_pvalue, u32>> accepted; /* (pvalue, index of the record that carried it) */
+  /* getMinSlot() :151-164: starts at firstSlot, wrap-aware */
+  i32 getMinSlot() const {
+    i32 minSlot = firstSlot;
+    for (auto& a : accepted)
+      if (jsub(a.first.slot, minSlot) < 0) minSlot = a.first.slot;
+    return minSlot;
+  }
+};
+
+struct Phase1Proposal { /* ProposalStateAtCoordinator :148-162, as far as phase 1 uses it */
+  i32 slot;
+  u32 kind; /* GPX_CO_* */
+  u32 src;
+  gpx_accepted_pvalue pv;
+  bool isStopRequest() const { return kind == GPX_CO_STOP_NEW || (kind == GPX_CO_PVALUE && (pv.flags & 2u)); }
+  bool isNoop() const { return kind == GPX_CO_NOOP; } /* requestValue.equals(NO_OP) */
+};
+
+struct PreActiveCoordinatorState { /* PaxosCoordinatorState.java:67-178 in the pre-active state */
+  i32 myBallotNum, myBallotCoord, nextProposalSlotNumber;
+  std::vector<i32> nodeSlotNumbers;
+  std::vector<i32> members;
+  WaitforUtility waitforMyBallot;
+  std::map<i32, std::pair<gpx_accepted_pvalue, u32>> carryoverProposals;
+  std::vector<Phase1Proposal> myProposals; /* in slot order (the range loop of combinePValuesOntoProposals) */
+  bool overflow = false, stopOrder = false;
+
+  PreActiveCoordinatorState(i32 bnum, i32 coord, i32 slot, const std::vector<i32>& m) /* ctor :163-178 + prepare :213-219 */
+      : myBallotNum(bnum), myBallotCoord(coord), nextProposalSlotNumber(slot), nodeSlotNumbers(m.size(), -1), members(m),
+        waitforMyBallot(m) {}
+  Ballot getBallot() const { return Ballot{myBallotNum, myBallotCoord}; }
+
+  bool isPreemptable(const PrepareReplyPacket& r) const { return r.ballot.compareTo(getBallot()) > 0; } /* :271-278 */
+
+  bool canIgnorePrepareReply(const PrepareReplyPacket& r) const { /* :287-316 */
+    if (r.ballot.compareTo(getBallot()) < 0) return true;
+    if (!waitforMyBallot.contains(r.acceptor)) return true;
+    int idx = waitforMyBallot.getIndex(r.acceptor);
+    return waitforMyBallot.responded[idx]; /* alreadyHeardFrom */
+  }
+
+  void recordSlotNumber(const PrepareReplyPacket& r) { /* :786-807 */
+    for (size_t i = 0; i < members.size(); i++)
+      if (members[i] == r.acceptor)
+        if (jsub(nodeSlotNumbers[i], r.getMinSlot()) < 0) nodeSlotNumbers[i] = r.getMinSlot();
+  }
+
+  bool isPrepareAcceptedByMajority(const PrepareReplyPacket& r) { /* :326-391 */
+    if (canIgnorePrepareReply(r)) return false;
+    recordSlotNumber(r);
+    for (auto& a : r.accepted) {
+      const i32 curSlot = a.first.slot;
+      auto ex = carryoverProposals.find(curSlot);
+      if (ex == carryoverProposals.end() ||
+          Ballot{a.first.bnum, a.first.bcoord}.compareTo(Ballot{ex->second.first.bnum, ex->second.first.bcoord}) > 0) {
+        carryoverProposals[curSlot] = a;
+        if (carryoverProposals.size() > GPX_MAX_CARRY) { /* device rule */
+          overflow = true;
+          return false;
+        }
+      }
+    }
+    waitforMyBallot.updateHeardFrom(r.acceptor);
+    return waitforMyBallot.heardFromMajority();
+  }
+
+  i32 getMaxPValueSlot() const { /* :903-914 */
+    bool have = false;
+    i32 maxSlot = 0;
+    for (auto& kv : carryoverProposals) {
+      if (!have) {
+        maxSlot = kv.first;
+        have = true;
+      }
+      if (jsub(kv.first, maxSlot) > 0) maxSlot = kv.first;
+    }
+    return maxSlot;
+  }
+  i32 getMaxMinCarryoverSlot() const { /* :921-931 */
+    i32 maxSlot = nodeSlotNumbers[0];
+    for (size_t i = 0; i < nodeSlotNumbers.size(); i++)
+      if (jsub(nodeSlotNumbers[i], maxSlot) > 0) maxSlot = nodeSlotNumbers[i];
+    return maxSlot;
+  }
+
+  /* PCS.propose :233-263 while not active: the proposal is queued at the next slot, no ACCEPT */
+  void proposePreActive(u32 kind) {
+    if (!myProposals.empty() && myProposals.back().slot == nextProposalSlotNumber - 1 && myProposals.back().isStopRequest())
+      return; /* :235-239 */
+    Phase1Proposal p;
+    memset(&p, 0, sizeof p);
+    p.slot = nextProposalSlotNumber;
+    p.kind = kind;
+    nextProposalSlotNumber = (i32)((u32)nextProposalSlotNumber + 1u);
+    myProposals.push_back(p);
+  }
+
+  void combinePValuesOntoProposals() { /* :393-444; preActives is empty (header comment of gpx_handle_prepare_replies) */
+    if (carryoverProposals.empty()) return;
+    const i32 maxCarryoverSlot = getMaxPValueSlot();
+    const i32 maxMinCarryoverSlot = getMaxMinCarryoverSlot();
+    if (jsub(maxCarryoverSlot, maxMinCarryoverSlot) >= GPX_MAX_PLAN) { /* device rule */
+      overflow = true;
+      return;
+    }
+    for (i32 curSlot = maxMinCarryoverSlot; jsub(curSlot, maxCarryoverSlot) <= 0; curSlot = (i32)((u32)curSlot + 1u)) {
+      Phase1Proposal p;
+      memset(&p, 0, sizeof p);
+      p.slot = curSlot;
+      auto c = carryoverProposals.find(curSlot);
+      if (c != carryoverProposals.end()) {
+        p.kind = GPX_CO_PVALUE;
+        p.pv = c->second.first;
+        p.src = c->second.second;
+      } else {
+        p.kind = GPX_CO_NOOP; /* makeNoopPValue(curSlot, null, ...) :886-897 */
+      }
+      myProposals.push_back(p);
+    }
+    nextProposalSlotNumber = (i32)((u32)maxCarryoverSlot + 1u); /* :436 */
+    processStop();
+  }
+
+  void processStop() { /* :478-554 */
+    bool stopExists = false;
+    for (const Phase1Proposal& psac1 : myProposals) {
+      if (!psac1.isStopRequest()) continue;
+      stopExists = true;
+      for (const Phase1Proposal& psac2 : myProposals)
+        if (!psac2.isStopRequest() && !psac2.isNoop() && jsub(psac1.slot, psac2.slot) < 0) {
+          /* both pvalues carry MY ballot here (ProposalStateAtCoordinator's ctor :153-157 re-stamps it), so neither
+           * "stop ballot > other ballot" :497 nor "<" :512 can hold: the reference reaches its assert(false) :527 */
+          stopOrder = true;
+        }
+    }
+    if (stopExists && !myProposals.empty()) {
+      const Phase1Proposal& last = myProposals.back(); /* myProposals.get(nextProposalSlotNumber - 1) */
+      if (!last.isStopRequest()) proposePreActive(GPX_CO_STOP_NEW); /* :538-542 */
+    }
+  }
+};
+}  // namespace
+
+int gpxo_handle_prepare_replies(gpxo_engine* e, uint32_t n, const gpx_election_rec* elections, uint32_t n_reply_recs,
+                                const gpx_prepare_reply_rec* replies, gpx_election_out* out) {
+  if (!e || (n && (!elections || !out)) || (n_reply_recs && !replies)) return GPX_EINVAL;
+  for (u32 i = 0; i < n; i++) {
+    if ((u64)elections[i].first_reply + elections[i].n_replies > n_reply_recs) return GPX_ERANGE;
+    for (u32 j = 0; j < i; j++)
+      if (elections[j].gid == elections[i].gid) return GPX_EINVAL; /* one election per group per call */
+  }
+  for (u32 i = 0; i < n; i++) {
+    const gpx_election_rec& el = elections[i];
+    gpx_election_out& o = out[i];
+    memset(&o, 0, sizeof o);
+    o.gid = el.gid;
+    o.verdict = GPX_EL_DROPPED;
+    for (int m = 0; m < GPX_MAX_GROUP_SIZE; m++) o.node_slots[m] = -1;
+    if (el.lane >= e->L() || !e->usable(el.gid, el.lane)) continue; /* PISM :456-460 */
+    Group& g = e->groups[el.gid];
+    if (e->memberIdx(g, e->lanes[el.lane].node) < 0) continue;
+    PreActiveCoordinatorState pcs(el.bnum, el.bcoord, el.slot, g.members);
+    int verdict = GPX_EL_WAITING;
+    for (u32 k = el.first_reply; k < el.first_reply + el.n_replies && verdict == GPX_EL_WAITING;) {
+      /* one PREPARE_REPLY = a record and its GPX_F_MORE continuations */
+      const gpx_prepare_reply_rec& h = replies[k];
+      PrepareReplyPacket pr;
+      pr.ballot = Ballot{h.bnum, h.bcoord};
+      const u32 idx = GPX_WHO_ACC(h.who);
+      const bool isVoid = GPX_WHO_FLAGS(h.who) & GPX_F_VOID;
+      pr.acceptor = idx < g.members.size() ? g.members[idx] : -1;
+      pr.firstSlot = (i32)((u32)h.first_slot + 1u); /* the record holds gcSlot */
+      for (;;) {
+        const gpx_prepare_reply_rec& r = replies[k];
+        for (u32 a = 0; a < r.n_accepted && a < GPX_MAX_WINDOW; a++) pr.accepted.push_back({r.accepted[a], k});
+        const bool more = (GPX_WHO_FLAGS(r.who) & GPX_F_MORE) && !(GPX_WHO_FLAGS(r.who) & GPX_F_VOID);
+        k++;
+        if (!more || k >= el.first_reply + el.n_replies) break;
+      }
+      if (isVoid) continue;
+      if (pcs.isPreemptable(pr)) { /* getPreActivesIfPreempted: the election is lost, the coordinator resigns */
+        verdict = GPX_EL_PREEMPTED;
+        break;
+      }
+      if (idx >= g.members.size()) continue; /* !Util.contains(acceptor, members) */
+      if (pcs.isPrepareAcceptedByMajority(pr)) { /* PaxosCoordinator.handlePrepareReply :281-299 */
+        pcs.combinePValuesOntoProposals();
+        verdict = GPX_EL_MAJORITY;
+      }
+      if (pcs.overflow) verdict = GPX_EL_OVERFLOW;
+    }
+    o.verdict = verdict;
+    for (size_t m = 0; m < pcs.nodeSlotNumbers.size() && m < GPX_MAX_GROUP_SIZE; m++) o.node_slots[m] = pcs.nodeSlotNumbers[m];
+    if (verdict != GPX_EL_MAJORITY) continue;
+    o.flags = pcs.stopOrder ? GPX_ELF_STOP_ORDER : 0;
+    o.n_plan = (uint16_t)pcs.myProposals.size();
+    for (size_t k = 0; k < pcs.myProposals.size(); k++) {
+      const Phase1Proposal& p = pcs.myProposals[k];
+      o.plan[k].slot = p.slot;
+      o.plan[k].kind = p.kind;
+      o.plan[k].src_reply = p.kind == GPX_CO_PVALUE ? p.src : 0;
+      if (p.kind == GPX_CO_PVALUE) o.plan[k].pv = p.pv;
+    }
+    /* spawnCommandersForProposals :556-575 is the caller's re-proposal of the plan; the coordinator it proposes
+     * through starts at the plan's first slot, ACTIVE (setCoordinatorActive :577-587), with the nodeSlotNumbers heard */
+    o.next_slot = pcs.myProposals.empty() ? pcs.nextProposalSlotNumber : pcs.myProposals[0].slot;
+    const Ballot nb = pcs.getBallot();
+    for (u32 l = 0; l < e->L(); l++) { /* coordinators of a lower ballot resign (PISM.handlePrepare at their node) */
+      Coordinator& C = e->lanes[l].coord[el.gid];
+      if (l != el.lane && C.exists && C.getBallot().compareTo(nb) > 0) continue;
+      C = Coordinator();
+      C.W = e->W();
+    }
+    Coordinator& C = e->lanes[el.lane].coord[el.gid];
+    C.create(nb.num, nb.coord, o.next_slot, g.members.size(), true);
+    C.active = true;
+    for (size_t m = 0; m < g.members.size(); m++)
+      if (jsub(C.nodeSlotNumbers[m], pcs.nodeSlotNumbers[m]) < 0) C.nodeSlotNumbers[m] = pcs.nodeSlotNumbers[m];
+  }
+  return GPX_OK;
+}
+
 /* PISM.handleBatchedAcceptReply :1370-1419 -> handleAcceptReply :1248-1365 per slot */
 int gpxo_handle_accept_replies(gpxo_engine* e, uint32_t n, const gpx_accept_reply_rec* replies,
                                gpx_decision_rec* out_decisions, uint32_t* n_decisions) {

@@ -12,9 +12,9 @@ from helpers import Engine, abi, make_config
 NODES = [100, 101, 102]
 
 
-def make_pm(lib, app_cls, **kw):
+def make_pm(lib, app_cls, p1b=False, **kw):
     eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20, **kw))
-    return PaxosManager(eng, [app_cls() for _ in NODES], NODES)
+    return PaxosManager(eng, [app_cls() for _ in NODES], NODES, device_phase1b=p1b)
 
 
 def drive(lib):
@@ -162,9 +162,9 @@ def test_pause_unpause_gpu(cuda_lib, oracle_lib):
 
 # ---- view change: host half of phase 1 over the device's phase 1a (PISM.checkRunForCoordinator :2090,
 #      handlePrepareReply :957, PCS.combinePValuesOntoProposals :393) ------------------------------------------------
-def drive_view_change(lib):
+def drive_view_change(lib, p1b=False):
     from helpers import make_requests
-    pm = make_pm(lib, HashChainApp, checkpoint_interval=100)
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=100, p1b=p1b)
     eng = pm.engine
     names = [f"TESTPaxosApp{i}" for i in range(9)]
     pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
@@ -227,6 +227,24 @@ def test_view_change_cpu(oracle_lib):
     drive_view_change(oracle_lib)
 
 
+def _same_end_state(a, b):
+    assert a.apps[0].state == b.apps[0].state and a.num_decisions == b.num_decisions
+    names = sorted(a.instances)
+    for lane in range(3):
+        ra = a.engine.dump_rows(np.array([a.instances[n].gid for n in names], dtype=np.uint32), lane)
+        rb = b.engine.dump_rows(np.array([b.instances[n].gid for n in names], dtype=np.uint32), lane)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), (lane, f)
+
+
+def test_phase1b_in_the_engine_equals_the_host_twin_cpu(oracle_lib):
+    """gpx_handle_prepare_replies (here: the oracle's restatement of PCS phase 1b) against the host-language twin
+    (tally_prepare_replies / combine_carryover + gpx_patch) through whole view changes: same rows, same executions"""
+    _same_end_state(drive_view_change(oracle_lib, p1b=True), drive_view_change(oracle_lib))
+    _same_end_state(drive_auto_election(oracle_lib, p1b=True), drive_auto_election(oracle_lib))
+    _same_end_state(drive_lagging_election(oracle_lib, p1b=True), drive_lagging_election(oracle_lib))
+
+
 @pytest.mark.gpu
 def test_view_change_gpu(cuda_lib, oracle_lib):
     g, o = drive_view_change(cuda_lib), drive_view_change(oracle_lib)
@@ -251,11 +269,18 @@ def _reply(acc_idx, ballot, accepted=(), gc_slot=-1, flags=0):
     return r
 
 
-def test_prepare_reply_tally_is_the_reference_self_test():
-    """PaxosCoordinatorState.main, phase-1 half (PaxosCoordinatorState.java:1008-1178): 43 members, my ballot (2, 21);
-    carry-overs at slots 2 (two ballots), 6, 7, 8, 9 reported by members[2], members[0], members[4]; then the even
-    members answer with nothing.  After combining: every proposal slot >= maxMinSlot (7), stops are only followed by
-    stops."""
+def test_prepare_reply_tally_follows_the_reference_code():
+    """The scenario of PaxosCoordinatorState.main's phase-1 half (PaxosCoordinatorState.java:1008-1178): 43 members, my
+    ballot (2, 21); carry-overs at slots 2 (two ballots), 6, 7, 8, 9 reported by members[2], members[0], members[4];
+    then the even members answer with nothing -- evaluated by the CODE the scenario runs through, where it and the
+    scenario's own assertions disagree:
+      * recordSlotNumber :786-807 records PrepareReplyPacket.getMinSlot() :151-164, which STARTS at firstSlot (gcSlot + 1
+        = 0 for these replies) -- so every heard member records 0, the view change fills from slot 0, and main()'s
+        `assert (slot >= maxMinSlot)` with maxMinSlot = 7 (:1165) cannot hold at this revision (it matches the static
+        getMinSlot(int, Map) :166-177 the packet stores in its unused minSlot field).  Filling from firstSlot is what
+        keeps a group live: slots 0, 1, 3, 4, 5 were accepted by nobody that answered and get no-ops;
+      * processStop :478-554 compares ballots that ProposalStateAtCoordinator's constructor :153-157 has re-stamped with
+        the new ballot, so it converts nothing; a regular request behind a STOP is its assert(false) branch."""
     from gigapaxos_b200.paxos_manager import PaxosManager
     R, my = 43, (2, 21)
     T = PaxosManager.tally_prepare_replies
@@ -271,26 +296,38 @@ def test_prepare_reply_tally_is_the_reference_self_test():
     for cut in (len(rs) - 1, len(rs)):
         verdict, ns, carry = T(rs[:cut], R, my)
         assert verdict == ("majority" if cut == len(rs) else "waiting")            # 22 of 43 heard only at the end
-    assert ns[2] == 2 and ns[0] == 2 and ns[4] == 7 and ns[6] == 0 and ns[1] == -1
+    assert ns[2] == 0 and ns[0] == 0 and ns[4] == 0 and ns[6] == 0 and ns[1] == -1   # getMinSlot() = firstSlot here
     assert sorted(carry) == [2, 6, 7, 8, 9] and int(carry[2][0]["bcoord"]) == 21    # the higher ballot wins slot 2
-    plan, nxt = PaxosManager.combine_carryover(carry, ns, acc_slot=0)
-    assert nxt == 7 and [sl for sl, _, _ in plan] == [7, 8, 9] and all(pv is not None for _, pv, _ in plan)
-    # processStop: a STOP with the higher ballot swallows a later regular request ...
+    plan, nxt, fl = PaxosManager.combine_carryover(carry, ns, acc_slot=0)
+    assert nxt == 0 and fl == 0 and [e[0] for e in plan] == list(range(10))
+    assert [e[1] for e in plan] == [abi.CO_NOOP, abi.CO_NOOP, abi.CO_PVALUE, abi.CO_NOOP, abi.CO_NOOP, abi.CO_NOOP,
+                                    abi.CO_PVALUE, abi.CO_PVALUE, abi.CO_PVALUE, abi.CO_PVALUE]
+    # acceptors that have garbage-collected through slot 6 answer firstSlot = 7: the fill starts there
+    rs7 = [_reply(2, my, [(7, 1, 20, False)], gc_slot=6), _reply(0, my, [(9, 1, 21, False)], gc_slot=6)]
+    rs7 += [_reply(i, my, gc_slot=6) for i in range(4, R, 2)]
+    verdict, ns, carry = T(rs7, R, my)
+    assert verdict == "majority" and ns[2] == ns[0] == ns[4] == 7
+    plan, nxt, _ = PaxosManager.combine_carryover(carry, ns, 0)
+    assert nxt == 7 and [(e[0], e[1]) for e in plan] == [(7, abi.CO_PVALUE), (8, abi.CO_NOOP), (9, abi.CO_PVALUE)]
+    # processStop: no conversion (same ballot everywhere after re-stamping); a request behind a STOP is flagged, and
+    # since the last proposal is not a STOP a fresh one follows (:538-542)
     rs[3] = _reply(4, my, [(7, 1, 21, False), (8, 1, 22, True), (9, 1, 20, False)])
     _, ns, carry = T(rs, R, my)
-    plan, _ = PaxosManager.combine_carryover(carry, ns, 0)
-    stops = [bool(int(pv["flags"]) & 2) for _, pv, _ in plan]
-    assert stops == [False, True, True] and int(plan[2][1]["req_id"]) == 1008
-    # ... and a STOP with the lower ballot becomes a no-op
-    rs[3] = _reply(4, my, [(7, 1, 21, False), (8, 1, 19, True), (9, 1, 20, False)])
+    plan, _, fl = PaxosManager.combine_carryover(carry, ns, 0)
+    assert fl == abi.ELF_STOP_ORDER and [e[1] for e in plan[7:]] == [abi.CO_PVALUE] * 3 + [abi.CO_STOP_NEW]
+    assert plan[-1][0] == 10 and bool(int(plan[8][2]["flags"]) & 2) and not (int(plan[9][2]["flags"]) & 2)
+    # a STOP in the last carried-over slot: nothing to add
+    rs[3] = _reply(4, my, [(7, 1, 21, False), (8, 1, 19, False), (9, 1, 20, True)])
     _, ns, carry = T(rs, R, my)
-    plan, _ = PaxosManager.combine_carryover(carry, ns, 0)
-    assert plan[1][1] is None and not (int(plan[2][1]["flags"]) & 2)
-    # a gap between carried-over slots is filled with a no-op (makeNoopPValue :886)
-    rs[3] = _reply(4, my, [(7, 1, 21, False), (9, 1, 20, False)])
-    _, ns, carry = T(rs, R, my)
-    plan, _ = PaxosManager.combine_carryover(carry, ns, 0)
-    assert [pv is None for _, pv, _ in plan] == [False, True, False]
+    plan, _, fl = PaxosManager.combine_carryover(carry, ns, 0)
+    assert fl == 0 and len(plan) == 10 and bool(int(plan[-1][2]["flags"]) & 2)
+    # a reply whose lowest accepted slot lies below its firstSlot (accepts added from the journal) records that slot
+    verdict, ns, carry = T([_reply(0, my, [(3, 1, 20, False)], gc_slot=5)] + [_reply(i, my, gc_slot=5) for i in range(2, R, 2)],
+                           R, my)
+    assert verdict == "majority" and ns[0] == 3 and ns[2] == 6
+    # device rules: more than GPX_MAX_PLAN slots to fill -> refused
+    verdict, ns, carry = T([_reply(0, my, [(40, 1, 20, False)])] + [_reply(i, my) for i in range(2, R, 2)], R, my)
+    assert verdict == "majority" and PaxosManager.combine_carryover(carry, ns, 0) is None
 
 
 # ---- catching up a lagging replica (PISM.syncLongDecisionGaps :1550 / handleSyncDecisionsPacket :2426 / checkpoint
@@ -371,10 +408,10 @@ def test_sync_decisions_gpu(cuda_lib, oracle_lib):
             assert np.array_equal(rg[f], ro[f]), (lane, f)
 
 
-def drive_auto_election(lib):
+def drive_auto_election(lib, p1b=False):
     """a proposal that finds no coordinator makes its entry replica run for coordinator (PISM.handleProposal :862-885
     -> checkRunForCoordinator(true)); the request is decided by the new coordinator in the next round"""
-    pm = make_pm(lib, HashChainApp)
+    pm = make_pm(lib, HashChainApp, p1b=p1b)
     names = [f"TESTPaxosApp{i}" for i in range(5)]
     pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
     for n in names:
@@ -412,10 +449,10 @@ def test_auto_election_gpu(cuda_lib, oracle_lib):
 # ---- a LAGGING replica runs for coordinator: with journaling the executed accepts have left the
 #      acceptors' memory; the preparer must still learn them (PISM.handlePrepare -> getLoggedAccepts,
 #      GET_ACCEPTED_PVALUES_FROM_DISK) or it would re-decide a decided slot with a new value ------------------------------
-def drive_lagging_election(lib):
+def drive_lagging_election(lib, p1b=False):
     from gigapaxos_b200.paxos_manager import RequestPacket
     from helpers import make_requests
-    pm = make_pm(lib, HashChainApp, checkpoint_interval=100)
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=100, p1b=p1b)
     eng = pm.engine
     names = [f"TESTPaxosApp{i}" for i in range(5)]
     pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
