@@ -116,3 +116,95 @@ def test_elected_coordinator_proposes_the_plan(oracle_lib):
     from test_paxos_manager import drive_view_change
     pm = drive_view_change(oracle_lib, p1b=True)
     assert pm.device_phase1b
+
+
+# ---- the CUDA kernel's own source, run on the host ---------------------------------------------------------------------
+# tests/emu/ compiles gigapaxos_b200/csrc/gpx_phase1b.cuh (k_prepare_tally as the GPU runs it: a scalar kernel over
+# gpx_dev.cuh's structs and index helpers) with g++ and runs it thread by thread.  State goes in as the arrays DevState
+# describes, taken from the oracle engine's rows before the call; outputs and the state the kernel leaves are held
+# against the oracle's.  What this cannot see is the launch glue in gpx_engine.cu -- that is the GPU test's job
+# (tests/test_zz_phase1b_gpu.py).
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    import ctypes
+    import subprocess
+    from helpers import ROOT
+    import os
+    out = str(tmp_path_factory.mktemp("emu") / "libp1b_emu.so")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no CUDA headers")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", cuda_inc,
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "gigapaxos_b200", "csrc"),
+                           "-x", "c++", os.path.join(ROOT, "tests", "emu", "p1b_emu.cpp"), "-o", out])
+    return ctypes.CDLL(out)
+
+
+def _state_arrays(rows, R, G, W, Rcap, rng):
+    """DevState's arrays for phase 1b from dumped rows: acc_aux [L][G], coord_row [L][G] int4, node_slots [L][Rcap][G],
+    prop_win [L][W][G] int4 (a nonzero pattern: only a resign / install may clear it)"""
+    L = R
+    aux = np.zeros((L, G), dtype=np.uint32)
+    crow = np.zeros((L, G, 4), dtype=np.int32)
+    nsl = np.full((L, Rcap, G), -7, dtype=np.int32)
+    for l in range(L):
+        r = rows[l]
+        aux[l] = (r["state"].astype(np.uint32) & 0xFF) | (rng.integers(0, 1 << 16, size=G).astype(np.uint32) << 8)
+        ex = r["coord_exists"] != 0
+        crow[l, :, 0] = np.where(ex, r["coord_bnum"], 0)
+        crow[l, :, 1] = np.where(ex, r["coord_bcoord"], 0)
+        crow[l, :, 2] = np.where(ex, r["next_proposal_slot"], 0)
+        crow[l, :, 3] = np.where(ex, 1 | np.where(r["coord_active"] != 0, 2, 0) | (rng.integers(0, 4, size=G) << 8), 0)
+        nsl[l, :R, :] = r["node_slots"][:, :R].T
+    pwin = rng.integers(1, 1 << 30, size=(L, W, G, 4)).astype(np.int32)
+    return aux, crow, nsl, pwin
+
+
+@pytest.mark.parametrize("R,seed,wrap,block", [(3, 11, False, 64), (3, 12, True, 1), (5, 13, False, 64), (5, 14, True, 7),
+                                               (1, 15, False, 64), (4, 16, False, 33)])
+def test_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, R, seed, wrap, block):
+    import ctypes as C
+    G, W = 160, 8
+    Rcap = R
+    rng = np.random.default_rng(seed)
+    eng = make_engine(oracle_lib, R, G)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for rnd in range(3):
+        preconditions(eng, R, G, rng)
+        els, reps = random_elections(R, G, rng, wrap)
+        rows = dump_all(eng, R, G)
+        aux, crow, nsl, pwin = _state_arrays(rows, R, G, W, Rcap, rng)
+        pwin0, crow0 = pwin.copy(), crow.copy()
+        live = (rows[0]["state"] != abi.ST_FREE).astype(np.uint8)
+        want = eng.handle_prepare_replies(els, reps)  # the oracle: outputs + its engine's new state
+        got = np.zeros(len(els), dtype=abi.election_out_dtype)
+        got.view(np.uint8)[:] = 0xAB  # the kernel must write every byte of its records
+        members = np.array(NODES5[:R], dtype=np.int32)
+        launches = emu_lib.emu_prepare_tally(G, R, W, Rcap, R, ptr(members), ptr(members), ptr(live), ptr(crow), ptr(aux),
+                                             ptr(nsl), ptr(pwin), len(els), ptr(els), ptr(reps), ptr(got), block)
+        assert launches == 1
+        assert_same_out(got, want)
+        after = dump_all(eng, R, G)
+        won = {int(o["gid"]): (int(e["lane"]), (int(e["bnum"]), int(e["bcoord"])))
+               for o, e in zip(want, els) if int(o["verdict"]) == abi.EL_MAJORITY}
+        for l in range(R):
+            a = after[l]
+            ex = a["coord_exists"] != 0
+            assert np.array_equal(crow[l, :, 0], np.where(ex, a["coord_bnum"], 0))
+            assert np.array_equal(crow[l, :, 1], np.where(ex, a["coord_bcoord"], 0))
+            assert np.array_equal(crow[l, :, 2], np.where(ex, a["next_proposal_slot"], 0))
+            for gid in range(G):
+                touched = False
+                if gid in won:
+                    lane, nb = won[gid]
+                    pre = crow0[l, gid]
+                    higher = (pre[3] & 1) and ((int(pre[0]), int(pre[1])) > nb)  # small non-negative ballots here
+                    touched = l == lane or not higher
+                    if l == lane:
+                        assert crow[l, gid, 3] == 3 and np.array_equal(nsl[l, :R, gid], a["node_slots"][gid, :R])
+                    elif touched:
+                        assert not crow[l, gid].any()
+                if touched:
+                    assert not pwin[l, :, gid].any()
+                else:
+                    assert np.array_equal(pwin[l, :, gid], pwin0[l, :, gid]) and np.array_equal(crow[l, gid], crow0[l, gid])

@@ -1,0 +1,84 @@
+"""Phase 1b on the device (k_prepare_tally behind gpx_handle_prepare_replies) against the oracle, through the C ABI:
+random batches of elections (every verdict, GPX_F_MORE continuation records, slots across the int wrap, R = 1..5) --
+the 896-byte result records byte for byte and every row of every lane afterwards -- and whole view changes of the host
+mirror with the tally inside the engine.  (The same kernel source also runs on the host in tests/test_phase1b.py.)
+
+The file sorts last on purpose: k_prepare_tally was written after the round's GPU minutes were spent, so its first run
+on a B200 is the driver's; nothing else depends on it."""
+import numpy as np
+import pytest
+
+from helpers import abi
+from p1b_cases import assert_same_out, dump_all, make_engine, preconditions, random_elections
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("R,seed,wrap", [(3, 21, False), (3, 22, True), (5, 23, False), (5, 24, True), (1, 25, False),
+                                         (4, 26, False), (2, 27, False)])
+def test_phase1b_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed, wrap):
+    G = 300
+    rng = np.random.default_rng(seed)
+    eg, eo = make_engine(cuda_lib, R, G), make_engine(oracle_lib, R, G)
+    verdicts = set()
+    for rnd in range(4):
+        st = rng.bit_generator.state
+        preconditions(eg, R, G, rng)
+        rng.bit_generator.state = st
+        preconditions(eo, R, G, rng)
+        els, reps = random_elections(R, G, rng, wrap)
+        got, want = eg.handle_prepare_replies(els, reps), eo.handle_prepare_replies(els, reps)
+        assert_same_out(got, want)
+        verdicts |= set(int(v) for v in want["verdict"])
+        for rg, ro in zip(dump_all(eg, R, G), dump_all(eo, R, G)):
+            for f in rg.dtype.names:
+                assert np.array_equal(rg[f], ro[f]), (rnd, f)
+    if R >= 3:
+        assert verdicts == {abi.EL_WAITING, abi.EL_MAJORITY, abi.EL_PREEMPTED, abi.EL_DROPPED, abi.EL_OVERFLOW}
+    assert eg.counters()["kernel_launches"] > 0
+
+
+def test_mass_failover_one_launch(cuda_lib, oracle_lib):
+    """a node is lost: every group elects in ONE call (20,000 elections, R = 3, each with a majority of replies carrying
+    accepted pvalues); result records and all rows equal the oracle's"""
+    R, G = 3, 20000
+    rng = np.random.default_rng(5)
+    eg, eo = make_engine(cuda_lib, R, G), make_engine(oracle_lib, R, G)
+    els = np.zeros(G, dtype=abi.election_dtype)
+    els["gid"] = rng.permutation(G)
+    els["lane"] = rng.integers(0, R, size=G)
+    els["bnum"], els["bcoord"] = 1, np.array([100, 101, 102])[els["lane"]]
+    els["slot"] = rng.integers(0, 50, size=G)
+    els["first_reply"], els["n_replies"] = np.arange(G) * 2, 2
+    reps = np.zeros(2 * G, dtype=abi.prepare_reply_dtype)
+    reps["gid"] = np.repeat(els["gid"], 2)
+    reps["bnum"], reps["bcoord"] = 1, np.repeat(els["bcoord"], 2)
+    reps["first_slot"] = np.repeat(els["slot"], 2) - 1
+    for j in range(2):
+        acc = (els["lane"] + j) % R
+        reps["who"][j::2] = acc | (els["lane"] << 8)
+        na = rng.integers(0, 4, size=G)
+        reps["n_accepted"][j::2] = na
+        for a in range(3):
+            sel = np.nonzero(na > a)[0]
+            pv = reps["accepted"][j::2][:, a]
+            pv["slot"][sel] = els["slot"][sel] + a + j
+            pv["bnum"][sel], pv["bcoord"][sel] = 0, 100 + j
+            pv["req_id"][sel] = rng.integers(1, 1 << 40, size=len(sel))
+            pv["payload_len"][sel], pv["flags"][sel] = 8, 1 << 16
+            v = reps["accepted"][j::2]
+            v[:, a] = pv
+            reps["accepted"][j::2] = v
+    got, want = eg.handle_prepare_replies(els, reps), eo.handle_prepare_replies(els, reps)
+    assert np.all(want["verdict"] == abi.EL_MAJORITY) and int(want["n_plan"].max()) >= 3
+    assert_same_out(got, want)
+    for rg, ro in zip(dump_all(eg, R, G), dump_all(eo, R, G)):
+        for f in rg.dtype.names:
+            assert np.array_equal(rg[f], ro[f]), f
+
+
+def test_view_changes_with_the_tally_in_the_engine(cuda_lib, oracle_lib):
+    from test_paxos_manager import _same_end_state, drive_auto_election, drive_lagging_election, drive_view_change
+    _same_end_state(drive_view_change(cuda_lib, p1b=True), drive_view_change(oracle_lib, p1b=True))
+    _same_end_state(drive_auto_election(cuda_lib, p1b=True), drive_auto_election(oracle_lib, p1b=True))
+    _same_end_state(drive_lagging_election(cuda_lib, p1b=True), drive_lagging_election(oracle_lib, p1b=True))
