@@ -70,6 +70,9 @@ public final class PaxosEngine implements AutoCloseable {
 	public static native int handleDecisions(long h, int n, ByteBuffer decisions, ByteBuffer execOut,
 			ByteBuffer extraExecOut, int extraCap, ByteBuffer nExtra);
 	public static native int handlePrepares(long h, int n, ByteBuffer prepares, ByteBuffer prepareRepliesOut);
+	/** phase 1b for n elections (gpx_election_rec, 32 B each) over nReplyRecs gpx_prepare_reply_rec; electionsOut: n x 896 B */
+	public static native int handlePrepareReplies(long h, int n, ByteBuffer elections, int nReplyRecs, ByteBuffer replies,
+			ByteBuffer electionsOut);
 
 	// ---- journal: AbstractPaxosLogger.BatchedLogger :691-716, SQLPaxosLogger.journal :965-1036 ----
 	/** fromAndBytes = {ring position the copy starts at, bytes being copied} */

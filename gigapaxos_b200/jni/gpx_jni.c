@@ -111,6 +111,8 @@ JNIEXPORT jint JNICALL GPX_JNI(logRelease)(JNIEnv* env, jclass cls, jlong h, jin
  *   ACCEPT_REPLY       -> handleAcceptReplies(PISM.handleAcceptReply :1248, PaxosCoordinatorState.handleAcceptReplyMyBallot :597)
  *   DECISION           -> handleDecisions    (PISM.handleCommittedRequest :1432, extractExecuteAndCheckpoint :1619)
  *   PREPARE            -> handlePrepares     (PISM.handlePrepare :900, PaxosAcceptor.handlePrepare :239)
+ *   PREPARE_REPLY      -> handlePrepareReplies (PISM.handlePrepareReply :1017, PaxosCoordinatorState :264-587: tally,
+ *                         carry-over, no-op fill, coordinator installed ACTIVE; the plan comes back for re-proposal)
  * counts come back through a direct IntBuffer / LongBuffer of one element. */
 JNIEXPORT jint JNICALL GPX_JNI(propose)(JNIEnv* env, jclass cls, jlong h, jint n, jobject reqs, jobject payload,
                                         jlong payload_bytes, jobject out_accepts, jobject n_accepts, jobject out_blob,
@@ -142,6 +144,12 @@ JNIEXPORT jint JNICALL GPX_JNI(handleDecisions)(JNIEnv* env, jclass cls, jlong h
 JNIEXPORT jint JNICALL GPX_JNI(handlePrepares)(JNIEnv* env, jclass cls, jlong h, jint n, jobject prepares, jobject out_replies) {
   return gpx_handle_prepares((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_pvalue_hdr*)buf(env, prepares),
                              (gpx_prepare_reply_rec*)buf(env, out_replies));
+}
+JNIEXPORT jint JNICALL GPX_JNI(handlePrepareReplies)(JNIEnv* env, jclass cls, jlong h, jint n, jobject elections,
+                                                     jint n_reply_recs, jobject replies, jobject out_elections) {
+  return gpx_handle_prepare_replies((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_election_rec*)buf(env, elections),
+                                    (uint32_t)n_reply_recs, (const gpx_prepare_reply_rec*)buf(env, replies),
+                                    (gpx_election_out*)buf(env, out_elections));
 }
 /* long logRead(long h, int lane, long from, ByteBuffer dst, long[] out {nCopied, head}): the synchronous journal read
  * (recovery / tests); the steady state uses logDrainAsync */

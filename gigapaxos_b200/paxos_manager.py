@@ -180,7 +180,8 @@ class _Instance:
 class PaxosManager:
     """Mirror of the PaxosManager calls on the hot path, for co-located replicas."""
 
-    def __init__(self, engine: Engine, apps: Sequence[Replicable], nodes: Sequence[int], device_phase1b: bool = False):
+    def __init__(self, engine: Engine, apps: Sequence[Replicable], nodes: Sequence[int],
+                 device_phase1b: Optional[bool] = None):
         if len(apps) != engine.n_lanes or len(nodes) != engine.n_lanes:
             raise ValueError("one app and one node id per lane")
         self.engine = engine
@@ -200,8 +201,8 @@ class PaxosManager:
         self._elect: Dict[str, int] = {}
         self.paused: Dict[str, List[str]] = {}  # paxosID -> HotRestoreInfo string per lane (the pause table)
         # phase 1b (tally of PREPARE_REPLYs, carry-over, no-op fill, install): inside the engine
-        # (gpx_handle_prepare_replies) or by the host-language twin below + gpx_patch
-        self.device_phase1b = device_phase1b
+        # (gpx_handle_prepare_replies, the default when the library has it) or by the host-language twin below + gpx_patch
+        self.device_phase1b = engine.L.has("handle_prepare_replies") if device_phase1b is None else device_phase1b
 
     # ---- instance management ------------------------------------------------------------
     def _alloc_gid(self) -> int:

@@ -12,8 +12,8 @@ NODES5 = [100, 101, 102, 103, 104]
 
 def make_engine(lib, R: int, G: int):
     nodes = NODES5[:R]
-    eng = Engine(lib, make_config(lib, n_lanes=R, max_groups=G, max_batch_recs=4096, max_batch_payload=1 << 20,
-                                  lane_node=nodes))
+    eng = Engine(lib, make_config(lib, n_lanes=R, max_groups=G, max_group_size=R, max_batch_recs=4096,
+                                  max_batch_payload=1 << 20, lane_node=nodes))
     eng.create_groups(group_descs(G, members=tuple(nodes)))
     return eng
 
@@ -121,3 +121,12 @@ def assert_same_out(a: np.ndarray, b: np.ndarray):
     for f in ("gid", "verdict", "next_slot", "n_plan", "flags", "node_slots"):
         assert np.array_equal(a[f], b[f]), (f, a[f], b[f])
     assert a.tobytes() == b.tobytes()
+
+
+def assert_same_rows(eng_a, eng_b, R: int, G: int, ctx=None):
+    """every field of every row of every lane; rows of destroyed groups (state FREE) only agree on being FREE"""
+    for ra, rb in zip(dump_all(eng_a, R, G), dump_all(eng_b, R, G)):
+        assert np.array_equal(ra["state"], rb["state"]), (ctx, "state")
+        live = rb["state"] != abi.ST_FREE
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f][live], rb[f][live]), (ctx, f)

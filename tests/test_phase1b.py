@@ -208,3 +208,16 @@ def test_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, R, seed, w
                     assert not pwin[l, :, gid].any()
                 else:
                     assert np.array_equal(pwin[l, :, gid], pwin0[l, :, gid]) and np.array_equal(crow[l, gid], crow0[l, gid])
+
+
+def test_phase1b_record_sizes_match_the_header(tmp_path):
+    import os
+    import subprocess
+    from helpers import ROOT
+    (tmp_path / "t.c").write_text('#include "gpx.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %d %d\\n", '
+                                  "sizeof(gpx_election_rec), sizeof(gpx_carryover), sizeof(gpx_election_out), "
+                                  "sizeof(gpx_prepare_reply_rec), GPX_MAX_CARRY, GPX_MAX_PLAN);}\n")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "t"), str(tmp_path / "t.c")])
+    out = [int(x) for x in subprocess.check_output([str(tmp_path / "t")]).decode().split()]
+    assert out == [abi.election_dtype.itemsize, abi.carryover_dtype.itemsize, abi.election_out_dtype.itemsize,
+                   abi.prepare_reply_dtype.itemsize, abi.GPX_MAX_CARRY, abi.GPX_MAX_PLAN] == [32, 48, 896, 288, 32, 16]

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from helpers import abi
-from p1b_cases import assert_same_out, dump_all, make_engine, preconditions, random_elections
+from p1b_cases import assert_same_out, assert_same_rows, make_engine, preconditions, random_elections
 
 pytestmark = pytest.mark.gpu
 
@@ -30,9 +30,7 @@ def test_phase1b_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed, wrap):
         got, want = eg.handle_prepare_replies(els, reps), eo.handle_prepare_replies(els, reps)
         assert_same_out(got, want)
         verdicts |= set(int(v) for v in want["verdict"])
-        for rg, ro in zip(dump_all(eg, R, G), dump_all(eo, R, G)):
-            for f in rg.dtype.names:
-                assert np.array_equal(rg[f], ro[f]), (rnd, f)
+        assert_same_rows(eg, eo, R, G, rnd)
     if R >= 3:
         assert verdicts == {abi.EL_WAITING, abi.EL_MAJORITY, abi.EL_PREEMPTED, abi.EL_DROPPED, abi.EL_OVERFLOW}
     assert eg.counters()["kernel_launches"] > 0
@@ -72,9 +70,7 @@ def test_mass_failover_one_launch(cuda_lib, oracle_lib):
     got, want = eg.handle_prepare_replies(els, reps), eo.handle_prepare_replies(els, reps)
     assert np.all(want["verdict"] == abi.EL_MAJORITY) and int(want["n_plan"].max()) >= 3
     assert_same_out(got, want)
-    for rg, ro in zip(dump_all(eg, R, G), dump_all(eo, R, G)):
-        for f in rg.dtype.names:
-            assert np.array_equal(rg[f], ro[f]), f
+    assert_same_rows(eg, eo, R, G)
 
 
 def test_view_changes_with_the_tally_in_the_engine(cuda_lib, oracle_lib):
