@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(GPX_P1B_BLOCK) k_prepare_tally(const __grid_co
           }
           nextSlot = (int)((unsigned)maxCarry + 1u); /* :436 */
           /* processStop :478-554: all ballots are the new one here, nothing is converted; a regular request behind a
-           * STOP is the reference's assert(false) :527 */
+           * STOP is the reference's assert(false) :524 */
           bool stopExists = false;
           for (uint32_t a = 0; a < np; a++) {
             if (!p_stop[a]) continue;

@@ -494,8 +494,8 @@ class PaxosManager:
     def _process_stop(plan: List[tuple], next_slot: int):
         """PCS.processStop :478-554.  Every proposal carries the NEW coordinator's ballot here (the constructor of
         ProposalStateAtCoordinator :153-157 re-stamps it), so neither of its two conversions (request behind a
-        higher-ballot STOP -> STOP :497-511, STOP before a higher-ballot request -> no-op :512-526) can be taken: a
-        regular request behind a STOP is the reference's assert(false) :527, reported as ELF_STOP_ORDER.  What remains
+        higher-ballot STOP -> STOP :495-509, STOP before a higher-ballot request -> no-op :510-523) can be taken: a
+        regular request behind a STOP is the reference's assert(false) :524, reported as ELF_STOP_ORDER.  What remains
         is the tail :538-542: a STOP was carried over but the last proposal is not one -> a fresh STOP behind it."""
         is_stop = lambda e: e[1] == abi.CO_STOP_NEW or (e[1] == abi.CO_PVALUE and bool(int(e[2]["flags"]) & 2))
         flags = 0

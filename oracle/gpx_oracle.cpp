@@ -1483,7 +1483,7 @@ struct PreActiveCoordinatorState { /* PaxosCoordinatorState.java:67-178 in the p
       for (const Phase1Proposal& psac2 : myProposals)
         if (!psac2.isStopRequest() && !psac2.isNoop() && jsub(psac1.slot, psac2.slot) < 0) {
           /* both pvalues carry MY ballot here (ProposalStateAtCoordinator's ctor :153-157 re-stamps it), so neither
-           * "stop ballot > other ballot" :497 nor "<" :512 can hold: the reference reaches its assert(false) :527 */
+           * "stop ballot > other ballot" :495 nor "<" :510 can hold: the reference reaches its assert(false) :524 */
           stopOrder = true;
         }
     }
