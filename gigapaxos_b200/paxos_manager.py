@@ -266,14 +266,14 @@ class PaxosManager:
     # ---- view change: the host half of phase 1 over the device's phase 1a -----------------------------------
     def runForCoordinator(self, paxosID: str, lane: int) -> bool:
         """PISM.checkRunForCoordinator(forceRun) :2090-2150 at the node of `lane`, then PISM.handlePrepareReply
-        :957-990 / PCS.isPrepareAcceptedByMajority :326-391, combinePValuesOntoProposals :393-444, processStop
+        :1017-1068 / PCS.isPrepareAcceptedByMajority :326-391, combinePValuesOntoProposals :393-444, processStop
         :478-554 and spawnCommandersForProposals :556-575 for the PREPARE_REPLYs of the local lanes.
 
-        The acceptors answer on the device (gpx_handle_prepares); the tally is host logic (rare, variable-size); the
-        result goes back as gpx_patch records (resign the old coordinator, install the new one, recordSlotNumber) and
-        the carried-over pvalues are re-proposed in slot order under the new ballot, their request bodies read from
-        the log ring of the acceptor that reported them.  Returns False when the election was preempted or found no
-        majority."""
+        The acceptors answer on the device (gpx_handle_prepares); the replies are tallied, the carry-over is laid out
+        and the new coordinator installed by gpx_handle_prepare_replies (or, device_phase1b = False, by the
+        host-language twin and gpx_patch records); the carried-over pvalues are then re-proposed in slot order under
+        the new ballot, their request bodies read from the log ring of the acceptor that reported them.  Returns False
+        when the election was preempted or found no majority."""
         inst = self.instances.get(paxosID)
         if inst is None or inst.stopped:
             return False
@@ -326,6 +326,69 @@ class PaxosManager:
                 reqs = self._requests_of(paxosID, pv, src, me)
             self._submit(reqs, carryover=True)
         return True
+
+    def runForCoordinators(self, paxosIDs: Sequence[str], lane: int) -> Dict[str, bool]:
+        """The mass case: the node that coordinated these groups is gone and the node of `lane` runs for coordinator of
+        all of them at once (the failure detector's sweep fires PISM.checkRunForCoordinator :2090-2150 per instance).
+        ONE gpx_handle_prepares call, ONE gpx_handle_prepare_replies call (k_prepare_tally: one thread per election),
+        then plan entry j of every elected group in round j (spawnCommandersForProposals :556-575) -- at most
+        GPX_MAX_PLAN + 1 rounds however many groups elect.  A group whose candidate is behind one of its acceptors takes
+        the single-group path (it needs the acceptors' logged accepts, or a sync, first)."""
+        eng, L, me = self.engine, self.engine.n_lanes, self.nodes[lane]
+        res: Dict[str, bool] = {}
+        names = []
+        for n in paxosIDs:
+            inst = self.instances.get(n)
+            if inst is None or inst.stopped:
+                res[n] = False
+            elif n not in res and n not in names:
+                names.append(n)
+        if not self.device_phase1b or not names:
+            for n in names:
+                res[n] = self.runForCoordinator(n, lane)
+            return res
+        gids = np.array([self.instances[n].gid for n in names], dtype=np.uint32)
+        rows = [eng.dump_rows(gids, l) for l in range(L)]
+        cur = rows[lane]
+        behind = np.zeros(len(names), dtype=bool)
+        for l in range(L):
+            if l != lane:
+                behind |= (rows[l]["acc_slot"].astype(np.int64) - cur["acc_slot"].astype(np.int64)).astype(np.int32) > 0
+        batch = [i for i in range(len(names)) if not behind[i]]
+        if batch:
+            b = np.array(batch)
+            prep = np.zeros(len(b), dtype=abi.decision_dtype)
+            prep["gid"], prep["slot"] = gids[b], cur["acc_slot"][b]  # PreparePacket(newBallot, paxosState.getSlot())
+            prep["bnum"], prep["bcoord"] = cur["acc_bnum"][b] + 1, me  # new Ballot(curBallot.ballotNumber + 1, myID)
+            prep["flags"], prep["dst_mask"] = abi.F_PREPARE, (1 << L) - 1
+            replies = eng.handle_prepares(prep)  # reply of PREPARE i at lane l: index i * L + l
+            els = np.zeros(len(b), dtype=abi.election_dtype)
+            els["gid"], els["lane"], els["bnum"], els["bcoord"] = prep["gid"], lane, prep["bnum"], me
+            els["slot"], els["first_reply"], els["n_replies"] = prep["slot"], np.arange(len(b)) * L, L
+            outs = eng.handle_prepare_replies(els, replies)
+            plans = {}
+            for k, i in enumerate(batch):
+                o = outs[k]
+                res[names[i]] = int(o["verdict"]) == abi.EL_MAJORITY
+                if res[names[i]] and int(o["n_plan"]):
+                    plans[names[i]] = o["plan"][: int(o["n_plan"])]
+            for j in range(max((len(p) for p in plans.values()), default=0)):
+                reqs: List[RequestPacket] = []
+                for n in sorted(plans, key=lambda x: self.instances[x].gid):
+                    if j >= len(plans[n]):
+                        continue
+                    c = plans[n][j]
+                    if int(c["kind"]) == abi.CO_NOOP:
+                        reqs.append(RequestPacket(n, 0, NO_OP, entry_replica=me))
+                    elif int(c["kind"]) == abi.CO_STOP_NEW:
+                        reqs.append(RequestPacket(n, 0, b"STOP", stop=True, entry_replica=me))  # PCS :541
+                    else:  # reply record index i * L + l: the acceptor at lane l holds the body
+                        reqs.extend(self._requests_of(n, c["pv"], int(c["src_reply"]) % L, me))
+                self._submit(reqs, carryover=True)
+        for i in range(len(names)):
+            if behind[i]:
+                res[names[i]] = self.runForCoordinator(names[i], lane)
+        return res
 
     def _phase1b_host(self, gid, lane, R, new_ballot, acc_slot, replies, logged):
         """phase 1b in the host language (tally_prepare_replies / combine_carryover), its result installed with
@@ -742,12 +805,16 @@ class PaxosManager:
             elif st == abi.RS_BATCHED and cur is not None:
                 batches[cur].append(reqs_l[i])
         done = self._apply(np.concatenate([ex, extra]), batches)
+        by_lane: Dict[int, List[str]] = {}
         for name, lane in self._elect.items():
-            if not self.runForCoordinator(name, lane):  # preempted / no majority: give the requests back
-                for r in self.queue.pop(name, []):
-                    self.slow_path.append((name, r.request_id, abi.RS_NOCOORD))
-                    self.outstanding.pop(r.request_id, None)
+            by_lane.setdefault(lane, []).append(name)
         self._elect = {}
+        for lane, names in by_lane.items():
+            for name, won in self.runForCoordinators(names, lane).items():
+                if not won:  # preempted / no majority: give the requests back
+                    for r in self.queue.pop(name, []):
+                        self.slow_path.append((name, r.request_id, abi.RS_NOCOORD))
+                        self.outstanding.pop(r.request_id, None)
         return done
 
     def _apply(self, ex: np.ndarray, batches: Dict[int, List[RequestPacket]]) -> int:

@@ -221,3 +221,64 @@ def test_phase1b_record_sizes_match_the_header(tmp_path):
     out = [int(x) for x in subprocess.check_output([str(tmp_path / "t")]).decode().split()]
     assert out == [abi.election_dtype.itemsize, abi.carryover_dtype.itemsize, abi.election_out_dtype.itemsize,
                    abi.prepare_reply_dtype.itemsize, abi.GPX_MAX_CARRY, abi.GPX_MAX_PLAN] == [32, 48, 896, 288, 32, 16]
+
+
+# ---- the mass case through the host mirror: one node is lost, the next one is elected in all its groups at once ---------
+def drive_mass_failover(lib, batched: bool, p1b: bool = True, n_groups: int = 40):
+    from gigapaxos_b200.paxos_manager import HashChainApp
+    from helpers import Engine, make_config, make_requests
+    NODES = [100, 101, 102]
+    eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20, checkpoint_interval=100))
+    pm = PaxosManager(eng, [HashChainApp() for _ in NODES], NODES, device_phase1b=p1b)
+    names = [f"TESTPaxosApp{i}" for i in range(n_groups)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    for r in range(3):
+        for n in names:
+            pm.propose(n, f"{n}:{r}".encode())
+        pm.run_round()
+    gids = np.array([pm.instances[n].gid for n in names], dtype=np.uint32)
+    rows0 = eng.dump_rows(gids, 0)
+    coord = np.array([NODES.index(int(r["acc_bcoord"])) for r in rows0])
+    dead = int(np.bincount(coord, minlength=3).argmax())  # the node that coordinates most groups is lost
+    mine = [i for i in range(n_groups) if coord[i] == dead]
+    assert len(mine) >= 5
+    # before it dies its ACCEPTs for up to three more slots reach a majority, a minority, one acceptor (a gap for some)
+    for k, reach in enumerate((0b011, 0b101, 0b110, 0b100)):
+        sel = [i for i in mine if (i + k) % 4 != 0]  # not every group gets every slot
+        if not sel:
+            continue
+        reqs, pay = make_requests(gids[sel], payload_len=7 + k, seed=6, round_no=k)
+        reqs["flags"] = dead << 8
+        reqs["entry_node"] = NODES[dead]
+        acc, blob, st = eng.propose(reqs, pay)
+        assert np.all(st > 0)
+        acc["dst_mask"] = reach
+        eng.handle_accepts(acc, blob)
+    new = (dead + 1) % 3
+    cand = [names[i] for i in mine]
+    if batched:
+        won = pm.runForCoordinators(cand + ["nonexistent"], new)
+        assert won.pop("nonexistent") is False
+    else:
+        won = {n: pm.runForCoordinator(n, new) for n in cand}
+    assert all(won.values()) and len(won) == len(mine)
+    rows = [eng.dump_rows(gids[mine], l) for l in range(3)]
+    assert np.all(rows[new]["coord_exists"] == 1) and np.all(rows[new]["coord_active"] == 1)
+    assert np.all(rows[new]["coord_bcoord"] == NODES[new]) and not rows[dead]["coord_exists"].any()
+    assert np.array_equal(rows[0]["acc_slot"], rows[1]["acc_slot"]) and np.array_equal(rows[1]["acc_slot"], rows[2]["acc_slot"])
+    assert np.all(rows[0]["acc_slot"] >= rows0["acc_slot"][mine] + 1)  # the carried-over slots were decided everywhere
+    s0 = pm.apps[0].state
+    assert all(a.state == s0 for a in pm.apps)
+    for n in names:  # business as usual under old and new coordinators
+        pm.propose(n, f"{n}:after".encode(), entry_node=NODES[new])
+    pm.run_round()
+    pm.flush()
+    assert all(a.state == pm.apps[0].state for a in pm.apps) and not pm.outstanding
+    return pm
+
+
+def test_mass_failover_batched_equals_one_by_one(oracle_lib):
+    from test_paxos_manager import _same_end_state
+    a = drive_mass_failover(oracle_lib, batched=True)
+    _same_end_state(a, drive_mass_failover(oracle_lib, batched=False))
+    _same_end_state(a, drive_mass_failover(oracle_lib, batched=False, p1b=False))

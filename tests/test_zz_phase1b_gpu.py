@@ -78,3 +78,11 @@ def test_view_changes_with_the_tally_in_the_engine(cuda_lib, oracle_lib):
     _same_end_state(drive_view_change(cuda_lib, p1b=True), drive_view_change(oracle_lib, p1b=True))
     _same_end_state(drive_auto_election(cuda_lib, p1b=True), drive_auto_election(oracle_lib, p1b=True))
     _same_end_state(drive_lagging_election(cuda_lib, p1b=True), drive_lagging_election(oracle_lib, p1b=True))
+
+
+def test_mass_failover_through_the_mirror(cuda_lib, oracle_lib):
+    """PaxosManager.runForCoordinators: one gpx_handle_prepares + one gpx_handle_prepare_replies call for all groups of the
+    lost node, then plan entry j of every elected group per round"""
+    from test_paxos_manager import _same_end_state
+    from test_phase1b import drive_mass_failover
+    _same_end_state(drive_mass_failover(cuda_lib, batched=True), drive_mass_failover(oracle_lib, batched=True))
