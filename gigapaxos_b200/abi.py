@@ -269,6 +269,16 @@ class Engine:
         rows = np.ascontiguousarray(rows, dtype=row_dtype)
         self.L.check(self.L.fn("load_rows")(self._h, C.c_uint32(len(rows)), _ptr(rows)))
 
+    def pause_groups(self, gids):
+        """The deactivation sweep (gpx_pause_groups): -> (rows [n, n_lanes] of gpx_row, paused [n] bool).  Rows of groups
+        that did not pause are zero."""
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        n = len(gids)
+        rows = np.zeros((max(n, 1), self.n_lanes), dtype=row_dtype)
+        paused = np.zeros(max(n, 1), dtype=np.uint8)
+        self.L.check(self.L.fn("pause_groups")(self._h, C.c_uint32(n), _ptr(gids), _ptr(rows), _ptr(paused)))
+        return rows[:n], paused[:n].astype(bool)
+
     def patch(self, patches: np.ndarray):
         patches = np.ascontiguousarray(patches, dtype=patch_dtype)
         self.L.check(self.L.fn("patch")(self._h, C.c_uint32(len(patches)), _ptr(patches)))

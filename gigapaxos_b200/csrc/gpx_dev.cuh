@@ -162,6 +162,69 @@ __device__ __forceinline__ GroupCtx group_ctx(const DevState& S, uint32_t gid) {
   return g;
 }
 
+/* ---- per-group helpers shared by the management kernels (gpx_kernels.cuh) and k_pause_groups (gpx_pause.cuh) ---- */
+/* the HotRestoreInfo field set of (gid, lane) (paxosutil/HotRestoreInfo.java:40-58, PISM.tryPause :2004-2025) */
+__device__ __forceinline__ void dump_row(const DevState& S, uint32_t lane, uint32_t gid, gpx_row& r) {
+  memset(&r, 0, sizeof r);
+  r.gid = gid;
+  r.lane = lane;
+  if (gid < S.G) {
+    const uint32_t meta = S.grp_meta[gid];
+    const size_t ri = row_idx(S, lane, gid);
+    const int4 row = S.acc_row[ri];
+    const int4 c = S.coord_row[ri];
+    const bool live = (meta & GPX_META_LIVE) != 0;
+    r.acc_slot = row.x;
+    r.acc_bnum = row.y;
+    r.acc_bcoord = row.z;
+    r.acc_gc_slot = row.w;
+    r.state = live ? (int)GPX_AUX_STATE(S.acc_aux[ri]) : GPX_ST_FREE;
+    const bool ex = ((unsigned)c.w & GPX_CF_EXISTS) != 0;
+    r.coord_exists = ex;
+    r.coord_active = ex && (((unsigned)c.w & GPX_CF_ACTIVE) != 0);
+    r.coord_bnum = ex ? c.x : 0;
+    r.coord_bcoord = ex ? c.y : 0;
+    r.next_proposal_slot = ex ? c.z : 0;
+    if (live) {
+      const MsetInfo* ms = &S.msets[meta & 0xffffu];
+      const uint32_t R = (meta >> 16) & 0xffu;
+      r.n_members = (int)R;
+      for (uint32_t m = 0; m < R; m++) {
+        r.members[m] = ms->nodes[m];
+        r.node_slots[m] = ex ? S.node_slots[ns_idx(S, lane, m, gid)] : 0;
+      }
+    }
+  }
+}
+/* gpx_get_group_flags' byte for (gid, lane), gid < S.G: the sticky group flags | NOT_CAUGHT_UP */
+__device__ __forceinline__ uint32_t group_flags(const DevState& S, uint32_t lane, uint32_t gid) {
+  const size_t ri = row_idx(S, lane, gid);
+  const uint32_t aux = S.acc_aux[ri];
+  /* PaxosAcceptor.caughtUp :452-459 / PCS.caughtUp :758 */
+  bool busy = GPX_AUX_PRESENT(aux) != 0; /* committedRequests not empty */
+  const int4 crow = S.coord_row[ri];
+  if (((unsigned)crow.w & GPX_CF_EXISTS) && ((unsigned)crow.w >> 8)) busy = true; /* myProposals not empty */
+  if (!S.journaling) { /* acceptedProposals not empty (journaling: accepted pvalues come from the log) */
+    const int gc = S.acc_row[ri].w;
+    for (uint32_t w = 0; w < S.W; w++) {
+      const size_t ai = 2 * win_idx(S, lane, w, gid);
+      const int4 a0 = S.acc_win[ai], a1 = S.acc_win[ai + 1];
+      if (((unsigned)a1.w & GPX_ENT_VALID) && jsub(a0.x, gc) > 0) busy = true;
+    }
+  }
+  return GPX_AUX_FLAGS(aux) | (busy ? GPX_GF_NOT_CAUGHT_UP_BIT : 0u);
+}
+/* PaxosManager.kill :2162 / softCrash :2284-2300: no instance behind this gid any more */
+__device__ __forceinline__ void free_group(const DevState& S, uint32_t gid) {
+  S.grp_meta[gid] = 0;
+  for (uint32_t l = 0; l < S.L; l++) {
+    const size_t ri = row_idx(S, l, gid);
+    S.acc_row[ri] = make_int4(0, -1, -1, -1);
+    S.acc_aux[ri] = GPX_ST_FREE;
+    S.coord_row[ri] = make_int4(0, 0, 0, 0);
+  }
+}
+
 __device__ __forceinline__ int4 ldg4(const void* p) { return *reinterpret_cast<const int4*>(p); }
 __device__ __forceinline__ void stg4(void* p, int4 v) { *reinterpret_cast<int4*>(p) = v; }
 /* streaming (read-once) 128-bit load: records and payloads are consumed exactly once */

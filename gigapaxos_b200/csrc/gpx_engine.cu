@@ -24,6 +24,7 @@
 #include "gpx_spread.cuh"
 #include "gpx_prepare.cuh"
 #include "gpx_phase1b.cuh"
+#include "gpx_pause.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -1544,6 +1545,58 @@ int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, e->d_misc, n, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  return GPX_OK;
+}
+
+/* the deactivation sweep: one launch of k_pause_groups (gpx_pause.cuh) */
+int gpx_pause_groups(gpx_engine* e, uint32_t n, const uint32_t* gids, gpx_row* out_rows, uint8_t* out_paused) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (n == 0) return GPX_OK;
+  if (!gids || !out_rows || !out_paused) return fail(GPX_EINVAL, "null argument");
+  {
+    std::vector<uint32_t> g(gids, gids + n);
+    std::sort(g.begin(), g.end());
+    if (std::adjacent_find(g.begin(), g.end()) != g.end()) return fail(GPX_EINVAL, "a gid appears twice in the batch");
+  }
+  const uint32_t L = e->cfg.n_lanes;
+  const size_t gid_bytes = ((size_t)n * 4 + 15) & ~(size_t)15;
+  const size_t row_bytes = (size_t)n * L * sizeof(gpx_row);
+  const size_t flag_off = gid_bytes + ((row_bytes + 15) & ~(size_t)15);
+  int rc = e->ensure_misc(flag_off + n);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  uint8_t* base = (uint8_t*)e->d_misc;
+  CK(cudaMemcpyAsync(base, gids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  PauseArgs A;
+  A.gids = (const uint32_t*)base;
+  A.n = n;
+  A.rows = (gpx_row*)(base + gid_bytes);
+  A.paused = base + flag_off;
+  k_pause_groups<<<cdiv(n, GPX_PAUSE_BLOCK), GPX_PAUSE_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_paused, A.paused, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  /* only the rows of the paused groups were written: copy those (runs of consecutive paused entries) */
+  for (uint32_t i = 0; i < n;) {
+    if (!out_paused[i]) {
+      i++;
+      continue;
+    }
+    uint32_t j = i;
+    while (j < n && out_paused[j]) j++;
+    CK(cudaMemcpyAsync(out_rows + (size_t)i * L, A.rows + (size_t)i * L, (size_t)(j - i) * L * sizeof(gpx_row),
+                       cudaMemcpyDeviceToHost, st));
+    i = j;
+  }
+  CK(cudaStreamSynchronize(st));
+  for (uint32_t i = 0; i < n; i++) { /* version and paxosID hash live on the host (as in gpx_dump_rows / _destroy_groups) */
+    if (!out_paused[i] || gids[i] >= e->cfg.max_groups) continue;
+    for (uint32_t l = 0; l < L; l++) {
+      out_rows[(size_t)i * L + l].version = e->h_version[gids[i]];
+      out_rows[(size_t)i * L + l].name_hash = e->h_name_hash[gids[i]];
+    }
+    e->h_name_hash[gids[i]] = e->h_version[gids[i]] = 0;
+  }
   return GPX_OK;
 }
 

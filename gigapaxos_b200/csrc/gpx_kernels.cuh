@@ -1582,51 +1582,15 @@ __global__ void k_destroy_groups(const __grid_constant__ DevState S, const uint3
   if (i >= n) return;
   const uint32_t gid = gids[i];
   if (gid >= S.G) return;
-  S.grp_meta[gid] = 0;
-  for (uint32_t l = 0; l < S.L; l++) {
-    const size_t ri = row_idx(S, l, gid);
-    S.acc_row[ri] = make_int4(0, -1, -1, -1);
-    S.acc_aux[ri] = GPX_ST_FREE;
-    S.coord_row[ri] = make_int4(0, 0, 0, 0);
-  }
+  free_group(S, gid);
 }
 
 __global__ void k_dump_rows(const __grid_constant__ DevState S, const uint32_t* gids, uint32_t n, uint32_t lane,
                             gpx_row* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t gid = gids[i];
   gpx_row r;
-  memset(&r, 0, sizeof r);
-  r.gid = gid;
-  r.lane = lane;
-  if (gid < S.G) {
-    const uint32_t meta = S.grp_meta[gid];
-    const size_t ri = row_idx(S, lane, gid);
-    const int4 row = S.acc_row[ri];
-    const int4 c = S.coord_row[ri];
-    const bool live = (meta & GPX_META_LIVE) != 0;
-    r.acc_slot = row.x;
-    r.acc_bnum = row.y;
-    r.acc_bcoord = row.z;
-    r.acc_gc_slot = row.w;
-    r.state = live ? (int)GPX_AUX_STATE(S.acc_aux[ri]) : GPX_ST_FREE;
-    const bool ex = ((unsigned)c.w & GPX_CF_EXISTS) != 0;
-    r.coord_exists = ex;
-    r.coord_active = ex && (((unsigned)c.w & GPX_CF_ACTIVE) != 0);
-    r.coord_bnum = ex ? c.x : 0;
-    r.coord_bcoord = ex ? c.y : 0;
-    r.next_proposal_slot = ex ? c.z : 0;
-    if (live) {
-      const MsetInfo* ms = &S.msets[meta & 0xffffu];
-      const uint32_t R = (meta >> 16) & 0xffu;
-      r.n_members = (int)R;
-      for (uint32_t m = 0; m < R; m++) {
-        r.members[m] = ms->nodes[m];
-        r.node_slots[m] = ex ? S.node_slots[ns_idx(S, lane, m, gid)] : 0;
-      }
-    }
-  }
+  dump_row(S, lane, gids[i], r);
   out[i] = r;
 }
 
@@ -1727,22 +1691,7 @@ __global__ void k_get_flags(const __grid_constant__ DevState S, uint32_t lane, c
     out[i] = 0;
     return;
   }
-  const uint32_t gid = gids[i];
-  const size_t ri = row_idx(S, lane, gid);
-  const uint32_t aux = S.acc_aux[ri];
-  /* PaxosAcceptor.caughtUp :452-459 / PCS.caughtUp :758 */
-  bool busy = GPX_AUX_PRESENT(aux) != 0; /* committedRequests not empty */
-  const int4 crow = S.coord_row[ri];
-  if (((unsigned)crow.w & GPX_CF_EXISTS) && ((unsigned)crow.w >> 8)) busy = true; /* myProposals not empty */
-  if (!S.journaling) { /* acceptedProposals not empty (journaling: accepted pvalues come from the log) */
-    const int gc = S.acc_row[ri].w;
-    for (uint32_t w = 0; w < S.W; w++) {
-      const size_t ai = 2 * win_idx(S, lane, w, gid);
-      const int4 a0 = S.acc_win[ai], a1 = S.acc_win[ai + 1];
-      if (((unsigned)a1.w & GPX_ENT_VALID) && jsub(a0.x, gc) > 0) busy = true;
-    }
-  }
-  out[i] = (uint8_t)(GPX_AUX_FLAGS(aux) | (busy ? GPX_GF_NOT_CAUGHT_UP_BIT : 0u));
+  out[i] = (uint8_t)group_flags(S, lane, gids[i]);
 }
 
 /* ============================== digests (DIGEST_REQUESTS) ============================== */

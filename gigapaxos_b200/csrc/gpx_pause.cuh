@@ -1,0 +1,51 @@
+/*
+ * gpx_pause.cuh -- k_pause_groups: the deactivation sweep as one launch (PaxosManager.Deactivator :2951 ->
+ * syncAndDeactivate :2806-2900 -> pause(Map, dequeue) :2327-2366; the contract is the comment above gpx_pause_groups
+ * in include/gpx.h).
+ *
+ * One thread per gid of the batch.  PISM.tryPause :2004-2035 at every local lane: the group is paused only if it is
+ * live, not stopped, and every lane is caught up (PaxosAcceptor.caughtUp :452-459, PaxosCoordinator.caughtUp: nothing
+ * committed-but-unexecuted, no proposal in flight, no live accepted pvalue when accepts are kept in memory).  Then the
+ * HotRestoreInfo field set of every lane goes to out_rows[i * L + lane] (dump_row: what gpx_dump_rows writes) and the
+ * gid is freed (free_group: what gpx_destroy_groups does -- forceStop + softCrash).  A group that does not pause is not
+ * touched and its rows are not written.  gigapaxos keeps millions of idle groups by moving them out of memory
+ * (PaxosConfig PAUSE_BATCH_SIZE :715, DEACTIVATION_PERIOD :291); here that is a sweep over the idle gids at HBM speed:
+ * 4 + 188 * L bytes out and ~40 * L bytes in per paused group.
+ *
+ * Plain C++ over gpx_dev.cuh (no warp primitives, no shared memory, no inline PTX): tests/emu/ runs this source on the
+ * host against the oracle.
+ */
+#pragma once
+#include "gpx_dev.cuh"
+
+struct PauseArgs {
+  const uint32_t* gids;
+  uint32_t n;
+  gpx_row* rows;   /* [n * L] */
+  uint8_t* paused; /* [n] */
+};
+
+#define GPX_PAUSE_BLOCK 128
+
+__global__ void __launch_bounds__(GPX_PAUSE_BLOCK) k_pause_groups(const __grid_constant__ DevState S,
+                                                                  const __grid_constant__ PauseArgs A) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) atomicAdd(&S.ctr[C_KERNEL_LAUNCHES], 1ull);
+  if (i >= A.n) return;
+  const uint32_t gid = A.gids[i];
+  const GroupCtx g = group_ctx(S, gid);
+  bool ok = g.live;
+  for (uint32_t l = 0; ok && l < S.L; l++) {
+    if (g.ms->idx_of_lane[l] == 0xffu) continue; /* this lane hosts no replica of the group */
+    if (!st_usable(S.acc_aux[row_idx(S, l, gid)])) ok = false; /* stopped / recovering: not a pause candidate */
+    else if (group_flags(S, l, gid) & GPX_GF_NOT_CAUGHT_UP_BIT) ok = false;
+  }
+  A.paused[i] = ok ? 1 : 0;
+  if (!ok) return;
+  for (uint32_t l = 0; l < S.L; l++) {
+    gpx_row r;
+    dump_row(S, l, gid, r);
+    A.rows[(size_t)i * S.L + l] = r;
+  }
+  free_group(S, gid);
+}

@@ -69,6 +69,8 @@ public final class PaxosEngine implements AutoCloseable {
 			ByteBuffer nDecisions);
 	public static native int handleDecisions(long h, int n, ByteBuffer decisions, ByteBuffer execOut,
 			ByteBuffer extraExecOut, int extraCap, ByteBuffer nExtra);
+	/** the Deactivator's batch (PaxosManager.pause(Map, dequeue)): rowsOut n x nLanes x 188 B, pausedOut n bytes; unpause = loadRows */
+	public static native int pauseGroups(long h, int n, ByteBuffer gids, ByteBuffer rowsOut, ByteBuffer pausedOut);
 	public static native int handlePrepares(long h, int n, ByteBuffer prepares, ByteBuffer prepareRepliesOut);
 	/** phase 1b for n elections (gpx_election_rec, 32 B each) over nReplyRecs gpx_prepare_reply_rec; electionsOut: n x 896 B */
 	public static native int handlePrepareReplies(long h, int n, ByteBuffer elections, int nReplyRecs, ByteBuffer replies,

@@ -145,6 +145,13 @@ JNIEXPORT jint JNICALL GPX_JNI(handlePrepares)(JNIEnv* env, jclass cls, jlong h,
   return gpx_handle_prepares((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_pvalue_hdr*)buf(env, prepares),
                              (gpx_prepare_reply_rec*)buf(env, out_replies));
 }
+/* int pauseGroups(long h, int n, ByteBuffer gids, ByteBuffer rowsOut [n x nLanes x gpx_row], ByteBuffer pausedOut [n]):
+ * PaxosManager.pause(Map, dequeue) :2327-2366 for the Deactivator's batch; unpause is loadRows */
+JNIEXPORT jint JNICALL GPX_JNI(pauseGroups)(JNIEnv* env, jclass cls, jlong h, jint n, jobject gids, jobject rows_out,
+                                            jobject paused_out) {
+  return gpx_pause_groups((gpx_engine*)(intptr_t)h, (uint32_t)n, (const uint32_t*)buf(env, gids), (gpx_row*)buf(env, rows_out),
+                          (uint8_t*)buf(env, paused_out));
+}
 JNIEXPORT jint JNICALL GPX_JNI(handlePrepareReplies)(JNIEnv* env, jclass cls, jlong h, jint n, jobject elections,
                                                      jint n_reply_recs, jobject replies, jobject out_elections) {
   return gpx_handle_prepare_replies((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_election_rec*)buf(env, elections),

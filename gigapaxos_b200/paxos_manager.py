@@ -692,6 +692,30 @@ class PaxosManager:
         self._release(paxosID)  # forceStop + removal from pinstances
         return True
 
+    def pauseBatch(self, paxosIDs: Sequence[str]) -> List[str]:
+        """PaxosManager.pause(Map, dequeue) :2327-2366, the body of the Deactivator's sweep (syncAndDeactivate :2806-2900):
+        ONE gpx_pause_groups call tries every candidate (PISM.tryPause at every replica), returns the HotRestoreInfo rows of
+        those that were caught up and frees their gids; the rows go into the pause table as the strings
+        SQLPaxosLogger.pause writes.  Returns the names that were paused."""
+        cand = [n for n in dict.fromkeys(paxosIDs)
+                if n in self.instances and not self.instances[n].stopped and not self.queue.get(n)]
+        if not cand:
+            return []
+        if not self.engine.L.has("pause_groups"):
+            return [n for n in cand if self.pause(n)]
+        gids = np.array([self.instances[n].gid for n in cand], dtype=np.uint32)
+        rows, ok = self.engine.pause_groups(gids)
+        done = []
+        for i, n in enumerate(cand):
+            if not ok[i]:
+                continue
+            self.paused[n] = [str(HotRestoreInfo.from_row(n, rows[i, lane])) for lane in range(self.engine.n_lanes)]
+            inst = self.instances.pop(n)  # the engine has already freed the gid (forceStop + softCrash)
+            self.gid_name.pop(inst.gid, None)
+            self.free_gids.append(inst.gid)
+            done.append(n)
+        return done
+
     def unpause(self, paxosID: str) -> bool:
         """PaxosManager.unpause :2370: rebuild the instance from its HotRestoreInfo (PISM.hotRestore :677-690)."""
         hris = self.paused.pop(paxosID, None)

@@ -571,6 +571,16 @@ int gpx_reset_counters(gpx_engine* e);
  * empty) is false.  PISM.tryPause :2004-2035 pauses an instance only when this bit is clear on every lane. */
 #define GPX_GF_NOT_CAUGHT_UP_BIT 4u
 int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out);
+/* ---- batched pause: the deactivation sweep (PaxosManager.Deactivator :2951 -> syncAndDeactivate :2806-2900 ->
+ * pause(Map, dequeue) :2327-2366, PAUSE_BATCH_SIZE PaxosConfig.java:715) as one launch.  For every gid of the batch,
+ * PISM.tryPause :2004-2035 at every local lane that hosts a replica: the group is paused only if it is live, every such
+ * acceptor is ACTIVE and every lane is caught up (GPX_GF_NOT_CAUGHT_UP_BIT clear).  Then out_rows[i * n_lanes + lane]
+ * = the HotRestoreInfo field set of every lane (what gpx_dump_rows returns; the caller turns them into the pause
+ * table's strings, SQLPaxosLogger.pause) and the gid is free as after gpx_destroy_groups (forceStop + softCrash
+ * :2284-2300).  out_paused[i] = 1 / 0; a group that does not pause is not touched and its rows are not written.
+ * No gid may appear twice (GPX_EINVAL).  Unpause (PaxosManager.unpause :2370, PISM.hotRestore :677-690) =
+ * gpx_load_rows. */
+int gpx_pause_groups(gpx_engine* e, uint32_t n, const uint32_t* gids, gpx_row* out_rows, uint8_t* out_paused);
 /* `active.<name>=host:port` entries (PaxosConfig.getActives :156-170) of the last
  * gpx_config_from_properties call, as "name=host:port\n" lines */
 int gpx_properties_actives(char* out, size_t cap);

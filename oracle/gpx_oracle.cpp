@@ -1776,6 +1776,33 @@ int gpxo_get_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32
   return GPX_OK;
 }
 
+/* PaxosManager.pause(Map, dequeue) :2327-2366 over PISM.tryPause :2004-2035 at every local replica of each group */
+int gpxo_pause_groups(gpxo_engine* e, uint32_t n, const uint32_t* gids, gpx_row* out_rows, uint8_t* out_paused) {
+  if (!e || (n && (!gids || !out_rows || !out_paused))) return GPX_EINVAL;
+  for (u32 i = 0; i < n; i++)
+    for (u32 j = 0; j < i; j++)
+      if (gids[i] == gids[j]) return GPX_EINVAL;
+  for (u32 i = 0; i < n; i++) {
+    const u32 gid = gids[i];
+    bool ok = gid < e->groups.size() && e->groups[gid].live;
+    for (u32 l = 0; ok && l < e->L(); l++) {
+      if (e->memberIdx(e->groups[gid], e->lanes[l].node) < 0) continue;
+      uint8_t fl = 0;
+      if (!e->usable(gid, l)) ok = false; /* tryPause is for a running instance */
+      else if (gpxo_get_group_flags(e, l, 1, &gid, &fl) != GPX_OK || (fl & GPX_GF_NOT_CAUGHT_UP_BIT)) ok = false;
+    }
+    out_paused[i] = ok ? 1 : 0;
+    if (!ok) continue;
+    for (u32 l = 0; l < e->L(); l++) {
+      int rc = gpxo_dump_rows(e, 1, &gid, l, &out_rows[(u64)i * e->L() + l]); /* the HotRestoreInfo :2009-2021 */
+      if (rc) return rc;
+    }
+    int rc = gpxo_destroy_groups(e, 1, &gid); /* forceStop :2025 + softCrash PaxosManager.java:2298 */
+    if (rc) return rc;
+  }
+  return GPX_OK;
+}
+
 int32_t gpxo_java_string_hash(const char* s, size_t len) { return javaStringHash(s, len); }
 int32_t gpxo_round_robin_coordinator(int32_t name_hash, const int32_t* sorted_members, int32_t n, int32_t ballotnum) {
   return roundRobinCoordinator(name_hash, sorted_members, n, ballotnum);

@@ -35,7 +35,7 @@ struct JNINativeInterface_ {
 
 EXPECTED = ["create", "destroy", "lastError", "createGroups", "destroyGroups", "dumpRows", "loadRows", "patch",
             "roundSubmit", "roundWait", "propose", "handleAccepts", "handleAcceptReplies", "handleDecisions",
-            "handlePrepares", "handlePrepareReplies", "logDrainAsync", "logDrainWait", "logRelease", "logRead", "getCpi", "getCounters",
+            "handlePrepares", "handlePrepareReplies", "pauseGroups", "logDrainAsync", "logDrainWait", "logRelease", "logRead", "getCpi", "getCounters",
             "spreadUniqueId", "spreadPlanNode", "spreadCreate", "spreadRound", "spreadDropped", "spreadDestroy"]
 
 

@@ -1,0 +1,198 @@
+"""The deactivation sweep as one call (gpx_pause_groups; PaxosManager.Deactivator :2951 -> syncAndDeactivate :2806 ->
+pause(Map, dequeue) :2327-2366 over PISM.tryPause :2004-2035).
+
+CPU: the oracle's entry point against the per-group path it replaces (gpx_get_group_flags x lanes + gpx_dump_rows x lanes
++ gpx_destroy_groups), through the host mirror; and k_pause_groups' own source (gigapaxos_b200/csrc/gpx_pause.cuh)
+compiled for the host (tests/emu) against the oracle.  The GPU test is in tests/test_zz_phase1b_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gigapaxos_b200.paxos_manager import HashChainApp, PaxosManager
+from helpers import ROOT, Engine, abi, group_descs, make_config, make_requests
+
+NODES = [100, 101, 102]
+
+
+def busy_engine(lib, G=120, seed=1, journaling=1, R=3):
+    """an engine whose groups are in assorted states: idle, with a commit waiting for its predecessor, with a proposal in
+    flight, stopped, destroyed"""
+    nodes = [100, 101, 102, 103, 104][:R]
+    eng = Engine(lib, make_config(lib, n_lanes=R, lane_node=nodes, max_group_size=R, max_groups=G, max_batch_recs=4096,
+                                  max_batch_payload=1 << 20, journaling_enabled=journaling))
+    eng.create_groups(group_descs(G, members=tuple(nodes)))
+    rng = np.random.default_rng(seed)
+    gids = np.arange(G, dtype=np.uint32)
+    for r in range(3):  # everybody decides three slots
+        reqs, pay = make_requests(gids, payload_len=5, seed=seed, round_no=r)
+        eng.round(reqs, pay)
+    rows0 = eng.dump_rows(gids, 0)
+    coord = np.array([nodes.index(int(x)) for x in rows0["acc_bcoord"]])
+    # a third of the groups: an ACCEPT goes out but is never tallied (a proposal in flight, accepted pvalues in memory)
+    sel = gids[rng.random(G) < 0.33]
+    if len(sel):
+        reqs, pay = make_requests(sel, payload_len=6, seed=seed, round_no=7)
+        reqs["flags"] = coord[sel] << 8
+        reqs["entry_node"] = np.array(nodes)[coord[sel]]
+        acc, blob, st = eng.propose(reqs, pay)
+        keep = rng.random(len(acc)) < 0.5
+        acc["dst_mask"] = np.where(keep, (1 << R) - 1, 0b1)
+        eng.handle_accepts(acc, blob)
+    # a few stopped, a few destroyed
+    p = np.zeros(6, dtype=abi.patch_dtype)
+    p["gid"], p["lane"], p["op"], p["a"] = rng.choice(G, 6, replace=False), rng.integers(0, R, 6), abi.PATCH_SET_STATE, abi.ST_STOPPED
+    eng.patch(p)
+    eng.destroy_groups(rng.choice(G, 5, replace=False).astype(np.uint32))
+    return eng
+
+
+def per_group_pause(eng, gids):
+    """what gpx_pause_groups replaces: flags and rows lane by lane, then destroy"""
+    L = eng.n_lanes
+    rows = np.zeros((len(gids), L), dtype=abi.row_dtype)
+    ok = np.zeros(len(gids), dtype=bool)
+    for i, g in enumerate(gids):
+        ga = np.array([g], dtype=np.uint32)
+        r = [eng.dump_rows(ga, l)[0] for l in range(L)]
+        ok[i] = all(int(x["state"]) in (abi.ST_ACTIVE_1, abi.ST_ACTIVE_2) for x in r) and not any(
+            int(eng.group_flags(ga, l)[0]) & abi.GF_NOT_CAUGHT_UP for l in range(L))
+        if ok[i]:
+            rows[i] = r
+            eng.destroy_groups(ga)
+    return rows, ok
+
+
+@pytest.mark.parametrize("journaling,R,seed", [(1, 3, 1), (0, 3, 2), (1, 5, 3), (0, 1, 4)])
+def test_oracle_pause_groups_equals_the_per_group_path(oracle_lib, journaling, R, seed):
+    G = 120
+    a, b = busy_engine(oracle_lib, G, seed, journaling, R), busy_engine(oracle_lib, G, seed, journaling, R)
+    gids = np.random.default_rng(seed).permutation(G + 3).astype(np.uint32)  # incl. gids beyond max_groups
+    gids = gids[gids < G + 3]
+    rows_a, ok_a = a.pause_groups(gids)
+    inb = gids < G
+    rows_b, ok_b = per_group_pause(b, gids[inb])
+    assert np.array_equal(ok_a[inb], ok_b) and not ok_a[~inb].any()
+    assert ok_a.sum() < len(gids) and (ok_a.sum() > 0 or not journaling)  # (accepts kept in memory: the last one stays)
+    assert rows_a[inb].tobytes() == rows_b.tobytes()
+    for l in range(R):
+        all_g = np.arange(G, dtype=np.uint32)
+        assert a.dump_rows(all_g, l).tobytes() == b.dump_rows(all_g, l).tobytes()
+    with pytest.raises(abi.GpxError):
+        a.pause_groups(np.array([1, 2, 1], dtype=np.uint32))
+    # unpause = gpx_load_rows: the paused groups come back exactly as they were dumped
+    back = rows_a[ok_a].reshape(-1)
+    a.load_rows(back)
+    for l in range(R):
+        again = a.dump_rows(gids[ok_a], l)
+        for f in again.dtype.names:
+            assert np.array_equal(again[f], rows_a[ok_a][:, l][f]), f
+
+
+def test_mirror_pause_batch(oracle_lib):
+    """PaxosManager.pauseBatch against pause() one by one: same pause table, same engine afterwards; paused instances come
+    back on demand"""
+    def drive(batch):
+        eng = Engine(oracle_lib, make_config(oracle_lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
+        pm = PaxosManager(eng, [HashChainApp() for _ in NODES], NODES)
+        names = [f"TESTPaxosApp{i}" for i in range(20)]
+        pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+        for r in range(3):
+            for n in names:
+                pm.propose(n, f"{n}:{r}".encode())
+            pm.run_round()
+        pm.propose(names[3], b"queued")  # not idle: a request is waiting
+        if batch:
+            done = pm.pauseBatch(names[:12] + ["nonexistent", names[0]])
+        else:
+            done = [n for n in names[:12] if pm.pause(n)]
+        assert sorted(done) == sorted(n for n in names[:12] if n != names[3])
+        assert all(pm.isPaused(n) and n not in pm.instances for n in done)
+        pm.run_round()
+        for n in names:  # propose -> unpause on demand
+            assert pm.propose(n, f"{n}:later".encode()) is not None
+        pm.run_round()
+        assert not pm.paused and all(a.state == pm.apps[0].state for a in pm.apps)
+        return pm
+    a, b = drive(True), drive(False)
+    assert a.apps[0].state == b.apps[0].state and a.num_decisions == b.num_decisions
+
+
+# ---- the CUDA kernel's own source on the host -------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libpause_emu.so")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no CUDA headers")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", cuda_inc,
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "gigapaxos_b200", "csrc"),
+                           "-x", "c++", os.path.join(ROOT, "tests", "emu", "pause_emu.cpp"), "-o", out])
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("journaling,R,seed,block", [(1, 3, 5, 128), (0, 3, 6, 1), (1, 5, 7, 33), (0, 2, 8, 128)])
+def test_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, journaling, R, seed, block):
+    """DevState's arrays are filled from the oracle engine's rows and group flags (committed / accepted windows are
+    synthesised so that every lane's caught-up answer is the oracle's), k_pause_groups runs thread by thread, and its
+    verdicts, rows and the state it leaves are the oracle's."""
+    G, W = 120, 8
+    nodes = [100, 101, 102, 103, 104][:R]
+    # (the oracle engine journals either way: with accepts kept in memory its last accepted pvalue never leaves and nothing
+    # pauses.  `journaling` here is the KERNEL's flag -- 0 makes it look through the synthesised accepted windows too)
+    eng = busy_engine(oracle_lib, G, seed, 1, R)
+    all_g = np.arange(G, dtype=np.uint32)
+    rows = [eng.dump_rows(all_g, l) for l in range(R)]
+    flags = [eng.group_flags(all_g, l) for l in range(R)]
+    rng = np.random.default_rng(seed)
+    live = (rows[0]["state"] != abi.ST_FREE).astype(np.uint8)
+    acc_row = np.zeros((R, G, 4), dtype=np.int32)
+    acc_aux = np.zeros((R, G), dtype=np.uint32)
+    acc_win = np.zeros((R, W, G, 8), dtype=np.int32)
+    coord_row = np.zeros((R, G, 4), dtype=np.int32)
+    node_slots = np.zeros((R, R, G), dtype=np.int32)
+    for l in range(R):
+        r = rows[l]
+        acc_row[l, :, 0], acc_row[l, :, 1], acc_row[l, :, 2], acc_row[l, :, 3] = r["acc_slot"], r["acc_bnum"], r["acc_bcoord"], r["acc_gc_slot"]
+        busy = (flags[l] & abi.GF_NOT_CAUGHT_UP) != 0
+        ex = r["coord_exists"] != 0
+        # a busy lane is busy for one of the three reasons the kernel looks at (the third only without journaling)
+        why = rng.integers(0, 3 if not journaling else 2, size=G)
+        present = np.where(busy & ((why == 0) | ((why == 1) & ~ex)), 1 << int(rng.integers(0, 8)), 0)
+        acc_aux[l] = (r["state"].astype(np.uint32) & 0xFF) | (present.astype(np.uint32) << 8) | ((flags[l].astype(np.uint32) & 3) << 24)
+        outstanding = np.where(busy & (why == 1) & ex, 1 + rng.integers(0, 3, size=G), 0)
+        coord_row[l, :, 0] = np.where(ex, r["coord_bnum"], 0)
+        coord_row[l, :, 1] = np.where(ex, r["coord_bcoord"], 0)
+        coord_row[l, :, 2] = np.where(ex, r["next_proposal_slot"], 0)
+        coord_row[l, :, 3] = np.where(ex, 1 | np.where(r["coord_active"] != 0, 2, 0) | (outstanding << 8), 0)
+        node_slots[l] = r["node_slots"][:, :R].T
+        # accepted window: stale entries everywhere (valid but garbage-collected: slot <= gc), a live one where `why` says so
+        w = int(rng.integers(0, W))
+        acc_win[l, :, :, 0] = (r["acc_gc_slot"] - rng.integers(0, 3, size=G))[None, :]
+        acc_win[l, :, :, 7] = 1  # GPX_ENT_VALID
+        livepv = busy & (why == 2)
+        acc_win[l, w, :, 0] = np.where(livepv, r["acc_gc_slot"] + 1 + rng.integers(0, 4, size=G), acc_win[l, w, :, 0])
+    gids = rng.permutation(G + 2).astype(np.uint32)
+    want_rows, want_ok = eng.pause_groups(gids)
+    got_rows = np.zeros((len(gids), R), dtype=abi.row_dtype)
+    got_ok = np.full(len(gids), 7, dtype=np.uint8)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    nodes_a = np.array(nodes, dtype=np.int32)
+    rc = emu_lib.emu_pause_groups(G, R, W, R, R, ptr(nodes_a), ptr(nodes_a), ptr(live), int(journaling), ptr(acc_row), ptr(acc_aux),
+                                  ptr(acc_win), ptr(coord_row), ptr(node_slots), len(gids), ptr(gids), ptr(got_rows), ptr(got_ok),
+                                  block)
+    assert rc == 1
+    assert np.array_equal(got_ok.astype(bool), want_ok) and 0 < want_ok.sum() < len(gids)
+    for f in got_rows.dtype.names:
+        if f in ("version", "name_hash"):  # kept on the host by the engine (gpx_dump_rows fills them in)
+            continue
+        assert np.array_equal(got_rows[f][want_ok], want_rows[f][want_ok]), f
+    assert not got_rows[~want_ok].view(np.uint8).any()  # rows of groups that did not pause are not written
+    after = [eng.dump_rows(all_g, l) for l in range(R)]
+    for l in range(R):
+        freed = after[l]["state"] == abi.ST_FREE
+        assert np.array_equal(acc_aux[l] & 0xFF, after[l]["state"].astype(np.uint32) & 0xFF)
+        assert np.array_equal(acc_row[l, :, 0][~freed], after[l]["acc_slot"][~freed])
+        assert np.all(acc_row[l][freed] == np.array([0, -1, -1, -1])) and not coord_row[l][freed].any()

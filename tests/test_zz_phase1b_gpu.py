@@ -86,3 +86,57 @@ def test_mass_failover_through_the_mirror(cuda_lib, oracle_lib):
     from test_paxos_manager import _same_end_state
     from test_phase1b import drive_mass_failover
     _same_end_state(drive_mass_failover(cuda_lib, batched=True), drive_mass_failover(oracle_lib, batched=True))
+
+
+# ---- the deactivation sweep (k_pause_groups behind gpx_pause_groups; also written after the GPU minutes were spent) -------
+@pytest.mark.parametrize("R,seed", [(3, 31), (5, 32), (1, 33)])
+def test_pause_groups_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed):
+    from test_pause_batch import busy_engine
+    G = 120
+    eg, eo = busy_engine(cuda_lib, G, seed, 1, R), busy_engine(oracle_lib, G, seed, 1, R)
+    assert_same_rows(eg, eo, R, G, "before")
+    gids = np.random.default_rng(seed).permutation(G + 3).astype(np.uint32)
+    rows_g, ok_g = eg.pause_groups(gids)
+    rows_o, ok_o = eo.pause_groups(gids)
+    assert np.array_equal(ok_g, ok_o) and 0 < ok_o.sum() < len(gids)
+    for f in rows_o.dtype.names:
+        assert np.array_equal(rows_g[f], rows_o[f]), f
+    assert_same_rows(eg, eo, R, G, "after the sweep")
+    eg.load_rows(rows_g[ok_g].reshape(-1))  # unpause
+    eo.load_rows(rows_o[ok_o].reshape(-1))
+    assert_same_rows(eg, eo, R, G, "after unpausing")
+    # the engine goes on deciding in the unpaused groups
+    from helpers import make_requests
+    back = np.sort(gids[ok_o])
+    reqs, pay = make_requests(back, payload_len=9, seed=seed, round_no=11)
+    sg, xg, _ = eg.round(reqs, pay)
+    so, xo, _ = eo.round(reqs, pay)
+    assert np.array_equal(sg, so) and np.all(so > 0)
+    assert_same_rows(eg, eo, R, G, "after a round")
+
+
+def test_pause_batch_through_the_mirror(cuda_lib, oracle_lib):
+    from gigapaxos_b200.paxos_manager import HashChainApp, PaxosManager
+    from helpers import Engine, make_config
+
+    def drive(lib):
+        eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
+        pm = PaxosManager(eng, [HashChainApp() for _ in range(3)], [100, 101, 102])
+        names = [f"TESTPaxosApp{i}" for i in range(20)]
+        pm.createPaxosInstanceBatch({n: None for n in names}, [100, 101, 102])
+        for r in range(3):
+            for n in names:
+                pm.propose(n, f"{n}:{r}".encode())
+            pm.run_round()
+        pm.propose(names[3], b"queued")
+        done = pm.pauseBatch(names[:12])
+        table = {n: list(pm.paused[n]) for n in done}
+        pm.run_round()
+        for n in names:
+            assert pm.propose(n, f"{n}:later".encode()) is not None
+        pm.run_round()
+        assert not pm.paused and all(a.state == pm.apps[0].state for a in pm.apps)
+        return pm, table
+    (g, tg), (o, to) = drive(cuda_lib), drive(oracle_lib)
+    assert tg == to and len(to) == 11  # the same HotRestoreInfo strings in the pause table
+    assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
