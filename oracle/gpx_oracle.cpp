@@ -1498,10 +1498,14 @@ struct PreActiveCoordinatorState { /* PaxosCoordinatorState.java:67-178 in the p
 int gpxo_handle_prepare_replies(gpxo_engine* e, uint32_t n, const gpx_election_rec* elections, uint32_t n_reply_recs,
                                 const gpx_prepare_reply_rec* replies, gpx_election_out* out) {
   if (!e || (n && (!elections || !out)) || (n_reply_recs && !replies)) return GPX_EINVAL;
-  for (u32 i = 0; i < n; i++) {
-    if ((u64)elections[i].first_reply + elections[i].n_replies > n_reply_recs) return GPX_ERANGE;
-    for (u32 j = 0; j < i; j++)
-      if (elections[j].gid == elections[i].gid) return GPX_EINVAL; /* one election per group per call */
+  {
+    std::vector<u32> seen(n);
+    for (u32 i = 0; i < n; i++) {
+      if ((u64)elections[i].first_reply + elections[i].n_replies > n_reply_recs) return GPX_ERANGE;
+      seen[i] = elections[i].gid;
+    }
+    std::sort(seen.begin(), seen.end());
+    if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) return GPX_EINVAL; /* one election per group per call */
   }
   for (u32 i = 0; i < n; i++) {
     const gpx_election_rec& el = elections[i];
@@ -1779,9 +1783,11 @@ int gpxo_get_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32
 /* PaxosManager.pause(Map, dequeue) :2327-2366 over PISM.tryPause :2004-2035 at every local replica of each group */
 int gpxo_pause_groups(gpxo_engine* e, uint32_t n, const uint32_t* gids, gpx_row* out_rows, uint8_t* out_paused) {
   if (!e || (n && (!gids || !out_rows || !out_paused))) return GPX_EINVAL;
-  for (u32 i = 0; i < n; i++)
-    for (u32 j = 0; j < i; j++)
-      if (gids[i] == gids[j]) return GPX_EINVAL;
+  {
+    std::vector<u32> seen(gids, gids + n);
+    std::sort(seen.begin(), seen.end());
+    if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) return GPX_EINVAL;
+  }
   for (u32 i = 0; i < n; i++) {
     const u32 gid = gids[i];
     bool ok = gid < e->groups.size() && e->groups[gid].live;
