@@ -13,6 +13,12 @@ the phase-2 path produces besides the DECISION / PREPARE forms of journal.py:
   BATCHED_ACCEPT (36)           digest mode: the coordinator's ACCEPTs of one (paxosID, ballot) as slot -> digest and
                                 slot -> requestID maps; BatchedAccept.toJSONObjectImpl :99-146, merge rule addBatchedAccept
                                 :194-209 (wrap-aware max of medianCheckpointedSlot, TreeMap.putAll)
+  PREPARE (2), PREPARE_REPLY (7)  phase 1 between nodes.  A PREPARE_REPLY carries the acceptor's accepted pvalues as full
+                                PValuePacket JSON objects incl. the request values (PrepareReplyPacket.toJSONObjectImpl
+                                :131-143, addAcceptedToJSON :191-199); on the engine side it is gpx_prepare_reply_rec
+                                records (continued with GPX_F_MORE past GPX_MAX_WINDOW pvalues, the analogue of
+                                PrepareReplyPacket.fragment :231-258) + the request bodies in a payload arena -- the
+                                input of gpx_handle_prepare_replies.
   BATCHED_PAXOS_PACKET (37)     PaxosPacketBatcher.batch :280-303: the messaging tasks of one batcher sweep grouped by
                                 recipient set (first-seen order: LinkedHashMap), each group's packets in one
                                 {"PP": [...]} wrapper; BatchedPaxosPacket.toJSONObjectImpl :77-84.  process() :270-277 does
@@ -26,7 +32,7 @@ from __future__ import annotations
 import json
 from typing import Dict, Iterable, List, Sequence, Tuple, Union
 
-PT_PREPARE, PT_ACCEPT, PT_DECISION, PT_ACCEPT_REPLY = 2, 3, 6, 8
+PT_REQUEST, PT_PREPARE, PT_ACCEPT, PT_DECISION, PT_PREPARE_REPLY, PT_ACCEPT_REPLY = 1, 2, 3, 6, 7, 8
 PT_BATCHED_ACCEPT, PT_BATCHED_PAXOS_PACKET, PT_PAXOS_PACKET = 36, 37, 90  # PaxosPacket.PaxosPacketType :202-291
 CHARSET = "iso-8859-1"  # PaxosPacket.CHARSET :439, BatchedAccept.CHARSET :36
 
@@ -168,6 +174,141 @@ def batch_digested_accepts(accs, names: Dict[int, Tuple[str, int]], groups: Dict
     return list(merged.values())
 
 
+# ---- PREPARE / PREPARE_REPLY ----------------------------------------------------------------------------------------
+def prepare_packet_json(paxos_id: str, version: int, bnum: int, bcoord: int, first_undecided_slot: int) -> bytes:
+    """PreparePacket.toJSONObjectImpl :78-86 (the same object journal.prepare_json journals)"""
+    d = _base(PT_PREPARE, paxos_id, version)
+    d.update({"B": f"{int(bnum)}:{int(bcoord)}", "PREP_MIN": int(first_undecided_slot)})
+    return _dumps(d)
+
+
+def _request_obj(paxos_id, version, pt, req_id, value: bytes, entry_replica, entry_time, stop) -> dict:
+    """RequestPacket.toJSONObjectImpl :652-695 (the keys this path sets: QID, QV, ET, E, STOP)"""
+    d = _base(pt, paxos_id, version)
+    d.update({"QID": int(req_id), "QV": bytes(value).decode(CHARSET), "ET": int(entry_time), "E": int(entry_replica)})
+    if stop:
+        d["STOP"] = True
+    return d
+
+
+def accepted_pvalue_obj(paxos_id: str, version: int, pv, blob: bytes, entry_replica: int = -1, entry_time: int = 0,
+                        pt: int = PT_ACCEPT) -> dict:
+    """One entry of ACC_MAP: the PValuePacket JSON (PaxosPacket.toJSONObject :478-494 + PValuePacket.toJSONObjectImpl
+    :184-193 {"B", "GC_S"} + ProposalPacket :63-67 {"S"} + the request) of an accepted pvalue record
+    (abi.accepted_pvalue_dtype) whose request body is `blob` in the engine's form: the raw requestValue for one request,
+    nreq x {reqID, len, flags} + the values for a batched slot (RequestPacket.batched -> "BATCH")."""
+    import numpy as np
+    from . import abi
+    nreq = int(pv["flags"]) >> 16
+    stop = bool(int(pv["flags"]) & 2)
+    if nreq <= 1:
+        d = _request_obj(paxos_id, version, pt, int(pv["req_id"]), blob, entry_replica, entry_time, stop)
+    else:
+        ents = np.frombuffer(blob[: 16 * nreq], dtype=abi.batch_ent_dtype)
+        off, objs = 16 * nreq, []
+        for e in ents:
+            objs.append(_request_obj(paxos_id, version, PT_REQUEST, int(e["req_id"]), blob[off: off + int(e["len"])],
+                                     entry_replica, entry_time, bool(int(e["flags"]) & abi.F_STOP)))
+            off += int(e["len"])
+        d = dict(objs[0])
+        d["PT"] = pt
+        d["BATCH"] = objs[1:]  # the first request carries the ones latched along (RequestPacket.latchToBatch); the slot is
+        # a stop when any of them is (RequestPacket.isStopRequest: stop || isAnyBatchedRequestStop)
+    d.update({"B": f"{int(pv['bnum'])}:{int(pv['bcoord'])}", "GC_S": -1, "S": int(pv["slot"])})
+    return d
+
+
+def prepare_reply_json(paxos_id: str, version: int, acceptor: int, bnum: int, bcoord: int, gc_slot: int,
+                       accepted: Sequence[dict], create_time: int = 0) -> bytes:
+    """PrepareReplyPacket(receiverID, ballot, accepted, gcSlot) :89-93 -> toJSONObjectImpl :131-143.  firstSlot = gcSlot + 1;
+    MIN_S / MAX_S are the static getMinSlot / getMaxSlot :166-190 over the accepted slots (firstSlot when there are none),
+    TOT_S their number (all three serve PrepareReplyAssembler's de-fragmentation)."""
+    first = _i32(int(gc_slot) + 1)
+    lo = hi = None
+    for a in accepted:
+        s = int(a["S"])
+        lo = s if lo is None or _i32(s - lo) < 0 else lo
+        hi = s if hi is None or _i32(s - hi) > 0 else hi
+    d = _base(PT_PREPARE_REPLY, paxos_id, version)
+    d.update({"ACCPTR": int(acceptor), "B": f"{int(bnum)}:{int(bcoord)}", "ACC_MAP": list(accepted), "PREPLY_MIN": first,
+              "MAX_S": first if hi is None else hi, "MIN_S": first if lo is None else lo, "TOT_S": len(accepted),
+              "CT": int(create_time)})
+    return _dumps(d)
+
+
+def prepare_replies_to_packets(replies, names: Dict[int, Tuple[str, int]], node_of_lane: Sequence[int], read_body) -> List[bytes]:
+    """gpx_handle_prepares' reply records (abi.prepare_reply_dtype, reply of PREPARE i at lane l at index i * L + l) as the
+    PREPARE_REPLY packets a Java coordinator expects.  read_body(lane, frame_ref, nbytes) -> the request blob from that
+    acceptor's log ring (Engine.log_read(lane, frame_ref * 16, nbytes))."""
+    from . import abi
+    L = len(node_of_lane)
+    out = []
+    for k, r in enumerate(replies):
+        who = int(r["who"])
+        if (who >> 16) & abi.F_VOID:
+            continue
+        lane = k % L
+        pid, ver = names[int(r["gid"])]
+        acc = [accepted_pvalue_obj(pid, ver, pv, read_body(lane, int(pv["frame_ref"]), int(pv["payload_len"])))
+               for pv in r["accepted"][: int(r["n_accepted"])]]
+        out.append(prepare_reply_json(pid, ver, node_of_lane[lane], int(r["bnum"]), int(r["bcoord"]), int(r["first_slot"]), acc))
+    return out
+
+
+def _pvalue_blob(a: dict):
+    """ACC_MAP entry -> (req_id, blob in the engine's form, nreq, stop)"""
+    import numpy as np
+    from . import abi
+    reqs = [a] + list(a.get("BATCH", []))
+    stop = any(bool(q.get("STOP", False)) for q in reqs)
+    if len(reqs) == 1:
+        return int(a["QID"]), a["QV"].encode(CHARSET), 1, stop
+    ents = np.zeros(len(reqs), dtype=abi.batch_ent_dtype)
+    vals = []
+    for i, q in enumerate(reqs):
+        v = q["QV"].encode(CHARSET)
+        ents[i]["req_id"], ents[i]["len"] = int(q["QID"]), len(v)
+        ents[i]["flags"] = abi.F_STOP if q.get("STOP", False) else 0
+        vals.append(v)
+    return int(a["QID"]), ents.tobytes() + b"".join(vals), len(reqs), stop
+
+
+def prepare_reply_to_records(pkt: Packet, gid: int, members: Sequence[int], preparer: int):
+    """A PREPARE_REPLY packet from a (remote) acceptor as the input of gpx_handle_prepare_replies: -> (records
+    [abi.prepare_reply_dtype], arena bytes).  More than GPX_MAX_WINDOW accepted pvalues continue in further records of
+    the same acceptor flagged GPX_F_MORE; the pvalues' frame_ref is the 16-byte unit offset of the request blob in the
+    returned arena (the caller adds the position it copies the arena to)."""
+    import numpy as np
+    from . import abi
+    j = pkt if isinstance(pkt, dict) else _loads(pkt)
+    assert j["type"] == PT_PAXOS_PACKET and j["PT"] == PT_PREPARE_REPLY
+    bn, bc = (int(x) for x in j["B"].split(":"))
+    members = list(members)
+    idx = members.index(int(j["ACCPTR"])) if int(j["ACCPTR"]) in members else 0xFF
+    dst = members.index(int(preparer)) if int(preparer) in members else 0xFF
+    acc = sorted(j.get("ACC_MAP", []), key=lambda a: int(a["S"]))  # TreeMap<Integer, PValuePacket>
+    arena = bytearray()
+    pvs = []
+    for a in acc:
+        rid, blob, nreq, stop = _pvalue_blob(a)
+        abn, abc = (int(x) for x in a["B"].split(":"))
+        pv = np.zeros((), dtype=abi.accepted_pvalue_dtype)
+        pv["slot"], pv["bnum"], pv["bcoord"], pv["frame_ref"] = int(a["S"]), abn, abc, len(arena) // 16
+        pv["req_id"], pv["payload_len"], pv["flags"] = rid, len(blob), (2 if stop else 0) | (nreq << 16)
+        arena += blob + bytes(-len(blob) % 16)
+        pvs.append(pv)
+    chunks = [pvs[k: k + abi.GPX_MAX_WINDOW] for k in range(0, len(pvs), abi.GPX_MAX_WINDOW)] or [[]]
+    recs = np.zeros(len(chunks), dtype=abi.prepare_reply_dtype)
+    for ci, ch in enumerate(chunks):
+        r = recs[ci]
+        r["gid"], r["first_slot"], r["bnum"], r["bcoord"] = gid, _i32(int(j["PREPLY_MIN"]) - 1), bn, bc
+        r["who"] = abi.who(idx, dst, abi.F_MORE if ci + 1 < len(chunks) else 0)
+        r["n_accepted"] = len(ch)
+        for k, pv in enumerate(ch):
+            r["accepted"][k] = pv
+    return recs, bytes(arena)
+
+
 # ---- BATCHED_PAXOS_PACKET ------------------------------------------------------------------------------------------
 Packet = Union[bytes, dict]
 """a packet on its way out: byteified (bytes not starting with '{'), a JSON string (bytes starting with '{') or a dict"""
@@ -241,6 +382,11 @@ def parse_packet(pkt: bytes) -> dict:
         return {"kind": "BATCHED_ACCEPT", "paxos_id": b.paxos_id, "version": b.version, "bnum": b.bnum, "bcoord": b.bcoord,
                 "median_cp": b.median_cp, "group": b.group, "slot_digests": dict(b.slot_digests),
                 "slot_request_ids": dict(b.slot_request_ids)}
+    if pt == PT_PREPARE_REPLY:
+        bn, bc = (int(x) for x in j["B"].split(":"))
+        return {"kind": "PREPARE_REPLY", "paxos_id": j["ID"], "version": j["V"], "acceptor": j["ACCPTR"], "bnum": bn,
+                "bcoord": bc, "first_slot": j["PREPLY_MIN"], "min_slot": j["MIN_S"], "max_slot": j["MAX_S"],
+                "total_count": j["TOT_S"], "accepted_slots": sorted(int(a["S"]) for a in j.get("ACC_MAP", []))}
     if pt == PT_BATCHED_PAXOS_PACKET:
         return {"kind": "BATCHED_PAXOS_PACKET", "packets": [parse_packet(_dumps(p)) for p in j["PP"]]}
     return journal.parse_packet(pkt)

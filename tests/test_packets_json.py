@@ -108,3 +108,114 @@ def test_journal_frames_are_charset_neutral():
     assert b.isascii() and journal.parse_packet(b)["paxos_id"] == "café"
     raw = json.dumps(json.loads(b), ensure_ascii=False).encode("iso-8859-1")
     assert journal.parse_packet(raw)["paxos_id"] == "café"
+
+
+# ---- PREPARE / PREPARE_REPLY (phase 1 between nodes; the input format of gpx_handle_prepare_replies) ------------------------
+def test_prepare_reply_packets_round_trip_and_elect(oracle_lib):
+    """acceptors' reply records -> the PREPARE_REPLY JSON a Java coordinator reads (PrepareReplyPacket.toJSONObjectImpl
+    :131-143) -> back to records + a payload arena -> gpx_handle_prepare_replies: the same election result as from the
+    original records, and the request bodies survive (incl. a batched slot)"""
+    import json
+    import numpy as np
+    from gigapaxos_b200 import abi, packets_json as pj
+    from helpers import Engine, group_descs, make_config, make_requests
+    NODES = [100, 101, 102]
+    G = 6
+    eng = Engine(oracle_lib, make_config(oracle_lib, max_groups=G, max_batch_recs=4096, max_batch_payload=1 << 20))
+    eng.create_groups(group_descs(G))
+    gids = np.arange(G, dtype=np.uint32)
+    for r in range(2):
+        reqs, pay = make_requests(gids, payload_len=4, seed=3, round_no=r)
+        eng.round(reqs, pay)
+    rows0 = eng.dump_rows(gids, 0)
+    coord = np.array([NODES.index(int(x)) for x in rows0["acc_bcoord"]])
+    # two more slots reach only some acceptors; the second is a batched slot (two requests of the group in one call)
+    for k, (reach, per) in enumerate(((0b011, 1), (0b110, 2))):
+        g2 = np.repeat(gids, per)
+        reqs, pay = make_requests(g2, payload_len=5 + 3 * k, seed=4, round_no=k)
+        reqs["flags"] = coord[g2] << 8
+        reqs["entry_node"] = np.array(NODES)[coord[g2]]
+        acc, blob, st = eng.propose(reqs, pay)
+        assert len(acc) == G and (per == 1 or np.all(acc["nreq"] == 2))
+        acc["dst_mask"] = reach
+        eng.handle_accepts(acc, blob)
+    cand = 2
+    cur = eng.dump_rows(gids, cand)
+    prep = np.zeros(G, dtype=abi.decision_dtype)
+    prep["gid"], prep["slot"], prep["bnum"], prep["bcoord"] = gids, cur["acc_slot"], cur["acc_bnum"] + 1, NODES[cand]
+    prep["flags"], prep["dst_mask"] = abi.F_PREPARE, 0b111
+    replies = eng.handle_prepares(prep)
+    names = {int(g): (f"NoopPaxosApp{int(g)}", 0) for g in gids}
+    read_body = lambda lane, frame_ref, n: bytes(eng.log_read(lane, frame_ref * 16, n)) if n else b""
+    pkts = pj.prepare_replies_to_packets(replies, names, NODES, read_body)
+    assert len(pkts) == 3 * G
+    j = json.loads(pkts[1].decode("ascii"))
+    assert set(j) == {"type", "PT", "ID", "V", "ACCPTR", "B", "ACC_MAP", "PREPLY_MIN", "MAX_S", "MIN_S", "TOT_S", "CT"}
+    assert j["type"] == 90 and j["PT"] == 7 and j["TOT_S"] == len(j["ACC_MAP"])
+    some = [a for p in pkts for a in json.loads(p.decode("ascii"))["ACC_MAP"]]
+    assert some and all({"type", "PT", "ID", "V", "B", "GC_S", "S", "QID", "QV", "ET", "E"} <= set(a) for a in some)
+    assert any("BATCH" in a and len(a["BATCH"]) == 1 for a in some)  # the batched slot: one request latched along
+    assert pj.parse_packet(pkts[0])["kind"] == "PREPARE_REPLY"
+    # back to records: one arena per packet, concatenated; frame_ref rebased
+    recs, arena = [], bytearray()
+    for k, p in enumerate(pkts):
+        r, a = pj.prepare_reply_to_records(p, int(replies[k]["gid"]), NODES, NODES[cand])
+        for rec in r:
+            for i in range(int(rec["n_accepted"])):
+                rec["accepted"][i]["frame_ref"] += len(arena) // 16
+        recs.append(r)
+        arena += a
+    recs = np.concatenate(recs)
+    assert len(recs) == len(replies)
+    for f in ("gid", "first_slot", "bnum", "bcoord", "n_accepted"):
+        assert np.array_equal(recs[f], replies[f]), f
+    assert np.array_equal(recs["who"] & 0xFFFF, replies["who"] & 0xFFFF)  # acceptor and preparer indices
+    for k, (a, b) in enumerate(zip(recs, replies)):
+        for i in range(int(b["n_accepted"])):
+            pa, pb = a["accepted"][i], b["accepted"][i]
+            for f in ("slot", "bnum", "bcoord", "req_id", "payload_len", "flags"):
+                assert pa[f] == pb[f], f
+            n, nreq = int(pb["payload_len"]), int(pb["flags"]) >> 16
+            got = bytes(arena[int(pa["frame_ref"]) * 16: int(pa["frame_ref"]) * 16 + n])
+            orig = read_body(k % 3, int(pb["frame_ref"]), n)  # the body in the log ring of the acceptor that replied
+            if nreq <= 1:
+                assert got == orig
+            else:  # (the entry-lane bits of a batched slot's table travel as "E", not in the blob)
+                ea = np.frombuffer(got[: 16 * nreq], dtype=abi.batch_ent_dtype)
+                eb = np.frombuffer(orig[: 16 * nreq], dtype=abi.batch_ent_dtype)
+                assert np.array_equal(ea["req_id"], eb["req_id"]) and np.array_equal(ea["len"], eb["len"])
+                assert got[16 * nreq:] == orig[16 * nreq:]
+    els = np.zeros(G, dtype=abi.election_dtype)
+    els["gid"], els["lane"], els["bnum"], els["bcoord"], els["slot"] = gids, cand, prep["bnum"], NODES[cand], prep["slot"]
+    els["first_reply"], els["n_replies"] = np.arange(G) * 3, 3
+    twin = Engine(oracle_lib, make_config(oracle_lib, max_groups=G, max_batch_recs=4096, max_batch_payload=1 << 20))
+    twin.create_groups(group_descs(G))
+    o1 = eng.handle_prepare_replies(els, replies)
+    o2 = twin.handle_prepare_replies(els, recs)
+    assert np.all(o1["verdict"] == abi.EL_MAJORITY) and int(o1["n_plan"].max()) >= 1
+    for f in ("verdict", "next_slot", "n_plan", "flags", "node_slots"):
+        assert np.array_equal(o1[f], o2[f]), f
+    for a, b in zip(o1, o2):
+        for i in range(int(a["n_plan"])):
+            assert a["plan"][i]["slot"] == b["plan"][i]["slot"] and a["plan"][i]["kind"] == b["plan"][i]["kind"]
+            assert a["plan"][i]["pv"]["req_id"] == b["plan"][i]["pv"]["req_id"]
+
+
+def test_prepare_reply_longer_than_the_window_is_continued():
+    from gigapaxos_b200 import abi, packets_json as pj
+    import numpy as np
+    acc = []
+    for s in range(11):
+        pv = np.zeros((), dtype=abi.accepted_pvalue_dtype)
+        pv["slot"], pv["bnum"], pv["bcoord"], pv["req_id"], pv["flags"] = 20 + s, 1, 100, 900 + s, 1 << 16
+        acc.append(pj.accepted_pvalue_obj("p", 0, pv, b"v%d" % s, entry_replica=100))
+    pkt = pj.prepare_reply_json("p", 0, 101, 2, 102, 19, acc)
+    d = pj.parse_packet(pkt)
+    assert (d["first_slot"], d["min_slot"], d["max_slot"], d["total_count"]) == (20, 20, 30, 11)
+    recs, arena = pj.prepare_reply_to_records(pkt, 5, [100, 101, 102], 102)
+    assert len(recs) == 2 and [int(r["n_accepted"]) for r in recs] == [8, 3]
+    assert abi.who_flags(int(recs[0]["who"])) & abi.F_MORE and not abi.who_flags(int(recs[1]["who"])) & abi.F_MORE
+    assert abi.who_acc(int(recs[0]["who"])) == 1 and abi.who_dst(int(recs[0]["who"])) == 2
+    assert [int(r["first_slot"]) for r in recs] == [19, 19] and len(arena) == 11 * 16
+    assert pj.parse_packet(pj.prepare_packet_json("p", 0, 2, 102, 20)) == {
+        "kind": "PREPARE", "paxos_id": "p", "version": 0, "bnum": 2, "bcoord": 102, "first_undecided_slot": 20}
