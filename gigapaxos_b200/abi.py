@@ -66,6 +66,11 @@ election_out_dtype = np.dtype([("gid", "<u4"), ("verdict", "<i4"), ("next_slot",
                                ("flags", "<u2"), ("node_slots", "<i4", (GPX_MAX_GROUP_SIZE,)),
                                ("plan", carryover_dtype, (GPX_MAX_PLAN + 1,))])
 assert election_dtype.itemsize == 32 and carryover_dtype.itemsize == 48 and election_out_dtype.itemsize == 896
+# gpx_log_find
+GPX_LOG_SPAN = 16
+log_want_dtype = np.dtype([("gid", "<u4"), ("min_slot", "<i4"), ("n_slots", "<u4"), ("reserved", "<u4")])
+log_hit_dtype = np.dtype([("decision", decision_dtype), ("accept", accept_dtype), ("blob_pos", "<u8"), ("reserved", "<u8")])
+assert log_want_dtype.itemsize == 16 and log_hit_dtype.itemsize == 96
 exec_sum_dtype = np.dtype([("slot", "<i4"), ("lane_mask", "u1"), ("flags", "u1"), ("nreq", "<u2")])
 ROUND_COMPACT = 1
 ROUND_PACKED_REQS = 2
@@ -268,6 +273,15 @@ class Engine:
     def load_rows(self, rows: np.ndarray):
         rows = np.ascontiguousarray(rows, dtype=row_dtype)
         self.L.check(self.L.fn("load_rows")(self._h, C.c_uint32(len(rows)), _ptr(rows)))
+
+    def log_find(self, lane: int, wants: np.ndarray, from_: int = 0) -> np.ndarray:
+        """The journal's index as a scan (gpx_log_find): per want (gid, min_slot, n_slots <= 16; sorted by gid) and slot the
+        LAST logged DECISION and ACCEPT image and the ring position of the accept's request blob.  -> [n, 16] log_hit."""
+        wants = np.ascontiguousarray(wants, dtype=log_want_dtype)
+        n = len(wants)
+        out = np.zeros((max(n, 1), GPX_LOG_SPAN), dtype=log_hit_dtype)
+        self.L.check(self.L.fn("log_find")(self._h, C.c_uint32(lane), C.c_uint64(from_), C.c_uint32(n), _ptr(wants), _ptr(out)))
+        return out[:n]
 
     def pause_groups(self, gids):
         """The deactivation sweep (gpx_pause_groups): -> (rows [n, n_lanes] of gpx_row, paused [n] bool).  Rows of groups

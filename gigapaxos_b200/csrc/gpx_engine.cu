@@ -25,6 +25,7 @@
 #include "gpx_prepare.cuh"
 #include "gpx_phase1b.cuh"
 #include "gpx_pause.cuh"
+#include "gpx_logfind.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -1443,6 +1444,58 @@ int gpx_log_read(gpx_engine* e, uint32_t lane, uint64_t from, void* dst, uint64_
     if (nb > first) CK(cudaMemcpy((uint8_t*)dst + first, e->S.ring[lane], nb - first, cudaMemcpyDeviceToHost));
   }
   if (n_copied) *n_copied = nb;
+  return GPX_OK;
+}
+
+/* the journal's index as a scan: k_log_dir -> k_log_scan -> k_log_hits (gpx_logfind.cuh) */
+int gpx_log_find(gpx_engine* e, uint32_t lane, uint64_t from, uint32_t n, const gpx_log_want* wants, gpx_log_hit* out) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  if (n == 0) return GPX_OK;
+  if (!wants || !out) return fail(GPX_EINVAL, "null argument");
+  if (from & 31) return fail(GPX_EINVAL, "from is not a segment boundary");
+  for (uint32_t i = 0; i < n; i++) {
+    if (wants[i].n_slots > GPX_LOG_SPAN) return fail(GPX_ERANGE, "n_slots > GPX_LOG_SPAN");
+    if (i && wants[i - 1].gid >= wants[i].gid) return fail(GPX_EINVAL, "wants must be sorted by gid, one per group");
+  }
+  CK(cudaDeviceSynchronize()); /* rounds may have been issued on a caller's stream; the head is read on the device */
+  const size_t cells = (size_t)n * GPX_LOG_SPAN;
+  /* a segment is at least 96 bytes; a directory of 2^20 entries (32 MiB) covers every ring the launches of this engine
+   * can fill with fewer segments than that, else LOGF_TOO_MANY */
+  const uint64_t seg_cap64 = std::min<uint64_t>(e->cfg.log_ring_bytes / 96 + 2, 1ull << 20);
+  const size_t want_bytes = ((size_t)n * sizeof(gpx_log_want) + 31) & ~(size_t)31;
+  const size_t seg_bytes = (size_t)seg_cap64 * sizeof(LogSeg);
+  const size_t best_bytes = 2 * cells * 8;
+  const size_t hit_bytes = cells * sizeof(gpx_log_hit);
+  int rc = e->ensure_misc(want_bytes + seg_bytes + 32 + best_bytes + hit_bytes);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  uint8_t* base = (uint8_t*)e->d_misc;
+  LogFindArgs A;
+  A.lane = lane;
+  A.n = n;
+  A.from = from;
+  A.wants = (const gpx_log_want*)base;
+  A.segs = (LogSeg*)(base + want_bytes);
+  A.seg_cap = (uint32_t)seg_cap64;
+  A.ctl = (unsigned long long*)(base + want_bytes + seg_bytes);
+  A.best = A.ctl + 4;
+  A.hits = (gpx_log_hit*)(base + want_bytes + seg_bytes + 32 + best_bytes);
+  CK(cudaMemcpyAsync(base, wants, (size_t)n * sizeof(gpx_log_want), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(A.ctl, 0, 32 + best_bytes, st));
+  k_log_dir<<<1, 32, 0, st>>>(e->S, A);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
+  k_log_scan<<<(unsigned)sms * 8u, GPX_LOGF_BLOCK, 0, st>>>(e->S, A);
+  k_log_hits<<<cdiv(cells, GPX_LOGF_BLOCK), GPX_LOGF_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  unsigned long long ctl[4];
+  CK(cudaMemcpyAsync(ctl, A.ctl, sizeof ctl, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out, A.hits, hit_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (ctl[LOGF_ERR] == LOGF_OVERWRITTEN) return fail(GPX_ERANGE, "bytes from `from` on were already overwritten");
+  if (ctl[LOGF_ERR] == LOGF_CORRUPT) return fail(GPX_EINVAL, "`from` is not a segment boundary");
+  if (ctl[LOGF_ERR] == LOGF_TOO_MANY) return fail(GPX_ERANGE, "more log segments than the scan's directory holds");
   return GPX_OK;
 }
 

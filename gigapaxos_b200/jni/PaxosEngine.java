@@ -82,6 +82,8 @@ public final class PaxosEngine implements AutoCloseable {
 	public static native int logDrainWait(long h);
 	public static native int logRelease(long h, int lane, long upto);
 	/** copiedAndHead = {bytes copied, ring head} */
+	/** getLoggedDecisions / getLoggedAccepts for n (gid, minSlot, nSlots <= 16) wants sorted by gid: hitsOut n x 16 x 96 B */
+	public static native int logFind(long h, int lane, long from, int n, ByteBuffer wants, ByteBuffer hitsOut);
 	public static native int logRead(long h, int lane, long from, ByteBuffer dst, long[] copiedAndHead);
 
 	// ---- replicas of a group on different GPUs: one engine (a single lane) per GPU process ----

@@ -158,6 +158,13 @@ JNIEXPORT jint JNICALL GPX_JNI(handlePrepareReplies)(JNIEnv* env, jclass cls, jl
                                     (uint32_t)n_reply_recs, (const gpx_prepare_reply_rec*)buf(env, replies),
                                     (gpx_election_out*)buf(env, out_elections));
 }
+/* int logFind(long h, int lane, long from, int n, ByteBuffer wants [n x 16 B], ByteBuffer hitsOut [n x 16 x 96 B]):
+ * AbstractPaxosLogger.getLoggedDecisions / getLoggedAccepts for a batch of (group, slot range) as a scan of the log ring */
+JNIEXPORT jint JNICALL GPX_JNI(logFind)(JNIEnv* env, jclass cls, jlong h, jint lane, jlong from, jint n, jobject wants,
+                                        jobject hits_out) {
+  return gpx_log_find((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint64_t)from, (uint32_t)n, (const gpx_log_want*)buf(env, wants),
+                      (gpx_log_hit*)buf(env, hits_out));
+}
 /* long logRead(long h, int lane, long from, ByteBuffer dst, long[] out {nCopied, head}): the synchronous journal read
  * (recovery / tests); the steady state uses logDrainAsync */
 JNIEXPORT jint JNICALL GPX_JNI(logRead)(JNIEnv* env, jclass cls, jlong h, jint lane, jlong from, jobject dst, jlongArray out) {

@@ -181,7 +181,7 @@ class PaxosManager:
     """Mirror of the PaxosManager calls on the hot path, for co-located replicas."""
 
     def __init__(self, engine: Engine, apps: Sequence[Replicable], nodes: Sequence[int],
-                 device_phase1b: Optional[bool] = None):
+                 device_phase1b: Optional[bool] = None, device_log_find: Optional[bool] = None):
         if len(apps) != engine.n_lanes or len(nodes) != engine.n_lanes:
             raise ValueError("one app and one node id per lane")
         self.engine = engine
@@ -203,6 +203,9 @@ class PaxosManager:
         # phase 1b (tally of PREPARE_REPLYs, carry-over, no-op fill, install): inside the engine
         # (gpx_handle_prepare_replies, the default when the library has it) or by the host-language twin below + gpx_patch
         self.device_phase1b = engine.L.has("handle_prepare_replies") if device_phase1b is None else device_phase1b
+        # logged decisions / accepts for a lagging replica: a scan of the donor's ring on the device (gpx_log_find) or a
+        # walk of the whole ring on the host
+        self.device_log_find = engine.L.has("log_find") if device_log_find is None else device_log_find
 
     # ---- instance management ------------------------------------------------------------
     def _alloc_gid(self) -> int:
@@ -464,6 +467,26 @@ class PaxosManager:
             if head > ring:
                 return None
             best = {}
+            if self.device_log_find:  # getLoggedAccepts as a scan of the acceptor's ring on the device (gpx_log_find)
+                top = _jadd(int(self.engine.dump_rows(np.array([gid], dtype=np.uint32), l)[0]["acc_slot"]),
+                            int(self.engine.cfg.window))
+                sl = first_slot
+                while _jsub(sl, top) < 0:
+                    w = np.zeros(1, dtype=abi.log_want_dtype)
+                    w["gid"], w["min_slot"], w["n_slots"] = gid, sl, min(abi.GPX_LOG_SPAN, _jsub(top, sl))
+                    for h in self.engine.log_find(l, w)[0][: int(w["n_slots"][0])]:
+                        a = h["accept"]
+                        if int(a["flags"]) & abi.F_VOID:
+                            continue
+                        pv = np.zeros(1, dtype=abi.accepted_pvalue_dtype)[0]
+                        pv["slot"], pv["bnum"], pv["bcoord"] = int(a["slot"]), int(a["bnum"]), int(a["bcoord"])
+                        pv["frame_ref"] = int(h["blob_pos"]) // 16
+                        pv["req_id"], pv["payload_len"] = int(a["req_id"]), int(a["payload_len"])
+                        pv["flags"] = (2 if int(a["flags"]) & abi.F_STOP else 0) | (int(a["nreq"]) << 16)
+                        best[int(a["slot"])] = pv
+                    sl = _jadd(sl, abi.GPX_LOG_SPAN)
+                out[l] = [best[k] for k in sorted(best)]
+                continue
             buf = self.engine.log_read(l, 0, head)
             for hdr, imgs, payload, pay_off in abi.parse_log(buf):
                 if int(hdr["rec_bytes"]) != 48:
@@ -599,15 +622,34 @@ class PaxosManager:
             return 0
         want = lambda sl: _jsub(sl, lo) >= 0 and _jsub(sl, hi) < 0
         accepts, decisions = {}, {}
-        for hdr, imgs, payload, _ in abi.parse_log(eng.log_read(donor)):
-            for a in imgs:
-                if (int(a["flags"]) & abi.F_VOID) or int(a["gid"]) != gid or not want(int(a["slot"])):
-                    continue
-                if int(hdr["rec_bytes"]) == 48:
-                    o, n = int(a["payload_off"]), int(a["payload_len"])
-                    accepts[(int(a["slot"]), int(a["bnum"]), int(a["bcoord"]))] = (a.copy(), bytes(payload[o: o + n]))
-                elif int(a["flags"]) & abi.F_DECISION:
-                    decisions[int(a["slot"])] = a.copy()
+        if self.device_log_find:
+            # getLoggedDecisions + getActualDecisions (PISM :2463-2502, :2539-2583) as scans of the donor's log ring on the
+            # device (gpx_log_find): per slot the decision and the accept logged last; only the found bodies cross PCIe
+            sl = lo
+            while _jsub(sl, hi) < 0:
+                w = np.zeros(1, dtype=abi.log_want_dtype)
+                w["gid"], w["min_slot"], w["n_slots"] = gid, sl, min(abi.GPX_LOG_SPAN, _jsub(hi, sl))
+                for h in eng.log_find(donor, w)[0][: int(w["n_slots"][0])]:
+                    d, a = h["decision"], h["accept"]
+                    if int(d["flags"]) & abi.F_VOID or int(a["flags"]) & abi.F_VOID:
+                        continue
+                    if (_jsub(int(a["bnum"]), int(d["bnum"])) or _jsub(int(a["bcoord"]), int(d["bcoord"]))) < 0:
+                        continue  # the accept on record is older than the decision: no body for it here
+                    n = int(a["payload_len"])
+                    body = bytes(eng.log_read(donor, int(h["blob_pos"]), n)) if n else b""
+                    decisions[int(d["slot"])] = d.copy()
+                    accepts[(int(d["slot"]), int(d["bnum"]), int(d["bcoord"]))] = (a.copy(), body)
+                sl = _jadd(sl, abi.GPX_LOG_SPAN)
+        else:
+            for hdr, imgs, payload, _ in abi.parse_log(eng.log_read(donor)):
+                for a in imgs:
+                    if (int(a["flags"]) & abi.F_VOID) or int(a["gid"]) != gid or not want(int(a["slot"])):
+                        continue
+                    if int(hdr["rec_bytes"]) == 48:
+                        o, n = int(a["payload_off"]), int(a["payload_len"])
+                        accepts[(int(a["slot"]), int(a["bnum"]), int(a["bcoord"]))] = (a.copy(), bytes(payload[o: o + n]))
+                    elif int(a["flags"]) & abi.F_DECISION:
+                        decisions[int(a["slot"])] = a.copy()
         executed, W, sl = 0, int(eng.cfg.window), lo
         while _jsub(sl, hi) < 0:
             chunk = []

@@ -558,6 +558,36 @@ int gpx_log_drain_wait(gpx_engine* e);
 int gpx_log_drain_skip(gpx_engine* e); /* drop the backlog: drain cursor and tail <- current heads */
 int gpx_log_release(gpx_engine* e, uint32_t lane, uint64_t upto);
 
+/* ---- finding logged pvalues: the journal's index as a scan ---------------------------------------------------------
+ * A replica that answers a SYNC_DECISIONS_REQUEST (PISM.handleSyncDecisionsPacket :2426-2510) or a PREPARE from a
+ * lagging node (PISM.handlePrepare :900-955 with GET_ACCEPTED_PVALUES_FROM_DISK) needs decisions / accepts that have
+ * left its memory: AbstractPaxosLogger.getLoggedDecisions :582 / getLoggedAccepts :568, which with journaling are
+ * SQLPaxosLogger.getLoggedFromMessageLog :3674-3756 -- look the (paxosID, slot range) up in the per-group
+ * paxosutil/LogIndex (:213-248), read those frames back from the journal files, and keep per slot the entry logged
+ * LAST (`accepts.put(packet.slot, packet)` :3746 in log order).  The engine keeps no index on the hot path; the log ring
+ * is in HBM, so the lookup is a scan of it: one thread walks the segment headers from `from` (a segment boundary:
+ * 0 while the ring has not wrapped, else a position handed out by gpx_log_drain_async / gpx_log_release) to the head,
+ * one thread per logged image matches (gid, slot) against the batch of wants (sorted by gid, one want per gid, at
+ * most GPX_LOG_SPAN slots each), the LAST logged DECISION and ACCEPT image per wanted slot win.
+ * out[i * GPX_LOG_SPAN + k] answers slot wants[i].min_slot + k: the two images (flags GPX_F_VOID where there is none;
+ * accept.payload_off is relative to its segment's payload area as in the ring) and the absolute ring position of the
+ * accept's request blob (gpx_log_read(lane, blob_pos, dst, accept.payload_len, ...)).  getActualDecisions :2539-2583
+ * (a meta decision gets its value from the logged accept of the slot) is the caller joining the two. */
+#define GPX_LOG_SPAN 16
+typedef struct gpx_log_want { /* 16 B */
+  uint32_t gid;
+  int32_t min_slot;
+  uint32_t n_slots;  /* <= GPX_LOG_SPAN */
+  uint32_t reserved;
+} gpx_log_want;
+typedef struct gpx_log_hit { /* 96 B */
+  gpx_decision_rec decision;
+  gpx_accept_rec accept;
+  uint64_t blob_pos;
+  uint64_t reserved;
+} gpx_log_hit;
+int gpx_log_find(gpx_engine* e, uint32_t lane, uint64_t from, uint32_t n, const gpx_log_want* wants, gpx_log_hit* out);
+
 /* ---- introspection ---------------------------------------------------------------- */
 int gpx_get_counters(gpx_engine* e, gpx_counters* out);
 int gpx_reset_counters(gpx_engine* e);

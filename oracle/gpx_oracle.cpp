@@ -1748,6 +1748,52 @@ int gpxo_log_read(gpxo_engine* e, uint32_t lane, uint64_t from, void* dst, uint6
   return GPX_OK;
 }
 
+/* AbstractPaxosLogger.getLoggedDecisions :582 / getLoggedAccepts :568 in the journaling form
+ * (SQLPaxosLogger.getLoggedFromMessageLog :3674-3756 over paxosutil/LogIndex.java:213-248): per wanted slot the entry
+ * logged LAST (`accepts.put(packet.slot, packet)` :3746, log order) */
+int gpxo_log_find(gpxo_engine* e, uint32_t lane, uint64_t from, uint32_t n, const gpx_log_want* wants, gpx_log_hit* out) {
+  if (!e || (n && (!wants || !out))) return GPX_EINVAL;
+  if (lane >= e->L()) return GPX_ERANGE;
+  for (u32 i = 0; i < n; i++) {
+    if (wants[i].n_slots > GPX_LOG_SPAN) return GPX_ERANGE;
+    if (i && wants[i - 1].gid >= wants[i].gid) return GPX_EINVAL; /* sorted by gid, one want per group */
+  }
+  const std::vector<uint8_t>& r = e->lanes[lane].ring;
+  for (u64 t = 0; t < (u64)n * GPX_LOG_SPAN; t++) {
+    memset(&out[t], 0, sizeof out[t]);
+    out[t].decision.flags = GPX_F_VOID;
+    out[t].accept.h.flags = GPX_F_VOID;
+  }
+  u64 off = from;
+  while (off + 64 <= r.size()) {
+    gpx_log_seg_hdr h;
+    memcpy(&h, &r[off], sizeof h);
+    if (h.magic != GPX_SEG_MAGIC || h.ring_off != off) return GPX_EINVAL; /* `from` is not a segment boundary */
+    const u64 imgs = off + 64, pay = imgs + (u64)h.n_slots * h.rec_bytes;
+    const bool isAcc = h.rec_bytes == 48, isDec = h.rec_bytes == 32 && h.type == GPX_F_DECISION;
+    for (u32 j = 0; (isAcc || isDec) && j < h.n_valid; j++) {
+      gpx_pvalue_hdr img;
+      memcpy(&img, &r[imgs + (u64)j * 32], 32);
+      if (img.flags & GPX_F_VOID) continue;
+      const gpx_log_want* w = std::lower_bound(wants, wants + n, img.gid,
+                                               [](const gpx_log_want& a, u32 g) { return a.gid < g; });
+      if (w == wants + n || w->gid != img.gid) continue;
+      const i32 k = jsub(img.slot, w->min_slot);
+      if (k < 0 || (u32)k >= w->n_slots) continue;
+      gpx_log_hit& hit = out[(u64)(w - wants) * GPX_LOG_SPAN + (u32)k];
+      if (isDec) {
+        hit.decision = img;
+      } else {
+        hit.accept.h = img;
+        memcpy(&hit.accept.payload_off, &r[imgs + (u64)h.n_slots * 32 + (u64)j * 16], 16);
+        hit.blob_pos = pay + hit.accept.payload_off;
+      }
+    }
+    off = (pay + ((h.payload_bytes + 15) & ~(u64)15) + 31) & ~(u64)31;
+  }
+  return GPX_OK;
+}
+
 /* drop the in-memory log (a drained / garbage-collected journal); used by long CPU-baseline runs */
 int gpxo_log_truncate(gpxo_engine* e) {
   for (auto& ln : e->lanes) {

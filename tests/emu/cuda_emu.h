@@ -44,6 +44,13 @@ static inline T atomicAdd(T* p, T v) { /* one thread at a time */
   return old;
 }
 
+template <class T>
+static inline T atomicMax(T* p, T v) {
+  T old = *p;
+  if (v > old) *p = v;
+  return old;
+}
+
 /* run kernel(args...) over grid x block threads, block by block, thread by thread */
 template <class K, class... Args>
 static void emu_launch(K kernel, unsigned grid, unsigned block, Args... args) {

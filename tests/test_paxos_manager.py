@@ -14,7 +14,7 @@ NODES = [100, 101, 102]
 
 def make_pm(lib, app_cls, p1b=False, **kw):
     eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20, **kw))
-    return PaxosManager(eng, [app_cls() for _ in NODES], NODES, device_phase1b=p1b)
+    return PaxosManager(eng, [app_cls() for _ in NODES], NODES, device_phase1b=p1b, device_log_find=p1b)
 
 
 def drive(lib):
@@ -332,10 +332,10 @@ def test_prepare_reply_tally_follows_the_reference_code():
 
 # ---- catching up a lagging replica (PISM.syncLongDecisionGaps :1550 / handleSyncDecisionsPacket :2426 / checkpoint
 #      transfer :1852) ------------------------------------------------------------------------------------------------
-def drive_sync(lib):
+def drive_sync(lib, p1b=False):
     from gigapaxos_b200.paxos_manager import RequestPacket
     from helpers import make_requests
-    pm = make_pm(lib, HashChainApp, checkpoint_interval=100)
+    pm = make_pm(lib, HashChainApp, checkpoint_interval=100, p1b=p1b)
     eng = pm.engine
     names = [f"TESTPaxosApp{i}" for i in range(6)]
     pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
@@ -393,7 +393,9 @@ def drive_sync(lib):
 
 
 def test_sync_decisions_cpu(oracle_lib):
-    drive_sync(oracle_lib)
+    a = drive_sync(oracle_lib)
+    b = drive_sync(oracle_lib, p1b=True)  # the donor's journal looked up by gpx_log_find instead of a host walk of the ring
+    assert a.apps[2].state == b.apps[2].state and a.num_decisions == b.num_decisions
 
 
 @pytest.mark.gpu

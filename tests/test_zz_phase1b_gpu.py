@@ -140,3 +140,63 @@ def test_pause_batch_through_the_mirror(cuda_lib, oracle_lib):
     (g, tg), (o, to) = drive(cuda_lib), drive(oracle_lib)
     assert tg == to and len(to) == 11  # the same HotRestoreInfo strings in the pause table
     assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
+
+
+# ---- the journal's index as a scan (k_log_dir / k_log_scan / k_log_hits behind gpx_log_find; same late arrival) -----------
+def _same_hits(eg, eo, lane, hg, ho):
+    """decision images byte for byte; accept images field by field except payload_off (the position of a batched slot's
+    constructed blob inside its segment depends on block scheduling) -- the blob CONTENT is compared"""
+    assert hg["decision"].tobytes() == ho["decision"].tobytes()
+    for f in abi.accept_dtype.names:
+        if f != "payload_off":
+            assert np.array_equal(hg["accept"][f], ho["accept"][f]), f
+    found = np.argwhere((ho["accept"]["flags"] & abi.F_VOID) == 0)
+    for i, k in found:
+        n = int(ho[i, k]["accept"]["payload_len"])
+        if n:
+            assert bytes(eg.log_read(lane, int(hg[i, k]["blob_pos"]), n)) == bytes(eo.log_read(lane, int(ho[i, k]["blob_pos"]), n))
+    return len(found)
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_log_find_kernels_equal_oracle(cuda_lib, oracle_lib, seed):
+    from test_log_find import logged_engine, random_wants
+    G = 40
+    (eg, hg_), (eo, ho_) = logged_engine(cuda_lib, G, seed), logged_engine(oracle_lib, G, seed)
+    assert hg_ == ho_  # the same ring positions call by call (no wrap)
+    rng = np.random.default_rng(seed)
+    found = 0
+    for lane in range(3):
+        for start in (0, ho_[lane][len(ho_[lane]) // 2]):
+            wants = random_wants(G, rng)
+            found += _same_hits(eg, eo, lane, eg.log_find(lane, wants, start), eo.log_find(lane, wants, start))
+    assert found > 50
+
+
+def test_log_find_on_a_ring_that_wrapped(cuda_lib, oracle_lib):
+    """a 128 KiB ring (no back-pressure: the oldest bytes are overwritten), the scan starts at the oldest call boundary that
+    is still intact: stale laps and skipped tails are not taken for segments, what is found is what the oracle finds in
+    the same calls"""
+    from test_log_find import logged_engine, random_wants
+    G, ring = 40, 1 << 17
+    kw = dict(rounds=70, log_ring_bytes=ring, max_batch_payload=1 << 14)
+    (eg, hg_), (eo, ho_) = logged_engine(cuda_lib, G, 43, **kw), logged_engine(oracle_lib, G, 43, **kw)
+    rng = np.random.default_rng(43)
+    found = 0
+    for lane in range(3):
+        assert len(hg_[lane]) == len(ho_[lane]) and hg_[lane][-1] > 2 * ring  # wrapped at least twice
+        i = next(j for j, p in enumerate(hg_[lane]) if hg_[lane][-1] - p <= ring)
+        assert 0 < i < len(hg_[lane]) - 1
+        wants = random_wants(G, rng, max_slot=72)
+        found += _same_hits(eg, eo, lane, eg.log_find(lane, wants, hg_[lane][i]), eo.log_find(lane, wants, ho_[lane][i]))
+        with pytest.raises(abi.GpxError):  # one lap too far back
+            eg.log_find(lane, wants, hg_[lane][0])
+    assert found > 20
+
+
+def test_sync_and_lagging_election_with_the_scan(cuda_lib, oracle_lib):
+    """the host mirror's catch-up (syncDecisions) and a lagging preparer's logged accepts, both looked up by gpx_log_find"""
+    from test_paxos_manager import _same_end_state, drive_lagging_election, drive_sync
+    g, o = drive_sync(cuda_lib, p1b=True), drive_sync(oracle_lib, p1b=True)
+    assert g.apps[2].state == o.apps[2].state and g.num_decisions == o.num_decisions
+    _same_end_state(drive_lagging_election(cuda_lib, p1b=True), drive_lagging_election(oracle_lib, p1b=True))
