@@ -10,10 +10,13 @@ from helpers import Engine, abi, group_descs, make_config
 NODES5 = [100, 101, 102, 103, 104]
 
 
-def make_engine(lib, R: int, G: int):
+def make_engine(lib, R: int, G: int, lane_nodes=None):
+    """lane_nodes: the nodes this engine hosts (default: all R members, lane l = member l).  A single-lane engine that hosts
+    one member of every group is a node of the spread placement: the other acceptors' replies come in as records."""
     nodes = NODES5[:R]
-    eng = Engine(lib, make_config(lib, n_lanes=R, max_groups=G, max_group_size=R, max_batch_recs=4096,
-                                  max_batch_payload=1 << 20, lane_node=nodes))
+    lane_nodes = nodes if lane_nodes is None else list(lane_nodes)
+    eng = Engine(lib, make_config(lib, n_lanes=len(lane_nodes), max_groups=G, max_group_size=R, max_batch_recs=4096,
+                                  max_batch_payload=1 << 20, lane_node=lane_nodes))
     eng.create_groups(group_descs(G, members=tuple(nodes)))
     return eng
 
@@ -21,16 +24,17 @@ def make_engine(lib, R: int, G: int):
 def preconditions(eng, R: int, G: int, rng) -> None:
     """coordinators of assorted ballots on assorted lanes, a few stopped acceptors, a few destroyed groups"""
     pts = []
+    L = eng.n_lanes
     for gid in range(G):
-        for l in range(R):
+        for l in range(L):
             k = int(rng.integers(0, 6))
             if k == 0:
                 pts.append((gid, l, abi.PATCH_RESIGN_COORD, 0, 0, 0, 0))
             elif k == 1:
-                pts.append((gid, l, abi.PATCH_INSTALL_COORD, int(rng.integers(0, 9)), NODES5[l], int(rng.integers(0, 30)),
+                pts.append((gid, l, abi.PATCH_INSTALL_COORD, int(rng.integers(0, 9)), int(eng.cfg.lane_node[l]), int(rng.integers(0, 30)),
                             int(rng.integers(0, 2))))
         if rng.integers(0, 40) == 0:
-            pts.append((gid, int(rng.integers(0, R)), abi.PATCH_SET_STATE, abi.ST_STOPPED, 0, 0, 0))
+            pts.append((gid, int(rng.integers(0, L)), abi.PATCH_SET_STATE, abi.ST_STOPPED, 0, 0, 0))
     p = np.zeros(len(pts), dtype=abi.patch_dtype)
     for i, t in enumerate(pts):
         p[i]["gid"], p[i]["lane"], p[i]["op"], p[i]["a"], p[i]["b"], p[i]["c"], p[i]["d"] = t
@@ -41,16 +45,18 @@ def preconditions(eng, R: int, G: int, rng) -> None:
         eng.destroy_groups(dead)
 
 
-def random_elections(R: int, G: int, rng, wrap: bool = False):
+def random_elections(R: int, G: int, rng, wrap: bool = False, lane_nodes=None):
     """-> (election records, reply records).  One election per group (a random subset of the groups, shuffled)."""
+    lane_nodes = NODES5[:R] if lane_nodes is None else list(lane_nodes)
+    L = len(lane_nodes)
     gids = [g for g in rng.permutation(G) if rng.integers(0, 10) < 8]
     els = np.zeros(len(gids), dtype=abi.election_dtype)
     recs = []
     base = 0x7FFFFFF0 if wrap else 0  # slots straddling the int wrap
     jint = lambda v: ((int(v) + (1 << 31)) % (1 << 32)) - (1 << 31)
     for i, gid in enumerate(gids):
-        lane = R if rng.integers(0, 16) == 0 else int(rng.integers(0, R))  # R = not a lane: dropped
-        my = (int(rng.integers(1, 8)), NODES5[lane % R])
+        lane = L if rng.integers(0, 16) == 0 else int(rng.integers(0, L))  # L = not a lane: dropped
+        my = (int(rng.integers(1, 8)), lane_nodes[lane % L])
         fus = int(rng.integers(0, 20))
         els[i]["gid"], els[i]["lane"], els[i]["bnum"], els[i]["bcoord"] = gid, lane, my[0], my[1]
         els[i]["slot"] = jint(base + fus)
@@ -99,7 +105,7 @@ def random_elections(R: int, G: int, rng, wrap: bool = False):
             for ci, ch in enumerate(chunks):
                 q = r.copy()
                 more = abi.F_MORE if ci + 1 < len(chunks) else 0
-                q["who"] = abi.who(idx if idx < R or rng.integers(0, 2) else 0xFF, lane % R, flags | more)
+                q["who"] = abi.who(idx if idx < R or rng.integers(0, 2) else 0xFF, NODES5.index(my[1]), flags | more)
                 q["n_accepted"] = len(ch)
                 for j, pv in enumerate(ch):
                     q["accepted"][j] = pv
@@ -111,7 +117,7 @@ def random_elections(R: int, G: int, rng, wrap: bool = False):
 
 def dump_all(eng, R: int, G: int):
     gids = np.arange(G, dtype=np.uint32)
-    return [eng.dump_rows(gids, l) for l in range(R)]
+    return [eng.dump_rows(gids, l) for l in range(eng.n_lanes)]
 
 
 def assert_same_out(a: np.ndarray, b: np.ndarray):

@@ -72,20 +72,22 @@ def twin_election(pm: PaxosManager, R: int, el, reps: np.ndarray):
     return out
 
 
-@pytest.mark.parametrize("R,seed,wrap", [(3, 1, False), (3, 2, True), (5, 3, False), (5, 4, True), (1, 5, False),
-                                         (4, 6, False)])
-def test_oracle_phase1b_equals_the_host_twin(oracle_lib, R, seed, wrap):
+@pytest.mark.parametrize("R,seed,wrap,lane_nodes", [(3, 1, False, None), (3, 2, True, None), (5, 3, False, None),
+                                                    (5, 4, True, None), (1, 5, False, None), (4, 6, False, None),
+                                                    (3, 7, False, [101]), (5, 8, True, [103, 100])])  # nodes of a spread placement
+def test_oracle_phase1b_equals_the_host_twin(oracle_lib, R, seed, wrap, lane_nodes):
     G = 160
     rng = np.random.default_rng(seed)
-    ea, eb = make_engine(oracle_lib, R, G), make_engine(oracle_lib, R, G)
-    pm = PaxosManager(eb, [NoopPaxosApp() for _ in range(R)], NODES5[:R])
+    ea, eb = make_engine(oracle_lib, R, G, lane_nodes), make_engine(oracle_lib, R, G, lane_nodes)
+    hosted = NODES5[:R] if lane_nodes is None else lane_nodes
+    pm = PaxosManager(eb, [NoopPaxosApp() for _ in hosted], hosted)
     verdicts = set()
     for rnd in range(4):
         st = rng.bit_generator.state
         preconditions(ea, R, G, rng)
         rng.bit_generator.state = st
         preconditions(eb, R, G, rng)
-        els, reps = random_elections(R, G, rng, wrap)
+        els, reps = random_elections(R, G, rng, wrap, lane_nodes)
         got = ea.handle_prepare_replies(els, reps)
         want = np.array([twin_election(pm, R, el, reps) for el in els], dtype=abi.election_out_dtype)
         assert_same_out(got, want)
@@ -143,7 +145,7 @@ def emu_lib(tmp_path_factory):
 def _state_arrays(rows, R, G, W, Rcap, rng):
     """DevState's arrays for phase 1b from dumped rows: acc_aux [L][G], coord_row [L][G] int4, node_slots [L][Rcap][G],
     prop_win [L][W][G] int4 (a nonzero pattern: only a resign / install may clear it)"""
-    L = R
+    L = len(rows)
     aux = np.zeros((L, G), dtype=np.uint32)
     crow = np.zeros((L, G, 4), dtype=np.int32)
     nsl = np.full((L, Rcap, G), -7, dtype=np.int32)
@@ -160,18 +162,20 @@ def _state_arrays(rows, R, G, W, Rcap, rng):
     return aux, crow, nsl, pwin
 
 
-@pytest.mark.parametrize("R,seed,wrap,block", [(3, 11, False, 64), (3, 12, True, 1), (5, 13, False, 64), (5, 14, True, 7),
-                                               (1, 15, False, 64), (4, 16, False, 33)])
-def test_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, R, seed, wrap, block):
+@pytest.mark.parametrize("R,seed,wrap,block,lane_nodes", [(3, 11, False, 64, None), (3, 12, True, 1, None), (5, 13, False, 64, None),
+                                                          (5, 14, True, 7, None), (1, 15, False, 64, None), (4, 16, False, 33, None),
+                                                          (3, 17, False, 64, [102]), (5, 18, True, 16, [101, 104])])
+def test_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, R, seed, wrap, block, lane_nodes):
     import ctypes as C
     G, W = 160, 8
     Rcap = R
     rng = np.random.default_rng(seed)
-    eng = make_engine(oracle_lib, R, G)
+    eng = make_engine(oracle_lib, R, G, lane_nodes)
+    L = eng.n_lanes
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     for rnd in range(3):
         preconditions(eng, R, G, rng)
-        els, reps = random_elections(R, G, rng, wrap)
+        els, reps = random_elections(R, G, rng, wrap, lane_nodes)
         rows = dump_all(eng, R, G)
         aux, crow, nsl, pwin = _state_arrays(rows, R, G, W, Rcap, rng)
         pwin0, crow0 = pwin.copy(), crow.copy()
@@ -180,14 +184,15 @@ def test_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, R, seed, w
         got = np.zeros(len(els), dtype=abi.election_out_dtype)
         got.view(np.uint8)[:] = 0xAB  # the kernel must write every byte of its records
         members = np.array(NODES5[:R], dtype=np.int32)
-        launches = emu_lib.emu_prepare_tally(G, R, W, Rcap, R, ptr(members), ptr(members), ptr(live), ptr(crow), ptr(aux),
+        hosted = members if lane_nodes is None else np.array(lane_nodes, dtype=np.int32)
+        launches = emu_lib.emu_prepare_tally(G, L, W, Rcap, R, ptr(members), ptr(hosted), ptr(live), ptr(crow), ptr(aux),
                                              ptr(nsl), ptr(pwin), len(els), ptr(els), ptr(reps), ptr(got), block)
         assert launches == 1
         assert_same_out(got, want)
         after = dump_all(eng, R, G)
         won = {int(o["gid"]): (int(e["lane"]), (int(e["bnum"]), int(e["bcoord"])))
                for o, e in zip(want, els) if int(o["verdict"]) == abi.EL_MAJORITY}
-        for l in range(R):
+        for l in range(L):
             a = after[l]
             ex = a["coord_exists"] != 0
             assert np.array_equal(crow[l, :, 0], np.where(ex, a["coord_bnum"], 0))

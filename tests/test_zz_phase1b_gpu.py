@@ -14,19 +14,21 @@ from p1b_cases import assert_same_out, assert_same_rows, make_engine, preconditi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("R,seed,wrap", [(3, 21, False), (3, 22, True), (5, 23, False), (5, 24, True), (1, 25, False),
-                                         (4, 26, False), (2, 27, False)])
-def test_phase1b_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed, wrap):
+@pytest.mark.parametrize("R,seed,wrap,lane_nodes", [(3, 21, False, None), (3, 22, True, None), (5, 23, False, None),
+                                                    (5, 24, True, None), (1, 25, False, None), (4, 26, False, None),
+                                                    (2, 27, False, None),
+                                                    (3, 28, False, [101]), (5, 29, True, [103, 100])])  # nodes of a spread placement
+def test_phase1b_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed, wrap, lane_nodes):
     G = 300
     rng = np.random.default_rng(seed)
-    eg, eo = make_engine(cuda_lib, R, G), make_engine(oracle_lib, R, G)
+    eg, eo = make_engine(cuda_lib, R, G, lane_nodes), make_engine(oracle_lib, R, G, lane_nodes)
     verdicts = set()
     for rnd in range(4):
         st = rng.bit_generator.state
         preconditions(eg, R, G, rng)
         rng.bit_generator.state = st
         preconditions(eo, R, G, rng)
-        els, reps = random_elections(R, G, rng, wrap)
+        els, reps = random_elections(R, G, rng, wrap, lane_nodes)
         got, want = eg.handle_prepare_replies(els, reps), eo.handle_prepare_replies(els, reps)
         assert_same_out(got, want)
         verdicts |= set(int(v) for v in want["verdict"])
