@@ -17,6 +17,13 @@
  * paxosutil/HotRestoreInfo.java:159-175 (the one literal-valued test), RFC 1321 vectors
  * for MD5 (digest bytes are "parity unpinned" by the reference).
  *
+ * Beyond phase 2 it restates, for the batch entry points added next to the hot path: phase 1a at the acceptors
+ * (gpxo_handle_prepares: PISM.handlePrepare, PaxosAcceptor.handlePrepare :239-297), phase 1b at the would-be
+ * coordinator (gpxo_handle_prepare_replies: PaxosCoordinatorState.java:264-587 -- from the CODE; where the class's
+ * own main() asserts something else), the deactivation sweep (gpxo_pause_groups: PISM.tryPause
+ * :2004-2035) and the journal look-ups (gpxo_log_find: SQLPaxosLogger.getLoggedFromMessageLog :3674-3756).  Of these
+ * only HotRestoreInfo's literal pins anything the reference produced: parity unpinned, as above.
+ *
  * It exposes the same record-level C ABI as include/gpx.h with the prefix gpxo_ so that
  * tests feed identical batches to the CUDA engine and to this file and compare bytes.
  *

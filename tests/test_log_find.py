@@ -54,10 +54,10 @@ def logged_engine(lib, G=40, seed=1, rounds=5, **cfg):
         mark()
     # the next node takes over every group: PREPAREs are logged, then the carried-over slots are accepted AGAIN under the
     # new ballot (the later entry must win) and decided
-    from gigapaxos_b200.paxos_manager import NoopPaxosApp, PaxosManager
+    from gigapaxos_b200.paxos_manager import NoopPaxosApp, PaxosManager, _Instance
     pm = PaxosManager(eng, [NoopPaxosApp() for _ in NODES], NODES, device_phase1b=lib.has("handle_prepare_replies"))
-    for i in range(G):
-        pm.instances[f"NoopPaxosApp{i}"] = __import__("gigapaxos_b200.paxos_manager", fromlist=["_Instance"])._Instance(i, 0, NODES)
+    for i in range(G):  # adopt the groups created above (group_descs names them NoopPaxosApp<i>, gid i)
+        pm.instances[f"NoopPaxosApp{i}"] = _Instance(i, 0, NODES)
         pm.gid_name[i] = f"NoopPaxosApp{i}"
     pm.next_gid = G
     for c in range(3):
