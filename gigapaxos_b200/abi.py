@@ -283,6 +283,18 @@ class Engine:
         self.L.check(self.L.fn("log_find")(self._h, C.c_uint32(lane), C.c_uint64(from_), C.c_uint32(n), _ptr(wants), _ptr(out)))
         return out[:n]
 
+    def select_groups(self, lane: int, mask: int, value: int, cap: Optional[int] = None) -> np.ndarray:
+        """The live, ACTIVE groups of `lane` with (flag byte & mask) == value, ascending (gpx_select_groups): the slow-path
+        list (mask = value = GF_NEEDS_SYNC) or the pause candidates (mask = GF_NOT_CAUGHT_UP, value = 0)."""
+        cap = int(self.cfg.max_groups) if cap is None else int(cap)
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        n = C.c_uint32(0)
+        self.L.check(self.L.fn("select_groups")(self._h, C.c_uint32(lane), C.c_uint32(mask), C.c_uint32(value), _ptr(out),
+                                                C.c_uint32(cap), C.byref(n)))
+        if n.value > cap:
+            raise GpxError(GPX_ERANGE, f"{n.value} groups match, buffer holds {cap}")
+        return out[: n.value].copy()
+
     def pause_groups(self, gids):
         """The deactivation sweep (gpx_pause_groups): -> (rows [n, n_lanes] of gpx_row, paused [n] bool).  Rows of groups
         that did not pause are zero."""

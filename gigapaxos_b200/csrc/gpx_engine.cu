@@ -1601,6 +1601,38 @@ int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t
   return GPX_OK;
 }
 
+/* the slow-path list / the candidates of a sweep: one launch of k_select_groups over all gids (gpx_pause.cuh) */
+int gpx_select_groups(gpx_engine* e, uint32_t lane, uint32_t mask, uint32_t value, uint32_t* out_gids, uint32_t cap,
+                      uint32_t* n_found) {
+  if (!e || !n_found || (!out_gids && cap)) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  int rc = e->ensure_misc(16 + (size_t)cap * 4);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  uint8_t* base = (uint8_t*)e->d_misc;
+  SelectArgs A;
+  A.lane = lane;
+  A.mask = mask;
+  A.value = value;
+  A.cap = cap;
+  A.n_found = (unsigned long long*)base;
+  A.gids = (uint32_t*)(base + 16);
+  CK(cudaMemsetAsync(base, 0, 16, st));
+  k_select_groups<<<cdiv(e->cfg.max_groups, GPX_PAUSE_BLOCK), GPX_PAUSE_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  unsigned long long found = 0;
+  CK(cudaMemcpyAsync(&found, A.n_found, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint32_t got = (uint32_t)std::min<unsigned long long>(found, cap);
+  if (got) {
+    CK(cudaMemcpyAsync(out_gids, A.gids, (size_t)got * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::sort(out_gids, out_gids + got);
+  }
+  *n_found = (uint32_t)std::min<unsigned long long>(found, 0xffffffffull);
+  return GPX_OK;
+}
+
 /* the deactivation sweep: one launch of k_pause_groups (gpx_pause.cuh) */
 int gpx_pause_groups(gpx_engine* e, uint32_t n, const uint32_t* gids, gpx_row* out_rows, uint8_t* out_paused) {
   if (!e) return fail(GPX_EINVAL, "null argument");

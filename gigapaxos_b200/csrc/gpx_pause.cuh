@@ -49,3 +49,27 @@ __global__ void __launch_bounds__(GPX_PAUSE_BLOCK) k_pause_groups(const __grid_c
   }
   free_group(S, gid);
 }
+
+/* ---- k_select_groups: the groups a sweep has to look at (gpx_select_groups) -------------------------------------------
+ * One thread per gid of the engine: live, this lane hosts a replica, its acceptor is ACTIVE and
+ * (group_flags & mask) == value -> the gid is appended (one atomicAdd per match; a sweep's matches are normally few --
+ * the groups that need a sync -- or the result is consumed in chunks of a pause batch).  The host sorts what comes
+ * back. */
+struct SelectArgs {
+  uint32_t lane, mask, value, cap;
+  uint32_t* gids;           /* [cap] */
+  unsigned long long* n_found;
+};
+
+__global__ void __launch_bounds__(GPX_PAUSE_BLOCK) k_select_groups(const __grid_constant__ DevState S,
+                                                                   const __grid_constant__ SelectArgs A) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid == 0) atomicAdd(&S.ctr[C_KERNEL_LAUNCHES], 1ull);
+  if (gid >= S.G) return;
+  const GroupCtx g = group_ctx(S, gid);
+  if (!g.live || g.ms->idx_of_lane[A.lane] == 0xffu) return;
+  if (!st_usable(S.acc_aux[row_idx(S, A.lane, gid)])) return;
+  if ((group_flags(S, A.lane, gid) & A.mask) != A.value) return;
+  const unsigned long long k = atomicAdd(A.n_found, 1ull);
+  if (k < A.cap) A.gids[k] = gid;
+}

@@ -69,6 +69,8 @@ public final class PaxosEngine implements AutoCloseable {
 			ByteBuffer nDecisions);
 	public static native int handleDecisions(long h, int n, ByteBuffer decisions, ByteBuffer execOut,
 			ByteBuffer extraExecOut, int extraCap, ByteBuffer nExtra);
+	/** the live ACTIVE groups of a lane whose flag byte satisfies (flags & mask) == value, ascending; nFound: one int */
+	public static native int selectGroups(long h, int lane, int mask, int value, ByteBuffer gidsOut, int cap, ByteBuffer nFound);
 	/** the Deactivator's batch (PaxosManager.pause(Map, dequeue)): rowsOut n x nLanes x 188 B, pausedOut n bytes; unpause = loadRows */
 	public static native int pauseGroups(long h, int n, ByteBuffer gids, ByteBuffer rowsOut, ByteBuffer pausedOut);
 	public static native int handlePrepares(long h, int n, ByteBuffer prepares, ByteBuffer prepareRepliesOut);

@@ -145,6 +145,13 @@ JNIEXPORT jint JNICALL GPX_JNI(handlePrepares)(JNIEnv* env, jclass cls, jlong h,
   return gpx_handle_prepares((gpx_engine*)(intptr_t)h, (uint32_t)n, (const gpx_pvalue_hdr*)buf(env, prepares),
                              (gpx_prepare_reply_rec*)buf(env, out_replies));
 }
+/* int selectGroups(long h, int lane, int mask, int value, ByteBuffer gidsOut [cap x 4 B], int cap, ByteBuffer nFound [4 B]):
+ * the groups a sweep of PaxosManager has to look at (slow-path list, pause candidates) */
+JNIEXPORT jint JNICALL GPX_JNI(selectGroups)(JNIEnv* env, jclass cls, jlong h, jint lane, jint mask, jint value, jobject gids_out,
+                                             jint cap, jobject n_found) {
+  return gpx_select_groups((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint32_t)mask, (uint32_t)value, (uint32_t*)buf(env, gids_out),
+                           (uint32_t)cap, (uint32_t*)buf(env, n_found));
+}
 /* int pauseGroups(long h, int n, ByteBuffer gids, ByteBuffer rowsOut [n x nLanes x gpx_row], ByteBuffer pausedOut [n]):
  * PaxosManager.pause(Map, dequeue) :2327-2366 for the Deactivator's batch; unpause is loadRows */
 JNIEXPORT jint JNICALL GPX_JNI(pauseGroups)(JNIEnv* env, jclass cls, jlong h, jint n, jobject gids, jobject rows_out,

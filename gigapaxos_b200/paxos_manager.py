@@ -758,6 +758,31 @@ class PaxosManager:
             done.append(n)
         return done
 
+    def syncAndDeactivate(self, pause: bool = True) -> Dict[str, int]:
+        """PaxosManager.syncAndDeactivate :2806-2900, the body of the Deactivator thread: every instance that is behind
+        catches up (syncPaxosInstance -> PISM.syncLongDecisionGaps :1550), every idle one is paused in batches.  The
+        reference tests each of pinstances in turn; here the engine names the groups (gpx_select_groups: one launch per
+        lane over all gids) -- those flagged NEEDS_SYNC, then those that are caught up on every lane -- and one
+        gpx_pause_groups call takes the idle ones out.  Returns {"synced": slots executed by catching up, "paused": n}."""
+        eng, L = self.engine, self.engine.n_lanes
+        if not (eng.L.has("select_groups") and eng.L.has("pause_groups")):
+            raise RuntimeError("the engine library has no gpx_select_groups / gpx_pause_groups")
+        synced = 0
+        for lane in range(L):
+            for gid in eng.select_groups(lane, abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC):
+                name = self.gid_name.get(int(gid))
+                if name is not None:
+                    synced += self.syncDecisions(name, lane)
+        paused: List[str] = []
+        if pause:
+            idle = None
+            for lane in range(L):
+                g = set(int(x) for x in eng.select_groups(lane, abi.GF_NOT_CAUGHT_UP, 0))
+                idle = g if idle is None else idle & g
+            names = [self.gid_name[g] for g in sorted(idle or ()) if g in self.gid_name]
+            paused = self.pauseBatch(names)
+        return {"synced": synced, "paused": len(paused)}
+
     def unpause(self, paxosID: str) -> bool:
         """PaxosManager.unpause :2370: rebuild the instance from its HotRestoreInfo (PISM.hotRestore :677-690)."""
         hris = self.paused.pop(paxosID, None)

@@ -601,6 +601,18 @@ int gpx_reset_counters(gpx_engine* e);
  * empty) is false.  PISM.tryPause :2004-2035 pauses an instance only when this bit is clear on every lane. */
 #define GPX_GF_NOT_CAUGHT_UP_BIT 4u
 int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint8_t* out);
+/* ---- the slow-path list / the candidates of a sweep --------------------------------------------------
+ * PaxosManager's sweeps walk ALL instances (syncAndDeactivate :2806-2900 iterates pinstances; the failure detector's
+ * checkRunForCoordinator pass likewise) and test each one; with millions of groups resident the test belongs where the
+ * state is.  gpx_select_groups returns the live groups of `lane` whose flag byte -- exactly what gpx_get_group_flags
+ * reports: GPX_GF_OVERFLOW_BIT | GPX_GF_NEEDS_SYNC_BIT | GPX_GF_NOT_CAUGHT_UP_BIT -- satisfies
+ * (flags & mask) == value and whose acceptor is ACTIVE: mask = value = GPX_GF_NEEDS_SYNC_BIT lists the groups to sync
+ * (PISM.syncLongDecisionGaps :1550), mask = GPX_GF_NOT_CAUGHT_UP_BIT, value = 0 the pause candidates
+ * (PISM.tryPause :2004).  out_gids[0 .. min(*n_found, cap)) in ascending order; *n_found is the number that matched
+ * (when it exceeds cap, which `cap` of them were returned is unspecified: ask again with a larger buffer). */
+int gpx_select_groups(gpx_engine* e, uint32_t lane, uint32_t mask, uint32_t value, uint32_t* out_gids, uint32_t cap,
+                      uint32_t* n_found);
+
 /* ---- batched pause: the deactivation sweep (PaxosManager.Deactivator :2951 -> syncAndDeactivate :2806-2900 ->
  * pause(Map, dequeue) :2327-2366, PAUSE_BATCH_SIZE PaxosConfig.java:715) as one launch.  For every gid of the batch,
  * PISM.tryPause :2004-2035 at every local lane that hosts a replica: the group is paused only if it is live, every such

@@ -1833,6 +1833,25 @@ int gpxo_get_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32
   return GPX_OK;
 }
 
+/* the test of a sweep over all instances (PaxosManager.syncAndDeactivate :2806-2900 iterates pinstances) */
+int gpxo_select_groups(gpxo_engine* e, uint32_t lane, uint32_t mask, uint32_t value, uint32_t* out_gids, uint32_t cap,
+                       uint32_t* n_found) {
+  if (!e || !n_found || (!out_gids && cap)) return GPX_EINVAL;
+  if (lane >= e->L()) return GPX_ERANGE;
+  u32 found = 0;
+  for (u32 gid = 0; gid < e->groups.size(); gid++) {
+    if (!e->usable(gid, lane) || e->memberIdx(e->groups[gid], e->lanes[lane].node) < 0) continue;
+    uint8_t fl = 0;
+    int rc = gpxo_get_group_flags(e, lane, 1, &gid, &fl);
+    if (rc) return rc;
+    if ((fl & mask) != value) continue;
+    if (found < cap) out_gids[found] = gid;
+    found++;
+  }
+  *n_found = found;
+  return GPX_OK;
+}
+
 /* PaxosManager.pause(Map, dequeue) :2327-2366 over PISM.tryPause :2004-2035 at every local replica of each group */
 int gpxo_pause_groups(gpxo_engine* e, uint32_t n, const uint32_t* gids, gpx_row* out_rows, uint8_t* out_paused) {
   if (!e || (n && (!gids || !out_rows || !out_paused))) return GPX_EINVAL;

@@ -196,3 +196,92 @@ def test_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, journaling
         assert np.array_equal(acc_aux[l] & 0xFF, after[l]["state"].astype(np.uint32) & 0xFF)
         assert np.array_equal(acc_row[l, :, 0][~freed], after[l]["acc_slot"][~freed])
         assert np.all(acc_row[l][freed] == np.array([0, -1, -1, -1])) and not coord_row[l][freed].any()
+
+
+# ---- gpx_select_groups: which groups a sweep has to look at --------------------------------------------------------------
+@pytest.mark.parametrize("R,seed", [(3, 11), (5, 12)])
+def test_oracle_select_groups_equals_the_per_group_flags(oracle_lib, R, seed):
+    G = 120
+    eng = busy_engine(oracle_lib, G, seed, 1, R)
+    all_g = np.arange(G, dtype=np.uint32)
+    for lane in range(R):
+        rows, flags = eng.dump_rows(all_g, lane), eng.group_flags(all_g, lane)
+        active = np.isin(rows["state"], (abi.ST_ACTIVE_1, abi.ST_ACTIVE_2))
+        for mask, value in ((abi.GF_NOT_CAUGHT_UP, 0), (abi.GF_NOT_CAUGHT_UP, abi.GF_NOT_CAUGHT_UP), (0, 0),
+                            (abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC)):
+            want = all_g[active & ((flags & mask) == value)]
+            assert np.array_equal(eng.select_groups(lane, mask, value), want)
+        n_idle = int((active & ((flags & abi.GF_NOT_CAUGHT_UP) == 0)).sum())
+        assert 0 < n_idle < G
+        with pytest.raises(abi.GpxError):
+            eng.select_groups(lane, abi.GF_NOT_CAUGHT_UP, 0, cap=n_idle - 1)  # more matches than the buffer holds
+
+
+def test_mirror_sync_and_deactivate(oracle_lib):
+    """PaxosManager.syncAndDeactivate: the engine names the groups; idle ones are paused in one batch and come back on
+    demand"""
+    eng = Engine(oracle_lib, make_config(oracle_lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
+    pm = PaxosManager(eng, [HashChainApp() for _ in NODES], NODES)
+    names = [f"TESTPaxosApp{i}" for i in range(24)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    for r in range(2):
+        for n in names:
+            pm.propose(n, f"{n}:{r}".encode())
+        pm.run_round()
+    pm.propose(names[5], b"waiting")  # queued at the host: not idle
+    res = pm.syncAndDeactivate()
+    assert res == {"synced": 0, "paused": 23} and not pm.isPaused(names[5])
+    assert len(eng.select_groups(0, 0, 0)) == 1
+    pm.run_round()
+    for n in names:
+        assert pm.propose(n, b"again") is not None
+    pm.run_round()
+    assert not pm.paused and all(a.state == pm.apps[0].state for a in pm.apps)
+
+
+@pytest.mark.parametrize("journaling,R,seed,block", [(1, 3, 21, 128), (0, 5, 22, 7)])
+def test_select_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, journaling, R, seed, block):
+    """k_select_groups on the state arrays of test_kernel_source_on_the_host_equals_oracle above"""
+    G, W = 120, 8
+    nodes = [100, 101, 102, 103, 104][:R]
+    eng = busy_engine(oracle_lib, G, seed, 1, R)
+    all_g = np.arange(G, dtype=np.uint32)
+    rows = [eng.dump_rows(all_g, l) for l in range(R)]
+    flags = [eng.group_flags(all_g, l) for l in range(R)]
+    rng = np.random.default_rng(seed)
+    live = (rows[0]["state"] != abi.ST_FREE).astype(np.uint8)
+    acc_row = np.zeros((R, G, 4), dtype=np.int32)
+    acc_aux = np.zeros((R, G), dtype=np.uint32)
+    acc_win = np.zeros((R, W, G, 8), dtype=np.int32)
+    coord_row = np.zeros((R, G, 4), dtype=np.int32)
+    for l in range(R):
+        r = rows[l]
+        acc_row[l, :, 3] = r["acc_gc_slot"]
+        busy = (flags[l] & abi.GF_NOT_CAUGHT_UP) != 0
+        ex = r["coord_exists"] != 0
+        why = rng.integers(0, 3 if not journaling else 2, size=G)
+        present = np.where(busy & ((why == 0) | ((why == 1) & ~ex)), 1 << int(rng.integers(0, 8)), 0)
+        sticky = rng.integers(0, 4, size=G).astype(np.uint32)  # OVERFLOW / NEEDS_SYNC bits
+        acc_aux[l] = (r["state"].astype(np.uint32) & 0xFF) | (present.astype(np.uint32) << 8) | (sticky << 24)
+        coord_row[l, :, 3] = np.where(ex, 1 | (np.where(busy & (why == 1), 2, 0) << 8), 0)
+        acc_win[l, :, :, 0] = (r["acc_gc_slot"] - 1)[None, :]
+        acc_win[l, :, :, 7] = 1
+        livepv = busy & (why == 2)
+        acc_win[l, 3, :, 0] = np.where(livepv, r["acc_gc_slot"] + 2, acc_win[l, 3, :, 0])
+        flags[l] = (flags[l] & abi.GF_NOT_CAUGHT_UP) | sticky.astype(np.uint8)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    nodes_a = np.array(nodes, dtype=np.int32)
+    for lane in range(R):
+        active = np.isin(rows[lane]["state"], (abi.ST_ACTIVE_1, abi.ST_ACTIVE_2))
+        for mask, value in ((abi.GF_NOT_CAUGHT_UP, 0), (abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC),
+                            (abi.GF_NEEDS_SYNC | abi.GF_NOT_CAUGHT_UP, abi.GF_NOT_CAUGHT_UP), (0, 0)):
+            want = all_g[active & ((flags[lane] & mask) == value)]
+            for cap in (G, max(len(want) - 2, 0)):
+                out = np.full(max(cap, 1), 0xFFFFFFFF, dtype=np.uint32)
+                found = np.zeros(1, dtype=np.uint64)
+                rc = emu_lib.emu_select_groups(G, R, W, R, R, ptr(nodes_a), ptr(nodes_a), ptr(live), int(journaling), ptr(acc_row),
+                                               ptr(acc_aux), ptr(acc_win), ptr(coord_row), lane, mask, value, ptr(out), cap,
+                                               ptr(found), block)
+                assert rc == 1 and int(found[0]) == len(want)
+                got = np.sort(out[: min(cap, len(want))])
+                assert np.array_equal(got, want) if cap >= len(want) else np.all(np.isin(got, want))

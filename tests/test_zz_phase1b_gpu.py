@@ -202,3 +202,39 @@ def test_sync_and_lagging_election_with_the_scan(cuda_lib, oracle_lib):
     g, o = drive_sync(cuda_lib, p1b=True), drive_sync(oracle_lib, p1b=True)
     assert g.apps[2].state == o.apps[2].state and g.num_decisions == o.num_decisions
     _same_end_state(drive_lagging_election(cuda_lib, p1b=True), drive_lagging_election(oracle_lib, p1b=True))
+
+
+@pytest.mark.parametrize("R,seed", [(3, 51), (5, 52)])
+def test_select_groups_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed):
+    from test_pause_batch import busy_engine
+    G = 120
+    eg, eo = busy_engine(cuda_lib, G, seed, 1, R), busy_engine(oracle_lib, G, seed, 1, R)
+    some = 0
+    for lane in range(R):
+        for mask, value in ((abi.GF_NOT_CAUGHT_UP, 0), (abi.GF_NOT_CAUGHT_UP, abi.GF_NOT_CAUGHT_UP), (0, 0),
+                            (abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC), (abi.GF_OVERFLOW | abi.GF_NEEDS_SYNC, 0)):
+            got, want = eg.select_groups(lane, mask, value), eo.select_groups(lane, mask, value)
+            assert np.array_equal(got, want), (lane, mask, value)
+            some += len(want)
+    assert some > G
+    # the sweep through the mirror: idle groups out in one batch, back on demand
+    from gigapaxos_b200.paxos_manager import HashChainApp, PaxosManager
+    from helpers import Engine, make_config
+
+    def drive(lib):
+        eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
+        pm = PaxosManager(eng, [HashChainApp() for _ in range(3)], [100, 101, 102])
+        names = [f"TESTPaxosApp{i}" for i in range(24)]
+        pm.createPaxosInstanceBatch({n: None for n in names}, [100, 101, 102])
+        for r in range(2):
+            for n in names:
+                pm.propose(n, f"{n}:{r}".encode())
+            pm.run_round()
+        pm.propose(names[5], b"waiting")
+        res = pm.syncAndDeactivate()
+        pm.run_round()
+        for n in names:
+            assert pm.propose(n, b"again") is not None
+        pm.run_round()
+        return res, pm.apps[0].state
+    assert drive(cuda_lib) == drive(oracle_lib)
