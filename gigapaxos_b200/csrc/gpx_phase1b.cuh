@@ -134,10 +134,14 @@ __global__ void __launch_bounds__(GPX_P1B_BLOCK) k_prepare_tally(const __grid_co
         int maxMin = ns[0]; /* getMaxMinCarryoverSlot :921-931 */
         for (uint32_t m = 1; m < R; m++)
           if (jsub(ns[m], maxMin) > 0) maxMin = ns[m];
-        if (jsub(maxCarry, maxMin) >= GPX_MAX_PLAN) {
+        const int span = jsub(maxCarry, maxMin); /* slots to fill - 1; negative: every carried-over slot lies below maxMin */
+        if (span >= GPX_MAX_PLAN) {
           verdict = GPX_EL_OVERFLOW; /* device rule */
         } else {
-          for (int cur = maxMin; jsub(cur, maxCarry) <= 0; cur = (int)((unsigned)cur + 1u)) {
+          /* for (curSlot = maxMin; curSlot - maxCarry <= 0; curSlot++) :408, counted so that no pair of slots (not even
+           * two that are 2^31 apart in a hostile record) can make it run away */
+          for (int d = 0; d <= span; d++) {
+            const int cur = (int)((unsigned)maxMin + (unsigned)d);
             uint32_t j = 0;
             while (j < ncarry && c_slot[j] != cur) j++;
             gpx_carryover* e = &o->plan[np];

@@ -566,13 +566,13 @@ class PaxosManager:
             max_carry = sl if max_carry is None or _jsub(sl, max_carry) > 0 else max_carry
         for v in node_slots:
             max_min = v if max_min is None or _jsub(v, max_min) > 0 else max_min
-        if _jsub(max_carry, max_min) >= abi.GPX_MAX_PLAN:
+        span = _jsub(max_carry, max_min)
+        if span >= abi.GPX_MAX_PLAN:
             return None
         plan: List[tuple] = []
-        sl = max_min
-        while _jsub(sl, max_carry) <= 0:
+        for d in range(span + 1):  # (span < 0: every carried-over slot lies below the slots to fill)
+            sl = _jadd(max_min, d)
             plan.append((sl, abi.CO_PVALUE) + carry[sl] if sl in carry else (sl, abi.CO_NOOP, None, 0))
-            sl = _jadd(sl, 1)
         plan, flags = PaxosManager._process_stop(plan, _jadd(max_carry, 1))
         return plan, (plan[0][0] if plan else _jadd(max_carry, 1)), flags
 

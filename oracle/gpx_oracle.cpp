@@ -1460,11 +1460,15 @@ struct PreActiveCoordinatorState { /* PaxosCoordinatorState.java:67-178 in the p
     if (carryoverProposals.empty()) return;
     const i32 maxCarryoverSlot = getMaxPValueSlot();
     const i32 maxMinCarryoverSlot = getMaxMinCarryoverSlot();
-    if (jsub(maxCarryoverSlot, maxMinCarryoverSlot) >= GPX_MAX_PLAN) { /* device rule */
+    const i32 span = jsub(maxCarryoverSlot, maxMinCarryoverSlot);
+    if (span >= GPX_MAX_PLAN) { /* device rule */
       overflow = true;
       return;
     }
-    for (i32 curSlot = maxMinCarryoverSlot; jsub(curSlot, maxCarryoverSlot) <= 0; curSlot = (i32)((u32)curSlot + 1u)) {
+    /* for (curSlot = maxMin; curSlot - maxCarry <= 0; curSlot++) :408 -- counted (span < 0: no iteration), so that two
+     * slots 2^31 apart in a hostile record cannot make it run away */
+    for (i32 d = 0; d <= span; d++) {
+      const i32 curSlot = (i32)((u32)maxMinCarryoverSlot + (u32)d);
       Phase1Proposal p;
       memset(&p, 0, sizeof p);
       p.slot = curSlot;

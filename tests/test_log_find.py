@@ -247,3 +247,18 @@ def test_kernel_source_on_a_ring_that_wraps(oracle_lib, emu_lib, seed):
         # one call too far back: its bytes are gone
         got, ctl = emu_find(emu_lib, ring, cap, head, call_pos[0], lane, wants)
         assert int(ctl[2]) == 1
+
+
+def test_a_header_with_absurd_sizes_is_not_followed(emu_lib):
+    """k_log_dir stops at a header whose sizes would move the walk backwards or beyond a lap (no launch writes such a
+    segment): reported as corrupt instead of walking on"""
+    cap = 1 << 12
+    ring = np.zeros(cap, dtype=np.uint8)
+    hdr = ring[:64].view(abi.seg_hdr_dtype)[0]
+    hdr["magic"], hdr["type"], hdr["n_slots"], hdr["n_valid"], hdr["rec_bytes"], hdr["ring_off"] = abi.SEG_MAGIC, abi.F_DECISION, 1, 1, 32, 0
+    wants = np.zeros(1, dtype=abi.log_want_dtype)
+    wants["n_slots"] = 4
+    for pb in ((1 << 64) - 64, 1 << 40):
+        ring[:64].view(abi.seg_hdr_dtype)[0]["payload_bytes"] = pb
+        got, ctl = emu_find(emu_lib, ring, cap, 2048, 0, 0, wants)
+        assert int(ctl[2]) == 2 and np.all(got["decision"]["flags"] == abi.F_VOID)

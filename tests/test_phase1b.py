@@ -287,3 +287,39 @@ def test_mass_failover_batched_equals_one_by_one(oracle_lib):
     a = drive_mass_failover(oracle_lib, batched=True)
     _same_end_state(a, drive_mass_failover(oracle_lib, batched=False))
     _same_end_state(a, drive_mass_failover(oracle_lib, batched=False, p1b=False))
+
+
+def test_slots_half_the_int_range_apart_do_not_run_away(oracle_lib, emu_lib):
+    """a (hostile or garbage) reply pair whose recorded minimum and carried-over maximum are exactly 2^31 apart: the
+    reference's fill loop `curSlot - maxCarryoverSlot <= 0` :408 would never end on it; oracle, twin and kernel count the
+    slots instead and agree that there is nothing to fill"""
+    import ctypes as C
+    R, G = 2, 4
+    INT_MIN = -(1 << 31)
+    eng, twin_eng = make_engine(oracle_lib, R, G), make_engine(oracle_lib, R, G)
+    els = np.zeros(1, dtype=abi.election_dtype)
+    els["gid"], els["lane"], els["bnum"], els["bcoord"], els["slot"], els["n_replies"] = 1, 0, 5, 100, 0, 2
+    reps = np.zeros(2, dtype=abi.prepare_reply_dtype)
+    reps["gid"], reps["bnum"], reps["bcoord"] = 1, 5, 100
+    reps["who"] = [abi.who(0, 0), abi.who(1, 0)]
+    reps["first_slot"] = -1  # gcSlot; firstSlot = 0
+    reps["n_accepted"] = [0, 1]
+    reps["accepted"][1][0]["slot"], reps["accepted"][1][0]["bnum"], reps["accepted"][1][0]["bcoord"] = INT_MIN, 1, 101
+    reps["accepted"][1][0]["flags"] = 1 << 16
+    rows = dump_all(eng, R, G)
+    out = eng.handle_prepare_replies(els, reps)[0]
+    # acceptor 0 records 0; acceptor 1's minimum INT_MIN is not "above" -1 and is not recorded: maxMin = 0, maxCarry = INT_MIN
+    assert int(out["verdict"]) == abi.EL_MAJORITY and list(out["node_slots"][:2]) == [0, -1]
+    assert int(out["n_plan"]) == 0 and int(out["next_slot"]) == INT_MIN + 1
+    pm = PaxosManager(twin_eng, [NoopPaxosApp() for _ in range(R)], NODES5[:R])
+    want = twin_election(pm, R, els[0], reps)
+    assert out.tobytes() == want.tobytes()
+    rng = np.random.default_rng(0)
+    aux, crow, nsl, pwin = _state_arrays(rows, R, G, 8, R, rng)
+    got = np.zeros(1, dtype=abi.election_out_dtype)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    members = np.array(NODES5[:R], dtype=np.int32)
+    live = np.ones(G, dtype=np.uint8)
+    assert emu_lib.emu_prepare_tally(G, R, 8, R, R, ptr(members), ptr(members), ptr(live), ptr(crow), ptr(aux), ptr(nsl), ptr(pwin),
+                                     1, ptr(els), ptr(reps), ptr(got), 64) == 1
+    assert got[0].tobytes() == out.tobytes()
