@@ -85,9 +85,13 @@ __global__ void k_log_dir(const __grid_constant__ DevState S, const __grid_const
     sg.pad = 0;
     A.segs[nseg++] = sg;
     nimg += h.n_valid;
-    const unsigned long long next =
-        (pos + 64ull + (unsigned long long)h.n_slots * h.rec_bytes + ((h.payload_bytes + 15ull) & ~15ull) + 31ull) & ~31ull;
-    if (next <= pos || next - pos > cap) { /* sizes no launch of this engine writes: do not follow them */
+    const unsigned long long body = (unsigned long long)h.n_slots * h.rec_bytes;
+    if (body > cap || h.payload_bytes > cap) { /* sizes no launch of this engine writes: do not follow them */
+      err = LOGF_CORRUPT;
+      break;
+    }
+    const unsigned long long next = (pos + 64ull + body + ((h.payload_bytes + 15ull) & ~15ull) + 31ull) & ~31ull;
+    if (next - pos > cap) {
       err = LOGF_CORRUPT;
       break;
     }
