@@ -295,6 +295,10 @@ class Engine:
             raise GpxError(GPX_ERANGE, f"{n.value} groups match, buffer holds {cap}")
         return out[: n.value].copy()
 
+    def clear_group_flags(self, lane: int, gids, mask: int):
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        self.L.check(self.L.fn("clear_group_flags")(self._h, C.c_uint32(lane), C.c_uint32(len(gids)), _ptr(gids), C.c_uint32(mask)))
+
     def pause_groups(self, gids):
         """The deactivation sweep (gpx_pause_groups): -> (rows [n, n_lanes] of gpx_row, paused [n] bool).  Rows of groups
         that did not pause are zero."""

@@ -1633,6 +1633,24 @@ int gpx_select_groups(gpx_engine* e, uint32_t lane, uint32_t mask, uint32_t valu
   return GPX_OK;
 }
 
+int gpx_clear_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint32_t mask) {
+  if (!e || (!gids && n)) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  if (n == 0) return GPX_OK;
+  { /* two threads must not read-modify-write the same word */
+    std::vector<uint32_t> g(gids, gids + n);
+    std::sort(g.begin(), g.end());
+    if (std::adjacent_find(g.begin(), g.end()) != g.end()) return fail(GPX_EINVAL, "a gid appears twice in the batch");
+  }
+  int rc = e->ensure_misc((size_t)n * 4);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->d_misc, gids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  k_clear_flags<<<cdiv(n, 128), 128, 0, e->stream>>>(e->S, lane, (const uint32_t*)e->d_misc, n, mask);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return GPX_OK;
+}
+
 /* the deactivation sweep: one launch of k_pause_groups (gpx_pause.cuh) */
 int gpx_pause_groups(gpx_engine* e, uint32_t n, const uint32_t* gids, gpx_row* out_rows, uint8_t* out_paused) {
   if (!e) return fail(GPX_EINVAL, "null argument");

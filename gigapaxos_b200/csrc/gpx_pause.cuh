@@ -73,3 +73,12 @@ __global__ void __launch_bounds__(GPX_PAUSE_BLOCK) k_select_groups(const __grid_
   const unsigned long long k = atomicAdd(A.n_found, 1ull);
   if (k < A.cap) A.gids[k] = gid;
 }
+
+/* gpx_clear_group_flags: the host has dealt with these slow-path entries */
+__global__ void k_clear_flags(const __grid_constant__ DevState S, uint32_t lane, const uint32_t* gids, uint32_t n,
+                              uint32_t mask) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || gids[i] >= S.G) return;
+  const size_t ri = row_idx(S, lane, gids[i]);
+  S.acc_aux[ri] &= ~((mask & (GPX_GF_OVERFLOW | GPX_GF_NEEDS_SYNC)) << 24);
+}

@@ -152,6 +152,9 @@ JNIEXPORT jint JNICALL GPX_JNI(selectGroups)(JNIEnv* env, jclass cls, jlong h, j
   return gpx_select_groups((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint32_t)mask, (uint32_t)value, (uint32_t*)buf(env, gids_out),
                            (uint32_t)cap, (uint32_t*)buf(env, n_found));
 }
+JNIEXPORT jint JNICALL GPX_JNI(clearGroupFlags)(JNIEnv* env, jclass cls, jlong h, jint lane, jint n, jobject gids, jint mask) {
+  return gpx_clear_group_flags((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint32_t)n, (const uint32_t*)buf(env, gids), (uint32_t)mask);
+}
 /* int pauseGroups(long h, int n, ByteBuffer gids, ByteBuffer rowsOut [n x nLanes x gpx_row], ByteBuffer pausedOut [n]):
  * PaxosManager.pause(Map, dequeue) :2327-2366 for the Deactivator's batch; unpause is loadRows */
 JNIEXPORT jint JNICALL GPX_JNI(pauseGroups)(JNIEnv* env, jclass cls, jlong h, jint n, jobject gids, jobject rows_out,

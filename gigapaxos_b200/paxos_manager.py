@@ -769,10 +769,13 @@ class PaxosManager:
             raise RuntimeError("the engine library has no gpx_select_groups / gpx_pause_groups")
         synced = 0
         for lane in range(L):
-            for gid in eng.select_groups(lane, abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC):
+            listed = eng.select_groups(lane, abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC)
+            for gid in listed:
                 name = self.gid_name.get(int(gid))
                 if name is not None:
                     synced += self.syncDecisions(name, lane)
+            if len(listed) and eng.L.has("clear_group_flags"):  # dealt with: out of the slow-path list
+                eng.clear_group_flags(lane, listed, abi.GF_NEEDS_SYNC | abi.GF_OVERFLOW)
         paused: List[str] = []
         if pause:
             idle = None

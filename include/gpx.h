@@ -613,6 +613,11 @@ int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t
 int gpx_select_groups(gpx_engine* e, uint32_t lane, uint32_t mask, uint32_t value, uint32_t* out_gids, uint32_t cap,
                       uint32_t* n_found);
 
+/* The OVERFLOW / NEEDS_SYNC bits are sticky: they stay until the host has dealt with the group (caught it up by a sync or
+ * a checkpoint transfer) and says so -- out of the slow-path list.  Clears `mask` (of those two bits) at `lane` for
+ * every gid given. */
+int gpx_clear_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint32_t mask);
+
 /* ---- batched pause: the deactivation sweep (PaxosManager.Deactivator :2951 -> syncAndDeactivate :2806-2900 ->
  * pause(Map, dequeue) :2327-2366, PAUSE_BATCH_SIZE PaxosConfig.java:715) as one launch.  For every gid of the batch,
  * PISM.tryPause :2004-2035 at every local lane that hosts a replica: the group is paused only if it is live, every such

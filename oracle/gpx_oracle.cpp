@@ -1837,6 +1837,14 @@ int gpxo_get_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32
   return GPX_OK;
 }
 
+int gpxo_clear_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint32_t mask) {
+  if (!e || (!gids && n)) return GPX_EINVAL;
+  if (lane >= e->L()) return GPX_ERANGE;
+  for (u32 k = 0; k < n; k++)
+    if (gids[k] < e->groups.size()) e->lanes[lane].acc[gids[k]].flags &= (uint8_t) ~(mask & (GF_OVERFLOW | GF_NEEDS_SYNC));
+  return GPX_OK;
+}
+
 /* the test of a sweep over all instances (PaxosManager.syncAndDeactivate :2806-2900 iterates pinstances) */
 int gpxo_select_groups(gpxo_engine* e, uint32_t lane, uint32_t mask, uint32_t value, uint32_t* out_gids, uint32_t cap,
                        uint32_t* n_found) {

@@ -285,3 +285,46 @@ def test_select_kernel_source_on_the_host_equals_oracle(oracle_lib, emu_lib, jou
                 assert rc == 1 and int(found[0]) == len(want)
                 got = np.sort(out[: min(cap, len(want))])
                 assert np.array_equal(got, want) if cap >= len(want) else np.all(np.isin(got, want))
+
+
+# ---- the slow-path list end to end: a replica that missed decisions is named by the engine, caught up, taken off the list ---
+def drive_flagged_sync(lib):
+    from gigapaxos_b200.paxos_manager import RequestPacket
+    eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20, checkpoint_interval=100))
+    pm = PaxosManager(eng, [HashChainApp() for _ in NODES], NODES)
+    names = [f"TESTPaxosApp{i}" for i in range(6)]
+    pm.createPaxosInstanceBatch({n: None for n in names}, NODES)
+    for r in range(2):
+        for n in names:
+            pm.propose(n, f"{n}:{r}".encode())
+        pm.run_round()
+    gids = np.array([pm.instances[n].gid for n in names], dtype=np.uint32)
+    rows0 = eng.dump_rows(gids, 0)
+    coord = [NODES.index(int(rows0[i]["acc_bcoord"])) for i in range(len(names))]
+    for k in range(11):  # lane 2 is cut off for 11 slots (more than the window), then hears the LAST decision only
+        reqs, pay = make_requests(gids, payload_len=5 + k % 7, seed=9, round_no=k)
+        reqs["flags"] = [c << 8 for c in coord]
+        reqs["entry_node"] = [NODES[c] for c in coord]
+        acc, blob, st = eng.propose(reqs, pay)
+        assert np.all(st > 0)
+        acc["dst_mask"] = 0b011
+        rep, _ = eng.handle_accepts(acc, blob)
+        dec = eng.handle_accept_replies(rep)
+        dec["dst_mask"] = 0b111 if k == 10 else 0b011
+        ex, extra = eng.handle_decisions(dec)
+        batches = {int(r["req_id"]): [RequestPacket(names[i], int(r["req_id"]),
+                                                    bytes(pay[int(r["payload_off"]): int(r["payload_off"]) + int(r["payload_len"])]),
+                                                    entry_replica=NODES[coord[i]])] for i, r in enumerate(reqs)}
+        pm._apply(np.concatenate([ex, extra]), batches)
+    listed = eng.select_groups(2, abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC)
+    assert np.array_equal(listed, np.sort(gids)) and len(eng.select_groups(0, abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC)) == 0
+    assert pm.apps[2].state != pm.apps[0].state
+    res = pm.syncAndDeactivate(pause=False)
+    assert res["synced"] == 11 * len(names) and pm.apps[2].state == pm.apps[0].state
+    assert len(eng.select_groups(2, abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC)) == 0  # dealt with: off the list
+    assert pm.syncAndDeactivate(pause=False) == {"synced": 0, "paused": 0}
+    return pm
+
+
+def test_slow_path_list_end_to_end(oracle_lib):
+    drive_flagged_sync(oracle_lib)

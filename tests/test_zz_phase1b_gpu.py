@@ -238,3 +238,11 @@ def test_select_groups_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed):
         pm.run_round()
         return res, pm.apps[0].state
     assert drive(cuda_lib) == drive(oracle_lib)
+
+
+def test_slow_path_list_end_to_end(cuda_lib, oracle_lib):
+    """a replica that missed more decisions than its window holds is flagged, gpx_select_groups names it, the mirror catches
+    it up (the donor's journal looked up by gpx_log_find) and gpx_clear_group_flags takes it off the list"""
+    from test_paxos_manager import _same_end_state
+    from test_pause_batch import drive_flagged_sync
+    _same_end_state(drive_flagged_sync(cuda_lib), drive_flagged_sync(oracle_lib))
