@@ -13,6 +13,11 @@ import subprocess
 import numpy as np
 import pytest
 
+# GPX_EMU_SANITIZE=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest ... : the emulated kernels under
+# AddressSanitizer + UBSan (every heap buffer numpy hands them gets red zones; so do their local arrays)
+import os as _os
+EMU_SANITIZE = ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if _os.environ.get("GPX_EMU_SANITIZE") else []
+
 from helpers import ROOT, Engine, abi, group_descs, make_config, make_requests
 
 NODES = [100, 101, 102]
@@ -142,7 +147,7 @@ def emu_lib(tmp_path_factory):
     cuda_inc = "/usr/local/cuda/include"
     if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("no CUDA headers")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", cuda_inc,
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", *EMU_SANITIZE, "-I", cuda_inc,
                            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "gigapaxos_b200", "csrc"),
                            "-x", "c++", os.path.join(ROOT, "tests", "emu", "logfind_emu.cpp"), "-o", out])
     lib = C.CDLL(out)

@@ -6,6 +6,11 @@ structured restatement -- verdict, nodeSlotNumbers, plan and the rows both leave
 import numpy as np
 import pytest
 
+# GPX_EMU_SANITIZE=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest ... : the emulated kernels under
+# AddressSanitizer + UBSan (every heap buffer numpy hands them gets red zones; so do their local arrays)
+import os as _os
+EMU_SANITIZE = ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if _os.environ.get("GPX_EMU_SANITIZE") else []
+
 from gigapaxos_b200.paxos_manager import NoopPaxosApp, PaxosManager
 from helpers import abi
 from p1b_cases import NODES5, assert_same_out, dump_all, make_engine, preconditions, random_elections
@@ -136,7 +141,7 @@ def emu_lib(tmp_path_factory):
     cuda_inc = "/usr/local/cuda/include"
     if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("no CUDA headers")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", cuda_inc,
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", *EMU_SANITIZE, "-I", cuda_inc,
                            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "gigapaxos_b200", "csrc"),
                            "-x", "c++", os.path.join(ROOT, "tests", "emu", "p1b_emu.cpp"), "-o", out])
     return ctypes.CDLL(out)
