@@ -799,6 +799,25 @@ class PaxosManager:
         self.engine.load_rows(rows)
         return True
 
+    def unpauseBatch(self, paxosIDs: Sequence[str]) -> List[str]:
+        """PaxosManager.unpause :2370 for many instances at once (a burst of requests for groups the sweep has moved out):
+        ONE gpx_load_rows call rebuilds all of them from their HotRestoreInfo strings (PISM.hotRestore :677-690)."""
+        rows, done = [], []
+        for n in dict.fromkeys(paxosIDs):
+            hris = self.paused.get(n)
+            if hris is None or n in self.instances:
+                continue
+            infos = [HotRestoreInfo.parse(h) for h in hris]
+            gid = self._alloc_gid()
+            self.instances[n] = _Instance(gid, infos[0].version, list(infos[0].members))
+            self.gid_name[gid] = n
+            rows += [h.to_row(gid, lane, self.nodes[lane]) for lane, h in enumerate(infos)]
+            del self.paused[n]
+            done.append(n)
+        if rows:
+            self.engine.load_rows(np.concatenate(rows))
+        return done
+
     def isPaused(self, paxosID: str) -> bool:
         return paxosID in self.paused
 

@@ -116,7 +116,10 @@ def test_mirror_pause_batch(oracle_lib):
         assert sorted(done) == sorted(n for n in names[:12] if n != names[3])
         assert all(pm.isPaused(n) and n not in pm.instances for n in done)
         pm.run_round()
-        for n in names:  # propose -> unpause on demand
+        if batch:  # half of them come back in one gpx_load_rows call, the rest on demand (propose -> unpause)
+            back = pm.unpauseBatch(done[::2] + ["nonexistent"])
+            assert back == done[::2] and all(not pm.isPaused(n) and n in pm.instances for n in back)
+        for n in names:
             assert pm.propose(n, f"{n}:later".encode()) is not None
         pm.run_round()
         assert not pm.paused and all(a.state == pm.apps[0].state for a in pm.apps)
