@@ -71,6 +71,7 @@ GPX_LOG_SPAN = 16
 log_want_dtype = np.dtype([("gid", "<u4"), ("min_slot", "<i4"), ("n_slots", "<u4"), ("reserved", "<u4")])
 log_hit_dtype = np.dtype([("decision", decision_dtype), ("accept", accept_dtype), ("blob_pos", "<u8"), ("reserved", "<u8")])
 assert log_want_dtype.itemsize == 16 and log_hit_dtype.itemsize == 96
+log_range_dtype = np.dtype([("pos", "<u8"), ("len", "<u4"), ("dst_off", "<u4")])
 exec_sum_dtype = np.dtype([("slot", "<i4"), ("lane_mask", "u1"), ("flags", "u1"), ("nreq", "<u2")])
 ROUND_COMPACT = 1
 ROUND_PACKED_REQS = 2
@@ -298,6 +299,22 @@ class Engine:
     def clear_group_flags(self, lane: int, gids, mask: int):
         gids = np.ascontiguousarray(gids, dtype=np.uint32)
         self.L.check(self.L.fn("clear_group_flags")(self._h, C.c_uint32(lane), C.c_uint32(len(gids)), _ptr(gids), C.c_uint32(mask)))
+
+    def log_gather(self, lane: int, positions, lengths) -> list:
+        """The byte ranges [pos, pos + len) of `lane`'s log ring (request bodies of gpx_log_find hits / carried-over
+        pvalues) in one call and one device->host copy (gpx_log_gather).  -> list of bytes."""
+        n = len(positions)
+        if n == 0:
+            return []
+        r = np.zeros(n, dtype=log_range_dtype)
+        r["pos"], r["len"] = positions, lengths
+        padded = (r["len"].astype(np.uint64) + 15) // 16 * 16
+        offs = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.uint64)
+        r["dst_off"] = offs
+        total = int(padded.sum())
+        buf = np.zeros(max(total, 16), dtype=np.uint8)
+        self.L.check(self.L.fn("log_gather")(self._h, C.c_uint32(lane), C.c_uint32(n), _ptr(r), _ptr(buf), C.c_uint64(total)))
+        return [bytes(buf[int(o): int(o) + int(l)]) for o, l in zip(offs, r["len"])]
 
     def pause_groups(self, gids):
         """The deactivation sweep (gpx_pause_groups): -> (rows [n, n_lanes] of gpx_row, paused [n] bool).  Rows of groups

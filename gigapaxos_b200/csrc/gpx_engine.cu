@@ -1499,6 +1499,53 @@ int gpx_log_find(gpx_engine* e, uint32_t lane, uint64_t from, uint32_t n, const 
   return GPX_OK;
 }
 
+/* the bodies of a batch of hits in one copy: k_log_gather (gpx_logfind.cuh) packs them into a staging buffer */
+int gpx_log_gather(gpx_engine* e, uint32_t lane, uint32_t n, const gpx_log_range* ranges, void* dst, uint64_t dst_bytes) {
+  if (!e) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  if (n == 0) return GPX_OK;
+  if (!ranges || !dst) return fail(GPX_EINVAL, "null argument");
+  CK(cudaDeviceSynchronize());
+  unsigned long long lp[2 * GPX_MAX_LANES];
+  CK(cudaMemcpy(lp, e->S.log_pos + (size_t)e->S.lp * 2 * GPX_MAX_LANES, sizeof lp, cudaMemcpyDeviceToHost));
+  const uint64_t head = lp[2 * lane], cap = e->S.ring_cap;
+  std::vector<uint32_t> first(n + 1);
+  uint64_t chunks = 0, top = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t nc = ((uint64_t)ranges[i].len + 15) >> 4;
+    if ((ranges[i].pos & 15) || (ranges[i].dst_off & 15)) return fail(GPX_EINVAL, "range not on a 16-byte boundary");
+    if (ranges[i].pos + 16 * nc > head || head - ranges[i].pos > cap) return fail(GPX_ERANGE, "range outside the live ring bytes");
+    if ((ranges[i].pos & (cap - 1)) + 16 * nc > cap) return fail(GPX_ERANGE, "range straddles the ring end");
+    if ((uint64_t)ranges[i].dst_off + 16 * nc > dst_bytes) return fail(GPX_ERANGE, "range beyond dst");
+    first[i] = (uint32_t)chunks;
+    chunks += nc;
+    top = std::max<uint64_t>(top, (uint64_t)ranges[i].dst_off + 16 * nc);
+    if (chunks > 0xffffffffull) return fail(GPX_ERANGE, "too many bytes for one gather");
+  }
+  first[n] = (uint32_t)chunks;
+  if (chunks == 0) return GPX_OK;
+  const size_t r_bytes = ((size_t)n * sizeof(gpx_log_range) + 15) & ~(size_t)15;
+  const size_t f_bytes = ((size_t)(n + 1) * 4 + 15) & ~(size_t)15;
+  int rc = e->ensure_misc(r_bytes + f_bytes + top);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  uint8_t* base = (uint8_t*)e->d_misc;
+  CK(cudaMemcpyAsync(base, ranges, (size_t)n * sizeof(gpx_log_range), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(base + r_bytes, first.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+  LogGatherArgs A;
+  A.lane = lane;
+  A.n = n;
+  A.ranges = (const gpx_log_range*)base;
+  A.first_chunk = (const uint32_t*)(base + r_bytes);
+  A.out = (int4*)(base + r_bytes + f_bytes);
+  CK(cudaMemsetAsync(A.out, 0, top, st)); /* gaps between ranges read as zero */
+  k_log_gather<<<cdiv(chunks, GPX_LOGF_BLOCK), GPX_LOGF_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, A.out, top, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GPX_OK;
+}
+
 /* Asynchronous drain (SQLPaxosLogger.journal :965-1036 appends the batch to the journal file; here the caller's
  * page-locked buffer stands for the file's write buffer).  Everything is enqueued: the copy runs on the engine's
  * drain stream behind the work already enqueued on `after_stream` (NULL = the engine's stream) and overlaps later

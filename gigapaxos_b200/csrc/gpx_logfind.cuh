@@ -170,3 +170,29 @@ __global__ void __launch_bounds__(GPX_LOGF_BLOCK) k_log_hits(const __grid_consta
   }
   A.hits[t] = hit;
 }
+
+/* ---- k_log_gather: the request bodies of a batch of hits, packed for one device->host copy (gpx_log_gather) ------------
+ * One thread per 16-byte chunk: chunk c belongs to the range r with first_chunk[r] <= c (binary search; the host lays the
+ * ranges out back to back in chunks), is read from the ring at the range's position (blobs start on 16-byte boundaries
+ * of a payload area padded to 16) and written to the staging buffer at the range's offset. */
+struct LogGatherArgs {
+  uint32_t lane, n;
+  const gpx_log_range* ranges;
+  const uint32_t* first_chunk; /* [n + 1] */
+  int4* out;                   /* staging, indexed by dst_off / 16 */
+};
+
+__global__ void __launch_bounds__(GPX_LOGF_BLOCK) k_log_gather(const __grid_constant__ DevState S,
+                                                               const __grid_constant__ LogGatherArgs A) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= A.first_chunk[A.n]) return;
+  uint32_t lo = 0, hi = A.n; /* the last range whose first chunk is <= c (empty ranges share a chunk index) */
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (A.first_chunk[mid] <= c) lo = mid;
+    else hi = mid;
+  }
+  const gpx_log_range r = A.ranges[lo];
+  const uint32_t k = c - A.first_chunk[lo];
+  A.out[(r.dst_off >> 4) + k] = *reinterpret_cast<const int4*>(ring_ptr(S, A.lane, r.pos + 16ull * k));
+}

@@ -88,6 +88,8 @@ public final class PaxosEngine implements AutoCloseable {
 	/** copiedAndHead = {bytes copied, ring head} */
 	/** getLoggedDecisions / getLoggedAccepts for n (gid, minSlot, nSlots <= 16) wants sorted by gid: hitsOut n x 16 x 96 B */
 	public static native int logFind(long h, int lane, long from, int n, ByteBuffer wants, ByteBuffer hitsOut);
+	/** the request bodies of n ranges {long pos, int len, int dstOff} of a lane's log ring into dst, one copy */
+	public static native int logGather(long h, int lane, int n, ByteBuffer ranges, ByteBuffer dst);
 	public static native int logRead(long h, int lane, long from, ByteBuffer dst, long[] copiedAndHead);
 
 	// ---- replicas of a group on different GPUs: one engine (a single lane) per GPU process ----

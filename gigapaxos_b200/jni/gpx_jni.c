@@ -175,6 +175,13 @@ JNIEXPORT jint JNICALL GPX_JNI(logFind)(JNIEnv* env, jclass cls, jlong h, jint l
   return gpx_log_find((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint64_t)from, (uint32_t)n, (const gpx_log_want*)buf(env, wants),
                       (gpx_log_hit*)buf(env, hits_out));
 }
+/* int logGather(long h, int lane, int n, ByteBuffer ranges [n x 16 B: pos, len, dstOff], ByteBuffer dst): the request
+ * bodies of a batch of logFind hits in one device->host copy */
+JNIEXPORT jint JNICALL GPX_JNI(logGather)(JNIEnv* env, jclass cls, jlong h, jint lane, jint n, jobject ranges, jobject dst) {
+  jlong cap = dst ? (*env)->GetDirectBufferCapacity(env, dst) : 0;
+  return gpx_log_gather((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint32_t)n, (const gpx_log_range*)buf(env, ranges), buf(env, dst),
+                        (uint64_t)cap);
+}
 /* long logRead(long h, int lane, long from, ByteBuffer dst, long[] out {nCopied, head}): the synchronous journal read
  * (recovery / tests); the steady state uses logDrainAsync */
 JNIEXPORT jint JNICALL GPX_JNI(logRead)(JNIEnv* env, jclass cls, jlong h, jint lane, jlong from, jobject dst, jlongArray out) {

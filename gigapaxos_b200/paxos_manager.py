@@ -375,6 +375,20 @@ class PaxosManager:
                 res[names[i]] = int(o["verdict"]) == abi.EL_MAJORITY
                 if res[names[i]] and int(o["n_plan"]):
                     plans[names[i]] = o["plan"][: int(o["n_plan"])]
+            # the request bodies of every carried-over pvalue, one gpx_log_gather per acceptor lane that holds some
+            # (reply record index i * L + l: the acceptor at lane l reported the pvalue and has its body in its ring)
+            body_of = {}
+            if eng.L.has("log_gather"):
+                per_lane: Dict[int, list] = {}
+                for n, plan in plans.items():
+                    for j, c in enumerate(plan):
+                        if int(c["kind"]) == abi.CO_PVALUE and int(c["pv"]["payload_len"]):
+                            per_lane.setdefault(int(c["src_reply"]) % L, []).append((n, j, c["pv"]))
+                for l, items in per_lane.items():
+                    got = eng.log_gather(l, [int(pv["frame_ref"]) * 16 for _, _, pv in items],
+                                         [int(pv["payload_len"]) for _, _, pv in items])
+                    for (n, j, _), b in zip(items, got):
+                        body_of[(n, j)] = b
             for j in range(max((len(p) for p in plans.values()), default=0)):
                 reqs: List[RequestPacket] = []
                 for n in sorted(plans, key=lambda x: self.instances[x].gid):
@@ -385,7 +399,9 @@ class PaxosManager:
                         reqs.append(RequestPacket(n, 0, NO_OP, entry_replica=me))
                     elif int(c["kind"]) == abi.CO_STOP_NEW:
                         reqs.append(RequestPacket(n, 0, b"STOP", stop=True, entry_replica=me))  # PCS :541
-                    else:  # reply record index i * L + l: the acceptor at lane l holds the body
+                    elif (n, j) in body_of or not int(c["pv"]["payload_len"]):
+                        reqs.extend(self._requests_from_blob(n, c["pv"], body_of.get((n, j), b""), me))
+                    else:
                         reqs.extend(self._requests_of(n, c["pv"], int(c["src_reply"]) % L, me))
                 self._submit(reqs, carryover=True)
         for i in range(len(names)):
@@ -629,14 +645,21 @@ class PaxosManager:
             while _jsub(sl, hi) < 0:
                 w = np.zeros(1, dtype=abi.log_want_dtype)
                 w["gid"], w["min_slot"], w["n_slots"] = gid, sl, min(abi.GPX_LOG_SPAN, _jsub(hi, sl))
+                good = []
                 for h in eng.log_find(donor, w)[0][: int(w["n_slots"][0])]:
                     d, a = h["decision"], h["accept"]
                     if int(d["flags"]) & abi.F_VOID or int(a["flags"]) & abi.F_VOID:
                         continue
                     if (_jsub(int(a["bnum"]), int(d["bnum"])) or _jsub(int(a["bcoord"]), int(d["bcoord"]))) < 0:
                         continue  # the accept on record is older than the decision: no body for it here
-                    n = int(a["payload_len"])
-                    body = bytes(eng.log_read(donor, int(h["blob_pos"]), n)) if n else b""
+                    good.append(h)
+                if eng.L.has("log_gather"):  # all bodies of the chunk in one device->host copy
+                    bodies = eng.log_gather(donor, [int(h["blob_pos"]) for h in good], [int(h["accept"]["payload_len"]) for h in good])
+                else:
+                    bodies = [bytes(eng.log_read(donor, int(h["blob_pos"]), int(h["accept"]["payload_len"])))
+                              if int(h["accept"]["payload_len"]) else b"" for h in good]
+                for h, body in zip(good, bodies):
+                    d, a = h["decision"], h["accept"]
                     decisions[int(d["slot"])] = d.copy()
                     accepts[(int(d["slot"]), int(d["bnum"]), int(d["bcoord"]))] = (a.copy(), body)
                 sl = _jadd(sl, abi.GPX_LOG_SPAN)

@@ -588,6 +588,17 @@ typedef struct gpx_log_hit { /* 96 B */
 } gpx_log_hit;
 int gpx_log_find(gpx_engine* e, uint32_t lane, uint64_t from, uint32_t n, const gpx_log_want* wants, gpx_log_hit* out);
 
+/* Request bodies for a batch of gpx_log_find hits (or of carried-over pvalues: position = frame_ref * 16) in ONE
+ * device->host copy: ranges[i] = {ring position, length, offset in dst (a multiple of 16)}; range i lands at
+ * dst + dst_off rounded up to whole 16-byte chunks (the ring's payload areas are padded to 16).  The journal analogue is
+ * SQLPaxosLogger.getJournaledMessage(FileOffsetLength[]) :3712, which reads the indexed frames back in one pass. */
+typedef struct gpx_log_range { /* 16 B */
+  uint64_t pos;
+  uint32_t len;
+  uint32_t dst_off;
+} gpx_log_range;
+int gpx_log_gather(gpx_engine* e, uint32_t lane, uint32_t n, const gpx_log_range* ranges, void* dst, uint64_t dst_bytes);
+
 /* ---- introspection ---------------------------------------------------------------- */
 int gpx_get_counters(gpx_engine* e, gpx_counters* out);
 int gpx_reset_counters(gpx_engine* e);

@@ -1805,6 +1805,23 @@ int gpxo_log_find(gpxo_engine* e, uint32_t lane, uint64_t from, uint32_t n, cons
   return GPX_OK;
 }
 
+/* SQLPaxosLogger.getJournaledMessage(FileOffsetLength[]) :3712: the indexed frames read back in one pass */
+int gpxo_log_gather(gpxo_engine* e, uint32_t lane, uint32_t n, const gpx_log_range* ranges, void* dst, uint64_t dst_bytes) {
+  if (!e || (n && (!ranges || !dst))) return GPX_EINVAL;
+  if (lane >= e->L()) return GPX_ERANGE;
+  const std::vector<uint8_t>& r = e->lanes[lane].ring;
+  u64 top = 0;
+  for (u32 i = 0; i < n; i++) {
+    const u64 nb = (((u64)ranges[i].len + 15) >> 4) << 4;
+    if ((ranges[i].pos & 15) || (ranges[i].dst_off & 15)) return GPX_EINVAL;
+    if (ranges[i].pos + nb > r.size() || (u64)ranges[i].dst_off + nb > dst_bytes) return GPX_ERANGE;
+    top = std::max<u64>(top, (u64)ranges[i].dst_off + nb);
+  }
+  memset(dst, 0, top);
+  for (u32 i = 0; i < n; i++) memcpy((uint8_t*)dst + ranges[i].dst_off, &r[ranges[i].pos], (((u64)ranges[i].len + 15) >> 4) << 4);
+  return GPX_OK;
+}
+
 /* drop the in-memory log (a drained / garbage-collected journal); used by long CPU-baseline runs */
 int gpxo_log_truncate(gpxo_engine* e) {
   for (auto& ln : e->lanes) {

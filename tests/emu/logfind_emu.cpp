@@ -44,3 +44,21 @@ extern "C" int emu_log_find(uint8_t* ring, uint64_t ring_cap, uint64_t head, uin
   for (int i = 0; i < 4; i++) ctl_out[i] = ctl[i];
   return (int)ctr[C_KERNEL_LAUNCHES];
 }
+
+extern "C" int emu_log_gather(uint8_t* ring, uint64_t ring_cap, uint32_t lane, uint32_t n, const gpx_log_range* ranges,
+                              const uint32_t* first_chunk, uint8_t* out, uint32_t block) {
+  if (lane >= GPX_MAX_LANES || (ring_cap & (ring_cap - 1)) || block == 0) return -1;
+  DevState S;
+  memset(&S, 0, sizeof S);
+  S.L = lane + 1;
+  S.ring[lane] = ring;
+  S.ring_cap = ring_cap;
+  LogGatherArgs A;
+  A.lane = lane;
+  A.n = n;
+  A.ranges = ranges;
+  A.first_chunk = first_chunk;
+  A.out = reinterpret_cast<int4*>(out);
+  emu_launch(k_log_gather, (first_chunk[n] + block - 1) / block + 1, block, S, A);
+  return 0;
+}

@@ -267,3 +267,45 @@ def test_a_header_with_absurd_sizes_is_not_followed(emu_lib):
         ring[:64].view(abi.seg_hdr_dtype)[0]["payload_bytes"] = pb
         got, ctl = emu_find(emu_lib, ring, cap, 2048, 0, 0, wants)
         assert int(ctl[2]) == 2 and np.all(got["decision"]["flags"] == abi.F_VOID)
+
+
+# ---- gpx_log_gather: the bodies of a batch of hits in one copy ---------------------------------------------------------------
+def test_log_gather_oracle_and_kernel_source(oracle_lib, emu_lib):
+    G = 40
+    eng, heads = logged_engine(oracle_lib, G, 9)
+    w = np.zeros(G, dtype=abi.log_want_dtype)
+    w["gid"], w["min_slot"], w["n_slots"] = np.arange(G), 1, 16
+    for lane in range(3):
+        h = eng.log_find(lane, w).reshape(-1)
+        h = h[(h["accept"]["flags"] & abi.F_VOID) == 0]
+        assert len(h) > 100
+        pos, ln = h["blob_pos"].astype(np.uint64), h["accept"]["payload_len"]
+        ln = ln.copy()
+        ln[::7] = 0  # some empty ranges in between
+        got = eng.log_gather(lane, pos, ln)
+        want = [bytes(eng.log_read(lane, int(p), int(n))) if n else b"" for p, n in zip(pos, ln)]
+        assert got == want and sum(len(b) for b in got) > 1000
+        # the kernel's source on the ring image (re-laid into a ring that wraps: positions modulo the ring size)
+        buf = eng.log_read(lane)
+        head = len(buf)
+        cap = 1 << int(np.ceil(np.log2(head + 64)))
+        ring = np.zeros(cap, dtype=np.uint8)
+        ring[:head] = buf
+        r = np.zeros(len(pos), dtype=abi.log_range_dtype)
+        r["pos"], r["len"] = pos, ln
+        padded = (ln.astype(np.uint64) + 15) // 16 * 16
+        r["dst_off"] = np.concatenate([[0], np.cumsum(padded)[:-1]])
+        first = np.concatenate([[0], np.cumsum(padded // 16)]).astype(np.uint32)
+        out = np.full(int(padded.sum()) + 64, 0xEE, dtype=np.uint8)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        for block in (1, 64, 256):
+            out[:] = 0xEE
+            assert emu_lib.emu_log_gather(ptr(ring), C.c_uint64(cap), lane, len(r), ptr(r), ptr(first), ptr(out), block) == 0
+            for o, n, b in zip(r["dst_off"], ln, want):
+                assert bytes(out[int(o): int(o) + int(n)]) == b
+            assert np.all(out[int(padded.sum()):] == 0xEE)  # nothing written past the last chunk
+    with pytest.raises(abi.GpxError):
+        eng.log_gather(0, [8], [4])  # not on a 16-byte boundary
+    with pytest.raises(abi.GpxError):
+        eng.log_gather(0, [eng.log_head(0)], [64])  # beyond the head
+    assert eng.log_gather(0, [], []) == []
