@@ -1,10 +1,19 @@
-"""Phase 1b on the device (k_prepare_tally behind gpx_handle_prepare_replies) against the oracle, through the C ABI:
-random batches of elections (every verdict, GPX_F_MORE continuation records, slots across the int wrap, R = 1..5) --
-the 896-byte result records byte for byte and every row of every lane afterwards -- and whole view changes of the host
-mirror with the tally inside the engine.  (The same kernel source also runs on the host in tests/test_phase1b.py.)
+"""The kernels beside the round that were written after this round's GPU minutes were spent, against the oracle through
+the C ABI -- PaxosManager's per-instance sweeps as launches:
 
-The file sorts last on purpose: k_prepare_tally was written after the round's GPU minutes were spent, so its first run
-on a B200 is the driver's; nothing else depends on it."""
+  k_prepare_tally (gpx_handle_prepare_replies)   phase 1b: random batches of elections (every verdict, GPX_F_MORE
+      continuation records, slots across the int wrap, R = 1..5, nodes of a spread placement) -- the 896-byte result
+      records byte for byte and every row of every lane afterwards; 20,000 elections in one launch; whole view changes
+      and the mass fail-over of the host mirror with the tally inside the engine;
+  k_pause_groups / k_select_groups / k_clear_flags (gpx_pause_groups, gpx_select_groups, gpx_clear_group_flags)   the
+      deactivation sweep and the slow-path list;
+  k_log_dir / k_log_scan / k_log_hits / k_log_gather (gpx_log_find, gpx_log_gather)   the journal's index as a scan of the
+      log ring, incl. a ring that wrapped; the mirror's catch-up and a lagging preparer's logged accepts through it.
+
+The same kernel sources also run on the host (tests/emu: test_phase1b.py, test_pause_batch.py, test_log_find.py).  The
+file sorts last on purpose: of these kernels only k_prepare_tally has met a B200 (its two R = 3 cases, with the round's
+last GPU seconds: profiles/r2l_phase1b_gpu_first_run.txt); for the rest the driver's round-end pass is the first run, and
+nothing else depends on them."""
 import numpy as np
 import pytest
 
