@@ -19,6 +19,10 @@ the phase-2 path produces besides the DECISION / PREPARE forms of journal.py:
                                 records (continued with GPX_F_MORE past GPX_MAX_WINDOW pvalues, the analogue of
                                 PrepareReplyPacket.fragment :231-258) + the request bodies in a payload arena -- the
                                 input of gpx_handle_prepare_replies.
+  SYNC_DECISIONS (32)           a replica asks for the decisions it missed (SyncDecisionsPacket.toJSONObjectImpl :79-88); the
+                                answer is the missing DECISIONs as full PValuePackets.  serve_sync_request looks them up
+                                with gpx_log_find + gpx_log_gather at the donor (PISM.handleSyncDecisionsPacket :2426-2510,
+                                getActualDecisions :2539-2583); decisions_to_records makes them replayable at the requester.
   BATCHED_PAXOS_PACKET (37)     PaxosPacketBatcher.batch :280-303: the messaging tasks of one batcher sweep grouped by
                                 recipient set (first-seen order: LinkedHashMap), each group's packets in one
                                 {"PP": [...]} wrapper; BatchedPaxosPacket.toJSONObjectImpl :77-84.  process() :270-277 does
@@ -33,7 +37,7 @@ import json
 from typing import Dict, Iterable, List, Sequence, Tuple, Union
 
 PT_REQUEST, PT_PREPARE, PT_ACCEPT, PT_DECISION, PT_PREPARE_REPLY, PT_ACCEPT_REPLY = 1, 2, 3, 6, 7, 8
-PT_BATCHED_ACCEPT, PT_BATCHED_PAXOS_PACKET, PT_PAXOS_PACKET = 36, 37, 90  # PaxosPacket.PaxosPacketType :202-291
+PT_SYNC_DECISIONS, PT_BATCHED_ACCEPT, PT_BATCHED_PAXOS_PACKET, PT_PAXOS_PACKET = 32, 36, 37, 90  # PaxosPacketType :202-291
 CHARSET = "iso-8859-1"  # PaxosPacket.CHARSET :439, BatchedAccept.CHARSET :36
 
 BATCH_ACROSS_GROUPS = True  # PaxosConfig.java:807
@@ -309,6 +313,82 @@ def prepare_reply_to_records(pkt: Packet, gid: int, members: Sequence[int], prep
     return recs, bytes(arena)
 
 
+# ---- SYNC_DECISIONS and the decisions that answer it ----------------------------------------------------------------
+def sync_decisions_json(paxos_id: str, version: int, node: int, max_decision_slot: int, missing: Sequence[int]) -> bytes:
+    """SyncDecisionsPacket.toJSONObjectImpl :79-88"""
+    d = _base(PT_SYNC_DECISIONS, paxos_id, version)
+    d.update({"SNDR": int(node), "MAX_S": int(max_decision_slot)})
+    if missing:
+        d["MISS"] = [int(x) for x in missing]
+    return _dumps(d)
+
+
+def serve_sync_request(engine, lane: int, gid: int, pkt: Packet, max_committed_slot: int) -> List[bytes]:
+    """PISM.handleSyncDecisionsPacket :2426-2510 at the donor `lane` of `engine`: the logged decisions from the first
+    missing slot up to maxDecisionSlot -- or, when the requester knows of none (maxDecisionSlot <= minMissingSlot), up to
+    what this replica has committed (:2470-2483) -- each with the request body of the logged accept of its slot
+    (getActualDecisions :2539-2583), as DECISION packets.  The journal is looked up by gpx_log_find, the bodies come
+    back in one gpx_log_gather."""
+    import numpy as np
+    from . import abi
+    j = pkt if isinstance(pkt, dict) else _loads(pkt)
+    assert j["type"] == PT_PAXOS_PACKET and j["PT"] == PT_SYNC_DECISIONS
+    missing = [int(x) for x in j.get("MISS", [])]
+    if not missing:
+        return []
+    lo = missing[0]
+    hi = int(j["MAX_S"]) if _i32(int(j["MAX_S"]) - lo) > 0 else max(lo + 1, int(max_committed_slot) + 1)
+    filt = set(missing) if _i32(int(j["MAX_S"]) - lo) > 0 else None  # :2485-2494: only the slots reported missing
+    hits = []
+    sl = lo
+    while _i32(hi - sl) > 0:
+        w = np.zeros(1, dtype=abi.log_want_dtype)
+        w["gid"], w["min_slot"], w["n_slots"] = gid, sl, min(abi.GPX_LOG_SPAN, _i32(hi - sl))
+        for h in engine.log_find(lane, w)[0][: int(w["n_slots"][0])]:
+            d, a = h["decision"], h["accept"]
+            if int(d["flags"]) & abi.F_VOID or int(a["flags"]) & abi.F_VOID:
+                continue  # "has no body for executed meta-decision" :2570: left out
+            if filt is not None and int(d["slot"]) not in filt:
+                continue
+            hits.append(h.copy())
+        sl = _i32(sl + abi.GPX_LOG_SPAN)
+    bodies = engine.log_gather(lane, [int(h["blob_pos"]) for h in hits], [int(h["accept"]["payload_len"]) for h in hits])
+    out = []
+    for h, body in zip(hits, bodies):
+        d, a = h["decision"], h["accept"]
+        pv = np.zeros((), dtype=abi.accepted_pvalue_dtype)
+        pv["slot"], pv["bnum"], pv["bcoord"], pv["req_id"] = int(a["slot"]), int(a["bnum"]), int(a["bcoord"]), int(a["req_id"])
+        pv["payload_len"] = int(a["payload_len"])
+        pv["flags"] = (2 if int(a["flags"]) & abi.F_STOP else 0) | (int(a["nreq"]) << 16)
+        obj = accepted_pvalue_obj(j["ID"], j["V"], pv, body, pt=PT_DECISION)
+        obj["GC_S"] = max(int(d["median_cp"]), -1)  # pvalue.makeDecision(getMedianCheckpointedSlot()) :2561
+        out.append(_dumps(obj))
+    return out
+
+
+def decisions_to_records(pkts: Sequence[Packet], gid: int, lane: int):
+    """DECISION packets with values (a sync reply) -> what replays them at `lane`: (accept records, blob arena, decision
+    records), slot order -- the ACCEPT carries the value into the acceptor's window, the DECISION commits it
+    (PISM.handleCommittedRequest :1432)."""
+    import numpy as np
+    from . import abi
+    objs = sorted((p if isinstance(p, dict) else _loads(p) for p in pkts), key=lambda o: _i32(int(o["S"])))
+    acc = np.zeros(len(objs), dtype=abi.accept_dtype)
+    dec = np.zeros(len(objs), dtype=abi.decision_dtype)
+    arena = bytearray()
+    for k, o in enumerate(objs):
+        assert o["PT"] == PT_DECISION
+        rid, blob, nreq, stop = _pvalue_blob(o)
+        bn, bc = (int(x) for x in o["B"].split(":"))
+        for r in (acc[k], dec[k]):
+            r["gid"], r["slot"], r["bnum"], r["bcoord"], r["req_id"], r["dst_mask"] = gid, int(o["S"]), bn, bc, rid, 1 << lane
+        acc[k]["median_cp"], acc[k]["flags"] = -1, abi.F_ACCEPT | (abi.F_STOP if stop else 0)
+        acc[k]["payload_off"], acc[k]["payload_len"], acc[k]["nreq"], acc[k]["sender"] = len(arena), len(blob), nreq, bc
+        dec[k]["median_cp"], dec[k]["flags"] = int(o["GC_S"]), abi.F_DECISION | (abi.F_STOP if stop else 0)
+        arena += blob + bytes(-len(blob) % 16)
+    return acc, np.frombuffer(bytes(arena), dtype=np.uint8), dec
+
+
 # ---- BATCHED_PAXOS_PACKET ------------------------------------------------------------------------------------------
 Packet = Union[bytes, dict]
 """a packet on its way out: byteified (bytes not starting with '{'), a JSON string (bytes starting with '{') or a dict"""
@@ -382,6 +462,9 @@ def parse_packet(pkt: bytes) -> dict:
         return {"kind": "BATCHED_ACCEPT", "paxos_id": b.paxos_id, "version": b.version, "bnum": b.bnum, "bcoord": b.bcoord,
                 "median_cp": b.median_cp, "group": b.group, "slot_digests": dict(b.slot_digests),
                 "slot_request_ids": dict(b.slot_request_ids)}
+    if pt == PT_SYNC_DECISIONS:
+        return {"kind": "SYNC_DECISIONS", "paxos_id": j["ID"], "version": j["V"], "node": j["SNDR"],
+                "max_decision_slot": j["MAX_S"], "missing": [int(x) for x in j.get("MISS", [])]}
     if pt == PT_PREPARE_REPLY:
         bn, bc = (int(x) for x in j["B"].split(":"))
         return {"kind": "PREPARE_REPLY", "paxos_id": j["ID"], "version": j["V"], "acceptor": j["ACCPTR"], "bnum": bn,

@@ -219,3 +219,13 @@ def test_prepare_reply_longer_than_the_window_is_continued():
     assert [int(r["first_slot"]) for r in recs] == [19, 19] and len(arena) == 11 * 16
     assert pj.parse_packet(pj.prepare_packet_json("p", 0, 2, 102, 20)) == {
         "kind": "PREPARE", "paxos_id": "p", "version": 0, "bnum": 2, "bcoord": 102, "first_undecided_slot": 20}
+
+
+def test_sync_decisions_packet():
+    from gigapaxos_b200 import packets_json as pj
+    import json
+    p = pj.sync_decisions_json("paxos0", 2, 101, 17, [12, 13, 15])
+    assert json.loads(p) == {"type": 90, "PT": 32, "ID": "paxos0", "V": 2, "SNDR": 101, "MAX_S": 17, "MISS": [12, 13, 15]}
+    assert pj.parse_packet(p) == {"kind": "SYNC_DECISIONS", "paxos_id": "paxos0", "version": 2, "node": 101,
+                                  "max_decision_slot": 17, "missing": [12, 13, 15]}
+    assert "MISS" not in json.loads(pj.sync_decisions_json("p", 0, 1, 3, []))  # SyncDecisionsPacket.toJSONObjectImpl :84-86

@@ -160,3 +160,122 @@ def test_view_change_between_nodes_over_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+# ---- catching up between nodes: SYNC_DECISIONS -> the donor's journal (gpx_log_find + gpx_log_gather) -> DECISIONs back ---
+def sync_history(seed=8, rounds=11):
+    """11 slots decided by nodes 100 and 101 while node 102 is cut off: -> (3-lane reference engine after them,
+    [(accept records, blob, decision records)] per round)"""
+    from helpers import Engine, abi, group_descs, make_config, make_requests, oracle_library
+    lib = oracle_library()
+    ref = Engine(lib, make_config(lib, max_groups=G, max_batch_recs=4096, max_batch_payload=1 << 20, checkpoint_interval=100))
+    ref.create_groups(group_descs(G, members=tuple(NODES)))
+    gids = np.arange(G, dtype=np.uint32)
+    rows0 = ref.dump_rows(gids, 0)
+    coord = np.array([NODES.index(int(x)) for x in rows0["acc_bcoord"]])
+    ok = coord != 2  # groups node 102 coordinates cannot progress without it: leave them alone
+    g2 = gids[ok]
+    out = []
+    for k in range(rounds):
+        per = np.where(np.arange(len(g2)) % 5 == k % 5, 2, 1)
+        gg = np.repeat(g2, per)
+        reqs, pay = make_requests(gg, payload_len=5 + k % 6, seed=seed, round_no=k)
+        reqs["flags"] = coord[gg] << 8
+        reqs["entry_node"] = np.array(NODES)[coord[gg]]
+        acc, blob, st = ref.propose(reqs, pay)
+        acc["dst_mask"] = 0b011
+        rep, _ = ref.handle_accepts(acc, blob)
+        dec = ref.handle_accept_replies(rep)
+        assert len(dec) == len(g2)
+        dec["dst_mask"] = 0b011
+        ref.handle_decisions(dec)
+        out.append((acc.copy(), blob.copy(), dec.copy()))
+    return ref, out, g2
+
+
+def sync_worker(rank, world, port, q):
+    try:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from gigapaxos_b200 import abi, packets_json as pj
+        from helpers import Engine, group_descs, make_config, oracle_library
+        lib = oracle_library()
+        me = NODES[rank]
+        eng = Engine(lib, make_config(lib, n_lanes=1, lane_node=[me], max_group_size=R, max_groups=G, max_batch_recs=4096,
+                                      max_batch_payload=1 << 20, checkpoint_interval=100))
+        eng.create_groups(group_descs(G, members=tuple(NODES)))
+        ref, hist, g2 = sync_history()
+        executed = 0
+        if rank != 2:  # nodes 100 and 101 accept and commit; 102 hears nothing
+            for acc, blob, dec in hist:
+                a, d = acc.copy(), dec.copy()
+                a["dst_mask"], d["dst_mask"] = 1, 1
+                eng.handle_accepts(a, blob)
+                ex, extra = eng.handle_decisions(d)
+                executed += int(((ex["flags"] & abi.F_VOID) == 0).sum()) + len(extra)
+            assert executed == len(hist) * len(g2)
+        names = {int(g): f"NoopPaxosApp{int(g)}" for g in g2}
+        donor, lagging = 0, 2
+        # ---- SYNC_DECISIONS: 102 -> 100, one packet per group (it knows of no decision: MISS = [its slot])
+        if rank == lagging:
+            rows = eng.dump_rows(g2, 0)
+            reqs = [pj.sync_decisions_json(names[int(g)], 0, me, int(rows[i]["acc_slot"]) - 1, [int(rows[i]["acc_slot"])])
+                    for i, g in enumerate(g2)]
+        else:
+            reqs = None
+        box = [reqs]
+        dist.broadcast_object_list(box, src=lagging)
+        # ---- the donor looks its journal up (gpx_log_find + gpx_log_gather) and answers with DECISIONs
+        if rank == donor:
+            rows = eng.dump_rows(g2, 0)
+            assert pj.parse_packet(box[0][0])["kind"] == "SYNC_DECISIONS"
+            answer = [pj.serve_sync_request(eng, 0, int(g), box[0][i], int(rows[i]["acc_slot"]) - 1) for i, g in enumerate(g2)]
+            assert all(len(a) == len(hist) for a in answer)
+        else:
+            answer = None
+        box = [answer]
+        dist.broadcast_object_list(box, src=donor)
+        if rank == lagging:  # replay, W slots at a time: accept (the value), then commit
+            W = int(eng.cfg.window)
+            got_exec = 0
+            for i, g in enumerate(g2):
+                acc, blob, dec = pj.decisions_to_records(box[0][i], int(g), 0)
+                for s in range(0, len(acc), W):
+                    a = acc[s: s + W].copy()
+                    lo = int(a["payload_off"].min())
+                    hi = int((a["payload_off"] + (a["payload_len"] + 15) // 16 * 16).max())
+                    a["payload_off"] -= lo
+                    eng.handle_accepts(a, blob[lo:hi])
+                    ex, extra = eng.handle_decisions(dec[s: s + W])
+                    got_exec += int(((ex["flags"] & abi.F_VOID) == 0).sum()) + len(extra)
+            assert got_exec == len(hist) * len(g2)
+            mine, theirs = eng.dump_rows(g2, 0), ref.dump_rows(g2, 0)
+            for f in ("acc_slot", "acc_bnum", "acc_bcoord"):
+                assert np.array_equal(mine[f], theirs[f]), f
+            # what was executed here is what the other nodes executed: the same request ids slot by slot
+            w = np.zeros(len(g2), dtype=abi.log_want_dtype)
+            w["gid"], w["min_slot"], w["n_slots"] = np.sort(g2), int(theirs["acc_slot"].min()) - len(hist), len(hist)
+            a, b = eng.log_find(0, w), ref.log_find(0, w)
+            assert np.array_equal(a["decision"]["req_id"], b["decision"]["req_id"])
+            assert ((b["decision"]["flags"] & abi.F_VOID) == 0).sum() == len(hist) * len(g2)
+        dist.barrier()
+        q.put((rank, "ok"))
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc()))
+        raise
+
+
+def test_sync_between_nodes_over_gloo():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
