@@ -72,6 +72,9 @@ log_want_dtype = np.dtype([("gid", "<u4"), ("min_slot", "<i4"), ("n_slots", "<u4
 log_hit_dtype = np.dtype([("decision", decision_dtype), ("accept", accept_dtype), ("blob_pos", "<u8"), ("reserved", "<u8")])
 assert log_want_dtype.itemsize == 16 and log_hit_dtype.itemsize == 96
 log_range_dtype = np.dtype([("pos", "<u8"), ("len", "<u4"), ("dst_off", "<u4")])
+missing_dtype = np.dtype([("gid", "<u4"), ("slot", "<i4"), ("max_decision_slot", "<i4"), ("n_missing", "<u2"),
+                          ("missing_too_much", "u1"), ("flags", "u1"), ("missing", "<i4", (GPX_MAX_WINDOW,))])
+assert missing_dtype.itemsize == 48
 exec_sum_dtype = np.dtype([("slot", "<i4"), ("lane_mask", "u1"), ("flags", "u1"), ("nreq", "<u2")])
 ROUND_COMPACT = 1
 ROUND_PACKED_REQS = 2
@@ -295,6 +298,14 @@ class Engine:
         if n.value > cap:
             raise GpxError(GPX_ERANGE, f"{n.value} groups match, buffer holds {cap}")
         return out[: n.value].copy()
+
+    def missing_decisions(self, lane: int, gids, size_limit: int = 400, too_much_gap: int = 400) -> np.ndarray:
+        """The fields of a SYNC_DECISIONS_REQUEST per group (gpx_missing_decisions): PISM.requestMissingDecisions :2292."""
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        out = np.zeros(max(len(gids), 1), dtype=missing_dtype)
+        self.L.check(self.L.fn("missing_decisions")(self._h, C.c_uint32(lane), C.c_uint32(len(gids)), _ptr(gids),
+                                                    C.c_int32(size_limit), C.c_int32(too_much_gap), _ptr(out)))
+        return out[: len(gids)]
 
     def clear_group_flags(self, lane: int, gids, mask: int):
         gids = np.ascontiguousarray(gids, dtype=np.uint32)

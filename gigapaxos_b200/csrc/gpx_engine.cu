@@ -1680,6 +1680,32 @@ int gpx_select_groups(gpx_engine* e, uint32_t lane, uint32_t mask, uint32_t valu
   return GPX_OK;
 }
 
+/* the fields of a SYNC_DECISIONS_REQUEST for a batch of groups: one launch of k_missing_decisions (gpx_pause.cuh) */
+int gpx_missing_decisions(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, int32_t size_limit,
+                          int32_t too_much_gap, gpx_missing_rec* out) {
+  if (!e || ((!gids || !out) && n)) return fail(GPX_EINVAL, "null argument");
+  if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");
+  if (n == 0) return GPX_OK;
+  const size_t gid_bytes = ((size_t)n * 4 + 15) & ~(size_t)15;
+  int rc = e->ensure_misc(gid_bytes + (size_t)n * sizeof(gpx_missing_rec));
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  uint8_t* base = (uint8_t*)e->d_misc;
+  CK(cudaMemcpyAsync(base, gids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  MissingArgs A;
+  A.lane = lane;
+  A.n = n;
+  A.gids = (const uint32_t*)base;
+  A.size_limit = size_limit;
+  A.too_much_gap = too_much_gap;
+  A.out = (gpx_missing_rec*)(base + gid_bytes);
+  k_missing_decisions<<<cdiv(n, GPX_PAUSE_BLOCK), GPX_PAUSE_BLOCK, 0, st>>>(e->S, A);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, A.out, (size_t)n * sizeof(gpx_missing_rec), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GPX_OK;
+}
+
 int gpx_clear_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint32_t mask) {
   if (!e || (!gids && n)) return fail(GPX_EINVAL, "null argument");
   if (lane >= e->cfg.n_lanes) return fail(GPX_ERANGE, "lane");

@@ -82,3 +82,66 @@ __global__ void k_clear_flags(const __grid_constant__ DevState S, uint32_t lane,
   const size_t ri = row_idx(S, lane, gids[i]);
   S.acc_aux[ri] &= ~((mask & (GPX_GF_OVERFLOW | GPX_GF_NEEDS_SYNC)) << 24);
 }
+
+/* ---- k_missing_decisions: the fields of a SYNC_DECISIONS_REQUEST for a batch of groups (gpx_missing_decisions) ---------
+ * One thread per gid.  committedRequests is the aux word's present mask over the window (slot s lives at s mod W, s in
+ * [slot, slot + W)), hasRequestValue its valued mask, acceptedProposals.containsKey(s) a live accepted-window entry of
+ * exactly that slot. */
+struct MissingArgs {
+  uint32_t lane, n;
+  const uint32_t* gids;
+  int32_t size_limit, too_much_gap;
+  gpx_missing_rec* out;
+};
+
+__global__ void __launch_bounds__(GPX_PAUSE_BLOCK) k_missing_decisions(const __grid_constant__ DevState S,
+                                                                       const __grid_constant__ MissingArgs A) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) atomicAdd(&S.ctr[C_KERNEL_LAUNCHES], 1ull);
+  if (i >= A.n) return;
+  const uint32_t gid = A.gids[i];
+  gpx_missing_rec r;
+  memset(&r, 0, sizeof r);
+  r.gid = gid;
+  const GroupCtx g = group_ctx(S, gid);
+  if (g.live && g.ms->idx_of_lane[A.lane] != 0xffu) {
+    const size_t ri = row_idx(S, A.lane, gid);
+    const uint32_t aux = S.acc_aux[ri];
+    const int4 row = S.acc_row[ri];
+    const int slot = row.x;
+    const uint32_t Wm = S.W - 1, present = GPX_AUX_PRESENT(aux), valued = GPX_AUX_VALUED(aux);
+    const bool stopped = GPX_AUX_STATE(aux) == GPX_ST_STOPPED;
+    r.slot = slot;
+    r.flags = (uint8_t)group_flags(S, A.lane, gid);
+    int maxCommitted = (int)((unsigned)slot - 1u); /* getMaxCommittedSlot :425-438 */
+    if (!stopped)
+      for (uint32_t d = 0; d < S.W; d++) {
+        const int s = (int)((unsigned)slot + d);
+        if ((present >> ((uint32_t)s & Wm)) & 1u) maxCommitted = s;
+      }
+    r.max_decision_slot = maxCommitted;
+    if (st_usable(aux)) { /* a stopped (or recovering) acceptor asks for nothing: :407-408 */
+      uint32_t nm = 0;
+      const int limit = (int)((unsigned)slot + (unsigned)A.size_limit);
+      for (uint32_t d = 0; d < S.W; d++) { /* getMissingCommittedSlots :415-421 */
+        const int s = (int)((unsigned)slot + d);
+        if (!(jsub(s, maxCommitted) < 0 && jsub(s, limit) < 0)) break;
+        const uint32_t w = (uint32_t)s & Wm;
+        bool missing = !((present >> w) & 1u);
+        if (!missing && !((valued >> w) & 1u)) { /* a value-less commit: is its accept here? */
+          const size_t ai = 2 * win_idx(S, A.lane, w, gid);
+          const int4 a0 = S.acc_win[ai], a1 = S.acc_win[ai + 1];
+          missing = !(((unsigned)a1.w & GPX_ENT_VALID) && a0.x == s && jsub(s, row.w) > 0);
+        }
+        if (missing) r.missing[nm++] = s;
+      }
+      if (nm == 0) r.missing[nm++] = slot; /* :2297-2298 */
+      r.n_missing = (uint16_t)nm;
+      /* isMissingTooMuch :2367-2370 = shouldSync(maxCommitted, gap) :2341-2361, DEFAULT_SYNC */
+      const int gap = jsub(maxCommitted, slot), th = A.too_much_gap;
+      const bool nontrivialInitialGap = gap >= th / 100, smallGapThreshold = th <= 1;
+      r.missing_too_much = (gap >= th) || ((slot == 0 || slot == 1) && (nontrivialInitialGap || smallGapThreshold));
+    }
+  }
+  A.out[i] = r;
+}

@@ -71,6 +71,8 @@ public final class PaxosEngine implements AutoCloseable {
 			ByteBuffer extraExecOut, int extraCap, ByteBuffer nExtra);
 	/** the live ACTIVE groups of a lane whose flag byte satisfies (flags & mask) == value, ascending; nFound: one int */
 	public static native int selectGroups(long h, int lane, int mask, int value, ByteBuffer gidsOut, int cap, ByteBuffer nFound);
+	/** per group: next slot, highest committed slot, the missing slots, isMissingTooMuch (48 B each): a SYNC_DECISIONS_REQUEST */
+	public static native int missingDecisions(long h, int lane, int n, ByteBuffer gids, int sizeLimit, int tooMuchGap, ByteBuffer out);
 	/** the host has dealt with these slow-path entries: clears OVERFLOW / NEEDS_SYNC (mask) at the lane */
 	public static native int clearGroupFlags(long h, int lane, int n, ByteBuffer gids, int mask);
 	/** the Deactivator's batch (PaxosManager.pause(Map, dequeue)): rowsOut n x nLanes x 188 B, pausedOut n bytes; unpause = loadRows */

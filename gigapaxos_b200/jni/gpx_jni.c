@@ -152,6 +152,13 @@ JNIEXPORT jint JNICALL GPX_JNI(selectGroups)(JNIEnv* env, jclass cls, jlong h, j
   return gpx_select_groups((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint32_t)mask, (uint32_t)value, (uint32_t*)buf(env, gids_out),
                            (uint32_t)cap, (uint32_t*)buf(env, n_found));
 }
+/* int missingDecisions(long h, int lane, int n, ByteBuffer gids, int sizeLimit, int tooMuchGap, ByteBuffer out [n x 48 B]):
+ * the fields of the SYNC_DECISIONS_REQUESTs PISM.requestMissingDecisions :2292 would send for these groups */
+JNIEXPORT jint JNICALL GPX_JNI(missingDecisions)(JNIEnv* env, jclass cls, jlong h, jint lane, jint n, jobject gids, jint size_limit,
+                                                 jint too_much_gap, jobject out) {
+  return gpx_missing_decisions((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint32_t)n, (const uint32_t*)buf(env, gids),
+                               (int32_t)size_limit, (int32_t)too_much_gap, (gpx_missing_rec*)buf(env, out));
+}
 JNIEXPORT jint JNICALL GPX_JNI(clearGroupFlags)(JNIEnv* env, jclass cls, jlong h, jint lane, jint n, jobject gids, jint mask) {
   return gpx_clear_group_flags((gpx_engine*)(intptr_t)h, (uint32_t)lane, (uint32_t)n, (const uint32_t*)buf(env, gids), (uint32_t)mask);
 }

@@ -318,7 +318,7 @@ def sync_decisions_json(paxos_id: str, version: int, node: int, max_decision_slo
     """SyncDecisionsPacket.toJSONObjectImpl :79-88"""
     d = _base(PT_SYNC_DECISIONS, paxos_id, version)
     d.update({"SNDR": int(node), "MAX_S": int(max_decision_slot)})
-    if missing:
+    if len(missing):
         d["MISS"] = [int(x) for x in missing]
     return _dumps(d)
 

@@ -624,6 +624,27 @@ int gpx_get_group_flags(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t
 int gpx_select_groups(gpx_engine* e, uint32_t lane, uint32_t mask, uint32_t value, uint32_t* out_gids, uint32_t cap,
                       uint32_t* n_found);
 
+/* What a listed group is missing: PISM.requestMissingDecisions :2292-2320 at `lane` for a batch of groups --
+ * PaxosAcceptor.getMaxCommittedSlot :425-438 (the highest committed slot held, slot - 1 when there is none or the acceptor
+ * is stopped), getMissingCommittedSlots(sizeLimit) :405-423 (from the next slot to execute up to the highest committed one:
+ * no commit there, or a value-less commit without its accept) -- [slot] itself when nothing else is missing (:2297-2298) --
+ * and isMissingTooMuch :2367-2370 = shouldSync(maxCommittedSlot, too_much_gap) :2341-2361 in its default mode (the
+ * reference passes getMaxSyncDecisionsGap()).  These are the fields of the SYNC_DECISIONS_REQUEST the host sends
+ * (SyncDecisionsPacket); whom to ask (:2305-2312) stays with the host.  With the bounded window a commit further than W
+ * slots ahead is not held (it was dropped and flagged NEEDS_SYNC), so at most W - 1 slots are listed.
+ * n_missing == 0: stopped / no live instance -- no request (getMissingCommittedSlots returns null). */
+typedef struct gpx_missing_rec { /* 48 B */
+  uint32_t gid;
+  int32_t slot;               /* paxosState.getSlot(): the next slot to execute */
+  int32_t max_decision_slot;  /* getMaxCommittedSlot() */
+  uint16_t n_missing;
+  uint8_t missing_too_much;
+  uint8_t flags;              /* the group's flag byte (GPX_GF_*) */
+  int32_t missing[GPX_MAX_WINDOW];
+} gpx_missing_rec;
+int gpx_missing_decisions(gpx_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, int32_t size_limit,
+                          int32_t too_much_gap, gpx_missing_rec* out);
+
 /* The OVERFLOW / NEEDS_SYNC bits are sticky: they stay until the host has dealt with the group (caught it up by a sync or
  * a checkpoint transfer) and says so -- out of the slow-path list.  Clears `mask` (of those two bits) at `lane` for
  * every gid given. */

@@ -1854,6 +1854,49 @@ int gpxo_get_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32
   return GPX_OK;
 }
 
+/* PISM.requestMissingDecisions :2292-2320 for a batch: PaxosAcceptor.getMaxCommittedSlot :425-438,
+ * getMissingCommittedSlots :405-423, PISM.isMissingTooMuch :2367-2370 / shouldSync :2341-2361 */
+int gpxo_missing_decisions(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, int32_t size_limit,
+                           int32_t too_much_gap, gpx_missing_rec* out) {
+  if (!e || ((!gids || !out) && n)) return GPX_EINVAL;
+  if (lane >= e->L()) return GPX_ERANGE;
+  for (u32 k = 0; k < n; k++) {
+    gpx_missing_rec& r = out[k];
+    memset(&r, 0, sizeof r);
+    const u32 gid = gids[k];
+    r.gid = gid;
+    if (gid >= e->groups.size() || !e->groups[gid].live || e->memberIdx(e->groups[gid], e->lanes[lane].node) < 0) continue;
+    const Acceptor& A = e->lanes[lane].acc[gid];
+    r.slot = A._slot;
+    uint8_t fl = 0;
+    gpxo_get_group_flags(e, lane, 1, &gid, &fl);
+    r.flags = fl;
+    /* getMaxCommittedSlot :425-438 */
+    i32 maxCommitted = (i32)((u32)A._slot - 1u);
+    if (!A.isStopped() && !A.committedRequests.empty()) {
+      maxCommitted = (i32)((u32)A._slot - 1u);
+      for (auto& kv : A.committedRequests)
+        if (jsub(kv.first, maxCommitted) > 0) maxCommitted = kv.first;
+    }
+    r.max_decision_slot = maxCommitted;
+    if (!e->usable(gid, lane)) continue; /* getMissingCommittedSlots returns null when stopped :407-408 */
+    /* getMissingCommittedSlots(sizeLimit) :405-423 */
+    u32 nm = 0;
+    const i32 limitSlot = (i32)((u32)A._slot + (u32)size_limit);
+    for (i32 i = A._slot; jsub(i, maxCommitted) < 0 && jsub(i, limitSlot) < 0 && nm < GPX_MAX_WINDOW; i = (i32)((u32)i + 1u)) {
+      auto c = A.committedRequests.find(i);
+      if (c == A.committedRequests.end() || (!c->second.has_value && !A.acceptedProposals.count(i))) r.missing[nm++] = i;
+    }
+    if (nm == 0) r.missing[nm++] = A._slot; /* requestMissingDecisions :2297-2298 */
+    r.n_missing = (uint16_t)nm;
+    /* shouldSync(maxDecisionSlot, threshold, DEFAULT_SYNC) :2341-2361 */
+    const i32 gap = jsub(maxCommitted, A._slot);
+    const bool nontrivialInitialGap = gap >= too_much_gap / 100, smallGapThreshold = too_much_gap <= 1;
+    r.missing_too_much = (gap >= too_much_gap) || ((A._slot == 0 || A._slot == 1) && (nontrivialInitialGap || smallGapThreshold));
+  }
+  return GPX_OK;
+}
+
 int gpxo_clear_group_flags(gpxo_engine* e, uint32_t lane, uint32_t n, const uint32_t* gids, uint32_t mask) {
   if (!e || (!gids && n)) return GPX_EINVAL;
   if (lane >= e->L()) return GPX_ERANGE;

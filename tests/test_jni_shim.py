@@ -35,7 +35,7 @@ struct JNINativeInterface_ {
 
 EXPECTED = ["create", "destroy", "lastError", "createGroups", "destroyGroups", "dumpRows", "loadRows", "patch",
             "roundSubmit", "roundWait", "propose", "handleAccepts", "handleAcceptReplies", "handleDecisions",
-            "handlePrepares", "handlePrepareReplies", "pauseGroups", "selectGroups", "clearGroupFlags", "logDrainAsync", "logDrainWait", "logRelease", "logRead", "logFind", "logGather", "getCpi", "getCounters",
+            "handlePrepares", "handlePrepareReplies", "pauseGroups", "selectGroups", "clearGroupFlags", "missingDecisions", "logDrainAsync", "logDrainWait", "logRelease", "logRead", "logFind", "logGather", "getCpi", "getCounters",
             "spreadUniqueId", "spreadPlanNode", "spreadCreate", "spreadRound", "spreadDropped", "spreadDestroy"]
 
 

@@ -336,3 +336,139 @@ def drive_flagged_sync(lib):
 
 def test_slow_path_list_end_to_end(oracle_lib):
     drive_flagged_sync(oracle_lib)
+
+
+# ---- gpx_missing_decisions: the fields of a SYNC_DECISIONS_REQUEST ------------------------------------------------------------
+def engine_with_holes(lib):
+    """lane 2 of every group: slot s gets no commit, s+1 a commit without its accept, s+2 commit and accept, s+3 the last
+    commit (groups 0..9); groups 10..19 are fully caught up; group 20's lane 2 is stopped"""
+    G = 24
+    eng = Engine(lib, make_config(lib, max_groups=G, max_batch_recs=4096, max_batch_payload=1 << 20, checkpoint_interval=100))
+    eng.create_groups(group_descs(G))
+    gids = np.arange(G, dtype=np.uint32)
+    for r in range(2):
+        reqs, pay = make_requests(gids, payload_len=4, seed=2, round_no=r)
+        eng.round(reqs, pay)
+    rows0 = eng.dump_rows(gids, 0)
+    coord = np.array([NODES.index(int(x)) for x in rows0["acc_bcoord"]])
+    sel = gids[:10][coord[:10] != 2]  # (a coordinator on lane 2 would see its own proposals)
+    for k in range(4):
+        reqs, pay = make_requests(sel, payload_len=5, seed=3, round_no=k)
+        reqs["flags"] = coord[sel] << 8
+        reqs["entry_node"] = np.array(NODES)[coord[sel]]
+        acc, blob, st = eng.propose(reqs, pay)
+        acc["dst_mask"] = 0b111 if k >= 2 else 0b011  # lane 2 hears the accepts of s+2, s+3 only
+        rep, _ = eng.handle_accepts(acc, blob)
+        dec = eng.handle_accept_replies(rep)
+        dec["dst_mask"] = 0b111 if k >= 1 else 0b011  # ... and the commits of s+1, s+2, s+3
+        eng.handle_decisions(dec)
+    p = np.zeros(1, dtype=abi.patch_dtype)
+    p["gid"], p["lane"], p["op"], p["a"] = 20, 2, abi.PATCH_SET_STATE, abi.ST_STOPPED
+    eng.patch(p)
+    return eng, sel
+
+
+def test_oracle_missing_decisions(oracle_lib):
+    eng, sel = engine_with_holes(oracle_lib)
+    all_g = np.arange(26, dtype=np.uint32)  # incl. two gids that do not exist
+    m = eng.missing_decisions(2, all_g)
+    rows = eng.dump_rows(all_g[:24], 2)
+    for g in sel:
+        r, s = m[g], int(rows[g]["acc_slot"])
+        assert int(r["slot"]) == s and int(r["max_decision_slot"]) == s + 3
+        assert list(r["missing"][: int(r["n_missing"])]) == [s, s + 1]  # no commit; a commit without its accept
+        assert not r["missing_too_much"] and int(r["flags"]) & abi.GF_NOT_CAUGHT_UP
+    for g in range(10, 20):
+        r, s = m[g], int(rows[g]["acc_slot"])
+        assert int(r["max_decision_slot"]) == s - 1 and list(r["missing"][: int(r["n_missing"])]) == [s]  # :2297-2298
+    assert int(m[20]["n_missing"]) == 0 and int(m[20]["max_decision_slot"]) == int(rows[20]["acc_slot"]) - 1  # stopped
+    assert int(m[24]["n_missing"]) == 0 and int(m[25]["slot"]) == 0
+    lim = eng.missing_decisions(2, sel, size_limit=1)
+    assert all(list(r["missing"][: int(r["n_missing"])]) == [int(r["slot"])] for r in lim)  # sizeLimit cuts the list
+    few = eng.missing_decisions(2, sel, too_much_gap=3)
+    assert all(r["missing_too_much"] for r in few)  # a gap of 3 >= the threshold
+    # the SYNC_DECISIONS packet built from a record
+    from gigapaxos_b200 import packets_json as pj
+    r = m[sel[0]]
+    pkt = pj.sync_decisions_json("NoopPaxosApp%d" % sel[0], 0, 102, int(r["max_decision_slot"]), r["missing"][: int(r["n_missing"])])
+    assert pj.parse_packet(pkt)["missing"] == [int(r["slot"]), int(r["slot"]) + 1]
+
+
+def model_missing(slot, gc, state, present, valued, win, W, size_limit, gap_th):
+    """PaxosAcceptor.getMaxCommittedSlot / getMissingCommittedSlots / PISM.isMissingTooMuch on one lane's window, in Python"""
+    i32 = lambda v: ((int(v) + (1 << 31)) % (1 << 32)) - (1 << 31)
+    max_c = i32(slot - 1)
+    if state != abi.ST_STOPPED:
+        for d in range(W):
+            s = i32(slot + d)
+            if (present >> (s & (W - 1))) & 1:
+                max_c = s
+    missing = []
+    if state in (abi.ST_ACTIVE_1, abi.ST_ACTIVE_2):
+        for d in range(W):
+            s = i32(slot + d)
+            if not (i32(s - max_c) < 0 and i32(s - i32(slot + size_limit)) < 0):
+                break
+            w = s & (W - 1)
+            if not (present >> w) & 1:
+                missing.append(s)
+            elif not (valued >> w) & 1:
+                e = win[w]
+                if not ((e[7] & 1) and e[0] == s and i32(s - gc) > 0):
+                    missing.append(s)
+        if not missing:
+            missing = [slot]
+        gap = i32(max_c - slot)
+        too = gap >= gap_th or (slot in (0, 1) and (gap >= int(gap_th / 100) or gap_th <= 1))
+    else:
+        too = False
+    return max_c, missing, too
+
+
+@pytest.mark.parametrize("seed,block,wrap", [(31, 128, False), (32, 5, True)])
+def test_missing_kernel_source_on_the_host_equals_the_model(emu_lib, seed, block, wrap):
+    rng = np.random.default_rng(seed)
+    G, L, W, R = 200, 3, 8, 3
+    base = 0x7FFFFFF0 if wrap else 0
+    i32 = lambda v: ((int(v) + (1 << 31)) % (1 << 32)) - (1 << 31)
+    live = (rng.random(G) < 0.9).astype(np.uint8)
+    acc_row = np.zeros((L, G, 4), dtype=np.int32)
+    acc_aux = np.zeros((L, G), dtype=np.uint32)
+    acc_win = np.zeros((L, W, G, 8), dtype=np.int32)
+    coord_row = np.zeros((L, G, 4), dtype=np.int32)
+    for l in range(L):
+        for g in range(G):
+            slot = i32(base + int(rng.integers(0, 40)))
+            gc = i32(slot - int(rng.integers(1, 6)))
+            state = int(rng.choice([abi.ST_ACTIVE_1, abi.ST_ACTIVE_1, abi.ST_ACTIVE_2, abi.ST_STOPPED, abi.ST_RECOVERY]))
+            present = int(rng.integers(0, 256)) if rng.random() < 0.7 else 0
+            valued = present & int(rng.integers(0, 256))
+            acc_row[l, g] = [slot, 1, 100, gc]
+            acc_aux[l, g] = state | (present << 8) | (valued << 16) | (int(rng.integers(0, 4)) << 24)
+            for w in range(W):
+                k = int(rng.integers(0, 4))  # the accept of the slot that maps here / of an older lap / invalid / below gc
+                s = next(i32(slot + d) for d in range(W) if (i32(slot + d) & (W - 1)) == w)
+                acc_win[l, w, g, 0] = [s, i32(s - W), s, i32(gc - 1)][k]
+                acc_win[l, w, g, 7] = 0 if k == 2 else 1
+    gids = rng.permutation(G + 3).astype(np.uint32)
+    nodes = np.array(NODES, dtype=np.int32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for lane in range(L):
+        for size_limit, gap_th in ((400, 400), (3, 400), (400, 4), (400, 1)):
+            out = np.zeros(len(gids), dtype=abi.missing_dtype)
+            out.view(np.uint8)[:] = 0x5A
+            assert emu_lib.emu_missing_decisions(G, L, W, R, ptr(nodes), ptr(nodes), ptr(live), 1, ptr(acc_row), ptr(acc_aux),
+                                                 ptr(acc_win), ptr(coord_row), lane, len(gids), ptr(gids), size_limit, gap_th,
+                                                 ptr(out), block) == 1
+            for r, g in zip(out, gids):
+                assert int(r["gid"]) == g
+                if g >= G or not live[g]:
+                    assert int(r["n_missing"]) == 0 and int(r["slot"]) == 0 and not r["missing"].any()
+                    continue
+                slot, gc = int(acc_row[lane, g, 0]), int(acc_row[lane, g, 3])
+                aux = int(acc_aux[lane, g])
+                max_c, missing, too = model_missing(slot, gc, aux & 0xFF, (aux >> 8) & 0xFF, (aux >> 16) & 0xFF,
+                                                    acc_win[lane, :, g], W, size_limit, gap_th)
+                assert int(r["slot"]) == slot and int(r["max_decision_slot"]) == max_c, (lane, g)
+                assert list(r["missing"][: int(r["n_missing"])]) == missing and bool(r["missing_too_much"]) == too, (lane, g)
+                assert not r["missing"][int(r["n_missing"]):].any()

@@ -259,3 +259,19 @@ def test_slow_path_list_end_to_end(cuda_lib, oracle_lib):
     from test_paxos_manager import _same_end_state
     from test_pause_batch import drive_flagged_sync
     _same_end_state(drive_flagged_sync(cuda_lib), drive_flagged_sync(oracle_lib))
+
+
+def test_missing_decisions_kernel_equals_oracle(cuda_lib, oracle_lib):
+    """k_missing_decisions: a lane with a slot without a commit, a commit without its accept, a stopped acceptor, groups that
+    are caught up, gids that do not exist -- the SYNC_DECISIONS fields byte for byte"""
+    from test_pause_batch import engine_with_holes
+    (eg, sel_g), (eo, sel_o) = engine_with_holes(cuda_lib), engine_with_holes(oracle_lib)
+    assert np.array_equal(sel_g, sel_o)
+    gids = np.arange(26, dtype=np.uint32)
+    some = 0
+    for lane in range(3):
+        for size_limit, gap in ((400, 400), (1, 400), (400, 3)):
+            got, want = eg.missing_decisions(lane, gids, size_limit, gap), eo.missing_decisions(lane, gids, size_limit, gap)
+            assert got.tobytes() == want.tobytes(), (lane, size_limit, gap)
+            some += int((want["n_missing"] > 1).sum())
+    assert some > 0
