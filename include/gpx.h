@@ -26,6 +26,13 @@
  *   gpx_round                <- one full pass of the above for co-located replicas
  *                               (PaxosManager.send :2098-2128 routing incl. loopback)
  *   gpx_log_read             <- SQLPaxosLogger.journal :965-1036 / Journaler.appendToLogFile :814-826
+ *   gpx_handle_prepares      <- PISM.handlePrepare :900-955, PaxosAcceptor.handlePrepare :239-297
+ *   gpx_handle_prepare_replies <- PISM.handlePrepareReply :1017-1068, PaxosCoordinatorState.java:264-587 (phase 1b)
+ *   gpx_select_groups / gpx_missing_decisions / gpx_clear_group_flags / gpx_pause_groups
+ *                            <- PaxosManager.syncAndDeactivate :2806-2900 (the sweep over pinstances),
+ *                               PISM.requestMissingDecisions :2292-2320, tryPause :2004-2035, pause(Map, dequeue) :2327-2366
+ *   gpx_log_find / gpx_log_gather <- AbstractPaxosLogger.getLoggedDecisions :582 / getLoggedAccepts :568
+ *                               (SQLPaxosLogger.getLoggedFromMessageLog :3674-3756, paxosutil/LogIndex.java:213-248)
  *   gpx_wire_*               <- paxospackets byte codecs (RequestPacket.java:819-1024,
  *                               AcceptPacket.java:95-138, BatchedAcceptReply.java:103-173,
  *                               BatchedCommit.java:184-252, PaxosPacket.java:443-476)
