@@ -47,6 +47,85 @@ def test_phase1b_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed, wrap, lane_
     assert eg.counters()["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("R,seed", [(3, 51), (5, 52)])
+def test_select_groups_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed):
+    from test_pause_batch import busy_engine
+    G = 120
+    eg, eo = busy_engine(cuda_lib, G, seed, 1, R), busy_engine(oracle_lib, G, seed, 1, R)
+    some = 0
+    for lane in range(R):
+        for mask, value in ((abi.GF_NOT_CAUGHT_UP, 0), (abi.GF_NOT_CAUGHT_UP, abi.GF_NOT_CAUGHT_UP), (0, 0),
+                            (abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC), (abi.GF_OVERFLOW | abi.GF_NEEDS_SYNC, 0)):
+            got, want = eg.select_groups(lane, mask, value), eo.select_groups(lane, mask, value)
+            assert np.array_equal(got, want), (lane, mask, value)
+            some += len(want)
+    assert some > G
+    # the sweep through the mirror: idle groups out in one batch, back on demand
+    from gigapaxos_b200.paxos_manager import HashChainApp, PaxosManager
+    from helpers import Engine, make_config
+
+    def drive(lib):
+        eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
+        pm = PaxosManager(eng, [HashChainApp() for _ in range(3)], [100, 101, 102])
+        names = [f"TESTPaxosApp{i}" for i in range(24)]
+        pm.createPaxosInstanceBatch({n: None for n in names}, [100, 101, 102])
+        for r in range(2):
+            for n in names:
+                pm.propose(n, f"{n}:{r}".encode())
+            pm.run_round()
+        pm.propose(names[5], b"waiting")
+        res = pm.syncAndDeactivate()
+        pm.run_round()
+        for n in names:
+            assert pm.propose(n, b"again") is not None
+        pm.run_round()
+        return res, pm.apps[0].state
+    assert drive(cuda_lib) == drive(oracle_lib)
+
+
+def test_missing_decisions_kernel_equals_oracle(cuda_lib, oracle_lib):
+    """k_missing_decisions: a lane with a slot without a commit, a commit without its accept, a stopped acceptor, groups that
+    are caught up, gids that do not exist -- the SYNC_DECISIONS fields byte for byte"""
+    from test_pause_batch import engine_with_holes
+    (eg, sel_g), (eo, sel_o) = engine_with_holes(cuda_lib), engine_with_holes(oracle_lib)
+    assert np.array_equal(sel_g, sel_o)
+    gids = np.arange(26, dtype=np.uint32)
+    some = 0
+    for lane in range(3):
+        for size_limit, gap in ((400, 400), (1, 400), (400, 3)):
+            got, want = eg.missing_decisions(lane, gids, size_limit, gap), eo.missing_decisions(lane, gids, size_limit, gap)
+            assert got.tobytes() == want.tobytes(), (lane, size_limit, gap)
+            some += int((want["n_missing"] > 1).sum())
+    assert some > 0
+
+
+# ---- the deactivation sweep (k_pause_groups behind gpx_pause_groups; also written after the GPU minutes were spent) -------
+@pytest.mark.parametrize("R,seed", [(3, 31), (5, 32), (1, 33)])
+def test_pause_groups_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed):
+    from test_pause_batch import busy_engine
+    G = 120
+    eg, eo = busy_engine(cuda_lib, G, seed, 1, R), busy_engine(oracle_lib, G, seed, 1, R)
+    assert_same_rows(eg, eo, R, G, "before")
+    gids = np.random.default_rng(seed).permutation(G + 3).astype(np.uint32)
+    rows_g, ok_g = eg.pause_groups(gids)
+    rows_o, ok_o = eo.pause_groups(gids)
+    assert np.array_equal(ok_g, ok_o) and 0 < ok_o.sum() < len(gids)
+    for f in rows_o.dtype.names:
+        assert np.array_equal(rows_g[f], rows_o[f]), f
+    assert_same_rows(eg, eo, R, G, "after the sweep")
+    eg.load_rows(rows_g[ok_g].reshape(-1))  # unpause
+    eo.load_rows(rows_o[ok_o].reshape(-1))
+    assert_same_rows(eg, eo, R, G, "after unpausing")
+    # the engine goes on deciding in the unpaused groups
+    from helpers import make_requests
+    back = np.sort(gids[ok_o])
+    reqs, pay = make_requests(back, payload_len=9, seed=seed, round_no=11)
+    sg, xg, _ = eg.round(reqs, pay)
+    so, xo, _ = eo.round(reqs, pay)
+    assert np.array_equal(sg, so) and np.all(so > 0)
+    assert_same_rows(eg, eo, R, G, "after a round")
+
+
 def test_mass_failover_one_launch(cuda_lib, oracle_lib):
     """a node is lost: every group elects in ONE call (20,000 elections, R = 3, each with a majority of replies carrying
     accepted pvalues); result records and all rows equal the oracle's"""
@@ -82,75 +161,6 @@ def test_mass_failover_one_launch(cuda_lib, oracle_lib):
     assert np.all(want["verdict"] == abi.EL_MAJORITY) and int(want["n_plan"].max()) >= 3
     assert_same_out(got, want)
     assert_same_rows(eg, eo, R, G)
-
-
-def test_view_changes_with_the_tally_in_the_engine(cuda_lib, oracle_lib):
-    from test_paxos_manager import _same_end_state, drive_auto_election, drive_lagging_election, drive_view_change
-    _same_end_state(drive_view_change(cuda_lib, p1b=True), drive_view_change(oracle_lib, p1b=True))
-    _same_end_state(drive_auto_election(cuda_lib, p1b=True), drive_auto_election(oracle_lib, p1b=True))
-    _same_end_state(drive_lagging_election(cuda_lib, p1b=True), drive_lagging_election(oracle_lib, p1b=True))
-
-
-def test_mass_failover_through_the_mirror(cuda_lib, oracle_lib):
-    """PaxosManager.runForCoordinators: one gpx_handle_prepares + one gpx_handle_prepare_replies call for all groups of the
-    lost node, then plan entry j of every elected group per round"""
-    from test_paxos_manager import _same_end_state
-    from test_phase1b import drive_mass_failover
-    _same_end_state(drive_mass_failover(cuda_lib, batched=True), drive_mass_failover(oracle_lib, batched=True))
-
-
-# ---- the deactivation sweep (k_pause_groups behind gpx_pause_groups; also written after the GPU minutes were spent) -------
-@pytest.mark.parametrize("R,seed", [(3, 31), (5, 32), (1, 33)])
-def test_pause_groups_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed):
-    from test_pause_batch import busy_engine
-    G = 120
-    eg, eo = busy_engine(cuda_lib, G, seed, 1, R), busy_engine(oracle_lib, G, seed, 1, R)
-    assert_same_rows(eg, eo, R, G, "before")
-    gids = np.random.default_rng(seed).permutation(G + 3).astype(np.uint32)
-    rows_g, ok_g = eg.pause_groups(gids)
-    rows_o, ok_o = eo.pause_groups(gids)
-    assert np.array_equal(ok_g, ok_o) and 0 < ok_o.sum() < len(gids)
-    for f in rows_o.dtype.names:
-        assert np.array_equal(rows_g[f], rows_o[f]), f
-    assert_same_rows(eg, eo, R, G, "after the sweep")
-    eg.load_rows(rows_g[ok_g].reshape(-1))  # unpause
-    eo.load_rows(rows_o[ok_o].reshape(-1))
-    assert_same_rows(eg, eo, R, G, "after unpausing")
-    # the engine goes on deciding in the unpaused groups
-    from helpers import make_requests
-    back = np.sort(gids[ok_o])
-    reqs, pay = make_requests(back, payload_len=9, seed=seed, round_no=11)
-    sg, xg, _ = eg.round(reqs, pay)
-    so, xo, _ = eo.round(reqs, pay)
-    assert np.array_equal(sg, so) and np.all(so > 0)
-    assert_same_rows(eg, eo, R, G, "after a round")
-
-
-def test_pause_batch_through_the_mirror(cuda_lib, oracle_lib):
-    from gigapaxos_b200.paxos_manager import HashChainApp, PaxosManager
-    from helpers import Engine, make_config
-
-    def drive(lib):
-        eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
-        pm = PaxosManager(eng, [HashChainApp() for _ in range(3)], [100, 101, 102])
-        names = [f"TESTPaxosApp{i}" for i in range(20)]
-        pm.createPaxosInstanceBatch({n: None for n in names}, [100, 101, 102])
-        for r in range(3):
-            for n in names:
-                pm.propose(n, f"{n}:{r}".encode())
-            pm.run_round()
-        pm.propose(names[3], b"queued")
-        done = pm.pauseBatch(names[:12])
-        table = {n: list(pm.paused[n]) for n in done}
-        pm.run_round()
-        for n in names:
-            assert pm.propose(n, f"{n}:later".encode()) is not None
-        pm.run_round()
-        assert not pm.paused and all(a.state == pm.apps[0].state for a in pm.apps)
-        return pm, table
-    (g, tg), (o, to) = drive(cuda_lib), drive(oracle_lib)
-    assert tg == to and len(to) == 11  # the same HotRestoreInfo strings in the pause table
-    assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
 
 
 # ---- the journal's index as a scan (k_log_dir / k_log_scan / k_log_hits behind gpx_log_find; same late arrival) -----------
@@ -209,6 +219,48 @@ def test_log_find_on_a_ring_that_wrapped(cuda_lib, oracle_lib):
     assert found > 20
 
 
+def test_view_changes_with_the_tally_in_the_engine(cuda_lib, oracle_lib):
+    from test_paxos_manager import _same_end_state, drive_auto_election, drive_lagging_election, drive_view_change
+    _same_end_state(drive_view_change(cuda_lib, p1b=True), drive_view_change(oracle_lib, p1b=True))
+    _same_end_state(drive_auto_election(cuda_lib, p1b=True), drive_auto_election(oracle_lib, p1b=True))
+    _same_end_state(drive_lagging_election(cuda_lib, p1b=True), drive_lagging_election(oracle_lib, p1b=True))
+
+
+def test_mass_failover_through_the_mirror(cuda_lib, oracle_lib):
+    """PaxosManager.runForCoordinators: one gpx_handle_prepares + one gpx_handle_prepare_replies call for all groups of the
+    lost node, then plan entry j of every elected group per round"""
+    from test_paxos_manager import _same_end_state
+    from test_phase1b import drive_mass_failover
+    _same_end_state(drive_mass_failover(cuda_lib, batched=True), drive_mass_failover(oracle_lib, batched=True))
+
+
+def test_pause_batch_through_the_mirror(cuda_lib, oracle_lib):
+    from gigapaxos_b200.paxos_manager import HashChainApp, PaxosManager
+    from helpers import Engine, make_config
+
+    def drive(lib):
+        eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
+        pm = PaxosManager(eng, [HashChainApp() for _ in range(3)], [100, 101, 102])
+        names = [f"TESTPaxosApp{i}" for i in range(20)]
+        pm.createPaxosInstanceBatch({n: None for n in names}, [100, 101, 102])
+        for r in range(3):
+            for n in names:
+                pm.propose(n, f"{n}:{r}".encode())
+            pm.run_round()
+        pm.propose(names[3], b"queued")
+        done = pm.pauseBatch(names[:12])
+        table = {n: list(pm.paused[n]) for n in done}
+        pm.run_round()
+        for n in names:
+            assert pm.propose(n, f"{n}:later".encode()) is not None
+        pm.run_round()
+        assert not pm.paused and all(a.state == pm.apps[0].state for a in pm.apps)
+        return pm, table
+    (g, tg), (o, to) = drive(cuda_lib), drive(oracle_lib)
+    assert tg == to and len(to) == 11  # the same HotRestoreInfo strings in the pause table
+    assert g.apps[0].state == o.apps[0].state and g.num_decisions == o.num_decisions
+
+
 def test_sync_and_lagging_election_with_the_scan(cuda_lib, oracle_lib):
     """the host mirror's catch-up (syncDecisions) and a lagging preparer's logged accepts, both looked up by gpx_log_find"""
     from test_paxos_manager import _same_end_state, drive_lagging_election, drive_sync
@@ -217,61 +269,9 @@ def test_sync_and_lagging_election_with_the_scan(cuda_lib, oracle_lib):
     _same_end_state(drive_lagging_election(cuda_lib, p1b=True), drive_lagging_election(oracle_lib, p1b=True))
 
 
-@pytest.mark.parametrize("R,seed", [(3, 51), (5, 52)])
-def test_select_groups_kernel_equals_oracle(cuda_lib, oracle_lib, R, seed):
-    from test_pause_batch import busy_engine
-    G = 120
-    eg, eo = busy_engine(cuda_lib, G, seed, 1, R), busy_engine(oracle_lib, G, seed, 1, R)
-    some = 0
-    for lane in range(R):
-        for mask, value in ((abi.GF_NOT_CAUGHT_UP, 0), (abi.GF_NOT_CAUGHT_UP, abi.GF_NOT_CAUGHT_UP), (0, 0),
-                            (abi.GF_NEEDS_SYNC, abi.GF_NEEDS_SYNC), (abi.GF_OVERFLOW | abi.GF_NEEDS_SYNC, 0)):
-            got, want = eg.select_groups(lane, mask, value), eo.select_groups(lane, mask, value)
-            assert np.array_equal(got, want), (lane, mask, value)
-            some += len(want)
-    assert some > G
-    # the sweep through the mirror: idle groups out in one batch, back on demand
-    from gigapaxos_b200.paxos_manager import HashChainApp, PaxosManager
-    from helpers import Engine, make_config
-
-    def drive(lib):
-        eng = Engine(lib, make_config(lib, max_groups=64, max_batch_recs=4096, max_batch_payload=1 << 20))
-        pm = PaxosManager(eng, [HashChainApp() for _ in range(3)], [100, 101, 102])
-        names = [f"TESTPaxosApp{i}" for i in range(24)]
-        pm.createPaxosInstanceBatch({n: None for n in names}, [100, 101, 102])
-        for r in range(2):
-            for n in names:
-                pm.propose(n, f"{n}:{r}".encode())
-            pm.run_round()
-        pm.propose(names[5], b"waiting")
-        res = pm.syncAndDeactivate()
-        pm.run_round()
-        for n in names:
-            assert pm.propose(n, b"again") is not None
-        pm.run_round()
-        return res, pm.apps[0].state
-    assert drive(cuda_lib) == drive(oracle_lib)
-
-
 def test_slow_path_list_end_to_end(cuda_lib, oracle_lib):
     """a replica that missed more decisions than its window holds is flagged, gpx_select_groups names it, the mirror catches
     it up (the donor's journal looked up by gpx_log_find) and gpx_clear_group_flags takes it off the list"""
     from test_paxos_manager import _same_end_state
     from test_pause_batch import drive_flagged_sync
     _same_end_state(drive_flagged_sync(cuda_lib), drive_flagged_sync(oracle_lib))
-
-
-def test_missing_decisions_kernel_equals_oracle(cuda_lib, oracle_lib):
-    """k_missing_decisions: a lane with a slot without a commit, a commit without its accept, a stopped acceptor, groups that
-    are caught up, gids that do not exist -- the SYNC_DECISIONS fields byte for byte"""
-    from test_pause_batch import engine_with_holes
-    (eg, sel_g), (eo, sel_o) = engine_with_holes(cuda_lib), engine_with_holes(oracle_lib)
-    assert np.array_equal(sel_g, sel_o)
-    gids = np.arange(26, dtype=np.uint32)
-    some = 0
-    for lane in range(3):
-        for size_limit, gap in ((400, 400), (1, 400), (400, 3)):
-            got, want = eg.missing_decisions(lane, gids, size_limit, gap), eo.missing_decisions(lane, gids, size_limit, gap)
-            assert got.tobytes() == want.tobytes(), (lane, size_limit, gap)
-            some += int((want["n_missing"] > 1).sum())
-    assert some > 0
